@@ -1,0 +1,116 @@
+/*
+ * sfb200.h -- C ABI of the B200-native numeric factorization engine for SparseFrame's supernodal
+ * Cholesky and LU.  Plain pointers and sizes only; every array uses the reference's own element
+ * types (Long = int64_t, Float = double; Include/arch.h:6-16).
+ *
+ * The drop-in boundary is the reference's factorize step:
+ *     int SparseFrame_factorize(struct common_info_struct*, struct gpu_info_struct*, struct matrix_info_struct*)
+ *         Cholesky/Source/SparseFrame.c:3019-3034, LU/Source/SparseFrame.c:3575-3590
+ * which reads the symbolic structure left in matrix_info by SparseFrame_analyze and fills matrix_info->Lsx.
+ * The entry points below are what that function binds to (see INTEGRATION.md for the stub).
+ *
+ * Three opaque objects:
+ *   sfb200_symbolic : result of symbolic analysis (host).       replaces SparseFrame_analyze, CH.c:1916-1978
+ *   sfb200_plan     : device-resident schedule for one symbolic structure: etree levels, batched task lists,
+ *                     relative-index maps, assembly map.          replaces the per-call setup of
+ *                     SparseFrame_factorize_supernodal, CH.c:2150-2265, and RelativeMap, CH.c:2055-2058
+ *   (numeric calls) : assemble + factorize on the GPU.            replaces CH.c:2104-2148 / LU.c:2622-2666
+ *
+ * All functions return 0 on success.  There is no CPU fallback: numeric entry points fail with
+ * SFB200_ERR_NO_DEVICE when no CUDA device is usable.
+ */
+#ifndef SFB200_H
+#define SFB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SFB200_CHOLESKY 0
+#define SFB200_LU       1
+
+#define SFB200_OK               0
+#define SFB200_ERR_ARG          1
+#define SFB200_ERR_ORDERING     2
+#define SFB200_ERR_NO_DEVICE    3
+#define SFB200_ERR_CUDA         4
+#define SFB200_ERR_NOT_POSDEF   5   /* a non-positive (Cholesky) or zero (LU) pivot was met; factor is unusable */
+#define SFB200_ERR_STATE        6
+
+typedef struct sfb200_symbolic sfb200_symbolic;
+typedef struct sfb200_plan sfb200_plan;
+
+const char *sfb200_version(void);
+const char *sfb200_last_error(void);
+
+/* ---- symbolic analysis (host only) ------------------------------------------------------------------ */
+
+/* Full analysis of a compressed-column matrix as SparseFrame_compress leaves it (CH.c:526-587):
+ * METIS ordering, etree, postorder, column counts, relaxed supernodes, row lists, stages.
+ * kind = SFB200_CHOLESKY | SFB200_LU; dev_slot_size = common_info->devSlotSize (the structure depends on it). */
+int sfb200_analyze(int kind, int is_symmetric, int64_t n, const int64_t *Cp, const int64_t *Ci, const double *Cx,
+                   uint64_t dev_slot_size, sfb200_symbolic **out);
+
+/* Wrap a structure computed elsewhere (e.g. by the reference's own SparseFrame_analyze): only what the
+ * factorize step reads.  Arrays are copied.  Up/Ui may be NULL (Cholesky, or LU on a symmetric matrix). */
+int sfb200_symbolic_wrap(int kind, int64_t n, int64_t nsuper, const int64_t *Super, const int64_t *Lsip,
+                         const int64_t *Lsxp, const int64_t *Lsi, const int64_t *Lp, const int64_t *Li,
+                         const int64_t *Up, const int64_t *Ui, sfb200_symbolic **out);
+
+/* Scalars: "n","nnz","nsuper","nfsuper","isize","xsize","csize","nstage","nsleaf","unnz".  -1 if unknown. */
+int64_t sfb200_symbolic_int(const sfb200_symbolic *s, const char *name);
+
+/* Arrays by the reference's field names: "Perm","Parent","Post","ColCount","Lp","Li","LTp","LTi","Up","Ui",
+ * "UTp","UTi","Super","SuperMap","Sparent","Lsip","Lsxp","Lsi","ST_Map","ST_Pointer","ST_Index","LeafQueue",
+ * "Aoffset","Moffset" (int64) and "Lx","LTx","Ux","UTx" (double).  Returns NULL if absent; *count = length. */
+const void *sfb200_symbolic_array(const sfb200_symbolic *s, const char *name, int64_t *count);
+
+/* Algorithmic flop count of the numeric factorization (SURVEY.md section 8d formulas). */
+double sfb200_symbolic_flops(const sfb200_symbolic *s);
+
+void sfb200_symbolic_free(sfb200_symbolic *s);
+
+/* ---- numeric plan (host build + one upload) ------------------------------------------------------------ */
+
+int sfb200_device_count(void);
+
+int sfb200_plan_create(const sfb200_symbolic *s, int device, sfb200_plan **out);
+void sfb200_plan_free(sfb200_plan *p);
+
+/* Scalars: "nlevels","nlaunches","nsmall","nlarge","relmap_entries","xsize_padded","device_bytes", ... */
+int64_t sfb200_plan_int(const sfb200_plan *p, const char *name);
+
+/* ---- numeric factorization ---------------------------------------------------------------------------- */
+
+/* Host-buffer call, the one SparseFrame_factorize maps to: uploads the values of the permuted matrix
+ * (Lx, and Ux for unsymmetric LU; same order as Lp/Li, Up/Ui), assembles, factorizes, and writes the
+ * factor into Lsx (xsize doubles, the reference's panel layout).  Lsx may be NULL to leave the factor on
+ * the device.  Blocks until done. */
+int sfb200_factorize(sfb200_plan *p, const double *Lx, const double *Ux, double *Lsx);
+
+/* Device-resident call: values already in HBM (device pointers), factor stays in HBM. Asynchronous on the
+ * plan's stream; sfb200_plan_sync() waits. */
+int sfb200_factorize_device(sfb200_plan *p, const double *d_Lx, const double *d_Ux);
+int sfb200_plan_sync(sfb200_plan *p);
+
+/* Copy the device-resident factor into the reference's host layout (xsize doubles). */
+int sfb200_download_factor(sfb200_plan *p, double *Lsx);
+
+/* Device time of the last factorize call in milliseconds (CUDA events on the plan's stream):
+ * which = 0 numeric only (assemble + factor), 1 = including H2D/D2H copies of the host-buffer call. */
+double sfb200_last_ms(const sfb200_plan *p, int which);
+
+/* Number of kernel launches the last factorize issued. */
+int64_t sfb200_last_launches(const sfb200_plan *p);
+
+/* Host pinned allocation helpers (so that callers can hand page-locked Lx/Lsx buffers). */
+void *sfb200_host_alloc(size_t bytes);
+void sfb200_host_free(void *ptr);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SFB200_H */
