@@ -1,0 +1,207 @@
+/*
+ * oracle/plan_host_exec.cpp -- TEST INFRASTRUCTURE, never linked into the product.
+ *
+ * A CPU interpreter of the engine's static schedule (csrc/plan.hpp).  It walks the same launch list the GPU
+ * replays and applies every op with plain loops, so that the schedule itself -- levels, blocked panel
+ * factorization, ancestor segments, relative-index tables, assembly map, padded layout, copy-out -- can be
+ * checked against the compiled reference on a box without a GPU.  The arithmetic each op stands for is the
+ * reference's: loadA (CH.c:1998-2028 / LU.c:2478-2536), SYRK/GEMM + mapped subtract (CH.c:2055-2086 /
+ * LU.c:2564-2604), POTRF + TRSM (CH.c:2134-2145), GETRF-nopiv + TRSM (LU.c:2652-2663).
+ */
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#include "plan.hpp"
+#include "symbolic.hpp"
+
+using namespace sfb200;
+
+namespace {
+
+int diag_cholesky(double *A, i64 ld, int nb) {
+    for (int j = 0; j < nb; ++j) {
+        double d = A[j + j * ld];
+        if (!(d > 0.0)) return 1;
+        d = std::sqrt(d);
+        A[j + j * ld] = d;
+        for (int i = j + 1; i < nb; ++i) A[i + j * ld] /= d;
+        for (int c = j + 1; c < nb; ++c)
+            for (int i = c; i < nb; ++i) A[i + c * ld] -= A[i + j * ld] * A[c + j * ld];
+    }
+    return 0;
+}
+
+int diag_lu(double *A, i64 ld, int nb) {
+    for (int k = 0; k < nb; ++k) {
+        const double piv = A[k + k * ld];
+        if (piv == 0.0) return 1;
+        for (int i = k + 1; i < nb; ++i) A[i + k * ld] /= piv;
+        for (int c = k + 1; c < nb; ++c)
+            for (int i = k + 1; i < nb; ++i) A[i + c * ld] -= A[i + k * ld] * A[k + c * ld];
+    }
+    return 0;
+}
+
+void trsm(double *X, const TrsmOp &t) {
+    const double *D = X + t.t_off;
+    for (int v = 0; v < t.nvec; ++v) {
+        double *b = X + t.b_off + (i64)v * t.vstride;
+        for (int j = 0; j < t.nb; ++j) {
+            double acc = b[(i64)j * t.estride];
+            for (int p = 0; p < j; ++p) {
+                const double tjp = (t.flags & T_TRANS) ? D[p + (i64)j * t.ldt] : D[j + (i64)p * t.ldt];
+                acc -= b[(i64)p * t.estride] * tjp;
+            }
+            if (!(t.flags & T_UNIT)) acc /= D[j + (i64)j * t.ldt];
+            b[(i64)j * t.estride] = acc;
+        }
+    }
+}
+
+void gemm(double *X, const GemmOp &g, const HostPlan &P) {
+    const double *A = X + g.a_off, *B = X + g.b_off;
+    for (int j = 0; j < g.N; ++j) {
+        int lim = 0;
+        i64 col = 0, relbase = 0;
+        if (g.flags & G_SCATTER) {
+            const i64 q = g.meta + j;
+            col = P.upd_coloff[q];
+            relbase = P.upd_relbase[q];
+            lim = (g.flags & G_LIM_SEGB) ? P.upd_segb[q] : (g.flags & G_LIM_SEGE) ? P.upd_sege[q] : j;
+            if (g.flags & G_LIM_SEGE) col += P.upd_uoff[q];
+        } else if (g.flags & G_LOWER) {
+            lim = j;
+        }
+        for (int i = lim; i < g.M; ++i) {
+            double acc = 0.0;
+            for (int k = 0; k < g.K; ++k) {
+                const double b = (g.flags & G_B_KMAJOR) ? B[k + (i64)j * g.ldb] : B[j + (i64)k * g.ldb];
+                acc += A[i + (i64)k * g.lda] * b;
+            }
+            if (g.flags & G_SCATTER) X[col + P.relmap[relbase + i]] -= acc;
+            else X[g.c_off + i + (i64)j * g.ldc] -= acc;
+        }
+    }
+}
+
+int small_front(double *X, const HostPlan &P, i64 s) {
+    const SnodeDev &d = P.snode[s];
+    const int n = d.nscol, R = d.nsrow, m = R - n;
+    double *A = X + d.xoff;
+    const i64 ld = d.ld;
+    GemmOp g{};
+    g.lda = g.ldb = d.ld; g.M = g.N = m; g.K = n; g.meta = d.lsip + n;
+    if (P.kind == Kind::Cholesky) {
+        for (int j = 0; j < n; ++j) {
+            double dj = A[j + j * ld];
+            if (!(dj > 0.0)) return 1;
+            dj = std::sqrt(dj);
+            A[j + j * ld] = dj;
+            for (int i = j + 1; i < R; ++i) A[i + j * ld] /= dj;
+            for (int c = j + 1; c < n; ++c)
+                for (int i = c; i < R; ++i) A[i + c * ld] -= A[i + j * ld] * A[c + j * ld];
+        }
+        if (m > 0) {
+            g.a_off = g.b_off = d.xoff + n; g.flags = G_LOWER | G_SCATTER;
+            gemm(X, g, P);
+        }
+    } else {
+        const int rows = R + m;      // L11\U11, L21, U12^T
+        for (int k = 0; k < n; ++k) {
+            const double piv = A[k + k * ld];
+            if (piv == 0.0) return 1;
+            for (int i = k + 1; i < R; ++i) A[i + k * ld] /= piv;                      // L column
+            for (int c = k + 1; c < n; ++c) {                                          // trailing columns
+                const double u = A[k + c * ld];
+                for (int i = k + 1; i < R; ++i) A[i + c * ld] -= A[i + k * ld] * u;
+                for (int i = R; i < rows; ++i) A[i + c * ld] -= A[i + k * ld] * A[c + k * ld];   // U12^T -= U12^T[:,k] L[c,k]
+            }
+        }
+        if (m > 0) {
+            g.a_off = d.xoff + n; g.b_off = d.xoff + R; g.flags = G_SCATTER | G_LIM_SEGB;
+            gemm(X, g, P);
+            g.a_off = d.xoff + R; g.b_off = d.xoff + n; g.flags = G_SCATTER | G_LIM_SEGE;
+            gemm(X, g, P);
+        }
+    }
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+/* analyze + plan + interpret.  Lsx_out receives the factor in the reference's layout (xsize doubles).
+ * Returns 0, or a negative code if analysis/plan failed, or a positive count of failed pivots. */
+long sfcheck_factorize(int kind, int is_symmetric, long n, const long *Cp, const long *Ci, const double *Cx,
+                       unsigned long long dev_slot, int nb, int outer, int small_a, int small_b, int ld_align,
+                       double *Lsx_out, long *stats /* [nlevels, nlaunches, nsmall, nlarge, relmap, xsize_pad] */) {
+    CscView A;
+    A.n = n; A.colptr = (const i64 *)Cp; A.rowind = (const i64 *)Ci; A.val = Cx; A.symmetric = is_symmetric != 0;
+    Symbolic S;
+    if (analyze(A, kind ? Kind::LU : Kind::Cholesky, dev_slot, S) != 0) return -1;
+    PlanParams prm;
+    if (nb > 0) prm.nb = nb;
+    if (outer > 0) prm.outer = outer;
+    if (small_a >= 0) prm.small_a_bytes = small_a;
+    if (small_b >= 0) prm.small_b_bytes = small_b;
+    if (ld_align > 0) prm.ld_align = ld_align;
+    HostPlan P;
+    const int rc = build_plan(S, prm, P);
+    if (rc != 0) return -10 - rc;
+    if (stats) {
+        stats[0] = P.nlevels; stats[1] = (long)P.launches.size(); stats[2] = P.nsmall; stats[3] = P.nlarge;
+        stats[4] = (long)P.relmap.size(); stats[5] = P.xsize_pad;
+    }
+    std::vector<double> X(P.xsize_pad, 0.0);
+    const bool lu = P.kind == Kind::LU;
+    for (i64 j = 0; j < S.n; ++j)
+        for (i64 p = S.L.ptr[j]; p < S.L.ptr[j + 1]; ++p)
+            if (P.asm_dst_l[p] >= 0) X[P.asm_dst_l[p]] = S.L.val[p];
+    if (lu) {
+        const Tri &U = P.split ? S.U : S.L;
+        for (i64 p = 0; p < P.unnz; ++p) X[P.asm_dst_u[p]] = U.val[p];
+    }
+    long bad = 0;
+    int last_level = -1;
+    for (const Launch &L : P.launches) {
+        if (L.level < last_level) return -100;          // schedule must be level-monotone
+        last_level = L.level;
+        switch (L.kind) {
+            case L_SMALL_A: case L_SMALL_B:
+                for (int k = 0; k < L.count; ++k) bad += small_front(X.data(), P, P.small_tasks[L.first + k]);
+                break;
+            case L_POTRF:
+                for (int k = 0; k < L.count; ++k) { const DiagOp &d = P.diag_ops[L.first + k]; bad += diag_cholesky(X.data() + d.a_off, d.ld, d.nb); }
+                break;
+            case L_GETRF:
+                for (int k = 0; k < L.count; ++k) { const DiagOp &d = P.diag_ops[L.first + k]; bad += diag_lu(X.data() + d.a_off, d.ld, d.nb); }
+                break;
+            case L_TRSM:
+                for (int k = 0; k < L.count; ++k) trsm(X.data(), P.trsm_ops[L.first + k]);
+                break;
+            case L_GEMM128: case L_GEMM64: {
+                // the tile prefix must be consistent with the geometry the kernels decode
+                i64 tiles = 0;
+                const int B = L.kind == L_GEMM128 ? 128 : 64;
+                for (int k = 0; k < L.count; ++k) {
+                    const GemmOp &g = P.gemm_ops[L.first + k];
+                    if (g.tile0 != tiles) return -101;
+                    tiles += gemm_tiles(g.M, g.N, B, (g.flags & G_LOWER) != 0);
+                    gemm(X.data(), g, P);
+                }
+                if (tiles != L.grid) return -102;
+                break;
+            }
+            default: return -103;
+        }
+    }
+    for (const PackTask &t : P.pack_tasks)
+        for (int c = 0; c < t.cols; ++c)
+            std::memcpy(Lsx_out + t.dst + (i64)c * t.rows, X.data() + t.src + (i64)c * t.ld, sizeof(double) * t.rows);
+    return bad;
+}
+
+}  // extern "C"

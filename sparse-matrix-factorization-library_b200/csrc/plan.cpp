@@ -1,0 +1,368 @@
+// Host plan builder -- see plan.hpp.
+#include "plan.hpp"
+
+#include <algorithm>
+#include <cassert>
+#include <map>
+
+namespace sfb200 {
+
+namespace {
+
+inline i64 round_up(i64 v, i64 a) { return (v + a - 1) / a * a; }
+
+struct SlotOps {
+    std::vector<DiagOp> diag;
+    std::vector<TrsmOp> trsm;
+    std::vector<GemmOp> gemm;
+};
+
+// Blocked right-looking factorization of one large Cholesky panel (replaces dpotrf_ + dtrsm_, CH.c:2135-2142,
+// and the blocked device POTRF of CH.c:2838-2940): nb-wide diagonal blocks inside outer-wide block columns.
+void emit_cholesky_panel(const SnodeDev &sn, const PlanParams &prm, std::map<int, SlotOps> &slots) {
+    const i64 x = sn.xoff, ld = sn.ld;
+    const int n = sn.nscol, R = sn.nsrow, nb = prm.nb, ob_w = prm.outer;
+    const int slots_per_outer = (ob_w / nb) * 3 + 1;
+    int ob = 0;
+    for (int J0 = 0; J0 < n; J0 += ob_w, ++ob) {
+        const int J1 = std::min(J0 + ob_w, n);
+        int ib = 0;
+        for (int j0 = J0; j0 < J1; j0 += nb, ++ib) {
+            const int j1 = std::min(j0 + nb, J1);
+            const int slot = ob * slots_per_outer + ib * 3;
+            slots[slot].diag.push_back(DiagOp{x + j0 + j0 * ld, (int32_t)ld, j1 - j0});
+            if (j1 < R) {
+                TrsmOp t{};
+                t.t_off = x + j0 + j0 * ld;
+                t.b_off = x + j1 + j0 * ld;
+                t.ldt = (int32_t)ld; t.nb = j1 - j0; t.nvec = R - j1;
+                t.estride = (int32_t)ld; t.vstride = 1; t.flags = 0;
+                slots[slot + 1].trsm.push_back(t);
+            }
+            if (j1 < J1) {
+                GemmOp g{};
+                g.a_off = x + j1 + j0 * ld; g.b_off = g.a_off; g.c_off = x + j1 + (i64)j1 * ld;
+                g.lda = g.ldb = g.ldc = (int32_t)ld;
+                g.M = R - j1; g.N = J1 - j1; g.K = j1 - j0; g.flags = G_LOWER;
+                slots[slot + 2].gemm.push_back(g);
+            }
+        }
+        if (J1 < n) {
+            GemmOp g{};
+            g.a_off = x + J1 + (i64)J0 * ld; g.b_off = g.a_off; g.c_off = x + J1 + (i64)J1 * ld;
+            g.lda = g.ldb = g.ldc = (int32_t)ld;
+            g.M = R - J1; g.N = n - J1; g.K = J1 - J0; g.flags = G_LOWER;
+            slots[ob * slots_per_outer + slots_per_outer - 1].gemm.push_back(g);
+        }
+    }
+}
+
+// LU panel (replaces magma_dgetrf_nopiv + dtrsm_, LU.c:2653-2660).  Rows [0,R) hold L11\U11 and L21, rows
+// [R, 2R-n) hold U12^T.
+void emit_lu_panel(const SnodeDev &sn, const PlanParams &prm, std::map<int, SlotOps> &slots) {
+    const i64 x = sn.xoff, ld = sn.ld;
+    const int n = sn.nscol, R = sn.nsrow, m = R - n, nb = prm.nb, ob_w = prm.outer;
+    const int slots_per_outer = (ob_w / nb) * 3 + 1;
+    int ob = 0;
+    for (int J0 = 0; J0 < n; J0 += ob_w, ++ob) {
+        const int J1 = std::min(J0 + ob_w, n);
+        int ib = 0;
+        for (int j0 = J0; j0 < J1; j0 += nb, ++ib) {
+            const int j1 = std::min(j0 + nb, J1);
+            const int w = j1 - j0;
+            const int slot = ob * slots_per_outer + ib * 3;
+            const i64 d = x + j0 + (i64)j0 * ld;
+            slots[slot].diag.push_back(DiagOp{d, (int32_t)ld, w});
+            auto trsm = [&](i64 b_off, int nvec, int es, int vs, int flags) {
+                if (nvec <= 0) return;
+                TrsmOp t{};
+                t.t_off = d; t.b_off = b_off; t.ldt = (int32_t)ld; t.nb = w; t.nvec = nvec;
+                t.estride = es; t.vstride = vs; t.flags = flags;
+                slots[slot + 1].trsm.push_back(t);
+            };
+            trsm(x + j1 + (i64)j0 * ld, R - j1, (int)ld, 1, T_TRANS);            // L below the block: X U11 = B
+            trsm(x + R + (i64)j0 * ld, m, (int)ld, 1, T_UNIT);                   // U12^T rows:        X L11^T = B
+            trsm(x + j0 + (i64)j1 * ld, n - j1, 1, (int)ld, T_UNIT);             // U11 row block, ALL later columns
+            auto gemm = [&](int slot_id, i64 a, i64 b, i64 c, int M, int N, int K, int flags) {
+                if (M <= 0 || N <= 0) return;
+                GemmOp g{};
+                g.a_off = a; g.b_off = b; g.c_off = c; g.lda = g.ldb = g.ldc = (int32_t)ld;
+                g.M = M; g.N = N; g.K = K; g.flags = flags;
+                slots[slot_id].gemm.push_back(g);
+            };
+            if (j1 < J1) {
+                // inner trailing update, columns [j1,J1): rows [j1,R) use the U row block (k-major B) ...
+                gemm(slot + 2, x + j1 + (i64)j0 * ld, x + j0 + (i64)j1 * ld, x + j1 + (i64)j1 * ld, R - j1, J1 - j1, w,
+                     G_B_KMAJOR);
+                // ... and the U12^T rows use the L block below the diagonal
+                gemm(slot + 2, x + R + (i64)j0 * ld, x + j1 + (i64)j0 * ld, x + R + (i64)j1 * ld, m, J1 - j1, w, 0);
+            }
+            if (J1 < n) {
+                // rows [j0+... of the U11 row blocks right of the outer block column are solved above (n - j1
+                // vectors), but the rows of THIS outer block below j1 still need the update of columns [J1,n) from
+                // this inner block: A[j1:J1, J1:n] -= L[j1:J1, j0:j1] * U[j0:j1, J1:n]
+                gemm(slot + 2, x + j1 + (i64)j0 * ld, x + j0 + (i64)J1 * ld, x + j1 + (i64)J1 * ld, J1 - j1, n - J1, w,
+                     G_B_KMAJOR);
+            }
+        }
+        if (J1 < n) {
+            const int slot = ob * slots_per_outer + slots_per_outer - 1;
+            const int K = J1 - J0;
+            GemmOp g{};
+            g.lda = g.ldb = g.ldc = (int32_t)ld;
+            g.K = K;
+            // A[J1:R, J1:n] -= L[J1:R, J0:J1] * U[J0:J1, J1:n]
+            g.a_off = x + J1 + (i64)J0 * ld; g.b_off = x + J0 + (i64)J1 * ld; g.c_off = x + J1 + (i64)J1 * ld;
+            g.M = R - J1; g.N = n - J1; g.flags = G_B_KMAJOR;
+            slots[slot].gemm.push_back(g);
+            // U12^T[:, J1:n] -= U12^T[:, J0:J1] * L[J1:n, J0:J1]^T
+            if (m > 0) {
+                g.a_off = x + R + (i64)J0 * ld; g.b_off = x + J1 + (i64)J0 * ld; g.c_off = x + R + (i64)J1 * ld;
+                g.M = m; g.N = n - J1; g.flags = 0;
+                slots[slot].gemm.push_back(g);
+            }
+        }
+    }
+}
+
+}  // namespace
+
+int build_plan(const Symbolic &S, const PlanParams &prm, HostPlan &P) {
+    P = HostPlan();
+    P.prm = prm;
+    P.kind = S.kind;
+    const bool lu = S.kind == Kind::LU;
+    P.split = lu && !S.symmetric;
+    const i64 n = S.n, ns = S.nsuper;
+    P.n = n; P.nsuper = ns; P.nnz = S.L.ptr.empty() ? 0 : S.L.ptr[n];
+    const Tri &Usrc = P.split ? S.U : S.L;     // LU on a symmetric matrix: U aliases L (LU.c:2718-2729)
+    P.unnz = lu ? (Usrc.ptr.empty() ? 0 : Usrc.ptr[n]) : 0;
+    P.isize = S.isize; P.xsize = S.xsize;
+    P.lsxp = S.Lsxp;
+    if (prm.nb < 8 || prm.nb > 64 || prm.outer % prm.nb != 0 || prm.ld_align < 1) return 1;
+
+    // ---- panels, levels -------------------------------------------------------------------------------------
+    P.snode.resize(ns);
+    std::vector<i64> sparent(ns, -1);
+    i64 xo = 0;
+    for (i64 s = 0; s < ns; ++s) {
+        SnodeDev &d = P.snode[s];
+        d.nscol = (int32_t)(S.Super[s + 1] - S.Super[s]);
+        d.nsrow = (int32_t)(S.Lsip[s + 1] - S.Lsip[s]);
+        d.lsip = S.Lsip[s];
+        const i64 rows = lu ? 2 * (i64)d.nsrow - d.nscol : d.nsrow;
+        d.ld = (int32_t)round_up(rows, prm.ld_align);
+        d.xoff = xo;
+        d.level = 0;
+        xo += (i64)d.ld * d.nscol;
+        if (d.nscol < d.nsrow) sparent[s] = S.SuperMap[S.Lsi[S.Lsip[s] + d.nscol]];
+        const double c = d.nscol, m = d.nsrow - d.nscol;
+        P.flops += lu ? 2.0 * c * c * c / 3.0 + 2.0 * m * c * c + 2.0 * m * m * c
+                      : c * c * c / 3.0 + m * c * c + m * (m + 1.0) * c;
+    }
+    P.xsize_pad = xo;
+    int maxlev = 0;
+    for (i64 s = 0; s < ns; ++s) {     // parents have larger indices (postordered)
+        const i64 p = sparent[s];
+        if (p >= 0) {
+            assert(p > s);
+            P.snode[p].level = std::max(P.snode[p].level, P.snode[s].level + 1);
+        }
+        maxlev = std::max(maxlev, (int)P.snode[s].level);
+    }
+    P.nlevels = ns > 0 ? maxlev + 1 : 0;
+
+    // ---- ancestor segments and relative-index tables -----------------------------------------------------------
+    struct Seg { i64 d; int32_t b, e; i64 rel_off; };
+    std::vector<std::vector<Seg>> incoming(ns);
+    P.upd_coloff.assign(S.isize, 0);
+    P.upd_relbase.assign(S.isize, 0);
+    P.upd_segb.assign(S.isize, 0);
+    P.upd_sege.assign(S.isize, 0);
+    P.upd_uoff.assign(lu ? S.isize : 0, 0);
+    i64 rel_total = 0;
+    for (i64 d = 0; d < ns; ++d) {
+        const SnodeDev &sd = P.snode[d];
+        const int m = sd.nsrow - sd.nscol;
+        const i64 *rows = S.Lsi.data() + sd.lsip + sd.nscol;
+        for (int b = 0; b < m;) {
+            const i64 t = S.SuperMap[rows[b]];
+            int e = b + 1;
+            while (e < m && S.SuperMap[rows[e]] == t) ++e;
+            incoming[t].push_back(Seg{d, b, e, rel_total});
+            const SnodeDev &st = P.snode[t];
+            for (int j = b; j < e; ++j) {
+                const i64 q = sd.lsip + sd.nscol + j;
+                P.upd_coloff[q] = st.xoff + (rows[j] - S.Super[t]) * (i64)st.ld;
+                P.upd_relbase[q] = rel_total - b;
+                P.upd_segb[q] = b;
+                P.upd_sege[q] = e;
+                if (lu) P.upd_uoff[q] = st.nsrow - st.nscol;
+            }
+            rel_total += m - b;
+            b = e;
+        }
+    }
+    if (rel_total > (i64)0x7fffffff * 8) return 2;
+    P.relmap.assign(rel_total, 0);
+
+    // one sweep over the targets: position map of the target's rows, then (a) every segment aimed at it and
+    // (b) the destinations of the matrix entries of its own columns (replaces Map, CH.c:2113-2114, and loadA's
+    // addressing, CH.c:2010-2018 / LU.c:2490-2517)
+    P.asm_dst_l.assign(P.nnz, 0);
+    P.asm_dst_u.assign(P.unnz, 0);
+    std::vector<int32_t> pos(n, -1);
+    for (i64 t = 0; t < ns; ++t) {
+        const SnodeDev &st = P.snode[t];
+        const i64 *trow = S.Lsi.data() + st.lsip;
+        for (int k = 0; k < st.nsrow; ++k) pos[trow[k]] = k;
+        for (const Seg &g : incoming[t]) {
+            const SnodeDev &sd = P.snode[g.d];
+            const int m = sd.nsrow - sd.nscol;
+            const i64 *rows = S.Lsi.data() + sd.lsip + sd.nscol;
+            for (int i = g.b; i < m; ++i) {
+                const int32_t r = pos[rows[i]];
+                if (r < 0) return 3;              // containment property violated: not a valid supernodal structure
+                P.relmap[g.rel_off + (i - g.b)] = r;
+            }
+        }
+        for (i64 j = S.Super[t]; j < S.Super[t + 1]; ++j) {
+            const i64 cj = j - S.Super[t];
+            for (i64 p = S.L.ptr[j]; p < S.L.ptr[j + 1]; ++p) {
+                const i64 i = S.L.idx[p];
+                if (pos[i] < 0) return 4;
+                // LU takes the diagonal from U (LU.c:2496): the L copy of a diagonal entry is skipped
+                P.asm_dst_l[p] = (lu && i == j) ? -1 : st.xoff + cj * st.ld + pos[i];
+            }
+            if (lu) {
+                for (i64 p = Usrc.ptr[j]; p < Usrc.ptr[j + 1]; ++p) {
+                    const i64 i = Usrc.idx[p];   // column index of an entry of row j of U
+                    if (pos[i] < 0) return 4;
+                    P.asm_dst_u[p] = pos[i] < st.nscol ? st.xoff + (i64)pos[i] * st.ld + cj
+                                                       : st.xoff + cj * st.ld + (st.nsrow - st.nscol) + pos[i];
+                }
+            }
+        }
+        for (int k = 0; k < st.nsrow; ++k) pos[trow[k]] = -1;
+    }
+
+    // ---- the launch schedule, level by level --------------------------------------------------------------------
+    std::vector<std::vector<i64>> by_level(P.nlevels);
+    for (i64 s = 0; s < ns; ++s) by_level[P.snode[s].level].push_back(s);
+
+    auto panel_bytes = [&](const SnodeDev &d) {
+        const i64 rows = lu ? 2 * (i64)d.nsrow - d.nscol : d.nsrow;
+        return rows * d.nscol * (i64)sizeof(double);
+    };
+    const int small_limits[4] = {std::min(2048, prm.small_a_bytes), prm.small_a_bytes, std::min(16384, prm.small_b_bytes),
+                                 prm.small_b_bytes};
+
+    for (int lev = 0; lev < P.nlevels; ++lev) {
+        std::vector<i64> cls[4];
+        std::map<int, SlotOps> slots;
+        std::vector<GemmOp> scatter;
+        for (i64 s : by_level[lev]) {
+            const SnodeDev &d = P.snode[s];
+            const i64 pb = panel_bytes(d);
+            int c = -1;
+            for (int k = 0; k < 4; ++k) if (pb <= small_limits[k]) { c = k; break; }
+            if (c >= 0) { cls[c].push_back(s); ++P.nsmall; continue; }
+            ++P.nlarge;
+            if (lu) emit_lu_panel(d, prm, slots); else emit_cholesky_panel(d, prm, slots);
+            const int m = d.nsrow - d.nscol;
+            if (m > 0) {
+                GemmOp g{};
+                g.lda = g.ldb = d.ld; g.ldc = 0; g.M = g.N = m; g.K = d.nscol;
+                g.meta = d.lsip + d.nscol;
+                if (!lu) {
+                    g.a_off = g.b_off = d.xoff + d.nscol;
+                    g.flags = G_LOWER | G_SCATTER;
+                    scatter.push_back(g);
+                } else {
+                    g.a_off = d.xoff + d.nscol; g.b_off = d.xoff + d.nsrow;      // L21 * (U12^T)^T, rows >= seg begin
+                    g.flags = G_SCATTER | G_LIM_SEGB;
+                    scatter.push_back(g);
+                    g.a_off = d.xoff + d.nsrow; g.b_off = d.xoff + d.nscol;      // U12^T * L21^T, rows >= seg end
+                    g.flags = G_SCATTER | G_LIM_SEGE;
+                    scatter.push_back(g);
+                }
+            }
+        }
+        for (int c = 0; c < 4; ++c) {
+            if (cls[c].empty()) continue;
+            Launch L{};
+            L.kind = c < 2 ? L_SMALL_A : L_SMALL_B;
+            L.level = lev;
+            L.first = (int32_t)P.small_tasks.size();
+            L.count = L.grid = (int32_t)cls[c].size();
+            i64 smem = 0;
+            for (i64 s : cls[c]) { P.small_tasks.push_back((int32_t)s); smem = std::max(smem, panel_bytes(P.snode[s])); }
+            L.smem = (int32_t)smem;
+            P.launches.push_back(L);
+        }
+        auto emit_gemm = [&](std::vector<GemmOp> &ops) {
+            for (int pass = 0; pass < 2; ++pass) {       // pass 0: 128x128 tiles, pass 1: 64x64 tiles
+                const int B = pass == 0 ? 128 : 64;
+                Launch L{};
+                L.kind = pass == 0 ? L_GEMM128 : L_GEMM64;
+                L.level = lev;
+                L.first = (int32_t)P.gemm_ops.size();
+                i64 tiles = 0;
+                for (GemmOp g : ops) {
+                    const bool big = g.M >= prm.gemm128_min_m && g.N > 64;
+                    if (big != (pass == 0)) continue;
+                    g.tile0 = (int32_t)tiles;
+                    tiles += gemm_tiles(g.M, g.N, B, (g.flags & G_LOWER) != 0);
+                    P.gemm_ops.push_back(g);
+                }
+                L.count = (int32_t)P.gemm_ops.size() - L.first;
+                L.grid = (int32_t)tiles;
+                if (L.count > 0) P.launches.push_back(L);
+            }
+        };
+        for (auto &kv : slots) {
+            SlotOps &so = kv.second;
+            if (!so.diag.empty()) {
+                Launch L{};
+                L.kind = lu ? L_GETRF : L_POTRF; L.level = lev;
+                L.first = (int32_t)P.diag_ops.size();
+                L.count = L.grid = (int32_t)so.diag.size();
+                P.diag_ops.insert(P.diag_ops.end(), so.diag.begin(), so.diag.end());
+                P.launches.push_back(L);
+            }
+            if (!so.trsm.empty()) {
+                Launch L{};
+                L.kind = L_TRSM; L.level = lev;
+                L.first = (int32_t)P.trsm_ops.size();
+                i64 ctas = 0;
+                for (TrsmOp t : so.trsm) {
+                    t.tile0 = (int32_t)ctas;
+                    ctas += (t.nvec + 63) / 64;
+                    P.trsm_ops.push_back(t);
+                }
+                L.count = (int32_t)so.trsm.size();
+                L.grid = (int32_t)ctas;
+                P.launches.push_back(L);
+            }
+            if (!so.gemm.empty()) emit_gemm(so.gemm);
+        }
+        if (!scatter.empty()) emit_gemm(scatter);
+    }
+
+    // ---- copy-out tasks ------------------------------------------------------------------------------------------
+    for (i64 s = 0; s < ns; ++s) {
+        const SnodeDev &d = P.snode[s];
+        const int rows = lu ? 2 * d.nsrow - d.nscol : d.nsrow;
+        const int chunk = std::max(1, 65536 / std::max(rows, 1));
+        for (int c0 = 0; c0 < d.nscol; c0 += chunk) {
+            PackTask t{};
+            t.src = d.xoff + (i64)c0 * d.ld;
+            t.dst = S.Lsxp[s] + (i64)c0 * rows;
+            t.rows = rows; t.ld = d.ld; t.cols = std::min(chunk, d.nscol - c0);
+            P.pack_tasks.push_back(t);
+        }
+    }
+    return 0;
+}
+
+}  // namespace sfb200

@@ -1,0 +1,60 @@
+// Static numeric schedule ("plan") for one symbolic structure.  Built once on the host from the supernodal
+// structure; the numeric phase replays it as a fixed sequence of batched kernel launches, one etree level after
+// another (replaces the dynamic ready-queue scheduler of SparseFrame_factorize_supernodal, CH.c:2264-2331,
+// 2960-2986, and the per-update RelativeMap construction of CH.c:2055-2058).
+#pragma once
+#include <vector>
+
+#include "plan_types.h"
+#include "symbolic.hpp"
+
+namespace sfb200 {
+
+struct PlanParams {
+    int ld_align = 2;            // panel leading dimensions / offsets are multiples of this many doubles
+    int nb = 64;                 // order of the diagonal blocks factored inside one CTA
+    int outer = 256;             // width of the outer block column (trailing updates run with K = outer)
+    int small_a_bytes = 6144;    // fronts whose whole panel fits: 64-thread CTA
+    int small_b_bytes = 49152;   //                              : 256-thread CTA
+    int gemm128_min_m = 192;     // GEMM ops with at least this many rows use 128x128 tiles, others 64x64
+};
+
+struct HostPlan {
+    Kind kind = Kind::Cholesky;
+    bool split = false;          // LU on an unsymmetric matrix: separate U values
+    PlanParams prm;
+    i64 n = 0, nsuper = 0, nnz = 0, unnz = 0, isize = 0, xsize = 0, xsize_pad = 0;
+    int nlevels = 0;
+    i64 nsmall = 0, nlarge = 0;
+
+    std::vector<SnodeDev> snode;            // nsuper
+    std::vector<i64> lsxp;                  // reference (unpadded) panel offsets, nsuper + 1
+    // per-row tables, indexed like Lsi (only off-diagonal positions are meaningful)
+    std::vector<i64> upd_coloff;            // padded offset of the ancestor column this row's global index owns
+    std::vector<i64> upd_relbase;           // relmap[relbase + i] = row of off-diagonal row i inside that ancestor
+    std::vector<int32_t> upd_segb, upd_sege;// first / one-past-last off-diagonal row of the row's ancestor segment
+    std::vector<int32_t> upd_uoff;          // LU: nsrow - nscol of the ancestor (row offset of its U12^T block)
+    std::vector<int32_t> relmap;
+    std::vector<i64> asm_dst_l, asm_dst_u;  // destination of every Lx (Ux) entry in the padded factor
+
+    std::vector<int32_t> small_tasks;
+    std::vector<DiagOp> diag_ops;
+    std::vector<TrsmOp> trsm_ops;
+    std::vector<GemmOp> gemm_ops;
+    std::vector<Launch> launches;
+    std::vector<PackTask> pack_tasks;
+
+    double flops = 0.0;                     // algorithmic flops
+};
+
+int build_plan(const Symbolic &S, const PlanParams &prm, HostPlan &P);
+
+// tile geometry shared by builder, kernels and the CPU interpreter
+inline i64 gemm_tiles(int M, int N, int B, bool lower) {
+    const i64 ni = (M + B - 1) / B, nj = (N + B - 1) / B;
+    if (!lower) return ni * nj;
+    const i64 tri = std::min(ni, nj);
+    return tri * (tri + 1) / 2 + (ni > nj ? (ni - nj) * nj : 0);
+}
+
+}  // namespace sfb200

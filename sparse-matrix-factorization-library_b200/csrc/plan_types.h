@@ -1,0 +1,99 @@
+// POD records shared by the host plan builder (plan.cpp), the device engine (engine.cu / kernels.cu) and the
+// CPU plan interpreter used only by the tests (oracle/plan_host_exec.cpp).
+//
+// Data layout in HBM ("padded Lsx"): one dense column-major panel per supernode, exactly the reference's Lsx
+// panel (CH.c:1632-1658; LU: LU.c:1946) except that the leading dimension is rounded up to a multiple of
+// ld_align doubles and every panel starts on a multiple of ld_align, so that 16-byte vector / TMA access is legal.
+//   Cholesky panel  : ld x nscol, rows [0,nscol) diagonal block (lower), rows [nscol,nsrow) L21
+//   LU panel        : ld x nscol, rows [0,nscol) L11\U11, [nscol,nsrow) L21, [nsrow, 2 nsrow - nscol) U12^T
+#pragma once
+#include <stdint.h>
+
+namespace sfb200 {
+
+struct SnodeDev {
+    int64_t xoff;    // element offset of the panel in the padded factor
+    int64_t lsip;    // offset of the row list in Lsi (and in the per-row update tables)
+    int32_t nscol;
+    int32_t nsrow;
+    int32_t ld;      // padded leading dimension
+    int32_t level;   // height above the deepest leaf below it (leaves = 0)
+};
+
+// ---- GEMM-shaped work: C (-)= A * B^T on DMMA tiles -------------------------------------------------------
+enum GemmFlags : int32_t {
+    G_LOWER     = 1 << 0,   // C is diagonal-aligned: only tiles/elements with row >= col are touched
+    G_SCATTER   = 1 << 1,   // C is not a dense block: elements are subtracted from ancestor panels through the
+                            // relative-index tables (replaces mappedSubtract, CH.cu:62-124 / cpuApply CH.c:2073-2086)
+    G_B_KMAJOR  = 1 << 2,   // B is stored K x N (k contiguous) instead of N x K        (LU: U11 row blocks)
+    G_LIM_SEGB  = 1 << 3,   // scatter mask: row >= first row of the column's ancestor segment   (LU, L side)
+    G_LIM_SEGE  = 1 << 4,   // scatter mask: row >= end of the column's ancestor segment, dest += u-offset (LU, U side)
+};
+
+struct GemmOp {
+    int64_t a_off, b_off, c_off;   // element offsets into the padded factor (c_off unused for scatter)
+    int32_t lda, ldb, ldc;
+    int32_t M, N, K;
+    int32_t flags;
+    int32_t tile0;                 // index of this op's first tile inside its launch
+    int64_t meta;                  // scatter: index of off-diagonal row 0 of the source supernode in the per-row tables
+};
+
+// ---- triangular solves with one nb x nb diagonal block ------------------------------------------------------
+// Every variant is the recurrence  x_j = (b_j - sum_{p<j} x_p T[j,p]) / T[j,j]  over independent vectors b.
+enum TrsmFlags : int32_t {
+    T_TRANS = 1 << 0,   // T[j,p] is read from the upper triangle: T[j,p] = D[p,j]      (LU: X U11 = B)
+    T_UNIT  = 1 << 1,   // unit diagonal                                                (LU: X L11^T = B, L11 X = B)
+};
+
+struct TrsmOp {
+    int64_t t_off;      // diagonal block D (ld = ldt)
+    int64_t b_off;      // first element of vector 0
+    int32_t ldt;
+    int32_t nb;         // block order (<= 64)
+    int32_t nvec;       // number of vectors
+    int32_t estride;    // stride between consecutive elements of one vector
+    int32_t vstride;    // stride between vectors
+    int32_t flags;
+    int32_t tile0;      // first CTA of this op inside its launch (one CTA per 64 vectors)
+    int32_t pad;
+};
+
+// ---- diagonal block factorization --------------------------------------------------------------------------
+struct DiagOp {
+    int64_t a_off;
+    int32_t ld;
+    int32_t nb;
+};
+
+// ---- one kernel launch of the static schedule ---------------------------------------------------------------
+enum LaunchKind : int32_t {
+    L_SMALL_A = 0,   // whole-front-in-shared-memory kernel, tiny fronts
+    L_SMALL_B = 1,   // same kernel, larger CTA / more shared memory
+    L_POTRF   = 2,   // Cholesky of nb x nb diagonal blocks
+    L_GETRF   = 3,   // no-pivot LU of nb x nb diagonal blocks
+    L_TRSM    = 4,
+    L_GEMM128 = 5,   // 128x128 CTA tiles
+    L_GEMM64  = 6,   // 64x64 CTA tiles
+};
+
+struct Launch {
+    int32_t kind;
+    int32_t level;
+    int32_t first;   // first op / task in the kind's array
+    int32_t count;   // ops / tasks
+    int32_t grid;    // CTAs
+    int32_t smem;    // dynamic shared memory bytes
+};
+
+// ---- final copy into the reference's unpadded layout -------------------------------------------------------
+struct PackTask {
+    int64_t src;     // padded offset
+    int64_t dst;     // offset in the reference's Lsx
+    int32_t rows;    // contiguous run length (panel rows)
+    int32_t ld;      // padded leading dimension
+    int32_t cols;
+    int32_t pad;
+};
+
+}  // namespace sfb200
