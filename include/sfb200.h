@@ -110,6 +110,9 @@ int64_t sfb200_last_launches(const sfb200_plan *p);
 void *sfb200_host_alloc(size_t bytes);
 void sfb200_host_free(void *ptr);
 
+/* FP64 pipe probe for the roofline denominators (TFLOP/s): which = 0 DFMA vector pipe, 1 DMMA tensor pipe. */
+double sfb200_probe_fp64_peak(int device, int which, int iters);
+
 #ifdef __cplusplus
 }
 #endif

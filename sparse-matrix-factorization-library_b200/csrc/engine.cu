@@ -1,0 +1,322 @@
+// Numeric half of the C ABI (include/sfb200.h): device-resident plan, schedule replay, copies.
+// Replaces the numeric phase of SparseFrame_factorize_supernodal (CH.c:2150-3017 / LU.c:2668-3573): no host-driven
+// per-descendant loop, no PCIe staging of panels, no cuBLAS / cuSOLVER -- a fixed sequence of batched launches over
+// a factor that never leaves HBM until the final copy-out.
+#include <chrono>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/sfb200.h"
+#include "capi_internal.hpp"
+#include "kernels.cuh"
+#include "plan.hpp"
+
+using namespace sfb200;
+
+struct sfb200_plan {
+    HostPlan H;
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};   // numeric begin/end, e2e begin/end
+    PlanDev D{};
+    // device copies of the plan
+    SnodeDev *d_snode = nullptr;
+    int64_t *d_coloff = nullptr, *d_relbase = nullptr, *d_asm_l = nullptr, *d_asm_u = nullptr;
+    int32_t *d_segb = nullptr, *d_sege = nullptr, *d_uoff = nullptr, *d_relmap = nullptr, *d_small = nullptr;
+    DiagOp *d_diag = nullptr;
+    TrsmOp *d_trsm = nullptr;
+    GemmOp *d_gemm = nullptr;
+    PackTask *d_pack = nullptr;
+    double *d_X = nullptr, *d_out = nullptr, *d_lx = nullptr, *d_ux = nullptr;
+    int *d_status = nullptr;
+    size_t device_bytes = 0;
+    float ms_numeric = 0.f, ms_e2e = 0.f;
+    int64_t launches = 0;
+    bool factored = false;
+};
+
+namespace {
+
+bool g_kernels_ready = false;
+
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) {                                                                   \
+            set_error(std::string(#call) + ": " + cudaGetErrorString(e_));                         \
+            return SFB200_ERR_CUDA;                                                                \
+        }                                                                                          \
+    } while (0)
+
+template <class T>
+int upload(sfb200_plan *p, T *&dptr, const std::vector<T> &h) {
+    dptr = nullptr;
+    if (h.empty()) return SFB200_OK;
+    CK(cudaMalloc((void **)&dptr, h.size() * sizeof(T)));
+    p->device_bytes += h.size() * sizeof(T);
+    CK(cudaMemcpyAsync(dptr, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice, p->stream));
+    return SFB200_OK;
+}
+
+int run_schedule(sfb200_plan *p) {
+    const HostPlan &H = p->H;
+    cudaStream_t st = p->stream;
+    CK(cudaMemsetAsync(p->d_status, 0, sizeof(int), st));
+    CK(cudaMemsetAsync(p->d_X, 0, sizeof(double) * (size_t)H.xsize_pad, st));
+    launch_assemble(p->d_lx, p->d_asm_l, H.nnz, p->d_X, st);
+    int64_t nl = 2;
+    if (H.kind == Kind::LU) {
+        launch_assemble(H.split ? p->d_ux : p->d_lx, p->d_asm_u, H.unnz, p->d_X, st);
+        ++nl;
+    }
+    for (const Launch &L : H.launches) {
+        switch (L.kind) {
+            case L_SMALL_A: launch_small(p->D, p->d_small + L.first, L.count, L.smem, false, st); break;
+            case L_SMALL_B: launch_small(p->D, p->d_small + L.first, L.count, L.smem, true, st); break;
+            case L_POTRF:
+            case L_GETRF: launch_diag(p->D, p->d_diag + L.first, L.count, st); break;
+            case L_TRSM: launch_trsm(p->D, p->d_trsm + L.first, L.count, L.grid, st); break;
+            case L_GEMM128: launch_gemm(p->D, p->d_gemm + L.first, L.count, L.grid, true, st); break;
+            case L_GEMM64: launch_gemm(p->D, p->d_gemm + L.first, L.count, L.grid, false, st); break;
+            default: set_error("corrupt plan: unknown launch kind"); return SFB200_ERR_STATE;
+        }
+        ++nl;
+    }
+    p->launches = nl;
+    CK(cudaGetLastError());
+    return SFB200_OK;
+}
+
+int check_status(sfb200_plan *p) {
+    int status = 0;
+    CK(cudaMemcpyAsync(&status, p->d_status, sizeof(int), cudaMemcpyDeviceToHost, p->stream));
+    CK(cudaStreamSynchronize(p->stream));
+    if (status & 1) {
+        set_error("non-positive (Cholesky) or zero (LU) pivot met");
+        return SFB200_ERR_NOT_POSDEF;
+    }
+    return SFB200_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int sfb200_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+void sfb200_plan_free(sfb200_plan *p) {
+    if (!p) return;
+    cudaSetDevice(p->device);
+    void *ptrs[] = {p->d_snode, p->d_coloff, p->d_relbase, p->d_asm_l, p->d_asm_u, p->d_segb, p->d_sege, p->d_uoff,
+                    p->d_relmap, p->d_small, p->d_diag, p->d_trsm, p->d_gemm, p->d_pack, p->d_X, p->d_out, p->d_lx,
+                    p->d_ux, p->d_status};
+    for (void *q : ptrs) if (q) cudaFree(q);
+    for (auto &e : p->ev) if (e) cudaEventDestroy(e);
+    if (p->stream) cudaStreamDestroy(p->stream);
+    delete p;
+}
+
+int sfb200_plan_create(const sfb200_symbolic *s, int device, sfb200_plan **out) {
+    if (!s || !out) { set_error("sfb200_plan_create: bad argument"); return SFB200_ERR_ARG; }
+    if (sfb200_device_count() <= device || device < 0) {
+        set_error("sfb200_plan_create: no usable CUDA device (this engine has no CPU fallback)");
+        return SFB200_ERR_NO_DEVICE;
+    }
+    auto *p = new sfb200_plan();
+    p->device = device;
+    PlanParams prm;
+    if (const char *e = getenv("SFB200_NB")) prm.nb = atoi(e);
+    if (const char *e = getenv("SFB200_OUTER")) prm.outer = atoi(e);
+    if (const char *e = getenv("SFB200_SMALL_A")) prm.small_a_bytes = atoi(e);
+    if (const char *e = getenv("SFB200_SMALL_B")) prm.small_b_bytes = atoi(e);
+    if (const char *e = getenv("SFB200_GEMM128_MIN")) prm.gemm128_min_m = atoi(e);
+    const int rc = build_plan(s->S, prm, p->H);
+    if (rc != 0) {
+        delete p;
+        set_error("sfb200_plan_create: structure is not a valid supernodal structure (code " + std::to_string(rc) + ")");
+        return SFB200_ERR_ARG;
+    }
+    int err = SFB200_OK;
+    auto fail = [&](int code) { sfb200_plan_free(p); return code; };
+    if (cudaSetDevice(device) != cudaSuccess) { set_error("cudaSetDevice failed"); return fail(SFB200_ERR_CUDA); }
+    if (!g_kernels_ready) {
+        if (kernels_init() != cudaSuccess) { set_error("kernel attribute setup failed (not an sm_100a device?)"); return fail(SFB200_ERR_CUDA); }
+        g_kernels_ready = true;
+    }
+    if (cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking) != cudaSuccess) { set_error("stream"); return fail(SFB200_ERR_CUDA); }
+    for (auto &e : p->ev) if (cudaEventCreate(&e) != cudaSuccess) { set_error("event"); return fail(SFB200_ERR_CUDA); }
+    const HostPlan &H = p->H;
+    if ((err = upload(p, p->d_snode, H.snode))) return fail(err);
+    if ((err = upload(p, p->d_coloff, H.upd_coloff))) return fail(err);
+    if ((err = upload(p, p->d_relbase, H.upd_relbase))) return fail(err);
+    if ((err = upload(p, p->d_segb, H.upd_segb))) return fail(err);
+    if ((err = upload(p, p->d_sege, H.upd_sege))) return fail(err);
+    if ((err = upload(p, p->d_uoff, H.upd_uoff))) return fail(err);
+    if ((err = upload(p, p->d_relmap, H.relmap))) return fail(err);
+    if ((err = upload(p, p->d_asm_l, H.asm_dst_l))) return fail(err);
+    if ((err = upload(p, p->d_asm_u, H.asm_dst_u))) return fail(err);
+    if ((err = upload(p, p->d_small, H.small_tasks))) return fail(err);
+    if ((err = upload(p, p->d_diag, H.diag_ops))) return fail(err);
+    if ((err = upload(p, p->d_trsm, H.trsm_ops))) return fail(err);
+    if ((err = upload(p, p->d_gemm, H.gemm_ops))) return fail(err);
+    if ((err = upload(p, p->d_pack, H.pack_tasks))) return fail(err);
+    auto dmalloc = [&](void **ptr, size_t bytes) {
+        if (bytes == 0) bytes = 8;
+        if (cudaMalloc(ptr, bytes) != cudaSuccess) { set_error("cudaMalloc of " + std::to_string(bytes) + " bytes failed"); return SFB200_ERR_CUDA; }
+        p->device_bytes += bytes;
+        return SFB200_OK;
+    };
+    if ((err = dmalloc((void **)&p->d_X, sizeof(double) * (size_t)H.xsize_pad))) return fail(err);
+    if ((err = dmalloc((void **)&p->d_lx, sizeof(double) * (size_t)H.nnz))) return fail(err);
+    if (H.split && (err = dmalloc((void **)&p->d_ux, sizeof(double) * (size_t)H.unnz))) return fail(err);
+    if ((err = dmalloc((void **)&p->d_status, sizeof(int)))) return fail(err);
+    if (cudaStreamSynchronize(p->stream) != cudaSuccess) { set_error("plan upload failed"); return fail(SFB200_ERR_CUDA); }
+    p->D.X = p->d_X;
+    p->D.snode = p->d_snode;
+    p->D.upd_coloff = p->d_coloff;
+    p->D.upd_relbase = p->d_relbase;
+    p->D.upd_segb = p->d_segb;
+    p->D.upd_sege = p->d_sege;
+    p->D.upd_uoff = p->d_uoff;
+    p->D.relmap = p->d_relmap;
+    p->D.status = p->d_status;
+    p->D.is_lu = H.kind == Kind::LU;
+    *out = p;
+    return SFB200_OK;
+}
+
+int64_t sfb200_plan_int(const sfb200_plan *p, const char *name) {
+    if (!p || !name) return -1;
+    const std::string k(name);
+    const HostPlan &H = p->H;
+    if (k == "nlevels") return H.nlevels;
+    if (k == "nlaunches") return (int64_t)H.launches.size();
+    if (k == "nsmall") return H.nsmall;
+    if (k == "nlarge") return H.nlarge;
+    if (k == "relmap_entries") return (int64_t)H.relmap.size();
+    if (k == "xsize_padded") return H.xsize_pad;
+    if (k == "xsize") return H.xsize;
+    if (k == "nnz") return H.nnz;
+    if (k == "unnz") return H.unnz;
+    if (k == "split") return H.split;
+    if (k == "device_bytes") return (int64_t)p->device_bytes;
+    if (k == "gemm_ops") return (int64_t)H.gemm_ops.size();
+    if (k == "trsm_ops") return (int64_t)H.trsm_ops.size();
+    if (k == "diag_ops") return (int64_t)H.diag_ops.size();
+    if (k == "device") return p->device;
+    return -1;
+}
+
+int sfb200_factorize_device(sfb200_plan *p, const double *d_Lx, const double *d_Ux) {
+    if (!p || !d_Lx) { set_error("sfb200_factorize_device: bad argument"); return SFB200_ERR_ARG; }
+    CK(cudaSetDevice(p->device));
+    const HostPlan &H = p->H;
+    CK(cudaEventRecord(p->ev[0], p->stream));
+    if (d_Lx != p->d_lx) CK(cudaMemcpyAsync(p->d_lx, d_Lx, sizeof(double) * (size_t)H.nnz, cudaMemcpyDeviceToDevice, p->stream));
+    if (H.split) {
+        if (!d_Ux) { set_error("unsymmetric LU needs Ux"); return SFB200_ERR_ARG; }
+        if (d_Ux != p->d_ux) CK(cudaMemcpyAsync(p->d_ux, d_Ux, sizeof(double) * (size_t)H.unnz, cudaMemcpyDeviceToDevice, p->stream));
+    }
+    const int rc = run_schedule(p);
+    if (rc) return rc;
+    CK(cudaEventRecord(p->ev[1], p->stream));
+    p->factored = true;
+    return SFB200_OK;
+}
+
+int sfb200_plan_sync(sfb200_plan *p) {
+    if (!p) return SFB200_ERR_ARG;
+    CK(cudaSetDevice(p->device));
+    const int rc = check_status(p);
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, p->ev[0], p->ev[1]) == cudaSuccess) p->ms_numeric = ms;
+    else cudaGetLastError();
+    return rc;
+}
+
+int sfb200_download_factor(sfb200_plan *p, double *Lsx) {
+    if (!p || !Lsx) { set_error("sfb200_download_factor: bad argument"); return SFB200_ERR_ARG; }
+    if (!p->factored) { set_error("sfb200_download_factor: nothing factorized yet"); return SFB200_ERR_STATE; }
+    CK(cudaSetDevice(p->device));
+    const HostPlan &H = p->H;
+    if (!p->d_out) {
+        CK(cudaMalloc((void **)&p->d_out, sizeof(double) * (size_t)std::max<i64>(H.xsize, 1)));
+        p->device_bytes += sizeof(double) * (size_t)H.xsize;
+    }
+    launch_pack(p->d_X, p->d_out, p->d_pack, (int)H.pack_tasks.size(), p->stream);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(Lsx, p->d_out, sizeof(double) * (size_t)H.xsize, cudaMemcpyDeviceToHost, p->stream));
+    CK(cudaStreamSynchronize(p->stream));
+    return SFB200_OK;
+}
+
+int sfb200_factorize(sfb200_plan *p, const double *Lx, const double *Ux, double *Lsx) {
+    if (!p || !Lx) { set_error("sfb200_factorize: bad argument"); return SFB200_ERR_ARG; }
+    CK(cudaSetDevice(p->device));
+    const HostPlan &H = p->H;
+    if (H.split && !Ux) { set_error("unsymmetric LU needs Ux"); return SFB200_ERR_ARG; }
+    CK(cudaEventRecord(p->ev[2], p->stream));
+    CK(cudaMemcpyAsync(p->d_lx, Lx, sizeof(double) * (size_t)H.nnz, cudaMemcpyHostToDevice, p->stream));
+    if (H.split) CK(cudaMemcpyAsync(p->d_ux, Ux, sizeof(double) * (size_t)H.unnz, cudaMemcpyHostToDevice, p->stream));
+    int rc = sfb200_factorize_device(p, p->d_lx, p->d_ux);
+    if (rc) return rc;
+    if (Lsx) {
+        rc = sfb200_download_factor(p, Lsx);
+        if (rc) return rc;
+    }
+    CK(cudaEventRecord(p->ev[3], p->stream));
+    rc = sfb200_plan_sync(p);
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, p->ev[2], p->ev[3]) == cudaSuccess) p->ms_e2e = ms;
+    else cudaGetLastError();
+    return rc;
+}
+
+double sfb200_last_ms(const sfb200_plan *p, int which) {
+    if (!p) return -1.0;
+    return which == 0 ? p->ms_numeric : p->ms_e2e;
+}
+
+int64_t sfb200_last_launches(const sfb200_plan *p) { return p ? p->launches : -1; }
+
+void *sfb200_host_alloc(size_t bytes) {
+    void *ptr = nullptr;
+    if (cudaMallocHost(&ptr, bytes ? bytes : 8) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return ptr;
+}
+void sfb200_host_free(void *ptr) { if (ptr) cudaFreeHost(ptr); }
+
+/* FP64 pipe probes for the roofline denominators: returns TFLOP/s.  which = 0 DFMA (vector pipe), 1 DMMA (tensor pipe) */
+double sfb200_probe_fp64_peak(int device, int which, int iters) {
+    if (sfb200_device_count() <= device) return -1.0;
+    cudaSetDevice(device);
+    const int grid = 148 * 8, block = 256;
+    double *d = nullptr;
+    if (cudaMalloc((void **)&d, sizeof(double) * grid * block) != cudaSuccess) return -1.0;
+    cudaEvent_t a, b;
+    cudaEventCreate(&a); cudaEventCreate(&b);
+    for (int rep = 0; rep < 2; ++rep) {
+        cudaEventRecord(a, 0);
+        if (which == 0) launch_peak_dfma(d, iters, grid, block, 0);
+        else launch_peak_dmma(d, iters, grid, block, 0);
+        cudaEventRecord(b, 0);
+        cudaEventSynchronize(b);
+    }
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, a, b);
+    cudaEventDestroy(a); cudaEventDestroy(b);
+    cudaFree(d);
+    if (cudaGetLastError() != cudaSuccess || ms <= 0.f) return -1.0;
+    const double threads = (double)grid * block;
+    const double flops = which == 0 ? threads * iters * 64.0 * 2.0                     /* 64 FMA per thread-iteration */
+                                    : (threads / 32.0) * iters * 32.0 * 512.0;         /* 32 DMMA x 256 FMA per warp-iteration */
+    return flops / (ms * 1e-3) / 1e12;
+}
+
+}  // extern "C"

@@ -1,0 +1,577 @@
+// Hand-written sm_100a kernels of the numeric factorization engine.
+//
+//   k_assemble   scatter of the permuted matrix values into the zeroed panels     (loadA, CH.c:1998-2028)
+//   k_small      one CTA per small front: whole panel in shared memory, factor, write back, and subtract its
+//                Schur update from the ancestor panels through the relative-index tables
+//                                                         (cpuApplyFactorize + cpuApply for small fronts, CH.c:2030-2148)
+//   k_diag       Cholesky / no-pivot LU of one nb x nb diagonal block per CTA      (dpotrf_, CH.c:2135; magma_dgetrf_nopiv, LU.c:2653)
+//   k_trsm       triangular solves against one diagonal block, one vector per thread (dtrsm_, CH.c:2142, LU.c:2660)
+//   k_gemm       FP64 tensor-core (DMMA m8n8k4) tiles  C -= A B^T  fed by a cp.async shared-memory pipeline; the epilogue
+//                either updates a dense block in place or performs the fused relative-index scatter-subtract
+//                                                         (dsyrk_/dgemm_ + mapped subtract, CH.c:2061-2086, CH.cu:62-124)
+//   k_pack       padded device layout -> the reference's Lsx layout
+#include "kernels.cuh"
+
+#include <cstdio>
+
+namespace sfb200 {
+
+namespace {
+
+// ---------------------------------------------------------------------------------------------------------------
+// small helpers
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async8(void *smem_dst, const void *gsrc, int src_bytes) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(d), "l"(gsrc), "r"(src_bytes));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+// D(8x8) += A(8x4) * B(4x8), FP64 tensor core.  lane = 4*g + t:  a = A[g][t], b = B[t][g], c0/c1 = D[g][2t], D[g][2t+1]
+__device__ __forceinline__ void dmma(double &c0, double &c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+// first op whose tile range contains `tile` (ops sorted by tile0)
+template <class Op>
+__device__ __forceinline__ int find_op(const Op *ops, int nops, int tile) {
+    int lo = 0, hi = nops - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (ops[mid].tile0 <= tile) lo = mid; else hi = mid - 1;
+    }
+    return lo;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// assembly
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void k_assemble(const double *__restrict__ vals, const int64_t *__restrict__ dst, int64_t count,
+                           double *__restrict__ X) {
+    for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < count; p += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t d = dst[p];
+        if (d >= 0) X[d] = vals[p];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// in-shared-memory panel factorizations.  Panel is column-major with leading dimension PR (= number of rows).
+// ---------------------------------------------------------------------------------------------------------------
+// Right-looking Cholesky of the leading n columns of a PR x n trapezoid (POTRF of the n x n block + TRSM of the rows
+// below in one sweep).  The diagonal is left un-rooted in shared memory (d_j); the caller stores sqrt(d_j).
+template <int NT>
+__device__ __forceinline__ void smem_cholesky(double *sh, int PR, int n, int *status) {
+    const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
+    constexpr int TY = NT / 32;
+    for (int j = 0; j < n; ++j) {
+        __syncthreads();
+        const double d = sh[j * PR + j];
+        if (!(d > 0.0) && tid == 0) atomicOr(status, 1);
+        const double rinv = 1.0 / sqrt(d);
+        double *colj = sh + j * PR;
+        for (int r = j + 1 + tid; r < PR; r += NT) colj[r] *= rinv;
+        __syncthreads();
+        for (int c = j + 1 + ty; c < n; c += TY) {
+            const double lcj = colj[c];
+            double *colc = sh + c * PR;
+            for (int r = c + tx; r < PR; r += 32) colc[r] = fma(-colj[r], lcj, colc[r]);
+        }
+    }
+    __syncthreads();
+}
+
+// Right-looking LU without pivoting of a panel whose first R rows are [L11\U11 ; L21] and whose rows [R, PR) are
+// U12^T (updated with the L entries of the diagonal block: U12^T[:,c] -= U12^T[:,k] * L[c,k]).
+template <int NT>
+__device__ __forceinline__ void smem_lu(double *sh, int PR, int R, int n, int *status) {
+    const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
+    constexpr int TY = NT / 32;
+    for (int k = 0; k < n; ++k) {
+        __syncthreads();
+        const double piv = sh[k * PR + k];
+        if (piv == 0.0 && tid == 0) atomicOr(status, 1);
+        const double rinv = 1.0 / piv;
+        double *colk = sh + k * PR;
+        for (int r = k + 1 + tid; r < R; r += NT) colk[r] *= rinv;
+        __syncthreads();
+        for (int c = k + 1 + ty; c < n; c += TY) {
+            double *colc = sh + c * PR;
+            const double u = colc[k], lck = colk[c];
+            for (int r = k + 1 + tx; r < R; r += 32) colc[r] = fma(-colk[r], u, colc[r]);
+            for (int r = R + tx; r < PR; r += 32) colc[r] = fma(-colk[r], lck, colc[r]);
+        }
+    }
+    __syncthreads();
+}
+
+// Schur update of a small front from shared memory, 4x4 register tiles, subtracted from the ancestors with
+// red.global.add.f64.  Sa/Sb: m x n blocks (leading dimension PR).  mode 0: rows >= column (Cholesky);
+// mode 1: rows >= first row of the column's ancestor segment (LU, L side); mode 2: rows >= segment end, U side.
+template <int NT>
+__device__ __forceinline__ void smem_scatter(const PlanDev &P, const double *Sa, const double *Sb, int m, int n, int PR,
+                                             int64_t meta, int mode) {
+    const int nb4 = (m + 3) >> 2;
+    const int ntile = mode == 0 ? nb4 * (nb4 + 1) / 2 : nb4 * nb4;
+    for (int t = threadIdx.x; t < ntile; t += NT) {
+        int bi, bj;
+        if (mode == 0) {
+            bi = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
+            while (bi * (bi + 1) / 2 > t) --bi;
+            while ((bi + 1) * (bi + 2) / 2 <= t) ++bi;
+            bj = t - bi * (bi + 1) / 2;
+        } else {
+            bi = t / nb4;
+            bj = t - bi * nb4;
+        }
+        const int i0 = bi << 2, j0 = bj << 2;
+        if (mode != 0) {
+            const int lim0 = mode == 1 ? P.upd_segb[meta + j0] : P.upd_sege[meta + j0];
+            if (i0 + 3 < lim0) continue;
+        }
+        int ia[4], ja[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { ia[e] = min(i0 + e, m - 1); ja[e] = min(j0 + e, m - 1); }
+        double acc[4][4];
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
+        for (int k = 0; k < n; ++k) {
+            const double *ca = Sa + k * PR, *cb = Sb + k * PR;
+            double av[4], bv[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) { av[e] = ca[ia[e]]; bv[e] = cb[ja[e]]; }
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int b = 0; b < 4; ++b) acc[a][b] = fma(av[a], bv[b], acc[a][b]);
+        }
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            const int j = j0 + b;
+            if (j >= m) break;
+            const int64_t q = meta + j;
+            int64_t col = P.upd_coloff[q];
+            const int64_t relb = P.upd_relbase[q];
+            int lim = j;
+            if (mode == 1) lim = P.upd_segb[q];
+            if (mode == 2) { lim = P.upd_sege[q]; col += P.upd_uoff[q]; }
+#pragma unroll
+            for (int a = 0; a < 4; ++a) {
+                const int i = i0 + a;
+                if (i < m && i >= lim) atomicAdd(P.X + col + P.relmap[relb + i], -acc[a][b]);
+            }
+        }
+    }
+}
+
+template <int NT, bool LU>
+__global__ void __launch_bounds__(NT) k_small(PlanDev P, const int32_t *__restrict__ tasks) {
+    extern __shared__ double sh[];
+    const SnodeDev sn = P.snode[tasks[blockIdx.x]];
+    const int n = sn.nscol, R = sn.nsrow, m = R - n;
+    const int PR = LU ? R + m : R;
+    const int ld = sn.ld, tid = threadIdx.x;
+    double *A = P.X + sn.xoff;
+    const int total = PR * n;
+    for (int idx = tid; idx < total; idx += NT) {
+        const int c = idx / PR, r = idx - c * PR;
+        sh[idx] = A[(int64_t)c * ld + r];
+    }
+    if (LU) smem_lu<NT>(sh, PR, R, n, P.status);
+    else smem_cholesky<NT>(sh, PR, n, P.status);
+    for (int idx = tid; idx < total; idx += NT) {
+        const int c = idx / PR, r = idx - c * PR;
+        double v = sh[idx];
+        if (LU) {
+            A[(int64_t)c * ld + r] = v;
+        } else if (r >= c) {
+            if (r == c) { v = sqrt(v); }
+            A[(int64_t)c * ld + r] = v;
+        }
+    }
+    if (m > 0) {
+        const int64_t meta = sn.lsip + n;
+        if (LU) {
+            smem_scatter<NT>(P, sh + n, sh + R, m, n, PR, meta, 1);
+            smem_scatter<NT>(P, sh + R, sh + n, m, n, PR, meta, 2);
+        } else {
+            smem_scatter<NT>(P, sh + n, sh + n, m, n, PR, meta, 0);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// diagonal blocks of the large fronts
+// ---------------------------------------------------------------------------------------------------------------
+template <bool LU>
+__global__ void __launch_bounds__(256) k_diag(PlanDev P, const DiagOp *__restrict__ ops) {
+    __shared__ double sh[64 * 64];
+    const DiagOp op = ops[blockIdx.x];
+    const int nb = op.nb, tid = threadIdx.x;
+    double *A = P.X + op.a_off;
+    const int total = nb * nb;
+    for (int idx = tid; idx < total; idx += 256) {
+        const int c = idx / nb, r = idx - c * nb;
+        sh[idx] = A[(int64_t)c * op.ld + r];
+    }
+    if (LU) smem_lu<256>(sh, nb, nb, nb, P.status);
+    else smem_cholesky<256>(sh, nb, nb, P.status);
+    for (int idx = tid; idx < total; idx += 256) {
+        const int c = idx / nb, r = idx - c * nb;
+        double v = sh[idx];
+        if (LU) {
+            A[(int64_t)c * op.ld + r] = v;
+        } else if (r >= c) {
+            if (r == c) v = sqrt(v);
+            A[(int64_t)c * op.ld + r] = v;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// triangular solve: x_j = (b_j - sum_{p<j} x_p T[j,p]) / T[j,j], one vector per thread held in registers,
+// T broadcast from shared memory.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(64) k_trsm(PlanDev P, const TrsmOp *__restrict__ ops, int nops) {
+    __shared__ __align__(16) double Ts[64 * 64];   // Ts[j*64 + p] = T[p][j] for p > j, zero elsewhere
+    __shared__ double rinv[64];
+    const TrsmOp op = ops[find_op(ops, nops, (int)blockIdx.x)];
+    const int tid = threadIdx.x, nb = op.nb;
+    const double *D = P.X + op.t_off;
+    const bool trans = (op.flags & T_TRANS) != 0, unit = (op.flags & T_UNIT) != 0;
+    for (int idx = tid; idx < 64 * 64; idx += 64) {
+        const int j = idx >> 6, p = idx & 63;
+        double v = 0.0;
+        if (p < nb && j < nb && p > j) v = trans ? D[j + (int64_t)p * op.ldt] : D[p + (int64_t)j * op.ldt];
+        Ts[idx] = v;
+    }
+    rinv[tid] = (tid < nb && !unit) ? 1.0 / D[tid + (int64_t)tid * op.ldt] : 1.0;
+    __syncthreads();
+
+    const int v = ((int)blockIdx.x - op.tile0) * 64 + tid;
+    if (v >= op.nvec) return;
+    double *B = P.X + op.b_off + (int64_t)v * op.vstride;
+    double b[64];
+    {
+        const double *bp = B;       // running pointer: 64 precomputed 64-bit addresses would not fit in registers
+#pragma unroll
+        for (int j = 0; j < 64; ++j) {
+            b[j] = j < nb ? *bp : 0.0;
+            bp += op.estride;
+        }
+    }
+    double *bout = B;
+#pragma unroll
+    for (int j = 0; j < 64; ++j) {
+        const double x = b[j] * rinv[j];
+        if (j < nb) *bout = x;      // x_j is final: store now so that its register dies here
+        bout += op.estride;
+        const double nx = -x;
+        // chunks of 16 columns with a compiler barrier in between: otherwise every shared-memory load of the
+        // column (up to 63 doubles) is hoisted in front of the FMAs and the vector no longer fits in registers
+#pragma unroll
+        for (int p0 = (j + 1) & ~15; p0 < 64; p0 += 16) {
+#pragma unroll
+            for (int p = p0; p < p0 + 16; ++p)
+                if (p > j) b[p] = fma(nx, Ts[j * 64 + p], b[p]);
+            asm volatile("" ::: "memory");
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// DMMA GEMM tiles.  C(BM x BN) -= A(BM x K) * B(BN x K)^T, operands column-major (rows contiguous).
+//   shared tile layout: [k][row] with a row stride of (BM + 4) doubles -> the 8-byte fragment loads of one half-warp
+//   (4 k x 4 rows) fall in 16 distinct 8-byte banks.
+//   The tensor-core product is issued transposed (D' = Bfrag x Afrag) so that each thread ends up holding two
+//   CONSECUTIVE ROWS of one column of C: 16 contiguous bytes of the column-major destination.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int GEMM_BK = 16;
+
+template <int BM, int BN, int WARPS_M, int WARPS_N, int STAGES>
+struct GemmCfg {
+    static constexpr int NT = WARPS_M * WARPS_N * 32;
+    static constexpr int WM = BM / WARPS_M, WN = BN / WARPS_N;
+    static constexpr int FM = WM / 8, FN = WN / 8;
+    static constexpr int SA = BM + 4, SB = BN + 4;
+    static constexpr int STAGE_DOUBLES = GEMM_BK * (SA + SB);
+    static constexpr int SMEM_BYTES = STAGES * STAGE_DOUBLES * 8;
+};
+
+template <int BM, int BN, int WARPS_M, int WARPS_N, int STAGES>
+__global__ void __launch_bounds__(WARPS_M *WARPS_N * 32)
+    k_gemm(PlanDev P, const GemmOp *__restrict__ ops, int nops) {
+    using Cfg = GemmCfg<BM, BN, WARPS_M, WARPS_N, STAGES>;
+    constexpr int NT = Cfg::NT, FM = Cfg::FM, FN = Cfg::FN, SA = Cfg::SA, SB = Cfg::SB;
+    static_assert(BM == BN, "triangular tile decode assumes square tiles");
+    extern __shared__ __align__(16) double smem[];
+
+    const GemmOp op = ops[find_op(ops, nops, (int)blockIdx.x)];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int M = op.M, N = op.N, K = op.K;
+
+    // ---- which tile -------------------------------------------------------------------------------------------
+    int ti, tj;
+    {
+        const int t = (int)blockIdx.x - op.tile0;
+        const int nj = (N + BN - 1) / BN;
+        if (op.flags & G_LOWER) {
+            const int tri = nj * (nj + 1) / 2;
+            if (t < tri) {
+                ti = (int)((sqrt(8.0 * (double)t + 1.0) - 1.0) * 0.5);
+                while (ti * (ti + 1) / 2 > t) --ti;
+                while ((ti + 1) * (ti + 2) / 2 <= t) ++ti;
+                tj = t - ti * (ti + 1) / 2;
+            } else {
+                const int r = t - tri;
+                ti = nj + r / nj;
+                tj = r - (r / nj) * nj;
+            }
+        } else {
+            ti = t / nj;
+            tj = t - ti * nj;
+        }
+    }
+    const int row0 = ti * BM, col0 = tj * BN;
+
+    // LU scatter ops are enumerated as full rectangles: leave early when the whole tile is masked
+    if (op.flags & (G_LIM_SEGB | G_LIM_SEGE)) {
+        const int lim0 = (op.flags & G_LIM_SEGB) ? P.upd_segb[op.meta + col0] : P.upd_sege[op.meta + col0];
+        if (min(row0 + BM, M) - 1 < lim0) return;
+    }
+
+    const double *Ag = P.X + op.a_off + row0;
+    const double *Bg = P.X + op.b_off + ((op.flags & G_B_KMAJOR) ? (int64_t)col0 * op.ldb : (int64_t)col0);
+    const int mrem = M - row0, nrem = N - col0;
+    const bool b_kmajor = (op.flags & G_B_KMAJOR) != 0;
+
+    auto load_stage = [&](int stage, int kt) {
+        double *As = smem + stage * Cfg::STAGE_DOUBLES;
+        double *Bs = As + GEMM_BK * SA;
+        const int k0 = kt * GEMM_BK;
+#pragma unroll
+        for (int e = tid; e < GEMM_BK * BM; e += NT) {
+            const int k = e / BM, r = e - k * BM;
+            const bool ok = (r < mrem) && (k0 + k < K);
+            const double *src = ok ? Ag + r + (int64_t)(k0 + k) * op.lda : Ag;
+            cp_async8(As + k * SA + r, src, ok ? 8 : 0);
+        }
+        if (!b_kmajor) {
+#pragma unroll
+            for (int e = tid; e < GEMM_BK * BN; e += NT) {
+                const int k = e / BN, r = e - k * BN;
+                const bool ok = (r < nrem) && (k0 + k < K);
+                const double *src = ok ? Bg + r + (int64_t)(k0 + k) * op.ldb : Bg;
+                cp_async8(Bs + k * SB + r, src, ok ? 8 : 0);
+            }
+        } else {
+#pragma unroll
+            for (int e = tid; e < GEMM_BK * BN; e += NT) {
+                const int r = e / GEMM_BK, k = e - r * GEMM_BK;
+                const bool ok = (r < nrem) && (k0 + k < K);
+                const double *src = ok ? Bg + (k0 + k) + (int64_t)r * op.ldb : Bg;
+                cp_async8(Bs + k * SB + r, src, ok ? 8 : 0);
+            }
+        }
+    };
+
+    double acc[FM][FN][2];
+#pragma unroll
+    for (int i = 0; i < FM; ++i)
+#pragma unroll
+        for (int j = 0; j < FN; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+    const int wm0 = (warp % WARPS_M) * Cfg::WM, wn0 = (warp / WARPS_M) * Cfg::WN;
+    const int g = lane >> 2, t4 = lane & 3;
+    const int KT = (K + GEMM_BK - 1) / GEMM_BK;
+
+#pragma unroll
+    for (int s = 0; s < STAGES - 1; ++s) {
+        if (s < KT) load_stage(s, s);
+        cp_async_commit();
+    }
+    for (int kt = 0; kt < KT; ++kt) {
+        cp_async_wait<STAGES - 2>();
+        __syncthreads();
+        if (kt + STAGES - 1 < KT) load_stage((kt + STAGES - 1) % STAGES, kt + STAGES - 1);
+        cp_async_commit();
+        const double *As = smem + (kt % STAGES) * Cfg::STAGE_DOUBLES;
+        const double *Bs = As + GEMM_BK * SA;
+#pragma unroll
+        for (int ks = 0; ks < GEMM_BK; ks += 4) {
+            double af[FM], bf[FN];
+#pragma unroll
+            for (int i = 0; i < FM; ++i) af[i] = As[(ks + t4) * SA + wm0 + 8 * i + g];
+#pragma unroll
+            for (int j = 0; j < FN; ++j) bf[j] = Bs[(ks + t4) * SB + wn0 + 8 * j + g];
+#pragma unroll
+            for (int i = 0; i < FM; ++i)
+#pragma unroll
+                for (int j = 0; j < FN; ++j) dmma(acc[i][j][0], acc[i][j][1], bf[j], af[i]);
+        }
+    }
+    cp_async_wait<0>();
+
+    // ---- epilogue: thread holds C[row0 + wm0 + 8i + 2*t4 + {0,1}][col0 + wn0 + 8j + g] -------------------------
+    if (op.flags & G_SCATTER) {
+#pragma unroll
+        for (int j = 0; j < FN; ++j) {
+            const int c = col0 + wn0 + 8 * j + g;
+            if (c >= N) continue;
+            const int64_t q = op.meta + c;
+            int64_t col = P.upd_coloff[q];
+            const int64_t relb = P.upd_relbase[q];
+            int lim = c;
+            if (op.flags & G_LIM_SEGB) lim = P.upd_segb[q];
+            if (op.flags & G_LIM_SEGE) { lim = P.upd_sege[q]; col += P.upd_uoff[q]; }
+            double *dst = P.X + col;
+            const int32_t *rel = P.relmap + relb;
+#pragma unroll
+            for (int i = 0; i < FM; ++i) {
+                const int r = row0 + wm0 + 8 * i + 2 * t4;
+                if (r < M && r >= lim) atomicAdd(dst + rel[r], -acc[i][j][0]);
+                if (r + 1 < M && r + 1 >= lim) atomicAdd(dst + rel[r + 1], -acc[i][j][1]);
+            }
+        }
+    } else {
+        double *Cg = P.X + op.c_off;
+        const bool lower = (op.flags & G_LOWER) != 0;
+#pragma unroll
+        for (int j = 0; j < FN; ++j) {
+            const int c = col0 + wn0 + 8 * j + g;
+            if (c >= N) continue;
+            double *colp = Cg + (int64_t)c * op.ldc;
+            const int lim = lower ? c : 0;
+#pragma unroll
+            for (int i = 0; i < FM; ++i) {
+                const int r = row0 + wm0 + 8 * i + 2 * t4;
+                if (r < M && r >= lim) colp[r] -= acc[i][j][0];
+                if (r + 1 < M && r + 1 >= lim) colp[r + 1] -= acc[i][j][1];
+            }
+        }
+    }
+}
+
+using Gemm128 = GemmCfg<128, 128, 2, 4, 3>;
+using Gemm64 = GemmCfg<64, 64, 2, 2, 4>;
+
+// ---------------------------------------------------------------------------------------------------------------
+// copy-out
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_pack(const double *__restrict__ X, double *__restrict__ out,
+                                               const PackTask *__restrict__ tasks) {
+    const PackTask t = tasks[blockIdx.x];
+    const int total = t.rows * t.cols;
+    for (int idx = threadIdx.x; idx < total; idx += 256) {
+        const int c = idx / t.rows, r = idx - c * t.rows;
+        out[t.dst + idx] = X[t.src + (int64_t)c * t.ld + r];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// FP64 pipe peak probes
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void k_peak_dfma(double *out, int iters) {
+    double a[8];
+    const double x = 1.0 + 1e-9 * threadIdx.x, y = 1e-9;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) a[i] = i + threadIdx.x;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int r = 0; r < 8; ++r)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) a[i] = fma(a[i], x, y);
+    }
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += a[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+__global__ void k_peak_dmma(double *out, int iters) {
+    double c[8][2];
+    const double a = 1.0 + 1e-9 * threadIdx.x, b = 1e-9 * (threadIdx.x + 1);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) c[i][0] = c[i][1] = i;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) dmma(c[i][0], c[i][1], a, b);
+    }
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += c[i][0] + c[i][1];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+}  // namespace
+
+// =================================================================================================================
+// launchers
+// =================================================================================================================
+cudaError_t kernels_init() {
+    cudaError_t e;
+    e = cudaFuncSetAttribute(k_gemm<128, 128, 2, 4, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, Gemm128::SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_gemm<64, 64, 2, 2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, Gemm64::SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_small<256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_small<256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    return e;
+}
+
+void launch_assemble(const double *vals, const int64_t *dst, int64_t count, double *X, cudaStream_t st) {
+    if (count <= 0) return;
+    const int block = 256;
+    const int grid = (int)std::min<int64_t>((count + block - 1) / block, 148 * 16);
+    k_assemble<<<grid, block, 0, st>>>(vals, dst, count, X);
+}
+
+void launch_small(const PlanDev &P, const int32_t *tasks, int count, int smem, bool big_cta, cudaStream_t st) {
+    if (count <= 0) return;
+    if (P.is_lu) {
+        if (big_cta) k_small<256, true><<<count, 256, smem, st>>>(P, tasks);
+        else k_small<64, true><<<count, 64, smem, st>>>(P, tasks);
+    } else {
+        if (big_cta) k_small<256, false><<<count, 256, smem, st>>>(P, tasks);
+        else k_small<64, false><<<count, 64, smem, st>>>(P, tasks);
+    }
+}
+
+void launch_diag(const PlanDev &P, const DiagOp *ops, int count, cudaStream_t st) {
+    if (count <= 0) return;
+    if (P.is_lu) k_diag<true><<<count, 256, 0, st>>>(P, ops);
+    else k_diag<false><<<count, 256, 0, st>>>(P, ops);
+}
+
+void launch_trsm(const PlanDev &P, const TrsmOp *ops, int count, int grid, cudaStream_t st) {
+    if (count <= 0 || grid <= 0) return;
+    k_trsm<<<grid, 64, 0, st>>>(P, ops, count);
+}
+
+void launch_gemm(const PlanDev &P, const GemmOp *ops, int count, int grid, bool tile128, cudaStream_t st) {
+    if (count <= 0 || grid <= 0) return;
+    if (tile128) k_gemm<128, 128, 2, 4, 3><<<grid, Gemm128::NT, Gemm128::SMEM_BYTES, st>>>(P, ops, count);
+    else k_gemm<64, 64, 2, 2, 4><<<grid, Gemm64::NT, Gemm64::SMEM_BYTES, st>>>(P, ops, count);
+}
+
+void launch_pack(const double *X, double *out, const PackTask *tasks, int count, cudaStream_t st) {
+    if (count <= 0) return;
+    k_pack<<<count, 256, 0, st>>>(X, out, tasks);
+}
+
+void launch_peak_dfma(double *out, int iters, int grid, int block, cudaStream_t st) {
+    k_peak_dfma<<<grid, block, 0, st>>>(out, iters);
+}
+void launch_peak_dmma(double *out, int iters, int grid, int block, cudaStream_t st) {
+    k_peak_dmma<<<grid, block, 0, st>>>(out, iters);
+}
+
+}  // namespace sfb200

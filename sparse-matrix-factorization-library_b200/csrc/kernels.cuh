@@ -1,0 +1,38 @@
+// Device-side interface of the numeric engine: the argument block every kernel receives and the launchers
+// the engine calls.  All kernels are hand-written for sm_100a; no cuBLAS / cuSOLVER anywhere.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "plan_types.h"
+
+namespace sfb200 {
+
+struct PlanDev {
+    double *X;                       // padded factor (see plan_types.h)
+    const SnodeDev *snode;
+    const int64_t *upd_coloff;
+    const int64_t *upd_relbase;
+    const int32_t *upd_segb;
+    const int32_t *upd_sege;
+    const int32_t *upd_uoff;
+    const int32_t *relmap;
+    int *status;                     // bit 0: bad pivot met
+    int is_lu;
+};
+
+// one-time: opt in to large dynamic shared memory for the kernels that need it
+cudaError_t kernels_init();
+
+void launch_assemble(const double *vals, const int64_t *dst, int64_t count, double *X, cudaStream_t st);
+void launch_small(const PlanDev &P, const int32_t *tasks, int count, int smem, bool big_cta, cudaStream_t st);
+void launch_diag(const PlanDev &P, const DiagOp *ops, int count, cudaStream_t st);
+void launch_trsm(const PlanDev &P, const TrsmOp *ops, int count, int grid, cudaStream_t st);
+void launch_gemm(const PlanDev &P, const GemmOp *ops, int count, int grid, bool tile128, cudaStream_t st);
+void launch_pack(const double *X, double *out, const PackTask *tasks, int count, cudaStream_t st);
+
+// micro-benchmarks of the two FP64 pipes (peak measurement for the roofline denominators)
+void launch_peak_dfma(double *out, int iters, int grid, int block, cudaStream_t st);
+void launch_peak_dmma(double *out, int iters, int grid, int block, cudaStream_t st);
+
+}  // namespace sfb200

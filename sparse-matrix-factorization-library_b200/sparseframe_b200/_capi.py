@@ -1,0 +1,73 @@
+"""ctypes binding of lib/libsfb200.so (C ABI: include/sfb200.h).  No torch types cross this boundary."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(os.path.dirname(_PKG), "lib", "libsfb200.so")
+
+_lib = None
+
+SYMBOLS = [
+    "sfb200_version", "sfb200_last_error", "sfb200_analyze", "sfb200_symbolic_wrap", "sfb200_symbolic_int",
+    "sfb200_symbolic_array", "sfb200_symbolic_flops", "sfb200_symbolic_free", "sfb200_device_count",
+    "sfb200_plan_create", "sfb200_plan_free", "sfb200_plan_int", "sfb200_factorize", "sfb200_factorize_device",
+    "sfb200_plan_sync", "sfb200_download_factor", "sfb200_last_ms", "sfb200_last_launches", "sfb200_host_alloc",
+    "sfb200_host_free", "sfb200_probe_fp64_peak",
+]
+
+
+class LibraryMissing(RuntimeError):
+    pass
+
+
+def lib():
+    """Load the native library.  There is no Python/CPU fallback: a missing extension is an error."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise LibraryMissing(
+            "native library %s is missing: run `make -C sparse-matrix-factorization-library_b200` "
+            "(or __graft_entry__.build()); this engine has no fallback path" % LIB_PATH)
+    L = C.CDLL(LIB_PATH)
+    vp, i64, u64, dbl, ci = C.c_void_p, C.c_int64, C.c_uint64, C.c_double, C.c_int
+    L.sfb200_version.restype = C.c_char_p
+    L.sfb200_last_error.restype = C.c_char_p
+    L.sfb200_analyze.argtypes = [ci, ci, i64, vp, vp, vp, u64, C.POINTER(vp)]
+    L.sfb200_symbolic_wrap.argtypes = [ci, i64, i64, vp, vp, vp, vp, vp, vp, vp, vp, C.POINTER(vp)]
+    L.sfb200_symbolic_int.restype = i64
+    L.sfb200_symbolic_int.argtypes = [vp, C.c_char_p]
+    L.sfb200_symbolic_array.restype = vp
+    L.sfb200_symbolic_array.argtypes = [vp, C.c_char_p, C.POINTER(i64)]
+    L.sfb200_symbolic_flops.restype = dbl
+    L.sfb200_symbolic_flops.argtypes = [vp]
+    L.sfb200_symbolic_free.argtypes = [vp]
+    L.sfb200_symbolic_free.restype = None
+    L.sfb200_device_count.restype = ci
+    L.sfb200_plan_create.argtypes = [vp, ci, C.POINTER(vp)]
+    L.sfb200_plan_free.argtypes = [vp]
+    L.sfb200_plan_free.restype = None
+    L.sfb200_plan_int.restype = i64
+    L.sfb200_plan_int.argtypes = [vp, C.c_char_p]
+    L.sfb200_factorize.argtypes = [vp, vp, vp, vp]
+    L.sfb200_factorize_device.argtypes = [vp, vp, vp]
+    L.sfb200_plan_sync.argtypes = [vp]
+    L.sfb200_download_factor.argtypes = [vp, vp]
+    L.sfb200_last_ms.restype = dbl
+    L.sfb200_last_ms.argtypes = [vp, ci]
+    L.sfb200_last_launches.restype = i64
+    L.sfb200_last_launches.argtypes = [vp]
+    L.sfb200_host_alloc.restype = vp
+    L.sfb200_host_alloc.argtypes = [C.c_size_t]
+    L.sfb200_host_free.argtypes = [vp]
+    L.sfb200_host_free.restype = None
+    L.sfb200_probe_fp64_peak.restype = dbl
+    L.sfb200_probe_fp64_peak.argtypes = [ci, ci, ci]
+    _lib = L
+    return L
+
+
+def last_error() -> str:
+    return lib().sfb200_last_error().decode()

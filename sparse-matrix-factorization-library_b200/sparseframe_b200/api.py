@@ -1,0 +1,281 @@
+"""Reference-shaped host API: compress / analyze / factorize / solve_supernodal / validate."""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import _capi
+
+# devSlotSize the reference computes for one B200 (GPU_SPLIT_LIMIT=4 virtual GPUs x 8 slots, CH.c:81-87,199);
+# the symbolic structure depends on it (CH.c:1476-1496, 1556-1574), so it is pinned and recorded with every number.
+DEFAULT_DEVSLOT = 5_380_000_000
+
+CHOLESKY, LU = 0, 1
+
+
+def _kind(kind) -> int:
+    if kind in (LU, "lu", "LU"):
+        return LU
+    if kind in (CHOLESKY, "cholesky", "chol", "Cholesky"):
+        return CHOLESKY
+    raise ValueError("kind must be 'cholesky' or 'lu'")
+
+
+@dataclass
+class Matrix:
+    """Compressed-column matrix as SparseFrame_compress leaves it (CH.c:526-587)."""
+    n: int
+    Cp: np.ndarray
+    Ci: np.ndarray
+    Cx: np.ndarray
+    symmetric: bool
+
+
+def compress(n, rows, cols, vals, symmetric=True) -> Matrix:
+    """Triplets -> CSC by a stable counting sort on the column (CH.c:560-576): file order is kept inside each
+    column, nothing is summed or sorted."""
+    rows = np.asarray(rows, dtype=np.int64)
+    cols = np.asarray(cols, dtype=np.int64)
+    vals = np.asarray(vals, dtype=np.float64)
+    order = np.argsort(cols, kind="stable")
+    cp = np.zeros(n + 1, dtype=np.int64)
+    np.add.at(cp, cols + 1, 1)
+    return Matrix(int(n), np.cumsum(cp), np.ascontiguousarray(rows[order]), np.ascontiguousarray(vals[order]),
+                  bool(symmetric))
+
+
+class Symbolic:
+    """Result of symbolic analysis (SparseFrame_analyze, CH.c:1916-1978 / LU.c:2233-2458)."""
+
+    _INT64 = ("Perm", "Parent", "Post", "ColCount", "Lp", "Li", "LTp", "LTi", "Up", "Ui", "UTp", "UTi", "Super",
+              "SuperMap", "Sparent", "Lsip", "Lsxp", "Lsi", "ST_Map", "ST_Pointer", "ST_Index", "LeafQueue",
+              "Aoffset", "Moffset", "CPCTp", "CPCTi")
+    _F64 = ("Lx", "LTx", "Ux", "UTx")
+
+    def __init__(self, handle, kind, devslot):
+        self._h = handle
+        self.kind = kind
+        self.devslot = devslot
+
+    def int(self, name) -> int:
+        return int(_capi.lib().sfb200_symbolic_int(self._h, name.encode()))
+
+    def array(self, name) -> np.ndarray:
+        cnt = C.c_int64()
+        p = _capi.lib().sfb200_symbolic_array(self._h, name.encode(), C.byref(cnt))
+        dt = np.float64 if name in self._F64 else np.int64
+        if not p or cnt.value == 0:
+            return np.zeros(0, dtype=dt)
+        buf = (C.c_char * (cnt.value * 8)).from_address(p)
+        return np.frombuffer(buf, dtype=dt, count=cnt.value).copy()
+
+    @property
+    def flops(self) -> float:
+        return float(_capi.lib().sfb200_symbolic_flops(self._h))
+
+    def close(self):
+        if self._h:
+            _capi.lib().sfb200_symbolic_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def analyze(A: Matrix, kind="cholesky", devslot=DEFAULT_DEVSLOT) -> Symbolic:
+    L = _capi.lib()
+    h = C.c_void_p()
+    rc = L.sfb200_analyze(_kind(kind), int(A.symmetric), A.n, A.Cp.ctypes.data, A.Ci.ctypes.data, A.Cx.ctypes.data,
+                          int(devslot), C.byref(h))
+    if rc != 0:
+        raise RuntimeError("sfb200_analyze failed (%d): %s" % (rc, _capi.last_error()))
+    return Symbolic(h, _kind(kind), int(devslot))
+
+
+def wrap_structure(kind, n, Super, Lsip, Lsxp, Lsi, Lp, Li, Up=None, Ui=None) -> Symbolic:
+    """Symbolic object around a structure computed elsewhere (e.g. by the reference's own analysis)."""
+    L = _capi.lib()
+    arrs = [np.ascontiguousarray(a, dtype=np.int64) for a in (Super, Lsip, Lsxp, Lsi, Lp, Li)]
+    up = np.ascontiguousarray(Up, dtype=np.int64) if Up is not None else None
+    ui = np.ascontiguousarray(Ui, dtype=np.int64) if Ui is not None else None
+    h = C.c_void_p()
+    rc = L.sfb200_symbolic_wrap(_kind(kind), int(n), len(arrs[0]) - 1, *[a.ctypes.data for a in arrs],
+                                up.ctypes.data if up is not None else None,
+                                ui.ctypes.data if ui is not None else None, C.byref(h))
+    if rc != 0:
+        raise RuntimeError("sfb200_symbolic_wrap failed (%d): %s" % (rc, _capi.last_error()))
+    return Symbolic(h, _kind(kind), 0)
+
+
+def device_count() -> int:
+    return int(_capi.lib().sfb200_device_count())
+
+
+def fp64_peak(device=0, which="dmma", iters=4096) -> float:
+    return float(_capi.lib().sfb200_probe_fp64_peak(int(device), 1 if which == "dmma" else 0, int(iters)))
+
+
+class Plan:
+    """Device-resident numeric schedule for one symbolic structure."""
+
+    def __init__(self, sym: Symbolic, device=0):
+        L = _capi.lib()
+        h = C.c_void_p()
+        rc = L.sfb200_plan_create(sym._h, int(device), C.byref(h))
+        if rc != 0:
+            raise RuntimeError("sfb200_plan_create failed (%d): %s" % (rc, _capi.last_error()))
+        self._h = h
+        self.sym = sym
+
+    def int(self, name) -> int:
+        return int(_capi.lib().sfb200_plan_int(self._h, name.encode()))
+
+    def factorize(self, Lx, Ux=None, out=None, download=True):
+        """Host-buffer factorization (what SparseFrame_factorize maps to).  Returns Lsx in the reference layout."""
+        L = _capi.lib()
+        Lx = np.ascontiguousarray(Lx, dtype=np.float64)
+        ux_p = None
+        if Ux is not None:
+            Ux = np.ascontiguousarray(Ux, dtype=np.float64)
+            ux_p = Ux.ctypes.data
+        if download and out is None:
+            out = np.empty(self.int("xsize"), dtype=np.float64)
+        rc = L.sfb200_factorize(self._h, Lx.ctypes.data, ux_p, out.ctypes.data if download else None)
+        if rc != 0:
+            raise RuntimeError("sfb200_factorize failed (%d): %s" % (rc, _capi.last_error()))
+        return out
+
+    def factorize_device(self, d_lx_ptr: int, d_ux_ptr: int = 0):
+        rc = _capi.lib().sfb200_factorize_device(self._h, d_lx_ptr, d_ux_ptr or None)
+        if rc != 0:
+            raise RuntimeError("sfb200_factorize_device failed (%d): %s" % (rc, _capi.last_error()))
+
+    def sync(self):
+        rc = _capi.lib().sfb200_plan_sync(self._h)
+        if rc != 0:
+            raise RuntimeError("factorization failed (%d): %s" % (rc, _capi.last_error()))
+
+    def download(self, out=None):
+        if out is None:
+            out = np.empty(self.int("xsize"), dtype=np.float64)
+        rc = _capi.lib().sfb200_download_factor(self._h, out.ctypes.data)
+        if rc != 0:
+            raise RuntimeError("sfb200_download_factor failed (%d): %s" % (rc, _capi.last_error()))
+        return out
+
+    def last_ms(self, which=0) -> float:
+        return float(_capi.lib().sfb200_last_ms(self._h, which))
+
+    def last_launches(self) -> int:
+        return int(_capi.lib().sfb200_last_launches(self._h))
+
+    def close(self):
+        if self._h:
+            _capi.lib().sfb200_plan_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def factorize(sym: Symbolic, device=0):
+    """analyze -> factorize in one call, values taken from the analysis (Lx / Ux)."""
+    plan = Plan(sym, device)
+    ux = sym.array("Ux") if (sym.kind == LU and sym.int("symmetric") == 0) else None
+    lsx = plan.factorize(sym.array("Lx"), ux)
+    return plan, lsx
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# consumers of the factor (host, numpy): SparseFrame_solve_supernodal / SparseFrame_validate
+# ---------------------------------------------------------------------------------------------------------------
+def solve_supernodal(kind, Super, Lsip, Lsxp, Lsi, Lsx, b):
+    """Forward/backward substitution over the supernodal factor (CH.c:3036-3139; LU.c:3592-3700), blocked per
+    supernode instead of scalar."""
+    from scipy.linalg import solve_triangular
+    lu = _kind(kind) == LU
+    x = np.array(b, dtype=np.float64, copy=True)
+    ns = len(Super) - 1
+    for s in range(ns):
+        nc = Super[s + 1] - Super[s]
+        nr = Lsip[s + 1] - Lsip[s]
+        ld = 2 * nr - nc if lu else nr
+        P = Lsx[Lsxp[s]:Lsxp[s] + nc * ld].reshape(nc, ld).T          # ld x nc panel
+        rows = Lsi[Lsip[s]:Lsip[s + 1]]
+        xs = solve_triangular(P[:nc, :nc], x[rows[:nc]], lower=True, unit_diagonal=lu, check_finite=False)
+        x[rows[:nc]] = xs
+        if nr > nc:
+            x[rows[nc:]] -= P[nc:nr, :] @ xs
+    for s in range(ns - 1, -1, -1):
+        nc = Super[s + 1] - Super[s]
+        nr = Lsip[s + 1] - Lsip[s]
+        ld = 2 * nr - nc if lu else nr
+        P = Lsx[Lsxp[s]:Lsxp[s] + nc * ld].reshape(nc, ld).T
+        rows = Lsi[Lsip[s]:Lsip[s + 1]]
+        rhs = x[rows[:nc]]
+        if nr > nc:
+            off = P[nr:, :] if lu else P[nc:nr, :]                     # LU: U12^T block, Cholesky: L21
+            rhs = rhs - off.T @ x[rows[nc:]]
+        if lu:
+            x[rows[:nc]] = solve_triangular(P[:nc, :nc], rhs, lower=False, check_finite=False)
+        else:
+            x[rows[:nc]] = solve_triangular(P[:nc, :nc], rhs, lower=True, trans="T", check_finite=False)
+    return x
+
+
+def validate(kind, n, Lp, Li, Lx, Super, Lsip, Lsxp, Lsi, Lsx, Up=None, Ui=None, Ux=None):
+    """The reference's self-check (CH.c:3141-3266): b_i = 1 + i/n, solve, r = A x - b in the PERMUTED system,
+    returns (residual as the reference prints it, relative backward error ||Ax-b|| / (||A|| ||x||))."""
+    import scipy.sparse as sp
+    b = 1.0 + np.arange(n, dtype=np.float64) / n
+    x = solve_supernodal(kind, Super, Lsip, Lsxp, Lsi, Lsx, b)
+    cols = np.repeat(np.arange(n), np.diff(Lp))
+    lower = sp.csc_matrix((Lx, Li, Lp), shape=(n, n))
+    if Up is None:
+        offd = sp.coo_matrix((Lx, (cols, Li)), shape=(n, n)).tocsc()
+        offd.setdiag(0)
+        A = lower + offd
+    else:
+        urow = np.repeat(np.arange(n), np.diff(Up))
+        strict = Li > cols
+        A = sp.coo_matrix((Lx[strict], (Li[strict], cols[strict])), shape=(n, n)).tocsc() + \
+            sp.coo_matrix((Ux, (urow, Ui)), shape=(n, n)).tocsc()
+    r = A @ x - b
+    anorm1 = abs(A).sum(axis=0).max()
+    xinf, binf, rinf = np.abs(x).max(), np.abs(b).max(), np.abs(r).max()
+    residual = rinf / (anorm1 * xinf + binf)
+    backward = rinf / (anorm1 * xinf)
+    return float(residual), float(backward)
+
+
+def lower_trapezoid_mask(kind, Super, Lsip, Lsxp, xsize):
+    """Entries of Lsx the reference defines.  Cholesky: the lower trapezoid of every panel (the strict upper
+    triangle of the diagonal block is never written, CH.c:2135).  LU: everything."""
+    mask = np.ones(int(xsize), dtype=bool)
+    if _kind(kind) == LU:
+        return mask
+    for s in range(len(Super) - 1):
+        nc = int(Super[s + 1] - Super[s])
+        nr = int(Lsip[s + 1] - Lsip[s])
+        if nc > 1:
+            blk = mask[Lsxp[s]:Lsxp[s] + nc * nr].reshape(nc, nr)
+            blk[:, :nc] = np.triu(np.ones((nc, nc), dtype=bool))
+    return mask
+
+
+def entrywise_rel_diff(a, b):
+    """max |a-b| / max(|a|,|b|) with 0/0 := 0 (explicit zeros of relaxed amalgamation must stay exactly zero)."""
+    den = np.maximum(np.abs(a), np.abs(b))
+    d = np.abs(a - b)
+    nz = den > 0
+    if not nz.any():
+        return 0.0
+    return float((d[nz] / den[nz]).max())
