@@ -265,7 +265,8 @@ int build_plan(const Symbolic &S, const PlanParams &prm, HostPlan &P) {
             const SnodeDev &d = P.snode[s];
             const i64 pb = panel_bytes(d);
             int c = -1;
-            for (int k = 0; k < 4; ++k) if (pb <= small_limits[k]) { c = k; break; }
+            if (d.nsrow - d.nscol <= prm.small_max_m)
+                for (int k = 0; k < 4; ++k) if (pb <= small_limits[k]) { c = k; break; }
             if (c >= 0) { cls[c].push_back(s); ++P.nsmall; continue; }
             ++P.nlarge;
             if (lu) emit_lu_panel(d, prm, slots); else emit_cholesky_panel(d, prm, slots);

@@ -16,6 +16,7 @@ struct PlanParams {
     int outer = 256;             // width of the outer block column (trailing updates run with K = outer)
     int small_a_bytes = 6144;    // fronts whose whole panel fits: 64-thread CTA
     int small_b_bytes = 49152;   //                              : 256-thread CTA
+    int small_max_m = 160;       // ... and only if the update (m x m) is small enough for one CTA
     int gemm128_min_m = 192;     // GEMM ops with at least this many rows use 128x128 tiles, others 64x64
 };
 
