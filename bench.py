@@ -1,0 +1,308 @@
+#!/usr/bin/env python
+"""bench.py -- FP64 numeric-factorization throughput of the B200 engine on BASELINE.json's configs.
+
+A "step" is one numeric factorization (assemble + factor) of one synthetic matrix whose symbolic analysis and plan were
+built beforehand (untimed, like the reference's SparseFrame_analyze).  N=1: configs[1], the 3-D 7-point Laplacian 100^3
+supernodal Cholesky.  Timed with CUDA events on the launching stream, K steps between barriers, max over ranks.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config cfg1..cfg5] [--impl reference]
+
+JSON keys beyond the base contract:
+  roofline     : dominant kernel (k_gemm<128x128>, FP64 tensor pipe): algorithmic flops / event-timed duration vs the
+                 DMMA peak probed in the same run (MEASURED_PEAKS.json has no FP64 entry); plus an "hbm" side entry for the
+                 small-front kernel.
+  cpu_baseline : the compiled reference's CPU path (oracle/_ref) on the box's host cores, bounded sample.
+  e2e          : the same metric through the C-ABI host-buffer call (sfb200_factorize) with pinned host Lx / Lsx:
+                 H2D of the matrix values and D2H of the whole factor inside the timed region.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "sparse-matrix-factorization-library_b200"))
+
+METRIC = "fp64_numeric_factorization_gflops"
+UNIT = "GFLOP/s"
+# bounded CPU sample of the same workload family (3-D 7-point Laplacian Cholesky): 64^3 is ~4e11 flop
+CPU_SAMPLE = {"cholesky": ("lap3d", 64), "lu": ("cd3d", 48), "lap2d": ("lap2d", 700), "el3d": ("el3d", 24)}
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def workload_name(cfg, gen, g, kind):
+    names = {"lap2d": "2-D 5-point Laplacian %d^2" % g, "lap3d": "3-D 7-point Laplacian %d^3" % g,
+             "el3d": "3-D 27-point 3-dof elasticity-like %d^3" % g, "cd3d": "3-D 7-point convection-diffusion %d^3" % g}
+    return "%s: supernodal %s, %s, FP64" % (cfg, "LU (no pivoting)" if kind == "lu" else "Cholesky", names[gen])
+
+
+class ClockSampler:
+    """nvidia-smi clocks and throttle reasons while the timed region runs."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index=0):
+        self.samples, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append(line.strip())
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm, mx, reasons = [], 0.0, set()
+        for s in self.samples:
+            f = [t.strip() for t in s.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx = max(mx, float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def reference_arm(args, cfg, gen, g, kind):
+    """--impl reference: the reference's own CPU implementation of the path (compiled from its sources into
+    oracle/_ref), all host threads, one bounded sample per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import sfref
+    import sparseframe_b200 as sf
+    sgen, sg = CPU_SAMPLE["lu" if kind == "lu" else ("cholesky" if gen == "lap3d" else gen)]
+    cores = os.cpu_count()
+    n, r, c, x, sym = sf.matrices.generate(sgen, sg)
+    ref = sfref.Reference(n, r, c, x, sym, kind=kind, blas_threads=min(cores, 16)).analyze()
+    A = sf.compress(n, r, c, x, sym)
+    flops = sf.analyze(A, kind).flops
+    times = []
+    for it in range(args.warmup + args.steps):
+        ref.factorize()
+        if it >= args.warmup:
+            times.append(ref.double("factorizeTime"))
+        log("reference step %d: %.3f s" % (it, ref.double("factorizeTime")))
+    total = sum(times)
+    value = flops * len(times) / total / 1e9
+    sample = "%s %d^%d (n=%d, %.3e flop/step), reference CPU worker path, OpenBLAS threads=%d" % (
+        sgen, sg, 2 if sgen == "lap2d" else 3, n, flops, min(cores, 16))
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(cfg, gen, g, kind), "sample": sample, "devSlotSize": sfref.DEFAULT_DEVSLOT},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "reference", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def cpu_baseline(kind, gen):
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import sfref
+    import sparseframe_b200 as sf
+    if not sfref.available(kind):
+        return None
+    sgen, sg = CPU_SAMPLE["lu" if kind == "lu" else ("cholesky" if gen == "lap3d" else gen)]
+    cores = os.cpu_count()
+    n, r, c, x, sym = sf.matrices.generate(sgen, sg)
+    ref = sfref.Reference(n, r, c, x, sym, kind=kind, blas_threads=min(cores, 16)).analyze()
+    flops = sf.analyze(sf.compress(n, r, c, x, sym), kind).flops
+    best = None
+    for _ in range(2):
+        ref.factorize()
+        t = ref.double("factorizeTime")
+        best = t if best is None else min(best, t)
+    ref.close()
+    return {"value": flops / best / 1e9, "unit": UNIT, "cores": cores, "kind": "reference",
+            "sample": "%s %d^%d (n=%d, %.3e flop), compiled reference CPU path (oracle/_ref), best of 2, %.2f s, "
+                      "OpenBLAS threads=%d (reference caps at 16, parameter.h:12)" % (
+                          sgen, sg, 2 if sgen == "lap2d" else 3, n, flops, best, min(cores, 16))}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--config", default=None)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    import sparseframe_b200 as sf
+    cfg = args.config or ("cfg2" if args.gpus == 1 else "cfg2")
+    gen, g, kind = sf.matrices.CONFIGS[cfg]
+    if args.impl == "reference":
+        reference_arm(args, cfg, gen, g, kind)
+        return
+
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available() or sf.device_count() < 1:
+        raise RuntimeError("bench.py needs a CUDA device: the numeric engine has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- untimed setup: matrix, symbolic analysis, plan (the reference's read + analyze) -------------------------
+    t0 = time.time()
+    n, r, c, x, sym = sf.matrices.generate(gen, g)
+    A = sf.compress(n, r, c, x, sym)
+    S = sf.analyze(A, kind)
+    t_analyze = time.time() - t0
+    t0 = time.time()
+    plan = sf.Plan(S, device=local_rank)
+    t_plan = time.time() - t0
+    flops = S.flops
+    split = kind == "lu" and not sym
+    lx = S.array("Lx")
+    ux = S.array("Ux") if split else None
+    log("rank %d: %s n=%d nsuper=%d xsize=%.3f GB flops=%.4e | analyze %.1fs plan %.2fs | levels %d launches %d "
+        "small %d large %d" % (rank, cfg, n, S.int("nsuper"), S.int("xsize") * 8e-9, flops, t_analyze, t_plan,
+                               plan.int("nlevels"), plan.int("nlaunches"), plan.int("nsmall"), plan.int("nlarge")))
+
+    stream = torch.cuda.current_stream()
+    plan.set_stream(stream.cuda_stream)
+    d_lx = torch.from_numpy(lx).cuda()
+    d_ux = torch.from_numpy(ux).cuda() if split else None
+
+    def step():
+        plan.factorize_device(d_lx.data_ptr(), d_ux.data_ptr() if split else 0)
+
+    # ---- device-resident metric ------------------------------------------------------------------------------------
+    for _ in range(args.warmup):
+        step()
+    plan.sync()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        step()
+    e1.record(stream)
+    barrier()
+    clocks = sampler.stop()
+    plan.sync()
+    ms = e0.elapsed_time(e1)
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    launches = plan.last_launches() * args.steps
+    # every rank factorizes the same matrix (replicas) until the etree-partitioned path lands: total work = world x
+    value = world * flops * args.steps / (ms_total * 1e-3) / 1e9
+
+    # ---- end-to-end through the host-buffer C-ABI call, pinned host memory ------------------------------------------
+    xsize = S.int("xsize")
+    h_lx = torch.from_numpy(lx).pin_memory()
+    h_ux = torch.from_numpy(ux).pin_memory() if split else None
+    h_out = torch.empty(xsize, dtype=torch.float64).pin_memory()
+    from sparseframe_b200 import _capi
+    L = _capi.lib()
+
+    def e2e_step():
+        rc = L.sfb200_factorize(plan._h, h_lx.data_ptr(), h_ux.data_ptr() if split else None, h_out.data_ptr())
+        if rc != 0:
+            raise RuntimeError(_capi.last_error())
+
+    e2e_step()
+    barrier()
+    e2e_steps = max(1, min(args.steps, 3))
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record(stream)
+    for _ in range(e2e_steps):
+        e2e_step()
+    f1.record(stream)
+    barrier()
+    t = torch.tensor([f0.elapsed_time(f1)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_ms = float(t.item()) / e2e_steps
+    e2e_value = world * flops / (e2e_ms * 1e-3) / 1e9
+
+    if rank == 0:
+        # ---- roofline of the dominant kernel: live CUDA-event profile of one replay ------------------------------
+        prof = plan.profile()
+        total_ms = sum(v["ms"] for v in prof.values())
+        dmma_peak = sf.fp64_peak(local_rank, "dmma", 8192)
+        dfma_peak = sf.fp64_peak(local_rank, "dfma", 8192)
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except OSError:
+            pass
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        dom = max(prof, key=lambda k: prof[k]["ms"])
+        d = prof[dom]
+        ach = d["flops"] / (d["ms"] * 1e-3) / 1e12
+        roof = {"kernel": dom, "bound": "tensor", "achieved": ach, "peak": dmma_peak, "unit": "TFLOP/s",
+                "frac": ach / dmma_peak if dmma_peak > 0 else None, "traffic": None,
+                "peak_source": "FP64 DMMA probe in this run (sfb200_probe_fp64_peak); MEASURED_PEAKS.json has no FP64 entry; "
+                               "DFMA vector pipe probe %.2f TFLOP/s" % dfma_peak,
+                "launches": d["launches"], "avg_launch_ms": d["ms"] / d["launches"], "share_of_step": d["ms"] / total_ms,
+                "whole_step": {"achieved": flops / (ms_total / args.steps * 1e-3) / 1e12,
+                               "frac": flops / (ms_total / args.steps * 1e-3) / 1e12 / dmma_peak if dmma_peak > 0 else None},
+                "kernels": {k: {"ms": round(v["ms"], 3), "launches": v["launches"],
+                                "tflops": v["flops"] / (v["ms"] * 1e-3) / 1e12,
+                                "gbs_algorithmic": v["bytes"] / (v["ms"] * 1e-3) / 1e9} for k, v in prof.items()},
+                "hbm": {"peak": hbm_peak, "unit": "GB/s",
+                        "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"}}
+        base = None if args.no_cpu_baseline else cpu_baseline(kind, gen)
+        out = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+            "scaling": "weak" if world > 1 else "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_name(cfg, gen, g, kind), "n": n, "nnz_stored": int(A.Cp[-1]),
+                       "nsuper": S.int("nsuper"), "factor_GB": xsize * 8e-9, "flops_per_step": flops,
+                       "devSlotSize": sf.DEFAULT_DEVSLOT, "l2": "factor (%.1f GB) >> 126 MB L2, no flush needed" % (xsize * 8e-9),
+                       "parallelism": "replicas x%d" % world if world > 1 else "1 GPU",
+                       "analyze_s": t_analyze, "plan_s": t_plan},
+            "clocks": clocks, "gpu_launches": int(launches),
+            "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms,
+                    "h2d_bytes_per_step": int(lx.nbytes + (ux.nbytes if split else 0)),
+                    "d2h_bytes_per_step": int(xsize * 8), "api": "sfb200_factorize (host Lx -> host Lsx, pinned)"},
+            "roofline": roof, "cpu_baseline": base,
+        }
+        print(json.dumps(out))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    plan.close()
+
+
+if __name__ == "__main__":
+    main()

@@ -96,6 +96,15 @@ int sfb200_factorize(sfb200_plan *p, const double *Lx, const double *Ux, double 
 int sfb200_factorize_device(sfb200_plan *p, const double *d_Lx, const double *d_Ux);
 int sfb200_plan_sync(sfb200_plan *p);
 
+/* Run the plan on a caller-owned CUDA stream (cudaStream_t passed as void*) instead of the plan's own one. */
+int sfb200_plan_set_stream(sfb200_plan *p, void *cuda_stream);
+
+/* Instrumented replay (CUDA events around every launch) of the last factorization's values; per-kernel totals are
+ * read back with sfb200_plan_profile_get(kind, what): kind 0/1 small fronts, 2 potrf, 3 getrf, 4 trsm, 5 gemm128,
+ * 6 gemm64; what 0 = ms, 1 = launches, 2 = algorithmic flops, 3 = algorithmic bytes. */
+int sfb200_plan_profile(sfb200_plan *p);
+double sfb200_plan_profile_get(const sfb200_plan *p, int kind, int what);
+
 /* Copy the device-resident factor into the reference's host layout (xsize doubles). */
 int sfb200_download_factor(sfb200_plan *p, double *Lsx);
 

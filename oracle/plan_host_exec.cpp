@@ -137,7 +137,8 @@ extern "C" {
  * Returns 0, or a negative code if analysis/plan failed, or a positive count of failed pivots. */
 long sfcheck_factorize(int kind, int is_symmetric, long n, const long *Cp, const long *Ci, const double *Cx,
                        unsigned long long dev_slot, int nb, int outer, int small_a, int small_b, int ld_align,
-                       double *Lsx_out, long *stats /* [nlevels, nlaunches, nsmall, nlarge, relmap, xsize_pad] */) {
+                       double *Lsx_out, long *stats /* [nlevels, nlaunches, nsmall, nlarge, relmap, xsize_pad, xsize, -] */,
+                       long out_len) {
     CscView A;
     A.n = n; A.colptr = (const i64 *)Cp; A.rowind = (const i64 *)Ci; A.val = Cx; A.symmetric = is_symmetric != 0;
     Symbolic S;
@@ -153,8 +154,9 @@ long sfcheck_factorize(int kind, int is_symmetric, long n, const long *Cp, const
     if (rc != 0) return -10 - rc;
     if (stats) {
         stats[0] = P.nlevels; stats[1] = (long)P.launches.size(); stats[2] = P.nsmall; stats[3] = P.nlarge;
-        stats[4] = (long)P.relmap.size(); stats[5] = P.xsize_pad;
+        stats[4] = (long)P.relmap.size(); stats[5] = P.xsize_pad; stats[6] = P.xsize;
     }
+    if (!Lsx_out || out_len < P.xsize) return 0;     // sizing call
     std::vector<double> X(P.xsize_pad, 0.0);
     const bool lu = P.kind == Kind::LU;
     for (i64 j = 0; j < S.n; ++j)

@@ -1,0 +1,116 @@
+"""oracle/sforacle.py -- TEST INFRASTRUCTURE: ctypes binding of oracle/_ref/libsforacle.so (oracle/sf_oracle.c, the
+plain-C restatement of the reference's numeric path) and of oracle/_ref/libsfcheck.so (oracle/plan_host_exec.cpp, the
+CPU interpreter of the engine's schedule).  Only tests/, __graft_entry__.smoke() and bench.py's baseline legs may
+import this module, and only as the checker."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_lib = None
+_chk = None
+
+
+def _i64(a):
+    return np.ascontiguousarray(a, dtype=np.int64)
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        _lib = C.CDLL(os.path.join(_HERE, "_ref", "libsforacle.so"))
+        _lib.sforacle_factorize.restype = C.c_long
+        _lib.sforacle_factorize.argtypes = [C.c_int, C.c_long, C.c_long] + [C.c_void_p] * 5 + [C.c_long, C.c_long] + \
+            [C.c_void_p] * 8
+        _lib.sforacle_solve.restype = None
+        _lib.sforacle_solve.argtypes = [C.c_int, C.c_long, C.c_long] + [C.c_void_p] * 7
+        _lib.sforacle_residual.restype = C.c_double
+        _lib.sforacle_residual.argtypes = [C.c_int, C.c_long] + [C.c_void_p] * 9
+    return _lib
+
+
+def factorize(kind, st, Lx, Ux=None):
+    """st: dict with Super, SuperMap, Lsip, Lsxp, Lsi, LeafQueue, Lp, Li (+Up, Ui), scalars csize, nsleaf."""
+    lu = kind in (1, "lu")
+    n = len(st["SuperMap"])
+    ns = len(st["Super"]) - 1
+    arr = {k: _i64(st[k]) for k in ("Super", "SuperMap", "Lsip", "Lsxp", "Lsi", "LeafQueue", "Lp", "Li")}
+    Lx = np.ascontiguousarray(Lx, dtype=np.float64)
+    up = ui = ux = None
+    if lu and Ux is not None:
+        up, ui, ux = _i64(st["Up"]), _i64(st["Ui"]), np.ascontiguousarray(Ux, dtype=np.float64)
+    out = np.zeros(int(arr["Lsxp"][-1]), dtype=np.float64)
+    bad = lib().sforacle_factorize(
+        int(lu), n, ns, arr["Super"].ctypes.data, arr["SuperMap"].ctypes.data, arr["Lsip"].ctypes.data,
+        arr["Lsxp"].ctypes.data, arr["Lsi"].ctypes.data, int(st["csize"]), int(st["nsleaf"]),
+        arr["LeafQueue"].ctypes.data, arr["Lp"].ctypes.data, arr["Li"].ctypes.data, Lx.ctypes.data,
+        up.ctypes.data if up is not None else None, ui.ctypes.data if ui is not None else None,
+        ux.ctypes.data if ux is not None else None, out.ctypes.data)
+    return out, int(bad)
+
+
+def solve(kind, st, Lsx, b):
+    lu = kind in (1, "lu")
+    n = len(b)
+    ns = len(st["Super"]) - 1
+    arr = {k: _i64(st[k]) for k in ("Super", "Lsip", "Lsxp", "Lsi")}
+    Lsx = np.ascontiguousarray(Lsx, dtype=np.float64)
+    b = np.ascontiguousarray(b, dtype=np.float64)
+    x = np.empty(n, dtype=np.float64)
+    lib().sforacle_solve(int(lu), n, ns, arr["Super"].ctypes.data, arr["Lsip"].ctypes.data, arr["Lsxp"].ctypes.data,
+                         arr["Lsi"].ctypes.data, Lsx.ctypes.data, b.ctypes.data, x.ctypes.data)
+    return x
+
+
+def residual(kind, st, Lx, b, x, Ux=None):
+    lu = kind in (1, "lu")
+    n = len(b)
+    lp, li = _i64(st["Lp"]), _i64(st["Li"])
+    Lx = np.ascontiguousarray(Lx, dtype=np.float64)
+    up = ui = ux = None
+    if lu and Ux is not None:
+        up, ui, ux = _i64(st["Up"]), _i64(st["Ui"]), np.ascontiguousarray(Ux, dtype=np.float64)
+    out = np.zeros(4)
+    b = np.ascontiguousarray(b, dtype=np.float64)
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    r = lib().sforacle_residual(int(lu), n, lp.ctypes.data, li.ctypes.data, Lx.ctypes.data,
+                                up.ctypes.data if up is not None else None, ui.ctypes.data if ui is not None else None,
+                                ux.ctypes.data if ux is not None else None, b.ctypes.data, x.ctypes.data,
+                                out.ctypes.data)
+    return float(r), out
+
+
+def validate(kind, st, Lx, Lsx, Ux=None):
+    """reference self-check: b_i = 1 + i/n (CH.c:3186) -> (printed residual, backward error ||r|| / (||A|| ||x||))"""
+    n = len(st["SuperMap"])
+    b = 1.0 + np.arange(n, dtype=np.float64) / n
+    x = solve(kind, st, Lsx, b)
+    res, norms = residual(kind, st, Lx, b, x, Ux)
+    return res, float(norms[3] / (norms[0] * norms[2]))
+
+
+def plan_check(kind, A_n, Cp, Ci, Cx, symmetric, devslot, nb=0, outer=0, small_a=-1, small_b=-1, ld_align=0):
+    """analyze + build the engine's schedule + interpret it on the CPU (oracle/plan_host_exec.cpp)."""
+    global _chk
+    if _chk is None:
+        _chk = C.CDLL(os.path.join(_HERE, "_ref", "libsfcheck.so"))
+        _chk.sfcheck_factorize.restype = C.c_long
+        _chk.sfcheck_factorize.argtypes = [C.c_int, C.c_int, C.c_long, C.c_void_p, C.c_void_p, C.c_void_p,
+                                           C.c_ulonglong] + [C.c_int] * 5 + [C.c_void_p, C.c_void_p, C.c_long]
+    Cp, Ci = _i64(Cp), _i64(Ci)
+    Cx = np.ascontiguousarray(Cx, dtype=np.float64)
+    stats = np.zeros(8, dtype=np.int64)
+    # first call sizes the output
+    rc = _chk.sfcheck_factorize(int(kind in (1, "lu")), int(symmetric), int(A_n), Cp.ctypes.data, Ci.ctypes.data,
+                                Cx.ctypes.data, int(devslot), nb, outer, small_a, small_b, ld_align, None,
+                                stats.ctypes.data, 0)
+    if rc < 0:
+        raise RuntimeError("plan check failed: %d" % rc)
+    out = np.zeros(int(stats[6]), dtype=np.float64)
+    rc = _chk.sfcheck_factorize(int(kind in (1, "lu")), int(symmetric), int(A_n), Cp.ctypes.data, Ci.ctypes.data,
+                                Cx.ctypes.data, int(devslot), nb, outer, small_a, small_b, ld_align, out.ctypes.data,
+                                stats.ctypes.data, out.size)
+    return out, int(rc), stats

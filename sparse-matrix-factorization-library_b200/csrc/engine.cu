@@ -19,6 +19,10 @@ struct sfb200_plan {
     HostPlan H;
     int device = 0;
     cudaStream_t stream = nullptr;
+    bool own_stream = true;
+    // per-launch-kind profile of the last sfb200_plan_profile() call: ms, launches, algorithmic flops, bytes
+    double prof_ms[8] = {0}, prof_flops[8] = {0}, prof_bytes[8] = {0};
+    int64_t prof_launches[8] = {0};
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};   // numeric begin/end, e2e begin/end
     PlanDev D{};
     // device copies of the plan
@@ -118,7 +122,7 @@ void sfb200_plan_free(sfb200_plan *p) {
                     p->d_ux, p->d_status};
     for (void *q : ptrs) if (q) cudaFree(q);
     for (auto &e : p->ev) if (e) cudaEventDestroy(e);
-    if (p->stream) cudaStreamDestroy(p->stream);
+    if (p->stream && p->own_stream) cudaStreamDestroy(p->stream);
     delete p;
 }
 
@@ -276,6 +280,101 @@ int sfb200_factorize(sfb200_plan *p, const double *Lx, const double *Ux, double 
     if (cudaEventElapsedTime(&ms, p->ev[2], p->ev[3]) == cudaSuccess) p->ms_e2e = ms;
     else cudaGetLastError();
     return rc;
+}
+
+int sfb200_plan_set_stream(sfb200_plan *p, void *cuda_stream) {
+    if (!p) return SFB200_ERR_ARG;
+    CK(cudaSetDevice(p->device));
+    CK(cudaStreamSynchronize(p->stream));
+    if (p->own_stream && p->stream) cudaStreamDestroy(p->stream);
+    p->stream = (cudaStream_t)cuda_stream;
+    p->own_stream = false;
+    return SFB200_OK;
+}
+
+/* One instrumented replay of the schedule on the values of the last factorize call: CUDA events around every launch,
+ * accumulated per launch kind.  Slower than a plain replay (event records serialise nothing but add ~2 us each). */
+int sfb200_plan_profile(sfb200_plan *p) {
+    if (!p) return SFB200_ERR_ARG;
+    CK(cudaSetDevice(p->device));
+    const HostPlan &H = p->H;
+    cudaStream_t st = p->stream;
+    const size_t nl = H.launches.size();
+    std::vector<cudaEvent_t> ev(nl + 1);
+    for (auto &e : ev) CK(cudaEventCreate(&e));
+    for (int k = 0; k < 8; ++k) { p->prof_ms[k] = p->prof_flops[k] = p->prof_bytes[k] = 0; p->prof_launches[k] = 0; }
+    CK(cudaMemsetAsync(p->d_status, 0, sizeof(int), st));
+    CK(cudaMemsetAsync(p->d_X, 0, sizeof(double) * (size_t)H.xsize_pad, st));
+    launch_assemble(p->d_lx, p->d_asm_l, H.nnz, p->d_X, st);
+    if (H.kind == Kind::LU) launch_assemble(H.split ? p->d_ux : p->d_lx, p->d_asm_u, H.unnz, p->d_X, st);
+    for (size_t i = 0; i < nl; ++i) {
+        const Launch &L = H.launches[i];
+        CK(cudaEventRecord(ev[i], st));
+        switch (L.kind) {
+            case L_SMALL_A: launch_small(p->D, p->d_small + L.first, L.count, L.smem, false, st); break;
+            case L_SMALL_B: launch_small(p->D, p->d_small + L.first, L.count, L.smem, true, st); break;
+            case L_POTRF: case L_GETRF: launch_diag(p->D, p->d_diag + L.first, L.count, st); break;
+            case L_TRSM: launch_trsm(p->D, p->d_trsm + L.first, L.count, L.grid, st); break;
+            case L_GEMM128: launch_gemm(p->D, p->d_gemm + L.first, L.count, L.grid, true, st); break;
+            case L_GEMM64: launch_gemm(p->D, p->d_gemm + L.first, L.count, L.grid, false, st); break;
+            default: break;
+        }
+    }
+    CK(cudaEventRecord(ev[nl], st));
+    CK(cudaStreamSynchronize(st));
+    CK(cudaGetLastError());
+    const bool lu = H.kind == Kind::LU;
+    for (size_t i = 0; i < nl; ++i) {
+        const Launch &L = H.launches[i];
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, ev[i], ev[i + 1]));
+        const int k = L.kind;
+        p->prof_ms[k] += ms;
+        p->prof_launches[k] += 1;
+        double fl = 0, by = 0;
+        for (int q = 0; q < L.count; ++q) {
+            if (k == L_GEMM128 || k == L_GEMM64) {
+                const GemmOp &g = H.gemm_ops[L.first + q];
+                // LU scatter ops are enumerated as full rectangles but only about half of each is wanted
+                const bool half = (g.flags & G_LOWER) != 0;
+                const double outputs = half ? (double)g.N * (g.N + 1) / 2 + (double)(g.M - g.N) * g.N
+                                            : ((g.flags & (G_LIM_SEGB | G_LIM_SEGE)) ? 0.5 * g.M * (double)g.N : (double)g.M * g.N);
+                fl += 2.0 * g.K * outputs;
+                by += 8.0 * ((double)g.M * g.K + (double)g.N * g.K) + 16.0 * outputs;
+            } else if (k == L_TRSM) {
+                const TrsmOp &t = H.trsm_ops[L.first + q];
+                fl += (double)t.nvec * t.nb * t.nb;
+                by += 16.0 * t.nvec * t.nb + 8.0 * t.nb * t.nb;
+            } else if (k == L_POTRF || k == L_GETRF) {
+                const DiagOp &d = H.diag_ops[L.first + q];
+                fl += (lu ? 2.0 : 1.0) * d.nb * (double)d.nb * d.nb / 3.0;
+                by += 16.0 * d.nb * d.nb;
+            } else {
+                const SnodeDev &sn = H.snode[H.small_tasks[L.first + q]];
+                const double c = sn.nscol, m = sn.nsrow - sn.nscol;
+                fl += lu ? 2.0 * c * c * c / 3.0 + 2.0 * m * c * c + 2.0 * m * m * c : c * c * c / 3.0 + m * c * c + m * (m + 1.0) * c;
+                const double pe = lu ? c * (2 * sn.nsrow - c) : c * sn.nsrow;
+                by += 16.0 * pe + 16.0 * (lu ? m * m : m * (m + 1) / 2);   // panel read+write, update entries read-modify-written
+            }
+        }
+        p->prof_flops[k] += fl;
+        p->prof_bytes[k] += by;
+    }
+    for (auto &e : ev) cudaEventDestroy(e);
+    return check_status(p);
+}
+
+/* kind: 0/1 small fronts (64/256-thread CTAs), 2 potrf, 3 getrf, 4 trsm, 5 gemm 128x128, 6 gemm 64x64.
+ * what: 0 = total ms, 1 = launches, 2 = algorithmic flops, 3 = algorithmic bytes */
+double sfb200_plan_profile_get(const sfb200_plan *p, int kind, int what) {
+    if (!p || kind < 0 || kind > 7) return -1.0;
+    switch (what) {
+        case 0: return p->prof_ms[kind];
+        case 1: return (double)p->prof_launches[kind];
+        case 2: return p->prof_flops[kind];
+        case 3: return p->prof_bytes[kind];
+    }
+    return -1.0;
 }
 
 double sfb200_last_ms(const sfb200_plan *p, int which) {

@@ -14,7 +14,8 @@ SYMBOLS = [
     "sfb200_symbolic_array", "sfb200_symbolic_flops", "sfb200_symbolic_free", "sfb200_device_count",
     "sfb200_plan_create", "sfb200_plan_free", "sfb200_plan_int", "sfb200_factorize", "sfb200_factorize_device",
     "sfb200_plan_sync", "sfb200_download_factor", "sfb200_last_ms", "sfb200_last_launches", "sfb200_host_alloc",
-    "sfb200_host_free", "sfb200_probe_fp64_peak",
+    "sfb200_host_free", "sfb200_probe_fp64_peak", "sfb200_plan_set_stream", "sfb200_plan_profile",
+    "sfb200_plan_profile_get",
 ]
 
 
@@ -65,6 +66,10 @@ def lib():
     L.sfb200_host_free.restype = None
     L.sfb200_probe_fp64_peak.restype = dbl
     L.sfb200_probe_fp64_peak.argtypes = [ci, ci, ci]
+    L.sfb200_plan_set_stream.argtypes = [vp, vp]
+    L.sfb200_plan_profile.argtypes = [vp]
+    L.sfb200_plan_profile_get.restype = dbl
+    L.sfb200_plan_profile_get.argtypes = [vp, ci, ci]
     _lib = L
     return L
 

@@ -168,6 +168,29 @@ class Plan:
             raise RuntimeError("sfb200_download_factor failed (%d): %s" % (rc, _capi.last_error()))
         return out
 
+    def set_stream(self, cuda_stream_ptr: int):
+        rc = _capi.lib().sfb200_plan_set_stream(self._h, cuda_stream_ptr)
+        if rc != 0:
+            raise RuntimeError("sfb200_plan_set_stream failed (%d): %s" % (rc, _capi.last_error()))
+
+    KERNELS = {0: "k_small<64>", 1: "k_small<256>", 2: "k_diag<potrf>", 3: "k_diag<getrf>", 4: "k_trsm",
+               5: "k_gemm<128x128>", 6: "k_gemm<64x64>"}
+
+    def profile(self):
+        """Instrumented replay: {kernel: dict(ms, launches, flops, bytes)} for the last factorization's values."""
+        L = _capi.lib()
+        rc = L.sfb200_plan_profile(self._h)
+        if rc != 0:
+            raise RuntimeError("sfb200_plan_profile failed (%d): %s" % (rc, _capi.last_error()))
+        out = {}
+        for k, name in self.KERNELS.items():
+            n = L.sfb200_plan_profile_get(self._h, k, 1)
+            if n > 0:
+                out[name] = dict(ms=L.sfb200_plan_profile_get(self._h, k, 0), launches=int(n),
+                                 flops=L.sfb200_plan_profile_get(self._h, k, 2),
+                                 bytes=L.sfb200_plan_profile_get(self._h, k, 3))
+        return out
+
     def last_ms(self, which=0) -> float:
         return float(_capi.lib().sfb200_last_ms(self._h, which))
 

@@ -1,0 +1,208 @@
+"""Parity of the CUDA path (through the C ABI, lib/libsfb200.so) against the oracle: golden vectors dumped from the
+compiled reference, the plain-C restatement, the compiled reference itself when its .so travelled, and
+size-independent properties at the BASELINE.json sizes.
+
+Bars (BASELINE.json north_star): symbolic structure bit-exact; factor entries within 1e-10 relative (0/0 := 0, explicit
+zeros must stay exactly zero); backward error ||Ax-b||/(||A|| ||x||) <= 1e-12."""
+import os
+
+import numpy as np
+import pytest
+
+import sforacle
+import sfref
+import sparseframe_b200 as sf
+from conftest import build_matrix
+
+pytestmark = pytest.mark.gpu
+
+ENTRY_TOL = 1e-10
+BACKWARD_TOL = 1e-12
+ENV_KEYS = ("SFB200_NB", "SFB200_OUTER", "SFB200_SMALL_A", "SFB200_SMALL_B", "SFB200_GEMM128_MIN")
+
+
+@pytest.fixture(autouse=True)
+def _clean_env():
+    for k in ENV_KEYS:
+        os.environ.pop(k, None)
+    yield
+    for k in ENV_KEYS:
+        os.environ.pop(k, None)
+
+
+def gpu_factor(S, env=None):
+    for k, v in (env or {}).items():
+        os.environ[k] = str(v)
+    plan = sf.Plan(S)
+    split = S.kind == 1 and S.int("symmetric") == 0
+    lsx = plan.factorize(S.array("Lx"), S.array("Ux") if split else None)
+    return plan, lsx
+
+
+def oracle_structure(S):
+    st = {k: S.array(k) for k in ("Super", "SuperMap", "Lsip", "Lsxp", "Lsi", "LeafQueue", "Lp", "Li")}
+    st["csize"], st["nsleaf"] = S.int("csize"), S.int("nsleaf")
+    if S.kind == 1 and S.int("symmetric") == 0:
+        st["Up"], st["Ui"] = S.array("Up"), S.array("Ui")
+    return st
+
+
+def compare(kind, st, ref_lsx, lsx, tol=ENTRY_TOL):
+    mask = sf.lower_trapezoid_mask(kind, st["Super"], st["Lsip"], st["Lsxp"], len(ref_lsx))
+    a, b = ref_lsx[mask], lsx[mask]
+    assert not np.isnan(b).any()
+    assert sf.entrywise_rel_diff(a, b) <= tol
+    assert np.array_equal(a == 0, b == 0), "explicit zeros must stay exactly zero"
+
+
+ENVS = [dict(), dict(SFB200_SMALL_A=0, SFB200_SMALL_B=0), dict(SFB200_NB=16, SFB200_OUTER=32, SFB200_SMALL_A=0, SFB200_SMALL_B=0),
+        dict(SFB200_NB=8, SFB200_OUTER=16, SFB200_SMALL_B=3000), dict(SFB200_GEMM128_MIN=32)]
+
+
+@pytest.mark.parametrize("env", ENVS, ids=[str(e) for e in ENVS])
+def test_golden_vectors(golden, env):
+    A, _ = build_matrix(golden["gen"], golden["grid"])
+    S = sf.analyze(A, golden["kind"], devslot=golden["devslot"])
+    for k in ("Perm", "Super", "SuperMap", "Lsip", "Lsxp", "Lsi"):
+        assert np.array_equal(S.array(k), golden[k]), k
+    plan, lsx = gpu_factor(S, env)
+    compare(golden["kind"], golden, golden["Lsx"], lsx)
+    res, backward = sforacle.validate(golden["kind"], oracle_structure(S), S.array("Lx"), lsx,
+                                      S.array("Ux") if "Ux" in golden else None)
+    assert backward <= BACKWARD_TOL
+    plan.close()
+
+
+CASES = [("lap2d", 120, "cholesky"), ("lap3d", 24, "cholesky"), ("el3d", 8, "cholesky"), ("cd3d", 20, "lu"),
+         ("lap3d", 16, "lu"), ("lap2d", 64, "lu")]
+
+
+@pytest.mark.parametrize("gen,g,kind", CASES)
+@pytest.mark.parametrize("env", [dict(), dict(SFB200_NB=32, SFB200_OUTER=64, SFB200_SMALL_B=8192)], ids=["default", "nb32"])
+def test_against_oracle_restatement(gen, g, kind, env):
+    A, _ = build_matrix(gen, g)
+    S = sf.analyze(A, kind)
+    st = oracle_structure(S)
+    ux = S.array("Ux") if "Up" in st else None
+    ref_lsx, bad = sforacle.factorize(kind, st, S.array("Lx"), ux)
+    assert bad == 0
+    plan, lsx = gpu_factor(S, env)
+    compare(kind, st, ref_lsx, lsx)
+    _, backward = sforacle.validate(kind, st, S.array("Lx"), lsx, ux)
+    assert backward <= BACKWARD_TOL
+    plan.close()
+
+
+@pytest.mark.skipif(not (sfref.available("cholesky") and sfref.available("lu")), reason="compiled reference did not travel")
+@pytest.mark.parametrize("gen,g,kind", [("lap3d", 40, "cholesky"), ("lap2d", 300, "cholesky"), ("cd3d", 32, "lu"),
+                                        ("el3d", 12, "cholesky")])
+def test_against_compiled_reference(gen, g, kind):
+    A, (n, r, c, x, sym) = build_matrix(gen, g)
+    ref = sfref.Reference(n, r, c, x, sym, kind=kind).analyze().factorize()
+    S = sf.analyze(A, kind)
+    for k in ("Perm", "Super", "Lsip", "Lsxp", "Lsi"):
+        assert np.array_equal(S.array(k), ref.array(k)[:len(S.array(k))]), k
+    plan, lsx = gpu_factor(S)
+    compare(kind, oracle_structure(S), ref.array("Lsx"), lsx)
+    ref.close()
+    plan.close()
+
+
+def test_foreign_structure_drop_in(golden):
+    """The drop-in boundary: the structure comes from somebody else's analysis (here: the golden arrays dumped from the
+    reference's SparseFrame_analyze), only the numeric step is ours."""
+    split = "Up" in golden
+    W = sf.api.wrap_structure(golden["kind"], golden["n"], golden["Super"], golden["Lsip"], golden["Lsxp"],
+                              golden["Lsi"], golden["Lp"], golden["Li"], golden["Up"] if split else None,
+                              golden["Ui"] if split else None)
+    plan = sf.Plan(W)
+    lsx = plan.factorize(golden["Lx"], golden["Ux"] if split else None)
+    compare(golden["kind"], golden, golden["Lsx"], lsx)
+    plan.close()
+
+
+def test_edge_cases():
+    # 1x1
+    S = sf.analyze(sf.compress(1, [0], [0], [4.0], True), "cholesky")
+    plan, lsx = gpu_factor(S)
+    assert lsx.tolist() == [2.0]
+    plan.close()
+    # diagonal matrix (no off-diagonals: METIS skipped, every column its own chain)
+    n = 9
+    d = np.arange(1.0, n + 1)
+    S = sf.analyze(sf.compress(n, np.arange(n), np.arange(n), d, True), "cholesky")
+    plan, lsx = gpu_factor(S)
+    st = oracle_structure(S)
+    ref_lsx, _ = sforacle.factorize("cholesky", st, S.array("Lx"))
+    compare("cholesky", st, ref_lsx, lsx)
+    plan.close()
+    # ragged: an arrow matrix (one dense row/column) gives one wide last supernode and many 1-column ones
+    n = 40
+    rows = np.concatenate([np.arange(n), np.full(n - 1, n - 1)])
+    cols = np.concatenate([np.arange(n), np.arange(n - 1)])
+    vals = np.concatenate([np.full(n, 50.0), np.full(n - 1, -1.0)])
+    S = sf.analyze(sf.compress(n, rows, cols, vals, True), "cholesky")
+    plan, lsx = gpu_factor(S)
+    st = oracle_structure(S)
+    ref_lsx, _ = sforacle.factorize("cholesky", st, S.array("Lx"))
+    compare("cholesky", st, ref_lsx, lsx)
+    plan.close()
+
+
+def test_indefinite_matrix_is_reported():
+    n, r, c, x, sym = sf.matrices.generate("lap2d", 10)
+    x = x.copy()
+    x[r == c] = -4.0
+    S = sf.analyze(sf.compress(n, r, c, x, sym), "cholesky")
+    plan = sf.Plan(S)
+    with pytest.raises(RuntimeError, match="pivot"):
+        plan.factorize(S.array("Lx"))
+    plan.close()
+
+
+def test_device_resident_api_and_repeatability():
+    import torch
+    A, _ = build_matrix("lap3d", 20)
+    S = sf.analyze(A, "cholesky")
+    plan = sf.Plan(S)
+    host = plan.factorize(S.array("Lx"))
+    d_lx = torch.from_numpy(S.array("Lx")).cuda()
+    plan.set_stream(torch.cuda.current_stream().cuda_stream)
+    plan.factorize_device(d_lx.data_ptr())
+    plan.sync()
+    dev = plan.download()
+    st = oracle_structure(S)
+    # atomics make the summation order vary run to run: repeatable to rounding, not bitwise
+    compare("cholesky", st, host, dev, tol=1e-12)
+    assert plan.last_launches() > 0 and plan.last_ms(0) > 0
+    prof = plan.profile()
+    assert sum(v["launches"] for v in prof.values()) == plan.int("nlaunches")
+    plan.close()
+
+
+def test_linearity_scaling_property():
+    """chol(4A) = 2 chol(A): scaling by a power of 4 is exact in binary floating point, so the two factors must agree
+    to summation-order rounding."""
+    A, _ = build_matrix("lap3d", 24)
+    S = sf.analyze(A, "cholesky")
+    plan = sf.Plan(S)
+    l1 = plan.factorize(S.array("Lx"))
+    l4 = plan.factorize(4.0 * S.array("Lx"))
+    st = oracle_structure(S)
+    compare("cholesky", st, 2.0 * l1, l4, tol=1e-12)
+    plan.close()
+
+
+@pytest.mark.parametrize("cfg", ["cfg1", "cfg2"])
+def test_full_size_backward_error(cfg):
+    """BASELINE.json configs[0] / configs[1] at full size: the oracle would take minutes, so check the
+    size-independent property -- solve with the factor and measure the backward error of the permuted system."""
+    gen, g, kind = sf.matrices.CONFIGS[cfg]
+    A, _ = build_matrix(gen, g)
+    S = sf.analyze(A, kind)
+    plan = sf.Plan(S)
+    lsx = plan.factorize(S.array("Lx"))
+    res, backward = sforacle.validate(kind, oracle_structure(S), S.array("Lx"), lsx)
+    assert backward <= BACKWARD_TOL
+    assert res <= 1e-13
+    plan.close()

@@ -1,0 +1,70 @@
+"""Host symbolic analysis (csrc/symbolic.cpp) must be BIT-EXACT with the reference's SparseFrame_analyze."""
+import numpy as np
+import pytest
+
+import sfref
+import sparseframe_b200 as sf
+from conftest import build_matrix
+
+INT_ARRAYS = ["Perm", "Parent", "Post", "ColCount", "Lp", "Li", "LTp", "LTi", "Super", "SuperMap", "Sparent", "Lsip",
+              "Lsxp", "Lsi", "ST_Map", "ST_Pointer", "ST_Index", "LeafQueue", "Aoffset", "Moffset"]
+
+
+def test_structure_bit_exact_with_golden(golden):
+    A, _ = build_matrix(golden["gen"], golden["grid"])
+    S = sf.analyze(A, golden["kind"], devslot=golden["devslot"])
+    for k in ("nsuper", "isize", "xsize", "csize", "nstage", "nsleaf"):
+        assert S.int(k) == golden[k], k
+    names = list(INT_ARRAYS)
+    if "Up" in golden:
+        names += ["Up", "Ui", "UTp", "UTi"]
+    for k in names:
+        assert np.array_equal(S.array(k), golden[k]), k
+    assert np.array_equal(S.array("Lx"), golden["Lx"])
+    if "Ux" in golden:
+        assert np.array_equal(S.array("Ux"), golden["Ux"])
+
+
+@pytest.mark.skipif(not sfref.available("cholesky"), reason="compiled reference not built")
+@pytest.mark.parametrize("gen,g,kind,slot", [
+    ("lap2d", 60, "cholesky", sf.DEFAULT_DEVSLOT), ("lap3d", 12, "cholesky", sf.DEFAULT_DEVSLOT),
+    ("lap2d", 150, "cholesky", 200_000), ("lap3d", 30, "cholesky", 3_000_000), ("el3d", 6, "cholesky", sf.DEFAULT_DEVSLOT),
+    ("cd3d", 12, "lu", sf.DEFAULT_DEVSLOT), ("cd3d", 20, "lu", 1_000_000), ("lap3d", 16, "lu", sf.DEFAULT_DEVSLOT),
+])
+def test_structure_bit_exact_with_compiled_reference(gen, g, kind, slot):
+    A, (n, r, c, x, sym) = build_matrix(gen, g)
+    ref = sfref.Reference(n, r, c, x, sym, kind=kind, devslot=slot).analyze()
+    assert np.array_equal(A.Cp, ref.array("Cp")) and np.array_equal(A.Ci, ref.array("Ci"))
+    S = sf.analyze(A, kind, devslot=slot)
+    names = list(INT_ARRAYS) + (["Up", "Ui", "UTp", "UTi"] if kind == "lu" and not sym else [])
+    for k in names:
+        a, b = S.array(k), ref.array(k)
+        assert np.array_equal(a, b[:len(a)]), k
+    for k in ("nsuper", "isize", "xsize", "csize", "nstage", "nsleaf"):
+        assert S.int(k) == ref.long(k), k
+    assert np.array_equal(S.array("Lx"), ref.array("Lx"))
+    ref.close()
+
+
+def test_diagonal_matrix_identity_order():
+    # no off-diagonals: METIS is skipped and the order is the identity (CH.c:933-939)
+    n = 7
+    A = sf.compress(n, np.arange(n), np.arange(n), np.arange(1.0, n + 1), True)
+    S = sf.analyze(A, "cholesky")
+    assert np.array_equal(np.sort(S.array("Perm")), np.arange(n))
+    assert S.int("xsize") == S.array("Lsxp")[-1]
+    assert np.all(S.array("Parent") == -1)
+
+
+def test_one_by_one():
+    A = sf.compress(1, [0], [0], [4.0], True)
+    S = sf.analyze(A, "cholesky")
+    assert S.int("nsuper") == 1 and S.int("xsize") == 1 and S.array("Lsi").tolist() == [0]
+
+
+def test_flop_formula():
+    A, _ = build_matrix("lap3d", 10)
+    S = sf.analyze(A, "cholesky")
+    nc = np.diff(S.array("Super")).astype(float)
+    m = np.diff(S.array("Lsip")) - nc
+    assert S.flops == pytest.approx(float((nc ** 3 / 3 + m * nc ** 2 + m * (m + 1) * nc).sum()), rel=1e-12)
