@@ -1,0 +1,8 @@
+/* Cholesky/Include/SparseFrame.h -- public header of the drop-in Cholesky library (reference: Cholesky/Include/SparseFrame.h:43 declares
+ * only SparseFrame(argc, argv); the analyze / factorize / solve entry points the reference exports without declaring
+ * are declared here too).  Types and prototypes live in dropin/sparseframe_abi.h. */
+#ifndef INCLUDE_SPARSEFRAME_H
+#define INCLUDE_SPARSEFRAME_H
+
+#include "../../dropin/sparseframe_abi.h"
+#endif

@@ -1,0 +1,522 @@
+/*
+ * sparseframe_dropin.cpp -- libSparseFrame.so for the B200 engine: the reference library's exported entry points
+ * (same names, same struct layouts, see sparseframe_abi.h) on top of the C ABI of include/sfb200.h.
+ *
+ * Built twice: plain -> Cholesky/Lib/libSparseFrame.so, -DSPARSEFRAME_LU -> LU/Lib/libSparseFrame.so, mirroring the
+ * reference's two trees (Cholesky/Lib/Makefile:3-22, LU/Lib/Makefile).
+ *
+ * What each entry point does here vs. the reference (CH.c = Cholesky/Source/SparseFrame.c):
+ *   SparseFrame_allocate_gpu   CH.c:16-285    no arenas / cuBLAS handles; only counts devices and derives devSlotSize with
+ *                                             the reference's formula (the symbolic structure depends on it)
+ *   SparseFrame_read_matrix    CH.c:400-691   MatrixMarket coordinate reader + compress, same semantics
+ *   SparseFrame_analyze        CH.c:1916-1978 host symbolic analysis (csrc/symbolic.cpp), bit-exact arrays, plus the
+ *                                             device plan (cached per matrix_info, freed by cleanup)
+ *   SparseFrame_factorize      CH.c:3019-3034 sfb200_factorize: H2D of Lx, GPU numeric factorization, D2H into Lsx
+ *   SparseFrame_solve_supernodal / _validate  CH.c:3036-3266  host loops, same formulae and printed line
+ *   SparseFrame                CH.c:3323-3467 same driver and report format (matrices processed one after another)
+ */
+#ifdef SPARSEFRAME_LU
+#define SF_KIND SFB200_LU
+#else
+#define SF_KIND SFB200_CHOLESKY
+#endif
+
+#include <libgen.h>
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#include <time.h>
+#include <unistd.h>
+
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "../../include/sfb200.h"
+#include "sparseframe_abi.h"
+
+namespace {
+
+struct Cached {
+    sfb200_symbolic *sym = nullptr;
+    sfb200_plan *plan = nullptr;
+    bool pinned_lsx = false;
+};
+std::map<const matrix_info_struct *, Cached> g_cache;
+std::mutex g_mutex;
+
+template <class T>
+T *dup_array(const sfb200_symbolic *s, const char *name, int64_t min_count = 0) {
+    int64_t cnt = 0;
+    const void *src = sfb200_symbolic_array(s, name, &cnt);
+    const int64_t alloc = cnt > min_count ? cnt : min_count;
+    T *dst = (T *)malloc((size_t)(alloc > 0 ? alloc : 1) * sizeof(T));
+    if (cnt > 0) memcpy(dst, src, (size_t)cnt * sizeof(T));
+    return dst;
+}
+
+void drop_cached(const matrix_info_struct *m) {
+    std::lock_guard<std::mutex> lk(g_mutex);
+    auto it = g_cache.find(m);
+    if (it == g_cache.end()) return;
+    if (it->second.plan) sfb200_plan_free(it->second.plan);
+    if (it->second.sym) sfb200_symbolic_free(it->second.sym);
+    g_cache.erase(it);
+}
+
+}  // namespace
+
+extern "C" {
+
+double SparseFrame_time(void) {
+    struct timespec tp;
+    clock_gettime(CLOCK_REALTIME, &tp);
+    return tp.tv_sec + (double)tp.tv_nsec / 1.0e9;
+}
+
+int SparseFrame_allocate_gpu(struct common_info_struct *common_info, struct gpu_info_struct **gpu_info_list_ptr) {
+    const int ngpu = sfb200_device_count();
+    common_info->numGPU_physical = ngpu;
+    common_info->numGPU = ngpu;
+    common_info->numCPU = 0;
+    printf("Num of CPU = %d\n", 0);
+    printf("Num of GPU = %d\n", ngpu);
+
+    /* devSlotSize exactly as the reference derives it (CH.c:36-41, 81-87, 199): 90 % of (device memory - 64 MiB),
+     * divided among GPU_SPLIT_LIMIT/ngpu virtual GPUs and 8 slots, rounded down to 1 MiB.  SF_DEVSLOT overrides. */
+    size_t min_dev = ngpu > 0 ? SIZE_MAX : 0;
+    const int split = ngpu > 0 ? (4 / ngpu > 1 ? 4 / ngpu : 1) : 1;
+    const int slots = SF_A_MULTIPLE + 1 + SF_B_MULTIPLE + SF_C_MULTIPLE + 1;
+    for (int d = 0; d < ngpu; ++d) {
+        cudaDeviceProp prop;
+        if (cudaGetDeviceProperties(&prop, d) != cudaSuccess) continue;
+        size_t sz = (size_t)(((double)prop.totalGlobalMem - 64.0 * 0x400 * 0x400) * 0.9);
+        sz /= split;
+        sz /= slots;
+        sz -= sz % (0x400 * 0x400);
+        sz *= slots;
+        if (sz < min_dev) min_dev = sz;
+    }
+    common_info->minDevMemSize = min_dev;
+    common_info->minHostMemSize = 0;
+    common_info->devSlotSize = min_dev / slots;
+    if (const char *e = getenv("SF_DEVSLOT")) common_info->devSlotSize = strtoull(e, nullptr, 10);
+
+    const int n = ngpu > 0 ? ngpu : 1;
+    *gpu_info_list_ptr = (struct gpu_info_struct *)calloc((size_t)n, sizeof(struct gpu_info_struct));
+    if (!*gpu_info_list_ptr) return 1;
+    for (int d = 0; d < n; ++d) {
+        (*gpu_info_list_ptr)[d].gpuIndex_physical = d < ngpu ? d : -1;
+        (*gpu_info_list_ptr)[d].lastMatrix = -1;
+        omp_init_lock(&(*gpu_info_list_ptr)[d].gpuLock);
+    }
+    printf("Device slot size = %zu bytes (B200 engine keeps the factor resident; value only steers the symbolic structure)\n\n",
+           common_info->devSlotSize);
+    return ngpu > 0 ? 0 : 1;
+}
+
+int SparseFrame_free_gpu(struct common_info_struct *common_info, struct gpu_info_struct **gpu_info_list_ptr) {
+    if (!*gpu_info_list_ptr) return 1;
+    const int n = common_info->numGPU > 0 ? common_info->numGPU : 1;
+    for (int d = 0; d < n; ++d) omp_destroy_lock(&(*gpu_info_list_ptr)[d].gpuLock);
+    free(*gpu_info_list_ptr);
+    *gpu_info_list_ptr = nullptr;
+    common_info->numGPU = 0;
+    return 0;
+}
+
+int SparseFrame_allocate_matrix(struct common_info_struct *common_info, struct matrix_info_struct **matrix_info_list_ptr) {
+    const int n = common_info->matrixThreadNum > 0 ? common_info->matrixThreadNum : 1;
+    *matrix_info_list_ptr = (struct matrix_info_struct *)calloc((size_t)n, sizeof(struct matrix_info_struct));
+    return *matrix_info_list_ptr ? 0 : 1;
+}
+
+int SparseFrame_free_matrix(struct common_info_struct *common_info, struct matrix_info_struct **matrix_info_list_ptr) {
+    if (!*matrix_info_list_ptr) return 1;
+    free(*matrix_info_list_ptr);
+    *matrix_info_list_ptr = nullptr;
+    common_info->numSparseMatrix = 0;
+    return 0;
+}
+
+int SparseFrame_initialize_matrix(struct matrix_info_struct *m) {
+    const int serial = m->serial;
+    const char *path = m->path;
+    memset(m, 0, sizeof(*m));
+    m->serial = serial;
+    m->path = path;
+#ifdef SPARSEFRAME_LU
+    m->factorizeType = TYPE_LU;
+#else
+    m->factorizeType = TYPE_CHOLESKY;
+#endif
+    m->permMethod = PERM_METIS;
+    return 0;
+}
+
+/* MatrixMarket coordinate reader: "real"/anything-else, "symmetric"/anything-else; explicit zeros are dropped,
+ * indices become 0-based (CH.c:423-521). */
+static int read_triplets(struct matrix_info_struct *m) {
+    char *line = nullptr;
+    size_t cap = 0;
+    char s0[1025], s1[1025], s2[1025], s3[1025], s4[1025];
+    auto next_line = [&]() { return getline(&line, &cap, m->file) != -1; };
+    bool ok = false;
+    while (next_line()) if (line[0] != '\0') { ok = true; break; }
+    if (!ok || strncmp(line, "%%MatrixMarket", 14) != 0) { printf("Matrix format error\n\n"); free(line); return 1; }
+    s3[0] = s4[0] = 0;
+    sscanf(line, "%1024s %1024s %1024s %1024s %1024s", s0, s1, s2, s3, s4);
+    m->isSymmetric = strcmp(s4, "symmetric") == 0;
+    m->isComplex = strcmp(s3, "real") != 0;
+    ok = false;
+    while (next_line()) if (line[0] != '\0' && line[0] != '%' && line[0] != '\n') { ok = true; break; }
+    long nrow = 0, ncol = 0, nz = 0;
+    if (!ok || sscanf(line, "%ld %ld %ld", &nrow, &ncol, &nz) != 3) { printf("Matrix format error\n\n"); free(line); return 1; }
+    printf("matrix %s is %s %s, ncol = %ld nrow = %ld nzmax = %ld\n\n", basename((char *)m->path),
+           m->isComplex ? "complex" : "real", m->isSymmetric ? "symmetric" : "unsymmetric", ncol, nrow, nz);
+    if (m->isComplex) { printf("Error: complex matrices are not supported by the B200 engine\n"); free(line); return 1; }
+    m->Tj = (Long *)malloc((size_t)(nz > 0 ? nz : 1) * sizeof(Long));
+    m->Ti = (Long *)malloc((size_t)(nz > 0 ? nz : 1) * sizeof(Long));
+    m->Tx = (Float *)malloc((size_t)(nz > 0 ? nz : 1) * sizeof(Float));
+    long cnt = 0;
+    while (next_line()) {
+        if (line[0] == '\0' || line[0] == '\n') continue;
+        long i, j;
+        double v, w;
+        const int got = sscanf(line, "%ld %ld %lg %lg", &i, &j, &v, &w);
+        if (got < 3) { printf("Error: invalid matrix entry\n"); free(line); return 1; }
+        if (v == 0.0) continue;
+        if (cnt >= nz) { printf("Error: nzmax exceeded\n"); free(line); return 1; }
+        m->Ti[cnt] = i - 1;
+        m->Tj[cnt] = j - 1;
+        m->Tx[cnt] = v;
+        ++cnt;
+    }
+    free(line);
+    m->ncol = ncol;
+    m->nrow = nrow;
+    m->nzmax = cnt;
+    return 0;
+}
+
+/* stable counting sort by column (CH.c:526-587): file order is kept inside each column, nothing is summed */
+int SparseFrame_compress(struct matrix_info_struct *m) {
+    const Long ncol = m->ncol, nz = m->nzmax;
+    m->Cp = (Long *)calloc((size_t)ncol + 1, sizeof(Long));
+    m->Ci = (Long *)malloc((size_t)(nz > 0 ? nz : 1) * sizeof(Long));
+    m->Cx = (Float *)malloc((size_t)(nz > 0 ? nz : 1) * sizeof(Float));
+    for (Long k = 0; k < nz; ++k) ++m->Cp[m->Tj[k] + 1];
+    for (Long j = 0; j < ncol; ++j) m->Cp[j + 1] += m->Cp[j];
+    std::vector<Long> cursor(m->Cp, m->Cp + ncol);
+    for (Long k = 0; k < nz; ++k) {
+        const Long p = cursor[m->Tj[k]]++;
+        m->Ci[p] = m->Ti[k];
+        m->Cx[p] = m->Tx[k];
+    }
+    free(m->Tj); free(m->Ti); free(m->Tx);
+    m->Tj = m->Ti = nullptr;
+    m->Tx = nullptr;
+    return 0;
+}
+
+int SparseFrame_read_matrix(struct matrix_info_struct *m) {
+    const double t0 = SparseFrame_time();
+    m->file = fopen(m->path, "r");
+    if (!m->file) return 1;
+    const int rc = read_triplets(m);
+    fclose(m->file);
+    m->file = nullptr;
+    if (rc) return rc;
+    /* callers of the reference own a workspace of this size (CH.c:679-684); kept for ABI parity, zeroed */
+    m->workSize = (size_t)(10 * m->nrow + (2 * m->nzmax - m->nrow) + 1) * sizeof(Long);
+    m->workspace = calloc(1, m->workSize);
+    SparseFrame_compress(m);
+    m->readTime = SparseFrame_time() - t0;
+    return 0;
+}
+
+int SparseFrame_analyze(struct common_info_struct *common_info, struct matrix_info_struct *m) {
+    const double t0 = SparseFrame_time();
+    drop_cached(m);
+    sfb200_symbolic *s = nullptr;
+    int rc = sfb200_analyze(SF_KIND, m->isSymmetric, m->nrow, (const int64_t *)m->Cp, (const int64_t *)m->Ci, m->Cx,
+                            (uint64_t)common_info->devSlotSize, &s);
+    if (rc) { printf("SparseFrame_analyze: %s\n", sfb200_last_error()); return rc; }
+    const Long n = m->nrow;
+    m->Perm = dup_array<Long>(s, "Perm");
+    m->Lp = dup_array<Long>(s, "Lp");
+    m->Li = dup_array<Long>(s, "Li", m->nzmax);
+    m->Lx = dup_array<Float>(s, "Lx", m->nzmax);
+    m->LTp = dup_array<Long>(s, "LTp");
+    m->LTi = dup_array<Long>(s, "LTi", m->nzmax);
+    m->LTx = dup_array<Float>(s, "LTx", m->nzmax);
+#ifdef SPARSEFRAME_LU
+    if (!m->isSymmetric) {
+        m->Up = dup_array<Long>(s, "Up");
+        m->Ui = dup_array<Long>(s, "Ui", m->nzmax);
+        m->Ux = dup_array<Float>(s, "Ux", m->nzmax);
+        m->UTp = dup_array<Long>(s, "UTp");
+        m->UTi = dup_array<Long>(s, "UTi", m->nzmax);
+        m->UTx = dup_array<Float>(s, "UTx", m->nzmax);
+        m->CPCTp = dup_array<Long>(s, "CPCTp");
+        m->CPCTi = dup_array<Long>(s, "CPCTi");
+        m->nzCPCT = m->CPCTp[n];
+    }
+#endif
+    m->Parent = dup_array<Long>(s, "Parent");
+    m->Post = dup_array<Long>(s, "Post");
+    m->ColCount = dup_array<Long>(s, "ColCount");
+    m->nsuper = sfb200_symbolic_int(s, "nsuper");
+    m->Super = dup_array<Long>(s, "Super", n + 1);
+    m->SuperMap = dup_array<Long>(s, "SuperMap");
+    m->Sparent = dup_array<Long>(s, "Sparent", n);
+    m->nsleaf = sfb200_symbolic_int(s, "nsleaf");
+    m->LeafQueue = dup_array<Long>(s, "LeafQueue");
+    m->isize = sfb200_symbolic_int(s, "isize");
+    m->xsize = sfb200_symbolic_int(s, "xsize");
+    m->csize = sfb200_symbolic_int(s, "csize");
+    m->Lsip = dup_array<Long>(s, "Lsip");
+    m->Lsxp = dup_array<Long>(s, "Lsxp");
+    m->Lsi = dup_array<Long>(s, "Lsi");
+    m->nstage = sfb200_symbolic_int(s, "nstage");
+    m->ST_Map = dup_array<Long>(s, "ST_Map");
+    m->ST_Pointer = dup_array<Long>(s, "ST_Pointer");
+    m->ST_Index = dup_array<Long>(s, "ST_Index");
+    m->Aoffset = dup_array<size_t>(s, "Aoffset");
+    m->Moffset = dup_array<size_t>(s, "Moffset");
+    /* the factor buffer: page-locked so that the copy-out of factorize runs at PCIe speed */
+    Cached c;
+    c.sym = s;
+    m->Lsx = (Float *)sfb200_host_alloc((size_t)(m->xsize > 0 ? m->xsize : 1) * sizeof(Float));
+    c.pinned_lsx = m->Lsx != nullptr;
+    if (!m->Lsx) m->Lsx = (Float *)malloc((size_t)(m->xsize > 0 ? m->xsize : 1) * sizeof(Float));
+    printf("nrow = %ld nfsuper = %ld nsuper = %ld nstage = %ld\n", n, (long)sfb200_symbolic_int(s, "nfsuper"), m->nsuper,
+           m->nstage);
+    /* the numeric plan (levels, batched task lists, relative-index tables) is symbolic work too: build + upload now */
+    if (sfb200_plan_create(s, 0, &c.plan) != SFB200_OK) {
+        printf("SparseFrame_analyze: no device plan (%s)\n", sfb200_last_error());
+        c.plan = nullptr;
+    }
+    {
+        std::lock_guard<std::mutex> lk(g_mutex);
+        g_cache[m] = c;
+    }
+    m->analyzeTime = SparseFrame_time() - t0;
+    return 0;
+}
+
+int SparseFrame_factorize(struct common_info_struct *common_info, struct gpu_info_struct *gpu_info_list,
+                          struct matrix_info_struct *m) {
+    (void)common_info;
+    const double t0 = SparseFrame_time();
+    Cached c;
+    {
+        std::lock_guard<std::mutex> lk(g_mutex);
+        auto it = g_cache.find(m);
+        if (it != g_cache.end()) c = it->second;
+    }
+    int rc = SFB200_OK;
+    if (!c.plan) {
+        /* structure produced by somebody else's analysis (e.g. the reference's): wrap what factorize reads */
+        const int64_t *up = nullptr, *ui = nullptr;
+#ifdef SPARSEFRAME_LU
+        if (!m->isSymmetric) { up = (const int64_t *)m->Up; ui = (const int64_t *)m->Ui; }
+#endif
+        rc = sfb200_symbolic_wrap(SF_KIND, m->nrow, m->nsuper, (const int64_t *)m->Super, (const int64_t *)m->Lsip,
+                                  (const int64_t *)m->Lsxp, (const int64_t *)m->Lsi, (const int64_t *)m->Lp,
+                                  (const int64_t *)m->Li, up, ui, &c.sym);
+        if (rc == SFB200_OK) rc = sfb200_plan_create(c.sym, 0, &c.plan);
+        if (rc != SFB200_OK) { printf("SparseFrame_factorize: %s\n", sfb200_last_error()); return rc; }
+        std::lock_guard<std::mutex> lk(g_mutex);
+        g_cache[m] = c;
+    }
+    if (gpu_info_list) omp_set_lock(&gpu_info_list[0].gpuLock);      /* one matrix at a time per device (CH.c:2287) */
+    const double *ux = nullptr;
+#ifdef SPARSEFRAME_LU
+    if (!m->isSymmetric) ux = m->Ux;
+#endif
+    rc = sfb200_factorize(c.plan, m->Lx, ux, m->Lsx);
+    if (gpu_info_list) omp_unset_lock(&gpu_info_list[0].gpuLock);
+    if (rc != SFB200_OK) printf("SparseFrame_factorize: %s\n", sfb200_last_error());
+    m->factorizeTime = SparseFrame_time() - t0;
+    return rc;
+}
+
+/* forward / backward substitution over the supernodal factor (CH.c:3074-3134, LU.c:3630-3694) */
+int SparseFrame_solve_supernodal(struct matrix_info_struct *m) {
+    const double t0 = SparseFrame_time();
+    const Long n = m->nrow, ns = m->nsuper;
+    const Long *Super = m->Super, *Lsip = m->Lsip, *Lsxp = m->Lsxp, *Lsi = m->Lsi;
+    const Float *Lsx = m->Lsx;
+    Float *x = m->Xx;
+    memcpy(x, m->Bx, (size_t)n * sizeof(Float));
+    for (Long s = 0; s < ns; ++s) {
+        const Long nc = Super[s + 1] - Super[s], nr = Lsip[s + 1] - Lsip[s];
+#ifdef SPARSEFRAME_LU
+        const Long ld = 2 * nr - nc;
+#else
+        const Long ld = nr;
+#endif
+        const Long *rows = Lsi + Lsip[s];
+        const Float *P = Lsx + Lsxp[s];
+        for (Long j = 0; j < nc; ++j) {
+#ifndef SPARSEFRAME_LU
+            x[rows[j]] /= P[j * ld + j];
+#endif
+            const Float xj = x[rows[j]];
+            for (Long i = j + 1; i < nr; ++i) x[rows[i]] -= P[j * ld + i] * xj;
+        }
+    }
+    for (Long s = ns - 1; s >= 0; --s) {
+        const Long nc = Super[s + 1] - Super[s], nr = Lsip[s + 1] - Lsip[s];
+        const Long *rows = Lsi + Lsip[s];
+        const Float *P = Lsx + Lsxp[s];
+#ifdef SPARSEFRAME_LU
+        const Long ld = 2 * nr - nc;
+        for (Long j = nc - 1; j >= 0; --j) {
+            Float acc = x[rows[j]];
+            for (Long i = j + 1; i < nc; ++i) acc -= P[i * ld + j] * x[rows[i]];
+            for (Long i = nc; i < nr; ++i) acc -= P[j * ld + (nr - nc) + i] * x[rows[i]];
+            x[rows[j]] = acc / P[j * ld + j];
+        }
+#else
+        const Long ld = nr;
+        for (Long j = nc - 1; j >= 0; --j) {
+            Float acc = x[rows[j]];
+            for (Long i = j + 1; i < nr; ++i) acc -= P[j * ld + i] * x[rows[i]];
+            x[rows[j]] = acc / P[j * ld + j];
+        }
+#endif
+    }
+    m->solveTime = SparseFrame_time() - t0;
+    return 0;
+}
+
+/* b_i = 1 + i/n, solve, residual of the permuted system, printed like the reference (CH.c:3141-3266) */
+int SparseFrame_validate(struct matrix_info_struct *m) {
+    const Long n = m->nrow;
+    m->Bx = (Float *)malloc((size_t)(n > 0 ? n : 1) * sizeof(Float));
+    m->Xx = (Float *)malloc((size_t)(n > 0 ? n : 1) * sizeof(Float));
+    m->Rx = (Float *)malloc((size_t)(n > 0 ? n : 1) * sizeof(Float));
+    for (Long i = 0; i < n; ++i) m->Bx[i] = 1 + i / (Float)n;
+    SparseFrame_solve_supernodal(m);
+    const Float *x = m->Xx;
+    Float *r = m->Rx;
+    std::vector<Float> colsum((size_t)(n > 0 ? n : 1), 0.0);
+    for (Long i = 0; i < n; ++i) r[i] = -m->Bx[i];
+    bool split = false;
+#ifdef SPARSEFRAME_LU
+    split = !m->isSymmetric;
+#endif
+    for (Long j = 0; j < n; ++j)
+        for (Long p = m->Lp[j]; p < m->Lp[j + 1]; ++p) {
+            const Long i = m->Li[p];
+            const Float v = m->Lx[p];
+            if (!split) {
+                r[i] += v * x[j];
+                colsum[j] += fabs(v);
+                if (i != j) { r[j] += v * x[i]; colsum[i] += fabs(v); }
+            } else if (i > j) {
+                r[i] += v * x[j];
+                colsum[j] += fabs(v);
+            }
+        }
+#ifdef SPARSEFRAME_LU
+    if (split)
+        for (Long i = 0; i < n; ++i)
+            for (Long p = m->Up[i]; p < m->Up[i + 1]; ++p) {
+                r[i] += m->Ux[p] * x[m->Ui[p]];
+                colsum[m->Ui[p]] += fabs(m->Ux[p]);
+            }
+#endif
+    Float anorm = 0, bnorm = 0, xnorm = 0, rnorm = 0;
+    for (Long i = 0; i < n; ++i) {
+        if (colsum[i] > anorm) anorm = colsum[i];
+        if (fabs(m->Bx[i]) > bnorm) bnorm = fabs(m->Bx[i]);
+        if (fabs(x[i]) > xnorm) xnorm = fabs(x[i]);
+        if (fabs(r[i]) > rnorm) rnorm = fabs(r[i]);
+    }
+    printf("anorm = %le bnorm = %le xnorm = %le rnorm = %le\n", anorm, bnorm, xnorm, rnorm);
+    m->residual = rnorm / (anorm * xnorm + bnorm);
+    return 0;
+}
+
+int SparseFrame_cleanup_matrix(struct matrix_info_struct *m) {
+    bool pinned = false;
+    {
+        std::lock_guard<std::mutex> lk(g_mutex);
+        auto it = g_cache.find(m);
+        if (it != g_cache.end()) pinned = it->second.pinned_lsx;
+    }
+    drop_cached(m);
+    void *owned[] = {m->Tj, m->Ti, m->Tx, m->Cp, m->Ci, m->Cx, m->Lp, m->Li, m->Lx, m->LTp, m->LTi, m->LTx, m->Perm,
+                     m->Post, m->Parent, m->ColCount, m->Super, m->SuperMap, m->Sparent, m->LeafQueue, m->Lsip, m->Lsxp,
+                     m->Lsi, m->ST_Map, m->ST_Pointer, m->ST_Index, m->Aoffset, m->Moffset, m->workspace, m->Bx, m->Xx,
+                     m->Rx};
+    for (void *q : owned) if (q) free(q);
+#ifdef SPARSEFRAME_LU
+    void *owned_lu[] = {m->CPCTp, m->CPCTi, m->Up, m->Ui, m->Ux, m->UTp, m->UTi, m->UTx};
+    for (void *q : owned_lu) if (q) free(q);
+#endif
+    if (m->Lsx) { if (pinned) sfb200_host_free(m->Lsx); else free(m->Lsx); }
+    const double rt = m->readTime, at = m->analyzeTime, ft = m->factorizeTime, st = m->solveTime;
+    const Float res = m->residual;
+    SparseFrame_initialize_matrix(m);
+    m->readTime = rt; m->analyzeTime = at; m->factorizeTime = ft; m->solveTime = st; m->residual = res;
+    return 0;
+}
+
+int SparseFrame(int argc, char **argv) {
+    struct common_info_struct common;
+    memset(&common, 0, sizeof(common));
+    struct gpu_info_struct *gpus = nullptr;
+    struct matrix_info_struct *mats = nullptr;
+
+    double t0 = SparseFrame_time();
+    if (SparseFrame_allocate_gpu(&common, &gpus) != 0) {
+        printf("SparseFrame: no CUDA device -- the B200 engine has no CPU fallback\n");
+        if (gpus) SparseFrame_free_gpu(&common, &gpus);
+        return 1;
+    }
+    common.numSparseMatrix = argc - 1;
+    common.matrixThreadNum = 1;
+    printf("Num of matrices = %d\n\n", common.numSparseMatrix);
+    SparseFrame_allocate_matrix(&common, &mats);
+    common.allocateTime = SparseFrame_time() - t0;
+    printf("Allocate time:        %lf\n\n", common.allocateTime);
+
+    t0 = SparseFrame_time();
+    for (int k = 0; k < common.numSparseMatrix; ++k) {
+        struct matrix_info_struct *m = mats;
+        m->serial = k;
+        m->path = argv[1 + k];
+        SparseFrame_initialize_matrix(m);
+        if (SparseFrame_read_matrix(m) != 0) { printf("cannot read %s\n\n", m->path); continue; }
+        if (SparseFrame_analyze(&common, m) != 0) { SparseFrame_cleanup_matrix(m); continue; }
+        cudaDeviceSynchronize();
+        SparseFrame_factorize(&common, gpus, m);
+        SparseFrame_validate(m);
+        SparseFrame_cleanup_matrix(m);
+        printf("Matrix name:    %s\n", basename((char *)argv[1 + k]));
+        printf("Read time:      %lf\n", m->readTime);
+        printf("Analyze time:   %lf\n", m->analyzeTime);
+        printf("Factorize time: %lf\n", m->factorizeTime);
+        printf("Solve time:     %lf\n", m->solveTime);
+        printf("residual (|Ax-b|)/(|A||x|+|b|): %le\n\n", m->residual);
+    }
+    common.computeTime = SparseFrame_time() - t0;
+    printf("Total computing time: %lf\n\n", common.computeTime);
+
+    t0 = SparseFrame_time();
+    SparseFrame_free_gpu(&common, &gpus);
+    SparseFrame_free_matrix(&common, &mats);
+    common.freeTime = SparseFrame_time() - t0;
+    printf("Free time:            %lf\n\n", common.freeTime);
+    return 0;
+}
+
+}  // extern "C"
