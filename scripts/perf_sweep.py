@@ -1,0 +1,42 @@
+"""Timing sweep over plan parameters for one config: analysis once, then one plan per environment setting."""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "sparse-matrix-factorization-library_b200"))
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+import sparseframe_b200 as sf  # noqa: E402
+
+cfg = sys.argv[1] if len(sys.argv) > 1 else "cfg2"
+gen, g, kind = sf.matrices.CONFIGS[cfg]
+n, r, c, x, sym = sf.matrices.generate(gen, g)
+S = sf.analyze(sf.compress(n, r, c, x, sym), kind)
+split = kind == "lu" and not sym
+lx, ux = S.array("Lx"), (S.array("Ux") if split else None)
+KEYS = ("SFB200_NB", "SFB200_OUTER", "SFB200_SMALL_A", "SFB200_SMALL_B", "SFB200_GEMM128_MIN")
+envs = [dict()]
+for spec in sys.argv[2:]:
+    envs.append(dict(kv.split("=") for kv in spec.split(",")))
+for env in envs:
+    for k in KEYS:
+        os.environ.pop(k, None)
+    os.environ.update(env)
+    plan = sf.Plan(S)
+    best = 1e30
+    for _ in range(3):
+        plan.factorize(lx, ux, download=False)
+        best = min(best, plan.last_ms(0))
+    prof = plan.profile()
+    line = "%s env=%s launches=%d numeric %.2f ms  %.2f TFLOP/s |" % (cfg, env, plan.int("nlaunches"), best, S.flops / best / 1e9)
+    for k, v in prof.items():
+        line += " %s %.1fms(%d, %.1fTF)" % (k.replace("k_", ""), v["ms"], v["launches"], v["flops"] / v["ms"] / 1e9)
+    print(line, flush=True)
+    if not env:
+        import sforacle
+        st = {k: S.array(k) for k in ("Super", "SuperMap", "Lsip", "Lsxp", "Lsi", "LeafQueue", "Lp", "Li")}
+        st["csize"], st["nsleaf"] = S.int("csize"), S.int("nsleaf")
+        if split:
+            st["Up"], st["Ui"] = S.array("Up"), S.array("Ui")
+        res, bwd = sforacle.validate(kind, st, lx, plan.download(), ux)
+        print("   residual %.2e backward %.2e" % (res, bwd), flush=True)
+    plan.close()

@@ -206,31 +206,103 @@ __global__ void __launch_bounds__(NT) k_small(PlanDev P, const int32_t *__restri
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// diagonal blocks of the large fronts
+// diagonal blocks of the large fronts: 64 x 64 (smaller blocks are padded with the identity) held in REGISTERS,
+// 256 threads as a 16 x 16 grid of 4 x 4 blocks.  One __syncthreads per column: in phase j every thread applies the
+// rank-1 update of column j to its block; the threads that own column j+1 then know its final entries and publish the
+// scaled column (and, for LU, the owners of row j+1 publish the row) for the next phase.  The running diagonal is
+// kept in shared memory (double-buffered) so that the owners of column j+1 can form the pivot without waiting for the
+// thread that owns the diagonal entry.
 // ---------------------------------------------------------------------------------------------------------------
 template <bool LU>
 __global__ void __launch_bounds__(256) k_diag(PlanDev P, const DiagOp *__restrict__ ops) {
-    __shared__ double sh[64 * 64];
+    __shared__ double lcol[2][64];
+    __shared__ double urow[2][64];
+    __shared__ double dsum[2][64];
     const DiagOp op = ops[blockIdx.x];
     const int nb = op.nb, tid = threadIdx.x;
+    const int ty = tid >> 4, tx = tid & 15;
+    const int r0 = ty << 2, c0 = tx << 2;
     double *A = P.X + op.a_off;
-    const int total = nb * nb;
-    for (int idx = tid; idx < total; idx += 256) {
-        const int c = idx / nb, r = idx - c * nb;
-        sh[idx] = A[(int64_t)c * op.ld + r];
+    const bool active = LU || ty >= tx;
+
+    double a[4][4];
+#pragma unroll
+    for (int cc = 0; cc < 4; ++cc)
+#pragma unroll
+        for (int rr = 0; rr < 4; ++rr) {
+            const int r = r0 + rr, c = c0 + cc;
+            a[rr][cc] = (r < nb && c < nb) ? A[(int64_t)c * op.ld + r] : (r == c ? 1.0 : 0.0);
+        }
+    if (ty == tx) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) dsum[0][r0 + e] = a[e][e];
     }
-    if (LU) smem_lu<256>(sh, nb, nb, nb, P.status);
-    else smem_cholesky<256>(sh, nb, nb, P.status);
-    for (int idx = tid; idx < total; idx += 256) {
-        const int c = idx / nb, r = idx - c * nb;
-        double v = sh[idx];
-        if (LU) {
-            A[(int64_t)c * op.ld + r] = v;
-        } else if (r >= c) {
-            if (r == c) v = sqrt(v);
-            A[(int64_t)c * op.ld + r] = v;
+    if (tid < 64) { lcol[0][tid] = 0.0; urow[0][tid] = 0.0; }
+    __syncthreads();
+
+    // phase j = -1 .. 62 prepares column j+1; phases 0..62 also apply column j.  (column 63 needs no update phase)
+    int buf = 0;
+#pragma unroll 1
+    for (int jb = 0; jb < 16; ++jb) {
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+            const int jn = jb * 4 + jj;          // column being prepared in this phase (= j + 1)
+            // ---- apply column j = jn - 1 (its scaled column / row are in lcol[buf], urow[buf]) ----------------------
+            double lr[4], uc[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                lr[e] = lcol[buf][r0 + e];
+                uc[e] = LU ? urow[buf][c0 + e] : lcol[buf][c0 + e];
+            }
+            if (active) {
+#pragma unroll
+                for (int cc = 0; cc < 4; ++cc)
+#pragma unroll
+                    for (int rr = 0; rr < 4; ++rr) a[rr][cc] = fma(-lr[rr], uc[cc], a[rr][cc]);
+            }
+            // ---- pivot of column jn from the running diagonal ---------------------------------------------------------
+            const double dprev = dsum[buf][jn];
+            const double lj = lcol[buf][jn], uj = LU ? urow[buf][jn] : lj;
+            const double d = fma(-lj, uj, dprev);
+            double rinv;
+            if (LU) {
+                if (d == 0.0 && tid == 0) atomicOr(P.status, 1);
+                rinv = 1.0 / d;
+            } else {
+                if (!(d > 0.0) && tid == 0) atomicOr(P.status, 1);
+                rinv = rsqrt(d);
+            }
+            const int nbuf = buf ^ 1;
+            if (tid < 64) dsum[nbuf][tid] = fma(-lcol[buf][tid], LU ? urow[buf][tid] : lcol[buf][tid], dsum[buf][tid]);
+            if (tx == jb && active) {            // owners of column jn: scale the entries below the diagonal, publish
+#pragma unroll
+                for (int rr = 0; rr < 4; ++rr) {
+                    const int r = r0 + rr;
+                    double v = 0.0;
+                    if (r > jn) { v = a[rr][jj] * rinv; a[rr][jj] = v; }
+                    else if (r == jn && !LU) a[rr][jj] = d * rinv;       // sqrt(d)
+                    lcol[nbuf][r] = v;
+                }
+            }
+            if (LU && ty == jb) {                // owners of row jn: publish the entries right of the diagonal
+#pragma unroll
+                for (int cc = 0; cc < 4; ++cc) {
+                    const int c = c0 + cc;
+                    urow[nbuf][c] = c > jn ? a[jj][cc] : 0.0;
+                }
+            }
+            buf = nbuf;
+            __syncthreads();
         }
     }
+
+#pragma unroll
+    for (int cc = 0; cc < 4; ++cc)
+#pragma unroll
+        for (int rr = 0; rr < 4; ++rr) {
+            const int r = r0 + rr, c = c0 + cc;
+            if (r < nb && c < nb && (LU || r >= c)) A[(int64_t)c * op.ld + r] = a[rr][cc];
+        }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -244,11 +316,17 @@ __global__ void __launch_bounds__(64) k_trsm(PlanDev P, const TrsmOp *__restrict
     const int tid = threadIdx.x, nb = op.nb;
     const double *D = P.X + op.t_off;
     const bool trans = (op.flags & T_TRANS) != 0, unit = (op.flags & T_UNIT) != 0;
-    for (int idx = tid; idx < 64 * 64; idx += 64) {
-        const int j = idx >> 6, p = idx & 63;
-        double v = 0.0;
-        if (p < nb && j < nb && p > j) v = trans ? D[j + (int64_t)p * op.ldt] : D[p + (int64_t)j * op.ldt];
-        Ts[idx] = v;
+    {
+        // thread p fetches row p of T: 64 independent loads in flight (a dependent load loop here used to cost more
+        // than the solve itself), then a conflict-free store of Ts[j*64 + p]
+        const int p = tid;
+        double t[64];
+        const double *rowp = trans ? D + (int64_t)p * op.ldt : D + p;
+        const int64_t step = trans ? 1 : op.ldt;
+#pragma unroll
+        for (int j = 0; j < 64; ++j) t[j] = (p < nb && j < p) ? rowp[(int64_t)j * step] : 0.0;
+#pragma unroll
+        for (int j = 0; j < 64; ++j) Ts[j * 64 + p] = t[j];
     }
     rinv[tid] = (tid < nb && !unit) ? 1.0 / D[tid + (int64_t)tid * op.ldt] : 1.0;
     __syncthreads();
