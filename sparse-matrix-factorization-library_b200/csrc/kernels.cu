@@ -274,7 +274,7 @@ __global__ void __launch_bounds__(256) k_diag(PlanDev P, const DiagOp *__restric
             }
             const int nbuf = buf ^ 1;
             if (tid < 64) dsum[nbuf][tid] = fma(-lcol[buf][tid], LU ? urow[buf][tid] : lcol[buf][tid], dsum[buf][tid]);
-            if (tx == jb && active) {            // owners of column jn: scale the entries below the diagonal, publish
+            if (tx == jb) {                      // owners of column jn (all 16, so every row of lcol is rewritten)
 #pragma unroll
                 for (int rr = 0; rr < 4; ++rr) {
                     const int r = r0 + rr;
