@@ -11,6 +11,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <string>
 #include <vector>
 
 #include "plan.hpp"
@@ -129,60 +130,39 @@ int small_front(double *X, const HostPlan &P, i64 s) {
     return 0;
 }
 
-}  // namespace
-
-extern "C" {
-
-/* analyze + plan + interpret.  Lsx_out receives the factor in the reference's layout (xsize doubles).
- * Returns 0, or a negative code if analysis/plan failed, or a positive count of failed pivots. */
-long sfcheck_factorize(int kind, int is_symmetric, long n, const long *Cp, const long *Ci, const double *Cx,
-                       unsigned long long dev_slot, int nb, int outer, int small_a, int small_b, int ld_align,
-                       double *Lsx_out, long *stats /* [nlevels, nlaunches, nsmall, nlarge, relmap, xsize_pad, xsize, -] */,
-                       long out_len) {
-    CscView A;
-    A.n = n; A.colptr = (const i64 *)Cp; A.rowind = (const i64 *)Ci; A.val = Cx; A.symmetric = is_symmetric != 0;
+struct CheckHandle {
     Symbolic S;
-    if (analyze(A, kind ? Kind::LU : Kind::Cholesky, dev_slot, S) != 0) return -1;
-    PlanParams prm;
-    if (nb > 0) prm.nb = nb;
-    if (outer > 0) prm.outer = outer;
-    if (small_a >= 0) prm.small_a_bytes = small_a;
-    if (small_b >= 0) prm.small_b_bytes = small_b;
-    if (ld_align > 0) prm.ld_align = ld_align;
     HostPlan P;
-    const int rc = build_plan(S, prm, P);
-    if (rc != 0) return -10 - rc;
-    if (stats) {
-        stats[0] = P.nlevels; stats[1] = (long)P.launches.size(); stats[2] = P.nsmall; stats[3] = P.nlarge;
-        stats[4] = (long)P.relmap.size(); stats[5] = P.xsize_pad; stats[6] = P.xsize;
-    }
-    if (!Lsx_out || out_len < P.xsize) return 0;     // sizing call
-    std::vector<double> X(P.xsize_pad, 0.0);
-    const bool lu = P.kind == Kind::LU;
-    for (i64 j = 0; j < S.n; ++j)
-        for (i64 p = S.L.ptr[j]; p < S.L.ptr[j + 1]; ++p)
-            if (P.asm_dst_l[p] >= 0) X[P.asm_dst_l[p]] = S.L.val[p];
-    if (lu) {
+};
+
+void assemble(const CheckHandle &h, double *X) {
+    const Symbolic &S = h.S;
+    const HostPlan &P = h.P;
+    for (i64 p = 0; p < P.nnz; ++p)
+        if (P.asm_dst_l[p] >= 0) X[P.asm_dst_l[p]] = S.L.val[p];
+    if (P.kind == Kind::LU) {
         const Tri &U = P.split ? S.U : S.L;
-        for (i64 p = 0; p < P.unnz; ++p) X[P.asm_dst_u[p]] = U.val[p];
+        for (i64 p = 0; p < P.unnz; ++p)
+            if (P.asm_dst_u[p] >= 0) X[P.asm_dst_u[p]] = U.val[p];
     }
+}
+
+long run_launches(const HostPlan &P, double *X, int first, int count) {
     long bad = 0;
-    int last_level = -1;
-    for (const Launch &L : P.launches) {
-        if (L.level < last_level) return -100;          // schedule must be level-monotone
-        last_level = L.level;
+    for (int li = first; li < first + count; ++li) {
+        const Launch &L = P.launches[li];
         switch (L.kind) {
             case L_SMALL_A: case L_SMALL_B:
-                for (int k = 0; k < L.count; ++k) bad += small_front(X.data(), P, P.small_tasks[L.first + k]);
+                for (int k = 0; k < L.count; ++k) bad += small_front(X, P, P.small_tasks[L.first + k]);
                 break;
             case L_POTRF:
-                for (int k = 0; k < L.count; ++k) { const DiagOp &d = P.diag_ops[L.first + k]; bad += diag_cholesky(X.data() + d.a_off, d.ld, d.nb); }
+                for (int k = 0; k < L.count; ++k) { const DiagOp &d = P.diag_ops[L.first + k]; bad += diag_cholesky(X + d.a_off, d.ld, d.nb); }
                 break;
             case L_GETRF:
-                for (int k = 0; k < L.count; ++k) { const DiagOp &d = P.diag_ops[L.first + k]; bad += diag_lu(X.data() + d.a_off, d.ld, d.nb); }
+                for (int k = 0; k < L.count; ++k) { const DiagOp &d = P.diag_ops[L.first + k]; bad += diag_lu(X + d.a_off, d.ld, d.nb); }
                 break;
             case L_TRSM:
-                for (int k = 0; k < L.count; ++k) trsm(X.data(), P.trsm_ops[L.first + k]);
+                for (int k = 0; k < L.count; ++k) trsm(X, P.trsm_ops[L.first + k]);
                 break;
             case L_GEMM128: case L_GEMM64: {
                 // the tile prefix must be consistent with the geometry the kernels decode
@@ -192,7 +172,7 @@ long sfcheck_factorize(int kind, int is_symmetric, long n, const long *Cp, const
                     const GemmOp &g = P.gemm_ops[L.first + k];
                     if (g.tile0 != tiles) return -101;
                     tiles += gemm_tiles(g.M, g.N, B, (g.flags & G_LOWER) != 0);
-                    gemm(X.data(), g, P);
+                    gemm(X, g, P);
                 }
                 if (tiles != L.grid) return -102;
                 break;
@@ -200,9 +180,164 @@ long sfcheck_factorize(int kind, int is_symmetric, long n, const long *Cp, const
             default: return -103;
         }
     }
+    return bad;
+}
+
+void pack(const HostPlan &P, const double *X, double *Lsx_out) {
     for (const PackTask &t : P.pack_tasks)
         for (int c = 0; c < t.cols; ++c)
-            std::memcpy(Lsx_out + t.dst + (i64)c * t.rows, X.data() + t.src + (i64)c * t.ld, sizeof(double) * t.rows);
+            std::memcpy(Lsx_out + t.dst + (i64)c * t.rows, X + t.src + (i64)c * t.ld, sizeof(double) * t.rows);
+}
+
+}  // namespace
+
+extern "C" {
+
+/* ---- handle API: one rank of a `world`-way etree partition (world = 1: the whole factorization) ------------------ */
+void *sfcheck_open(int kind, int is_symmetric, long n, const long *Cp, const long *Ci, const double *Cx,
+                   unsigned long long dev_slot, int nb, int outer, int small_a, int small_b, int ld_align, int rank,
+                   int world) {
+    CscView A;
+    A.n = n; A.colptr = (const i64 *)Cp; A.rowind = (const i64 *)Ci; A.val = Cx; A.symmetric = is_symmetric != 0;
+    auto *h = new CheckHandle();
+    if (analyze(A, kind ? Kind::LU : Kind::Cholesky, dev_slot, h->S) != 0) { delete h; return nullptr; }
+    PlanParams prm;
+    if (nb > 0) prm.nb = nb;
+    if (outer > 0) prm.outer = outer;
+    if (small_a >= 0) prm.small_a_bytes = small_a;
+    if (small_b >= 0) prm.small_b_bytes = small_b;
+    if (ld_align > 0) prm.ld_align = ld_align;
+    if (build_plan(h->S, prm, h->P, rank, world) != 0) { delete h; return nullptr; }
+    return h;
+}
+void sfcheck_close(void *hv) { delete (CheckHandle *)hv; }
+
+long sfcheck_int(void *hv, const char *name) {
+    const HostPlan &P = ((CheckHandle *)hv)->P;
+    const std::string k(name);
+    if (k == "nlevels") return P.nlevels;
+    if (k == "nlaunches") return (long)P.launches.size();
+    if (k == "nsmall") return P.nsmall;
+    if (k == "nlarge") return P.nlarge;
+    if (k == "relmap") return (long)P.relmap.size();
+    if (k == "xsize_pad") return P.xsize_pad;
+    if (k == "xsize") return P.xsize;
+    if (k == "nphases") return (long)P.phases.size();
+    if (k == "nreduces") return (long)P.reduces.size();
+    if (k == "nsuper") return P.nsuper;
+    return -1;
+}
+double sfcheck_double(void *hv, const char *name) {
+    const HostPlan &P = ((CheckHandle *)hv)->P;
+    const std::string k(name);
+    if (k == "flops") return P.flops;
+    if (k == "local_flops") return P.local_flops;
+    return -1;
+}
+/* out = {reduce_first, reduce_count, launch_first, launch_count, level} */
+void sfcheck_phase(void *hv, int k, long *out) {
+    const Phase &ph = ((CheckHandle *)hv)->P.phases[k];
+    out[0] = ph.reduce_first; out[1] = ph.reduce_count; out[2] = ph.launch_first; out[3] = ph.launch_count; out[4] = ph.level;
+}
+/* out = {offset, count, root, lo, hi} */
+void sfcheck_reduce(void *hv, int i, long *out) {
+    const ReduceStep &r = ((CheckHandle *)hv)->P.reduces[i];
+    out[0] = r.offset; out[1] = r.count; out[2] = r.root; out[3] = r.lo; out[4] = r.hi;
+}
+void sfcheck_owner(void *hv, int *owner) {
+    const HostPlan &P = ((CheckHandle *)hv)->P;
+    for (i64 s = 0; s < P.nsuper; ++s) owner[s] = P.owner[s];
+}
+/* X: xsize_pad doubles, zeroed by the caller */
+void sfcheck_begin(void *hv, double *X) { assemble(*(CheckHandle *)hv, X); }
+long sfcheck_run_phase(void *hv, int k, double *X) {
+    const HostPlan &P = ((CheckHandle *)hv)->P;
+    return run_launches(P, X, P.phases[k].launch_first, P.phases[k].launch_count);
+}
+/* copy only the panels this rank owns into Lsx_out (reference layout); others are left untouched */
+void sfcheck_pack_owned(void *hv, const double *X, double *Lsx_out) {
+    const HostPlan &P = ((CheckHandle *)hv)->P;
+    const bool lu = P.kind == Kind::LU;
+    for (i64 s = 0; s < P.nsuper; ++s) {
+        if (P.owner[s] != P.rank) continue;
+        const SnodeDev &d = P.snode[s];
+        const int rows = lu ? 2 * d.nsrow - d.nscol : d.nsrow;
+        for (int c = 0; c < d.nscol; ++c)
+            std::memcpy(Lsx_out + P.lsxp[s] + (i64)c * rows, X + d.xoff + (i64)c * d.ld, sizeof(double) * rows);
+    }
+}
+
+/* analyze + plan + interpret on one rank.  Lsx_out receives the factor in the reference's layout (xsize doubles).
+ * Returns 0, or a negative code if analysis/plan failed, or a positive count of failed pivots. */
+long sfcheck_factorize(int kind, int is_symmetric, long n, const long *Cp, const long *Ci, const double *Cx,
+                       unsigned long long dev_slot, int nb, int outer, int small_a, int small_b, int ld_align,
+                       double *Lsx_out, long *stats /* [nlevels, nlaunches, nsmall, nlarge, relmap, xsize_pad, xsize, -] */,
+                       long out_len) {
+    auto *h = (CheckHandle *)sfcheck_open(kind, is_symmetric, n, Cp, Ci, Cx, dev_slot, nb, outer, small_a, small_b, ld_align, 0, 1);
+    if (!h) return -1;
+    const HostPlan &P = h->P;
+    if (stats) {
+        stats[0] = P.nlevels; stats[1] = (long)P.launches.size(); stats[2] = P.nsmall; stats[3] = P.nlarge;
+        stats[4] = (long)P.relmap.size(); stats[5] = P.xsize_pad; stats[6] = P.xsize;
+    }
+    if (!Lsx_out || out_len < P.xsize) { delete h; return 0; }     // sizing call
+    std::vector<double> X(P.xsize_pad, 0.0);
+    assemble(*h, X.data());
+    int last_level = -1;
+    for (const Launch &L : P.launches) {
+        if (L.level < last_level) { delete h; return -100; }       // schedule must be level-monotone
+        last_level = L.level;
+    }
+    const long bad = run_launches(P, X.data(), 0, (int)P.launches.size());
+    pack(P, X.data(), Lsx_out);
+    delete h;
+    return bad;
+}
+
+/* All `world` ranks simulated in one process: every rank has its own zeroed image of the padded factor, phases run in
+ * lock step, reduce steps sum the images of the contributing ranks into the owner's.  Lsx_out = union of the owned
+ * panels.  balance[r] receives the flops owned by rank r. */
+long sfcheck_factorize_partitioned(int kind, int is_symmetric, long n, const long *Cp, const long *Ci, const double *Cx,
+                                   unsigned long long dev_slot, int nb, int outer, int small_a, int small_b, int world,
+                                   double *Lsx_out, double *balance, long *nreduce_out) {
+    std::vector<CheckHandle *> H(world);
+    for (int r = 0; r < world; ++r) {
+        H[r] = (CheckHandle *)sfcheck_open(kind, is_symmetric, n, Cp, Ci, Cx, dev_slot, nb, outer, small_a, small_b, 0, r, world);
+        if (!H[r]) return -1;
+    }
+    const i64 xp = H[0]->P.xsize_pad;
+    std::vector<std::vector<double>> X(world, std::vector<double>(xp, 0.0));
+    for (int r = 0; r < world; ++r) { assemble(*H[r], X[r].data()); if (balance) balance[r] = H[r]->P.local_flops; }
+    long bad = 0, nred = 0;
+    const size_t nph = H[0]->P.phases.size();
+    for (size_t k = 0; k < nph; ++k) {
+        // collectives first: every contributing rank must list the same step
+        for (int r = 0; r < world; ++r) {
+            const Phase &ph = H[r]->P.phases[k];
+            for (int i = ph.reduce_first; i < ph.reduce_first + ph.reduce_count; ++i) {
+                const ReduceStep &st = H[r]->P.reduces[i];
+                if (st.root != r) continue;                       // the owner drives the sum
+                for (int q = st.lo; q < st.hi; ++q) {
+                    if (q == r) continue;
+                    bool listed = false;
+                    const Phase &pq = H[q]->P.phases[k];
+                    for (int j = pq.reduce_first; j < pq.reduce_first + pq.reduce_count; ++j)
+                        if (H[q]->P.reduces[j].offset == st.offset && H[q]->P.reduces[j].count == st.count) listed = true;
+                    if (!listed) return -200;
+                    for (i64 e = 0; e < st.count; ++e) X[r][st.offset + e] += X[q][st.offset + e];
+                }
+                ++nred;
+            }
+        }
+        for (int r = 0; r < world; ++r) {
+            const long b = run_launches(H[r]->P, X[r].data(), H[r]->P.phases[k].launch_first, H[r]->P.phases[k].launch_count);
+            if (b < 0) return b;
+            bad += b;
+        }
+    }
+    for (int r = 0; r < world; ++r) sfcheck_pack_owned(H[r], X[r].data(), Lsx_out);
+    if (nreduce_out) *nreduce_out = nred;
+    for (auto *h : H) delete h;
     return bad;
 }
 

@@ -13,6 +13,7 @@
 #include "kernels.cuh"
 
 #include <cstdio>
+#include <cstdlib>
 
 namespace sfb200 {
 
@@ -24,6 +25,10 @@ namespace {
 __device__ __forceinline__ void cp_async8(void *smem_dst, const void *gsrc, int src_bytes) {
     const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(d), "l"(gsrc), "r"(src_bytes));
+}
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc, int src_bytes) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(d), "l"(gsrc), "r"(src_bytes));
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 template <int N>
@@ -428,18 +433,43 @@ __global__ void __launch_bounds__(WARPS_M *WARPS_N * 32)
     const int mrem = M - row0, nrem = N - col0;
     const bool b_kmajor = (op.flags & G_B_KMAJOR) != 0;
 
+    // 16-byte copies whenever the operand's columns start on even element offsets (always true for the in-place
+    // trailing updates; true for a scatter op when the front has an even number of columns)
+    const bool a_vec = (((op.a_off | (int64_t)op.lda) & 1) == 0);
+    const bool b_vec = !b_kmajor && (((op.b_off | (int64_t)op.ldb) & 1) == 0);
+
     auto load_stage = [&](int stage, int kt) {
         double *As = smem + stage * Cfg::STAGE_DOUBLES;
         double *Bs = As + GEMM_BK * SA;
         const int k0 = kt * GEMM_BK;
+        if (a_vec) {
 #pragma unroll
-        for (int e = tid; e < GEMM_BK * BM; e += NT) {
-            const int k = e / BM, r = e - k * BM;
-            const bool ok = (r < mrem) && (k0 + k < K);
-            const double *src = ok ? Ag + r + (int64_t)(k0 + k) * op.lda : Ag;
-            cp_async8(As + k * SA + r, src, ok ? 8 : 0);
+            for (int e = tid; e < GEMM_BK * BM / 2; e += NT) {
+                const int k = e / (BM / 2), r = 2 * (e - k * (BM / 2));
+                const int rem = (k0 + k < K) ? mrem - r : 0;
+                const int bytes = rem >= 2 ? 16 : (rem == 1 ? 8 : 0);
+                const double *src = bytes ? Ag + r + (int64_t)(k0 + k) * op.lda : Ag;
+                cp_async16(As + k * SA + r, src, bytes);
+            }
+        } else {
+#pragma unroll
+            for (int e = tid; e < GEMM_BK * BM; e += NT) {
+                const int k = e / BM, r = e - k * BM;
+                const bool ok = (r < mrem) && (k0 + k < K);
+                const double *src = ok ? Ag + r + (int64_t)(k0 + k) * op.lda : Ag;
+                cp_async8(As + k * SA + r, src, ok ? 8 : 0);
+            }
         }
-        if (!b_kmajor) {
+        if (b_vec) {
+#pragma unroll
+            for (int e = tid; e < GEMM_BK * BN / 2; e += NT) {
+                const int k = e / (BN / 2), r = 2 * (e - k * (BN / 2));
+                const int rem = (k0 + k < K) ? nrem - r : 0;
+                const int bytes = rem >= 2 ? 16 : (rem == 1 ? 8 : 0);
+                const double *src = bytes ? Bg + r + (int64_t)(k0 + k) * op.ldb : Bg;
+                cp_async16(Bs + k * SB + r, src, bytes);
+            }
+        } else if (!b_kmajor) {
 #pragma unroll
             for (int e = tid; e < GEMM_BK * BN; e += NT) {
                 const int k = e / BN, r = e - k * BN;
@@ -519,23 +549,45 @@ __global__ void __launch_bounds__(WARPS_M *WARPS_N * 32)
     } else {
         double *Cg = P.X + op.c_off;
         const bool lower = (op.flags & G_LOWER) != 0;
+        // rows r are even; with even c_off and ldc every (r, r+1) pair is one aligned 16-byte word of the column
+        const bool vec = (((op.c_off | (int64_t)op.ldc) & 1) == 0);
 #pragma unroll
         for (int j = 0; j < FN; ++j) {
             const int c = col0 + wn0 + 8 * j + g;
             if (c >= N) continue;
             double *colp = Cg + (int64_t)c * op.ldc;
             const int lim = lower ? c : 0;
+            // all loads of the column first (independent, all in flight), then the stores: a load/modify/store chain
+            // per element would expose one global-memory round trip per element
+            double2 cv[FM];
 #pragma unroll
             for (int i = 0; i < FM; ++i) {
                 const int r = row0 + wm0 + 8 * i + 2 * t4;
-                if (r < M && r >= lim) colp[r] -= acc[i][j][0];
-                if (r + 1 < M && r + 1 >= lim) colp[r + 1] -= acc[i][j][1];
+                cv[i] = make_double2(0.0, 0.0);
+                if (r + 1 < M && r + 1 >= lim) {
+                    if (vec) cv[i] = *reinterpret_cast<const double2 *>(colp + r);
+                    else { cv[i].x = colp[r]; cv[i].y = colp[r + 1]; }
+                } else if (r < M && r >= lim) {
+                    cv[i].x = colp[r];
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < FM; ++i) {
+                const int r = row0 + wm0 + 8 * i + 2 * t4;
+                const bool w0 = r < M && r >= lim, w1 = r + 1 < M && r + 1 >= lim;
+                const double v0 = cv[i].x - acc[i][j][0], v1 = cv[i].y - acc[i][j][1];
+                if (w0 && w1 && vec) *reinterpret_cast<double2 *>(colp + r) = make_double2(v0, v1);
+                else {
+                    if (w0) colp[r] = v0;
+                    if (w1) colp[r + 1] = v1;
+                }
             }
         }
     }
 }
 
 using Gemm128 = GemmCfg<128, 128, 2, 4, 3>;
+using Gemm128w16 = GemmCfg<128, 128, 4, 4, 3>;
 using Gemm64 = GemmCfg<64, 64, 2, 2, 4>;
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -597,6 +649,8 @@ cudaError_t kernels_init() {
     cudaError_t e;
     e = cudaFuncSetAttribute(k_gemm<128, 128, 2, 4, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, Gemm128::SMEM_BYTES);
     if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_gemm<128, 128, 4, 4, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, Gemm128w16::SMEM_BYTES);
+    if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(k_gemm<64, 64, 2, 2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, Gemm64::SMEM_BYTES);
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(k_small<256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
@@ -636,7 +690,9 @@ void launch_trsm(const PlanDev &P, const TrsmOp *ops, int count, int grid, cudaS
 
 void launch_gemm(const PlanDev &P, const GemmOp *ops, int count, int grid, bool tile128, cudaStream_t st) {
     if (count <= 0 || grid <= 0) return;
-    if (tile128) k_gemm<128, 128, 2, 4, 3><<<grid, Gemm128::NT, Gemm128::SMEM_BYTES, st>>>(P, ops, count);
+    static const bool w16 = getenv("SFB200_GEMM_WARPS") && atoi(getenv("SFB200_GEMM_WARPS")) == 16;
+    if (tile128 && w16) k_gemm<128, 128, 4, 4, 3><<<grid, Gemm128w16::NT, Gemm128w16::SMEM_BYTES, st>>>(P, ops, count);
+    else if (tile128) k_gemm<128, 128, 2, 4, 3><<<grid, Gemm128::NT, Gemm128::SMEM_BYTES, st>>>(P, ops, count);
     else k_gemm<64, 64, 2, 2, 4><<<grid, Gemm64::NT, Gemm64::SMEM_BYTES, st>>>(P, ops, count);
 }
 

@@ -127,8 +127,11 @@ void emit_lu_panel(const SnodeDev &sn, const PlanParams &prm, std::map<int, Slot
 
 }  // namespace
 
-int build_plan(const Symbolic &S, const PlanParams &prm, HostPlan &P) {
+int build_plan(const Symbolic &S, const PlanParams &prm, HostPlan &P, int rank, int world) {
     P = HostPlan();
+    if (world < 1 || rank < 0 || rank >= world) return 1;
+    P.rank = rank;
+    P.world = world;
     P.prm = prm;
     P.kind = S.kind;
     const bool lu = S.kind == Kind::LU;
@@ -171,6 +174,66 @@ int build_plan(const Symbolic &S, const PlanParams &prm, HostPlan &P) {
         maxlev = std::max(maxlev, (int)P.snode[s].level);
     }
     P.nlevels = ns > 0 ? maxlev + 1 : 0;
+
+    // ---- ownership: proportional mapping of the supernodal etree onto `world` ranks -----------------------------------
+    // Every supernode starts with the rank range of its parent; the children of a node share the node's range in
+    // proportion to their subtree work (largest first).  A node whose range has collapsed to one rank roots a local
+    // subtree; nodes with a wider range ("shared") are owned by the first rank of the range and receive partial updates
+    // from every rank in it.
+    P.owner.assign(ns, 0);
+    P.group_lo.assign(ns, 0);
+    P.group_hi.assign(ns, 1);
+    if (world > 1) {
+        std::vector<double> work(ns), subtree(ns);
+        for (i64 s = 0; s < ns; ++s) {
+            const double c = P.snode[s].nscol, m = P.snode[s].nsrow - P.snode[s].nscol;
+            work[s] = lu ? 2.0 * c * c * c / 3.0 + 2.0 * m * c * c + 2.0 * m * m * c : c * c * c / 3.0 + m * c * c + m * (m + 1.0) * c;
+            subtree[s] = work[s];
+        }
+        std::vector<std::vector<i64>> kids(ns);
+        std::vector<i64> roots;
+        for (i64 s = 0; s < ns; ++s) {
+            if (sparent[s] >= 0) { subtree[sparent[s]] += subtree[s]; kids[sparent[s]].push_back(s); }   // children precede parents
+            else roots.push_back(s);
+        }
+        auto split = [&](std::vector<i64> &nodes, int lo, int hi) {
+            // hand the ranks [lo,hi) to `nodes` in proportion to subtree work, each node a contiguous non-empty range
+            std::sort(nodes.begin(), nodes.end(), [&](i64 a, i64 b) { return subtree[a] != subtree[b] ? subtree[a] > subtree[b] : a < b; });
+            double total = 0;
+            for (i64 c : nodes) total += subtree[c];
+            const int g = hi - lo;
+            double before = 0;
+            for (i64 c : nodes) {
+                int a = lo + (int)(g * (total > 0 ? before / total : 0.0));
+                int b = lo + (int)(g * (total > 0 ? (before + subtree[c]) / total : 0.0) + 1e-9);
+                a = std::min(a, hi - 1);
+                b = std::max(std::min(b, hi), a + 1);
+                P.group_lo[c] = a;
+                P.group_hi[c] = b;
+                before += subtree[c];
+            }
+        };
+        split(roots, 0, world);
+        for (i64 s = ns - 1; s >= 0; --s) {      // parents before children
+            if (P.group_hi[s] - P.group_lo[s] > 1 && !kids[s].empty()) split(kids[s], P.group_lo[s], P.group_hi[s]);
+            else for (i64 c : kids[s]) { P.group_lo[c] = P.group_lo[s]; P.group_hi[c] = P.group_lo[s] + 1; }
+            if (P.group_hi[s] - P.group_lo[s] > 1 && kids[s].empty()) P.group_hi[s] = P.group_lo[s] + 1;
+            P.owner[s] = P.group_lo[s];
+        }
+        // a shared node only needs the ranks that really own something below it (or the node itself)
+        std::vector<int32_t> lo_used(ns), hi_used(ns);
+        for (i64 s = 0; s < ns; ++s) { lo_used[s] = P.owner[s]; hi_used[s] = P.owner[s] + 1; }
+        for (i64 s = 0; s < ns; ++s)
+            if (sparent[s] >= 0) {
+                lo_used[sparent[s]] = std::min(lo_used[sparent[s]], lo_used[s]);
+                hi_used[sparent[s]] = std::max(hi_used[sparent[s]], hi_used[s]);
+            }
+        for (i64 s = 0; s < ns; ++s) { P.group_lo[s] = lo_used[s]; P.group_hi[s] = hi_used[s]; P.owner[s] = std::min<int32_t>(P.owner[s], hi_used[s] - 1); }
+        for (i64 s = 0; s < ns; ++s) if (P.owner[s] == rank) P.local_flops += work[s];
+    } else {
+        P.local_flops = P.flops;
+    }
+    auto mine = [&](i64 s) { return P.owner[s] == rank; };
 
     // ---- ancestor segments and relative-index tables -----------------------------------------------------------
     struct Seg { i64 d; int32_t b, e; i64 rel_off; };
@@ -228,6 +291,11 @@ int build_plan(const Symbolic &S, const PlanParams &prm, HostPlan &P) {
         }
         for (i64 j = S.Super[t]; j < S.Super[t + 1]; ++j) {
             const i64 cj = j - S.Super[t];
+            if (!mine(t)) {       // another rank assembles this panel: here it only collects partial updates
+                for (i64 p = S.L.ptr[j]; p < S.L.ptr[j + 1]; ++p) P.asm_dst_l[p] = -1;
+                if (lu) for (i64 p = Usrc.ptr[j]; p < Usrc.ptr[j + 1]; ++p) P.asm_dst_u[p] = -1;
+                continue;
+            }
             for (i64 p = S.L.ptr[j]; p < S.L.ptr[j + 1]; ++p) {
                 const i64 i = S.L.idx[p];
                 if (pos[i] < 0) return 4;
@@ -261,8 +329,15 @@ int build_plan(const Symbolic &S, const PlanParams &prm, HostPlan &P) {
         std::vector<i64> cls[4];
         std::map<int, SlotOps> slots;
         std::vector<GemmOp> scatter;
+        Phase ph{};
+        ph.level = lev;
+        ph.reduce_first = (int32_t)P.reduces.size();
+        ph.launch_first = (int32_t)P.launches.size();
         for (i64 s : by_level[lev]) {
             const SnodeDev &d = P.snode[s];
+            if (P.group_hi[s] - P.group_lo[s] > 1 && rank >= P.group_lo[s] && rank < P.group_hi[s])
+                P.reduces.push_back(ReduceStep{d.xoff, (i64)d.ld * d.nscol, P.owner[s], P.group_lo[s], P.group_hi[s]});
+            if (!mine(s)) continue;
             const i64 pb = panel_bytes(d);
             int c = -1;
             if (d.nsrow - d.nscol <= prm.small_max_m)
@@ -348,6 +423,9 @@ int build_plan(const Symbolic &S, const PlanParams &prm, HostPlan &P) {
             if (!so.gemm.empty()) emit_gemm(so.gemm);
         }
         if (!scatter.empty()) emit_gemm(scatter);
+        ph.reduce_count = (int32_t)P.reduces.size() - ph.reduce_first;
+        ph.launch_count = (int32_t)P.launches.size() - ph.launch_first;
+        P.phases.push_back(ph);
     }
 
     // ---- copy-out tasks ------------------------------------------------------------------------------------------

@@ -46,9 +46,18 @@ struct HostPlan {
     std::vector<PackTask> pack_tasks;
 
     double flops = 0.0;                     // algorithmic flops
+
+    // ---- etree partition over `world` GPUs (proportional mapping of subtrees) -------------------------
+    int rank = 0, world = 1;
+    std::vector<int32_t> owner;             // owning rank of every supernode
+    std::vector<int32_t> group_lo, group_hi;// ranks [lo,hi) that hold descendants of the supernode (hi-lo > 1: "shared")
+    double local_flops = 0.0;               // flops of the supernodes this rank owns
+    std::vector<ReduceStep> reduces;        // sums of partial panel images into the owner, grouped by phase
+    std::vector<Phase> phases;              // one per etree level: reduce steps first, then the level's launches
 };
 
-int build_plan(const Symbolic &S, const PlanParams &prm, HostPlan &P);
+// world == 1: every supernode is owned by rank 0, no reduce steps.
+int build_plan(const Symbolic &S, const PlanParams &prm, HostPlan &P, int rank = 0, int world = 1);
 
 // tile geometry shared by builder, kernels and the CPU interpreter
 inline i64 gemm_tiles(int M, int N, int B, bool lower) {

@@ -86,6 +86,22 @@ struct Launch {
     int32_t smem;    // dynamic shared memory bytes
 };
 
+// ---- multi-GPU: one etree level = one phase; before its launches, the partial images of the level's shared panels
+// (panels whose descendants live on several ranks) are summed into the owner ------------------------------------------
+struct ReduceStep {
+    int64_t offset;  // element offset of the panel in the padded factor
+    int64_t count;   // elements
+    int32_t root;    // owner rank (= lo)
+    int32_t lo, hi;  // contributing ranks [lo, hi)
+};
+
+struct Phase {
+    int32_t level;
+    int32_t reduce_first, reduce_count;
+    int32_t launch_first, launch_count;
+    int32_t pad;
+};
+
 // ---- final copy into the reference's unpadded layout -------------------------------------------------------
 struct PackTask {
     int64_t src;     // padded offset
