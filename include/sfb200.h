@@ -78,6 +78,24 @@ void sfb200_symbolic_free(sfb200_symbolic *s);
 int sfb200_device_count(void);
 
 int sfb200_plan_create(const sfb200_symbolic *s, int device, sfb200_plan **out);
+
+/* One rank of an etree-subtree partition over `world` GPUs (one process per GPU).  Whole subtrees are local to a rank;
+ * the supernodes above them ("top") are owned by single ranks and receive partial updates from several: every rank keeps
+ * a full-size zero-initialised image of the factor, accumulates its updates there, and before level L is factorized
+ * the images of level L's shared panels are summed into their owners.  The sums are the caller's job (NCCL reduce
+ * through torch.distributed in sparseframe_b200/parallel.py): the plan only lists them.
+ *   sfb200_plan_int: "nphases", "nreduces", "rank", "world";  sfb200_plan_double: "flops", "local_flops"
+ *   phase k  = etree level k: first its reduce steps [reduce_first, +reduce_count), then its launches
+ *   reduce i = {offset, count (elements of the padded factor), root, lo, hi}: ranks in [lo,hi) take part, root receives;
+ *              the list is identical on every rank. */
+int sfb200_plan_create_part(const sfb200_symbolic *s, int device, int rank, int world, sfb200_plan **out);
+double sfb200_plan_double(const sfb200_plan *p, const char *name);
+int sfb200_plan_phase_info(const sfb200_plan *p, int k, int64_t out[5]);
+int sfb200_plan_reduce_info(const sfb200_plan *p, int i, int64_t out[5]);
+int sfb200_plan_owner(const sfb200_plan *p, int32_t *owner /* nsuper */);
+void *sfb200_plan_factor_ptr(sfb200_plan *p);                 /* device pointer of the padded factor image */
+int sfb200_phase_begin(sfb200_plan *p, const double *d_Lx, const double *d_Ux);   /* zero + assemble owned panels */
+int sfb200_phase_run(sfb200_plan *p, int k);                  /* launches of phase k, asynchronous */
 void sfb200_plan_free(sfb200_plan *p);
 
 /* Scalars: "nlevels","nlaunches","nsmall","nlarge","relmap_entries","xsize_padded","device_bytes", ... */

@@ -203,7 +203,8 @@ void *sfcheck_open(int kind, int is_symmetric, long n, const long *Cp, const lon
     if (analyze(A, kind ? Kind::LU : Kind::Cholesky, dev_slot, h->S) != 0) { delete h; return nullptr; }
     PlanParams prm;
     if (nb > 0) prm.nb = nb;
-    if (outer > 0) prm.outer = outer;
+    if (outer > 0) prm.outer = outer % 100000;
+    if (outer >= 100000) prm.outer2 = outer / 100000;     // test hook: outer = outer2 * 100000 + outer
     if (small_a >= 0) prm.small_a_bytes = small_a;
     if (small_b >= 0) prm.small_b_bytes = small_b;
     if (ld_align > 0) prm.ld_align = ld_align;
@@ -319,13 +320,15 @@ long sfcheck_factorize_partitioned(int kind, int is_symmetric, long n, const lon
                 if (st.root != r) continue;                       // the owner drives the sum
                 for (int q = st.lo; q < st.hi; ++q) {
                     if (q == r) continue;
-                    bool listed = false;
-                    const Phase &pq = H[q]->P.phases[k];
-                    for (int j = pq.reduce_first; j < pq.reduce_first + pq.reduce_count; ++j)
-                        if (H[q]->P.reduces[j].offset == st.offset && H[q]->P.reduces[j].count == st.count) listed = true;
-                    if (!listed) return -200;
+                    // every rank must hold the identical step at the identical position (collectives are matched by order)
+                    const ReduceStep &sq = H[q]->P.reduces[i];
+                    if (sq.offset != st.offset || sq.count != st.count || sq.root != st.root || sq.lo != st.lo || sq.hi != st.hi) return -200;
                     for (i64 e = 0; e < st.count; ++e) X[r][st.offset + e] += X[q][st.offset + e];
                 }
+                // ranks outside [lo,hi) must not have touched the panel
+                for (int q = 0; q < world; ++q)
+                    if (q < st.lo || q >= st.hi)
+                        for (i64 e = 0; e < st.count; ++e) if (X[q][st.offset + e] != 0.0) return -201;
                 ++nred;
             }
         }

@@ -114,3 +114,82 @@ def plan_check(kind, A_n, Cp, Ci, Cx, symmetric, devslot, nb=0, outer=0, small_a
                                 Cx.ctypes.data, int(devslot), nb, outer, small_a, small_b, ld_align, out.ctypes.data,
                                 stats.ctypes.data, out.size)
     return out, int(rc), stats
+
+
+class CheckBackend:
+    """One rank of a `world`-way etree partition executed by the CPU plan interpreter (oracle/plan_host_exec.cpp).
+    Same backend protocol as sparseframe_b200.parallel.DeviceBackend, so that the multi-rank orchestration can be
+    tested with gloo on a box without GPUs."""
+
+    def __init__(self, kind, A, devslot, rank, world, nb=0, outer=0, small_a=-1, small_b=-1):
+        import torch
+        global _chk
+        if _chk is None:
+            _chk = C.CDLL(os.path.join(_HERE, "_ref", "libsfcheck.so"))
+        L = _chk
+        L.sfcheck_open.restype = C.c_void_p
+        L.sfcheck_open.argtypes = [C.c_int, C.c_int, C.c_long, C.c_void_p, C.c_void_p, C.c_void_p, C.c_ulonglong] + [C.c_int] * 7
+        L.sfcheck_int.restype = C.c_long
+        L.sfcheck_int.argtypes = [C.c_void_p, C.c_char_p]
+        L.sfcheck_double.restype = C.c_double
+        L.sfcheck_double.argtypes = [C.c_void_p, C.c_char_p]
+        for f in ("sfcheck_phase", "sfcheck_reduce"):
+            getattr(L, f).argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        L.sfcheck_owner.argtypes = [C.c_void_p, C.c_void_p]
+        L.sfcheck_begin.argtypes = [C.c_void_p, C.c_void_p]
+        L.sfcheck_run_phase.restype = C.c_long
+        L.sfcheck_run_phase.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        L.sfcheck_pack_owned.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.sfcheck_close.argtypes = [C.c_void_p]
+        self.L = L
+        self.A = A
+        self.h = L.sfcheck_open(int(kind in (1, "lu")), int(A.symmetric), A.n, A.Cp.ctypes.data, A.Ci.ctypes.data,
+                                A.Cx.ctypes.data, int(devslot), nb, outer, small_a, small_b, 0, rank, world)
+        if not self.h:
+            raise RuntimeError("sfcheck_open failed")
+        self.rank, self.world = rank, world
+        self.nphases = self.int("nphases")
+        self.X = np.zeros(self.int("xsize_pad"))
+        self.image = torch.from_numpy(self.X)          # shares memory with X
+        self.bad = 0
+
+        def info(fn, k):
+            out = np.zeros(5, dtype=np.int64)
+            fn(self.h, k, out.ctypes.data)
+            return [int(v) for v in out]
+        self.phases = [dict(zip(("reduce_first", "reduce_count", "launch_first", "launch_count", "level"),
+                                info(L.sfcheck_phase, k))) for k in range(self.nphases)]
+        self.reduces = [dict(zip(("offset", "count", "root", "lo", "hi"), info(L.sfcheck_reduce, i)))
+                        for i in range(self.int("nreduces"))]
+
+    def int(self, name):
+        return int(self.L.sfcheck_int(self.h, name.encode()))
+
+    def double(self, name):
+        return float(self.L.sfcheck_double(self.h, name.encode()))
+
+    def owner(self):
+        out = np.zeros(self.int("nsuper"), dtype=np.int32)
+        self.L.sfcheck_owner(self.h, out.ctypes.data)
+        return out
+
+    def begin(self):
+        self.X[:] = 0.0
+        self.bad = 0
+        self.L.sfcheck_begin(self.h, self.X.ctypes.data)
+
+    def run_phase(self, k):
+        self.bad += self.L.sfcheck_run_phase(self.h, k, self.X.ctypes.data)
+
+    def finish(self):
+        pass
+
+    def pack_owned(self):
+        out = np.zeros(self.int("xsize"))
+        self.L.sfcheck_pack_owned(self.h, self.X.ctypes.data, out.ctypes.data)
+        return out
+
+    def close(self):
+        if self.h:
+            self.L.sfcheck_close(self.h)
+            self.h = None

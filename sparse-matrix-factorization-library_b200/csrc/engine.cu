@@ -64,33 +64,51 @@ int upload(sfb200_plan *p, T *&dptr, const std::vector<T> &h) {
     return SFB200_OK;
 }
 
-int run_schedule(sfb200_plan *p) {
+int issue_launch(sfb200_plan *p, const Launch &L) {
+    cudaStream_t st = p->stream;
+    switch (L.kind) {
+        case L_SMALL_A: launch_small(p->D, p->d_small + L.first, L.count, L.smem, false, st); break;
+        case L_SMALL_B: launch_small(p->D, p->d_small + L.first, L.count, L.smem, true, st); break;
+        case L_POTRF:
+        case L_GETRF: launch_diag(p->D, p->d_diag + L.first, L.count, st); break;
+        case L_TRSM: launch_trsm(p->D, p->d_trsm + L.first, L.count, L.grid, st); break;
+        case L_GEMM128: launch_gemm(p->D, p->d_gemm + L.first, L.count, L.grid, true, st); break;
+        case L_GEMM64: launch_gemm(p->D, p->d_gemm + L.first, L.count, L.grid, false, st); break;
+        default: set_error("corrupt plan: unknown launch kind"); return SFB200_ERR_STATE;
+    }
+    return SFB200_OK;
+}
+
+// zero the factor, scatter the matrix values of the panels this rank owns
+int begin_factor(sfb200_plan *p) {
     const HostPlan &H = p->H;
     cudaStream_t st = p->stream;
     CK(cudaMemsetAsync(p->d_status, 0, sizeof(int), st));
     CK(cudaMemsetAsync(p->d_X, 0, sizeof(double) * (size_t)H.xsize_pad, st));
     launch_assemble(p->d_lx, p->d_asm_l, H.nnz, p->d_X, st);
-    int64_t nl = 2;
+    p->launches = 2;
     if (H.kind == Kind::LU) {
         launch_assemble(H.split ? p->d_ux : p->d_lx, p->d_asm_u, H.unnz, p->d_X, st);
-        ++nl;
+        ++p->launches;
     }
-    for (const Launch &L : H.launches) {
-        switch (L.kind) {
-            case L_SMALL_A: launch_small(p->D, p->d_small + L.first, L.count, L.smem, false, st); break;
-            case L_SMALL_B: launch_small(p->D, p->d_small + L.first, L.count, L.smem, true, st); break;
-            case L_POTRF:
-            case L_GETRF: launch_diag(p->D, p->d_diag + L.first, L.count, st); break;
-            case L_TRSM: launch_trsm(p->D, p->d_trsm + L.first, L.count, L.grid, st); break;
-            case L_GEMM128: launch_gemm(p->D, p->d_gemm + L.first, L.count, L.grid, true, st); break;
-            case L_GEMM64: launch_gemm(p->D, p->d_gemm + L.first, L.count, L.grid, false, st); break;
-            default: set_error("corrupt plan: unknown launch kind"); return SFB200_ERR_STATE;
-        }
-        ++nl;
+    return SFB200_OK;
+}
+
+int run_launches(sfb200_plan *p, size_t first, size_t count) {
+    const HostPlan &H = p->H;
+    for (size_t i = first; i < first + count; ++i) {
+        const int rc = issue_launch(p, H.launches[i]);
+        if (rc) return rc;
+        ++p->launches;
     }
-    p->launches = nl;
     CK(cudaGetLastError());
     return SFB200_OK;
+}
+
+int run_schedule(sfb200_plan *p) {
+    const int rc = begin_factor(p);
+    if (rc) return rc;
+    return run_launches(p, 0, p->H.launches.size());
 }
 
 int check_status(sfb200_plan *p) {
@@ -127,7 +145,11 @@ void sfb200_plan_free(sfb200_plan *p) {
 }
 
 int sfb200_plan_create(const sfb200_symbolic *s, int device, sfb200_plan **out) {
-    if (!s || !out) { set_error("sfb200_plan_create: bad argument"); return SFB200_ERR_ARG; }
+    return sfb200_plan_create_part(s, device, 0, 1, out);
+}
+
+int sfb200_plan_create_part(const sfb200_symbolic *s, int device, int rank, int world, sfb200_plan **out) {
+    if (!s || !out || world < 1 || rank < 0 || rank >= world) { set_error("sfb200_plan_create: bad argument"); return SFB200_ERR_ARG; }
     if (sfb200_device_count() <= device || device < 0) {
         set_error("sfb200_plan_create: no usable CUDA device (this engine has no CPU fallback)");
         return SFB200_ERR_NO_DEVICE;
@@ -137,10 +159,11 @@ int sfb200_plan_create(const sfb200_symbolic *s, int device, sfb200_plan **out) 
     PlanParams prm;
     if (const char *e = getenv("SFB200_NB")) prm.nb = atoi(e);
     if (const char *e = getenv("SFB200_OUTER")) prm.outer = atoi(e);
+    if (const char *e = getenv("SFB200_OUTER2")) prm.outer2 = atoi(e);
     if (const char *e = getenv("SFB200_SMALL_A")) prm.small_a_bytes = atoi(e);
     if (const char *e = getenv("SFB200_SMALL_B")) prm.small_b_bytes = atoi(e);
     if (const char *e = getenv("SFB200_GEMM128_MIN")) prm.gemm128_min_m = atoi(e);
-    const int rc = build_plan(s->S, prm, p->H);
+    const int rc = build_plan(s->S, prm, p->H, rank, world);
     if (rc != 0) {
         delete p;
         set_error("sfb200_plan_create: structure is not a valid supernodal structure (code " + std::to_string(rc) + ")");
@@ -214,7 +237,68 @@ int64_t sfb200_plan_int(const sfb200_plan *p, const char *name) {
     if (k == "trsm_ops") return (int64_t)H.trsm_ops.size();
     if (k == "diag_ops") return (int64_t)H.diag_ops.size();
     if (k == "device") return p->device;
+    if (k == "nphases") return (int64_t)H.phases.size();
+    if (k == "nreduces") return (int64_t)H.reduces.size();
+    if (k == "rank") return H.rank;
+    if (k == "world") return H.world;
+    if (k == "nsuper") return H.nsuper;
     return -1;
+}
+
+double sfb200_plan_double(const sfb200_plan *p, const char *name) {
+    if (!p || !name) return -1.0;
+    const std::string k(name);
+    if (k == "flops") return p->H.flops;
+    if (k == "local_flops") return p->H.local_flops;
+    return -1.0;
+}
+
+int sfb200_plan_phase_info(const sfb200_plan *p, int k, int64_t *out) {
+    if (!p || !out || k < 0 || k >= (int)p->H.phases.size()) return SFB200_ERR_ARG;
+    const Phase &ph = p->H.phases[k];
+    out[0] = ph.reduce_first; out[1] = ph.reduce_count; out[2] = ph.launch_first; out[3] = ph.launch_count; out[4] = ph.level;
+    return SFB200_OK;
+}
+
+int sfb200_plan_reduce_info(const sfb200_plan *p, int i, int64_t *out) {
+    if (!p || !out || i < 0 || i >= (int)p->H.reduces.size()) return SFB200_ERR_ARG;
+    const ReduceStep &r = p->H.reduces[i];
+    out[0] = r.offset; out[1] = r.count; out[2] = r.root; out[3] = r.lo; out[4] = r.hi;
+    return SFB200_OK;
+}
+
+int sfb200_plan_owner(const sfb200_plan *p, int32_t *owner) {
+    if (!p || !owner) return SFB200_ERR_ARG;
+    for (i64 s = 0; s < p->H.nsuper; ++s) owner[s] = p->H.owner[s];
+    return SFB200_OK;
+}
+
+void *sfb200_plan_factor_ptr(sfb200_plan *p) { return p ? (void *)p->d_X : nullptr; }
+
+int sfb200_phase_begin(sfb200_plan *p, const double *d_Lx, const double *d_Ux) {
+    if (!p || !d_Lx) { set_error("sfb200_phase_begin: bad argument"); return SFB200_ERR_ARG; }
+    CK(cudaSetDevice(p->device));
+    const HostPlan &H = p->H;
+    CK(cudaEventRecord(p->ev[0], p->stream));
+    if (d_Lx != p->d_lx) CK(cudaMemcpyAsync(p->d_lx, d_Lx, sizeof(double) * (size_t)H.nnz, cudaMemcpyDeviceToDevice, p->stream));
+    if (H.split) {
+        if (!d_Ux) { set_error("unsymmetric LU needs Ux"); return SFB200_ERR_ARG; }
+        if (d_Ux != p->d_ux) CK(cudaMemcpyAsync(p->d_ux, d_Ux, sizeof(double) * (size_t)H.unnz, cudaMemcpyDeviceToDevice, p->stream));
+    }
+    return begin_factor(p);
+}
+
+int sfb200_phase_run(sfb200_plan *p, int k) {
+    if (!p || k < 0 || k >= (int)p->H.phases.size()) { set_error("sfb200_phase_run: bad phase"); return SFB200_ERR_ARG; }
+    CK(cudaSetDevice(p->device));
+    const Phase &ph = p->H.phases[k];
+    const int rc = run_launches(p, (size_t)ph.launch_first, (size_t)ph.launch_count);
+    if (rc) return rc;
+    if (k + 1 == (int)p->H.phases.size()) {
+        CK(cudaEventRecord(p->ev[1], p->stream));
+        p->factored = true;
+    }
+    return SFB200_OK;
 }
 
 int sfb200_factorize_device(sfb200_plan *p, const double *d_Lx, const double *d_Ux) {
@@ -310,15 +394,7 @@ int sfb200_plan_profile(sfb200_plan *p) {
     for (size_t i = 0; i < nl; ++i) {
         const Launch &L = H.launches[i];
         CK(cudaEventRecord(ev[i], st));
-        switch (L.kind) {
-            case L_SMALL_A: launch_small(p->D, p->d_small + L.first, L.count, L.smem, false, st); break;
-            case L_SMALL_B: launch_small(p->D, p->d_small + L.first, L.count, L.smem, true, st); break;
-            case L_POTRF: case L_GETRF: launch_diag(p->D, p->d_diag + L.first, L.count, st); break;
-            case L_TRSM: launch_trsm(p->D, p->d_trsm + L.first, L.count, L.grid, st); break;
-            case L_GEMM128: launch_gemm(p->D, p->d_gemm + L.first, L.count, L.grid, true, st); break;
-            case L_GEMM64: launch_gemm(p->D, p->d_gemm + L.first, L.count, L.grid, false, st); break;
-            default: break;
-        }
+        if (issue_launch(p, L)) return SFB200_ERR_STATE;
     }
     CK(cudaEventRecord(ev[nl], st));
     CK(cudaStreamSynchronize(st));

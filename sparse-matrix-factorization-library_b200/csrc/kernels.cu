@@ -374,10 +374,10 @@ __global__ void __launch_bounds__(64) k_trsm(PlanDev P, const TrsmOp *__restrict
 //   The tensor-core product is issued transposed (D' = Bfrag x Afrag) so that each thread ends up holding two
 //   CONSECUTIVE ROWS of one column of C: 16 contiguous bytes of the column-major destination.
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int GEMM_BK = 16;
 
-template <int BM, int BN, int WARPS_M, int WARPS_N, int STAGES>
+template <int BM, int BN, int WARPS_M, int WARPS_N, int STAGES, int BK = 16>
 struct GemmCfg {
+    static constexpr int GEMM_BK = BK;
     static constexpr int NT = WARPS_M * WARPS_N * 32;
     static constexpr int WM = BM / WARPS_M, WN = BN / WARPS_N;
     static constexpr int FM = WM / 8, FN = WN / 8;
@@ -386,10 +386,11 @@ struct GemmCfg {
     static constexpr int SMEM_BYTES = STAGES * STAGE_DOUBLES * 8;
 };
 
-template <int BM, int BN, int WARPS_M, int WARPS_N, int STAGES>
+template <int BM, int BN, int WARPS_M, int WARPS_N, int STAGES, int BK>
 __global__ void __launch_bounds__(WARPS_M *WARPS_N * 32)
     k_gemm(PlanDev P, const GemmOp *__restrict__ ops, int nops) {
-    using Cfg = GemmCfg<BM, BN, WARPS_M, WARPS_N, STAGES>;
+    using Cfg = GemmCfg<BM, BN, WARPS_M, WARPS_N, STAGES, BK>;
+    constexpr int GEMM_BK = BK;
     constexpr int NT = Cfg::NT, FM = Cfg::FM, FN = Cfg::FN, SA = Cfg::SA, SB = Cfg::SB;
     static_assert(BM == BN, "triangular tile decode assumes square tiles");
     extern __shared__ __align__(16) double smem[];
@@ -586,9 +587,11 @@ __global__ void __launch_bounds__(WARPS_M *WARPS_N * 32)
     }
 }
 
-using Gemm128 = GemmCfg<128, 128, 2, 4, 3>;
-using Gemm128w16 = GemmCfg<128, 128, 4, 4, 3>;
-using Gemm64 = GemmCfg<64, 64, 2, 2, 4>;
+using Gemm128 = GemmCfg<128, 128, 2, 4, 3, 16>;
+using Gemm128w16 = GemmCfg<128, 128, 4, 4, 3, 16>;
+using Gemm128k32 = GemmCfg<128, 128, 2, 4, 3, 32>;
+using Gemm128w16k32 = GemmCfg<128, 128, 4, 4, 3, 32>;
+using Gemm64 = GemmCfg<64, 64, 2, 2, 4, 16>;
 
 // ---------------------------------------------------------------------------------------------------------------
 // copy-out
@@ -645,14 +648,18 @@ __global__ void k_peak_dmma(double *out, int iters) {
 // =================================================================================================================
 // launchers
 // =================================================================================================================
+template <class Cfg, int BM, int BN, int WM, int WN, int ST, int BK>
+cudaError_t gemm_optin() {
+    return cudaFuncSetAttribute(k_gemm<BM, BN, WM, WN, ST, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+}
+
 cudaError_t kernels_init() {
     cudaError_t e;
-    e = cudaFuncSetAttribute(k_gemm<128, 128, 2, 4, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, Gemm128::SMEM_BYTES);
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(k_gemm<128, 128, 4, 4, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, Gemm128w16::SMEM_BYTES);
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(k_gemm<64, 64, 2, 2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, Gemm64::SMEM_BYTES);
-    if (e != cudaSuccess) return e;
+    if ((e = gemm_optin<Gemm128, 128, 128, 2, 4, 3, 16>()) != cudaSuccess) return e;
+    if ((e = gemm_optin<Gemm128w16, 128, 128, 4, 4, 3, 16>()) != cudaSuccess) return e;
+    if ((e = gemm_optin<Gemm128k32, 128, 128, 2, 4, 3, 32>()) != cudaSuccess) return e;
+    if ((e = gemm_optin<Gemm128w16k32, 128, 128, 4, 4, 3, 32>()) != cudaSuccess) return e;
+    if ((e = gemm_optin<Gemm64, 64, 64, 2, 2, 4, 16>()) != cudaSuccess) return e;
     e = cudaFuncSetAttribute(k_small<256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(k_small<256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
@@ -690,10 +697,18 @@ void launch_trsm(const PlanDev &P, const TrsmOp *ops, int count, int grid, cudaS
 
 void launch_gemm(const PlanDev &P, const GemmOp *ops, int count, int grid, bool tile128, cudaStream_t st) {
     if (count <= 0 || grid <= 0) return;
-    static const bool w16 = getenv("SFB200_GEMM_WARPS") && atoi(getenv("SFB200_GEMM_WARPS")) == 16;
-    if (tile128 && w16) k_gemm<128, 128, 4, 4, 3><<<grid, Gemm128w16::NT, Gemm128w16::SMEM_BYTES, st>>>(P, ops, count);
-    else if (tile128) k_gemm<128, 128, 2, 4, 3><<<grid, Gemm128::NT, Gemm128::SMEM_BYTES, st>>>(P, ops, count);
-    else k_gemm<64, 64, 2, 2, 4><<<grid, Gemm64::NT, Gemm64::SMEM_BYTES, st>>>(P, ops, count);
+    // SFB200_GEMM_VARIANT: 0 = 8 warps, BK 16 (default); 1 = 16 warps, BK 16; 2 = 8 warps, BK 32; 3 = 16 warps, BK 32
+    static const int variant = getenv("SFB200_GEMM_VARIANT") ? atoi(getenv("SFB200_GEMM_VARIANT")) : 0;
+    if (!tile128) {
+        k_gemm<64, 64, 2, 2, 4, 16><<<grid, Gemm64::NT, Gemm64::SMEM_BYTES, st>>>(P, ops, count);
+        return;
+    }
+    switch (variant) {
+        case 1: k_gemm<128, 128, 4, 4, 3, 16><<<grid, Gemm128w16::NT, Gemm128w16::SMEM_BYTES, st>>>(P, ops, count); break;
+        case 2: k_gemm<128, 128, 2, 4, 3, 32><<<grid, Gemm128k32::NT, Gemm128k32::SMEM_BYTES, st>>>(P, ops, count); break;
+        case 3: k_gemm<128, 128, 4, 4, 3, 32><<<grid, Gemm128w16k32::NT, Gemm128w16k32::SMEM_BYTES, st>>>(P, ops, count); break;
+        default: k_gemm<128, 128, 2, 4, 3, 16><<<grid, Gemm128::NT, Gemm128::SMEM_BYTES, st>>>(P, ops, count); break;
+    }
 }
 
 void launch_pack(const double *X, double *out, const PackTask *tasks, int count, cudaStream_t st) {

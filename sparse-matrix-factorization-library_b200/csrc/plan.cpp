@@ -17,113 +17,85 @@ struct SlotOps {
     std::vector<GemmOp> gemm;
 };
 
-// Blocked right-looking factorization of one large Cholesky panel (replaces dpotrf_ + dtrsm_, CH.c:2135-2142,
-// and the blocked device POTRF of CH.c:2838-2940): nb-wide diagonal blocks inside outer-wide block columns.
-void emit_cholesky_panel(const SnodeDev &sn, const PlanParams &prm, std::map<int, SlotOps> &slots) {
-    const i64 x = sn.xoff, ld = sn.ld;
-    const int n = sn.nscol, R = sn.nsrow, nb = prm.nb, ob_w = prm.outer;
-    const int slots_per_outer = (ob_w / nb) * 3 + 1;
-    int ob = 0;
-    for (int J0 = 0; J0 < n; J0 += ob_w, ++ob) {
-        const int J1 = std::min(J0 + ob_w, n);
-        int ib = 0;
-        for (int j0 = J0; j0 < J1; j0 += nb, ++ib) {
-            const int j1 = std::min(j0 + nb, J1);
-            const int slot = ob * slots_per_outer + ib * 3;
-            slots[slot].diag.push_back(DiagOp{x + j0 + j0 * ld, (int32_t)ld, j1 - j0});
-            if (j1 < R) {
-                TrsmOp t{};
-                t.t_off = x + j0 + j0 * ld;
-                t.b_off = x + j1 + j0 * ld;
-                t.ldt = (int32_t)ld; t.nb = j1 - j0; t.nvec = R - j1;
-                t.estride = (int32_t)ld; t.vstride = 1; t.flags = 0;
-                slots[slot + 1].trsm.push_back(t);
-            }
-            if (j1 < J1) {
-                GemmOp g{};
-                g.a_off = x + j1 + j0 * ld; g.b_off = g.a_off; g.c_off = x + j1 + (i64)j1 * ld;
-                g.lda = g.ldb = g.ldc = (int32_t)ld;
-                g.M = R - j1; g.N = J1 - j1; g.K = j1 - j0; g.flags = G_LOWER;
-                slots[slot + 2].gemm.push_back(g);
-            }
-        }
-        if (J1 < n) {
-            GemmOp g{};
-            g.a_off = x + J1 + (i64)J0 * ld; g.b_off = g.a_off; g.c_off = x + J1 + (i64)J1 * ld;
-            g.lda = g.ldb = g.ldc = (int32_t)ld;
-            g.M = R - J1; g.N = n - J1; g.K = J1 - J0; g.flags = G_LOWER;
-            slots[ob * slots_per_outer + slots_per_outer - 1].gemm.push_back(g);
-        }
-    }
-}
+// Recursive blocked right-looking factorization of one large panel (replaces dpotrf_ + dtrsm_, CH.c:2135-2142, the
+// blocked device POTRF of CH.c:2838-2940, and magma_dgetrf_nopiv + dtrsm_, LU.c:2653-2660).
+//
+// widths = {nb, outer, outer2...}: a block of level d is cut into sub-blocks of width widths[d-1]; after a sub-block
+// [b0,b1) of the block [c0,c1) has been factorized, only the REST OF THAT BLOCK is updated (K = b1-b0), so the trailing
+// updates of the big fronts run with K = the widest level.  Level-0 blocks (<= nb columns) are one k_diag + k_trsm.
+// Every op gets a slot number that depends only on its position in this recursion, never on the front's size: op t of
+// all large fronts of an etree level share one launch.
+//
+// LU panel rows: [0,R) = L11\U11 and L21, [R, R+m) = U12^T.  After sub-block b of block [c0,c1):
+//   G1  rows [b1,R)   x cols [b1,c1)  -= L[.,b] U[b,.]        (B operand = U row block, k-major)
+//   G2  U12^T rows    x cols [b1,c1)  -= U12^T[.,b] L[.,b]^T
+//   G3  rows [b1,c1)  x cols [c1,n)   -= L[.,b] U[b,.]        (keeps the U entries right of the block current)
+// Cholesky only has G1, lower-masked.
+struct PanelEmitter {
+    const SnodeDev &sn;
+    const bool lu;
+    const std::vector<int> &widths;
+    std::map<int, SlotOps> &slots;
+    std::vector<int> nslots;      // nslots[d] = slots used by one block of level d
 
-// LU panel (replaces magma_dgetrf_nopiv + dtrsm_, LU.c:2653-2660).  Rows [0,R) hold L11\U11 and L21, rows
-// [R, 2R-n) hold U12^T.
-void emit_lu_panel(const SnodeDev &sn, const PlanParams &prm, std::map<int, SlotOps> &slots) {
-    const i64 x = sn.xoff, ld = sn.ld;
-    const int n = sn.nscol, R = sn.nsrow, m = R - n, nb = prm.nb, ob_w = prm.outer;
-    const int slots_per_outer = (ob_w / nb) * 3 + 1;
-    int ob = 0;
-    for (int J0 = 0; J0 < n; J0 += ob_w, ++ob) {
-        const int J1 = std::min(J0 + ob_w, n);
-        int ib = 0;
-        for (int j0 = J0; j0 < J1; j0 += nb, ++ib) {
-            const int j1 = std::min(j0 + nb, J1);
-            const int w = j1 - j0;
-            const int slot = ob * slots_per_outer + ib * 3;
-            const i64 d = x + j0 + (i64)j0 * ld;
-            slots[slot].diag.push_back(DiagOp{d, (int32_t)ld, w});
-            auto trsm = [&](i64 b_off, int nvec, int es, int vs, int flags) {
-                if (nvec <= 0) return;
-                TrsmOp t{};
-                t.t_off = d; t.b_off = b_off; t.ldt = (int32_t)ld; t.nb = w; t.nvec = nvec;
-                t.estride = es; t.vstride = vs; t.flags = flags;
-                slots[slot + 1].trsm.push_back(t);
-            };
-            trsm(x + j1 + (i64)j0 * ld, R - j1, (int)ld, 1, T_TRANS);            // L below the block: X U11 = B
-            trsm(x + R + (i64)j0 * ld, m, (int)ld, 1, T_UNIT);                   // U12^T rows:        X L11^T = B
-            trsm(x + j0 + (i64)j1 * ld, n - j1, 1, (int)ld, T_UNIT);             // U11 row block, ALL later columns
-            auto gemm = [&](int slot_id, i64 a, i64 b, i64 c, int M, int N, int K, int flags) {
-                if (M <= 0 || N <= 0) return;
-                GemmOp g{};
-                g.a_off = a; g.b_off = b; g.c_off = c; g.lda = g.ldb = g.ldc = (int32_t)ld;
-                g.M = M; g.N = N; g.K = K; g.flags = flags;
-                slots[slot_id].gemm.push_back(g);
-            };
-            if (j1 < J1) {
-                // inner trailing update, columns [j1,J1): rows [j1,R) use the U row block (k-major B) ...
-                gemm(slot + 2, x + j1 + (i64)j0 * ld, x + j0 + (i64)j1 * ld, x + j1 + (i64)j1 * ld, R - j1, J1 - j1, w,
-                     G_B_KMAJOR);
-                // ... and the U12^T rows use the L block below the diagonal
-                gemm(slot + 2, x + R + (i64)j0 * ld, x + j1 + (i64)j0 * ld, x + R + (i64)j1 * ld, m, J1 - j1, w, 0);
-            }
-            if (J1 < n) {
-                // rows [j0+... of the U11 row blocks right of the outer block column are solved above (n - j1
-                // vectors), but the rows of THIS outer block below j1 still need the update of columns [J1,n) from
-                // this inner block: A[j1:J1, J1:n] -= L[j1:J1, j0:j1] * U[j0:j1, J1:n]
-                gemm(slot + 2, x + j1 + (i64)j0 * ld, x + j0 + (i64)J1 * ld, x + j1 + (i64)J1 * ld, J1 - j1, n - J1, w,
-                     G_B_KMAJOR);
-            }
+    PanelEmitter(const SnodeDev &s, bool is_lu, const std::vector<int> &w, std::map<int, SlotOps> &sl)
+        : sn(s), lu(is_lu), widths(w), slots(sl) {
+        nslots.assign(widths.size() + 1, 0);
+        nslots[0] = 2;
+        for (size_t d = 1; d < widths.size(); ++d) nslots[d] = (widths[d] / widths[d - 1]) * (nslots[d - 1] + 1);
+    }
+
+    void gemm(int slot, i64 a, i64 b, i64 c, int M, int N, int K, int flags) {
+        if (M <= 0 || N <= 0 || K <= 0) return;
+        GemmOp g{};
+        g.a_off = a; g.b_off = b; g.c_off = c; g.lda = g.ldb = g.ldc = sn.ld;
+        g.M = M; g.N = N; g.K = K; g.flags = flags;
+        slots[slot].gemm.push_back(g);
+    }
+    void trsm(int slot, i64 d, int w, i64 b_off, int nvec, int es, int vs, int flags) {
+        if (nvec <= 0) return;
+        TrsmOp t{};
+        t.t_off = d; t.b_off = b_off; t.ldt = sn.ld; t.nb = w; t.nvec = nvec; t.estride = es; t.vstride = vs; t.flags = flags;
+        slots[slot].trsm.push_back(t);
+    }
+
+    void leaf(int j0, int j1, int slot) {
+        const i64 x = sn.xoff, ld = sn.ld;
+        const int n = sn.nscol, R = sn.nsrow, m = R - n, w = j1 - j0;
+        const i64 d = x + j0 + (i64)j0 * ld;
+        slots[slot].diag.push_back(DiagOp{d, sn.ld, w});
+        if (!lu) {
+            trsm(slot + 1, d, w, x + j1 + (i64)j0 * ld, R - j1, sn.ld, 1, 0);
+        } else {
+            trsm(slot + 1, d, w, x + j1 + (i64)j0 * ld, R - j1, sn.ld, 1, T_TRANS);     // L below the block: X U11 = B
+            trsm(slot + 1, d, w, x + R + (i64)j0 * ld, m, sn.ld, 1, T_UNIT);           // U12^T rows:        X L11^T = B
+            trsm(slot + 1, d, w, x + j0 + (i64)j1 * ld, n - j1, 1, sn.ld, T_UNIT);     // U11 row block, ALL later columns
         }
-        if (J1 < n) {
-            const int slot = ob * slots_per_outer + slots_per_outer - 1;
-            const int K = J1 - J0;
-            GemmOp g{};
-            g.lda = g.ldb = g.ldc = (int32_t)ld;
-            g.K = K;
-            // A[J1:R, J1:n] -= L[J1:R, J0:J1] * U[J0:J1, J1:n]
-            g.a_off = x + J1 + (i64)J0 * ld; g.b_off = x + J0 + (i64)J1 * ld; g.c_off = x + J1 + (i64)J1 * ld;
-            g.M = R - J1; g.N = n - J1; g.flags = G_B_KMAJOR;
-            slots[slot].gemm.push_back(g);
-            // U12^T[:, J1:n] -= U12^T[:, J0:J1] * L[J1:n, J0:J1]^T
-            if (m > 0) {
-                g.a_off = x + R + (i64)J0 * ld; g.b_off = x + J1 + (i64)J0 * ld; g.c_off = x + R + (i64)J1 * ld;
-                g.M = m; g.N = n - J1; g.flags = 0;
-                slots[slot].gemm.push_back(g);
+    }
+
+    void block(int c0, int c1, int depth, int slot) {
+        if (depth == 0) { leaf(c0, c1, slot); return; }
+        const i64 x = sn.xoff, ld = sn.ld;
+        const int n = sn.nscol, R = sn.nsrow, m = R - n;
+        const int w = widths[depth - 1], stride = nslots[depth - 1] + 1;
+        int i = 0;
+        for (int b0 = c0; b0 < c1; b0 += w, ++i) {
+            const int b1 = std::min(b0 + w, c1), K = b1 - b0;
+            block(b0, b1, depth - 1, slot + i * stride);
+            if (b1 >= c1) continue;
+            const int gs = slot + i * stride + nslots[depth - 1];
+            if (!lu) {
+                gemm(gs, x + b1 + (i64)b0 * ld, x + b1 + (i64)b0 * ld, x + b1 + (i64)b1 * ld, R - b1, c1 - b1, K, G_LOWER);
+            } else {
+                gemm(gs, x + b1 + (i64)b0 * ld, x + b0 + (i64)b1 * ld, x + b1 + (i64)b1 * ld, R - b1, c1 - b1, K, G_B_KMAJOR);
+                gemm(gs, x + R + (i64)b0 * ld, x + b1 + (i64)b0 * ld, x + R + (i64)b1 * ld, m, c1 - b1, K, 0);
+                gemm(gs, x + b1 + (i64)b0 * ld, x + b0 + (i64)c1 * ld, x + b1 + (i64)c1 * ld, c1 - b1, n - c1, K, G_B_KMAJOR);
             }
         }
     }
-}
+
+    void run() { block(0, sn.nscol, (int)widths.size(), 0); }
+};
 
 }  // namespace
 
@@ -143,6 +115,9 @@ int build_plan(const Symbolic &S, const PlanParams &prm, HostPlan &P, int rank, 
     P.isize = S.isize; P.xsize = S.xsize;
     P.lsxp = S.Lsxp;
     if (prm.nb < 8 || prm.nb > 64 || prm.outer % prm.nb != 0 || prm.ld_align < 1) return 1;
+    if (prm.outer2 != 0 && (prm.outer2 % prm.outer != 0 || prm.outer2 <= prm.outer)) return 1;
+    std::vector<int> widths = {prm.nb, prm.outer};
+    if (prm.outer2 > 0) widths.push_back(prm.outer2);
 
     // ---- panels, levels -------------------------------------------------------------------------------------
     P.snode.resize(ns);
@@ -175,11 +150,12 @@ int build_plan(const Symbolic &S, const PlanParams &prm, HostPlan &P, int rank, 
     }
     P.nlevels = ns > 0 ? maxlev + 1 : 0;
 
-    // ---- ownership: proportional mapping of the supernodal etree onto `world` ranks -----------------------------------
-    // Every supernode starts with the rank range of its parent; the children of a node share the node's range in
-    // proportion to their subtree work (largest first).  A node whose range has collapsed to one rank roots a local
-    // subtree; nodes with a wider range ("shared") are owned by the first rank of the range and receive partial updates
-    // from every rank in it.
+    // ---- ownership: etree subtrees onto `world` ranks ------------------------------------------------------
+    // Start from the roots and keep opening the heaviest subtree (its root joins the "top" set, its children become
+    // subtrees of their own) until the subtrees pack onto the ranks within 5 % of perfect balance (longest-processing-
+    // time packing).  Whole subtrees are local to one rank.  Top supernodes receive partial updates from several ranks:
+    // each goes to the rank with the least work so far, and the partial panel images are summed into that owner
+    // (ReduceStep) right before its level is factorized.
     P.owner.assign(ns, 0);
     P.group_lo.assign(ns, 0);
     P.group_hi.assign(ns, 1);
@@ -191,44 +167,58 @@ int build_plan(const Symbolic &S, const PlanParams &prm, HostPlan &P, int rank, 
             subtree[s] = work[s];
         }
         std::vector<std::vector<i64>> kids(ns);
-        std::vector<i64> roots;
+        std::vector<i64> frontier;
         for (i64 s = 0; s < ns; ++s) {
             if (sparent[s] >= 0) { subtree[sparent[s]] += subtree[s]; kids[sparent[s]].push_back(s); }   // children precede parents
-            else roots.push_back(s);
+            else frontier.push_back(s);
         }
-        auto split = [&](std::vector<i64> &nodes, int lo, int hi) {
-            // hand the ranks [lo,hi) to `nodes` in proportion to subtree work, each node a contiguous non-empty range
-            std::sort(nodes.begin(), nodes.end(), [&](i64 a, i64 b) { return subtree[a] != subtree[b] ? subtree[a] > subtree[b] : a < b; });
+        std::vector<char> is_top(ns, 0);
+        std::vector<int32_t> where(ns, -1);
+        std::vector<double> load(world, 0.0);
+        auto pack = [&]() {
+            std::sort(frontier.begin(), frontier.end(), [&](i64 a, i64 b) { return subtree[a] != subtree[b] ? subtree[a] > subtree[b] : a < b; });
+            std::fill(load.begin(), load.end(), 0.0);
             double total = 0;
-            for (i64 c : nodes) total += subtree[c];
-            const int g = hi - lo;
-            double before = 0;
-            for (i64 c : nodes) {
-                int a = lo + (int)(g * (total > 0 ? before / total : 0.0));
-                int b = lo + (int)(g * (total > 0 ? (before + subtree[c]) / total : 0.0) + 1e-9);
-                a = std::min(a, hi - 1);
-                b = std::max(std::min(b, hi), a + 1);
-                P.group_lo[c] = a;
-                P.group_hi[c] = b;
-                before += subtree[c];
+            for (i64 q : frontier) {
+                const int r = (int)(std::min_element(load.begin(), load.end()) - load.begin());
+                where[q] = r;
+                load[r] += subtree[q];
+                total += subtree[q];
             }
+            return std::make_pair(*std::max_element(load.begin(), load.end()), total);
         };
-        split(roots, 0, world);
-        for (i64 s = ns - 1; s >= 0; --s) {      // parents before children
-            if (P.group_hi[s] - P.group_lo[s] > 1 && !kids[s].empty()) split(kids[s], P.group_lo[s], P.group_hi[s]);
-            else for (i64 c : kids[s]) { P.group_lo[c] = P.group_lo[s]; P.group_hi[c] = P.group_lo[s] + 1; }
-            if (P.group_hi[s] - P.group_lo[s] > 1 && kids[s].empty()) P.group_hi[s] = P.group_lo[s] + 1;
-            P.owner[s] = P.group_lo[s];
+        while (true) {
+            const auto mt = pack();
+            if (mt.first <= 1.05 * mt.second / world || (i64)frontier.size() >= 64 * (i64)world) break;
+            size_t pick = frontier.size();
+            for (size_t k = 0; k < frontier.size(); ++k)        // frontier is sorted: first splittable = heaviest
+                if (!kids[frontier[k]].empty()) { pick = k; break; }
+            if (pick == frontier.size()) break;
+            const i64 q = frontier[pick];
+            is_top[q] = 1;
+            frontier.erase(frontier.begin() + pick);
+            frontier.insert(frontier.end(), kids[q].begin(), kids[q].end());
         }
-        // a shared node only needs the ranks that really own something below it (or the node itself)
-        std::vector<int32_t> lo_used(ns), hi_used(ns);
-        for (i64 s = 0; s < ns; ++s) { lo_used[s] = P.owner[s]; hi_used[s] = P.owner[s] + 1; }
+        for (i64 s = ns - 1; s >= 0; --s) {                      // parents before children: local subtrees inherit
+            if (is_top[s]) continue;
+            if (where[s] < 0) where[s] = where[sparent[s]];
+            P.owner[s] = where[s];
+        }
+        std::vector<i64> tops;
+        for (i64 s = 0; s < ns; ++s) if (is_top[s]) tops.push_back(s);
+        std::sort(tops.begin(), tops.end(), [&](i64 a, i64 b) { return work[a] != work[b] ? work[a] > work[b] : a < b; });
+        for (i64 t : tops) {
+            const int r = (int)(std::min_element(load.begin(), load.end()) - load.begin());
+            P.owner[t] = r;
+            load[r] += work[t];
+        }
+        // contributing rank range of every supernode = owners found in its subtree (bottom-up), plus its own owner
+        for (i64 s = 0; s < ns; ++s) { P.group_lo[s] = P.owner[s]; P.group_hi[s] = P.owner[s] + 1; }
         for (i64 s = 0; s < ns; ++s)
             if (sparent[s] >= 0) {
-                lo_used[sparent[s]] = std::min(lo_used[sparent[s]], lo_used[s]);
-                hi_used[sparent[s]] = std::max(hi_used[sparent[s]], hi_used[s]);
+                P.group_lo[sparent[s]] = std::min(P.group_lo[sparent[s]], P.group_lo[s]);
+                P.group_hi[sparent[s]] = std::max(P.group_hi[sparent[s]], P.group_hi[s]);
             }
-        for (i64 s = 0; s < ns; ++s) { P.group_lo[s] = lo_used[s]; P.group_hi[s] = hi_used[s]; P.owner[s] = std::min<int32_t>(P.owner[s], hi_used[s] - 1); }
         for (i64 s = 0; s < ns; ++s) if (P.owner[s] == rank) P.local_flops += work[s];
     } else {
         P.local_flops = P.flops;
@@ -335,7 +325,7 @@ int build_plan(const Symbolic &S, const PlanParams &prm, HostPlan &P, int rank, 
         ph.launch_first = (int32_t)P.launches.size();
         for (i64 s : by_level[lev]) {
             const SnodeDev &d = P.snode[s];
-            if (P.group_hi[s] - P.group_lo[s] > 1 && rank >= P.group_lo[s] && rank < P.group_hi[s])
+            if (P.group_hi[s] - P.group_lo[s] > 1)      // the same list on every rank; a rank outside [lo,hi) skips the step
                 P.reduces.push_back(ReduceStep{d.xoff, (i64)d.ld * d.nscol, P.owner[s], P.group_lo[s], P.group_hi[s]});
             if (!mine(s)) continue;
             const i64 pb = panel_bytes(d);
@@ -344,7 +334,7 @@ int build_plan(const Symbolic &S, const PlanParams &prm, HostPlan &P, int rank, 
                 for (int k = 0; k < 4; ++k) if (pb <= small_limits[k]) { c = k; break; }
             if (c >= 0) { cls[c].push_back(s); ++P.nsmall; continue; }
             ++P.nlarge;
-            if (lu) emit_lu_panel(d, prm, slots); else emit_cholesky_panel(d, prm, slots);
+            PanelEmitter(d, lu, widths, slots).run();
             const int m = d.nsrow - d.nscol;
             if (m > 0) {
                 GemmOp g{};

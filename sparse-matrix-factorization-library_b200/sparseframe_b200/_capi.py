@@ -15,7 +15,8 @@ SYMBOLS = [
     "sfb200_plan_create", "sfb200_plan_free", "sfb200_plan_int", "sfb200_factorize", "sfb200_factorize_device",
     "sfb200_plan_sync", "sfb200_download_factor", "sfb200_last_ms", "sfb200_last_launches", "sfb200_host_alloc",
     "sfb200_host_free", "sfb200_probe_fp64_peak", "sfb200_plan_set_stream", "sfb200_plan_profile",
-    "sfb200_plan_profile_get",
+    "sfb200_plan_profile_get", "sfb200_plan_create_part", "sfb200_plan_double", "sfb200_plan_phase_info",
+    "sfb200_plan_reduce_info", "sfb200_plan_owner", "sfb200_plan_factor_ptr", "sfb200_phase_begin", "sfb200_phase_run",
 ]
 
 
@@ -66,6 +67,16 @@ def lib():
     L.sfb200_host_free.restype = None
     L.sfb200_probe_fp64_peak.restype = dbl
     L.sfb200_probe_fp64_peak.argtypes = [ci, ci, ci]
+    L.sfb200_plan_create_part.argtypes = [vp, ci, ci, ci, C.POINTER(vp)]
+    L.sfb200_plan_double.restype = dbl
+    L.sfb200_plan_double.argtypes = [vp, C.c_char_p]
+    L.sfb200_plan_phase_info.argtypes = [vp, ci, vp]
+    L.sfb200_plan_reduce_info.argtypes = [vp, ci, vp]
+    L.sfb200_plan_owner.argtypes = [vp, vp]
+    L.sfb200_plan_factor_ptr.restype = vp
+    L.sfb200_plan_factor_ptr.argtypes = [vp]
+    L.sfb200_phase_begin.argtypes = [vp, vp, vp]
+    L.sfb200_phase_run.argtypes = [vp, ci]
     L.sfb200_plan_set_stream.argtypes = [vp, vp]
     L.sfb200_plan_profile.argtypes = [vp]
     L.sfb200_plan_profile_get.restype = dbl

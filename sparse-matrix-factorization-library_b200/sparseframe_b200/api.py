@@ -123,14 +123,48 @@ def fp64_peak(device=0, which="dmma", iters=4096) -> float:
 class Plan:
     """Device-resident numeric schedule for one symbolic structure."""
 
-    def __init__(self, sym: Symbolic, device=0):
+    def __init__(self, sym: Symbolic, device=0, rank=0, world=1):
         L = _capi.lib()
         h = C.c_void_p()
-        rc = L.sfb200_plan_create(sym._h, int(device), C.byref(h))
+        rc = L.sfb200_plan_create_part(sym._h, int(device), int(rank), int(world), C.byref(h))
         if rc != 0:
             raise RuntimeError("sfb200_plan_create failed (%d): %s" % (rc, _capi.last_error()))
         self._h = h
         self.sym = sym
+        self.rank, self.world = int(rank), int(world)
+
+    # ---- etree-partitioned execution (one rank of `world`): see parallel.py ------------------------------------
+    def double(self, name) -> float:
+        return float(_capi.lib().sfb200_plan_double(self._h, name.encode()))
+
+    def phase_info(self, k):
+        out = np.zeros(5, dtype=np.int64)
+        _capi.lib().sfb200_plan_phase_info(self._h, int(k), out.ctypes.data)
+        return dict(reduce_first=int(out[0]), reduce_count=int(out[1]), launch_first=int(out[2]),
+                    launch_count=int(out[3]), level=int(out[4]))
+
+    def reduce_info(self, i):
+        out = np.zeros(5, dtype=np.int64)
+        _capi.lib().sfb200_plan_reduce_info(self._h, int(i), out.ctypes.data)
+        return dict(offset=int(out[0]), count=int(out[1]), root=int(out[2]), lo=int(out[3]), hi=int(out[4]))
+
+    def owner(self) -> np.ndarray:
+        out = np.zeros(self.int("nsuper"), dtype=np.int32)
+        _capi.lib().sfb200_plan_owner(self._h, out.ctypes.data)
+        return out
+
+    def factor_ptr(self) -> int:
+        return int(_capi.lib().sfb200_plan_factor_ptr(self._h))
+
+    def phase_begin(self, d_lx_ptr: int, d_ux_ptr: int = 0):
+        rc = _capi.lib().sfb200_phase_begin(self._h, d_lx_ptr, d_ux_ptr or None)
+        if rc != 0:
+            raise RuntimeError("sfb200_phase_begin failed (%d): %s" % (rc, _capi.last_error()))
+
+    def phase_run(self, k):
+        rc = _capi.lib().sfb200_phase_run(self._h, int(k))
+        if rc != 0:
+            raise RuntimeError("sfb200_phase_run failed (%d): %s" % (rc, _capi.last_error()))
 
     def int(self, name) -> int:
         return int(_capi.lib().sfb200_plan_int(self._h, name.encode()))

@@ -206,3 +206,51 @@ def test_full_size_backward_error(cfg):
     assert backward <= BACKWARD_TOL
     assert res <= 1e-13
     plan.close()
+
+
+@pytest.mark.parametrize("gen,g,kind,world", [("lap3d", 20, "cholesky", 2), ("lap3d", 20, "cholesky", 4), ("cd3d", 16, "lu", 3)])
+def test_partitioned_plans_emulated_on_one_gpu(gen, g, kind, world):
+    """The etree-partitioned device path without NCCL: all `world` rank plans live on this one GPU, phases run in lock
+    step and the reduce steps are done with torch adds -- the same order of operations torch.distributed gives."""
+    import torch
+    from sparseframe_b200.parallel import DeviceBackend, owned_mask
+    A, _ = build_matrix(gen, g)
+    S = sf.analyze(A, kind)
+    split = kind == "lu" and S.int("symmetric") == 0
+    d_lx = torch.from_numpy(S.array("Lx")).cuda()
+    d_ux = torch.from_numpy(S.array("Ux")).cuda() if split else None
+    plans = [sf.Plan(S, rank=r, world=world) for r in range(world)]
+    stream = torch.cuda.current_stream()
+    for p in plans:
+        p.set_stream(stream.cuda_stream)
+    backs = [DeviceBackend(p, d_lx, d_ux) for p in plans]
+    assert sum(p.double("local_flops") for p in plans) == pytest.approx(S.flops, rel=1e-12)
+    for b in backs:
+        b.begin()
+    nred = 0
+    for k in range(backs[0].nphases):
+        ph = backs[0].phases[k]
+        for i in range(ph["reduce_first"], ph["reduce_first"] + ph["reduce_count"]):
+            r = backs[0].reduces[i]
+            sl = slice(r["offset"], r["offset"] + r["count"])
+            for q in range(r["lo"], r["hi"]):
+                if q != r["root"]:
+                    backs[r["root"]].image[sl] += backs[q].image[sl]
+            nred += 1
+        for b in backs:
+            b.run_phase(k)
+    for b in backs:
+        b.finish()
+    assert nred > 0
+    Lsxp = S.array("Lsxp")
+    merged = np.zeros(S.int("xsize"))
+    owner = plans[0].owner()
+    for r, p in enumerate(plans):
+        m = owned_mask(owner, Lsxp, r)
+        merged[m] = p.download()[m]
+    st = oracle_structure(S)
+    ref_lsx, bad = sforacle.factorize(kind, st, S.array("Lx"), S.array("Ux") if split else None)
+    assert bad == 0
+    compare(kind, st, ref_lsx, merged)
+    for p in plans:
+        p.close()

@@ -10,7 +10,9 @@ import sparseframe_b200 as sf
 from conftest import build_matrix
 
 PARAMS = [dict(), dict(small_a=0, small_b=0), dict(nb=16, outer=32, small_a=0, small_b=0),
-          dict(nb=8, outer=16, small_b=3000), dict(ld_align=1), dict(ld_align=16, nb=32, outer=64)]
+          dict(nb=8, outer=16, small_b=3000), dict(ld_align=1), dict(ld_align=16, nb=32, outer=64),
+          # three blocking levels (test hook of oracle/plan_host_exec.cpp: outer = outer2 * 100000 + outer)
+          dict(nb=8, outer=64 * 100000 + 16, small_a=0, small_b=0), dict(nb=16, outer=128 * 100000 + 32, small_b=4096)]
 
 
 @pytest.mark.parametrize("prm", PARAMS, ids=[str(p) for p in PARAMS])
