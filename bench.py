@@ -154,7 +154,8 @@ def main():
     args = ap.parse_args()
 
     import sparseframe_b200 as sf
-    cfg = args.config or ("cfg2" if args.gpus == 1 else "cfg2")
+    # N=1: BASELINE.json configs[1]; N>1: configs[4], the etree-partitioned 160^3 case (SFB200_BENCH_MGPU_CFG overrides)
+    cfg = args.config or ("cfg2" if args.gpus == 1 else os.environ.get("SFB200_BENCH_MGPU_CFG", "cfg5"))
     gen, g, kind = sf.matrices.CONFIGS[cfg]
     if args.impl == "reference":
         reference_arm(args, cfg, gen, g, kind)
@@ -184,7 +185,7 @@ def main():
     S = sf.analyze(A, kind)
     t_analyze = time.time() - t0
     t0 = time.time()
-    plan = sf.Plan(S, device=local_rank)
+    plan = sf.Plan(S, device=local_rank, rank=rank, world=world)
     t_plan = time.time() - t0
     flops = S.flops
     split = kind == "lu" and not sym
@@ -199,8 +200,16 @@ def main():
     d_lx = torch.from_numpy(lx).cuda()
     d_ux = torch.from_numpy(ux).cuda() if split else None
 
+    pf = None
+    if world > 1:
+        from sparseframe_b200.parallel import DeviceBackend, PartitionedFactorization
+        pf = PartitionedFactorization(DeviceBackend(plan, d_lx, d_ux), dist)
+
     def step():
-        plan.factorize_device(d_lx.data_ptr(), d_ux.data_ptr() if split else 0)
+        if pf is not None:
+            pf.factorize()          # phases of the local subtrees + NCCL reduces of the shared panels
+        else:
+            plan.factorize_device(d_lx.data_ptr(), d_ux.data_ptr() if split else 0)
 
     # ---- device-resident metric ------------------------------------------------------------------------------------
     for _ in range(args.warmup):
@@ -223,21 +232,49 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_total = float(t.item())
     launches = plan.last_launches() * args.steps
-    # every rank factorizes the same matrix (replicas) until the etree-partitioned path lands: total work = world x
-    value = world * flops * args.steps / (ms_total * 1e-3) / 1e9
+    # N>1: ONE matrix, etree subtrees spread over the ranks (strong scaling): the job's flops are the matrix's flops
+    value = flops * args.steps / (ms_total * 1e-3) / 1e9
 
-    # ---- end-to-end through the host-buffer C-ABI call, pinned host memory ------------------------------------------
+    # ---- end-to-end with HOST buffers (pinned): H2D of the matrix values, factorization, D2H of the factor ------------
     xsize = S.int("xsize")
     h_lx = torch.from_numpy(lx).pin_memory()
     h_ux = torch.from_numpy(ux).pin_memory() if split else None
-    h_out = torch.empty(xsize, dtype=torch.float64).pin_memory()
     from sparseframe_b200 import _capi
     L = _capi.lib()
+    if world == 1:
+        h_out = torch.empty(xsize, dtype=torch.float64).pin_memory()
+        d2h_bytes = xsize * 8
 
-    def e2e_step():
-        rc = L.sfb200_factorize(plan._h, h_lx.data_ptr(), h_ux.data_ptr() if split else None, h_out.data_ptr())
-        if rc != 0:
-            raise RuntimeError(_capi.last_error())
+        def e2e_step():
+            rc = L.sfb200_factorize(plan._h, h_lx.data_ptr(), h_ux.data_ptr() if split else None, h_out.data_ptr())
+            if rc != 0:
+                raise RuntimeError(_capi.last_error())
+    else:
+        # every rank uploads the values and brings home the panels it owns (contiguous runs of the padded image)
+        owner = plan.owner()
+        snode_off = plan.panel_offsets()
+        image = pf.b.image
+        runs = []
+        mine = np.flatnonzero(owner == rank)
+        if mine.size:
+            brk = np.flatnonzero(np.diff(mine) != 1)
+            starts = np.concatenate([[mine[0]], mine[brk + 1]])
+            ends = np.concatenate([mine[brk], [mine[-1]]])
+            runs = [(int(snode_off[a]), int(snode_off[b + 1])) for a, b in zip(starts, ends)]
+        own_elems = sum(b - a for a, b in runs)
+        h_out = torch.empty(max(own_elems, 1), dtype=torch.float64).pin_memory()
+        d2h_bytes = own_elems * 8
+
+        def e2e_step():
+            d_lx.copy_(h_lx, non_blocking=True)
+            if split:
+                d_ux.copy_(h_ux, non_blocking=True)
+            pf.factorize()
+            pos = 0
+            for a, b in runs:
+                h_out[pos:pos + (b - a)].copy_(image[a:b], non_blocking=True)
+                pos += b - a
+            torch.cuda.synchronize()
 
     e2e_step()
     barrier()
@@ -249,10 +286,18 @@ def main():
     f1.record(stream)
     barrier()
     t = torch.tensor([f0.elapsed_time(f1)], dtype=torch.float64, device="cuda")
+    d2h_total = torch.tensor([float(d2h_bytes)], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(d2h_total, op=dist.ReduceOp.SUM)
     e2e_ms = float(t.item()) / e2e_steps
-    e2e_value = world * flops / (e2e_ms * 1e-3) / 1e9
+    e2e_value = flops / (e2e_ms * 1e-3) / 1e9
+    shares = torch.tensor([plan.double("local_flops") / flops], dtype=torch.float64, device="cuda")
+    share_list = [torch.zeros_like(shares) for _ in range(world)]
+    if world > 1:
+        dist.all_gather(share_list, shares)
+    else:
+        share_list = [shares]
 
     if rank == 0:
         # ---- roofline of the dominant kernel: live CUDA-event profile of one replay ------------------------------
@@ -285,16 +330,21 @@ def main():
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_total / args.steps, "higher_is_better": True,
-            "scaling": "weak" if world > 1 else "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload_name(cfg, gen, g, kind), "n": n, "nnz_stored": int(A.Cp[-1]),
                        "nsuper": S.int("nsuper"), "factor_GB": xsize * 8e-9, "flops_per_step": flops,
                        "devSlotSize": sf.DEFAULT_DEVSLOT, "l2": "factor (%.1f GB) >> 126 MB L2, no flush needed" % (xsize * 8e-9),
-                       "parallelism": "replicas x%d" % world if world > 1 else "1 GPU",
+                       "parallelism": ("etree subtrees over %d GPUs, %d NCCL reduces of shared panels per step, "
+                                       "flop share per rank %s" % (world, plan.int("nreduces"),
+                                                                   [round(float(v.item()), 3) for v in share_list]))
+                       if world > 1 else "1 GPU",
                        "analyze_s": t_analyze, "plan_s": t_plan},
             "clocks": clocks, "gpu_launches": int(launches),
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms,
-                    "h2d_bytes_per_step": int(lx.nbytes + (ux.nbytes if split else 0)),
-                    "d2h_bytes_per_step": int(xsize * 8), "api": "sfb200_factorize (host Lx -> host Lsx, pinned)"},
+                    "h2d_bytes_per_step": int(world * (lx.nbytes + (ux.nbytes if split else 0))),
+                    "d2h_bytes_per_step": int(d2h_total.item()),
+                    "api": "sfb200_factorize (host Lx -> host Lsx, pinned)" if world == 1 else
+                           "per rank: H2D values, partitioned factorization, D2H of the owned panels (pinned)"},
             "roofline": roof, "cpu_baseline": base,
         }
         print(json.dumps(out))

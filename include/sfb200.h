@@ -94,6 +94,7 @@ int sfb200_plan_phase_info(const sfb200_plan *p, int k, int64_t out[5]);
 int sfb200_plan_reduce_info(const sfb200_plan *p, int i, int64_t out[5]);
 int sfb200_plan_owner(const sfb200_plan *p, int32_t *owner /* nsuper */);
 void *sfb200_plan_factor_ptr(sfb200_plan *p);                 /* device pointer of the padded factor image */
+int sfb200_plan_panel_offsets(const sfb200_plan *p, int64_t *xoff /* nsuper + 1 */);   /* panel offsets in that image */
 int sfb200_phase_begin(sfb200_plan *p, const double *d_Lx, const double *d_Ux);   /* zero + assemble owned panels */
 int sfb200_phase_run(sfb200_plan *p, int k);                  /* launches of phase k, asynchronous */
 void sfb200_plan_free(sfb200_plan *p);

@@ -275,6 +275,13 @@ int sfb200_plan_owner(const sfb200_plan *p, int32_t *owner) {
 
 void *sfb200_plan_factor_ptr(sfb200_plan *p) { return p ? (void *)p->d_X : nullptr; }
 
+int sfb200_plan_panel_offsets(const sfb200_plan *p, int64_t *xoff) {
+    if (!p || !xoff) return SFB200_ERR_ARG;
+    for (i64 s = 0; s < p->H.nsuper; ++s) xoff[s] = p->H.snode[s].xoff;
+    xoff[p->H.nsuper] = p->H.xsize_pad;
+    return SFB200_OK;
+}
+
 int sfb200_phase_begin(sfb200_plan *p, const double *d_Lx, const double *d_Ux) {
     if (!p || !d_Lx) { set_error("sfb200_phase_begin: bad argument"); return SFB200_ERR_ARG; }
     CK(cudaSetDevice(p->device));
@@ -437,6 +444,8 @@ int sfb200_plan_profile(sfb200_plan *p) {
         p->prof_bytes[k] += by;
     }
     for (auto &e : ev) cudaEventDestroy(e);
+    // a partitioned plan replayed alone misses the other ranks' contributions: its pivots mean nothing
+    if (H.world > 1) { CK(cudaStreamSynchronize(st)); return SFB200_OK; }
     return check_status(p);
 }
 
@@ -471,7 +480,10 @@ void sfb200_host_free(void *ptr) { if (ptr) cudaFreeHost(ptr); }
 double sfb200_probe_fp64_peak(int device, int which, int iters) {
     if (sfb200_device_count() <= device) return -1.0;
     cudaSetDevice(device);
-    const int grid = 148 * 8, block = 256;
+    // which: 0 DFMA, 1 DMMA (register operands, 8 accumulators/warp), 2 DMMA fed from shared memory like the GEMM inner
+    // loop (1 CTA of 8 warps per SM), 3 same tile shape with register-resident fragments
+    const bool tile = which >= 2;
+    const int grid = tile ? 148 : 148 * 8, block = 256;
     double *d = nullptr;
     if (cudaMalloc((void **)&d, sizeof(double) * grid * block) != cudaSuccess) return -1.0;
     cudaEvent_t a, b;
@@ -479,7 +491,8 @@ double sfb200_probe_fp64_peak(int device, int which, int iters) {
     for (int rep = 0; rep < 2; ++rep) {
         cudaEventRecord(a, 0);
         if (which == 0) launch_peak_dfma(d, iters, grid, block, 0);
-        else launch_peak_dmma(d, iters, grid, block, 0);
+        else if (which == 1) launch_peak_dmma(d, iters, grid, block, 0);
+        else launch_peak_dmma_tile(d, iters, grid, which == 2 ? 0 : 1, 0);
         cudaEventRecord(b, 0);
         cudaEventSynchronize(b);
     }
@@ -489,8 +502,10 @@ double sfb200_probe_fp64_peak(int device, int which, int iters) {
     cudaFree(d);
     if (cudaGetLastError() != cudaSuccess || ms <= 0.f) return -1.0;
     const double threads = (double)grid * block;
-    const double flops = which == 0 ? threads * iters * 64.0 * 2.0                     /* 64 FMA per thread-iteration */
-                                    : (threads / 32.0) * iters * 32.0 * 512.0;         /* 32 DMMA x 256 FMA per warp-iteration */
+    double flops;
+    if (which == 0) flops = threads * iters * 64.0 * 2.0;                        /* 64 FMA per thread-iteration */
+    else if (which == 1) flops = (threads / 32.0) * iters * 32.0 * 512.0;        /* 32 DMMA x 256 FMA per warp-iteration */
+    else flops = (threads / 32.0) * iters * 128.0 * 512.0;                       /* 4 k-steps x 32 DMMA per warp-iteration */
     return flops / (ms * 1e-3) / 1e12;
 }
 

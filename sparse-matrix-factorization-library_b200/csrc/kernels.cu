@@ -643,6 +643,50 @@ __global__ void k_peak_dmma(double *out, int iters) {
     out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+// DMMA fed from shared memory exactly like the k_gemm<128,128> inner loop (8 warps, 64x32 warp tiles, 12 fragment
+// loads per 32 DMMA), but with no global traffic and no barriers: the ceiling of the inner loop itself.
+// mode 0: fragments re-read from shared memory every k-step; mode 1: fragments loaded once (register operands).
+__global__ void __launch_bounds__(256) k_peak_dmma_tile(double *out, int iters, int mode) {
+    constexpr int SA = 132, BK = 16;
+    __shared__ double As[BK * SA], Bs[BK * SA];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int i = tid; i < BK * SA; i += 256) { As[i] = 1.0 + 1e-6 * i; Bs[i] = 1.0 - 1e-6 * i; }
+    __syncthreads();
+    const int wm0 = (warp % 2) * 64, wn0 = (warp / 2) * 32, g = lane >> 2, t4 = lane & 3;
+    double acc[8][4][2];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+    double af[8], bf[4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) af[i] = As[t4 * SA + wm0 + 8 * i + g];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) bf[j] = Bs[t4 * SA + wn0 + 8 * j + g];
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int ks = 0; ks < BK; ks += 4) {
+            if (mode == 0) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) af[i] = As[(ks + t4) * SA + wm0 + 8 * i + g];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) bf[j] = Bs[(ks + t4) * SA + wn0 + 8 * j + g];
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) dmma(acc[i][j][0], acc[i][j][1], bf[j], af[i]);
+        }
+        if (mode == 0) asm volatile("" ::: "memory");
+    }
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) s += acc[i][j][0] + acc[i][j][1];
+    out[blockIdx.x * blockDim.x + tid] = s;
+}
+
 }  // namespace
 
 // =================================================================================================================
@@ -721,6 +765,9 @@ void launch_peak_dfma(double *out, int iters, int grid, int block, cudaStream_t 
 }
 void launch_peak_dmma(double *out, int iters, int grid, int block, cudaStream_t st) {
     k_peak_dmma<<<grid, block, 0, st>>>(out, iters);
+}
+void launch_peak_dmma_tile(double *out, int iters, int grid, int mode, cudaStream_t st) {
+    k_peak_dmma_tile<<<grid, 256, 0, st>>>(out, iters, mode);
 }
 
 }  // namespace sfb200

@@ -34,5 +34,6 @@ void launch_pack(const double *X, double *out, const PackTask *tasks, int count,
 // micro-benchmarks of the two FP64 pipes (peak measurement for the roofline denominators)
 void launch_peak_dfma(double *out, int iters, int grid, int block, cudaStream_t st);
 void launch_peak_dmma(double *out, int iters, int grid, int block, cudaStream_t st);
+void launch_peak_dmma_tile(double *out, int iters, int grid, int mode, cudaStream_t st);
 
 }  // namespace sfb200

@@ -117,7 +117,8 @@ def device_count() -> int:
 
 
 def fp64_peak(device=0, which="dmma", iters=4096) -> float:
-    return float(_capi.lib().sfb200_probe_fp64_peak(int(device), 1 if which == "dmma" else 0, int(iters)))
+    code = {"dfma": 0, "dmma": 1, "dmma_smem_tile": 2, "dmma_reg_tile": 3}[which]
+    return float(_capi.lib().sfb200_probe_fp64_peak(int(device), code, int(iters)))
 
 
 class Plan:
@@ -151,6 +152,11 @@ class Plan:
     def owner(self) -> np.ndarray:
         out = np.zeros(self.int("nsuper"), dtype=np.int32)
         _capi.lib().sfb200_plan_owner(self._h, out.ctypes.data)
+        return out
+
+    def panel_offsets(self) -> np.ndarray:
+        out = np.zeros(self.int("nsuper") + 1, dtype=np.int64)
+        _capi.lib().sfb200_plan_panel_offsets(self._h, out.ctypes.data)
         return out
 
     def factor_ptr(self) -> int:
