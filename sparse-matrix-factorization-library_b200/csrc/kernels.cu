@@ -434,58 +434,113 @@ __global__ void __launch_bounds__(WARPS_M *WARPS_N * 32)
     const int mrem = M - row0, nrem = N - col0;
     const bool b_kmajor = (op.flags & G_B_KMAJOR) != 0;
 
+    // ---- operand staging: per-thread copy descriptors computed ONCE ----------------------------------------------
+    // Every thread copies the same row offset of NP consecutive passes of k-rows, so a stage is NP cp.async per operand
+    // whose source advances by a fixed stride; per k-iteration only one pointer add and one k-bound compare per copy
+    // remain (a generic index -> (k,row) decode per copy costs more issue slots than the DMMAs of the stage).
     // 16-byte copies whenever the operand's columns start on even element offsets (always true for the in-place
-    // trailing updates; true for a scatter op when the front has an even number of columns)
+    // trailing updates; true for a scatter op when the front has an even number of columns).
     const bool a_vec = (((op.a_off | (int64_t)op.lda) & 1) == 0);
     const bool b_vec = !b_kmajor && (((op.b_off | (int64_t)op.ldb) & 1) == 0);
 
+    struct Stager {
+        const double *src;      // source of copy 0 for the current k-iteration
+        int64_t pass_step;      // elements between consecutive copies of one stage
+        int64_t iter_step;      // elements between consecutive k-iterations
+        int k_first;            // k offset (inside the stage) of copy 0   [row-major operands]
+        int k_pass;             // k-rows per pass                           [row-major operands]
+        int dst;                // shared-memory offset (doubles) of copy 0 inside the operand's stage buffer
+        int dst_step;           // ... and between consecutive copies
+        int bytes;              // 16 / 8 / 0: valid bytes of this thread's row position (row-major operands)
+        int r_first, r_pass;    // k-major B only: row of copy 0 and rows per pass
+    };
+    auto make_rowmajor = [&](const double *base, int ld, int rows_rem, int stride_s, bool vec) {
+        Stager st{};
+        const int tpr = vec ? (BM / 2) : BM;                 // threads per k-row (BM == BN)
+        const int r = (tid % tpr) * (vec ? 2 : 1);
+        st.k_first = tid / tpr;
+        st.k_pass = NT / tpr;
+        const int rem = rows_rem - r;
+        st.bytes = vec ? (rem >= 2 ? 16 : (rem == 1 ? 8 : 0)) : (rem >= 1 ? 8 : 0);
+        st.src = base + r + (int64_t)st.k_first * ld;
+        st.pass_step = (int64_t)st.k_pass * ld;
+        st.iter_step = (int64_t)GEMM_BK * ld;
+        st.dst = st.k_first * stride_s + r;
+        st.dst_step = st.k_pass * stride_s;
+        return st;
+    };
+    Stager sa = make_rowmajor(Ag, op.lda, mrem, SA, a_vec);
+    Stager sb;
+    if (!b_kmajor) {
+        sb = make_rowmajor(Bg, op.ldb, nrem, SB, b_vec);
+    } else {                                                  // element (k, r) of the tile lives at Bg[k + r * ldb]
+        sb = Stager{};
+        const int k = tid % GEMM_BK;
+        sb.r_first = tid / GEMM_BK;
+        sb.r_pass = NT / GEMM_BK;
+        sb.k_first = k;
+        sb.src = Bg + k + (int64_t)sb.r_first * op.ldb;
+        sb.pass_step = (int64_t)sb.r_pass * op.ldb;
+        sb.iter_step = GEMM_BK;
+        sb.dst = k * SB + sb.r_first;
+        sb.dst_step = sb.r_pass;
+    }
+
+    // issues the copies of k-iteration `kt` into `stage`; must be called with kt increasing by one each time
     auto load_stage = [&](int stage, int kt) {
         double *As = smem + stage * Cfg::STAGE_DOUBLES;
         double *Bs = As + GEMM_BK * SA;
-        const int k0 = kt * GEMM_BK;
-        if (a_vec) {
+        const int krem = K - kt * GEMM_BK;                    // valid k-rows of this stage
+        {
+            const double *p = sa.src;
+            if (a_vec) {
+                constexpr int NP = GEMM_BK / (NT / (BM / 2));
 #pragma unroll
-            for (int e = tid; e < GEMM_BK * BM / 2; e += NT) {
-                const int k = e / (BM / 2), r = 2 * (e - k * (BM / 2));
-                const int rem = (k0 + k < K) ? mrem - r : 0;
-                const int bytes = rem >= 2 ? 16 : (rem == 1 ? 8 : 0);
-                const double *src = bytes ? Ag + r + (int64_t)(k0 + k) * op.lda : Ag;
-                cp_async16(As + k * SA + r, src, bytes);
-            }
-        } else {
+                for (int i = 0; i < NP; ++i) {
+                    const int bytes = (sa.k_first + i * (NT / (BM / 2)) < krem) ? sa.bytes : 0;
+                    cp_async16(As + sa.dst + i * sa.dst_step, bytes ? p : Ag, bytes);
+                    p += sa.pass_step;
+                }
+            } else {
+                constexpr int NP = GEMM_BK / (NT / BM);
 #pragma unroll
-            for (int e = tid; e < GEMM_BK * BM; e += NT) {
-                const int k = e / BM, r = e - k * BM;
-                const bool ok = (r < mrem) && (k0 + k < K);
-                const double *src = ok ? Ag + r + (int64_t)(k0 + k) * op.lda : Ag;
-                cp_async8(As + k * SA + r, src, ok ? 8 : 0);
+                for (int i = 0; i < NP; ++i) {
+                    const int bytes = (sa.k_first + i * (NT / BM) < krem) ? sa.bytes : 0;
+                    cp_async8(As + sa.dst + i * sa.dst_step, bytes ? p : Ag, bytes);
+                    p += sa.pass_step;
+                }
             }
+            sa.src += sa.iter_step;
         }
-        if (b_vec) {
+        {
+            const double *p = sb.src;
+            if (b_vec) {
+                constexpr int NP = GEMM_BK / (NT / (BN / 2));
 #pragma unroll
-            for (int e = tid; e < GEMM_BK * BN / 2; e += NT) {
-                const int k = e / (BN / 2), r = 2 * (e - k * (BN / 2));
-                const int rem = (k0 + k < K) ? nrem - r : 0;
-                const int bytes = rem >= 2 ? 16 : (rem == 1 ? 8 : 0);
-                const double *src = bytes ? Bg + r + (int64_t)(k0 + k) * op.ldb : Bg;
-                cp_async16(Bs + k * SB + r, src, bytes);
-            }
-        } else if (!b_kmajor) {
+                for (int i = 0; i < NP; ++i) {
+                    const int bytes = (sb.k_first + i * (NT / (BN / 2)) < krem) ? sb.bytes : 0;
+                    cp_async16(Bs + sb.dst + i * sb.dst_step, bytes ? p : Bg, bytes);
+                    p += sb.pass_step;
+                }
+            } else if (!b_kmajor) {
+                constexpr int NP = GEMM_BK / (NT / BN);
 #pragma unroll
-            for (int e = tid; e < GEMM_BK * BN; e += NT) {
-                const int k = e / BN, r = e - k * BN;
-                const bool ok = (r < nrem) && (k0 + k < K);
-                const double *src = ok ? Bg + r + (int64_t)(k0 + k) * op.ldb : Bg;
-                cp_async8(Bs + k * SB + r, src, ok ? 8 : 0);
-            }
-        } else {
+                for (int i = 0; i < NP; ++i) {
+                    const int bytes = (sb.k_first + i * (NT / BN) < krem) ? sb.bytes : 0;
+                    cp_async8(Bs + sb.dst + i * sb.dst_step, bytes ? p : Bg, bytes);
+                    p += sb.pass_step;
+                }
+            } else {
+                constexpr int NP = BN / (NT / GEMM_BK);
+                const bool kok = sb.k_first < krem;
 #pragma unroll
-            for (int e = tid; e < GEMM_BK * BN; e += NT) {
-                const int r = e / GEMM_BK, k = e - r * GEMM_BK;
-                const bool ok = (r < nrem) && (k0 + k < K);
-                const double *src = ok ? Bg + (k0 + k) + (int64_t)r * op.ldb : Bg;
-                cp_async8(Bs + k * SB + r, src, ok ? 8 : 0);
+                for (int i = 0; i < NP; ++i) {
+                    const int bytes = (kok && sb.r_first + i * sb.r_pass < nrem) ? 8 : 0;
+                    cp_async8(Bs + sb.dst + i * sb.dst_step, bytes ? p : Bg, bytes);
+                    p += sb.pass_step;
+                }
             }
+            sb.src += sb.iter_step;
         }
     };
 
