@@ -214,6 +214,7 @@ int sfb200_plan_create_part(const sfb200_symbolic *s, int device, int rank, int 
     p->D.relmap = p->d_relmap;
     p->D.status = p->d_status;
     p->D.is_lu = H.kind == Kind::LU;
+    p->D.dbg = getenv("SFB200_DBG") ? atoi(getenv("SFB200_DBG")) : 0;
     *out = p;
     return SFB200_OK;
 }

@@ -559,10 +559,11 @@ __global__ void __launch_bounds__(WARPS_M *WARPS_N * 32)
         if (s < KT) load_stage(s, s);
         cp_async_commit();
     }
+    const bool dbg_nocopy = (P.dbg & 1) != 0, dbg_nobar = (P.dbg & 2) != 0;
     for (int kt = 0; kt < KT; ++kt) {
         cp_async_wait<STAGES - 2>();
-        __syncthreads();
-        if (kt + STAGES - 1 < KT) load_stage((kt + STAGES - 1) % STAGES, kt + STAGES - 1);
+        if (!dbg_nobar) __syncthreads();
+        if (kt + STAGES - 1 < KT && !dbg_nocopy) load_stage((kt + STAGES - 1) % STAGES, kt + STAGES - 1);
         cp_async_commit();
         const double *As = smem + (kt % STAGES) * Cfg::STAGE_DOUBLES;
         const double *Bs = As + GEMM_BK * SA;

@@ -19,6 +19,7 @@ struct PlanDev {
     const int32_t *relmap;
     int *status;                     // bit 0: bad pivot met
     int is_lu;
+    int dbg;                         // timing experiments only (SFB200_DBG): bit0 no staging copies, bit1 no barriers
 };
 
 // one-time: opt in to large dynamic shared memory for the kernels that need it
