@@ -123,6 +123,8 @@ int sfb200_plan_set_stream(sfb200_plan *p, void *cuda_stream);
  * 6 gemm64; what 0 = ms, 1 = launches, 2 = algorithmic flops, 3 = algorithmic bytes. */
 int sfb200_plan_profile(sfb200_plan *p);
 double sfb200_plan_profile_get(const sfb200_plan *p, int kind, int what);
+/* per launch i of the schedule: out[8] = {kind, level, grid, ops, ms, algorithmic flops, max K, min K} */
+int sfb200_plan_profile_launch(const sfb200_plan *p, int i, double *out);
 
 /* Copy the device-resident factor into the reference's host layout (xsize doubles). */
 int sfb200_download_factor(sfb200_plan *p, double *Lsx);

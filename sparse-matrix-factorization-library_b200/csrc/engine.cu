@@ -23,6 +23,8 @@ struct sfb200_plan {
     // per-launch-kind profile of the last sfb200_plan_profile() call: ms, launches, algorithmic flops, bytes
     double prof_ms[8] = {0}, prof_flops[8] = {0}, prof_bytes[8] = {0};
     int64_t prof_launches[8] = {0};
+    std::vector<float> prof_launch_ms;     // per launch of the schedule
+    std::vector<double> prof_launch_flops;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};   // numeric begin/end, e2e begin/end
     PlanDev D{};
     // device copies of the plan
@@ -395,6 +397,8 @@ int sfb200_plan_profile(sfb200_plan *p) {
     std::vector<cudaEvent_t> ev(nl + 1);
     for (auto &e : ev) CK(cudaEventCreate(&e));
     for (int k = 0; k < 8; ++k) { p->prof_ms[k] = p->prof_flops[k] = p->prof_bytes[k] = 0; p->prof_launches[k] = 0; }
+    p->prof_launch_ms.clear();
+    p->prof_launch_flops.clear();
     CK(cudaMemsetAsync(p->d_status, 0, sizeof(int), st));
     CK(cudaMemsetAsync(p->d_X, 0, sizeof(double) * (size_t)H.xsize_pad, st));
     launch_assemble(p->d_lx, p->d_asm_l, H.nnz, p->d_X, st);
@@ -443,6 +447,8 @@ int sfb200_plan_profile(sfb200_plan *p) {
         }
         p->prof_flops[k] += fl;
         p->prof_bytes[k] += by;
+        p->prof_launch_ms.push_back(ms);
+        p->prof_launch_flops.push_back(fl);
     }
     for (auto &e : ev) cudaEventDestroy(e);
     // a partitioned plan replayed alone misses the other ranks' contributions: its pivots mean nothing
@@ -461,6 +467,19 @@ double sfb200_plan_profile_get(const sfb200_plan *p, int kind, int what) {
         case 3: return p->prof_bytes[kind];
     }
     return -1.0;
+}
+
+/* per-launch record of the last profile: out = {kind, level, grid, count, ms, algorithmic flops, max K of its ops, min K} */
+int sfb200_plan_profile_launch(const sfb200_plan *p, int i, double *out) {
+    if (!p || !out || i < 0 || i >= (int)p->prof_launch_ms.size()) return SFB200_ERR_ARG;
+    const Launch &L = p->H.launches[i];
+    out[0] = L.kind; out[1] = L.level; out[2] = L.grid; out[3] = L.count;
+    out[4] = p->prof_launch_ms[i]; out[5] = p->prof_launch_flops[i];
+    double kmax = 0, kmin = 1e30;
+    if (L.kind == L_GEMM128 || L.kind == L_GEMM64)
+        for (int q = 0; q < L.count; ++q) { const double k = p->H.gemm_ops[L.first + q].K; kmax = std::max(kmax, k); kmin = std::min(kmin, k); }
+    out[6] = kmax; out[7] = kmin < 1e29 ? kmin : 0;
+    return SFB200_OK;
 }
 
 double sfb200_last_ms(const sfb200_plan *p, int which) {

@@ -231,6 +231,16 @@ class Plan:
                                  bytes=L.sfb200_plan_profile_get(self._h, k, 3))
         return out
 
+    def profile_launches(self):
+        """Per-launch rows of the last profile(): kind, level, grid, ops, ms, flops, kmax, kmin."""
+        rows = []
+        out = np.zeros(8)
+        for i in range(self.int("nlaunches")):
+            if _capi.lib().sfb200_plan_profile_launch(self._h, i, out.ctypes.data) != 0:
+                break
+            rows.append(out.copy())
+        return np.array(rows)
+
     def last_ms(self, which=0) -> float:
         return float(_capi.lib().sfb200_last_ms(self._h, which))
 
