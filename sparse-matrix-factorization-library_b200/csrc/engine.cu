@@ -37,6 +37,15 @@ struct sfb200_plan {
     PackTask *d_pack = nullptr;
     double *d_X = nullptr, *d_out = nullptr, *d_lx = nullptr, *d_ux = nullptr;
     int *d_status = nullptr;
+    // streamed copy-out (host-buffer call with a page-locked Lsx): copy stream, per-level work lists
+    cudaStream_t copy_stream = nullptr;
+    std::vector<cudaEvent_t> copy_events;
+    size_t copy_events_used = 0;
+    cudaEvent_t copy_done = nullptr;
+    PackTask *d_spack = nullptr;                       // pack tasks of the SMALL panels, grouped by level
+    std::vector<std::pair<int, int>> spack_range;      // per level: [first, count) in d_spack
+    std::vector<std::vector<i64>> big_by_level;        // per level: supernodes copied by the DMA engine
+    int top_width = 256;                               // width of the widest blocking level
     size_t device_bytes = 0;
     float ms_numeric = 0.f, ms_e2e = 0.f;
     int64_t launches = 0;
@@ -142,6 +151,10 @@ void sfb200_plan_free(sfb200_plan *p) {
                     p->d_ux, p->d_status};
     for (void *q : ptrs) if (q) cudaFree(q);
     for (auto &e : p->ev) if (e) cudaEventDestroy(e);
+    for (auto &e : p->copy_events) if (e) cudaEventDestroy(e);
+    if (p->copy_done) cudaEventDestroy(p->copy_done);
+    if (p->d_spack) cudaFree(p->d_spack);
+    if (p->copy_stream) cudaStreamDestroy(p->copy_stream);
     if (p->stream && p->own_stream) cudaStreamDestroy(p->stream);
     delete p;
 }
@@ -205,6 +218,34 @@ int sfb200_plan_create_part(const sfb200_symbolic *s, int device, int rank, int 
     if ((err = dmalloc((void **)&p->d_lx, sizeof(double) * (size_t)H.nnz))) return fail(err);
     if (H.split && (err = dmalloc((void **)&p->d_ux, sizeof(double) * (size_t)H.unnz))) return fail(err);
     if ((err = dmalloc((void **)&p->d_status, sizeof(int)))) return fail(err);
+    {   // copy-out work lists: small panels go through k_pack (written straight into mapped host memory), panels of
+        // at least 1 MiB through the DMA engine (cudaMemcpy2DAsync), block column by block column for the widest fronts
+        const bool lu = H.kind == Kind::LU;
+        p->top_width = prm.outer2 > 0 ? prm.outer2 : prm.outer;
+        p->big_by_level.assign(H.nlevels, {});
+        std::vector<std::vector<PackTask>> small(H.nlevels);
+        for (i64 sidx = 0; sidx < H.nsuper; ++sidx) {
+            const SnodeDev &d = H.snode[sidx];
+            const int rows = lu ? 2 * d.nsrow - d.nscol : d.nsrow;
+            if ((i64)rows * d.nscol * 8 >= (1 << 20)) { p->big_by_level[d.level].push_back(sidx); continue; }
+            const int chunk = std::max(1, 65536 / std::max(rows, 1));
+            for (int c0 = 0; c0 < d.nscol; c0 += chunk) {
+                PackTask t{};
+                t.src = d.xoff + (i64)c0 * d.ld;
+                t.dst = H.lsxp[sidx] + (i64)c0 * rows;
+                t.rows = rows; t.ld = d.ld; t.cols = std::min(chunk, d.nscol - c0);
+                small[d.level].push_back(t);
+            }
+        }
+        std::vector<PackTask> flat;
+        for (int l = 0; l < H.nlevels; ++l) {
+            p->spack_range.push_back({(int)flat.size(), (int)small[l].size()});
+            flat.insert(flat.end(), small[l].begin(), small[l].end());
+        }
+        if ((err = upload(p, p->d_spack, flat))) return fail(err);
+        if (cudaStreamCreateWithFlags(&p->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreateWithFlags(&p->copy_done, cudaEventDisableTiming) != cudaSuccess) { set_error("copy stream"); return fail(SFB200_ERR_CUDA); }
+    }
     if (cudaStreamSynchronize(p->stream) != cudaSuccess) { set_error("plan upload failed"); return fail(SFB200_ERR_CUDA); }
     p->D.X = p->d_X;
     p->D.snode = p->d_snode;
@@ -354,19 +395,114 @@ int sfb200_download_factor(sfb200_plan *p, double *Lsx) {
     return SFB200_OK;
 }
 
+namespace {
+
+cudaEvent_t next_copy_event(sfb200_plan *p) {
+    if (p->copy_events_used == p->copy_events.size()) {
+        cudaEvent_t e = nullptr;
+        if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        p->copy_events.push_back(e);
+    }
+    return p->copy_events[p->copy_events_used++];
+}
+
+// copy columns [c0,c1) of supernode s from the padded factor to the reference layout on the host (DMA engine)
+int copy_columns(sfb200_plan *p, i64 sidx, int c0, int c1, double *Lsx) {
+    const HostPlan &H = p->H;
+    const SnodeDev &d = H.snode[sidx];
+    const int rows = H.kind == Kind::LU ? 2 * d.nsrow - d.nscol : d.nsrow;
+    CK(cudaMemcpy2DAsync(Lsx + H.lsxp[sidx] + (i64)c0 * rows, sizeof(double) * rows, p->d_X + d.xoff + (i64)c0 * d.ld,
+                         sizeof(double) * d.ld, sizeof(double) * rows, (size_t)(c1 - c0), cudaMemcpyDeviceToHost,
+                         p->copy_stream));
+    return SFB200_OK;
+}
+
+// Factorization with the copy-out streamed behind it: as soon as an etree level (or, for the widest fronts, a block
+// column of the level) is final, its panels leave for the host on a second stream while the next level computes.
+int factorize_streamed(sfb200_plan *p, double *Lsx, double *Lsx_dev_alias) {
+    const HostPlan &H = p->H;
+    int rc = begin_factor(p);
+    if (rc) return rc;
+    p->copy_events_used = 0;
+    auto publish = [&]() -> cudaEvent_t {            // everything issued so far on the main stream is visible to copies
+        cudaEvent_t e = next_copy_event(p);
+        if (!e) return nullptr;
+        if (cudaEventRecord(e, p->stream) != cudaSuccess || cudaStreamWaitEvent(p->copy_stream, e, 0) != cudaSuccess) return nullptr;
+        return e;
+    };
+    for (const Phase &ph : H.phases) {
+        const int lev = ph.level;
+        const std::vector<i64> &big = p->big_by_level[lev];
+        std::vector<int> sent(big.size(), 0);            // columns of each big front already on their way
+        int cur_block = -1;
+        for (int li = ph.launch_first; li < ph.launch_first + ph.launch_count; ++li) {
+            const Launch &L = H.launches[li];
+            if (L.top_block > cur_block && cur_block >= 0) {
+                // the schedule moves on to block column L.top_block: everything left of it is final in every front
+                bool any = false;
+                for (size_t b = 0; b < big.size(); ++b)
+                    if (std::min<int>(H.snode[big[b]].nscol, L.top_block * p->top_width) > sent[b]) any = true;
+                if (any) {
+                    if (!publish()) { set_error("event"); return SFB200_ERR_CUDA; }
+                    for (size_t b = 0; b < big.size(); ++b) {
+                        const int c1 = std::min<int>(H.snode[big[b]].nscol, L.top_block * p->top_width);
+                        if (c1 > sent[b]) { rc = copy_columns(p, big[b], sent[b], c1, Lsx); if (rc) return rc; sent[b] = c1; }
+                    }
+                }
+            }
+            if (L.top_block >= 0) cur_block = std::max(cur_block, (int)L.top_block);
+            rc = issue_launch(p, L);
+            if (rc) return rc;
+            ++p->launches;
+        }
+        // the level is final: remaining columns of its big fronts, then all of its small fronts
+        if (!publish()) { set_error("event"); return SFB200_ERR_CUDA; }
+        for (size_t b = 0; b < big.size(); ++b) {
+            const int n = H.snode[big[b]].nscol;
+            if (sent[b] < n) { rc = copy_columns(p, big[b], sent[b], n, Lsx); if (rc) return rc; }
+        }
+        const auto range = p->spack_range[lev];
+        if (range.second > 0) launch_pack(p->d_X, Lsx_dev_alias, p->d_spack + range.first, range.second, p->copy_stream);
+    }
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(p->copy_done, p->copy_stream));
+    CK(cudaStreamWaitEvent(p->stream, p->copy_done, 0));
+    return SFB200_OK;
+}
+
+}  // namespace
+
 int sfb200_factorize(sfb200_plan *p, const double *Lx, const double *Ux, double *Lsx) {
     if (!p || !Lx) { set_error("sfb200_factorize: bad argument"); return SFB200_ERR_ARG; }
     CK(cudaSetDevice(p->device));
     const HostPlan &H = p->H;
     if (H.split && !Ux) { set_error("unsymmetric LU needs Ux"); return SFB200_ERR_ARG; }
+    if (H.world > 1) { set_error("sfb200_factorize: partitioned plans are driven phase by phase (sfb200_phase_*)"); return SFB200_ERR_STATE; }
+    // page-locked destination -> stream the copy-out behind the factorization; pageable -> pack + one copy at the end
+    double *alias = nullptr;
+    if (Lsx && !getenv("SFB200_NO_STREAMED_COPY")) {
+        cudaPointerAttributes attr;
+        if (cudaPointerGetAttributes(&attr, Lsx) == cudaSuccess && attr.type == cudaMemoryTypeHost && attr.devicePointer)
+            alias = (double *)attr.devicePointer;
+        else cudaGetLastError();
+    }
     CK(cudaEventRecord(p->ev[2], p->stream));
     CK(cudaMemcpyAsync(p->d_lx, Lx, sizeof(double) * (size_t)H.nnz, cudaMemcpyHostToDevice, p->stream));
     if (H.split) CK(cudaMemcpyAsync(p->d_ux, Ux, sizeof(double) * (size_t)H.unnz, cudaMemcpyHostToDevice, p->stream));
-    int rc = sfb200_factorize_device(p, p->d_lx, p->d_ux);
-    if (rc) return rc;
-    if (Lsx) {
-        rc = sfb200_download_factor(p, Lsx);
+    int rc;
+    if (alias) {
+        CK(cudaEventRecord(p->ev[0], p->stream));
+        rc = factorize_streamed(p, Lsx, alias);
         if (rc) return rc;
+        CK(cudaEventRecord(p->ev[1], p->stream));
+        p->factored = true;
+    } else {
+        rc = sfb200_factorize_device(p, p->d_lx, p->d_ux);
+        if (rc) return rc;
+        if (Lsx) {
+            rc = sfb200_download_factor(p, Lsx);
+            if (rc) return rc;
+        }
     }
     CK(cudaEventRecord(p->ev[3], p->stream));
     rc = sfb200_plan_sync(p);

@@ -359,6 +359,7 @@ int build_plan(const Symbolic &S, const PlanParams &prm, HostPlan &P, int rank, 
             Launch L{};
             L.kind = c < 2 ? L_SMALL_A : L_SMALL_B;
             L.level = lev;
+            L.top_block = -1;
             L.first = (int32_t)P.small_tasks.size();
             L.count = L.grid = (int32_t)cls[c].size();
             i64 smem = 0;
@@ -366,12 +367,16 @@ int build_plan(const Symbolic &S, const PlanParams &prm, HostPlan &P, int rank, 
             L.smem = (int32_t)smem;
             P.launches.push_back(L);
         }
-        auto emit_gemm = [&](std::vector<GemmOp> &ops) {
+        auto emit_gemm = [&](std::vector<GemmOp> &ops, int top_block) {
+            // longest tiles first: the CTAs of a launch are dispatched in index order, so the deep-K ops must not be
+            // the ones left running alone at the end of the launch
+            std::stable_sort(ops.begin(), ops.end(), [](const GemmOp &a, const GemmOp &b) { return a.K > b.K; });
             for (int pass = 0; pass < 2; ++pass) {       // pass 0: 128x128 tiles, pass 1: 64x64 tiles
                 const int B = pass == 0 ? 128 : 64;
                 Launch L{};
                 L.kind = pass == 0 ? L_GEMM128 : L_GEMM64;
                 L.level = lev;
+                L.top_block = top_block;
                 L.first = (int32_t)P.gemm_ops.size();
                 i64 tiles = 0;
                 for (GemmOp g : ops) {
@@ -386,11 +391,15 @@ int build_plan(const Symbolic &S, const PlanParams &prm, HostPlan &P, int rank, 
                 if (L.count > 0) P.launches.push_back(L);
             }
         };
+        // slots of one top-level block column are consecutive: slot / (nslots of a top-level sub-block + 1)
+        int top_stride = 2 + 1;
+        for (size_t d = 1; d < widths.size(); ++d) top_stride = (widths[d] / widths[d - 1]) * top_stride + 1;
         for (auto &kv : slots) {
             SlotOps &so = kv.second;
+            const int top_block = kv.first / top_stride;
             if (!so.diag.empty()) {
                 Launch L{};
-                L.kind = lu ? L_GETRF : L_POTRF; L.level = lev;
+                L.kind = lu ? L_GETRF : L_POTRF; L.level = lev; L.top_block = top_block;
                 L.first = (int32_t)P.diag_ops.size();
                 L.count = L.grid = (int32_t)so.diag.size();
                 P.diag_ops.insert(P.diag_ops.end(), so.diag.begin(), so.diag.end());
@@ -398,7 +407,7 @@ int build_plan(const Symbolic &S, const PlanParams &prm, HostPlan &P, int rank, 
             }
             if (!so.trsm.empty()) {
                 Launch L{};
-                L.kind = L_TRSM; L.level = lev;
+                L.kind = L_TRSM; L.level = lev; L.top_block = top_block;
                 L.first = (int32_t)P.trsm_ops.size();
                 i64 ctas = 0;
                 for (TrsmOp t : so.trsm) {
@@ -410,9 +419,9 @@ int build_plan(const Symbolic &S, const PlanParams &prm, HostPlan &P, int rank, 
                 L.grid = (int32_t)ctas;
                 P.launches.push_back(L);
             }
-            if (!so.gemm.empty()) emit_gemm(so.gemm);
+            if (!so.gemm.empty()) emit_gemm(so.gemm, top_block);
         }
-        if (!scatter.empty()) emit_gemm(scatter);
+        if (!scatter.empty()) emit_gemm(scatter, -1);
         ph.reduce_count = (int32_t)P.reduces.size() - ph.reduce_first;
         ph.launch_count = (int32_t)P.launches.size() - ph.launch_first;
         P.phases.push_back(ph);

@@ -14,7 +14,7 @@ struct PlanParams {
     int ld_align = 2;            // panel leading dimensions / offsets are multiples of this many doubles
     int nb = 64;                 // order of the diagonal blocks factored inside one CTA
     int outer = 256;             // width of the second blocking level (its trailing updates run with K = outer)
-    int outer2 = 0;              // optional third level (0 = off): trailing updates of the widest fronts with K = outer2
+    int outer2 = 1024;           // third level (0 = off): trailing updates of the widest fronts with K = outer2
     int small_a_bytes = 6144;    // fronts whose whole panel fits: 64-thread CTA
     int small_b_bytes = 49152;   //                              : 256-thread CTA
     int small_max_m = 160;       // ... and only if the update (m x m) is small enough for one CTA

@@ -84,6 +84,10 @@ struct Launch {
     int32_t count;   // ops / tasks
     int32_t grid;    // CTAs
     int32_t smem;    // dynamic shared memory bytes
+    int32_t top_block; // large-front launches: index of the widest-level block column this launch works on (-1: small fronts
+                     // / scatter).  When it moves from i to i+1 inside a level, block column i of every large front of the
+                     // level is final -> can be copied out while the rest is still being factorized
+    int32_t pad;
 };
 
 // ---- multi-GPU: one etree level = one phase; before its launches, the partial images of the level's shared panels

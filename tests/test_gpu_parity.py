@@ -254,3 +254,29 @@ def test_partitioned_plans_emulated_on_one_gpu(gen, g, kind, world):
     compare(kind, st, ref_lsx, merged)
     for p in plans:
         p.close()
+
+
+def test_streamed_copy_out_into_pinned_memory():
+    """Page-locked destination: the factor is copied out level by level (and block column by block column for the wide
+    fronts) behind the factorization.  Must give the same factor as the pack-then-copy path used for pageable memory."""
+    import torch
+    for gen, g, kind, env in (("lap3d", 28, "cholesky", dict(SFB200_OUTER=128, SFB200_OUTER2=256)),
+                              ("lap2d", 200, "cholesky", dict()), ("cd3d", 22, "lu", dict(SFB200_OUTER=128, SFB200_OUTER2=0))):
+        for k, v in env.items():
+            os.environ[k] = str(v)
+        A, _ = build_matrix(gen, g)
+        S = sf.analyze(A, kind)
+        split = kind == "lu" and S.int("symmetric") == 0
+        plan = sf.Plan(S)
+        ux = S.array("Ux") if split else None
+        pageable = plan.factorize(S.array("Lx"), ux)
+        pinned = torch.full((S.int("xsize"),), float("nan"), dtype=torch.float64).pin_memory()
+        out = plan.factorize(S.array("Lx"), ux, out=pinned.numpy())
+        st = oracle_structure(S)
+        assert not np.isnan(out).any()
+        compare(kind, st, pageable, out, tol=1e-12)
+        ref_lsx, bad = sforacle.factorize(kind, st, S.array("Lx"), ux)
+        compare(kind, st, ref_lsx, out)
+        plan.close()
+        for k in env:
+            os.environ.pop(k, None)
