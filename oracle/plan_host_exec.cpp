@@ -10,6 +10,7 @@
  */
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -61,28 +62,35 @@ void trsm(double *X, const TrsmOp &t) {
     }
 }
 
-void gemm(double *X, const GemmOp &g, const HostPlan &P) {
-    const double *A = X + g.a_off, *B = X + g.b_off;
-    for (int j = 0; j < g.N; ++j) {
-        int lim = 0;
-        i64 col = 0, relbase = 0;
-        if (g.flags & G_SCATTER) {
-            const i64 q = g.meta + j;
-            col = P.upd_coloff[q];
-            relbase = P.upd_relbase[q];
-            lim = (g.flags & G_LIM_SEGB) ? P.upd_segb[q] : (g.flags & G_LIM_SEGE) ? P.upd_sege[q] : j;
-            if (g.flags & G_LIM_SEGE) col += P.upd_uoff[q];
-        } else if (g.flags & G_LOWER) {
-            lim = j;
-        }
-        for (int i = lim; i < g.M; ++i) {
-            double acc = 0.0;
-            for (int k = 0; k < g.K; ++k) {
-                const double b = (g.flags & G_B_KMAJOR) ? B[k + (i64)j * g.ldb] : B[j + (i64)k * g.ldb];
-                acc += A[i + (i64)k * g.lda] * b;
+// one op; B = tile size of its launch (tiles matter only when the op is shared between ranks: tile_mod > 1)
+void gemm(double *X, const GemmOp &g, const HostPlan &P, int B = 128) {
+    const double *A = X + g.a_off, *Bm = X + g.b_off;
+    const bool lower = (g.flags & G_LOWER) != 0;
+    const i64 ntile = gemm_tiles(g.M, g.N, B, lower);
+    for (i64 t = g.tile_rem; t < ntile; t += g.tile_mod) {
+        int ti, tj;
+        decode_tile(t, g.M, g.N, B, lower, ti, tj);
+        for (int j = tj * B; j < std::min(g.N, (tj + 1) * B); ++j) {
+            int lim = 0;
+            i64 col = 0, relbase = 0;
+            if (g.flags & G_SCATTER) {
+                const i64 q = g.meta + j;
+                col = P.upd_coloff[q];
+                relbase = P.upd_relbase[q];
+                lim = (g.flags & G_LIM_SEGB) ? P.upd_segb[q] : (g.flags & G_LIM_SEGE) ? P.upd_sege[q] : j;
+                if (g.flags & G_LIM_SEGE) col += P.upd_uoff[q];
+            } else if (lower) {
+                lim = j;
             }
-            if (g.flags & G_SCATTER) X[col + P.relmap[relbase + i]] -= acc;
-            else X[g.c_off + i + (i64)j * g.ldc] -= acc;
+            for (int i = std::max(lim, ti * B); i < std::min(g.M, (ti + 1) * B); ++i) {
+                double acc = 0.0;
+                for (int k = 0; k < g.K; ++k) {
+                    const double b = (g.flags & G_B_KMAJOR) ? Bm[k + (i64)j * g.ldb] : Bm[j + (i64)k * g.ldb];
+                    acc += A[i + (i64)k * g.lda] * b;
+                }
+                if (g.flags & G_SCATTER) X[col + P.relmap[relbase + i]] -= acc;
+                else X[g.c_off + i + (i64)j * g.ldc] -= acc;
+            }
         }
     }
 }
@@ -93,7 +101,7 @@ int small_front(double *X, const HostPlan &P, i64 s) {
     double *A = X + d.xoff;
     const i64 ld = d.ld;
     GemmOp g{};
-    g.lda = g.ldb = d.ld; g.M = g.N = m; g.K = n; g.meta = d.lsip + n;
+    g.lda = g.ldb = d.ld; g.M = g.N = m; g.K = n; g.meta = d.lsip + n; g.tile_mod = 1; g.tile_rem = 0;
     if (P.kind == Kind::Cholesky) {
         for (int j = 0; j < n; ++j) {
             double dj = A[j + j * ld];
@@ -171,8 +179,8 @@ long run_launches(const HostPlan &P, double *X, int first, int count) {
                 for (int k = 0; k < L.count; ++k) {
                     const GemmOp &g = P.gemm_ops[L.first + k];
                     if (g.tile0 != tiles) return -101;
-                    tiles += gemm_tiles(g.M, g.N, B, (g.flags & G_LOWER) != 0);
-                    gemm(X, g, P);
+                    tiles += share_of_tiles(gemm_tiles(g.M, g.N, B, (g.flags & G_LOWER) != 0), g.tile_mod, g.tile_rem);
+                    gemm(X, g, P, B);
                 }
                 if (tiles != L.grid) return -102;
                 break;
@@ -208,6 +216,7 @@ void *sfcheck_open(int kind, int is_symmetric, long n, const long *Cp, const lon
     if (small_a >= 0) prm.small_a_bytes = small_a;
     if (small_b >= 0) prm.small_b_bytes = small_b;
     if (ld_align > 0) prm.ld_align = ld_align;
+    if (const char *e = getenv("SFCHECK_DIST_MIN_M")) prm.dist_scatter_min_m = atoi(e);
     if (build_plan(h->S, prm, h->P, rank, world) != 0) { delete h; return nullptr; }
     return h;
 }
@@ -225,6 +234,7 @@ long sfcheck_int(void *hv, const char *name) {
     if (k == "xsize") return P.xsize;
     if (k == "nphases") return (long)P.phases.size();
     if (k == "nreduces") return (long)P.reduces.size();
+    if (k == "nbcasts") return (long)P.bcasts.size();
     if (k == "nsuper") return P.nsuper;
     return -1;
 }
@@ -235,10 +245,16 @@ double sfcheck_double(void *hv, const char *name) {
     if (k == "local_flops") return P.local_flops;
     return -1;
 }
-/* out = {reduce_first, reduce_count, launch_first, launch_count, level} */
+/* out[9] = {reduce_first, reduce_count, launch_first, launch_count, level, bcast_first, bcast_count, launch_b_first, launch_b_count} */
 void sfcheck_phase(void *hv, int k, long *out) {
     const Phase &ph = ((CheckHandle *)hv)->P.phases[k];
     out[0] = ph.reduce_first; out[1] = ph.reduce_count; out[2] = ph.launch_first; out[3] = ph.launch_count; out[4] = ph.level;
+    out[5] = ph.bcast_first; out[6] = ph.bcast_count; out[7] = ph.launch_b_first; out[8] = ph.launch_b_count;
+}
+/* out = {offset, count, root, lo, hi} */
+void sfcheck_bcast(void *hv, int i, long *out) {
+    const ReduceStep &r = ((CheckHandle *)hv)->P.bcasts[i];
+    out[0] = r.offset; out[1] = r.count; out[2] = r.root; out[3] = r.lo; out[4] = r.hi;
 }
 /* out = {offset, count, root, lo, hi} */
 void sfcheck_reduce(void *hv, int i, long *out) {
@@ -251,9 +267,10 @@ void sfcheck_owner(void *hv, int *owner) {
 }
 /* X: xsize_pad doubles, zeroed by the caller */
 void sfcheck_begin(void *hv, double *X) { assemble(*(CheckHandle *)hv, X); }
-long sfcheck_run_phase(void *hv, int k, double *X) {
+long sfcheck_run_phase(void *hv, int k, int part, double *X) {
     const HostPlan &P = ((CheckHandle *)hv)->P;
-    return run_launches(P, X, P.phases[k].launch_first, P.phases[k].launch_count);
+    const Phase &ph = P.phases[k];
+    return part == 0 ? run_launches(P, X, ph.launch_first, ph.launch_count) : run_launches(P, X, ph.launch_b_first, ph.launch_b_count);
 }
 /* copy only the panels this rank owns into Lsx_out (reference layout); others are left untouched */
 void sfcheck_pack_owned(void *hv, const double *X, double *Lsx_out) {
@@ -334,6 +351,25 @@ long sfcheck_factorize_partitioned(int kind, int is_symmetric, long n, const lon
         }
         for (int r = 0; r < world; ++r) {
             const long b = run_launches(H[r]->P, X[r].data(), H[r]->P.phases[k].launch_first, H[r]->P.phases[k].launch_count);
+            if (b < 0) return b;
+            bad += b;
+        }
+        // factored shared panels travel from the owner to its group ...
+        {
+            const Phase &ph = H[0]->P.phases[k];
+            for (int i = ph.bcast_first; i < ph.bcast_first + ph.bcast_count; ++i) {
+                const ReduceStep &st = H[0]->P.bcasts[i];
+                for (int q = st.lo; q < st.hi; ++q) {
+                    const ReduceStep &sq = H[q]->P.bcasts[i];
+                    if (sq.offset != st.offset || sq.count != st.count || sq.root != st.root) return -202;
+                    if (q != st.root) std::memcpy(X[q].data() + st.offset, X[st.root].data() + st.offset, sizeof(double) * st.count);
+                }
+                ++nred;
+            }
+        }
+        // ... and every rank of the group computes its share of their Schur-update tiles
+        for (int r = 0; r < world; ++r) {
+            const long b = run_launches(H[r]->P, X[r].data(), H[r]->P.phases[k].launch_b_first, H[r]->P.phases[k].launch_b_count);
             if (b < 0) return b;
             bad += b;
         }

@@ -138,7 +138,8 @@ class CheckBackend:
         L.sfcheck_owner.argtypes = [C.c_void_p, C.c_void_p]
         L.sfcheck_begin.argtypes = [C.c_void_p, C.c_void_p]
         L.sfcheck_run_phase.restype = C.c_long
-        L.sfcheck_run_phase.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        L.sfcheck_run_phase.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        L.sfcheck_bcast.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         L.sfcheck_pack_owned.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.sfcheck_close.argtypes = [C.c_void_p]
         self.L = L
@@ -153,14 +154,17 @@ class CheckBackend:
         self.image = torch.from_numpy(self.X)          # shares memory with X
         self.bad = 0
 
-        def info(fn, k):
-            out = np.zeros(5, dtype=np.int64)
+        def info(fn, k, n=5):
+            out = np.zeros(n, dtype=np.int64)
             fn(self.h, k, out.ctypes.data)
             return [int(v) for v in out]
-        self.phases = [dict(zip(("reduce_first", "reduce_count", "launch_first", "launch_count", "level"),
-                                info(L.sfcheck_phase, k))) for k in range(self.nphases)]
+        self.phases = [dict(zip(("reduce_first", "reduce_count", "launch_first", "launch_count", "level", "bcast_first",
+                                 "bcast_count", "launch_b_first", "launch_b_count"), info(L.sfcheck_phase, k, 9)))
+                       for k in range(self.nphases)]
         self.reduces = [dict(zip(("offset", "count", "root", "lo", "hi"), info(L.sfcheck_reduce, i)))
                         for i in range(self.int("nreduces"))]
+        self.bcasts = [dict(zip(("offset", "count", "root", "lo", "hi"), info(L.sfcheck_bcast, i)))
+                       for i in range(self.int("nbcasts"))]
 
     def int(self, name):
         return int(self.L.sfcheck_int(self.h, name.encode()))
@@ -178,8 +182,8 @@ class CheckBackend:
         self.bad = 0
         self.L.sfcheck_begin(self.h, self.X.ctypes.data)
 
-    def run_phase(self, k):
-        self.bad += self.L.sfcheck_run_phase(self.h, k, self.X.ctypes.data)
+    def run_phase(self, k, part=0):
+        self.bad += self.L.sfcheck_run_phase(self.h, k, part, self.X.ctypes.data)
 
     def finish(self):
         pass

@@ -178,6 +178,7 @@ int sfb200_plan_create_part(const sfb200_symbolic *s, int device, int rank, int 
     if (const char *e = getenv("SFB200_SMALL_A")) prm.small_a_bytes = atoi(e);
     if (const char *e = getenv("SFB200_SMALL_B")) prm.small_b_bytes = atoi(e);
     if (const char *e = getenv("SFB200_GEMM128_MIN")) prm.gemm128_min_m = atoi(e);
+    if (const char *e = getenv("SFB200_DIST_MIN_M")) prm.dist_scatter_min_m = atoi(e);
     const int rc = build_plan(s->S, prm, p->H, rank, world);
     if (rc != 0) {
         delete p;
@@ -283,6 +284,7 @@ int64_t sfb200_plan_int(const sfb200_plan *p, const char *name) {
     if (k == "device") return p->device;
     if (k == "nphases") return (int64_t)H.phases.size();
     if (k == "nreduces") return (int64_t)H.reduces.size();
+    if (k == "nbcasts") return (int64_t)H.bcasts.size();
     if (k == "rank") return H.rank;
     if (k == "world") return H.world;
     if (k == "nsuper") return H.nsuper;
@@ -301,6 +303,14 @@ int sfb200_plan_phase_info(const sfb200_plan *p, int k, int64_t *out) {
     if (!p || !out || k < 0 || k >= (int)p->H.phases.size()) return SFB200_ERR_ARG;
     const Phase &ph = p->H.phases[k];
     out[0] = ph.reduce_first; out[1] = ph.reduce_count; out[2] = ph.launch_first; out[3] = ph.launch_count; out[4] = ph.level;
+    out[5] = ph.bcast_first; out[6] = ph.bcast_count; out[7] = ph.launch_b_first; out[8] = ph.launch_b_count;
+    return SFB200_OK;
+}
+
+int sfb200_plan_bcast_info(const sfb200_plan *p, int i, int64_t *out) {
+    if (!p || !out || i < 0 || i >= (int)p->H.bcasts.size()) return SFB200_ERR_ARG;
+    const ReduceStep &r = p->H.bcasts[i];
+    out[0] = r.offset; out[1] = r.count; out[2] = r.root; out[3] = r.lo; out[4] = r.hi;
     return SFB200_OK;
 }
 
@@ -339,13 +349,15 @@ int sfb200_phase_begin(sfb200_plan *p, const double *d_Lx, const double *d_Ux) {
     return begin_factor(p);
 }
 
-int sfb200_phase_run(sfb200_plan *p, int k) {
+int sfb200_phase_run(sfb200_plan *p, int k, int part) {
     if (!p || k < 0 || k >= (int)p->H.phases.size()) { set_error("sfb200_phase_run: bad phase"); return SFB200_ERR_ARG; }
     CK(cudaSetDevice(p->device));
     const Phase &ph = p->H.phases[k];
-    const int rc = run_launches(p, (size_t)ph.launch_first, (size_t)ph.launch_count);
+    const int rc = part == 0 ? run_launches(p, (size_t)ph.launch_first, (size_t)ph.launch_count)
+                             : run_launches(p, (size_t)ph.launch_b_first, (size_t)ph.launch_b_count);
     if (rc) return rc;
-    if (k + 1 == (int)p->H.phases.size()) {
+    const bool last = k + 1 == (int)p->H.phases.size() && (part == 1 || ph.launch_b_count == 0);
+    if (last) {
         CK(cudaEventRecord(p->ev[1], p->stream));
         p->factored = true;
     }

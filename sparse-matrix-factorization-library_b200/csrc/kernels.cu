@@ -402,7 +402,7 @@ __global__ void __launch_bounds__(WARPS_M *WARPS_N * 32)
     // ---- which tile -------------------------------------------------------------------------------------------
     int ti, tj;
     {
-        const int t = (int)blockIdx.x - op.tile0;
+        const int t = ((int)blockIdx.x - op.tile0) * op.tile_mod + op.tile_rem;      // multi-GPU: this rank's share of the tiles
         const int nj = (N + BN - 1) / BN;
         if (op.flags & G_LOWER) {
             const int tri = nj * (nj + 1) / 2;

@@ -49,7 +49,7 @@ struct PanelEmitter {
         if (M <= 0 || N <= 0 || K <= 0) return;
         GemmOp g{};
         g.a_off = a; g.b_off = b; g.c_off = c; g.lda = g.ldb = g.ldc = sn.ld;
-        g.M = M; g.N = N; g.K = K; g.flags = flags;
+        g.M = M; g.N = N; g.K = K; g.flags = flags; g.tile_mod = 1; g.tile_rem = 0;
         slots[slot].gemm.push_back(g);
     }
     void trsm(int slot, i64 d, int w, i64 b_off, int nvec, int es, int vs, int flags) {
@@ -323,36 +323,50 @@ int build_plan(const Symbolic &S, const PlanParams &prm, HostPlan &P, int rank, 
         ph.level = lev;
         ph.reduce_first = (int32_t)P.reduces.size();
         ph.launch_first = (int32_t)P.launches.size();
+        ph.bcast_first = (int32_t)P.bcasts.size();
+        std::vector<GemmOp> scatter_dist;           // this rank's share of the Schur updates of shared fronts
         for (i64 s : by_level[lev]) {
             const SnodeDev &d = P.snode[s];
-            if (P.group_hi[s] - P.group_lo[s] > 1)      // the same list on every rank; a rank outside [lo,hi) skips the step
-                P.reduces.push_back(ReduceStep{d.xoff, (i64)d.ld * d.nscol, P.owner[s], P.group_lo[s], P.group_hi[s]});
+            const int m = d.nsrow - d.nscol;
+            const int glo = P.group_lo[s], ghi = P.group_hi[s];
+            const bool shared = ghi - glo > 1;
+            if (shared)      // the same list on every rank; a rank outside [lo,hi) skips the step
+                P.reduces.push_back(ReduceStep{d.xoff, (i64)d.ld * d.nscol, P.owner[s], glo, ghi});
+            // Schur update of a shared front: the owner broadcasts the factored panel to its group and every rank of
+            // the group computes 1/G of the update tiles into its own image of the ancestors (summed later anyway)
+            const bool dist = shared && m >= prm.dist_scatter_min_m;
+            auto scatter_ops = [&](std::vector<GemmOp> &out, int mod, int rem) {
+                if (m <= 0) return;
+                GemmOp g{};
+                g.lda = g.ldb = d.ld; g.ldc = 0; g.M = g.N = m; g.K = d.nscol;
+                g.meta = d.lsip + d.nscol;
+                g.tile_mod = mod; g.tile_rem = rem;
+                if (!lu) {
+                    g.a_off = g.b_off = d.xoff + d.nscol;
+                    g.flags = G_LOWER | G_SCATTER;
+                    out.push_back(g);
+                } else {
+                    g.a_off = d.xoff + d.nscol; g.b_off = d.xoff + d.nsrow;      // L21 * (U12^T)^T, rows >= seg begin
+                    g.flags = G_SCATTER | G_LIM_SEGB;
+                    out.push_back(g);
+                    g.a_off = d.xoff + d.nsrow; g.b_off = d.xoff + d.nscol;      // U12^T * L21^T, rows >= seg end
+                    g.flags = G_SCATTER | G_LIM_SEGE;
+                    out.push_back(g);
+                }
+            };
+            if (dist) {
+                P.bcasts.push_back(ReduceStep{d.xoff, (i64)d.ld * d.nscol, P.owner[s], glo, ghi});
+                if (rank >= glo && rank < ghi) scatter_ops(scatter_dist, ghi - glo, rank - glo);
+            }
             if (!mine(s)) continue;
             const i64 pb = panel_bytes(d);
             int c = -1;
             if (d.nsrow - d.nscol <= prm.small_max_m)
                 for (int k = 0; k < 4; ++k) if (pb <= small_limits[k]) { c = k; break; }
-            if (c >= 0) { cls[c].push_back(s); ++P.nsmall; continue; }
+            if (c >= 0 && !dist) { cls[c].push_back(s); ++P.nsmall; continue; }
             ++P.nlarge;
             PanelEmitter(d, lu, widths, slots).run();
-            const int m = d.nsrow - d.nscol;
-            if (m > 0) {
-                GemmOp g{};
-                g.lda = g.ldb = d.ld; g.ldc = 0; g.M = g.N = m; g.K = d.nscol;
-                g.meta = d.lsip + d.nscol;
-                if (!lu) {
-                    g.a_off = g.b_off = d.xoff + d.nscol;
-                    g.flags = G_LOWER | G_SCATTER;
-                    scatter.push_back(g);
-                } else {
-                    g.a_off = d.xoff + d.nscol; g.b_off = d.xoff + d.nsrow;      // L21 * (U12^T)^T, rows >= seg begin
-                    g.flags = G_SCATTER | G_LIM_SEGB;
-                    scatter.push_back(g);
-                    g.a_off = d.xoff + d.nsrow; g.b_off = d.xoff + d.nscol;      // U12^T * L21^T, rows >= seg end
-                    g.flags = G_SCATTER | G_LIM_SEGE;
-                    scatter.push_back(g);
-                }
-            }
+            if (!dist) scatter_ops(scatter, 1, 0);
         }
         for (int c = 0; c < 4; ++c) {
             if (cls[c].empty()) continue;
@@ -383,7 +397,7 @@ int build_plan(const Symbolic &S, const PlanParams &prm, HostPlan &P, int rank, 
                     const bool big = g.M >= prm.gemm128_min_m && g.N > 64;
                     if (big != (pass == 0)) continue;
                     g.tile0 = (int32_t)tiles;
-                    tiles += gemm_tiles(g.M, g.N, B, (g.flags & G_LOWER) != 0);
+                    tiles += share_of_tiles(gemm_tiles(g.M, g.N, B, (g.flags & G_LOWER) != 0), g.tile_mod, g.tile_rem);
                     P.gemm_ops.push_back(g);
                 }
                 L.count = (int32_t)P.gemm_ops.size() - L.first;
@@ -424,6 +438,10 @@ int build_plan(const Symbolic &S, const PlanParams &prm, HostPlan &P, int rank, 
         if (!scatter.empty()) emit_gemm(scatter, -1);
         ph.reduce_count = (int32_t)P.reduces.size() - ph.reduce_first;
         ph.launch_count = (int32_t)P.launches.size() - ph.launch_first;
+        ph.bcast_count = (int32_t)P.bcasts.size() - ph.bcast_first;
+        ph.launch_b_first = (int32_t)P.launches.size();
+        if (!scatter_dist.empty()) emit_gemm(scatter_dist, -1);
+        ph.launch_b_count = (int32_t)P.launches.size() - ph.launch_b_first;
         P.phases.push_back(ph);
     }
 

@@ -19,6 +19,7 @@ struct PlanParams {
     int small_b_bytes = 49152;   //                              : 256-thread CTA
     int small_max_m = 160;       // ... and only if the update (m x m) is small enough for one CTA
     int gemm128_min_m = 192;     // GEMM ops with at least this many rows use 128x128 tiles, others 64x64
+    int dist_scatter_min_m = 512;// multi-GPU: Schur updates of shared fronts with at least this many rows are split over the group
 };
 
 struct HostPlan {
@@ -54,6 +55,7 @@ struct HostPlan {
     std::vector<int32_t> group_lo, group_hi;// ranks [lo,hi) that hold descendants of the supernode (hi-lo > 1: "shared")
     double local_flops = 0.0;               // flops of the supernodes this rank owns
     std::vector<ReduceStep> reduces;        // sums of partial panel images into the owner, grouped by phase
+    std::vector<ReduceStep> bcasts;         // factored shared panels sent from the owner to its group, grouped by phase
     std::vector<Phase> phases;              // one per etree level: reduce steps first, then the level's launches
 };
 
@@ -61,6 +63,24 @@ struct HostPlan {
 int build_plan(const Symbolic &S, const PlanParams &prm, HostPlan &P, int rank = 0, int world = 1);
 
 // tile geometry shared by builder, kernels and the CPU interpreter
+// tiles of an op that rank-share (mod, rem) computes
+inline i64 share_of_tiles(i64 total, int mod, int rem) { return total > rem ? (total - rem + mod - 1) / mod : 0; }
+
+// tile index -> (block row, block column), the enumeration k_gemm decodes (lower ops list only tiles on/below the diagonal)
+inline void decode_tile(i64 t, int M, int N, int B, bool lower, int &ti, int &tj) {
+    const i64 nj = (N + B - 1) / B;
+    if (!lower) { ti = (int)(t / nj); tj = (int)(t - (i64)ti * nj); return; }
+    const i64 tri = nj * (nj + 1) / 2;
+    if (t < tri) {
+        i64 r = 0;
+        while ((r + 1) * (r + 2) / 2 <= t) ++r;
+        ti = (int)r; tj = (int)(t - r * (r + 1) / 2);
+    } else {
+        const i64 q = t - tri;
+        ti = (int)(nj + q / nj); tj = (int)(q % nj);
+    }
+}
+
 inline i64 gemm_tiles(int M, int N, int B, bool lower) {
     const i64 ni = (M + B - 1) / B, nj = (N + B - 1) / B;
     if (!lower) return ni * nj;

@@ -35,8 +35,9 @@ struct GemmOp {
     int32_t lda, ldb, ldc;
     int32_t M, N, K;
     int32_t flags;
-    int32_t tile0;                 // index of this op's first tile inside its launch
+    int32_t tile0;                 // index of this op's first CTA inside its launch
     int64_t meta;                  // scatter: index of off-diagonal row 0 of the source supernode in the per-row tables
+    int32_t tile_mod, tile_rem;    // multi-GPU: this rank computes the tiles t with t % tile_mod == tile_rem (1, 0 = all)
 };
 
 // ---- triangular solves with one nb x nb diagonal block ------------------------------------------------------
@@ -99,10 +100,14 @@ struct ReduceStep {
     int32_t lo, hi;  // contributing ranks [lo, hi)
 };
 
+// Phase = one etree level:  reduce steps -> launches A (local fronts + the shared fronts this rank owns) ->
+// broadcasts of the shared fronts factorized in A -> launches B (this rank's share of their Schur-update tiles).
 struct Phase {
     int32_t level;
     int32_t reduce_first, reduce_count;
-    int32_t launch_first, launch_count;
+    int32_t launch_first, launch_count;      // A
+    int32_t bcast_first, bcast_count;        // entries of HostPlan::bcasts (same ReduceStep record: root sends)
+    int32_t launch_b_first, launch_b_count;  // B
     int32_t pad;
 };
 

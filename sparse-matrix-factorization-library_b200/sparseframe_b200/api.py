@@ -139,10 +139,16 @@ class Plan:
         return float(_capi.lib().sfb200_plan_double(self._h, name.encode()))
 
     def phase_info(self, k):
-        out = np.zeros(5, dtype=np.int64)
+        out = np.zeros(9, dtype=np.int64)
         _capi.lib().sfb200_plan_phase_info(self._h, int(k), out.ctypes.data)
         return dict(reduce_first=int(out[0]), reduce_count=int(out[1]), launch_first=int(out[2]),
-                    launch_count=int(out[3]), level=int(out[4]))
+                    launch_count=int(out[3]), level=int(out[4]), bcast_first=int(out[5]), bcast_count=int(out[6]),
+                    launch_b_first=int(out[7]), launch_b_count=int(out[8]))
+
+    def bcast_info(self, i):
+        out = np.zeros(5, dtype=np.int64)
+        _capi.lib().sfb200_plan_bcast_info(self._h, int(i), out.ctypes.data)
+        return dict(offset=int(out[0]), count=int(out[1]), root=int(out[2]), lo=int(out[3]), hi=int(out[4]))
 
     def reduce_info(self, i):
         out = np.zeros(5, dtype=np.int64)
@@ -167,8 +173,8 @@ class Plan:
         if rc != 0:
             raise RuntimeError("sfb200_phase_begin failed (%d): %s" % (rc, _capi.last_error()))
 
-    def phase_run(self, k):
-        rc = _capi.lib().sfb200_phase_run(self._h, int(k))
+    def phase_run(self, k, part=0):
+        rc = _capi.lib().sfb200_phase_run(self._h, int(k), int(part))
         if rc != 0:
             raise RuntimeError("sfb200_phase_run failed (%d): %s" % (rc, _capi.last_error()))
 

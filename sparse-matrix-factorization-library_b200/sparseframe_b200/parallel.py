@@ -35,19 +35,22 @@ class DeviceBackend:
         self.image = torch.as_tensor(_CudaView(plan.factor_ptr(), plan.int("xsize_padded")), device=d_lx.device)
         self.phases = [plan.phase_info(k) for k in range(self.nphases)]
         self.reduces = [plan.reduce_info(i) for i in range(plan.int("nreduces"))]
+        self.bcasts = [plan.bcast_info(i) for i in range(plan.int("nbcasts"))]
 
     def begin(self):
         self.plan.phase_begin(self.d_lx.data_ptr(), self.d_ux.data_ptr() if self.d_ux is not None else 0)
 
-    def run_phase(self, k):
-        self.plan.phase_run(k)
+    def run_phase(self, k, part=0):
+        self.plan.phase_run(k, part)
 
     def finish(self):
         self.plan.sync()
 
 
 class PartitionedFactorization:
-    """Phase loop: for every etree level, first the reduce steps of its shared panels, then the level's launches."""
+    """Phase loop, one phase per etree level: reduce the partial images of the level's shared panels into their owners,
+    run the level's launches (A), broadcast the shared panels that were just factorized to their groups, run every rank's
+    share of their Schur-update tiles (B)."""
 
     def __init__(self, backend, dist=None):
         self.b = backend
@@ -55,17 +58,19 @@ class PartitionedFactorization:
         self.groups = {}
         if dist is not None and backend.world > 1:
             # groups must be created by every rank, in the same order: the reduce list is identical on all ranks
-            for r in backend.reduces:
+            for r in list(backend.reduces) + list(backend.bcasts):
                 key = (r["lo"], r["hi"])
                 if key not in self.groups:
                     full = key == (0, backend.world)
                     self.groups[key] = None if full else dist.new_group(ranks=list(range(key[0], key[1])))
         self.reduced_bytes = 0
+        self.bcast_bytes = 0
 
     def factorize(self):
         b = self.b
         b.begin()
         self.reduced_bytes = 0
+        self.bcast_bytes = 0
         for k in range(b.nphases):
             ph = b.phases[k]
             for i in range(ph["reduce_first"], ph["reduce_first"] + ph["reduce_count"]):
@@ -74,7 +79,17 @@ class PartitionedFactorization:
                     view = b.image[r["offset"]:r["offset"] + r["count"]]
                     self.dist.reduce(view, dst=r["root"], op=self.dist.ReduceOp.SUM, group=self.groups[(r["lo"], r["hi"])])
                     self.reduced_bytes += 8 * r["count"]
-            b.run_phase(k)
+            b.run_phase(k, 0)
+            # factored shared panels go from their owner to the group, then everybody computes its share of their
+            # Schur-update tiles (part B of the phase)
+            for i in range(ph["bcast_first"], ph["bcast_first"] + ph["bcast_count"]):
+                r = b.bcasts[i]
+                if b.world > 1 and r["lo"] <= b.rank < r["hi"]:
+                    view = b.image[r["offset"]:r["offset"] + r["count"]]
+                    self.dist.broadcast(view, src=r["root"], group=self.groups[(r["lo"], r["hi"])])
+                    self.bcast_bytes += 8 * r["count"]
+            if ph["launch_b_count"] > 0:
+                b.run_phase(k, 1)
         b.finish()
 
 

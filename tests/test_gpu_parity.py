@@ -214,12 +214,14 @@ def test_partitioned_plans_emulated_on_one_gpu(gen, g, kind, world):
     step and the reduce steps are done with torch adds -- the same order of operations torch.distributed gives."""
     import torch
     from sparseframe_b200.parallel import DeviceBackend, owned_mask
+    os.environ["SFB200_DIST_MIN_M"] = "48"       # small fronts too: exercise the broadcast + tile-share path
     A, _ = build_matrix(gen, g)
     S = sf.analyze(A, kind)
     split = kind == "lu" and S.int("symmetric") == 0
     d_lx = torch.from_numpy(S.array("Lx")).cuda()
     d_ux = torch.from_numpy(S.array("Ux")).cuda() if split else None
     plans = [sf.Plan(S, rank=r, world=world) for r in range(world)]
+    os.environ.pop("SFB200_DIST_MIN_M", None)
     stream = torch.cuda.current_stream()
     for p in plans:
         p.set_stream(stream.cuda_stream)
@@ -227,7 +229,7 @@ def test_partitioned_plans_emulated_on_one_gpu(gen, g, kind, world):
     assert sum(p.double("local_flops") for p in plans) == pytest.approx(S.flops, rel=1e-12)
     for b in backs:
         b.begin()
-    nred = 0
+    nred = nbc = 0
     for k in range(backs[0].nphases):
         ph = backs[0].phases[k]
         for i in range(ph["reduce_first"], ph["reduce_first"] + ph["reduce_count"]):
@@ -238,9 +240,19 @@ def test_partitioned_plans_emulated_on_one_gpu(gen, g, kind, world):
                     backs[r["root"]].image[sl] += backs[q].image[sl]
             nred += 1
         for b in backs:
-            b.run_phase(k)
+            b.run_phase(k, 0)
+        for i in range(ph["bcast_first"], ph["bcast_first"] + ph["bcast_count"]):
+            r = backs[0].bcasts[i]
+            sl = slice(r["offset"], r["offset"] + r["count"])
+            for q in range(r["lo"], r["hi"]):
+                if q != r["root"]:
+                    backs[q].image[sl] = backs[r["root"]].image[sl]
+            nbc += 1
+        for b in backs:
+            b.run_phase(k, 1)
     for b in backs:
         b.finish()
+    assert nbc > 0, "the test should exercise the distributed Schur updates"
     assert nred > 0
     Lsxp = S.array("Lsxp")
     merged = np.zeros(S.int("xsize"))

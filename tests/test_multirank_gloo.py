@@ -27,6 +27,7 @@ def _worker(rank, world, port, gen, g, kind, devslot, out_path):
     from sparseframe_b200.parallel import PartitionedFactorization
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
+    os.environ["SFCHECK_DIST_MIN_M"] = "8"       # tiny fronts too: exercise the broadcast + tile-share path
     dist.init_process_group("gloo", rank=rank, world_size=world)
     A = sf.compress(*sf.matrices.generate(gen, g))
     backend = sforacle.CheckBackend(kind, A, devslot, rank, world)
@@ -35,19 +36,19 @@ def _worker(rank, world, port, gen, g, kind, devslot, out_path):
     assert backend.bad == 0
     owned = torch.from_numpy(backend.pack_owned())      # zeros outside the owned panels -> SUM = union
     dist.reduce(owned, dst=0, op=dist.ReduceOp.SUM)
-    stats = torch.tensor([backend.double("local_flops"), float(pf.reduced_bytes)], dtype=torch.float64)
-    gathered = [torch.zeros(2, dtype=torch.float64) for _ in range(world)] if rank == 0 else None
+    stats = torch.tensor([backend.double("local_flops"), float(pf.reduced_bytes), float(pf.bcast_bytes)], dtype=torch.float64)
+    gathered = [torch.zeros(3, dtype=torch.float64) for _ in range(world)] if rank == 0 else None
     dist.gather(stats, gathered, dst=0)
     if rank == 0:
         np.savez(out_path, lsx=owned.numpy(), stats=torch.stack(gathered).numpy(), total=backend.double("flops"),
-                 nreduces=backend.int("nreduces"))
+                 nreduces=backend.int("nreduces"), nbcasts=backend.int("nbcasts"))
     dist.barrier()
     dist.destroy_process_group()
     backend.close()
 
 
 @pytest.mark.parametrize("world", [2, 3])
-@pytest.mark.parametrize("name", ["lap3d_8_chol", "cd3d_8_lu", "lap2d_20_chol"])
+@pytest.mark.parametrize("name", ["lap3d_10_chol_slot", "cd3d_8_lu", "lap2d_20_chol"])
 def test_partitioned_factorization_over_gloo(world, name, tmp_path):
     import torch.multiprocessing as mp
     sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -65,6 +66,10 @@ def test_partitioned_factorization_over_gloo(world, name, tmp_path):
     # every flop is owned by exactly one rank, and something really had to be exchanged
     assert res["stats"][:, 0].sum() == pytest.approx(float(res["total"]), rel=1e-12)
     assert int(res["nreduces"]) > 0 and res["stats"][:, 1].sum() > 0
+    # shared fronts with off-diagonal rows are broadcast and their Schur update is split over the group
+    assert (res["stats"][:, 2].sum() > 0) == (int(res["nbcasts"]) > 0)
+    if name == "lap3d_10_chol_slot":
+        assert int(res["nbcasts"]) > 0, "this case must exercise the distributed Schur updates"
 
 
 def test_partition_simulated_up_to_8_ranks():
