@@ -314,13 +314,14 @@ def main():
         dom = max(prof, key=lambda k: prof[k]["ms"])
         d = prof[dom]
         ach = d["flops"] / (d["ms"] * 1e-3) / 1e12
-        roof = {"kernel": dom, "bound": "tensor", "achieved": ach, "peak": dmma_peak, "unit": "TFLOP/s",
+        roof = {"kernel": dom + (" (rank 0's share of the partitioned schedule)" if world > 1 else ""), "bound": "tensor", "achieved": ach, "peak": dmma_peak, "unit": "TFLOP/s",
                 "frac": ach / dmma_peak if dmma_peak > 0 else None, "traffic": None,
                 "peak_source": "FP64 DMMA probe in this run (sfb200_probe_fp64_peak); MEASURED_PEAKS.json has no FP64 entry; "
                                "DFMA vector pipe probe %.2f TFLOP/s" % dfma_peak,
                 "launches": d["launches"], "avg_launch_ms": d["ms"] / d["launches"], "share_of_step": d["ms"] / total_ms,
                 "whole_step": {"achieved": flops / (ms_total / args.steps * 1e-3) / 1e12,
-                               "frac": flops / (ms_total / args.steps * 1e-3) / 1e12 / dmma_peak if dmma_peak > 0 else None},
+                               "peak": dmma_peak * world,
+                               "frac": flops / (ms_total / args.steps * 1e-3) / 1e12 / (dmma_peak * world) if dmma_peak > 0 else None},
                 "kernels": {k: {"ms": round(v["ms"], 3), "launches": v["launches"],
                                 "tflops": v["flops"] / (v["ms"] * 1e-3) / 1e12,
                                 "gbs_algorithmic": v["bytes"] / (v["ms"] * 1e-3) / 1e9} for k, v in prof.items()},

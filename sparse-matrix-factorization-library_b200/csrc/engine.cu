@@ -575,8 +575,10 @@ int sfb200_plan_profile(sfb200_plan *p) {
                 const bool half = (g.flags & G_LOWER) != 0;
                 const double outputs = half ? (double)g.N * (g.N + 1) / 2 + (double)(g.M - g.N) * g.N
                                             : ((g.flags & (G_LIM_SEGB | G_LIM_SEGE)) ? 0.5 * g.M * (double)g.N : (double)g.M * g.N);
-                fl += 2.0 * g.K * outputs;
-                by += 8.0 * ((double)g.M * g.K + (double)g.N * g.K) + 16.0 * outputs;
+                // multi-GPU: only this rank's share of the op's tiles is computed here
+                const double share = g.tile_mod > 1 ? 1.0 / g.tile_mod : 1.0;
+                fl += 2.0 * g.K * outputs * share;
+                by += (8.0 * ((double)g.M * g.K + (double)g.N * g.K) + 16.0 * outputs) * share;
             } else if (k == L_TRSM) {
                 const TrsmOp &t = H.trsm_ops[L.first + q];
                 fl += (double)t.nvec * t.nb * t.nb;
