@@ -172,10 +172,10 @@ long run_launches(const HostPlan &P, double *X, int first, int count) {
             case L_TRSM:
                 for (int k = 0; k < L.count; ++k) trsm(X, P.trsm_ops[L.first + k]);
                 break;
-            case L_GEMM128: case L_GEMM64: {
+            case L_GEMM128: case L_GEMM64: case L_GEMM128WS: {
                 // the tile prefix must be consistent with the geometry the kernels decode
                 i64 tiles = 0;
-                const int B = L.kind == L_GEMM128 ? 128 : 64;
+                const int B = L.kind == L_GEMM64 ? 64 : 128;
                 for (int k = 0; k < L.count; ++k) {
                     const GemmOp &g = P.gemm_ops[L.first + k];
                     if (g.tile0 != tiles) return -101;

@@ -12,7 +12,7 @@ plan.factorize(S.array("Lx"), S.array("Ux") if (kind == "lu") else None, downloa
 plan.profile()
 rows = plan.profile_launches()
 peak = 37.0e12
-names = {0: "smallA", 1: "smallB", 2: "potrf", 3: "getrf", 4: "trsm", 5: "gemm128", 6: "gemm64"}
+names = {0: "smallA", 1: "smallB", 2: "potrf", 3: "getrf", 4: "trsm", 5: "gemm128", 6: "gemm64", 7: "gemmWS"}
 print("total profiled ms %.2f" % rows[:, 4].sum())
 # per level summary
 for lev in sorted(set(rows[:, 1].astype(int))):
@@ -23,7 +23,7 @@ for lev in sorted(set(rows[:, 1].astype(int))):
         if len(rk): line += " %s %d launches %.2f ms (%.1f TF/s)" % (names[k], len(rk), rk[:, 4].sum(), rk[:, 5].sum() / max(rk[:, 4].sum(), 1e-9) / 1e9)
     print(line)
 # gemm128 launches by K class
-g = rows[rows[:, 0] == 5]
+g = rows[(rows[:, 0] == 5) | (rows[:, 0] == 7)]
 for lo, hi in ((0, 65), (65, 257), (257, 1025), (1025, 1e9)):
     sel = (g[:, 6] >= lo) & (g[:, 6] < hi)
     if sel.any():

@@ -85,6 +85,7 @@ int issue_launch(sfb200_plan *p, const Launch &L) {
         case L_TRSM: launch_trsm(p->D, p->d_trsm + L.first, L.count, L.grid, st); break;
         case L_GEMM128: launch_gemm(p->D, p->d_gemm + L.first, L.count, L.grid, true, st); break;
         case L_GEMM64: launch_gemm(p->D, p->d_gemm + L.first, L.count, L.grid, false, st); break;
+        case L_GEMM128WS: launch_gemm_ws(p->D, p->d_gemm + L.first, L.count, L.grid, st); break;
         default: set_error("corrupt plan: unknown launch kind"); return SFB200_ERR_STATE;
     }
     return SFB200_OK;
@@ -179,6 +180,7 @@ int sfb200_plan_create_part(const sfb200_symbolic *s, int device, int rank, int 
     if (const char *e = getenv("SFB200_SMALL_B")) prm.small_b_bytes = atoi(e);
     if (const char *e = getenv("SFB200_GEMM128_MIN")) prm.gemm128_min_m = atoi(e);
     if (const char *e = getenv("SFB200_DIST_MIN_M")) prm.dist_scatter_min_m = atoi(e);
+    if (const char *e = getenv("SFB200_GEMM_WS")) prm.use_ws = atoi(e);
     const int rc = build_plan(s->S, prm, p->H, rank, world);
     if (rc != 0) {
         delete p;
@@ -477,6 +479,7 @@ int factorize_streamed(sfb200_plan *p, double *Lsx, double *Lsx_dev_alias) {
         if (range.second > 0) launch_pack(p->d_X, Lsx_dev_alias, p->d_spack + range.first, range.second, p->copy_stream);
     }
     CK(cudaGetLastError());
+    CK(cudaEventRecord(p->ev[1], p->stream));            // end of the numeric work; the copy tail is only in the e2e time
     CK(cudaEventRecord(p->copy_done, p->copy_stream));
     CK(cudaStreamWaitEvent(p->stream, p->copy_done, 0));
     return SFB200_OK;
@@ -506,7 +509,6 @@ int sfb200_factorize(sfb200_plan *p, const double *Lx, const double *Ux, double 
         CK(cudaEventRecord(p->ev[0], p->stream));
         rc = factorize_streamed(p, Lsx, alias);
         if (rc) return rc;
-        CK(cudaEventRecord(p->ev[1], p->stream));
         p->factored = true;
     } else {
         rc = sfb200_factorize_device(p, p->d_lx, p->d_ux);
@@ -569,7 +571,7 @@ int sfb200_plan_profile(sfb200_plan *p) {
         p->prof_launches[k] += 1;
         double fl = 0, by = 0;
         for (int q = 0; q < L.count; ++q) {
-            if (k == L_GEMM128 || k == L_GEMM64) {
+            if (k == L_GEMM128 || k == L_GEMM64 || k == L_GEMM128WS) {
                 const GemmOp &g = H.gemm_ops[L.first + q];
                 // LU scatter ops are enumerated as full rectangles but only about half of each is wanted
                 const bool half = (g.flags & G_LOWER) != 0;
@@ -626,7 +628,7 @@ int sfb200_plan_profile_launch(const sfb200_plan *p, int i, double *out) {
     out[0] = L.kind; out[1] = L.level; out[2] = L.grid; out[3] = L.count;
     out[4] = p->prof_launch_ms[i]; out[5] = p->prof_launch_flops[i];
     double kmax = 0, kmin = 1e30;
-    if (L.kind == L_GEMM128 || L.kind == L_GEMM64)
+    if (L.kind == L_GEMM128 || L.kind == L_GEMM64 || L.kind == L_GEMM128WS)
         for (int q = 0; q < L.count; ++q) { const double k = p->H.gemm_ops[L.first + q].K; kmax = std::max(kmax, k); kmin = std::min(kmin, k); }
     out[6] = kmax; out[7] = kmin < 1e29 ? kmin : 0;
     return SFB200_OK;

@@ -643,6 +643,250 @@ __global__ void __launch_bounds__(WARPS_M *WARPS_N * 32)
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Warp-specialized persistent DMMA GEMM (128 x 128 tiles).
+//
+//   warp 0 of the producer warpgroup : stages operands with cp.async.bulk (the TMA engine: SASS UBLKCP), one 1-KB bulk
+//       copy per k-row and operand, completion counted in bytes on a "full" mbarrier.  No per-thread address math,
+//       no LDGSTS, no CTA-wide barrier anywhere in the main loop.
+//   8 consumer warps (2 x 4, 64 x 32 register tiles) : wait on "full", DMMA from shared memory, release the stage on an
+//       "empty" mbarrier; epilogue (in-place update or fused relative-index scatter) straight from registers.
+//   setmaxnreg moves the producer group's registers to the consumers.
+//   Persistent: a CTA walks the launch's tile list with a stride of gridDim.x, and the stage ring keeps running across
+//   tiles, so the producer is already filling the next tile's stages while the consumers are in the epilogue.
+//
+// Bulk copies need 16-byte aligned global addresses: when a tile's first row sits on an odd element offset the copy
+// starts one element earlier and the consumers read the tile with a one-row shift (the shared tile has 4 spare rows).
+// Rows read beyond the op's extent are finite garbage or zeros and only feed outputs the epilogue masks; k-rows beyond K
+// are zero-filled by the producer warp.
+// ---------------------------------------------------------------------------------------------------------------
+namespace ws {
+constexpr int BM = 128, BN = 128, BK = 16, STAGES = 4, SA = 132;
+constexpr int STAGE_DOUBLES = 2 * BK * SA;
+constexpr int SMEM_BYTES = STAGES * STAGE_DOUBLES * 8 + 2 * STAGES * 8 + 64;
+constexpr int NT = 384;
+
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *b, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(b)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *b) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(b)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *b, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *b, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra.uni WAIT_DONE;\n"
+        "bra.uni WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(smem_u32(b)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+struct TileInfo {
+    GemmOp op;
+    int row0, col0;
+    bool skip;
+};
+
+__device__ __forceinline__ TileInfo locate_tile(const PlanDev &P, const GemmOp *ops, int nops, int cta_tile) {
+    TileInfo ti;
+    ti.op = ops[find_op(ops, nops, cta_tile)];
+    const GemmOp &op = ti.op;
+    const int t = (cta_tile - op.tile0) * op.tile_mod + op.tile_rem;
+    const int nj = (op.N + BN - 1) / BN;
+    int bi, bj;
+    if (op.flags & G_LOWER) {
+        const int tri = nj * (nj + 1) / 2;
+        if (t < tri) {
+            bi = (int)((sqrt(8.0 * (double)t + 1.0) - 1.0) * 0.5);
+            while (bi * (bi + 1) / 2 > t) --bi;
+            while ((bi + 1) * (bi + 2) / 2 <= t) ++bi;
+            bj = t - bi * (bi + 1) / 2;
+        } else {
+            const int r = t - tri;
+            bi = nj + r / nj;
+            bj = r - (r / nj) * nj;
+        }
+    } else {
+        bi = t / nj;
+        bj = t - bi * nj;
+    }
+    ti.row0 = bi * BM;
+    ti.col0 = bj * BN;
+    ti.skip = false;
+    if (op.flags & (G_LIM_SEGB | G_LIM_SEGE)) {       // LU scatter ops are enumerated as full rectangles
+        const int lim0 = (op.flags & G_LIM_SEGB) ? P.upd_segb[op.meta + ti.col0] : P.upd_sege[op.meta + ti.col0];
+        ti.skip = min(ti.row0 + BM, op.M) - 1 < lim0;
+    }
+    return ti;
+}
+}  // namespace ws
+
+__global__ void __launch_bounds__(ws::NT, 1) k_gemm_ws(PlanDev P, const GemmOp *__restrict__ ops, int nops, int total_tiles) {
+    using namespace ws;
+    extern __shared__ __align__(128) double smem_ws[];
+    double *smem = smem_ws;
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem + STAGES * STAGE_DOUBLES);
+    uint64_t *empty = full + STAGES;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 8); }
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    __syncthreads();
+
+    if (warp < 4) {
+        // =========================================== producer warpgroup ===========================================
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 40;\n");
+        if (warp != 0) return;
+        int stage = 0;
+        unsigned phase = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            const TileInfo ti = locate_tile(P, ops, nops, tile);
+            if (ti.skip) continue;
+            const GemmOp &op = ti.op;
+            const int mrem = min(BM, op.M - ti.row0), nrem = min(BN, op.N - ti.col0);
+            const double *Ag = P.X + op.a_off + ti.row0, *Bg = P.X + op.b_off + ti.col0;
+            const int sha = (int)((op.a_off + ti.row0) & 1), shb = (int)((op.b_off + ti.col0) & 1);
+            const unsigned bytes_a = (unsigned)(((mrem + sha + 1) & ~1) * 8), bytes_b = (unsigned)(((nrem + shb + 1) & ~1) * 8);
+            // lanes 0-15 stage the 16 k-rows of A, lanes 16-31 those of B: one bulk copy per lane and stage
+            const int k = lane & 15;
+            const bool is_b = lane >= 16;
+            const double *src = (is_b ? Bg - shb + (int64_t)k * op.ldb : Ag - sha + (int64_t)k * op.lda);
+            const int64_t step = (int64_t)BK * (is_b ? op.ldb : op.lda);
+            const unsigned bytes = is_b ? bytes_b : bytes_a;
+            const int KT = (op.K + BK - 1) / BK;
+            for (int kt = 0; kt < KT; ++kt) {
+                mbar_wait(empty + stage, phase ^ 1);
+                double *dst = smem + stage * STAGE_DOUBLES + (is_b ? BK * SA : 0) + k * SA;
+                const int krem = op.K - kt * BK;
+                if (k < krem) {
+                    bulk_g2s(dst, src, bytes, full + stage);
+                } else {
+                    for (int e = 0; e < SA; ++e) dst[e] = 0.0;      // k-rows beyond K must contribute nothing
+                }
+                src += step;
+                __syncwarp();
+                if (lane == 0) mbar_arrive_expect_tx(full + stage, (unsigned)min(krem, BK) * (bytes_a + bytes_b));
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+        return;
+    }
+
+    // ================================================ consumer warps ================================================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;\n");
+    const int cw = warp - 4;
+    const int wm0 = (cw % 2) * 64, wn0 = (cw / 2) * 32;
+    const int g = lane >> 2, t4 = lane & 3;
+    constexpr int FM = 8, FN = 4;
+    int stage = 0;
+    unsigned phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const TileInfo ti = locate_tile(P, ops, nops, tile);
+        if (ti.skip) continue;
+        const GemmOp &op = ti.op;
+        const int M = op.M, N = op.N, row0 = ti.row0, col0 = ti.col0;
+        const int sha = (int)((op.a_off + row0) & 1), shb = (int)((op.b_off + col0) & 1);
+        double acc[FM][FN][2];
+#pragma unroll
+        for (int i = 0; i < FM; ++i)
+#pragma unroll
+            for (int j = 0; j < FN; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+        const int KT = (op.K + BK - 1) / BK;
+        for (int kt = 0; kt < KT; ++kt) {
+            mbar_wait(full + stage, phase);
+            const double *As = smem + stage * STAGE_DOUBLES + sha + wm0 + g;
+            const double *Bs = smem + stage * STAGE_DOUBLES + BK * SA + shb + wn0 + g;
+#pragma unroll
+            for (int ks = 0; ks < BK; ks += 4) {
+                double af[FM], bf[FN];
+#pragma unroll
+                for (int i = 0; i < FM; ++i) af[i] = As[(ks + t4) * SA + 8 * i];
+#pragma unroll
+                for (int j = 0; j < FN; ++j) bf[j] = Bs[(ks + t4) * SA + 8 * j];
+#pragma unroll
+                for (int i = 0; i < FM; ++i)
+#pragma unroll
+                    for (int j = 0; j < FN; ++j) dmma(acc[i][j][0], acc[i][j][1], bf[j], af[i]);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(empty + stage);
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+
+        // ---- epilogue: thread holds C[row0 + wm0 + 8i + 2*t4 + {0,1}][col0 + wn0 + 8j + g] ---------------------
+        if (op.flags & G_SCATTER) {
+#pragma unroll
+            for (int j = 0; j < FN; ++j) {
+                const int c = col0 + wn0 + 8 * j + g;
+                if (c >= N) continue;
+                const int64_t q = op.meta + c;
+                int64_t col = P.upd_coloff[q];
+                const int64_t relb = P.upd_relbase[q];
+                int lim = c;
+                if (op.flags & G_LIM_SEGB) lim = P.upd_segb[q];
+                if (op.flags & G_LIM_SEGE) { lim = P.upd_sege[q]; col += P.upd_uoff[q]; }
+                double *dst = P.X + col;
+                const int32_t *rel = P.relmap + relb;
+#pragma unroll
+                for (int i = 0; i < FM; ++i) {
+                    const int r = row0 + wm0 + 8 * i + 2 * t4;
+                    if (r < M && r >= lim) atomicAdd(dst + rel[r], -acc[i][j][0]);
+                    if (r + 1 < M && r + 1 >= lim) atomicAdd(dst + rel[r + 1], -acc[i][j][1]);
+                }
+            }
+        } else {
+            double *Cg = P.X + op.c_off;
+            const bool lower = (op.flags & G_LOWER) != 0;
+            const bool vec = (((op.c_off | (int64_t)op.ldc) & 1) == 0);
+#pragma unroll
+            for (int j = 0; j < FN; ++j) {
+                const int c = col0 + wn0 + 8 * j + g;
+                if (c >= N) continue;
+                double *colp = Cg + (int64_t)c * op.ldc;
+                const int lim = lower ? c : 0;
+                double2 cv[FM];
+#pragma unroll
+                for (int i = 0; i < FM; ++i) {
+                    const int r = row0 + wm0 + 8 * i + 2 * t4;
+                    cv[i] = make_double2(0.0, 0.0);
+                    if (r + 1 < M && r + 1 >= lim) {
+                        if (vec) cv[i] = *reinterpret_cast<const double2 *>(colp + r);
+                        else { cv[i].x = colp[r]; cv[i].y = colp[r + 1]; }
+                    } else if (r < M && r >= lim) {
+                        cv[i].x = colp[r];
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < FM; ++i) {
+                    const int r = row0 + wm0 + 8 * i + 2 * t4;
+                    const bool w0 = r < M && r >= lim, w1 = r + 1 < M && r + 1 >= lim;
+                    const double v0 = cv[i].x - acc[i][j][0], v1 = cv[i].y - acc[i][j][1];
+                    if (w0 && w1 && vec) *reinterpret_cast<double2 *>(colp + r) = make_double2(v0, v1);
+                    else {
+                        if (w0) colp[r] = v0;
+                        if (w1) colp[r + 1] = v1;
+                    }
+                }
+            }
+        }
+    }
+}
+
 using Gemm128 = GemmCfg<128, 128, 2, 4, 3, 16>;
 using Gemm128w16 = GemmCfg<128, 128, 4, 4, 3, 16>;
 using Gemm128k32 = GemmCfg<128, 128, 2, 4, 3, 32>;
@@ -760,6 +1004,7 @@ cudaError_t kernels_init() {
     if ((e = gemm_optin<Gemm128k32, 128, 128, 2, 4, 3, 32>()) != cudaSuccess) return e;
     if ((e = gemm_optin<Gemm128w16k32, 128, 128, 4, 4, 3, 32>()) != cudaSuccess) return e;
     if ((e = gemm_optin<Gemm64, 64, 64, 2, 2, 4, 16>()) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(k_gemm_ws, cudaFuncAttributeMaxDynamicSharedMemorySize, ws::SMEM_BYTES)) != cudaSuccess) return e;
     e = cudaFuncSetAttribute(k_small<256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(k_small<256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
@@ -809,6 +1054,14 @@ void launch_gemm(const PlanDev &P, const GemmOp *ops, int count, int grid, bool 
         case 3: k_gemm<128, 128, 4, 4, 3, 32><<<grid, Gemm128w16k32::NT, Gemm128w16k32::SMEM_BYTES, st>>>(P, ops, count); break;
         default: k_gemm<128, 128, 2, 4, 3, 16><<<grid, Gemm128::NT, Gemm128::SMEM_BYTES, st>>>(P, ops, count); break;
     }
+}
+
+void launch_gemm_ws(const PlanDev &P, const GemmOp *ops, int count, int tiles, cudaStream_t st) {
+    if (count <= 0 || tiles <= 0) return;
+    static int sms = 0;
+    if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); if (sms <= 0) sms = 148; }
+    const int grid = tiles < sms ? tiles : sms;          // persistent: one CTA per SM walks the tile list
+    k_gemm_ws<<<grid, ws::NT, ws::SMEM_BYTES, st>>>(P, ops, count, tiles);
 }
 
 void launch_pack(const double *X, double *out, const PackTask *tasks, int count, cudaStream_t st) {

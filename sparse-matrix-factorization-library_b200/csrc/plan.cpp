@@ -385,17 +385,21 @@ int build_plan(const Symbolic &S, const PlanParams &prm, HostPlan &P, int rank, 
             // longest tiles first: the CTAs of a launch are dispatched in index order, so the deep-K ops must not be
             // the ones left running alone at the end of the launch
             std::stable_sort(ops.begin(), ops.end(), [](const GemmOp &a, const GemmOp &b) { return a.K > b.K; });
-            for (int pass = 0; pass < 2; ++pass) {       // pass 0: 128x128 tiles, pass 1: 64x64 tiles
-                const int B = pass == 0 ? 128 : 64;
+            for (int pass = 0; pass < 3; ++pass) {
+                // pass 0: 128x128 tiles, warp-specialized persistent kernel (every op whose B operand is row-major);
+                // pass 1: 128x128 tiles, classic kernel (k-major B: LU's U row blocks); pass 2: 64x64 tiles
+                const int B = pass < 2 ? 128 : 64;
                 Launch L{};
-                L.kind = pass == 0 ? L_GEMM128 : L_GEMM64;
+                L.kind = pass == 0 ? L_GEMM128WS : pass == 1 ? L_GEMM128 : L_GEMM64;
                 L.level = lev;
                 L.top_block = top_block;
                 L.first = (int32_t)P.gemm_ops.size();
                 i64 tiles = 0;
                 for (GemmOp g : ops) {
                     const bool big = g.M >= prm.gemm128_min_m && g.N > 64;
-                    if (big != (pass == 0)) continue;
+                    const bool ws_ok = prm.use_ws && !(g.flags & G_B_KMAJOR);
+                    const int want = !big ? 2 : (ws_ok ? 0 : 1);
+                    if (want != pass) continue;
                     g.tile0 = (int32_t)tiles;
                     tiles += share_of_tiles(gemm_tiles(g.M, g.N, B, (g.flags & G_LOWER) != 0), g.tile_mod, g.tile_rem);
                     P.gemm_ops.push_back(g);

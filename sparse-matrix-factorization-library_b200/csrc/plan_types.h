@@ -76,6 +76,7 @@ enum LaunchKind : int32_t {
     L_TRSM    = 4,
     L_GEMM128 = 5,   // 128x128 CTA tiles
     L_GEMM64  = 6,   // 64x64 CTA tiles
+    L_GEMM128WS = 7, // 128x128 tiles, persistent warp-specialized kernel: bulk-copy (TMA) producer warp + 8 DMMA consumer warps
 };
 
 struct Launch {
