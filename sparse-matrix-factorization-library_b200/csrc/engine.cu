@@ -37,6 +37,11 @@ struct sfb200_plan {
     PackTask *d_pack = nullptr;
     double *d_X = nullptr, *d_out = nullptr, *d_lx = nullptr, *d_ux = nullptr;
     int *d_status = nullptr;
+    // look-ahead: side stream for the REST part of the top-level trailing updates
+    cudaStream_t side_stream = nullptr;
+    cudaEvent_t ev_to_side = nullptr, ev_from_side = nullptr;
+    bool side_pending = false;
+    int spare_sms = 16;
     // streamed copy-out (host-buffer call with a page-locked Lsx): copy stream, per-level work lists
     cudaStream_t copy_stream = nullptr;
     std::vector<cudaEvent_t> copy_events;
@@ -75,8 +80,7 @@ int upload(sfb200_plan *p, T *&dptr, const std::vector<T> &h) {
     return SFB200_OK;
 }
 
-int issue_launch(sfb200_plan *p, const Launch &L) {
-    cudaStream_t st = p->stream;
+int issue_launch_on(sfb200_plan *p, const Launch &L, cudaStream_t st, int spare_sms) {
     switch (L.kind) {
         case L_SMALL_A: launch_small(p->D, p->d_small + L.first, L.count, L.smem, false, st); break;
         case L_SMALL_B: launch_small(p->D, p->d_small + L.first, L.count, L.smem, true, st); break;
@@ -85,8 +89,38 @@ int issue_launch(sfb200_plan *p, const Launch &L) {
         case L_TRSM: launch_trsm(p->D, p->d_trsm + L.first, L.count, L.grid, st); break;
         case L_GEMM128: launch_gemm(p->D, p->d_gemm + L.first, L.count, L.grid, true, st); break;
         case L_GEMM64: launch_gemm(p->D, p->d_gemm + L.first, L.count, L.grid, false, st); break;
-        case L_GEMM128WS: launch_gemm_ws(p->D, p->d_gemm + L.first, L.count, L.grid, st); break;
+        case L_GEMM128WS: launch_gemm_ws(p->D, p->d_gemm + L.first, L.count, L.grid, spare_sms, st); break;
         default: set_error("corrupt plan: unknown launch kind"); return SFB200_ERR_STATE;
+    }
+    return SFB200_OK;
+}
+
+// single-stream issue (profiling replays and the streamed copy-out keep everything on the main stream)
+int issue_launch(sfb200_plan *p, const Launch &L) { return issue_launch_on(p, L, p->stream, 0); }
+
+// look-ahead aware issue: LF_SIDE launches go to the side stream behind everything issued so far on the main stream and
+// leave `spare` SMs to the main stream's critical path; LF_WAIT_SIDE launches first join the side stream
+int issue_launch_la(sfb200_plan *p, const Launch &L) {
+    if (p->side_stream && (L.flags & LF_SIDE)) {
+        CK(cudaEventRecord(p->ev_to_side, p->stream));
+        CK(cudaStreamWaitEvent(p->side_stream, p->ev_to_side, 0));
+        const int rc = issue_launch_on(p, L, p->side_stream, p->spare_sms);
+        if (rc) return rc;
+        CK(cudaEventRecord(p->ev_from_side, p->side_stream));
+        p->side_pending = true;
+        return SFB200_OK;
+    }
+    if (p->side_pending && (L.flags & LF_WAIT_SIDE)) {
+        CK(cudaStreamWaitEvent(p->stream, p->ev_from_side, 0));
+        p->side_pending = false;
+    }
+    return issue_launch_on(p, L, p->stream, 0);
+}
+
+int join_side(sfb200_plan *p) {
+    if (p->side_pending) {
+        CK(cudaStreamWaitEvent(p->stream, p->ev_from_side, 0));
+        p->side_pending = false;
     }
     return SFB200_OK;
 }
@@ -109,18 +143,24 @@ int begin_factor(sfb200_plan *p) {
 int run_launches(sfb200_plan *p, size_t first, size_t count) {
     const HostPlan &H = p->H;
     for (size_t i = first; i < first + count; ++i) {
-        const int rc = issue_launch(p, H.launches[i]);
+        const int rc = issue_launch_la(p, H.launches[i]);
         if (rc) return rc;
         ++p->launches;
     }
+    const int rc = join_side(p);          // an etree level ends with the side stream drained
+    if (rc) return rc;
     CK(cudaGetLastError());
     return SFB200_OK;
 }
 
 int run_schedule(sfb200_plan *p) {
-    const int rc = begin_factor(p);
+    int rc = begin_factor(p);
     if (rc) return rc;
-    return run_launches(p, 0, p->H.launches.size());
+    for (const Phase &ph : p->H.phases) {        // level by level: each one ends with the side stream joined
+        if ((rc = run_launches(p, (size_t)ph.launch_first, (size_t)ph.launch_count))) return rc;
+        if ((rc = run_launches(p, (size_t)ph.launch_b_first, (size_t)ph.launch_b_count))) return rc;
+    }
+    return SFB200_OK;
 }
 
 int check_status(sfb200_plan *p) {
@@ -156,6 +196,9 @@ void sfb200_plan_free(sfb200_plan *p) {
     if (p->copy_done) cudaEventDestroy(p->copy_done);
     if (p->d_spack) cudaFree(p->d_spack);
     if (p->copy_stream) cudaStreamDestroy(p->copy_stream);
+    if (p->ev_to_side) cudaEventDestroy(p->ev_to_side);
+    if (p->ev_from_side) cudaEventDestroy(p->ev_from_side);
+    if (p->side_stream) cudaStreamDestroy(p->side_stream);
     if (p->stream && p->own_stream) cudaStreamDestroy(p->stream);
     delete p;
 }
@@ -181,6 +224,7 @@ int sfb200_plan_create_part(const sfb200_symbolic *s, int device, int rank, int 
     if (const char *e = getenv("SFB200_GEMM128_MIN")) prm.gemm128_min_m = atoi(e);
     if (const char *e = getenv("SFB200_DIST_MIN_M")) prm.dist_scatter_min_m = atoi(e);
     if (const char *e = getenv("SFB200_GEMM_WS")) prm.use_ws = atoi(e);
+    if (const char *e = getenv("SFB200_LOOKAHEAD")) prm.lookahead = atoi(e);
     const int rc = build_plan(s->S, prm, p->H, rank, world);
     if (rc != 0) {
         delete p;
@@ -246,6 +290,14 @@ int sfb200_plan_create_part(const sfb200_symbolic *s, int device, int rank, int 
             flat.insert(flat.end(), small[l].begin(), small[l].end());
         }
         if ((err = upload(p, p->d_spack, flat))) return fail(err);
+        if (prm.lookahead && prm.outer2 > 0) {
+            if (const char *e = getenv("SFB200_SPARE_SMS")) p->spare_sms = atoi(e);
+            int lo_prio = 0, hi_prio = 0;
+            cudaDeviceGetStreamPriorityRange(&lo_prio, &hi_prio);
+            if (cudaStreamCreateWithPriority(&p->side_stream, cudaStreamNonBlocking, lo_prio) != cudaSuccess ||
+                cudaEventCreateWithFlags(&p->ev_to_side, cudaEventDisableTiming) != cudaSuccess ||
+                cudaEventCreateWithFlags(&p->ev_from_side, cudaEventDisableTiming) != cudaSuccess) { set_error("side stream"); return fail(SFB200_ERR_CUDA); }
+        }
         if (cudaStreamCreateWithFlags(&p->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
             cudaEventCreateWithFlags(&p->copy_done, cudaEventDisableTiming) != cudaSuccess) { set_error("copy stream"); return fail(SFB200_ERR_CUDA); }
     }
@@ -465,10 +517,11 @@ int factorize_streamed(sfb200_plan *p, double *Lsx, double *Lsx_dev_alias) {
                 }
             }
             if (L.top_block >= 0) cur_block = std::max(cur_block, (int)L.top_block);
-            rc = issue_launch(p, L);
+            rc = issue_launch_la(p, L);
             if (rc) return rc;
             ++p->launches;
         }
+        if ((rc = join_side(p))) return rc;
         // the level is final: remaining columns of its big fronts, then all of its small fronts
         if (!publish()) { set_error("event"); return SFB200_ERR_CUDA; }
         for (size_t b = 0; b < big.size(); ++b) {

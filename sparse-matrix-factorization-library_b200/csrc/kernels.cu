@@ -225,7 +225,9 @@ __global__ void __launch_bounds__(256) k_diag(PlanDev P, const DiagOp *__restric
     __shared__ double dsum[2][64];
     const DiagOp op = ops[blockIdx.x];
     const int nb = op.nb, tid = threadIdx.x;
-    const int ty = tid >> 4, tx = tid & 15;
+    // a warp holds two block COLUMNS (tx) and all 16 block rows (ty): the owners of a column -- the only threads that
+    // need the pivot's reciprocal square root, a long dependent sequence -- sit in one warp, the other seven skip it
+    const int ty = tid & 15, tx = tid >> 4;
     const int r0 = ty << 2, c0 = tx << 2;
     double *A = P.X + op.a_off;
     const bool active = LU || ty >= tx;
@@ -265,21 +267,21 @@ __global__ void __launch_bounds__(256) k_diag(PlanDev P, const DiagOp *__restric
 #pragma unroll
                     for (int rr = 0; rr < 4; ++rr) a[rr][cc] = fma(-lr[rr], uc[cc], a[rr][cc]);
             }
-            // ---- pivot of column jn from the running diagonal ---------------------------------------------------------
-            const double dprev = dsum[buf][jn];
-            const double lj = lcol[buf][jn], uj = LU ? urow[buf][jn] : lj;
-            const double d = fma(-lj, uj, dprev);
-            double rinv;
-            if (LU) {
-                if (d == 0.0 && tid == 0) atomicOr(P.status, 1);
-                rinv = 1.0 / d;
-            } else {
-                if (!(d > 0.0) && tid == 0) atomicOr(P.status, 1);
-                rinv = rsqrt(d);
-            }
             const int nbuf = buf ^ 1;
             if (tid < 64) dsum[nbuf][tid] = fma(-lcol[buf][tid], LU ? urow[buf][tid] : lcol[buf][tid], dsum[buf][tid]);
             if (tx == jb) {                      // owners of column jn (all 16, so every row of lcol is rewritten)
+                // ---- pivot of column jn from the running diagonal -----------------------------------------------------
+                const double dprev = dsum[buf][jn];
+                const double lj = lcol[buf][jn], uj = LU ? urow[buf][jn] : lj;
+                const double d = fma(-lj, uj, dprev);
+                double rinv;
+                if (LU) {
+                    if (d == 0.0 && ty == 0) atomicOr(P.status, 1);
+                    rinv = 1.0 / d;
+                } else {
+                    if (!(d > 0.0) && ty == 0) atomicOr(P.status, 1);
+                    rinv = rsqrt(d);
+                }
 #pragma unroll
                 for (int rr = 0; rr < 4; ++rr) {
                     const int r = r0 + rr;
@@ -1056,11 +1058,12 @@ void launch_gemm(const PlanDev &P, const GemmOp *ops, int count, int grid, bool 
     }
 }
 
-void launch_gemm_ws(const PlanDev &P, const GemmOp *ops, int count, int tiles, cudaStream_t st) {
+void launch_gemm_ws(const PlanDev &P, const GemmOp *ops, int count, int tiles, int spare_sms, cudaStream_t st) {
     if (count <= 0 || tiles <= 0) return;
     static int sms = 0;
     if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); if (sms <= 0) sms = 148; }
-    const int grid = tiles < sms ? tiles : sms;          // persistent: one CTA per SM walks the tile list
+    const int avail = sms - spare_sms > 8 ? sms - spare_sms : 8;      // look-ahead: leave a few SMs to the critical path
+    const int grid = tiles < avail ? tiles : avail;      // persistent: one CTA per SM walks the tile list
     k_gemm_ws<<<grid, ws::NT, ws::SMEM_BYTES, st>>>(P, ops, count, tiles);
 }
 

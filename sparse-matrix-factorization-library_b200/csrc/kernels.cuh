@@ -30,7 +30,7 @@ void launch_small(const PlanDev &P, const int32_t *tasks, int count, int smem, b
 void launch_diag(const PlanDev &P, const DiagOp *ops, int count, cudaStream_t st);
 void launch_trsm(const PlanDev &P, const TrsmOp *ops, int count, int grid, cudaStream_t st);
 void launch_gemm(const PlanDev &P, const GemmOp *ops, int count, int grid, bool tile128, cudaStream_t st);
-void launch_gemm_ws(const PlanDev &P, const GemmOp *ops, int count, int tiles, cudaStream_t st);
+void launch_gemm_ws(const PlanDev &P, const GemmOp *ops, int count, int tiles, int spare_sms, cudaStream_t st);
 void launch_pack(const double *X, double *out, const PackTask *tasks, int count, cudaStream_t st);
 
 // micro-benchmarks of the two FP64 pipes (peak measurement for the roofline denominators)

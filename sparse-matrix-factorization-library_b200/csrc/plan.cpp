@@ -15,6 +15,8 @@ struct SlotOps {
     std::vector<DiagOp> diag;
     std::vector<TrsmOp> trsm;
     std::vector<GemmOp> gemm;
+    std::vector<GemmOp> side;     // look-ahead: REST part of a top-level trailing update (side stream)
+    bool next_of_split = false;   // gemm holds NEXT parts: they must wait for the previous block's REST
 };
 
 // Recursive blocked right-looking factorization of one large panel (replaces dpotrf_ + dtrsm_, CH.c:2135-2142, the
@@ -38,6 +40,8 @@ struct PanelEmitter {
     std::map<int, SlotOps> &slots;
     std::vector<int> nslots;      // nslots[d] = slots used by one block of level d
 
+    bool lookahead = false;
+
     PanelEmitter(const SnodeDev &s, bool is_lu, const std::vector<int> &w, std::map<int, SlotOps> &sl)
         : sn(s), lu(is_lu), widths(w), slots(sl) {
         nslots.assign(widths.size() + 1, 0);
@@ -45,12 +49,12 @@ struct PanelEmitter {
         for (size_t d = 1; d < widths.size(); ++d) nslots[d] = (widths[d] / widths[d - 1]) * (nslots[d - 1] + 1);
     }
 
-    void gemm(int slot, i64 a, i64 b, i64 c, int M, int N, int K, int flags) {
+    void gemm(int slot, i64 a, i64 b, i64 c, int M, int N, int K, int flags, bool side = false) {
         if (M <= 0 || N <= 0 || K <= 0) return;
         GemmOp g{};
         g.a_off = a; g.b_off = b; g.c_off = c; g.lda = g.ldb = g.ldc = sn.ld;
         g.M = M; g.N = N; g.K = K; g.flags = flags; g.tile_mod = 1; g.tile_rem = 0;
-        slots[slot].gemm.push_back(g);
+        (side ? slots[slot].side : slots[slot].gemm).push_back(g);
     }
     void trsm(int slot, i64 d, int w, i64 b_off, int nvec, int es, int vs, int flags) {
         if (nvec <= 0) return;
@@ -84,11 +88,23 @@ struct PanelEmitter {
             block(b0, b1, depth - 1, slot + i * stride);
             if (b1 >= c1) continue;
             const int gs = slot + i * stride + nslots[depth - 1];
+            // look-ahead split of the TOP-level update: [b1, s1) = the next block column (main stream), [s1, c1) = the rest
+            const bool split = lookahead && depth == (int)widths.size() && b1 + w < c1;
+            const int s1 = split ? b1 + w : c1;
+            if (split) slots[gs].next_of_split = true;
             if (!lu) {
-                gemm(gs, x + b1 + (i64)b0 * ld, x + b1 + (i64)b0 * ld, x + b1 + (i64)b1 * ld, R - b1, c1 - b1, K, G_LOWER);
+                // C rows [b1,R) x cols [b1,s1) is diagonal-aligned; the REST block (cols >= s1) only has rows >= s1 below
+                // its own diagonal, so it is issued as its own diagonal-aligned op on rows [s1,R)
+                gemm(gs, x + b1 + (i64)b0 * ld, x + b1 + (i64)b0 * ld, x + b1 + (i64)b1 * ld, R - b1, s1 - b1, K, G_LOWER);
+                if (split)
+                    gemm(gs, x + s1 + (i64)b0 * ld, x + s1 + (i64)b0 * ld, x + s1 + (i64)s1 * ld, R - s1, c1 - s1, K, G_LOWER, true);
             } else {
-                gemm(gs, x + b1 + (i64)b0 * ld, x + b0 + (i64)b1 * ld, x + b1 + (i64)b1 * ld, R - b1, c1 - b1, K, G_B_KMAJOR);
-                gemm(gs, x + R + (i64)b0 * ld, x + b1 + (i64)b0 * ld, x + R + (i64)b1 * ld, m, c1 - b1, K, 0);
+                gemm(gs, x + b1 + (i64)b0 * ld, x + b0 + (i64)b1 * ld, x + b1 + (i64)b1 * ld, R - b1, s1 - b1, K, G_B_KMAJOR);
+                gemm(gs, x + R + (i64)b0 * ld, x + b1 + (i64)b0 * ld, x + R + (i64)b1 * ld, m, s1 - b1, K, 0);
+                if (split) {
+                    gemm(gs, x + b1 + (i64)b0 * ld, x + b0 + (i64)s1 * ld, x + b1 + (i64)s1 * ld, R - b1, c1 - s1, K, G_B_KMAJOR, true);
+                    gemm(gs, x + R + (i64)b0 * ld, x + s1 + (i64)b0 * ld, x + R + (i64)s1 * ld, m, c1 - s1, K, 0, true);
+                }
                 gemm(gs, x + b1 + (i64)b0 * ld, x + b0 + (i64)c1 * ld, x + b1 + (i64)c1 * ld, c1 - b1, n - c1, K, G_B_KMAJOR);
             }
         }
@@ -365,7 +381,7 @@ int build_plan(const Symbolic &S, const PlanParams &prm, HostPlan &P, int rank, 
                 for (int k = 0; k < 4; ++k) if (pb <= small_limits[k]) { c = k; break; }
             if (c >= 0 && !dist) { cls[c].push_back(s); ++P.nsmall; continue; }
             ++P.nlarge;
-            PanelEmitter(d, lu, widths, slots).run();
+            { PanelEmitter pe(d, lu, widths, slots); pe.lookahead = prm.lookahead && prm.outer2 > 0; pe.run(); }
             if (!dist) scatter_ops(scatter, 1, 0);
         }
         for (int c = 0; c < 4; ++c) {
@@ -381,7 +397,7 @@ int build_plan(const Symbolic &S, const PlanParams &prm, HostPlan &P, int rank, 
             L.smem = (int32_t)smem;
             P.launches.push_back(L);
         }
-        auto emit_gemm = [&](std::vector<GemmOp> &ops, int top_block) {
+        auto emit_gemm = [&](std::vector<GemmOp> &ops, int top_block, int lflags = 0) {
             // longest tiles first: the CTAs of a launch are dispatched in index order, so the deep-K ops must not be
             // the ones left running alone at the end of the launch
             std::stable_sort(ops.begin(), ops.end(), [](const GemmOp &a, const GemmOp &b) { return a.K > b.K; });
@@ -393,6 +409,7 @@ int build_plan(const Symbolic &S, const PlanParams &prm, HostPlan &P, int rank, 
                 L.kind = pass == 0 ? L_GEMM128WS : pass == 1 ? L_GEMM128 : L_GEMM64;
                 L.level = lev;
                 L.top_block = top_block;
+                L.flags = lflags;
                 L.first = (int32_t)P.gemm_ops.size();
                 i64 tiles = 0;
                 for (GemmOp g : ops) {
@@ -437,14 +454,15 @@ int build_plan(const Symbolic &S, const PlanParams &prm, HostPlan &P, int rank, 
                 L.grid = (int32_t)ctas;
                 P.launches.push_back(L);
             }
-            if (!so.gemm.empty()) emit_gemm(so.gemm, top_block);
+            if (!so.gemm.empty()) emit_gemm(so.gemm, top_block, so.next_of_split ? LF_WAIT_SIDE : 0);
+            if (!so.side.empty()) emit_gemm(so.side, top_block, LF_SIDE);
         }
-        if (!scatter.empty()) emit_gemm(scatter, -1);
+        if (!scatter.empty()) emit_gemm(scatter, -1, LF_WAIT_SIDE);
         ph.reduce_count = (int32_t)P.reduces.size() - ph.reduce_first;
         ph.launch_count = (int32_t)P.launches.size() - ph.launch_first;
         ph.bcast_count = (int32_t)P.bcasts.size() - ph.bcast_first;
         ph.launch_b_first = (int32_t)P.launches.size();
-        if (!scatter_dist.empty()) emit_gemm(scatter_dist, -1);
+        if (!scatter_dist.empty()) emit_gemm(scatter_dist, -1, LF_WAIT_SIDE);
         ph.launch_b_count = (int32_t)P.launches.size() - ph.launch_b_first;
         P.phases.push_back(ph);
     }

@@ -89,7 +89,16 @@ struct Launch {
     int32_t top_block; // large-front launches: index of the widest-level block column this launch works on (-1: small fronts
                      // / scatter).  When it moves from i to i+1 inside a level, block column i of every large front of the
                      // level is final -> can be copied out while the rest is still being factorized
-    int32_t pad;
+    int32_t flags;   // LaunchFlags
+};
+
+// Look-ahead: the top-level trailing update of block column b is split into NEXT (the columns of block b+1, main stream)
+// and REST (everything right of it, side stream, on all but a few SMs).  Block column b+1 is then factorized on the main
+// stream -- a chain of small latency-bound kernels -- while REST(b) keeps the machine busy.  NEXT(b+1) touches columns
+// REST(b) also updates, so it waits for it.
+enum LaunchFlags : int32_t {
+    LF_SIDE      = 1 << 0,   // issue on the side stream (after everything issued so far on the main stream)
+    LF_WAIT_SIDE = 1 << 1,   // main-stream launch that must wait for the side stream's work issued so far
 };
 
 // ---- multi-GPU: one etree level = one phase; before its launches, the partial images of the level's shared panels
