@@ -313,9 +313,16 @@ def main():
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
         dom = max(prof, key=lambda k: prof[k]["ms"])
         d = prof[dom]
+        traffic = None
+        try:    # dram bytes of the dominant kernel from the committed ncu --set full capture (not measurable live)
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(dom)
+        except (OSError, ValueError):
+            pass
         ach = d["flops"] / (d["ms"] * 1e-3) / 1e12
         roof = {"kernel": dom + (" (rank 0's share of the partitioned schedule)" if world > 1 else ""), "bound": "tensor", "achieved": ach, "peak": dmma_peak, "unit": "TFLOP/s",
-                "frac": ach / dmma_peak if dmma_peak > 0 else None, "traffic": None,
+                "frac": ach / dmma_peak if dmma_peak > 0 else None,
+                "traffic": (traffic["dram_bytes_read"] + traffic["dram_bytes_write"]) if traffic else None,
+                "traffic_detail": traffic,
                 "peak_source": "FP64 DMMA probe in this run (sfb200_probe_fp64_peak); MEASURED_PEAKS.json has no FP64 entry; "
                                "DFMA vector pipe probe %.2f TFLOP/s" % dfma_peak,
                 "launches": d["launches"], "avg_launch_ms": d["ms"] / d["launches"], "share_of_step": d["ms"] / total_ms,

@@ -290,7 +290,7 @@ int sfb200_plan_create_part(const sfb200_symbolic *s, int device, int rank, int 
             flat.insert(flat.end(), small[l].begin(), small[l].end());
         }
         if ((err = upload(p, p->d_spack, flat))) return fail(err);
-        if (prm.lookahead && prm.outer2 > 0) {
+        if (prm.lookahead) {
             if (const char *e = getenv("SFB200_SPARE_SMS")) p->spare_sms = atoi(e);
             int lo_prio = 0, hi_prio = 0;
             cudaDeviceGetStreamPriorityRange(&lo_prio, &hi_prio);

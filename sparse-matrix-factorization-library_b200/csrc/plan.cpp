@@ -381,7 +381,7 @@ int build_plan(const Symbolic &S, const PlanParams &prm, HostPlan &P, int rank, 
                 for (int k = 0; k < 4; ++k) if (pb <= small_limits[k]) { c = k; break; }
             if (c >= 0 && !dist) { cls[c].push_back(s); ++P.nsmall; continue; }
             ++P.nlarge;
-            { PanelEmitter pe(d, lu, widths, slots); pe.lookahead = prm.lookahead && prm.outer2 > 0; pe.run(); }
+            { PanelEmitter pe(d, lu, widths, slots); pe.lookahead = prm.lookahead != 0; pe.run(); }
             if (!dist) scatter_ops(scatter, 1, 0);
         }
         for (int c = 0; c < 4; ++c) {
