@@ -133,7 +133,16 @@ int sfb200_plan_profile_launch(const sfb200_plan *p, int i, double *out);
 /* Copy the device-resident factor into the reference's host layout (xsize doubles). */
 int sfb200_download_factor(sfb200_plan *p, double *Lsx);
 
-/* Device time of the last factorize call in milliseconds (CUDA events on the plan's stream):
+/* ---- consumers of the device-resident factor ---------------------------------------------------------
+ * Forward/backward substitution on the GPU, replacing SparseFrame_solve_supernodal (CH.c:3036-3139, LU.c:3592-3700).
+ * B: n x nrhs, column-major, leading dimension n, in the PERMUTED ordering (like matrix_info->Bx); overwritten by X. */
+int sfb200_solve(sfb200_plan *p, double *B, int nrhs);                /* host buffer */
+int sfb200_solve_device(sfb200_plan *p, double *d_B, int nrhs);       /* device buffer */
+/* Residual of the permuted system with the matrix values of the last factorize (SparseFrame_validate, CH.c:3197-3263):
+ * out[5] = {||A||_1, ||b||_inf, ||x||_inf, ||Ax-b||_inf, ||Ax-b||_inf / (||A||_1 ||x||_inf + ||b||_inf)}. */
+int sfb200_residual(sfb200_plan *p, const double *x, const double *b, double out[5]);
+
+/* Device time of the last factorize call in milliseconds (which = 2: the last solve) (CUDA events on the plan's stream):
  * which = 0 numeric only (assemble + factor), 1 = including H2D/D2H copies of the host-buffer call. */
 double sfb200_last_ms(const sfb200_plan *p, int which);
 

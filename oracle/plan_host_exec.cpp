@@ -285,6 +285,64 @@ void sfcheck_pack_owned(void *hv, const double *X, double *Lsx_out) {
     }
 }
 
+/* ---- interpreter of the triangular-solve schedule (same task lists the solve kernels consume) ---------------------- */
+static void solve_task(const HostPlan &P, const SolveTask &t, int kind, const double *X, double *b) {
+    const bool lu = P.kind == Kind::LU;
+    auto gidx = [&](int i) { return i < t.nscol ? (i64)t.col0 + i : (i64)P.lsi32[t.lsip + i]; };
+    const double *D = X + t.xoff + t.j0 + (i64)t.j0 * t.ld;
+    double *xb = b + t.col0 + t.j0;
+    switch (kind) {
+        case S_DIAG_F:
+            for (int j = 0; j < t.w; ++j) {
+                if (!lu) xb[j] /= D[j + (i64)j * t.ld];
+                for (int i = j + 1; i < t.w; ++i) xb[i] -= D[i + (i64)j * t.ld] * xb[j];
+            }
+            break;
+        case S_DIAG_B:
+            for (int j = t.w - 1; j >= 0; --j) {
+                xb[j] /= D[j + (i64)j * t.ld];
+                for (int i = 0; i < j; ++i) xb[i] -= (lu ? D[i + (i64)j * t.ld] : D[j + (i64)i * t.ld]) * xb[j];
+            }
+            break;
+        case S_UPD_F:
+            for (int i = t.r0; i < t.r1; ++i) {
+                double acc = 0;
+                for (int jj = 0; jj < t.w; ++jj) acc += X[t.xoff + i + (i64)(t.j0 + jj) * t.ld] * xb[jj];
+                b[gidx(i)] -= acc;
+            }
+            break;
+        case S_UPD_B: {
+            const int shift = lu ? t.nsrow - t.nscol : 0;
+            for (int jj = 0; jj < t.w; ++jj) {
+                double acc = 0;
+                for (int i = t.r0; i < t.r1; ++i) acc += X[t.xoff + shift + i + (i64)(t.j0 + jj) * t.ld] * b[gidx(i)];
+                xb[jj] -= acc;
+            }
+            break;
+        }
+        case S_UPD_BU:
+            for (int jj = 0; jj < t.w; ++jj) {
+                double acc = 0;
+                for (int c = t.r0; c < t.r1; ++c) acc += X[t.xoff + t.j0 + jj + (i64)c * t.ld] * b[t.col0 + c];
+                xb[jj] -= acc;
+            }
+            break;
+    }
+}
+
+/* factorize on the interpreter, then solve A x = b (permuted ordering) through the solve schedule; x overwrites b */
+long sfcheck_factor_solve(void *hv, double *b) {
+    CheckHandle &h = *(CheckHandle *)hv;
+    const HostPlan &P = h.P;
+    if (P.world != 1) return -1;
+    std::vector<double> X(P.xsize_pad, 0.0);
+    assemble(h, X.data());
+    const long bad = run_launches(P, X.data(), 0, (int)P.launches.size());
+    for (const SolveLaunch &L : P.solve_fwd) for (int k = 0; k < L.count; ++k) solve_task(P, P.solve_tasks[L.first + k], L.kind, X.data(), b);
+    for (const SolveLaunch &L : P.solve_bwd) for (int k = 0; k < L.count; ++k) solve_task(P, P.solve_tasks[L.first + k], L.kind, X.data(), b);
+    return bad;
+}
+
 /* analyze + plan + interpret on one rank.  Lsx_out receives the factor in the reference's layout (xsize doubles).
  * Returns 0, or a negative code if analysis/plan failed, or a positive count of failed pivots. */
 long sfcheck_factorize(int kind, int is_symmetric, long n, const long *Cp, const long *Ci, const double *Cx,

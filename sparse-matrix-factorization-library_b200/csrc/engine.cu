@@ -36,6 +36,14 @@ struct sfb200_plan {
     GemmOp *d_gemm = nullptr;
     PackTask *d_pack = nullptr;
     double *d_X = nullptr, *d_out = nullptr, *d_lx = nullptr, *d_ux = nullptr;
+    // triangular solve / residual
+    int32_t *d_lsi32 = nullptr, *d_nz_col = nullptr, *d_unz_row = nullptr;
+    int64_t *d_nz_row = nullptr, *d_unz_col = nullptr;
+    SolveTask *d_solve = nullptr;
+    double *d_rhs = nullptr, *d_work = nullptr;     // d_work: b copy, r, column sums (3 n)
+    size_t rhs_capacity = 0;
+    unsigned long long *d_norms = nullptr;
+    float ms_solve = 0.f;
     int *d_status = nullptr;
     // look-ahead: side stream for the REST part of the top-level trailing updates
     cudaStream_t side_stream = nullptr;
@@ -187,6 +195,8 @@ int sfb200_device_count(void) {
 void sfb200_plan_free(sfb200_plan *p) {
     if (!p) return;
     cudaSetDevice(p->device);
+    void *sptrs[] = {p->d_lsi32, p->d_nz_col, p->d_unz_row, p->d_nz_row, p->d_unz_col, p->d_solve, p->d_rhs, p->d_work, p->d_norms};
+    for (void *q : sptrs) if (q) cudaFree(q);
     void *ptrs[] = {p->d_snode, p->d_coloff, p->d_relbase, p->d_asm_l, p->d_asm_u, p->d_segb, p->d_sege, p->d_uoff,
                     p->d_relmap, p->d_small, p->d_diag, p->d_trsm, p->d_gemm, p->d_pack, p->d_X, p->d_out, p->d_lx,
                     p->d_ux, p->d_status};
@@ -255,6 +265,12 @@ int sfb200_plan_create_part(const sfb200_symbolic *s, int device, int rank, int 
     if ((err = upload(p, p->d_trsm, H.trsm_ops))) return fail(err);
     if ((err = upload(p, p->d_gemm, H.gemm_ops))) return fail(err);
     if ((err = upload(p, p->d_pack, H.pack_tasks))) return fail(err);
+    if ((err = upload(p, p->d_lsi32, H.lsi32))) return fail(err);
+    if ((err = upload(p, p->d_nz_col, H.nz_col))) return fail(err);
+    if ((err = upload(p, p->d_nz_row, H.nz_row))) return fail(err);
+    if ((err = upload(p, p->d_unz_row, H.unz_row))) return fail(err);
+    if ((err = upload(p, p->d_unz_col, H.unz_col))) return fail(err);
+    if ((err = upload(p, p->d_solve, H.solve_tasks))) return fail(err);
     auto dmalloc = [&](void **ptr, size_t bytes) {
         if (bytes == 0) bytes = 8;
         if (cudaMalloc(ptr, bytes) != cudaSuccess) { set_error("cudaMalloc of " + std::to_string(bytes) + " bytes failed"); return SFB200_ERR_CUDA; }
@@ -687,9 +703,81 @@ int sfb200_plan_profile_launch(const sfb200_plan *p, int i, double *out) {
     return SFB200_OK;
 }
 
+/* ---- device-resident triangular solve and residual -------------------------------------------------- */
+namespace {
+int ensure_rhs(sfb200_plan *p, int nrhs) {
+    const size_t need = (size_t)p->H.n * (size_t)nrhs;
+    if (need > p->rhs_capacity) {
+        if (p->d_rhs) cudaFree(p->d_rhs);
+        CK(cudaMalloc((void **)&p->d_rhs, sizeof(double) * std::max<size_t>(need, 1)));
+        p->rhs_capacity = need;
+    }
+    if (!p->d_work) CK(cudaMalloc((void **)&p->d_work, sizeof(double) * 3 * (size_t)std::max<i64>(p->H.n, 1)));
+    if (!p->d_norms) CK(cudaMalloc((void **)&p->d_norms, sizeof(unsigned long long) * 4));
+    return SFB200_OK;
+}
+}  // namespace
+
+int sfb200_solve_device(sfb200_plan *p, double *d_B, int nrhs) {
+    if (!p || !d_B || nrhs < 1) { set_error("sfb200_solve_device: bad argument"); return SFB200_ERR_ARG; }
+    if (!p->factored) { set_error("sfb200_solve: nothing factorized yet"); return SFB200_ERR_STATE; }
+    if (p->H.world > 1) { set_error("sfb200_solve: not available on partitioned plans"); return SFB200_ERR_STATE; }
+    CK(cudaSetDevice(p->device));
+    const HostPlan &H = p->H;
+    const bool lu = H.kind == Kind::LU;
+    cudaEvent_t a, b;
+    CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b));
+    CK(cudaEventRecord(a, p->stream));
+    for (const SolveLaunch &L : H.solve_fwd) launch_solve(p->d_X, p->d_lsi32, d_B, H.n, nrhs, lu, p->d_solve + L.first, L.kind, L.count, p->stream);
+    for (const SolveLaunch &L : H.solve_bwd) launch_solve(p->d_X, p->d_lsi32, d_B, H.n, nrhs, lu, p->d_solve + L.first, L.kind, L.count, p->stream);
+    CK(cudaEventRecord(b, p->stream));
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(p->stream));
+    cudaEventElapsedTime(&p->ms_solve, a, b);
+    cudaEventDestroy(a); cudaEventDestroy(b);
+    return SFB200_OK;
+}
+
+int sfb200_solve(sfb200_plan *p, double *B, int nrhs) {
+    if (!p || !B || nrhs < 1) { set_error("sfb200_solve: bad argument"); return SFB200_ERR_ARG; }
+    CK(cudaSetDevice(p->device));
+    int rc = ensure_rhs(p, nrhs);
+    if (rc) return rc;
+    const size_t bytes = sizeof(double) * (size_t)p->H.n * (size_t)nrhs;
+    CK(cudaMemcpyAsync(p->d_rhs, B, bytes, cudaMemcpyHostToDevice, p->stream));
+    rc = sfb200_solve_device(p, p->d_rhs, nrhs);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(B, p->d_rhs, bytes, cudaMemcpyDeviceToHost, p->stream));
+    CK(cudaStreamSynchronize(p->stream));
+    return SFB200_OK;
+}
+
+/* out = {||A||_1, ||b||_inf, ||x||_inf, ||Ax-b||_inf, rnorm/(anorm*xnorm+bnorm)} with the matrix values of the last factorize */
+int sfb200_residual(sfb200_plan *p, const double *x, const double *b, double *out) {
+    if (!p || !x || !b || !out) { set_error("sfb200_residual: bad argument"); return SFB200_ERR_ARG; }
+    if (p->H.world > 1) { set_error("sfb200_residual: not available on partitioned plans"); return SFB200_ERR_STATE; }
+    CK(cudaSetDevice(p->device));
+    int rc = ensure_rhs(p, 1);
+    if (rc) return rc;
+    const HostPlan &H = p->H;
+    const size_t nb = sizeof(double) * (size_t)H.n;
+    double *d_b = p->d_work, *d_r = p->d_work + H.n, *d_w = p->d_work + 2 * H.n;
+    CK(cudaMemcpyAsync(p->d_rhs, x, nb, cudaMemcpyHostToDevice, p->stream));
+    CK(cudaMemcpyAsync(d_b, b, nb, cudaMemcpyHostToDevice, p->stream));
+    launch_residual(p->d_lx, p->d_nz_row, p->d_nz_col, H.nnz, p->d_ux, p->d_unz_row, p->d_unz_col, H.unnz, H.split, p->d_rhs, d_b,
+                    d_r, d_w, H.n, p->d_norms, p->stream);
+    CK(cudaGetLastError());
+    unsigned long long bits[4];
+    CK(cudaMemcpyAsync(bits, p->d_norms, sizeof(bits), cudaMemcpyDeviceToHost, p->stream));
+    CK(cudaStreamSynchronize(p->stream));
+    for (int k = 0; k < 4; ++k) memcpy(out + k, bits + k, sizeof(double));
+    out[4] = out[3] / (out[0] * out[2] + out[1]);
+    return SFB200_OK;
+}
+
 double sfb200_last_ms(const sfb200_plan *p, int which) {
     if (!p) return -1.0;
-    return which == 0 ? p->ms_numeric : p->ms_e2e;
+    return which == 0 ? p->ms_numeric : which == 1 ? p->ms_e2e : p->ms_solve;
 }
 
 int64_t sfb200_last_launches(const sfb200_plan *p) { return p ? p->launches : -1; }

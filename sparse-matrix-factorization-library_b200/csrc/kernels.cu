@@ -909,6 +909,156 @@ __global__ void __launch_bounds__(256) k_pack(const double *__restrict__ X, doub
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// Device-resident triangular solves over the padded factor (replaces the scalar host loops of
+// SparseFrame_solve_supernodal, CH.c:3074-3134 / LU.c:3630-3694).  HBM-bound: every factor entry is read once per sweep.
+// Right-hand sides: n x nrhs, column-major, leading dimension n, PERMUTED ordering (as matrix_info->Bx / Xx).
+// ---------------------------------------------------------------------------------------------------------------
+struct SolveArgs {
+    const double *X;            // padded factor
+    const int32_t *lsi;         // row lists
+    double *rhs;                // n x nrhs
+    int64_t n;
+    int nrhs;
+    int is_lu;
+};
+
+__device__ __forceinline__ int solve_gidx(const SolveTask &t, const int32_t *lsi, int i) {
+    return i < t.nscol ? t.col0 + i : lsi[t.lsip + i];
+}
+
+// x_b = T^-1 b_b on one 64 x 64 diagonal block (64 threads, column-oriented elimination in shared memory)
+//   mode 0: forward, T lower (unit diagonal for LU);  mode 1: backward Cholesky, T = L^T;  mode 2: backward LU, T = U
+__global__ void __launch_bounds__(64) k_solve_diag(SolveArgs A, const SolveTask *__restrict__ tasks, int mode) {
+    __shared__ double T[64 * 65];
+    __shared__ double v[64];
+    const SolveTask t = tasks[blockIdx.x];
+    const int tid = threadIdx.x, w = t.w;
+    const double *D = A.X + t.xoff + t.j0 + (int64_t)t.j0 * t.ld;
+    for (int idx = tid; idx < w * w; idx += 64) {
+        const int c = idx / w, r = idx - c * w;
+        T[r * 65 + c] = D[(int64_t)c * t.ld + r];         // T[r][c] = block(r, c)
+    }
+    const bool unit = A.is_lu && mode == 0;
+    const int64_t g0 = t.col0 + t.j0;
+    for (int q = 0; q < A.nrhs; ++q) {
+        double *b = A.rhs + (int64_t)q * A.n + g0;
+        __syncthreads();
+        if (tid < w) v[tid] = b[tid];
+        __syncthreads();
+        for (int s = 0; s < w; ++s) {
+            const int j = mode == 0 ? s : w - 1 - s;
+            // coefficient of unknown j in equation i:  mode 0: block(i, j), i > j;  mode 1: block(j, i) (L^T), i < j;
+            //                                           mode 2: block(i, j) (U), i < j
+            if (tid == j && !unit) v[j] = v[j] / T[j * 65 + j];
+            __syncthreads();
+            const double xj = v[j];
+            const bool later = mode == 0 ? tid > j : tid < j;
+            if (tid < w && later) {
+                const double coef = mode == 1 ? T[j * 65 + tid] : T[tid * 65 + j];
+                v[tid] = fma(-coef, xj, v[tid]);
+            }
+            __syncthreads();
+        }
+        if (tid < w) b[tid] = v[tid];
+    }
+}
+
+// forward: b[rows] -= L[rows, block] x_block, one thread per panel row of the slab
+__global__ void __launch_bounds__(256) k_solve_upd_fwd(SolveArgs A, const SolveTask *__restrict__ tasks) {
+    __shared__ double xb[64];
+    const SolveTask t = tasks[blockIdx.x];
+    const double *P = A.X + t.xoff + (int64_t)t.j0 * t.ld;
+    for (int q = 0; q < A.nrhs; ++q) {
+        double *b = A.rhs + (int64_t)q * A.n;
+        __syncthreads();
+        if (threadIdx.x < t.w) xb[threadIdx.x] = b[t.col0 + t.j0 + threadIdx.x];
+        __syncthreads();
+        for (int i = t.r0 + threadIdx.x; i < t.r1; i += 256) {
+            double acc = 0.0;
+            for (int jj = 0; jj < t.w; ++jj) acc = fma(P[(int64_t)jj * t.ld + i], xb[jj], acc);
+            atomicAdd(b + solve_gidx(t, A.lsi, i), -acc);
+        }
+    }
+}
+
+// backward: b_block -= M[rows, block]^T x[rows] over a slab of rows; M = L (Cholesky) or the U12^T rows (LU).
+// Warp w handles block columns w, w+8, ...; lanes stride the rows (coalesced), shuffle reduction, one atomic per column.
+__global__ void __launch_bounds__(256) k_solve_upd_bwd(SolveArgs A, const SolveTask *__restrict__ tasks) {
+    __shared__ double xs[1024];
+    const SolveTask t = tasks[blockIdx.x];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int rowshift = A.is_lu ? t.nsrow - t.nscol : 0;         // LU: off-diagonal row i lives at panel row i + (R - n)
+    const double *P = A.X + t.xoff + (int64_t)t.j0 * t.ld + rowshift;
+    const int cnt = t.r1 - t.r0;
+    for (int q = 0; q < A.nrhs; ++q) {
+        double *b = A.rhs + (int64_t)q * A.n;
+        __syncthreads();
+        for (int k = threadIdx.x; k < cnt; k += 256) xs[k] = b[solve_gidx(t, A.lsi, t.r0 + k)];
+        __syncthreads();
+        for (int jj = warp; jj < t.w; jj += 8) {
+            const double *col = P + (int64_t)jj * t.ld + t.r0;
+            double acc = 0.0;
+            for (int k = lane; k < cnt; k += 32) acc = fma(col[k], xs[k], acc);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+            if (lane == 0) atomicAdd(b + t.col0 + t.j0 + jj, -acc);
+        }
+    }
+}
+
+// backward, LU only: b_block -= U11[block rows, columns c in slab] x[c]; thread jj owns block row jj
+__global__ void __launch_bounds__(64) k_solve_upd_bwd_u(SolveArgs A, const SolveTask *__restrict__ tasks) {
+    const SolveTask t = tasks[blockIdx.x];
+    const int jj = threadIdx.x;
+    if (jj >= t.w) return;
+    const double *P = A.X + t.xoff + t.j0 + jj;
+    for (int q = 0; q < A.nrhs; ++q) {
+        double *b = A.rhs + (int64_t)q * A.n;
+        double acc = 0.0;
+        for (int c = t.r0; c < t.r1; ++c) acc = fma(P[(int64_t)c * t.ld], b[t.col0 + c], acc);
+        atomicAdd(b + t.col0 + t.j0 + jj, -acc);
+    }
+}
+
+// residual of the permuted system (SparseFrame_validate, CH.c:3197-3259): r = A x - b, column sums of |A|
+//   sym: entries of lower(P A P^T) by column (row >= col, mirrored);  !sym: L part takes strictly-lower entries only
+__global__ void k_residual_lower(const double *__restrict__ vals, const int64_t *__restrict__ rows, const int32_t *__restrict__ cols,
+                                 int64_t nnz, int mirror, int strict, const double *__restrict__ x, double *r, double *colsum) {
+    for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < nnz; p += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t i = rows[p];
+        const int j = cols[p];
+        const double v = vals[p];
+        if (strict && i <= j) continue;
+        atomicAdd(r + i, v * x[j]);
+        atomicAdd(colsum + j, fabs(v));
+        if (mirror && i != j) { atomicAdd(r + j, v * x[i]); atomicAdd(colsum + i, fabs(v)); }
+    }
+}
+// U part of an unsymmetric matrix: entry p is (row urow[p], column ucol[p])
+__global__ void k_residual_upper(const double *__restrict__ vals, const int32_t *__restrict__ urow, const int64_t *__restrict__ ucol,
+                                 int64_t nnz, const double *__restrict__ x, double *r, double *colsum) {
+    for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < nnz; p += (int64_t)gridDim.x * blockDim.x) {
+        atomicAdd(r + urow[p], vals[p] * x[ucol[p]]);
+        atomicAdd(colsum + ucol[p], fabs(vals[p]));
+    }
+}
+// out[k] = max_i |v_k[i]| for the four vectors (non-negative doubles order like their bit patterns)
+__global__ void k_absmax4(const double *a, const double *b, const double *c, const double *d, int64_t n, unsigned long long *out) {
+    double m[4] = {0, 0, 0, 0};
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        m[0] = fmax(m[0], fabs(a[i])); m[1] = fmax(m[1], fabs(b[i])); m[2] = fmax(m[2], fabs(c[i])); m[3] = fmax(m[3], fabs(d[i]));
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        for (int o = 16; o > 0; o >>= 1) m[k] = fmax(m[k], __shfl_xor_sync(0xffffffffu, m[k], o));
+        if ((threadIdx.x & 31) == 0) atomicMax(out + k, (unsigned long long)__double_as_longlong(m[k]));
+    }
+}
+__global__ void k_axpby(double *r, const double *b, double alpha, int64_t n) {       // r = alpha * b
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) r[i] = alpha * b[i];
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // FP64 pipe peak probes
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void k_peak_dfma(double *out, int iters) {
@@ -1070,6 +1220,32 @@ void launch_gemm_ws(const PlanDev &P, const GemmOp *ops, int count, int tiles, i
 void launch_pack(const double *X, double *out, const PackTask *tasks, int count, cudaStream_t st) {
     if (count <= 0) return;
     k_pack<<<count, 256, 0, st>>>(X, out, tasks);
+}
+
+void launch_solve(const double *X, const int32_t *lsi, double *rhs, int64_t n, int nrhs, bool lu, const SolveTask *tasks,
+                  int kind, int count, cudaStream_t st) {
+    if (count <= 0) return;
+    SolveArgs A{X, lsi, rhs, n, nrhs, lu ? 1 : 0};
+    switch (kind) {
+        case S_DIAG_F: k_solve_diag<<<count, 64, 0, st>>>(A, tasks, 0); break;
+        case S_DIAG_B: k_solve_diag<<<count, 64, 0, st>>>(A, tasks, lu ? 2 : 1); break;
+        case S_UPD_F: k_solve_upd_fwd<<<count, 256, 0, st>>>(A, tasks); break;
+        case S_UPD_B: k_solve_upd_bwd<<<count, 256, 0, st>>>(A, tasks); break;
+        case S_UPD_BU: k_solve_upd_bwd_u<<<count, 64, 0, st>>>(A, tasks); break;
+        default: break;
+    }
+}
+
+void launch_residual(const double *lx, const int64_t *li, const int32_t *lcol, int64_t nnz, const double *ux, const int32_t *urow,
+                     const int64_t *ui, int64_t unnz, bool split, const double *x, const double *b, double *r, double *colsum,
+                     int64_t n, unsigned long long *out4, cudaStream_t st) {
+    const int block = 256, grid = 148 * 8;
+    k_axpby<<<grid, block, 0, st>>>(r, b, -1.0, n);
+    cudaMemsetAsync(colsum, 0, sizeof(double) * n, st);
+    cudaMemsetAsync(out4, 0, sizeof(unsigned long long) * 4, st);
+    k_residual_lower<<<grid, block, 0, st>>>(lx, li, lcol, nnz, split ? 0 : 1, split ? 1 : 0, x, r, colsum);
+    if (split) k_residual_upper<<<grid, block, 0, st>>>(ux, urow, ui, unnz, x, r, colsum);
+    k_absmax4<<<grid, block, 0, st>>>(colsum, b, x, r, n, out4);
 }
 
 void launch_peak_dfma(double *out, int iters, int grid, int block, cudaStream_t st) {

@@ -33,6 +33,13 @@ void launch_gemm(const PlanDev &P, const GemmOp *ops, int count, int grid, bool 
 void launch_gemm_ws(const PlanDev &P, const GemmOp *ops, int count, int tiles, int spare_sms, cudaStream_t st);
 void launch_pack(const double *X, double *out, const PackTask *tasks, int count, cudaStream_t st);
 
+// device-resident triangular solve / residual
+void launch_solve(const double *X, const int32_t *lsi, double *rhs, int64_t n, int nrhs, bool lu, const SolveTask *tasks,
+                  int kind, int count, cudaStream_t st);
+void launch_residual(const double *lx, const int64_t *li, const int32_t *lcol, int64_t nnz, const double *ux, const int32_t *urow,
+                     const int64_t *ui, int64_t unnz, bool split, const double *x, const double *b, double *r, double *colsum,
+                     int64_t n, unsigned long long *out4, cudaStream_t st);
+
 // micro-benchmarks of the two FP64 pipes (peak measurement for the roofline denominators)
 void launch_peak_dfma(double *out, int iters, int grid, int block, cudaStream_t st);
 void launch_peak_dmma(double *out, int iters, int grid, int block, cudaStream_t st);

@@ -467,6 +467,66 @@ int build_plan(const Symbolic &S, const PlanParams &prm, HostPlan &P, int rank, 
         P.phases.push_back(ph);
     }
 
+    // ---- triangular-solve schedule (device-resident factor; single-GPU plans only) -----------------------------------
+    if (world == 1) {
+        P.lsi32.assign(S.Lsi.begin(), S.Lsi.end());
+        P.nz_col.resize(P.nnz);
+        for (i64 j = 0; j < n; ++j) for (i64 p = S.L.ptr[j]; p < S.L.ptr[j + 1]; ++p) P.nz_col[p] = (int32_t)j;
+        P.nz_row.assign(S.L.idx.begin(), S.L.idx.begin() + P.nnz);
+        if (P.split) {
+            P.unz_col.assign(S.U.idx.begin(), S.U.idx.begin() + P.unnz);
+            P.unz_row.resize(P.unnz);
+            for (i64 i = 0; i < n; ++i) for (i64 p = S.U.ptr[i]; p < S.U.ptr[i + 1]; ++p) P.unz_row[p] = (int32_t)i;
+        }
+        const int SB = 64, SLAB = 1024;
+        auto base_task = [&](i64 s, int j0) {
+            const SnodeDev &d = P.snode[s];
+            SolveTask t{};
+            t.xoff = d.xoff; t.lsip = d.lsip; t.ld = d.ld; t.nsrow = d.nsrow; t.nscol = d.nscol;
+            t.col0 = (int32_t)S.Super[s]; t.j0 = j0; t.w = std::min(SB, d.nscol - j0);
+            return t;
+        };
+        auto push_launch = [&](std::vector<SolveLaunch> &dst, int kind, const std::vector<SolveTask> &tasks) {
+            if (tasks.empty()) return;
+            dst.push_back(SolveLaunch{kind, (int32_t)P.solve_tasks.size(), (int32_t)tasks.size(), 0});
+            P.solve_tasks.insert(P.solve_tasks.end(), tasks.begin(), tasks.end());
+        };
+        for (int pass = 0; pass < 2; ++pass) {           // 0 forward, 1 backward
+            for (int li = 0; li < P.nlevels; ++li) {
+                const int lev = pass == 0 ? li : P.nlevels - 1 - li;
+                int maxblk = 0;
+                for (i64 s : by_level[lev]) maxblk = std::max(maxblk, (P.snode[s].nscol + SB - 1) / SB);
+                for (int bi = 0; bi < maxblk; ++bi) {
+                    const int blk = pass == 0 ? bi : maxblk - 1 - bi;
+                    std::vector<SolveTask> diag, upd, updu;
+                    for (i64 s : by_level[lev]) {
+                        const SnodeDev &d = P.snode[s];
+                        const int j0 = blk * SB;
+                        if (j0 >= d.nscol) continue;
+                        SolveTask t = base_task(s, j0);
+                        diag.push_back(t);
+                        const int j1 = j0 + t.w;
+                        if (pass == 0 || !lu) {
+                            for (int r = j1; r < d.nsrow; r += SLAB) { t.r0 = r; t.r1 = std::min(r + SLAB, (int)d.nsrow); upd.push_back(t); }
+                        } else {
+                            // LU backward: U12 through the U12^T rows (off-diagonal rows), U11 through later panel columns
+                            for (int r = d.nscol; r < d.nsrow; r += SLAB) { t.r0 = r; t.r1 = std::min(r + SLAB, (int)d.nsrow); upd.push_back(t); }
+                            for (int c = j1; c < d.nscol; c += SLAB) { t.r0 = c; t.r1 = std::min(c + SLAB, (int)d.nscol); updu.push_back(t); }
+                        }
+                    }
+                    if (pass == 0) {
+                        push_launch(P.solve_fwd, S_DIAG_F, diag);
+                        push_launch(P.solve_fwd, S_UPD_F, upd);
+                    } else {
+                        push_launch(P.solve_bwd, S_UPD_B, upd);
+                        push_launch(P.solve_bwd, S_UPD_BU, updu);
+                        push_launch(P.solve_bwd, S_DIAG_B, diag);
+                    }
+                }
+            }
+        }
+    }
+
     // ---- copy-out tasks ------------------------------------------------------------------------------------------
     for (i64 s = 0; s < ns; ++s) {
         const SnodeDev &d = P.snode[s];

@@ -49,6 +49,14 @@ struct HostPlan {
     std::vector<Launch> launches;
     std::vector<PackTask> pack_tasks;
 
+    // triangular-solve schedule (single-GPU plans): forward levels ascending, backward descending
+    std::vector<int32_t> lsi32;             // row lists as int32
+    std::vector<int32_t> nz_col;            // column of every Lx entry (row of every Ux entry): device residual
+    std::vector<int32_t> unz_row;
+    std::vector<i64> nz_row, unz_col;       // row of every Lx entry, column of every Ux entry
+    std::vector<SolveTask> solve_tasks;
+    std::vector<SolveLaunch> solve_fwd, solve_bwd;
+
     double flops = 0.0;                     // algorithmic flops
 
     // ---- etree partition over `world` GPUs (proportional mapping of subtrees) -------------------------

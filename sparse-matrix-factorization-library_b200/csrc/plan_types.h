@@ -121,6 +121,29 @@ struct Phase {
     int32_t pad;
 };
 
+// ---- device-resident triangular solves (SparseFrame_solve_supernodal, CH.c:3036-3139 / LU.c:3592-3700) --------------
+// One task = one 64-column block of one front, optionally restricted to a slab of rows.
+struct SolveTask {
+    int64_t xoff;      // panel offset in the padded factor
+    int64_t lsip;      // offset of the front's row list
+    int32_t ld, nsrow, nscol;
+    int32_t col0;      // global index of the front's first column
+    int32_t j0, w;     // block columns [j0, j0 + w)
+    int32_t r0, r1;    // update tasks: panel rows [r0, r1)  (LU backward, U11 part: panel COLUMNS [r0, r1))
+};
+
+enum SolveKind : int32_t {
+    S_DIAG_F = 0,   // x_b = T^-1 b_b, T = lower triangle of the block (unit diagonal for LU)
+    S_UPD_F  = 1,   // b[rows] -= L[rows, b] x_b                         (rows below the block, atomics)
+    S_UPD_B  = 2,   // b_b -= L[rows, b]^T x[rows]   (Cholesky) / b_b -= U12[b, rows] x[rows] (LU, from the U12^T rows)
+    S_UPD_BU = 3,   // LU: b_b -= U11[b, later columns] x[later columns]
+    S_DIAG_B = 4,   // x_b = T^-T b_b (Cholesky) / x_b = U_bb^-1 b_b (LU)
+};
+
+struct SolveLaunch {
+    int32_t kind, first, count, pad;
+};
+
 // ---- final copy into the reference's unpadded layout -------------------------------------------------------
 struct PackTask {
     int64_t src;     // padded offset

@@ -349,6 +349,21 @@ int SparseFrame_factorize(struct common_info_struct *common_info, struct gpu_inf
 /* forward / backward substitution over the supernodal factor (CH.c:3074-3134, LU.c:3630-3694) */
 int SparseFrame_solve_supernodal(struct matrix_info_struct *m) {
     const double t0 = SparseFrame_time();
+    {   // the factor of this matrix is still resident on the GPU: substitute there (row f1) instead of the host loops
+        Cached c;
+        {
+            std::lock_guard<std::mutex> lk(g_mutex);
+            auto it = g_cache.find(m);
+            if (it != g_cache.end()) c = it->second;
+        }
+        if (c.plan && !getenv("SF_HOST_SOLVE")) {
+            memcpy(m->Xx, m->Bx, (size_t)m->nrow * sizeof(Float));
+            if (sfb200_solve(c.plan, m->Xx, 1) == SFB200_OK) {
+                m->solveTime = SparseFrame_time() - t0;
+                return 0;
+            }
+        }
+    }
     const Long n = m->nrow, ns = m->nsuper;
     const Long *Super = m->Super, *Lsip = m->Lsip, *Lsxp = m->Lsxp, *Lsi = m->Lsi;
     const Float *Lsx = m->Lsx;

@@ -17,7 +17,7 @@ SYMBOLS = [
     "sfb200_host_free", "sfb200_probe_fp64_peak", "sfb200_plan_set_stream", "sfb200_plan_profile",
     "sfb200_plan_profile_get", "sfb200_plan_create_part", "sfb200_plan_double", "sfb200_plan_phase_info",
     "sfb200_plan_reduce_info", "sfb200_plan_owner", "sfb200_plan_factor_ptr", "sfb200_phase_begin", "sfb200_phase_run",
-    "sfb200_plan_panel_offsets", "sfb200_plan_profile_launch", "sfb200_plan_bcast_info",
+    "sfb200_plan_panel_offsets", "sfb200_plan_profile_launch", "sfb200_plan_bcast_info", "sfb200_solve", "sfb200_solve_device", "sfb200_residual",
 ]
 
 
@@ -81,6 +81,9 @@ def lib():
     L.sfb200_phase_begin.argtypes = [vp, vp, vp]
     L.sfb200_phase_run.argtypes = [vp, ci, ci]
     L.sfb200_plan_bcast_info.argtypes = [vp, ci, vp]
+    L.sfb200_solve.argtypes = [vp, vp, ci]
+    L.sfb200_solve_device.argtypes = [vp, vp, ci]
+    L.sfb200_residual.argtypes = [vp, vp, vp, vp]
     L.sfb200_plan_set_stream.argtypes = [vp, vp]
     L.sfb200_plan_profile.argtypes = [vp]
     L.sfb200_plan_profile_get.restype = dbl

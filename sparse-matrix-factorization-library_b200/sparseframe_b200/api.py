@@ -247,6 +247,25 @@ class Plan:
             rows.append(out.copy())
         return np.array(rows)
 
+    def solve(self, b):
+        """x = A^-1 b on the GPU with the resident factor (permuted ordering); b: (n,) or (n, nrhs) Fortran-ordered."""
+        x = np.array(b, dtype=np.float64, order="F", copy=True)
+        nrhs = 1 if x.ndim == 1 else x.shape[1]
+        rc = _capi.lib().sfb200_solve(self._h, x.ctypes.data, nrhs)
+        if rc != 0:
+            raise RuntimeError("sfb200_solve failed (%d): %s" % (rc, _capi.last_error()))
+        return x
+
+    def residual(self, x, b):
+        """dict(anorm, bnorm, xnorm, rnorm, residual) of the permuted system, computed on the GPU."""
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        b = np.ascontiguousarray(b, dtype=np.float64)
+        out = np.zeros(5)
+        rc = _capi.lib().sfb200_residual(self._h, x.ctypes.data, b.ctypes.data, out.ctypes.data)
+        if rc != 0:
+            raise RuntimeError("sfb200_residual failed (%d): %s" % (rc, _capi.last_error()))
+        return dict(zip(("anorm", "bnorm", "xnorm", "rnorm", "residual"), out.tolist()))
+
     def last_ms(self, which=0) -> float:
         return float(_capi.lib().sfb200_last_ms(self._h, which))
 

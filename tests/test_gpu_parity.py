@@ -292,3 +292,36 @@ def test_streamed_copy_out_into_pinned_memory():
         plan.close()
         for k in env:
             os.environ.pop(k, None)
+
+
+@pytest.mark.parametrize("gen,g,kind", [("lap3d", 24, "cholesky"), ("lap2d", 150, "cholesky"), ("cd3d", 20, "lu"),
+                                        ("lap3d", 14, "lu"), ("el3d", 8, "cholesky")])
+def test_device_solve_and_residual(gen, g, kind):
+    """Row f1: forward/backward substitution and the reference's residual check on the GPU, against the oracle's
+    restatement of SparseFrame_solve_supernodal / SparseFrame_validate."""
+    A, _ = build_matrix(gen, g)
+    S = sf.analyze(A, kind)
+    st = oracle_structure(S)
+    split = "Up" in st
+    ux = S.array("Ux") if split else None
+    plan = sf.Plan(S)
+    lsx = plan.factorize(S.array("Lx"), ux)
+    n = A.n
+    b = 1.0 + np.arange(n) / n                      # the reference's right-hand side (CH.c:3186)
+    x = plan.solve(b)
+    x_ref = sforacle.solve(kind, st, lsx, b)
+    assert np.max(np.abs(x - x_ref)) <= 1e-11 * np.max(np.abs(x_ref))
+    dev = plan.residual(x, b)
+    res_ref, norms = sforacle.residual(kind, st, S.array("Lx"), b, x, ux)
+    assert dev["anorm"] == pytest.approx(norms[0], rel=1e-13)
+    assert dev["bnorm"] == norms[1] and dev["xnorm"] == norms[2]
+    assert dev["rnorm"] <= 1e-12 * dev["anorm"] * dev["xnorm"]
+    assert dev["rnorm"] / (dev["anorm"] * dev["xnorm"]) <= BACKWARD_TOL
+    # several right-hand sides at once
+    B = np.asfortranarray(np.stack([b, np.cos(np.arange(n)), np.ones(n)], axis=1))
+    Xm = plan.solve(B)
+    for k in range(3):
+        xk = sforacle.solve(kind, st, lsx, B[:, k])
+        assert np.max(np.abs(Xm[:, k] - xk)) <= 1e-11 * np.max(np.abs(xk))
+    assert plan.last_ms(2) > 0
+    plan.close()

@@ -50,3 +50,35 @@ def test_schedule_flags_indefinite():
     A = sf.compress(n, r, c, x, sym)
     _, bad, _ = sforacle.plan_check("cholesky", A.n, A.Cp, A.Ci, A.Cx, True, sf.DEFAULT_DEVSLOT)
     assert bad > 0
+
+
+@pytest.mark.parametrize("gen,g,kind", [("lap3d", 14, "cholesky"), ("lap2d", 90, "cholesky"), ("cd3d", 12, "lu"), ("lap3d", 10, "lu"),
+                                        ("el3d", 6, "cholesky")])
+def test_solve_schedule_on_interpreter(gen, g, kind):
+    """The device solve's task lists (64-column blocks, row slabs, LU's U11 / U12^T split), interpreted on the CPU:
+    x must match the oracle's restatement of SparseFrame_solve_supernodal and give a tiny backward error."""
+    import ctypes as C
+    import os
+    A, _ = build_matrix(gen, g)
+    S = sf.analyze(A, kind)
+    backend = sforacle.CheckBackend(kind, A, sf.DEFAULT_DEVSLOT, 0, 1)
+    lib = backend.L
+    lib.sfcheck_factor_solve.restype = C.c_long
+    lib.sfcheck_factor_solve.argtypes = [C.c_void_p, C.c_void_p]
+    n = A.n
+    b = 1.0 + np.arange(n) / n
+    x = b.copy()
+    assert lib.sfcheck_factor_solve(backend.h, x.ctypes.data) == 0
+    st = {k: S.array(k) for k in ("Super", "SuperMap", "Lsip", "Lsxp", "Lsi", "LeafQueue", "Lp", "Li")}
+    st["csize"], st["nsleaf"] = S.int("csize"), S.int("nsleaf")
+    split = kind == "lu" and S.int("symmetric") == 0
+    ux = None
+    if split:
+        st["Up"], st["Ui"] = S.array("Up"), S.array("Ui")
+        ux = S.array("Ux")
+    lsx, bad = sforacle.factorize(kind, st, S.array("Lx"), ux)
+    x_ref = sforacle.solve(kind, st, lsx, b)
+    assert np.max(np.abs(x - x_ref)) <= 1e-11 * np.max(np.abs(x_ref))
+    res, norms = sforacle.residual(kind, st, S.array("Lx"), b, x, ux)
+    assert norms[3] / (norms[0] * norms[2]) <= 1e-12
+    backend.close()
