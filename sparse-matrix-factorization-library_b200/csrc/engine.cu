@@ -58,6 +58,11 @@ struct sfb200_plan {
     PackTask *d_spack = nullptr;                       // pack tasks of the SMALL panels, grouped by level
     std::vector<std::pair<int, int>> spack_range;      // per level: [first, count) in d_spack
     std::vector<std::vector<i64>> big_by_level;        // per level: supernodes copied by the DMA engine
+    // small panels are first packed on the device into the dense reference layout (d_out), then leave as contiguous runs
+    // of the dense buffer: per level, [offset, count) element ranges that become final at that level.  All levels up to
+    // `merge_level` are flushed together (their supernodes are neighbours in the postorder, so the runs are long).
+    std::vector<std::vector<std::pair<i64, i64>>> small_runs;
+    int merge_level = 0;
     int top_width = 256;                               // width of the widest blocking level
     size_t device_bytes = 0;
     float ms_numeric = 0.f, ms_e2e = 0.f;
@@ -306,6 +311,30 @@ int sfb200_plan_create_part(const sfb200_symbolic *s, int device, int rank, int 
             flat.insert(flat.end(), small[l].begin(), small[l].end());
         }
         if ((err = upload(p, p->d_spack, flat))) return fail(err);
+        {
+            // flush point: the first level above which fewer than 4096 supernodes remain (the many tiny leaf-side levels
+            // go out in one batch of long runs)
+            std::vector<i64> cnt(H.nlevels + 1, 0);
+            for (i64 sidx = 0; sidx < H.nsuper; ++sidx) ++cnt[H.snode[sidx].level];
+            i64 above = H.nsuper;
+            p->merge_level = 0;
+            for (int l = 0; l < H.nlevels; ++l) { above -= cnt[l]; p->merge_level = l; if (above < 4096) break; }
+            p->small_runs.assign(H.nlevels, {});
+            auto is_small = [&](i64 sidx) {
+                const SnodeDev &d = H.snode[sidx];
+                const int rows = lu ? 2 * d.nsrow - d.nscol : d.nsrow;
+                return (i64)rows * d.nscol * 8 < (1 << 20);
+            };
+            auto flush_level = [&](i64 sidx) { return std::max<int>(H.snode[sidx].level, p->merge_level); };
+            for (i64 sidx = 0; sidx < H.nsuper;) {
+                if (!is_small(sidx)) { ++sidx; continue; }
+                const int fl = flush_level(sidx);
+                i64 e = sidx + 1;
+                while (e < H.nsuper && is_small(e) && flush_level(e) == fl) ++e;
+                p->small_runs[fl].push_back({H.lsxp[sidx], H.lsxp[e] - H.lsxp[sidx]});
+                sidx = e;
+            }
+        }
         if (prm.lookahead) {
             if (const char *e = getenv("SFB200_SPARE_SMS")) p->spare_sms = atoi(e);
             int lo_prio = 0, hi_prio = 0;
@@ -501,8 +530,12 @@ int copy_columns(sfb200_plan *p, i64 sidx, int c0, int c1, double *Lsx) {
 
 // Factorization with the copy-out streamed behind it: as soon as an etree level (or, for the widest fronts, a block
 // column of the level) is final, its panels leave for the host on a second stream while the next level computes.
-int factorize_streamed(sfb200_plan *p, double *Lsx, double *Lsx_dev_alias) {
+int factorize_streamed(sfb200_plan *p, double *Lsx) {
     const HostPlan &H = p->H;
+    if (!p->d_out) {
+        CK(cudaMalloc((void **)&p->d_out, sizeof(double) * (size_t)std::max<i64>(H.xsize, 1)));
+        p->device_bytes += sizeof(double) * (size_t)H.xsize;
+    }
     int rc = begin_factor(p);
     if (rc) return rc;
     p->copy_events_used = 0;
@@ -545,7 +578,10 @@ int factorize_streamed(sfb200_plan *p, double *Lsx, double *Lsx_dev_alias) {
             if (sent[b] < n) { rc = copy_columns(p, big[b], sent[b], n, Lsx); if (rc) return rc; }
         }
         const auto range = p->spack_range[lev];
-        if (range.second > 0) launch_pack(p->d_X, Lsx_dev_alias, p->d_spack + range.first, range.second, p->copy_stream);
+        if (range.second > 0) launch_pack(p->d_X, p->d_out, p->d_spack + range.first, range.second, p->copy_stream);
+        for (const auto &run : p->small_runs[lev])
+            CK(cudaMemcpyAsync(Lsx + run.first, p->d_out + run.first, sizeof(double) * (size_t)run.second, cudaMemcpyDeviceToHost,
+                               p->copy_stream));
     }
     CK(cudaGetLastError());
     CK(cudaEventRecord(p->ev[1], p->stream));            // end of the numeric work; the copy tail is only in the e2e time
@@ -576,7 +612,7 @@ int sfb200_factorize(sfb200_plan *p, const double *Lx, const double *Ux, double 
     int rc;
     if (alias) {
         CK(cudaEventRecord(p->ev[0], p->stream));
-        rc = factorize_streamed(p, Lsx, alias);
+        rc = factorize_streamed(p, Lsx);
         if (rc) return rc;
         p->factored = true;
     } else {
