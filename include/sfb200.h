@@ -80,27 +80,27 @@ int sfb200_device_count(void);
 int sfb200_plan_create(const sfb200_symbolic *s, int device, sfb200_plan **out);
 
 /* One rank of an etree-subtree partition over `world` GPUs (one process per GPU).  Whole subtrees are local to a rank;
- * the supernodes above them ("top") are owned by single ranks and receive partial updates from several: every rank keeps
- * a full-size zero-initialised image of the factor, accumulates its updates there, and before level L is factorized
- * the images of level L's shared panels are summed into their owners.  The sums are the caller's job (NCCL reduce
- * through torch.distributed in sparseframe_b200/parallel.py): the plan only lists them.
- *   sfb200_plan_int: "nphases", "nreduces", "rank", "world";  sfb200_plan_double: "flops", "local_flops"
- *   phase k  = etree level k: reduce steps -> launches part 0 -> broadcasts of the shared panels factorized in part 0
- *              (owner -> group) -> launches part 1 (every rank computes 1/G of those fronts' Schur-update tiles)
- *   reduce i = {offset, count (elements of the padded factor), root, lo, hi}: ranks in [lo,hi) take part, root receives;
- *              the list is identical on every rank. */
+ * the supernodes above them ("top") are shared by a contiguous group of ranks [lo,hi) and receive partial updates from
+ * all of them: every rank keeps a full-size zero-initialised image of the factor and accumulates its updates there.
+ * The plan of a rank is a list of SEGMENTS; a segment is a list of collectives on regions of that image followed by
+ * kernel launches.  The collectives are the caller's job (NCCL through torch.distributed in
+ * sparseframe_b200/parallel.py, on the plan's stream): the plan only lists them, identically on every rank.
+ *   sfb200_plan_int: "nsegments", "ncolls", "rank", "world";  sfb200_plan_double: "flops", "local_flops"
+ *   segment k = {coll_first, coll_count, launch_first, launch_count, level}
+ *   coll i    = {type, offset, count (elements of the padded factor), root, lo, hi}; ranks outside [lo,hi) skip it
+ *       type 0 reduce:     the images of a shared panel are summed into its owner (root) before it is factorized
+ *       type 1 all-reduce: ... into every rank of the group (wide Cholesky panels are factorized by the whole group,
+ *                          block columns owned round-robin)
+ *       type 2 broadcast:  root's image of a factored panel / block column replaces the group's */
 int sfb200_plan_create_part(const sfb200_symbolic *s, int device, int rank, int world, sfb200_plan **out);
 double sfb200_plan_double(const sfb200_plan *p, const char *name);
-int sfb200_plan_phase_info(const sfb200_plan *p, int k, int64_t out[9]);   /* + {bcast_first, bcast_count, launch_b_first, launch_b_count} */
-int sfb200_plan_bcast_info(const sfb200_plan *p, int i, int64_t out[5]);   /* factored shared panel: root sends to [lo,hi) */
-int sfb200_plan_reduce_info(const sfb200_plan *p, int i, int64_t out[5]);
+int sfb200_plan_segment_info(const sfb200_plan *p, int k, int64_t out[5]);
+int sfb200_plan_coll_info(const sfb200_plan *p, int i, int64_t out[6]);
 int sfb200_plan_owner(const sfb200_plan *p, int32_t *owner /* nsuper */);
 void *sfb200_plan_factor_ptr(sfb200_plan *p);                 /* device pointer of the padded factor image */
 int sfb200_plan_panel_offsets(const sfb200_plan *p, int64_t *xoff /* nsuper + 1 */);   /* panel offsets in that image */
-int sfb200_phase_begin(sfb200_plan *p, const double *d_Lx, const double *d_Ux);   /* zero + assemble owned panels */
-int sfb200_phase_run(sfb200_plan *p, int k, int part);        /* launches of phase k, asynchronous.  part 0: the level's
-                                                               * fronts; part 1 (after the phase's broadcasts): this rank's
-                                                               * share of the Schur-update tiles of the shared fronts */
+int sfb200_partition_begin(sfb200_plan *p, const double *d_Lx, const double *d_Ux);   /* zero + assemble owned panels */
+int sfb200_segment_run(sfb200_plan *p, int k);                /* launches of segment k, asynchronous on the plan's stream */
 void sfb200_plan_free(sfb200_plan *p);
 
 /* Scalars: "nlevels","nlaunches","nsmall","nlarge","relmap_entries","xsize_padded","device_bytes", ... */

@@ -217,6 +217,7 @@ void *sfcheck_open(int kind, int is_symmetric, long n, const long *Cp, const lon
     if (small_b >= 0) prm.small_b_bytes = small_b;
     if (ld_align > 0) prm.ld_align = ld_align;
     if (const char *e = getenv("SFCHECK_DIST_MIN_M")) prm.dist_scatter_min_m = atoi(e);
+    if (const char *e = getenv("SFCHECK_DIST_PANEL_MIN")) prm.dist_panel_min_cols = atoi(e);
     if (build_plan(h->S, prm, h->P, rank, world) != 0) { delete h; return nullptr; }
     return h;
 }
@@ -233,8 +234,8 @@ long sfcheck_int(void *hv, const char *name) {
     if (k == "xsize_pad") return P.xsize_pad;
     if (k == "xsize") return P.xsize;
     if (k == "nphases") return (long)P.phases.size();
-    if (k == "nreduces") return (long)P.reduces.size();
-    if (k == "nbcasts") return (long)P.bcasts.size();
+    if (k == "nsegments") return (long)P.segments.size();
+    if (k == "ncolls") return (long)P.colls.size();
     if (k == "nsuper") return P.nsuper;
     return -1;
 }
@@ -245,21 +246,15 @@ double sfcheck_double(void *hv, const char *name) {
     if (k == "local_flops") return P.local_flops;
     return -1;
 }
-/* out[9] = {reduce_first, reduce_count, launch_first, launch_count, level, bcast_first, bcast_count, launch_b_first, launch_b_count} */
-void sfcheck_phase(void *hv, int k, long *out) {
-    const Phase &ph = ((CheckHandle *)hv)->P.phases[k];
-    out[0] = ph.reduce_first; out[1] = ph.reduce_count; out[2] = ph.launch_first; out[3] = ph.launch_count; out[4] = ph.level;
-    out[5] = ph.bcast_first; out[6] = ph.bcast_count; out[7] = ph.launch_b_first; out[8] = ph.launch_b_count;
+/* out[5] = {coll_first, coll_count, launch_first, launch_count, level} */
+void sfcheck_segment(void *hv, int k, long *out) {
+    const Segment &sg = ((CheckHandle *)hv)->P.segments[k];
+    out[0] = sg.coll_first; out[1] = sg.coll_count; out[2] = sg.launch_first; out[3] = sg.launch_count; out[4] = sg.level;
 }
-/* out = {offset, count, root, lo, hi} */
-void sfcheck_bcast(void *hv, int i, long *out) {
-    const ReduceStep &r = ((CheckHandle *)hv)->P.bcasts[i];
-    out[0] = r.offset; out[1] = r.count; out[2] = r.root; out[3] = r.lo; out[4] = r.hi;
-}
-/* out = {offset, count, root, lo, hi} */
-void sfcheck_reduce(void *hv, int i, long *out) {
-    const ReduceStep &r = ((CheckHandle *)hv)->P.reduces[i];
-    out[0] = r.offset; out[1] = r.count; out[2] = r.root; out[3] = r.lo; out[4] = r.hi;
+/* out[6] = {type, offset, count, root, lo, hi} */
+void sfcheck_coll(void *hv, int i, long *out) {
+    const Coll &c = ((CheckHandle *)hv)->P.colls[i];
+    out[0] = c.type; out[1] = c.offset; out[2] = c.count; out[3] = c.root; out[4] = c.lo; out[5] = c.hi;
 }
 void sfcheck_owner(void *hv, int *owner) {
     const HostPlan &P = ((CheckHandle *)hv)->P;
@@ -267,10 +262,10 @@ void sfcheck_owner(void *hv, int *owner) {
 }
 /* X: xsize_pad doubles, zeroed by the caller */
 void sfcheck_begin(void *hv, double *X) { assemble(*(CheckHandle *)hv, X); }
-long sfcheck_run_phase(void *hv, int k, int part, double *X) {
+long sfcheck_run_segment(void *hv, int k, double *X) {
     const HostPlan &P = ((CheckHandle *)hv)->P;
-    const Phase &ph = P.phases[k];
-    return part == 0 ? run_launches(P, X, ph.launch_first, ph.launch_count) : run_launches(P, X, ph.launch_b_first, ph.launch_b_count);
+    const Segment &sg = P.segments[k];
+    return run_launches(P, X, sg.launch_first, sg.launch_count);
 }
 /* copy only the panels this rank owns into Lsx_out (reference layout); others are left untouched */
 void sfcheck_pack_owned(void *hv, const double *X, double *Lsx_out) {
@@ -370,12 +365,12 @@ long sfcheck_factorize(int kind, int is_symmetric, long n, const long *Cp, const
     return bad;
 }
 
-/* All `world` ranks simulated in one process: every rank has its own zeroed image of the padded factor, phases run in
- * lock step, reduce steps sum the images of the contributing ranks into the owner's.  Lsx_out = union of the owned
- * panels.  balance[r] receives the flops owned by rank r. */
+/* All `world` ranks simulated in one process: every rank has its own zeroed image of the padded factor, segments run in
+ * lock step, the collectives of a segment act on the images of the ranks of their group.  Lsx_out = union of the owned
+ * panels.  balance[r] receives the flops owned by rank r; ncoll_out[3] counts the collectives met by type. */
 long sfcheck_factorize_partitioned(int kind, int is_symmetric, long n, const long *Cp, const long *Ci, const double *Cx,
                                    unsigned long long dev_slot, int nb, int outer, int small_a, int small_b, int world,
-                                   double *Lsx_out, double *balance, long *nreduce_out) {
+                                   double *Lsx_out, double *balance, long *ncoll_out) {
     std::vector<CheckHandle *> H(world);
     for (int r = 0; r < world; ++r) {
         H[r] = (CheckHandle *)sfcheck_open(kind, is_symmetric, n, Cp, Ci, Cx, dev_slot, nb, outer, small_a, small_b, 0, r, world);
@@ -384,56 +379,47 @@ long sfcheck_factorize_partitioned(int kind, int is_symmetric, long n, const lon
     const i64 xp = H[0]->P.xsize_pad;
     std::vector<std::vector<double>> X(world, std::vector<double>(xp, 0.0));
     for (int r = 0; r < world; ++r) { assemble(*H[r], X[r].data()); if (balance) balance[r] = H[r]->P.local_flops; }
-    long bad = 0, nred = 0;
-    const size_t nph = H[0]->P.phases.size();
-    for (size_t k = 0; k < nph; ++k) {
-        // collectives first: every contributing rank must list the same step
-        for (int r = 0; r < world; ++r) {
-            const Phase &ph = H[r]->P.phases[k];
-            for (int i = ph.reduce_first; i < ph.reduce_first + ph.reduce_count; ++i) {
-                const ReduceStep &st = H[r]->P.reduces[i];
-                if (st.root != r) continue;                       // the owner drives the sum
-                for (int q = st.lo; q < st.hi; ++q) {
-                    if (q == r) continue;
-                    // every rank must hold the identical step at the identical position (collectives are matched by order)
-                    const ReduceStep &sq = H[q]->P.reduces[i];
-                    if (sq.offset != st.offset || sq.count != st.count || sq.root != st.root || sq.lo != st.lo || sq.hi != st.hi) return -200;
-                    for (i64 e = 0; e < st.count; ++e) X[r][st.offset + e] += X[q][st.offset + e];
-                }
+    long bad = 0, ncoll[3] = {0, 0, 0};
+    const size_t nseg = H[0]->P.segments.size();
+    for (int r = 1; r < world; ++r)
+        if (H[r]->P.segments.size() != nseg || H[r]->P.colls.size() != H[0]->P.colls.size()) return -199;
+    std::vector<double> sum;
+    for (size_t k = 0; k < nseg; ++k) {
+        const Segment &sg = H[0]->P.segments[k];
+        for (int i = sg.coll_first; i < sg.coll_first + sg.coll_count; ++i) {
+            const Coll &c = H[0]->P.colls[i];
+            // every rank must hold the identical step at the identical position (collectives are matched by order)
+            for (int q = 1; q < world; ++q) {
+                const Coll &cq = H[q]->P.colls[i];
+                const Segment &sq = H[q]->P.segments[k];
+                if (sq.coll_first != sg.coll_first || sq.coll_count != sg.coll_count) return -198;
+                if (cq.type != c.type || cq.offset != c.offset || cq.count != c.count || cq.root != c.root || cq.lo != c.lo || cq.hi != c.hi) return -200;
+            }
+            if (c.type == C_BCAST) {
+                for (int q = c.lo; q < c.hi; ++q)
+                    if (q != c.root) std::memcpy(X[q].data() + c.offset, X[c.root].data() + c.offset, sizeof(double) * c.count);
+            } else {
                 // ranks outside [lo,hi) must not have touched the panel
                 for (int q = 0; q < world; ++q)
-                    if (q < st.lo || q >= st.hi)
-                        for (i64 e = 0; e < st.count; ++e) if (X[q][st.offset + e] != 0.0) return -201;
-                ++nred;
+                    if (q < c.lo || q >= c.hi)
+                        for (i64 e = 0; e < c.count; ++e) if (X[q][c.offset + e] != 0.0) return -201;
+                sum.assign(X[c.root].begin() + c.offset, X[c.root].begin() + c.offset + c.count);
+                for (int q = c.lo; q < c.hi; ++q)
+                    if (q != c.root) for (i64 e = 0; e < c.count; ++e) sum[e] += X[q][c.offset + e];
+                for (int q = c.lo; q < c.hi; ++q)
+                    if (q == c.root || c.type == C_ALLREDUCE) std::memcpy(X[q].data() + c.offset, sum.data(), sizeof(double) * c.count);
             }
+            ++ncoll[c.type];
         }
         for (int r = 0; r < world; ++r) {
-            const long b = run_launches(H[r]->P, X[r].data(), H[r]->P.phases[k].launch_first, H[r]->P.phases[k].launch_count);
-            if (b < 0) return b;
-            bad += b;
-        }
-        // factored shared panels travel from the owner to its group ...
-        {
-            const Phase &ph = H[0]->P.phases[k];
-            for (int i = ph.bcast_first; i < ph.bcast_first + ph.bcast_count; ++i) {
-                const ReduceStep &st = H[0]->P.bcasts[i];
-                for (int q = st.lo; q < st.hi; ++q) {
-                    const ReduceStep &sq = H[q]->P.bcasts[i];
-                    if (sq.offset != st.offset || sq.count != st.count || sq.root != st.root) return -202;
-                    if (q != st.root) std::memcpy(X[q].data() + st.offset, X[st.root].data() + st.offset, sizeof(double) * st.count);
-                }
-                ++nred;
-            }
-        }
-        // ... and every rank of the group computes its share of their Schur-update tiles
-        for (int r = 0; r < world; ++r) {
-            const long b = run_launches(H[r]->P, X[r].data(), H[r]->P.phases[k].launch_b_first, H[r]->P.phases[k].launch_b_count);
+            const Segment &sr = H[r]->P.segments[k];
+            const long b = run_launches(H[r]->P, X[r].data(), sr.launch_first, sr.launch_count);
             if (b < 0) return b;
             bad += b;
         }
     }
     for (int r = 0; r < world; ++r) sfcheck_pack_owned(H[r], X[r].data(), Lsx_out);
-    if (nreduce_out) *nreduce_out = nred;
+    if (ncoll_out) for (int t = 0; t < 3; ++t) ncoll_out[t] = ncoll[t];
     for (auto *h : H) delete h;
     return bad;
 }

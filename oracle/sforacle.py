@@ -133,13 +133,12 @@ class CheckBackend:
         L.sfcheck_int.argtypes = [C.c_void_p, C.c_char_p]
         L.sfcheck_double.restype = C.c_double
         L.sfcheck_double.argtypes = [C.c_void_p, C.c_char_p]
-        for f in ("sfcheck_phase", "sfcheck_reduce"):
+        for f in ("sfcheck_segment", "sfcheck_coll"):
             getattr(L, f).argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         L.sfcheck_owner.argtypes = [C.c_void_p, C.c_void_p]
         L.sfcheck_begin.argtypes = [C.c_void_p, C.c_void_p]
-        L.sfcheck_run_phase.restype = C.c_long
-        L.sfcheck_run_phase.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
-        L.sfcheck_bcast.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        L.sfcheck_run_segment.restype = C.c_long
+        L.sfcheck_run_segment.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         L.sfcheck_pack_owned.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.sfcheck_close.argtypes = [C.c_void_p]
         self.L = L
@@ -149,22 +148,18 @@ class CheckBackend:
         if not self.h:
             raise RuntimeError("sfcheck_open failed")
         self.rank, self.world = rank, world
-        self.nphases = self.int("nphases")
         self.X = np.zeros(self.int("xsize_pad"))
         self.image = torch.from_numpy(self.X)          # shares memory with X
         self.bad = 0
 
-        def info(fn, k, n=5):
+        def info(fn, k, n):
             out = np.zeros(n, dtype=np.int64)
             fn(self.h, k, out.ctypes.data)
             return [int(v) for v in out]
-        self.phases = [dict(zip(("reduce_first", "reduce_count", "launch_first", "launch_count", "level", "bcast_first",
-                                 "bcast_count", "launch_b_first", "launch_b_count"), info(L.sfcheck_phase, k, 9)))
-                       for k in range(self.nphases)]
-        self.reduces = [dict(zip(("offset", "count", "root", "lo", "hi"), info(L.sfcheck_reduce, i)))
-                        for i in range(self.int("nreduces"))]
-        self.bcasts = [dict(zip(("offset", "count", "root", "lo", "hi"), info(L.sfcheck_bcast, i)))
-                       for i in range(self.int("nbcasts"))]
+        self.segments = [dict(zip(("coll_first", "coll_count", "launch_first", "launch_count", "level"),
+                                  info(L.sfcheck_segment, k, 5))) for k in range(self.int("nsegments"))]
+        self.colls = [dict(zip(("type", "offset", "count", "root", "lo", "hi"), info(L.sfcheck_coll, i, 6)))
+                      for i in range(self.int("ncolls"))]
 
     def int(self, name):
         return int(self.L.sfcheck_int(self.h, name.encode()))
@@ -182,8 +177,8 @@ class CheckBackend:
         self.bad = 0
         self.L.sfcheck_begin(self.h, self.X.ctypes.data)
 
-    def run_phase(self, k, part=0):
-        self.bad += self.L.sfcheck_run_phase(self.h, k, part, self.X.ctypes.data)
+    def run_segment(self, k):
+        self.bad += self.L.sfcheck_run_segment(self.h, k, self.X.ctypes.data)
 
     def finish(self):
         pass

@@ -46,8 +46,8 @@ for it in range(4):
     dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     if rank == 0:
         print("iter %d: %.2f ms  %.2f TFLOP/s (world %d)" % (it, ms.item(), S.flops / ms.item() / 1e9, world), flush=True)
-print("rank %d: analyze %.1fs, owns %.3f of the flops, reduces %d, reduced %.3f GB, phases %d, launches %d" % (
-    rank, t_an, share, plan.int("nreduces"), pf.reduced_bytes / 1e9, plan.int("nphases"), plan.int("nlaunches")), flush=True)
+print("rank %d: analyze %.1fs, owns %.3f of the flops, collectives %d, reduced %.3f GB, segments %d, launches %d" % (
+    rank, t_an, share, plan.int("ncolls"), pf.reduced_bytes / 1e9, plan.int("nsegments"), plan.int("nlaunches")), flush=True)
 if check:
     mine = plan.download()
     mask = owned_mask(plan.owner(), S.array("Lsxp"), rank)

@@ -171,7 +171,6 @@ int run_schedule(sfb200_plan *p) {
     if (rc) return rc;
     for (const Phase &ph : p->H.phases) {        // level by level: each one ends with the side stream joined
         if ((rc = run_launches(p, (size_t)ph.launch_first, (size_t)ph.launch_count))) return rc;
-        if ((rc = run_launches(p, (size_t)ph.launch_b_first, (size_t)ph.launch_b_count))) return rc;
     }
     return SFB200_OK;
 }
@@ -238,6 +237,7 @@ int sfb200_plan_create_part(const sfb200_symbolic *s, int device, int rank, int 
     if (const char *e = getenv("SFB200_SMALL_B")) prm.small_b_bytes = atoi(e);
     if (const char *e = getenv("SFB200_GEMM128_MIN")) prm.gemm128_min_m = atoi(e);
     if (const char *e = getenv("SFB200_DIST_MIN_M")) prm.dist_scatter_min_m = atoi(e);
+    if (const char *e = getenv("SFB200_DIST_PANEL_MIN")) prm.dist_panel_min_cols = atoi(e);
     if (const char *e = getenv("SFB200_GEMM_WS")) prm.use_ws = atoi(e);
     if (const char *e = getenv("SFB200_LOOKAHEAD")) prm.lookahead = atoi(e);
     const int rc = build_plan(s->S, prm, p->H, rank, world);
@@ -382,8 +382,8 @@ int64_t sfb200_plan_int(const sfb200_plan *p, const char *name) {
     if (k == "diag_ops") return (int64_t)H.diag_ops.size();
     if (k == "device") return p->device;
     if (k == "nphases") return (int64_t)H.phases.size();
-    if (k == "nreduces") return (int64_t)H.reduces.size();
-    if (k == "nbcasts") return (int64_t)H.bcasts.size();
+    if (k == "nsegments") return (int64_t)H.segments.size();
+    if (k == "ncolls") return (int64_t)H.colls.size();
     if (k == "rank") return H.rank;
     if (k == "world") return H.world;
     if (k == "nsuper") return H.nsuper;
@@ -398,25 +398,17 @@ double sfb200_plan_double(const sfb200_plan *p, const char *name) {
     return -1.0;
 }
 
-int sfb200_plan_phase_info(const sfb200_plan *p, int k, int64_t *out) {
-    if (!p || !out || k < 0 || k >= (int)p->H.phases.size()) return SFB200_ERR_ARG;
-    const Phase &ph = p->H.phases[k];
-    out[0] = ph.reduce_first; out[1] = ph.reduce_count; out[2] = ph.launch_first; out[3] = ph.launch_count; out[4] = ph.level;
-    out[5] = ph.bcast_first; out[6] = ph.bcast_count; out[7] = ph.launch_b_first; out[8] = ph.launch_b_count;
+int sfb200_plan_segment_info(const sfb200_plan *p, int k, int64_t *out) {
+    if (!p || !out || k < 0 || k >= (int)p->H.segments.size()) return SFB200_ERR_ARG;
+    const Segment &sg = p->H.segments[k];
+    out[0] = sg.coll_first; out[1] = sg.coll_count; out[2] = sg.launch_first; out[3] = sg.launch_count; out[4] = sg.level;
     return SFB200_OK;
 }
 
-int sfb200_plan_bcast_info(const sfb200_plan *p, int i, int64_t *out) {
-    if (!p || !out || i < 0 || i >= (int)p->H.bcasts.size()) return SFB200_ERR_ARG;
-    const ReduceStep &r = p->H.bcasts[i];
-    out[0] = r.offset; out[1] = r.count; out[2] = r.root; out[3] = r.lo; out[4] = r.hi;
-    return SFB200_OK;
-}
-
-int sfb200_plan_reduce_info(const sfb200_plan *p, int i, int64_t *out) {
-    if (!p || !out || i < 0 || i >= (int)p->H.reduces.size()) return SFB200_ERR_ARG;
-    const ReduceStep &r = p->H.reduces[i];
-    out[0] = r.offset; out[1] = r.count; out[2] = r.root; out[3] = r.lo; out[4] = r.hi;
+int sfb200_plan_coll_info(const sfb200_plan *p, int i, int64_t *out) {
+    if (!p || !out || i < 0 || i >= (int)p->H.colls.size()) return SFB200_ERR_ARG;
+    const Coll &c = p->H.colls[i];
+    out[0] = c.type; out[1] = c.offset; out[2] = c.count; out[3] = c.root; out[4] = c.lo; out[5] = c.hi;
     return SFB200_OK;
 }
 
@@ -435,8 +427,8 @@ int sfb200_plan_panel_offsets(const sfb200_plan *p, int64_t *xoff) {
     return SFB200_OK;
 }
 
-int sfb200_phase_begin(sfb200_plan *p, const double *d_Lx, const double *d_Ux) {
-    if (!p || !d_Lx) { set_error("sfb200_phase_begin: bad argument"); return SFB200_ERR_ARG; }
+int sfb200_partition_begin(sfb200_plan *p, const double *d_Lx, const double *d_Ux) {
+    if (!p || !d_Lx) { set_error("sfb200_partition_begin: bad argument"); return SFB200_ERR_ARG; }
     CK(cudaSetDevice(p->device));
     const HostPlan &H = p->H;
     CK(cudaEventRecord(p->ev[0], p->stream));
@@ -448,15 +440,13 @@ int sfb200_phase_begin(sfb200_plan *p, const double *d_Lx, const double *d_Ux) {
     return begin_factor(p);
 }
 
-int sfb200_phase_run(sfb200_plan *p, int k, int part) {
-    if (!p || k < 0 || k >= (int)p->H.phases.size()) { set_error("sfb200_phase_run: bad phase"); return SFB200_ERR_ARG; }
+int sfb200_segment_run(sfb200_plan *p, int k) {
+    if (!p || k < 0 || k >= (int)p->H.segments.size()) { set_error("sfb200_segment_run: bad segment"); return SFB200_ERR_ARG; }
     CK(cudaSetDevice(p->device));
-    const Phase &ph = p->H.phases[k];
-    const int rc = part == 0 ? run_launches(p, (size_t)ph.launch_first, (size_t)ph.launch_count)
-                             : run_launches(p, (size_t)ph.launch_b_first, (size_t)ph.launch_b_count);
+    const Segment &sg = p->H.segments[k];
+    const int rc = run_launches(p, (size_t)sg.launch_first, (size_t)sg.launch_count);
     if (rc) return rc;
-    const bool last = k + 1 == (int)p->H.phases.size() && (part == 1 || ph.launch_b_count == 0);
-    if (last) {
+    if (k + 1 == (int)p->H.segments.size()) {
         CK(cudaEventRecord(p->ev[1], p->stream));
         p->factored = true;
     }

@@ -331,72 +331,13 @@ int build_plan(const Symbolic &S, const PlanParams &prm, HostPlan &P, int rank, 
     const int small_limits[4] = {std::min(2048, prm.small_a_bytes), prm.small_a_bytes, std::min(16384, prm.small_b_bytes),
                                  prm.small_b_bytes};
 
+    // top-level stride of the slot numbering (see PanelEmitter): slots of one top-level block column are consecutive
+    int top_stride = 2 + 1;
+    for (size_t d = 1; d < widths.size(); ++d) top_stride = (widths[d] / widths[d - 1]) * top_stride + 1;
+    const std::vector<int> dist_widths = {prm.nb, prm.outer};       // blocking inside group-factorized panels
+    const int Wd = prm.outer;
+
     for (int lev = 0; lev < P.nlevels; ++lev) {
-        std::vector<i64> cls[4];
-        std::map<int, SlotOps> slots;
-        std::vector<GemmOp> scatter;
-        Phase ph{};
-        ph.level = lev;
-        ph.reduce_first = (int32_t)P.reduces.size();
-        ph.launch_first = (int32_t)P.launches.size();
-        ph.bcast_first = (int32_t)P.bcasts.size();
-        std::vector<GemmOp> scatter_dist;           // this rank's share of the Schur updates of shared fronts
-        for (i64 s : by_level[lev]) {
-            const SnodeDev &d = P.snode[s];
-            const int m = d.nsrow - d.nscol;
-            const int glo = P.group_lo[s], ghi = P.group_hi[s];
-            const bool shared = ghi - glo > 1;
-            if (shared)      // the same list on every rank; a rank outside [lo,hi) skips the step
-                P.reduces.push_back(ReduceStep{d.xoff, (i64)d.ld * d.nscol, P.owner[s], glo, ghi});
-            // Schur update of a shared front: the owner broadcasts the factored panel to its group and every rank of
-            // the group computes 1/G of the update tiles into its own image of the ancestors (summed later anyway)
-            const bool dist = shared && m >= prm.dist_scatter_min_m;
-            auto scatter_ops = [&](std::vector<GemmOp> &out, int mod, int rem) {
-                if (m <= 0) return;
-                GemmOp g{};
-                g.lda = g.ldb = d.ld; g.ldc = 0; g.M = g.N = m; g.K = d.nscol;
-                g.meta = d.lsip + d.nscol;
-                g.tile_mod = mod; g.tile_rem = rem;
-                if (!lu) {
-                    g.a_off = g.b_off = d.xoff + d.nscol;
-                    g.flags = G_LOWER | G_SCATTER;
-                    out.push_back(g);
-                } else {
-                    g.a_off = d.xoff + d.nscol; g.b_off = d.xoff + d.nsrow;      // L21 * (U12^T)^T, rows >= seg begin
-                    g.flags = G_SCATTER | G_LIM_SEGB;
-                    out.push_back(g);
-                    g.a_off = d.xoff + d.nsrow; g.b_off = d.xoff + d.nscol;      // U12^T * L21^T, rows >= seg end
-                    g.flags = G_SCATTER | G_LIM_SEGE;
-                    out.push_back(g);
-                }
-            };
-            if (dist) {
-                P.bcasts.push_back(ReduceStep{d.xoff, (i64)d.ld * d.nscol, P.owner[s], glo, ghi});
-                if (rank >= glo && rank < ghi) scatter_ops(scatter_dist, ghi - glo, rank - glo);
-            }
-            if (!mine(s)) continue;
-            const i64 pb = panel_bytes(d);
-            int c = -1;
-            if (d.nsrow - d.nscol <= prm.small_max_m)
-                for (int k = 0; k < 4; ++k) if (pb <= small_limits[k]) { c = k; break; }
-            if (c >= 0 && !dist) { cls[c].push_back(s); ++P.nsmall; continue; }
-            ++P.nlarge;
-            { PanelEmitter pe(d, lu, widths, slots); pe.lookahead = prm.lookahead != 0; pe.run(); }
-            if (!dist) scatter_ops(scatter, 1, 0);
-        }
-        for (int c = 0; c < 4; ++c) {
-            if (cls[c].empty()) continue;
-            Launch L{};
-            L.kind = c < 2 ? L_SMALL_A : L_SMALL_B;
-            L.level = lev;
-            L.top_block = -1;
-            L.first = (int32_t)P.small_tasks.size();
-            L.count = L.grid = (int32_t)cls[c].size();
-            i64 smem = 0;
-            for (i64 s : cls[c]) { P.small_tasks.push_back((int32_t)s); smem = std::max(smem, panel_bytes(P.snode[s])); }
-            L.smem = (int32_t)smem;
-            P.launches.push_back(L);
-        }
         auto emit_gemm = [&](std::vector<GemmOp> &ops, int top_block, int lflags = 0) {
             // longest tiles first: the CTAs of a launch are dispatched in index order, so the deep-K ops must not be
             // the ones left running alone at the end of the launch
@@ -426,44 +367,197 @@ int build_plan(const Symbolic &S, const PlanParams &prm, HostPlan &P, int rank, 
                 if (L.count > 0) P.launches.push_back(L);
             }
         };
-        // slots of one top-level block column are consecutive: slot / (nslots of a top-level sub-block + 1)
-        int top_stride = 2 + 1;
-        for (size_t d = 1; d < widths.size(); ++d) top_stride = (widths[d] / widths[d - 1]) * top_stride + 1;
-        for (auto &kv : slots) {
-            SlotOps &so = kv.second;
-            const int top_block = kv.first / top_stride;
-            if (!so.diag.empty()) {
-                Launch L{};
-                L.kind = lu ? L_GETRF : L_POTRF; L.level = lev; L.top_block = top_block;
-                L.first = (int32_t)P.diag_ops.size();
-                L.count = L.grid = (int32_t)so.diag.size();
-                P.diag_ops.insert(P.diag_ops.end(), so.diag.begin(), so.diag.end());
-                P.launches.push_back(L);
-            }
-            if (!so.trsm.empty()) {
-                Launch L{};
-                L.kind = L_TRSM; L.level = lev; L.top_block = top_block;
-                L.first = (int32_t)P.trsm_ops.size();
-                i64 ctas = 0;
-                for (TrsmOp t : so.trsm) {
-                    t.tile0 = (int32_t)ctas;
-                    ctas += (t.nvec + 63) / 64;
-                    P.trsm_ops.push_back(t);
+        auto emit_slots = [&](std::map<int, SlotOps> &slots, int stride) {
+            for (auto &kv : slots) {
+                SlotOps &so = kv.second;
+                const int top_block = stride > 0 ? kv.first / stride : -1;
+                if (!so.diag.empty()) {
+                    Launch L{};
+                    L.kind = lu ? L_GETRF : L_POTRF; L.level = lev; L.top_block = top_block;
+                    L.first = (int32_t)P.diag_ops.size();
+                    L.count = L.grid = (int32_t)so.diag.size();
+                    P.diag_ops.insert(P.diag_ops.end(), so.diag.begin(), so.diag.end());
+                    P.launches.push_back(L);
                 }
-                L.count = (int32_t)so.trsm.size();
-                L.grid = (int32_t)ctas;
-                P.launches.push_back(L);
+                if (!so.trsm.empty()) {
+                    Launch L{};
+                    L.kind = L_TRSM; L.level = lev; L.top_block = top_block;
+                    L.first = (int32_t)P.trsm_ops.size();
+                    i64 ctas = 0;
+                    for (TrsmOp t : so.trsm) {
+                        t.tile0 = (int32_t)ctas;
+                        ctas += (t.nvec + 63) / 64;
+                        P.trsm_ops.push_back(t);
+                    }
+                    L.count = (int32_t)so.trsm.size();
+                    L.grid = (int32_t)ctas;
+                    P.launches.push_back(L);
+                }
+                if (!so.gemm.empty()) emit_gemm(so.gemm, top_block, so.next_of_split ? LF_WAIT_SIDE : 0);
+                if (!so.side.empty()) emit_gemm(so.side, top_block, LF_SIDE);
             }
-            if (!so.gemm.empty()) emit_gemm(so.gemm, top_block, so.next_of_split ? LF_WAIT_SIDE : 0);
-            if (!so.side.empty()) emit_gemm(so.side, top_block, LF_SIDE);
+        };
+        // a segment = the collectives gathered so far, then the launches emitted since the previous segment ended
+        Phase ph{};
+        ph.level = lev;
+        ph.launch_first = (int32_t)P.launches.size();
+        ph.seg_first = (int32_t)P.segments.size();
+        int seg_launch0 = (int32_t)P.launches.size(), seg_coll0 = (int32_t)P.colls.size();
+        auto end_segment = [&]() {
+            Segment sg{};
+            sg.level = lev;
+            sg.coll_first = seg_coll0; sg.coll_count = (int32_t)P.colls.size() - seg_coll0;
+            sg.launch_first = seg_launch0; sg.launch_count = (int32_t)P.launches.size() - seg_launch0;
+            P.segments.push_back(sg);         // also when empty: segment k means the same step on every rank
+            seg_launch0 = (int32_t)P.launches.size();
+            seg_coll0 = (int32_t)P.colls.size();
+        };
+
+        std::vector<i64> cls[4];
+        std::map<int, SlotOps> slots;
+        std::vector<GemmOp> scatter;                // Schur updates computed entirely by the front's owner
+        std::vector<GemmOp> scatter_dist;           // this rank's share of the Schur updates of shared fronts
+        std::vector<Coll> panel_bcasts;             // factored shared panels, owner -> group (before the shared updates)
+        std::vector<i64> dist_panels;               // shared fronts factorized by their whole group
+        for (i64 s : by_level[lev]) {
+            const SnodeDev &d = P.snode[s];
+            const int m = d.nsrow - d.nscol;
+            const int glo = P.group_lo[s], ghi = P.group_hi[s];
+            const bool shared = ghi - glo > 1;
+            const bool in_group = rank >= glo && rank < ghi;
+            const i64 panel_elems = (i64)d.ld * d.nscol;
+            // (1) a wide shared Cholesky front is factorized by its whole group: every rank gets the summed panel
+            //     (all-reduce), block columns are owned round-robin, each one is broadcast once it is factorized
+            const bool dist_panel = shared && !lu && d.nscol >= prm.dist_panel_min_cols;
+            // (2) Schur update of a shared front: every rank of the group computes 1/G of the update tiles into its own
+            //     image of the ancestors (summed later anyway); needs the factored panel everywhere
+            const bool dist_update = shared && m >= prm.dist_scatter_min_m;
+            if (shared) P.colls.push_back(Coll{d.xoff, panel_elems, dist_panel ? C_ALLREDUCE : C_REDUCE, P.owner[s], glo, ghi});
+            auto scatter_ops = [&](std::vector<GemmOp> &out, int mod, int rem) {
+                if (m <= 0) return;
+                GemmOp g{};
+                g.lda = g.ldb = d.ld; g.ldc = 0; g.M = g.N = m; g.K = d.nscol;
+                g.meta = d.lsip + d.nscol;
+                g.tile_mod = mod; g.tile_rem = rem;
+                if (!lu) {
+                    g.a_off = g.b_off = d.xoff + d.nscol;
+                    g.flags = G_LOWER | G_SCATTER;
+                    out.push_back(g);
+                } else {
+                    g.a_off = d.xoff + d.nscol; g.b_off = d.xoff + d.nsrow;      // L21 * (U12^T)^T, rows >= seg begin
+                    g.flags = G_SCATTER | G_LIM_SEGB;
+                    out.push_back(g);
+                    g.a_off = d.xoff + d.nsrow; g.b_off = d.xoff + d.nscol;      // U12^T * L21^T, rows >= seg end
+                    g.flags = G_SCATTER | G_LIM_SEGE;
+                    out.push_back(g);
+                }
+            };
+            if (dist_update) {
+                if (!dist_panel) panel_bcasts.push_back(Coll{d.xoff, panel_elems, C_BCAST, P.owner[s], glo, ghi});
+                if (in_group) scatter_ops(scatter_dist, ghi - glo, rank - glo);
+            }
+            if (dist_panel) {
+                dist_panels.push_back(s);
+                if (!dist_update && mine(s)) scatter_ops(scatter, 1, 0);
+                if (mine(s)) ++P.nlarge;
+                continue;
+            }
+            if (!mine(s)) continue;
+            const i64 pb = panel_bytes(d);
+            int c = -1;
+            if (d.nsrow - d.nscol <= prm.small_max_m)
+                for (int k = 0; k < 4; ++k) if (pb <= small_limits[k]) { c = k; break; }
+            if (c >= 0 && !dist_update) { cls[c].push_back(s); ++P.nsmall; continue; }
+            ++P.nlarge;
+            { PanelEmitter pe(d, lu, widths, slots); pe.lookahead = prm.lookahead != 0; pe.run(); }
+            if (!dist_update) scatter_ops(scatter, 1, 0);
         }
+        for (int c = 0; c < 4; ++c) {
+            if (cls[c].empty()) continue;
+            Launch L{};
+            L.kind = c < 2 ? L_SMALL_A : L_SMALL_B;
+            L.level = lev;
+            L.top_block = -1;
+            L.first = (int32_t)P.small_tasks.size();
+            L.count = L.grid = (int32_t)cls[c].size();
+            i64 smem = 0;
+            for (i64 s : cls[c]) { P.small_tasks.push_back((int32_t)s); smem = std::max(smem, panel_bytes(P.snode[s])); }
+            L.smem = (int32_t)smem;
+            P.launches.push_back(L);
+        }
+        emit_slots(slots, top_stride);
+        // the owner-computed Schur updates of fronts factorized by a group must wait for the group's work: they go last
+        std::vector<GemmOp> scatter_late;
+        if (!dist_panels.empty()) scatter_late.swap(scatter);
         if (!scatter.empty()) emit_gemm(scatter, -1, LF_WAIT_SIDE);
-        ph.reduce_count = (int32_t)P.reduces.size() - ph.reduce_first;
-        ph.launch_count = (int32_t)P.launches.size() - ph.launch_first;
-        ph.bcast_count = (int32_t)P.bcasts.size() - ph.bcast_first;
-        ph.launch_b_first = (int32_t)P.launches.size();
+
+        // ---- group-factorized panels: block column b is owned by rank lo + b % G -----------------------------------------
+        if (!dist_panels.empty()) {
+            int nsteps = 0;
+            for (i64 s : dist_panels) nsteps = std::max(nsteps, (P.snode[s].nscol + Wd - 1) / Wd);
+            auto block_owner = [&](i64 s, int b) { return P.group_lo[s] + b % (P.group_hi[s] - P.group_lo[s]); };
+            auto factor_block = [&](int b) {         // F(b): diag / trsm / inner updates of block column b, on its owner
+                std::map<int, SlotOps> fs;
+                for (i64 s : dist_panels) {
+                    const SnodeDev &d = P.snode[s];
+                    const int b0 = b * Wd;
+                    if (b0 >= d.nscol || block_owner(s, b) != rank) continue;
+                    PanelEmitter pe(d, false, dist_widths, fs);
+                    pe.block(b0, std::min(b0 + Wd, (int)d.nscol), 1, 0);
+                }
+                emit_slots(fs, 0);
+            };
+            // Look-ahead across ranks: the owner of block column b+1 applies step b to that block column only, factorizes
+            // it and lets the rest of its step-b updates wait until the broadcast of b+1 has been issued -- the other
+            // ranks meanwhile apply step b to everything they own, so nobody waits for the owner's bulk update.
+            std::vector<GemmOp> deferred;
+            factor_block(0);
+            for (int b = 0; b < nsteps; ++b) {
+                end_segment();
+                // the factorized block column travels to the group (whole columns: a contiguous run of the image) ...
+                for (i64 s : dist_panels) {
+                    const SnodeDev &d = P.snode[s];
+                    const int b0 = b * Wd, b1 = std::min(b0 + Wd, (int)d.nscol);
+                    if (b0 < d.nscol) P.colls.push_back(Coll{d.xoff + (i64)b0 * d.ld, (i64)(b1 - b0) * d.ld, C_BCAST, block_owner(s, b), P.group_lo[s], P.group_hi[s]});
+                }
+                if (!deferred.empty()) { emit_gemm(deferred, -1, 0); deferred.clear(); }
+                // ... every rank applies it to the later block columns it owns, then the owner of the next one factorizes it
+                std::vector<GemmOp> next, rest;
+                for (i64 s : dist_panels) {
+                    const SnodeDev &d = P.snode[s];
+                    if (rank < P.group_lo[s] || rank >= P.group_hi[s]) continue;
+                    const int b0 = b * Wd, b1 = std::min(b0 + Wd, (int)d.nscol), nblk = (d.nscol + Wd - 1) / Wd;
+                    if (b0 >= d.nscol) continue;
+                    for (int c = b + 1; c < nblk; ++c) {
+                        if (block_owner(s, c) != rank) continue;
+                        const int c0 = c * Wd, c1 = std::min(c0 + Wd, (int)d.nscol);
+                        GemmOp g{};
+                        g.a_off = g.b_off = d.xoff + c0 + (i64)b0 * d.ld;
+                        g.c_off = d.xoff + c0 + (i64)c0 * d.ld;
+                        g.lda = g.ldb = g.ldc = d.ld;
+                        g.M = d.nsrow - c0; g.N = c1 - c0; g.K = b1 - b0;
+                        g.flags = G_LOWER; g.tile_mod = 1; g.tile_rem = 0;
+                        (c == b + 1 ? next : rest).push_back(g);
+                    }
+                }
+                if (!next.empty()) {
+                    emit_gemm(next, -1, 0);
+                    factor_block(b + 1);
+                    deferred.swap(rest);
+                } else if (!rest.empty()) {
+                    emit_gemm(rest, -1, 0);
+                }
+            }
+            if (!deferred.empty()) emit_gemm(deferred, -1, 0);
+            if (!scatter_late.empty()) emit_gemm(scatter_late, -1, LF_WAIT_SIDE);
+        }
+        end_segment();
+        // ---- shared Schur updates: factored panels to the group, then everybody's share of the tiles ------------------
+        P.colls.insert(P.colls.end(), panel_bcasts.begin(), panel_bcasts.end());
         if (!scatter_dist.empty()) emit_gemm(scatter_dist, -1, LF_WAIT_SIDE);
-        ph.launch_b_count = (int32_t)P.launches.size() - ph.launch_b_first;
+        end_segment();
+        ph.launch_count = (int32_t)P.launches.size() - ph.launch_first;
+        ph.seg_count = (int32_t)P.segments.size() - ph.seg_first;
         P.phases.push_back(ph);
     }
 

@@ -22,6 +22,8 @@ struct PlanParams {
     int lookahead = 1;           // split the top-level trailing updates (see LaunchFlags) -- needs outer2 > 0
     int use_ws = 1;              // big GEMM ops with a row-major B go to the warp-specialized bulk-copy kernel
     int dist_scatter_min_m = 512;// multi-GPU: Schur updates of shared fronts with at least this many rows are split over the group
+    int dist_panel_min_cols = 2048; // multi-GPU: shared Cholesky fronts at least this wide are factorized by the whole group
+                                 // (1-D block-cyclic over `outer`-wide block columns, one broadcast per block column)
 };
 
 struct HostPlan {
@@ -64,9 +66,9 @@ struct HostPlan {
     std::vector<int32_t> owner;             // owning rank of every supernode
     std::vector<int32_t> group_lo, group_hi;// ranks [lo,hi) that hold descendants of the supernode (hi-lo > 1: "shared")
     double local_flops = 0.0;               // flops of the supernodes this rank owns
-    std::vector<ReduceStep> reduces;        // sums of partial panel images into the owner, grouped by phase
-    std::vector<ReduceStep> bcasts;         // factored shared panels sent from the owner to its group, grouped by phase
-    std::vector<Phase> phases;              // one per etree level: reduce steps first, then the level's launches
+    std::vector<Coll> colls;                // collectives, grouped by segment (identical list on every rank)
+    std::vector<Segment> segments;          // collectives, then launches
+    std::vector<Phase> phases;              // one per etree level
 };
 
 // world == 1: every supernode is owned by rank 0, no reduce steps.

@@ -101,23 +101,33 @@ enum LaunchFlags : int32_t {
     LF_WAIT_SIDE = 1 << 1,   // main-stream launch that must wait for the side stream's work issued so far
 };
 
-// ---- multi-GPU: one etree level = one phase; before its launches, the partial images of the level's shared panels
-// (panels whose descendants live on several ranks) are summed into the owner ------------------------------------------
-struct ReduceStep {
-    int64_t offset;  // element offset of the panel in the padded factor
-    int64_t count;   // elements
-    int32_t root;    // owner rank (= lo)
-    int32_t lo, hi;  // contributing ranks [lo, hi)
+// ---- multi-GPU: the schedule of one rank is a list of SEGMENTS: first the segment's collectives (issued by the host
+// layer through torch.distributed / NCCL on the plan's stream), then its launches.  Collective lists are identical on
+// every rank (collectives are matched by order); a rank outside [lo,hi) skips the entry. --------------------------------
+enum CollType : int32_t {
+    C_REDUCE    = 0,   // sum the ranks' partial images of a shared panel into its owner (root)
+    C_ALLREDUCE = 1,   // ... into every rank of the group (panels factorized by the whole group)
+    C_BCAST     = 2,   // root's image of the region overwrites the group's (factored panel / block column)
 };
 
-// Phase = one etree level:  reduce steps -> launches A (local fronts + the shared fronts this rank owns) ->
-// broadcasts of the shared fronts factorized in A -> launches B (this rank's share of their Schur-update tiles).
+struct Coll {
+    int64_t offset;    // element offset in the padded factor image
+    int64_t count;     // elements (always a contiguous run of whole columns)
+    int32_t type, root, lo, hi;
+};
+
+struct Segment {
+    int32_t level;
+    int32_t coll_first, coll_count;
+    int32_t launch_first, launch_count;
+    int32_t pad;
+};
+
+// all launches of one etree level (single-GPU consumers: streamed copy-out, look-ahead joins)
 struct Phase {
     int32_t level;
-    int32_t reduce_first, reduce_count;
-    int32_t launch_first, launch_count;      // A
-    int32_t bcast_first, bcast_count;        // entries of HostPlan::bcasts (same ReduceStep record: root sends)
-    int32_t launch_b_first, launch_b_count;  // B
+    int32_t launch_first, launch_count;
+    int32_t seg_first, seg_count;
     int32_t pad;
 };
 

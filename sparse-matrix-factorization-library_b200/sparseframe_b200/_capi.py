@@ -15,9 +15,9 @@ SYMBOLS = [
     "sfb200_plan_create", "sfb200_plan_free", "sfb200_plan_int", "sfb200_factorize", "sfb200_factorize_device",
     "sfb200_plan_sync", "sfb200_download_factor", "sfb200_last_ms", "sfb200_last_launches", "sfb200_host_alloc",
     "sfb200_host_free", "sfb200_probe_fp64_peak", "sfb200_plan_set_stream", "sfb200_plan_profile",
-    "sfb200_plan_profile_get", "sfb200_plan_create_part", "sfb200_plan_double", "sfb200_plan_phase_info",
-    "sfb200_plan_reduce_info", "sfb200_plan_owner", "sfb200_plan_factor_ptr", "sfb200_phase_begin", "sfb200_phase_run",
-    "sfb200_plan_panel_offsets", "sfb200_plan_profile_launch", "sfb200_plan_bcast_info", "sfb200_solve", "sfb200_solve_device", "sfb200_residual",
+    "sfb200_plan_profile_get", "sfb200_plan_create_part", "sfb200_plan_double", "sfb200_plan_segment_info",
+    "sfb200_plan_coll_info", "sfb200_plan_owner", "sfb200_plan_factor_ptr", "sfb200_partition_begin", "sfb200_segment_run",
+    "sfb200_plan_panel_offsets", "sfb200_plan_profile_launch", "sfb200_solve", "sfb200_solve_device", "sfb200_residual",
 ]
 
 
@@ -71,16 +71,15 @@ def lib():
     L.sfb200_plan_create_part.argtypes = [vp, ci, ci, ci, C.POINTER(vp)]
     L.sfb200_plan_double.restype = dbl
     L.sfb200_plan_double.argtypes = [vp, C.c_char_p]
-    L.sfb200_plan_phase_info.argtypes = [vp, ci, vp]
-    L.sfb200_plan_reduce_info.argtypes = [vp, ci, vp]
+    L.sfb200_plan_segment_info.argtypes = [vp, ci, vp]
+    L.sfb200_plan_coll_info.argtypes = [vp, ci, vp]
     L.sfb200_plan_owner.argtypes = [vp, vp]
     L.sfb200_plan_factor_ptr.restype = vp
     L.sfb200_plan_factor_ptr.argtypes = [vp]
     L.sfb200_plan_panel_offsets.argtypes = [vp, vp]
     L.sfb200_plan_profile_launch.argtypes = [vp, ci, vp]
-    L.sfb200_phase_begin.argtypes = [vp, vp, vp]
-    L.sfb200_phase_run.argtypes = [vp, ci, ci]
-    L.sfb200_plan_bcast_info.argtypes = [vp, ci, vp]
+    L.sfb200_partition_begin.argtypes = [vp, vp, vp]
+    L.sfb200_segment_run.argtypes = [vp, ci]
     L.sfb200_solve.argtypes = [vp, vp, ci]
     L.sfb200_solve_device.argtypes = [vp, vp, ci]
     L.sfb200_residual.argtypes = [vp, vp, vp, vp]

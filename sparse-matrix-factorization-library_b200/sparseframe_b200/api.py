@@ -138,22 +138,17 @@ class Plan:
     def double(self, name) -> float:
         return float(_capi.lib().sfb200_plan_double(self._h, name.encode()))
 
-    def phase_info(self, k):
-        out = np.zeros(9, dtype=np.int64)
-        _capi.lib().sfb200_plan_phase_info(self._h, int(k), out.ctypes.data)
-        return dict(reduce_first=int(out[0]), reduce_count=int(out[1]), launch_first=int(out[2]),
-                    launch_count=int(out[3]), level=int(out[4]), bcast_first=int(out[5]), bcast_count=int(out[6]),
-                    launch_b_first=int(out[7]), launch_b_count=int(out[8]))
-
-    def bcast_info(self, i):
+    def segment_info(self, k):
         out = np.zeros(5, dtype=np.int64)
-        _capi.lib().sfb200_plan_bcast_info(self._h, int(i), out.ctypes.data)
-        return dict(offset=int(out[0]), count=int(out[1]), root=int(out[2]), lo=int(out[3]), hi=int(out[4]))
+        _capi.lib().sfb200_plan_segment_info(self._h, int(k), out.ctypes.data)
+        return dict(coll_first=int(out[0]), coll_count=int(out[1]), launch_first=int(out[2]), launch_count=int(out[3]),
+                    level=int(out[4]))
 
-    def reduce_info(self, i):
-        out = np.zeros(5, dtype=np.int64)
-        _capi.lib().sfb200_plan_reduce_info(self._h, int(i), out.ctypes.data)
-        return dict(offset=int(out[0]), count=int(out[1]), root=int(out[2]), lo=int(out[3]), hi=int(out[4]))
+    def coll_info(self, i):
+        out = np.zeros(6, dtype=np.int64)
+        _capi.lib().sfb200_plan_coll_info(self._h, int(i), out.ctypes.data)
+        return dict(type=int(out[0]), offset=int(out[1]), count=int(out[2]), root=int(out[3]), lo=int(out[4]),
+                    hi=int(out[5]))
 
     def owner(self) -> np.ndarray:
         out = np.zeros(self.int("nsuper"), dtype=np.int32)
@@ -168,15 +163,15 @@ class Plan:
     def factor_ptr(self) -> int:
         return int(_capi.lib().sfb200_plan_factor_ptr(self._h))
 
-    def phase_begin(self, d_lx_ptr: int, d_ux_ptr: int = 0):
-        rc = _capi.lib().sfb200_phase_begin(self._h, d_lx_ptr, d_ux_ptr or None)
+    def partition_begin(self, d_lx_ptr: int, d_ux_ptr: int = 0):
+        rc = _capi.lib().sfb200_partition_begin(self._h, d_lx_ptr, d_ux_ptr or None)
         if rc != 0:
-            raise RuntimeError("sfb200_phase_begin failed (%d): %s" % (rc, _capi.last_error()))
+            raise RuntimeError("sfb200_partition_begin failed (%d): %s" % (rc, _capi.last_error()))
 
-    def phase_run(self, k, part=0):
-        rc = _capi.lib().sfb200_phase_run(self._h, int(k), int(part))
+    def segment_run(self, k):
+        rc = _capi.lib().sfb200_segment_run(self._h, int(k))
         if rc != 0:
-            raise RuntimeError("sfb200_phase_run failed (%d): %s" % (rc, _capi.last_error()))
+            raise RuntimeError("sfb200_segment_run failed (%d): %s" % (rc, _capi.last_error()))
 
     def int(self, name) -> int:
         return int(_capi.lib().sfb200_plan_int(self._h, name.encode()))

@@ -1,14 +1,18 @@
 """Etree-subtree-partitioned factorization over several GPUs of one box: one process per GPU,
 torch.distributed for the plumbing.
 
-Each rank factorizes the subtrees it owns.  Updates aimed at a "top" supernode owned by another rank are accumulated in
-the rank's own zero-initialised image of that panel; before the owner factorizes the level of that supernode, the
-images are summed into the owner with a reduce (NCCL over NVLink on GPUs, gloo in the CPU tests).  That sum is the one
-real exchange step of the path -- the reference's equivalent is its host-RAM round trip of factored panels
-(CH.c:2596-2685); nothing else is communicated.
+Each rank factorizes the subtrees it owns.  The supernodes above them ("top") are shared by a group of ranks: every rank
+accumulates its updates to them in its own zero-initialised image of the factor, and the plan lists the exchange steps
+(csrc/plan_types.h `Coll`) that turn the images into the factor:
+  reduce      the images of a shared panel are summed into its owner right before its level is factorized;
+  all-reduce  ... into the whole group, for wide Cholesky panels that the group factorizes together (block columns
+              owned round-robin, one broadcast per factorized block column);
+  broadcast   a factored panel / block column goes to the group, which then splits the tiles of its Schur update.
+NCCL over NVLink on GPUs, gloo in the CPU tests.  The reference's equivalent of these steps is its host-RAM round trip
+of factored panels (CH.c:2596-2685); nothing else is communicated.
 
-The phase loop is backend-agnostic so that the same orchestration code runs on the GPU engine (`DeviceBackend`) and, in
-the CPU test tier, on the plan interpreter of the oracle (tests/test_multirank_gloo.py).
+The segment loop is backend-agnostic so that the same orchestration code runs on the GPU engine (`DeviceBackend`) and,
+in the CPU test tier, on the plan interpreter of the oracle (tests/test_multirank_gloo.py).
 """
 from __future__ import annotations
 
@@ -23,6 +27,9 @@ class _CudaView:
                                          "version": 2}
 
 
+REDUCE, ALLREDUCE, BCAST = 0, 1, 2
+
+
 class DeviceBackend:
     """One rank's sfb200_plan (created with rank/world) behind the backend protocol."""
 
@@ -30,66 +37,64 @@ class DeviceBackend:
         import torch
         self.plan = plan
         self.rank, self.world = plan.rank, plan.world
-        self.nphases = plan.int("nphases")
         self.d_lx, self.d_ux = d_lx, d_ux
         self.image = torch.as_tensor(_CudaView(plan.factor_ptr(), plan.int("xsize_padded")), device=d_lx.device)
-        self.phases = [plan.phase_info(k) for k in range(self.nphases)]
-        self.reduces = [plan.reduce_info(i) for i in range(plan.int("nreduces"))]
-        self.bcasts = [plan.bcast_info(i) for i in range(plan.int("nbcasts"))]
+        self.segments = [plan.segment_info(k) for k in range(plan.int("nsegments"))]
+        self.colls = [plan.coll_info(i) for i in range(plan.int("ncolls"))]
 
     def begin(self):
-        self.plan.phase_begin(self.d_lx.data_ptr(), self.d_ux.data_ptr() if self.d_ux is not None else 0)
+        self.plan.partition_begin(self.d_lx.data_ptr(), self.d_ux.data_ptr() if self.d_ux is not None else 0)
 
-    def run_phase(self, k, part=0):
-        self.plan.phase_run(k, part)
+    def run_segment(self, k):
+        self.plan.segment_run(k)
 
     def finish(self):
         self.plan.sync()
 
 
 class PartitionedFactorization:
-    """Phase loop, one phase per etree level: reduce the partial images of the level's shared panels into their owners,
-    run the level's launches (A), broadcast the shared panels that were just factorized to their groups, run every rank's
-    share of their Schur-update tiles (B)."""
+    """Segment loop: the segment's collectives on regions of the factor image, then its launches."""
 
     def __init__(self, backend, dist=None):
         self.b = backend
         self.dist = dist
         self.groups = {}
         if dist is not None and backend.world > 1:
-            # groups must be created by every rank, in the same order: the reduce list is identical on all ranks
-            for r in list(backend.reduces) + list(backend.bcasts):
-                key = (r["lo"], r["hi"])
+            # groups must be created by every rank, in the same order: the collective list is identical on all ranks
+            for c in backend.colls:
+                key = (c["lo"], c["hi"])
                 if key not in self.groups:
                     full = key == (0, backend.world)
                     self.groups[key] = None if full else dist.new_group(ranks=list(range(key[0], key[1])))
-        self.reduced_bytes = 0
-        self.bcast_bytes = 0
+        self.bytes = {REDUCE: 0, ALLREDUCE: 0, BCAST: 0}
+
+    @property
+    def reduced_bytes(self):
+        return self.bytes[REDUCE] + self.bytes[ALLREDUCE]
+
+    @property
+    def bcast_bytes(self):
+        return self.bytes[BCAST]
 
     def factorize(self):
-        b = self.b
+        b, dist = self.b, self.dist
         b.begin()
-        self.reduced_bytes = 0
-        self.bcast_bytes = 0
-        for k in range(b.nphases):
-            ph = b.phases[k]
-            for i in range(ph["reduce_first"], ph["reduce_first"] + ph["reduce_count"]):
-                r = b.reduces[i]
-                if b.world > 1 and r["lo"] <= b.rank < r["hi"]:
-                    view = b.image[r["offset"]:r["offset"] + r["count"]]
-                    self.dist.reduce(view, dst=r["root"], op=self.dist.ReduceOp.SUM, group=self.groups[(r["lo"], r["hi"])])
-                    self.reduced_bytes += 8 * r["count"]
-            b.run_phase(k, 0)
-            # factored shared panels go from their owner to the group, then everybody computes its share of their
-            # Schur-update tiles (part B of the phase)
-            for i in range(ph["bcast_first"], ph["bcast_first"] + ph["bcast_count"]):
-                r = b.bcasts[i]
-                if b.world > 1 and r["lo"] <= b.rank < r["hi"]:
-                    view = b.image[r["offset"]:r["offset"] + r["count"]]
-                    self.dist.broadcast(view, src=r["root"], group=self.groups[(r["lo"], r["hi"])])
-                    self.bcast_bytes += 8 * r["count"]
-            if ph["launch_b_count"] > 0:
-                b.run_phase(k, 1)
+        self.bytes = {REDUCE: 0, ALLREDUCE: 0, BCAST: 0}
+        for k, sg in enumerate(b.segments):
+            for i in range(sg["coll_first"], sg["coll_first"] + sg["coll_count"]):
+                c = b.colls[i]
+                if b.world == 1 or not (c["lo"] <= b.rank < c["hi"]):
+                    continue
+                view = b.image[c["offset"]:c["offset"] + c["count"]]
+                group = self.groups[(c["lo"], c["hi"])]
+                if c["type"] == REDUCE:
+                    dist.reduce(view, dst=c["root"], op=dist.ReduceOp.SUM, group=group)
+                elif c["type"] == ALLREDUCE:
+                    dist.all_reduce(view, op=dist.ReduceOp.SUM, group=group)
+                else:
+                    dist.broadcast(view, src=c["root"], group=group)
+                self.bytes[c["type"]] += 8 * c["count"]
+            b.run_segment(k)
         b.finish()
 
 

@@ -208,52 +208,63 @@ def test_full_size_backward_error(cfg):
     plan.close()
 
 
-@pytest.mark.parametrize("gen,g,kind,world", [("lap3d", 20, "cholesky", 2), ("lap3d", 20, "cholesky", 4), ("cd3d", 16, "lu", 3)])
-def test_partitioned_plans_emulated_on_one_gpu(gen, g, kind, world):
-    """The etree-partitioned device path without NCCL: all `world` rank plans live on this one GPU, phases run in lock
-    step and the reduce steps are done with torch adds -- the same order of operations torch.distributed gives."""
+@pytest.mark.parametrize("gen,g,kind,world,group_panels", [
+    ("lap3d", 20, "cholesky", 2, 0), ("lap3d", 20, "cholesky", 4, 0), ("cd3d", 16, "lu", 3, 0),
+    ("lap3d", 24, "cholesky", 2, 1), ("lap3d", 24, "cholesky", 4, 1), ("lap3d", 24, "cholesky", 3, 1)])
+def test_partitioned_plans_emulated_on_one_gpu(gen, g, kind, world, group_panels):
+    """The etree-partitioned device path without NCCL: all `world` rank plans live on this one GPU, segments run in
+    lock step and the collectives are done with torch adds / copies -- the same order of operations torch.distributed
+    gives.  group_panels: shared fronts of >= 256 columns are factorized by their whole group (128-wide block columns
+    owned round-robin, one broadcast per block column)."""
     import torch
-    from sparseframe_b200.parallel import DeviceBackend, owned_mask
-    os.environ["SFB200_DIST_MIN_M"] = "48"       # small fronts too: exercise the broadcast + tile-share path
+    from sparseframe_b200.parallel import DeviceBackend, owned_mask, REDUCE, ALLREDUCE, BCAST
+    env = dict(SFB200_DIST_MIN_M="48")           # small fronts too: exercise the broadcast + tile-share path
+    env["SFB200_DIST_PANEL_MIN"] = "256" if group_panels else "1000000"
+    if group_panels:
+        env.update(SFB200_OUTER="128", SFB200_OUTER2="256")
+    os.environ.update(env)
     A, _ = build_matrix(gen, g)
     S = sf.analyze(A, kind)
     split = kind == "lu" and S.int("symmetric") == 0
     d_lx = torch.from_numpy(S.array("Lx")).cuda()
     d_ux = torch.from_numpy(S.array("Ux")).cuda() if split else None
     plans = [sf.Plan(S, rank=r, world=world) for r in range(world)]
-    os.environ.pop("SFB200_DIST_MIN_M", None)
+    for k in env:
+        os.environ.pop(k, None)
     stream = torch.cuda.current_stream()
     for p in plans:
         p.set_stream(stream.cuda_stream)
     backs = [DeviceBackend(p, d_lx, d_ux) for p in plans]
     assert sum(p.double("local_flops") for p in plans) == pytest.approx(S.flops, rel=1e-12)
+    assert all(b.colls == backs[0].colls and len(b.segments) == len(backs[0].segments) for b in backs)
     for b in backs:
         b.begin()
-    nred = nbc = 0
-    for k in range(backs[0].nphases):
-        ph = backs[0].phases[k]
-        for i in range(ph["reduce_first"], ph["reduce_first"] + ph["reduce_count"]):
-            r = backs[0].reduces[i]
-            sl = slice(r["offset"], r["offset"] + r["count"])
-            for q in range(r["lo"], r["hi"]):
-                if q != r["root"]:
-                    backs[r["root"]].image[sl] += backs[q].image[sl]
-            nred += 1
+    ncoll = [0, 0, 0]
+    for k, sg in enumerate(backs[0].segments):
+        for i in range(sg["coll_first"], sg["coll_first"] + sg["coll_count"]):
+            c = backs[0].colls[i]
+            sl = slice(c["offset"], c["offset"] + c["count"])
+            group = range(c["lo"], c["hi"])
+            if c["type"] == BCAST:
+                for q in group:
+                    if q != c["root"]:
+                        backs[q].image[sl] = backs[c["root"]].image[sl]
+            else:
+                for q in group:
+                    if q != c["root"]:
+                        backs[c["root"]].image[sl] += backs[q].image[sl]
+                if c["type"] == ALLREDUCE:
+                    for q in group:
+                        if q != c["root"]:
+                            backs[q].image[sl] = backs[c["root"]].image[sl]
+            ncoll[c["type"]] += 1
         for b in backs:
-            b.run_phase(k, 0)
-        for i in range(ph["bcast_first"], ph["bcast_first"] + ph["bcast_count"]):
-            r = backs[0].bcasts[i]
-            sl = slice(r["offset"], r["offset"] + r["count"])
-            for q in range(r["lo"], r["hi"]):
-                if q != r["root"]:
-                    backs[q].image[sl] = backs[r["root"]].image[sl]
-            nbc += 1
-        for b in backs:
-            b.run_phase(k, 1)
+            b.run_segment(k)
     for b in backs:
         b.finish()
-    assert nbc > 0, "the test should exercise the distributed Schur updates"
-    assert nred > 0
+    assert ncoll[BCAST] > 0, "the test should exercise the distributed Schur updates"
+    assert ncoll[REDUCE] + ncoll[ALLREDUCE] > 0
+    assert (ncoll[ALLREDUCE] > 0) == bool(group_panels)
     Lsxp = S.array("Lsxp")
     merged = np.zeros(S.int("xsize"))
     owner = plans[0].owner()

@@ -17,7 +17,7 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, gen, g, kind, devslot, out_path):
+def _worker(rank, world, port, gen, g, kind, devslot, group_panels, out_path):
     sys.path.insert(0, os.path.join(ROOT, "sparse-matrix-factorization-library_b200"))
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import torch
@@ -28,35 +28,40 @@ def _worker(rank, world, port, gen, g, kind, devslot, out_path):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     os.environ["SFCHECK_DIST_MIN_M"] = "8"       # tiny fronts too: exercise the broadcast + tile-share path
+    # group_panels: shared Cholesky fronts of >= 24 columns are factorized by their whole group in 16-wide block columns
+    os.environ["SFCHECK_DIST_PANEL_MIN"] = "24" if group_panels else "1000000"
     dist.init_process_group("gloo", rank=rank, world_size=world)
     A = sf.compress(*sf.matrices.generate(gen, g))
-    backend = sforacle.CheckBackend(kind, A, devslot, rank, world)
+    backend = sforacle.CheckBackend(kind, A, devslot, rank, world, nb=8 if group_panels else 0, outer=16 if group_panels else 0)
     pf = PartitionedFactorization(backend, dist)
     pf.factorize()
     assert backend.bad == 0
     owned = torch.from_numpy(backend.pack_owned())      # zeros outside the owned panels -> SUM = union
     dist.reduce(owned, dst=0, op=dist.ReduceOp.SUM)
-    stats = torch.tensor([backend.double("local_flops"), float(pf.reduced_bytes), float(pf.bcast_bytes)], dtype=torch.float64)
-    gathered = [torch.zeros(3, dtype=torch.float64) for _ in range(world)] if rank == 0 else None
+    stats = torch.tensor([backend.double("local_flops"), float(pf.reduced_bytes), float(pf.bcast_bytes),
+                          float(pf.bytes[1])], dtype=torch.float64)
+    gathered = [torch.zeros(4, dtype=torch.float64) for _ in range(world)] if rank == 0 else None
     dist.gather(stats, gathered, dst=0)
     if rank == 0:
         np.savez(out_path, lsx=owned.numpy(), stats=torch.stack(gathered).numpy(), total=backend.double("flops"),
-                 nreduces=backend.int("nreduces"), nbcasts=backend.int("nbcasts"))
+                 ncoll=np.bincount([c["type"] for c in backend.colls], minlength=3))
     dist.barrier()
     dist.destroy_process_group()
     backend.close()
 
 
-@pytest.mark.parametrize("world", [2, 3])
-@pytest.mark.parametrize("name", ["lap3d_10_chol_slot", "cd3d_8_lu", "lap2d_20_chol"])
-def test_partitioned_factorization_over_gloo(world, name, tmp_path):
+@pytest.mark.parametrize("world,name,group_panels", [
+    (2, "lap3d_10_chol_slot", 0), (3, "lap3d_10_chol_slot", 0), (2, "cd3d_8_lu", 0), (3, "cd3d_8_lu", 0),
+    (2, "lap2d_20_chol", 0), (3, "lap2d_20_chol", 0),
+    (2, "lap3d_10_chol_slot", 1), (3, "lap3d_10_chol_slot", 1), (3, "cd3d_8_lu", 1)])
+def test_partitioned_factorization_over_gloo(world, name, group_panels, tmp_path):
     import torch.multiprocessing as mp
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     from conftest import load_golden
     import sparseframe_b200 as sf
     gold = load_golden(os.path.join(ROOT, "tests", "golden", name + ".npz"))
     out = str(tmp_path / "out.npz")
-    mp.spawn(_worker, args=(world, _free_port(), gold["gen"], gold["grid"], gold["kind"], gold["devslot"], out),
+    mp.spawn(_worker, args=(world, _free_port(), gold["gen"], gold["grid"], gold["kind"], gold["devslot"], group_panels, out),
              nprocs=world, join=True)
     res = np.load(out)
     mask = sf.lower_trapezoid_mask(gold["kind"], gold["Super"], gold["Lsip"], gold["Lsxp"], gold["xsize"])
@@ -64,17 +69,26 @@ def test_partitioned_factorization_over_gloo(world, name, tmp_path):
     assert sf.entrywise_rel_diff(a, b) <= 1e-10
     assert np.array_equal(a == 0, b == 0)
     # every flop is owned by exactly one rank, and something really had to be exchanged
+    ncoll = res["ncoll"]
     assert res["stats"][:, 0].sum() == pytest.approx(float(res["total"]), rel=1e-12)
-    assert int(res["nreduces"]) > 0 and res["stats"][:, 1].sum() > 0
+    assert ncoll[0] + ncoll[1] > 0 and res["stats"][:, 1].sum() > 0
     # shared fronts with off-diagonal rows are broadcast and their Schur update is split over the group
-    assert (res["stats"][:, 2].sum() > 0) == (int(res["nbcasts"]) > 0)
+    assert (res["stats"][:, 2].sum() > 0) == (ncoll[2] > 0)
     if name == "lap3d_10_chol_slot":
-        assert int(res["nbcasts"]) > 0, "this case must exercise the distributed Schur updates"
+        assert ncoll[2] > 0, "this case must exercise the distributed Schur updates"
+        assert (ncoll[1] > 0) == bool(group_panels), "group-factorized panels are announced by all-reduces"
+        assert (res["stats"][:, 3].sum() > 0) == bool(group_panels)
+    if gold["kind"] == "lu":
+        assert ncoll[1] == 0, "LU panels stay with their owner"
 
 
-def test_partition_simulated_up_to_8_ranks():
-    """All ranks simulated inside one process (oracle/plan_host_exec.cpp): ownership, reduce lists and phases stay
-    consistent for world sizes up to 8, and the result equals the compiled reference / oracle."""
+@pytest.mark.parametrize("group_panels", [0, 1])
+def test_partition_simulated_up_to_8_ranks(group_panels, monkeypatch):
+    """All ranks simulated inside one process (oracle/plan_host_exec.cpp): ownership, collective lists and segments
+    stay consistent for world sizes up to 8, and the result equals the compiled reference / oracle.  group_panels: the
+    wide shared Cholesky fronts are factorized by their groups (16-wide block columns owned round-robin)."""
+    monkeypatch.setenv("SFCHECK_DIST_PANEL_MIN", "32" if group_panels else "1000000")
+    monkeypatch.setenv("SFCHECK_DIST_MIN_M", "24" if group_panels else "512")
     import ctypes as C
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import sforacle
@@ -98,11 +112,14 @@ def test_partition_simulated_up_to_8_ranks():
         for world in (2, 4, 5, 8):
             out = np.full(S.int("xsize"), np.nan)
             bal = np.zeros(world)
-            nred = C.c_long()
+            ncoll = (C.c_long * 3)()
             rc = lib.sfcheck_factorize_partitioned(int(kind == "lu"), int(A.symmetric), A.n, A.Cp.ctypes.data,
-                                                   A.Ci.ctypes.data, A.Cx.ctypes.data, sf.DEFAULT_DEVSLOT, 0, 0, -1, -1,
-                                                   world, out.ctypes.data, bal.ctypes.data, C.byref(nred))
+                                                   A.Ci.ctypes.data, A.Cx.ctypes.data, sf.DEFAULT_DEVSLOT,
+                                                   8 if group_panels else 0, 16 if group_panels else 0, -1, -1,
+                                                   world, out.ctypes.data, bal.ctypes.data, ncoll)
             assert rc == 0
+            assert ncoll[0] + ncoll[1] > 0
+            assert (ncoll[1] > 0) == (bool(group_panels) and kind == "cholesky")
             assert sf.entrywise_rel_diff(ref[mask], out[mask]) <= 1e-10
             assert bal.sum() == pytest.approx(S.flops, rel=1e-12)
             assert bal.max() / bal.sum() < 0.75          # no rank is left with (almost) everything
