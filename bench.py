@@ -25,6 +25,19 @@ import time
 
 import numpy as np
 
+# The contract is ONE JSON line on stdout.  Native code below us also writes there (the compiled reference prints its
+# supernode counts, NCCL its version banner): fd 1 is pointed at stderr for the life of the process and the JSON line
+# goes to the saved descriptor.
+_REAL_STDOUT = os.fdopen(os.dup(1), "w")
+sys.stdout.flush()
+os.dup2(2, 1)
+
+
+def emit(obj):
+    _REAL_STDOUT.write(json.dumps(obj) + "\n")
+    _REAL_STDOUT.flush()
+
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.join(ROOT, "sparse-matrix-factorization-library_b200"))
 
@@ -110,14 +123,14 @@ def reference_arm(args, cfg, gen, g, kind):
     value = flops * len(times) / total / 1e9
     sample = "%s %d^%d (n=%d, %.3e flop/step), reference CPU worker path, OpenBLAS threads=%d" % (
         sgen, sg, 2 if sgen == "lap2d" else 3, n, flops, min(cores, 16))
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": workload_name(cfg, gen, g, kind), "sample": sample, "devSlotSize": sfref.DEFAULT_DEVSLOT},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "reference", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }))
+    })
 
 
 def cpu_baseline(kind, gen):
@@ -355,7 +368,7 @@ def main():
                            "per rank: H2D values, partitioned factorization, D2H of the owned panels (pinned)"},
             "roofline": roof, "cpu_baseline": base,
         }
-        print(json.dumps(out))
+        emit(out)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
