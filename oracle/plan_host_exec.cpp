@@ -155,40 +155,62 @@ void assemble(const CheckHandle &h, double *X) {
     }
 }
 
-long run_launches(const HostPlan &P, double *X, int first, int count) {
+long run_one(const HostPlan &P, double *X, const Launch &L) {
     long bad = 0;
-    for (int li = first; li < first + count; ++li) {
-        const Launch &L = P.launches[li];
-        switch (L.kind) {
-            case L_SMALL_A: case L_SMALL_B:
-                for (int k = 0; k < L.count; ++k) bad += small_front(X, P, P.small_tasks[L.first + k]);
-                break;
-            case L_POTRF:
-                for (int k = 0; k < L.count; ++k) { const DiagOp &d = P.diag_ops[L.first + k]; bad += diag_cholesky(X + d.a_off, d.ld, d.nb); }
-                break;
-            case L_GETRF:
-                for (int k = 0; k < L.count; ++k) { const DiagOp &d = P.diag_ops[L.first + k]; bad += diag_lu(X + d.a_off, d.ld, d.nb); }
-                break;
-            case L_TRSM:
-                for (int k = 0; k < L.count; ++k) trsm(X, P.trsm_ops[L.first + k]);
-                break;
-            case L_GEMM128: case L_GEMM64: case L_GEMM128WS: {
-                // the tile prefix must be consistent with the geometry the kernels decode
-                i64 tiles = 0;
-                const int B = L.kind == L_GEMM64 ? 64 : 128;
-                for (int k = 0; k < L.count; ++k) {
-                    const GemmOp &g = P.gemm_ops[L.first + k];
-                    if (g.tile0 != tiles) return -101;
-                    tiles += share_of_tiles(gemm_tiles(g.M, g.N, B, (g.flags & G_LOWER) != 0), g.tile_mod, g.tile_rem);
-                    gemm(X, g, P, B);
-                }
-                if (tiles != L.grid) return -102;
-                break;
+    switch (L.kind) {
+        case L_SMALL_A: case L_SMALL_B:
+            for (int k = 0; k < L.count; ++k) bad += small_front(X, P, P.small_tasks[L.first + k]);
+            break;
+        case L_POTRF:
+            for (int k = 0; k < L.count; ++k) { const DiagOp &d = P.diag_ops[L.first + k]; bad += diag_cholesky(X + d.a_off, d.ld, d.nb); }
+            break;
+        case L_GETRF:
+            for (int k = 0; k < L.count; ++k) { const DiagOp &d = P.diag_ops[L.first + k]; bad += diag_lu(X + d.a_off, d.ld, d.nb); }
+            break;
+        case L_TRSM:
+            for (int k = 0; k < L.count; ++k) trsm(X, P.trsm_ops[L.first + k]);
+            break;
+        case L_GEMM128: case L_GEMM64: case L_GEMM128WS: {
+            // the tile prefix must be consistent with the geometry the kernels decode
+            i64 tiles = 0;
+            const int B = L.kind == L_GEMM64 ? 64 : 128;
+            for (int k = 0; k < L.count; ++k) {
+                const GemmOp &g = P.gemm_ops[L.first + k];
+                if (g.tile0 != tiles) return -101;
+                tiles += share_of_tiles(gemm_tiles(g.M, g.N, B, (g.flags & G_LOWER) != 0), g.tile_mod, g.tile_rem);
+                gemm(X, g, P, B);
             }
-            default: return -103;
+            if (tiles != L.grid) return -102;
+            break;
         }
+        default: return -103;
     }
     return bad;
+}
+
+/* The engine puts LF_SIDE launches on a second stream: they may run any time between their issue point and the next
+ * LF_WAIT_SIDE launch (or the end of the range, where the engine joins the side stream).  The default order here is
+ * "immediately"; SFCHECK_SIDE_LATE=1 runs them as LATE as that contract allows, so that a side launch that overlaps
+ * something the main stream does in between shows up as a wrong factor in the CPU test tier. */
+long run_launches(const HostPlan &P, double *X, int first, int count) {
+    const bool late = getenv("SFCHECK_SIDE_LATE") != nullptr;
+    std::vector<int> deferred;
+    long bad = 0;
+    auto flush = [&]() -> long {
+        for (int li : deferred) { const long b = run_one(P, X, P.launches[li]); if (b < 0) return b; bad += b; }
+        deferred.clear();
+        return 0;
+    };
+    for (int li = first; li < first + count; ++li) {
+        const Launch &L = P.launches[li];
+        if (late && (L.flags & LF_SIDE)) { deferred.push_back(li); continue; }
+        if (L.flags & LF_WAIT_SIDE) { const long b = flush(); if (b < 0) return b; }
+        const long b = run_one(P, X, L);
+        if (b < 0) return b;
+        bad += b;
+    }
+    const long b = flush();
+    return b < 0 ? b : bad;
 }
 
 void pack(const HostPlan &P, const double *X, double *Lsx_out) {

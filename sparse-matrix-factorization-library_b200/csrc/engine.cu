@@ -312,19 +312,29 @@ int sfb200_plan_create_part(const sfb200_symbolic *s, int device, int rank, int 
         }
         if ((err = upload(p, p->d_spack, flat))) return fail(err);
         {
-            // flush point: the first level above which fewer than 4096 supernodes remain (the many tiny leaf-side levels
-            // go out in one batch of long runs)
-            std::vector<i64> cnt(H.nlevels + 1, 0);
-            for (i64 sidx = 0; sidx < H.nsuper; ++sidx) ++cnt[H.snode[sidx].level];
-            i64 above = H.nsuper;
-            p->merge_level = 0;
-            for (int l = 0; l < H.nlevels; ++l) { above -= cnt[l]; p->merge_level = l; if (above < 4096) break; }
-            p->small_runs.assign(H.nlevels, {});
+            // Flush point: every level up to `merge_level` leaves in one batch when that level is final.  Each run costs
+            // one copy call (a few microseconds of host time during which no kernel is enqueued), and the leaf-side levels
+            // interleave in the postorder -- cfg2: 18 246 runs if every level flushes on its own, 467 when levels 0..5 go
+            // together -- so the merge level is the lowest one that keeps the whole factorization under 512 runs.
             auto is_small = [&](i64 sidx) {
                 const SnodeDev &d = H.snode[sidx];
                 const int rows = lu ? 2 * d.nsrow - d.nscol : d.nsrow;
                 return (i64)rows * d.nscol * 8 < (1 << 20);
             };
+            auto count_runs = [&](int ml) {
+                i64 runs = 0;
+                int prev = -1;
+                for (i64 sidx = 0; sidx < H.nsuper; ++sidx) {
+                    if (!is_small(sidx)) { prev = -1; continue; }
+                    const int fl = std::max<int>(H.snode[sidx].level, ml);
+                    if (fl != prev) ++runs;
+                    prev = fl;
+                }
+                return runs;
+            };
+            p->merge_level = 0;
+            while (p->merge_level + 1 < H.nlevels && count_runs(p->merge_level) > 512) ++p->merge_level;
+            p->small_runs.assign(H.nlevels, {});
             auto flush_level = [&](i64 sidx) { return std::max<int>(H.snode[sidx].level, p->merge_level); };
             for (i64 sidx = 0; sidx < H.nsuper;) {
                 if (!is_small(sidx)) { ++sidx; continue; }
@@ -529,6 +539,9 @@ int factorize_streamed(sfb200_plan *p, double *Lsx) {
     int rc = begin_factor(p);
     if (rc) return rc;
     p->copy_events_used = 0;
+    // SFB200_COPY_TRACE=1: per level, when the kernels and when the copies finished (stderr; timing experiments only)
+    const bool trace = getenv("SFB200_COPY_TRACE") != nullptr;
+    std::vector<cudaEvent_t> tr_main, tr_copy;
     auto publish = [&]() -> cudaEvent_t {            // everything issued so far on the main stream is visible to copies
         cudaEvent_t e = next_copy_event(p);
         if (!e) return nullptr;
@@ -572,11 +585,27 @@ int factorize_streamed(sfb200_plan *p, double *Lsx) {
         for (const auto &run : p->small_runs[lev])
             CK(cudaMemcpyAsync(Lsx + run.first, p->d_out + run.first, sizeof(double) * (size_t)run.second, cudaMemcpyDeviceToHost,
                                p->copy_stream));
+        if (trace) {
+            cudaEvent_t a, b;
+            CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b));
+            CK(cudaEventRecord(a, p->stream)); CK(cudaEventRecord(b, p->copy_stream));
+            tr_main.push_back(a); tr_copy.push_back(b);
+        }
     }
     CK(cudaGetLastError());
     CK(cudaEventRecord(p->ev[1], p->stream));            // end of the numeric work; the copy tail is only in the e2e time
     CK(cudaEventRecord(p->copy_done, p->copy_stream));
     CK(cudaStreamWaitEvent(p->stream, p->copy_done, 0));
+    if (trace) {
+        CK(cudaStreamSynchronize(p->stream));
+        for (size_t i = 0; i < tr_main.size(); ++i) {
+            float tm = 0, tc = 0;
+            cudaEventElapsedTime(&tm, p->ev[0], tr_main[i]);
+            cudaEventElapsedTime(&tc, p->ev[0], tr_copy[i]);
+            fprintf(stderr, "copy trace: level %2d kernels done %8.2f ms, copies done %8.2f ms\n", H.phases[i].level, tm, tc);
+            cudaEventDestroy(tr_main[i]); cudaEventDestroy(tr_copy[i]);
+        }
+    }
     return SFB200_OK;
 }
 
@@ -587,7 +616,7 @@ int sfb200_factorize(sfb200_plan *p, const double *Lx, const double *Ux, double 
     CK(cudaSetDevice(p->device));
     const HostPlan &H = p->H;
     if (H.split && !Ux) { set_error("unsymmetric LU needs Ux"); return SFB200_ERR_ARG; }
-    if (H.world > 1) { set_error("sfb200_factorize: partitioned plans are driven phase by phase (sfb200_phase_*)"); return SFB200_ERR_STATE; }
+    if (H.world > 1) { set_error("sfb200_factorize: partitioned plans are driven segment by segment (sfb200_segment_run)"); return SFB200_ERR_STATE; }
     // page-locked destination -> stream the copy-out behind the factorization; pageable -> pack + one copy at the end
     double *alias = nullptr;
     if (Lsx && !getenv("SFB200_NO_STREAMED_COPY")) {

@@ -91,7 +91,9 @@ struct PanelEmitter {
             // look-ahead split of the TOP-level update: [b1, s1) = the next block column (main stream), [s1, c1) = the rest
             const bool split = lookahead && depth == (int)widths.size() && b1 + w < c1;
             const int s1 = split ? b1 + w : c1;
-            if (split) slots[gs].next_of_split = true;
+            // every top-level update after the first one touches columns the side stream may still be updating (the REST of
+            // the previous block column): its launches join the side stream first -- also the last, unsplit ones
+            if (lookahead && depth == (int)widths.size() && i > 0) slots[gs].next_of_split = true;
             if (!lu) {
                 // C rows [b1,R) x cols [b1,s1) is diagonal-aligned; the REST block (cols >= s1) only has rows >= s1 below
                 // its own diagonal, so it is issued as its own diagonal-aligned op on rows [s1,R)
@@ -102,7 +104,11 @@ struct PanelEmitter {
                 gemm(gs, x + b1 + (i64)b0 * ld, x + b0 + (i64)b1 * ld, x + b1 + (i64)b1 * ld, R - b1, s1 - b1, K, G_B_KMAJOR);
                 gemm(gs, x + R + (i64)b0 * ld, x + b1 + (i64)b0 * ld, x + R + (i64)b1 * ld, m, s1 - b1, K, 0);
                 if (split) {
-                    gemm(gs, x + b1 + (i64)b0 * ld, x + b0 + (i64)s1 * ld, x + b1 + (i64)s1 * ld, R - b1, c1 - s1, K, G_B_KMAJOR, true);
+                    // LU: the next block column's factorization also works on its ROW block right of the diagonal (the U11 row
+                    // solves and the row-block updates reach every later column), so rows [b1,s1) of the rest stay on the
+                    // main stream; the side stream gets rows >= s1 only
+                    gemm(gs, x + b1 + (i64)b0 * ld, x + b0 + (i64)s1 * ld, x + b1 + (i64)s1 * ld, s1 - b1, c1 - s1, K, G_B_KMAJOR);
+                    gemm(gs, x + s1 + (i64)b0 * ld, x + b0 + (i64)s1 * ld, x + s1 + (i64)s1 * ld, R - s1, c1 - s1, K, G_B_KMAJOR, true);
                     gemm(gs, x + R + (i64)b0 * ld, x + s1 + (i64)b0 * ld, x + R + (i64)s1 * ld, m, c1 - s1, K, 0, true);
                 }
                 gemm(gs, x + b1 + (i64)b0 * ld, x + b0 + (i64)c1 * ld, x + b1 + (i64)c1 * ld, c1 - b1, n - c1, K, G_B_KMAJOR);

@@ -208,6 +208,44 @@ def test_full_size_backward_error(cfg):
     plan.close()
 
 
+def test_full_size_cfg4_lu_device_residual():
+    """BASELINE.json's LU config (3-D convection-diffusion 100^3, 14 GB factor, fronts wide enough for every blocking
+    level and for the look-ahead split) at full size: factorize without copy-out, solve and take the reference's
+    residual on the device (the device solve itself is checked against the oracle in test_device_solve_and_residual)."""
+    gen, g, kind = sf.matrices.CONFIGS["cfg4"]
+    A, _ = build_matrix(gen, g)
+    S = sf.analyze(A, kind)
+    plan = sf.Plan(S)
+    plan.factorize(S.array("Lx"), S.array("Ux"), download=False)
+    b = 1.0 + np.arange(A.n) / A.n
+    x = plan.solve(b)
+    dev = plan.residual(x, b)
+    assert dev["rnorm"] / (dev["anorm"] * dev["xnorm"]) <= BACKWARD_TOL
+    plan.close()
+
+
+@pytest.mark.parametrize("gen,g,kind", [("cd3d", 30, "lu"), ("lap3d", 30, "lu"), ("lap3d", 34, "cholesky")])
+def test_lookahead_split_with_narrow_blocking(gen, g, kind):
+    """Top fronts of ~900-1150 columns with a 64/128/256 blocking: four or more top-level block columns, so the trailing
+    updates are split between the main and the side stream (look-ahead), for LU as well as Cholesky."""
+    env = dict(SFB200_OUTER="128", SFB200_OUTER2="256")
+    os.environ.update(env)
+    try:
+        A, _ = build_matrix(gen, g)
+        S = sf.analyze(A, kind)
+        st = oracle_structure(S)
+        ux = S.array("Ux") if "Up" in st else None
+        plan = sf.Plan(S)
+    finally:
+        for k in env:
+            os.environ.pop(k, None)
+    ref_lsx, bad = sforacle.factorize(kind, st, S.array("Lx"), ux)
+    assert bad == 0
+    for _ in range(3):                     # a race would not need to show on the first run
+        compare(kind, st, ref_lsx, plan.factorize(S.array("Lx"), ux))
+    plan.close()
+
+
 @pytest.mark.parametrize("gen,g,kind,world,group_panels", [
     ("lap3d", 20, "cholesky", 2, 0), ("lap3d", 20, "cholesky", 4, 0), ("cd3d", 16, "lu", 3, 0),
     ("lap3d", 24, "cholesky", 2, 1), ("lap3d", 24, "cholesky", 4, 1), ("lap3d", 24, "cholesky", 3, 1)])

@@ -82,3 +82,28 @@ def test_solve_schedule_on_interpreter(gen, g, kind):
     res, norms = sforacle.residual(kind, st, S.array("Lx"), b, x, ux)
     assert norms[3] / (norms[0] * norms[2]) <= 1e-12
     backend.close()
+
+
+@pytest.mark.parametrize("gen,g,kind", [("cd3d", 16, "lu"), ("lap3d", 16, "cholesky"), ("lap3d", 12, "lu")])
+def test_lookahead_side_launches_may_run_late(gen, g, kind, monkeypatch):
+    """Look-ahead: the engine runs LF_SIDE launches on a second stream, any time up to the next LF_WAIT_SIDE launch.  The
+    interpreter's default order is "immediately"; here they run as late as the contract allows (SFCHECK_SIDE_LATE), with
+    a blocking small enough (8 / 16 / 32) that the top fronts are split.  Same factor either way, or the split
+    regions overlap something the main stream does in between."""
+    monkeypatch.setenv("SFCHECK_SIDE_LATE", "1")
+    A, _ = build_matrix(gen, g)
+    S = sf.analyze(A, kind)
+    st = {k: S.array(k) for k in ("Super", "SuperMap", "Lsip", "Lsxp", "Lsi", "LeafQueue", "Lp", "Li")}
+    st["csize"], st["nsleaf"] = S.int("csize"), S.int("nsleaf")
+    split = kind == "lu" and S.int("symmetric") == 0
+    ux = None
+    if split:
+        st["Up"], st["Ui"] = S.array("Up"), S.array("Ui")
+        ux = S.array("Ux")
+    ref, bad = sforacle.factorize(kind, st, S.array("Lx"), ux)
+    assert bad == 0
+    out, bad, stats = sforacle.plan_check(kind, A.n, A.Cp, A.Ci, A.Cx, A.symmetric, sf.DEFAULT_DEVSLOT, nb=8,
+                                          outer=32 * 100000 + 16, small_a=0, small_b=0)
+    assert bad == 0
+    mask = sf.lower_trapezoid_mask(kind, st["Super"], st["Lsip"], st["Lsxp"], S.int("xsize"))
+    assert sf.entrywise_rel_diff(ref[mask], out[mask]) <= 1e-10
