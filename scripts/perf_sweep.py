@@ -30,8 +30,13 @@ for env in envs:
     line = "%s env=%s launches=%d numeric %.2f ms  %.2f TFLOP/s |" % (cfg, env, plan.int("nlaunches"), best, S.flops / best / 1e9)
     for k, v in prof.items():
         line += " %s %.1fms(%d, %.1fTF)" % (k.replace("k_", ""), v["ms"], v["launches"], v["flops"] / v["ms"] / 1e9)
+    if os.environ.get("SFB200_SWEEP_VALIDATE"):       # device solve + residual for every setting
+        import numpy as np
+        b = 1.0 + np.arange(n) / n
+        d = plan.residual(plan.solve(b), b)
+        line += " | device backward error %.2e" % (d["rnorm"] / (d["anorm"] * d["xnorm"]))
     print(line, flush=True)
-    if not env:
+    if not env and not os.environ.get("SFB200_SWEEP_VALIDATE"):
         import sforacle
         st = {k: S.array(k) for k in ("Super", "SuperMap", "Lsip", "Lsxp", "Lsi", "LeafQueue", "Lp", "Li")}
         st["csize"], st["nsleaf"] = S.int("csize"), S.int("nsleaf")

@@ -663,7 +663,10 @@ __global__ void __launch_bounds__(WARPS_M *WARPS_N * 32)
 // are zero-filled by the producer warp.
 // ---------------------------------------------------------------------------------------------------------------
 namespace ws {
-constexpr int BM = 128, BN = 128, BK = 16, STAGES = 4, SA = 132;
+#ifndef SFB200_WS_STAGES
+#define SFB200_WS_STAGES 4
+#endif
+constexpr int BM = 128, BN = 128, BK = 16, STAGES = SFB200_WS_STAGES, SA = 132;
 constexpr int STAGE_DOUBLES = 2 * BK * SA;
 constexpr int SMEM_BYTES = STAGES * STAGE_DOUBLES * 8 + 2 * STAGES * 8 + 64;
 constexpr int NT = 384;
@@ -772,6 +775,11 @@ __global__ void __launch_bounds__(ws::NT, 1) k_gemm_ws(PlanDev P, const GemmOp *
             const int KT = (op.K + BK - 1) / BK;
             for (int kt = 0; kt < KT; ++kt) {
                 mbar_wait(empty + stage, phase ^ 1);
+                // The stage was last read through the generic proxy (the consumers' shared-memory loads, this warp's zero
+                // fill); the bulk copies below write it through the async proxy.  The mbarrier orders the warps, the proxy
+                // fence orders the two proxies: without it a 6-stage build of this kernel produced wrong factors (backward
+                // error 1e-5 on lap3d 64^3, run-to-run different), with it 6/6 runs are clean.
+                asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
                 double *dst = smem + stage * STAGE_DOUBLES + (is_b ? BK * SA : 0) + k * SA;
                 const int krem = op.K - kt * BK;
                 if (k < krem) {

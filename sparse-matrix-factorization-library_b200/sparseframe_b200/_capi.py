@@ -5,7 +5,8 @@ import ctypes as C
 import os
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(os.path.dirname(_PKG), "lib", "libsfb200.so")
+# SFB200_LIBRARY: another build of the same library (kernel experiments: scripts/perf_sweep.py); never a fallback
+LIB_PATH = os.environ.get("SFB200_LIBRARY") or os.path.join(os.path.dirname(_PKG), "lib", "libsfb200.so")
 
 _lib = None
 
