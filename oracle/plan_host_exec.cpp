@@ -46,6 +46,19 @@ int diag_lu(double *A, i64 ld, int nb) {
     return 0;
 }
 
+// leaf look-ahead: the update a G_SKIP_HEAD GEMM left to this diagonal block
+void diag_pending_update(double *X, const DiagOp &d, bool lu) {
+    if (d.upd_k <= 0) return;
+    double *A = X + d.a_off;
+    const double *L = X + d.l_off, *U = X + d.u_off;
+    for (int c = 0; c < d.nb; ++c)
+        for (int r = lu ? 0 : c; r < d.nb; ++r) {
+            double acc = 0.0;
+            for (int k = 0; k < d.upd_k; ++k) acc += L[r + (i64)k * d.ld] * (lu ? U[k + (i64)c * d.ld] : L[c + (i64)k * d.ld]);
+            A[r + (i64)c * d.ld] -= acc;
+        }
+}
+
 void trsm(double *X, const TrsmOp &t) {
     const double *D = X + t.t_off;
     for (int v = 0; v < t.nvec; ++v) {
@@ -82,6 +95,7 @@ void gemm(double *X, const GemmOp &g, const HostPlan &P, int B = 128) {
             } else if (lower) {
                 lim = j;
             }
+            if ((g.flags & G_SKIP_HEAD) && j < (int)g.meta) lim = std::max(lim, (int)g.meta);   // the next diagonal block's own
             for (int i = std::max(lim, ti * B); i < std::min(g.M, (ti + 1) * B); ++i) {
                 double acc = 0.0;
                 for (int k = 0; k < g.K; ++k) {
@@ -162,10 +176,10 @@ long run_one(const HostPlan &P, double *X, const Launch &L) {
             for (int k = 0; k < L.count; ++k) bad += small_front(X, P, P.small_tasks[L.first + k]);
             break;
         case L_POTRF:
-            for (int k = 0; k < L.count; ++k) { const DiagOp &d = P.diag_ops[L.first + k]; bad += diag_cholesky(X + d.a_off, d.ld, d.nb); }
+            for (int k = 0; k < L.count; ++k) { const DiagOp &d = P.diag_ops[L.first + k]; diag_pending_update(X, d, false); bad += diag_cholesky(X + d.a_off, d.ld, d.nb); }
             break;
         case L_GETRF:
-            for (int k = 0; k < L.count; ++k) { const DiagOp &d = P.diag_ops[L.first + k]; bad += diag_lu(X + d.a_off, d.ld, d.nb); }
+            for (int k = 0; k < L.count; ++k) { const DiagOp &d = P.diag_ops[L.first + k]; diag_pending_update(X, d, true); bad += diag_lu(X + d.a_off, d.ld, d.nb); }
             break;
         case L_TRSM:
             for (int k = 0; k < L.count; ++k) trsm(X, P.trsm_ops[L.first + k]);
@@ -189,27 +203,32 @@ long run_one(const HostPlan &P, double *X, const Launch &L) {
 }
 
 /* The engine puts LF_SIDE launches on a second stream: they may run any time between their issue point and the next
- * LF_WAIT_SIDE launch (or the end of the range, where the engine joins the side stream).  The default order here is
+ * LF_WAIT_SIDE launch (or the end of the range, where the engine joins the side stream); LF_DIAG_AHEAD launches likewise
+ * up to the next LF_WAIT_DIAG launch.  The default order here is
  * "immediately"; SFCHECK_SIDE_LATE=1 runs them as LATE as that contract allows, so that a side launch that overlaps
  * something the main stream does in between shows up as a wrong factor in the CPU test tier. */
 long run_launches(const HostPlan &P, double *X, int first, int count) {
     const bool late = getenv("SFCHECK_SIDE_LATE") != nullptr;
-    std::vector<int> deferred;
+    std::vector<int> deferred, deferred_diag;
     long bad = 0;
-    auto flush = [&]() -> long {
-        for (int li : deferred) { const long b = run_one(P, X, P.launches[li]); if (b < 0) return b; bad += b; }
-        deferred.clear();
+    auto flush = [&](std::vector<int> &q) -> long {
+        for (int li : q) { const long b = run_one(P, X, P.launches[li]); if (b < 0) return b; bad += b; }
+        q.clear();
         return 0;
     };
     for (int li = first; li < first + count; ++li) {
         const Launch &L = P.launches[li];
         if (late && (L.flags & LF_SIDE)) { deferred.push_back(li); continue; }
-        if (L.flags & LF_WAIT_SIDE) { const long b = flush(); if (b < 0) return b; }
+        if (late && (L.flags & LF_DIAG_AHEAD)) { deferred_diag.push_back(li); continue; }
+        if (L.flags & LF_WAIT_SIDE) { const long b = flush(deferred); if (b < 0) return b; }
+        if (L.flags & LF_WAIT_DIAG) { const long b = flush(deferred_diag); if (b < 0) return b; }
         const long b = run_one(P, X, L);
         if (b < 0) return b;
         bad += b;
     }
-    const long b = flush();
+    long b = flush(deferred);
+    if (b < 0) return b;
+    b = flush(deferred_diag);
     return b < 0 ? b : bad;
 }
 

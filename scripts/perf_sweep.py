@@ -13,7 +13,7 @@ n, r, c, x, sym = sf.matrices.generate(gen, g)
 S = sf.analyze(sf.compress(n, r, c, x, sym), kind)
 split = kind == "lu" and not sym
 lx, ux = S.array("Lx"), (S.array("Ux") if split else None)
-KEYS = ("SFB200_NB", "SFB200_OUTER", "SFB200_SMALL_A", "SFB200_SMALL_B", "SFB200_GEMM128_MIN", "SFB200_GEMM_WS", "SFB200_OUTER2", "SFB200_LOOKAHEAD", "SFB200_SPARE_SMS")
+KEYS = ("SFB200_NB", "SFB200_OUTER", "SFB200_SMALL_A", "SFB200_SMALL_B", "SFB200_GEMM128_MIN", "SFB200_GEMM_WS", "SFB200_OUTER2", "SFB200_LOOKAHEAD", "SFB200_SPARE_SMS", "SFB200_LEAF_LOOKAHEAD", "SFB200_LEAVE_SMS")
 envs = [dict()]
 for spec in sys.argv[2:]:
     envs.append(dict(kv.split("=") for kv in spec.split(",")))

@@ -5,7 +5,9 @@
 #include <chrono>
 #include <cstdio>
 #include <cstring>
+#include <map>
 #include <string>
+#include <tuple>
 #include <vector>
 
 #include "../../include/sfb200.h"
@@ -50,6 +52,19 @@ struct sfb200_plan {
     cudaEvent_t ev_to_side = nullptr, ev_from_side = nullptr;
     bool side_pending = false;
     int spare_sms = 16;
+    // leaf look-ahead: diagonal blocks flagged LF_DIAG_AHEAD are factorized on their own (high-priority) stream
+    cudaStream_t diag_stream = nullptr;
+    cudaEvent_t ev_to_diag = nullptr, ev_from_diag = nullptr;
+    bool diag_pending = false;
+    int leave_sms = 2;
+    // The schedule is static, so each replayed piece (the whole device-resident factorization, the whole streamed
+    // factorization into one destination, one multi-GPU segment) is captured once as a CUDA graph and launched from then
+    // on: kernel-to-kernel gaps and the cross-stream dependencies of the look-ahead become graph edges.
+    // (The first replay of a piece is issued plainly -- one-shot callers never pay for capture + instantiation, and lazily
+    // created helper objects exist by the time the second replay is captured.)
+    struct CachedGraph { cudaGraphExec_t exec; int64_t launches; };
+    std::map<std::tuple<int, size_t, size_t, const void *>, CachedGraph> graphs;
+    bool use_graphs = true;
     // streamed copy-out (host-buffer call with a page-locked Lsx): copy stream, per-level work lists
     cudaStream_t copy_stream = nullptr;
     std::vector<cudaEvent_t> copy_events;
@@ -123,17 +138,35 @@ int issue_launch_la(sfb200_plan *p, const Launch &L) {
         p->side_pending = true;
         return SFB200_OK;
     }
+    if (p->diag_stream && (L.flags & LF_DIAG_AHEAD)) {
+        CK(cudaEventRecord(p->ev_to_diag, p->stream));
+        CK(cudaStreamWaitEvent(p->diag_stream, p->ev_to_diag, 0));
+        const int rc = issue_launch_on(p, L, p->diag_stream, 0);
+        if (rc) return rc;
+        CK(cudaEventRecord(p->ev_from_diag, p->diag_stream));
+        p->diag_pending = true;
+        return SFB200_OK;
+    }
     if (p->side_pending && (L.flags & LF_WAIT_SIDE)) {
         CK(cudaStreamWaitEvent(p->stream, p->ev_from_side, 0));
         p->side_pending = false;
     }
-    return issue_launch_on(p, L, p->stream, 0);
+    if (p->diag_pending && (L.flags & LF_WAIT_DIAG)) {
+        CK(cudaStreamWaitEvent(p->stream, p->ev_from_diag, 0));
+        p->diag_pending = false;
+    }
+    // a persistent GEMM that runs next to a diagonal block leaves it a couple of SMs
+    return issue_launch_on(p, L, p->stream, (p->diag_stream && (L.flags & LF_LEAVE_SMS)) ? p->leave_sms : 0);
 }
 
 int join_side(sfb200_plan *p) {
     if (p->side_pending) {
         CK(cudaStreamWaitEvent(p->stream, p->ev_from_side, 0));
         p->side_pending = false;
+    }
+    if (p->diag_pending) {
+        CK(cudaStreamWaitEvent(p->stream, p->ev_from_diag, 0));
+        p->diag_pending = false;
     }
     return SFB200_OK;
 }
@@ -166,13 +199,51 @@ int run_launches(sfb200_plan *p, size_t first, size_t count) {
     return SFB200_OK;
 }
 
-int run_schedule(sfb200_plan *p) {
-    int rc = begin_factor(p);
-    if (rc) return rc;
-    for (const Phase &ph : p->H.phases) {        // level by level: each one ends with the side stream joined
-        if ((rc = run_launches(p, (size_t)ph.launch_first, (size_t)ph.launch_count))) return rc;
+// Replay `issue` (stream-ordered work on p->stream and the plan's helper streams, joined at the end) through a cached
+// CUDA graph: captured the first time the key is seen, launched afterwards.
+template <class F>
+int run_graphed(sfb200_plan *p, int kind, size_t first, size_t count, const void *tag, F issue) {
+    if (!p->use_graphs) return issue();
+    const auto key = std::make_tuple(kind, first, count, tag);
+    auto it = p->graphs.find(key);
+    if (it == p->graphs.end()) {
+        p->graphs.emplace(key, sfb200_plan::CachedGraph{nullptr, 0});
+        return issue();
     }
+    if (!it->second.exec) {
+        const int64_t before = p->launches;
+        CK(cudaStreamBeginCapture(p->stream, cudaStreamCaptureModeThreadLocal));
+        const int rc = issue();
+        cudaGraph_t g = nullptr;
+        const cudaError_t e = cudaStreamEndCapture(p->stream, &g);
+        if (rc || e != cudaSuccess || !g) {
+            if (g) cudaGraphDestroy(g);
+            cudaGetLastError();
+            if (!rc) set_error(std::string("stream capture failed: ") + cudaGetErrorString(e));
+            return rc ? rc : SFB200_ERR_CUDA;
+        }
+        cudaGraphExec_t ex = nullptr;
+        const cudaError_t ei = cudaGraphInstantiate(&ex, g, 0);
+        cudaGraphDestroy(g);
+        if (ei != cudaSuccess) { set_error(std::string("cudaGraphInstantiate: ") + cudaGetErrorString(ei)); return SFB200_ERR_CUDA; }
+        it->second = sfb200_plan::CachedGraph{ex, p->launches - before};
+        p->launches = before;
+    }
+    CK(cudaGraphLaunch(it->second.exec, p->stream));
+    p->launches += it->second.launches;
     return SFB200_OK;
+}
+
+int run_schedule(sfb200_plan *p) {
+    p->launches = 0;
+    return run_graphed(p, 0, 0, p->H.launches.size(), nullptr, [&]() -> int {
+        int rc = begin_factor(p);
+        if (rc) return rc;
+        for (const Phase &ph : p->H.phases) {        // level by level: each one ends with the side stream joined
+            if ((rc = run_launches(p, (size_t)ph.launch_first, (size_t)ph.launch_count))) return rc;
+        }
+        return SFB200_OK;
+    });
 }
 
 int check_status(sfb200_plan *p) {
@@ -213,6 +284,10 @@ void sfb200_plan_free(sfb200_plan *p) {
     if (p->ev_to_side) cudaEventDestroy(p->ev_to_side);
     if (p->ev_from_side) cudaEventDestroy(p->ev_from_side);
     if (p->side_stream) cudaStreamDestroy(p->side_stream);
+    for (auto &kv : p->graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+    if (p->ev_to_diag) cudaEventDestroy(p->ev_to_diag);
+    if (p->ev_from_diag) cudaEventDestroy(p->ev_from_diag);
+    if (p->diag_stream) cudaStreamDestroy(p->diag_stream);
     if (p->stream && p->own_stream) cudaStreamDestroy(p->stream);
     delete p;
 }
@@ -240,6 +315,7 @@ int sfb200_plan_create_part(const sfb200_symbolic *s, int device, int rank, int 
     if (const char *e = getenv("SFB200_DIST_PANEL_MIN")) prm.dist_panel_min_cols = atoi(e);
     if (const char *e = getenv("SFB200_GEMM_WS")) prm.use_ws = atoi(e);
     if (const char *e = getenv("SFB200_LOOKAHEAD")) prm.lookahead = atoi(e);
+    if (const char *e = getenv("SFB200_LEAF_LOOKAHEAD")) prm.leaf_lookahead = atoi(e);
     const int rc = build_plan(s->S, prm, p->H, rank, world);
     if (rc != 0) {
         delete p;
@@ -286,6 +362,14 @@ int sfb200_plan_create_part(const sfb200_symbolic *s, int device, int rank, int 
     if ((err = dmalloc((void **)&p->d_lx, sizeof(double) * (size_t)H.nnz))) return fail(err);
     if (H.split && (err = dmalloc((void **)&p->d_ux, sizeof(double) * (size_t)H.unnz))) return fail(err);
     if ((err = dmalloc((void **)&p->d_status, sizeof(int)))) return fail(err);
+    if (prm.leaf_lookahead) {
+        if (const char *e = getenv("SFB200_LEAVE_SMS")) p->leave_sms = atoi(e);
+        int lo_prio = 0, hi_prio = 0;
+        cudaDeviceGetStreamPriorityRange(&lo_prio, &hi_prio);
+        if (cudaStreamCreateWithPriority(&p->diag_stream, cudaStreamNonBlocking, hi_prio) != cudaSuccess ||
+            cudaEventCreateWithFlags(&p->ev_to_diag, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&p->ev_from_diag, cudaEventDisableTiming) != cudaSuccess) { set_error("diagonal-block stream"); return fail(SFB200_ERR_CUDA); }
+    }
     {   // copy-out work lists: small panels go through k_pack (written straight into mapped host memory), panels of
         // at least 1 MiB through the DMA engine (cudaMemcpy2DAsync), block column by block column for the widest fronts
         const bool lu = H.kind == Kind::LU;
@@ -368,6 +452,7 @@ int sfb200_plan_create_part(const sfb200_symbolic *s, int device, int rank, int 
     p->D.status = p->d_status;
     p->D.is_lu = H.kind == Kind::LU;
     p->D.dbg = getenv("SFB200_DBG") ? atoi(getenv("SFB200_DBG")) : 0;
+    if (const char *e = getenv("SFB200_GRAPHS")) p->use_graphs = atoi(e) != 0;
     *out = p;
     return SFB200_OK;
 }
@@ -454,8 +539,11 @@ int sfb200_segment_run(sfb200_plan *p, int k) {
     if (!p || k < 0 || k >= (int)p->H.segments.size()) { set_error("sfb200_segment_run: bad segment"); return SFB200_ERR_ARG; }
     CK(cudaSetDevice(p->device));
     const Segment &sg = p->H.segments[k];
-    const int rc = run_launches(p, (size_t)sg.launch_first, (size_t)sg.launch_count);
-    if (rc) return rc;
+    if (sg.launch_count > 0) {
+        const int rc = run_graphed(p, 2, (size_t)sg.launch_first, (size_t)sg.launch_count, nullptr,
+                                   [&]() -> int { return run_launches(p, (size_t)sg.launch_first, (size_t)sg.launch_count); });
+        if (rc) return rc;
+    }
     if (k + 1 == (int)p->H.segments.size()) {
         CK(cudaEventRecord(p->ev[1], p->stream));
         p->factored = true;
@@ -530,17 +618,12 @@ int copy_columns(sfb200_plan *p, i64 sidx, int c0, int c1, double *Lsx) {
 
 // Factorization with the copy-out streamed behind it: as soon as an etree level (or, for the widest fronts, a block
 // column of the level) is final, its panels leave for the host on a second stream while the next level computes.
-int factorize_streamed(sfb200_plan *p, double *Lsx) {
+int factorize_streamed_issue(sfb200_plan *p, double *Lsx, bool trace) {
     const HostPlan &H = p->H;
-    if (!p->d_out) {
-        CK(cudaMalloc((void **)&p->d_out, sizeof(double) * (size_t)std::max<i64>(H.xsize, 1)));
-        p->device_bytes += sizeof(double) * (size_t)H.xsize;
-    }
     int rc = begin_factor(p);
     if (rc) return rc;
     p->copy_events_used = 0;
     // SFB200_COPY_TRACE=1: per level, when the kernels and when the copies finished (stderr; timing experiments only)
-    const bool trace = getenv("SFB200_COPY_TRACE") != nullptr;
     std::vector<cudaEvent_t> tr_main, tr_copy;
     auto publish = [&]() -> cudaEvent_t {            // everything issued so far on the main stream is visible to copies
         cudaEvent_t e = next_copy_event(p);
@@ -593,7 +676,7 @@ int factorize_streamed(sfb200_plan *p, double *Lsx) {
         }
     }
     CK(cudaGetLastError());
-    CK(cudaEventRecord(p->ev[1], p->stream));            // end of the numeric work; the copy tail is only in the e2e time
+    if (trace) CK(cudaEventRecord(p->ev[1], p->stream));
     CK(cudaEventRecord(p->copy_done, p->copy_stream));
     CK(cudaStreamWaitEvent(p->stream, p->copy_done, 0));
     if (trace) {
@@ -606,6 +689,24 @@ int factorize_streamed(sfb200_plan *p, double *Lsx) {
             cudaEventDestroy(tr_main[i]); cudaEventDestroy(tr_copy[i]);
         }
     }
+    return SFB200_OK;
+}
+
+// Streamed copy-out: kernels, k_pack launches and device-to-host copies of one factorization into `Lsx`, replayed as one
+// CUDA graph per destination buffer from the second call on.
+int factorize_streamed(sfb200_plan *p, double *Lsx) {
+    const HostPlan &H = p->H;
+    if (!p->d_out) {
+        CK(cudaMalloc((void **)&p->d_out, sizeof(double) * (size_t)std::max<i64>(H.xsize, 1)));
+        p->device_bytes += sizeof(double) * (size_t)H.xsize;
+    }
+    const bool trace = getenv("SFB200_COPY_TRACE") != nullptr;
+    p->launches = 0;
+    int rc;
+    if (trace) rc = factorize_streamed_issue(p, Lsx, true);
+    else rc = run_graphed(p, 1, 0, H.launches.size(), Lsx, [&]() -> int { return factorize_streamed_issue(p, Lsx, false); });
+    if (rc) return rc;
+    if (!trace) CK(cudaEventRecord(p->ev[1], p->stream));      // includes the copy tail (the pieces are one graph)
     return SFB200_OK;
 }
 

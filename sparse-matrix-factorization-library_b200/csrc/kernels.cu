@@ -240,6 +240,44 @@ __global__ void __launch_bounds__(256) k_diag(PlanDev P, const DiagOp *__restric
             const int r = r0 + rr, c = c0 + cc;
             a[rr][cc] = (r < nb && c < nb) ? A[(int64_t)c * op.ld + r] : (r == c ? 1.0 : 0.0);
         }
+    if (op.upd_k > 0) {
+        // leaf look-ahead: the K = upd_k update of the previous leaf was left to this block (G_SKIP_HEAD on the GEMM side),
+        // A -= L * U with L = rows of this block in the previous leaf's columns; Cholesky: U = L^T, lower triangle only
+        __shared__ double Ls[16][65];
+        __shared__ double Us[LU ? 16 : 1][65];
+        const double *Lg = P.X + op.l_off, *Ug = P.X + op.u_off;
+        for (int k0 = 0; k0 < op.upd_k; k0 += 16) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int idx = tid + 256 * q;
+                {
+                    const int kk = idx >> 6, r = idx & 63, k = k0 + kk;          // rows contiguous
+                    Ls[kk][r] = (r < nb && k < op.upd_k) ? Lg[r + (int64_t)k * op.ld] : 0.0;
+                }
+                if (LU) {
+                    const int c = idx >> 4, kk = idx & 15, k = k0 + kk;          // k contiguous
+                    Us[kk][c] = (c < nb && k < op.upd_k) ? Ug[k + (int64_t)c * op.ld] : 0.0;
+                }
+            }
+            __syncthreads();
+            if (active) {
+#pragma unroll
+                for (int kk = 0; kk < 16; ++kk) {
+                    double lr[4], uc[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        lr[e] = Ls[kk][r0 + e];
+                        uc[e] = LU ? Us[kk][c0 + e] : Ls[kk][c0 + e];
+                    }
+#pragma unroll
+                    for (int cc = 0; cc < 4; ++cc)
+#pragma unroll
+                        for (int rr = 0; rr < 4; ++rr) a[rr][cc] = fma(-lr[rr], uc[cc], a[rr][cc]);
+                }
+            }
+            __syncthreads();
+        }
+    }
     if (ty == tx) {
 #pragma unroll
         for (int e = 0; e < 4; ++e) dsum[0][r0 + e] = a[e][e];
@@ -608,6 +646,7 @@ __global__ void __launch_bounds__(WARPS_M *WARPS_N * 32)
     } else {
         double *Cg = P.X + op.c_off;
         const bool lower = (op.flags & G_LOWER) != 0;
+        const int head = (op.flags & G_SKIP_HEAD) ? (int)op.meta : 0;
         // rows r are even; with even c_off and ldc every (r, r+1) pair is one aligned 16-byte word of the column
         const bool vec = (((op.c_off | (int64_t)op.ldc) & 1) == 0);
 #pragma unroll
@@ -615,7 +654,8 @@ __global__ void __launch_bounds__(WARPS_M *WARPS_N * 32)
             const int c = col0 + wn0 + 8 * j + g;
             if (c >= N) continue;
             double *colp = Cg + (int64_t)c * op.ldc;
-            const int lim = lower ? c : 0;
+            // G_SKIP_HEAD: rows < head of the columns < head belong to the next diagonal block's own update
+            const int lim = max(lower ? c : 0, c < head ? head : 0);
             // all loads of the column first (independent, all in flight), then the stores: a load/modify/store chain
             // per element would expose one global-memory round trip per element
             double2 cv[FM];
@@ -862,13 +902,15 @@ __global__ void __launch_bounds__(ws::NT, 1) k_gemm_ws(PlanDev P, const GemmOp *
         } else {
             double *Cg = P.X + op.c_off;
             const bool lower = (op.flags & G_LOWER) != 0;
+        const int head = (op.flags & G_SKIP_HEAD) ? (int)op.meta : 0;
             const bool vec = (((op.c_off | (int64_t)op.ldc) & 1) == 0);
 #pragma unroll
             for (int j = 0; j < FN; ++j) {
                 const int c = col0 + wn0 + 8 * j + g;
                 if (c >= N) continue;
                 double *colp = Cg + (int64_t)c * op.ldc;
-                const int lim = lower ? c : 0;
+                // G_SKIP_HEAD: rows < head of the columns < head belong to the next diagonal block's own update
+            const int lim = max(lower ? c : 0, c < head ? head : 0);
                 double2 cv[FM];
 #pragma unroll
                 for (int i = 0; i < FM; ++i) {

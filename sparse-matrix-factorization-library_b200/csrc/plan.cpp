@@ -17,6 +17,8 @@ struct SlotOps {
     std::vector<GemmOp> gemm;
     std::vector<GemmOp> side;     // look-ahead: REST part of a top-level trailing update (side stream)
     bool next_of_split = false;   // gemm holds NEXT parts: they must wait for the previous block's REST
+    bool diag_ahead = false;      // leaf look-ahead: the diagonal blocks apply the previous leaf's update themselves ...
+    bool feeds_diag_ahead = false;   // ... which this slot's gemm ops therefore leave alone (G_SKIP_HEAD)
 };
 
 // Recursive blocked right-looking factorization of one large panel (replaces dpotrf_ + dtrsm_, CH.c:2135-2142, the
@@ -41,6 +43,7 @@ struct PanelEmitter {
     std::vector<int> nslots;      // nslots[d] = slots used by one block of level d
 
     bool lookahead = false;
+    bool leaf_lookahead = false;
 
     PanelEmitter(const SnodeDev &s, bool is_lu, const std::vector<int> &w, std::map<int, SlotOps> &sl)
         : sn(s), lu(is_lu), widths(w), slots(sl) {
@@ -49,11 +52,12 @@ struct PanelEmitter {
         for (size_t d = 1; d < widths.size(); ++d) nslots[d] = (widths[d] / widths[d - 1]) * (nslots[d - 1] + 1);
     }
 
-    void gemm(int slot, i64 a, i64 b, i64 c, int M, int N, int K, int flags, bool side = false) {
+    void gemm(int slot, i64 a, i64 b, i64 c, int M, int N, int K, int flags, bool side = false, int skip_head = 0) {
         if (M <= 0 || N <= 0 || K <= 0) return;
         GemmOp g{};
         g.a_off = a; g.b_off = b; g.c_off = c; g.lda = g.ldb = g.ldc = sn.ld;
         g.M = M; g.N = N; g.K = K; g.flags = flags; g.tile_mod = 1; g.tile_rem = 0;
+        if (skip_head > 0) { g.flags |= G_SKIP_HEAD; g.meta = skip_head; slots[slot].feeds_diag_ahead = true; }
         (side ? slots[slot].side : slots[slot].gemm).push_back(g);
     }
     void trsm(int slot, i64 d, int w, i64 b_off, int nvec, int es, int vs, int flags) {
@@ -63,11 +67,20 @@ struct PanelEmitter {
         slots[slot].trsm.push_back(t);
     }
 
-    void leaf(int j0, int j1, int slot) {
+    // prev0 >= 0: the update of the previous leaf [prev0, j0) to this diagonal block is still pending (leaf look-ahead)
+    void leaf(int j0, int j1, int slot, int prev0 = -1) {
         const i64 x = sn.xoff, ld = sn.ld;
         const int n = sn.nscol, R = sn.nsrow, m = R - n, w = j1 - j0;
         const i64 d = x + j0 + (i64)j0 * ld;
-        slots[slot].diag.push_back(DiagOp{d, sn.ld, w});
+        DiagOp dop{};
+        dop.a_off = d; dop.ld = sn.ld; dop.nb = w;
+        if (prev0 >= 0) {
+            dop.l_off = x + j0 + (i64)prev0 * ld;       // rows of this block in the previous leaf's columns
+            dop.u_off = x + prev0 + (i64)j0 * ld;       // LU: the previous leaf's row block in this block's columns
+            dop.upd_k = j0 - prev0;
+            slots[slot].diag_ahead = true;
+        }
+        slots[slot].diag.push_back(dop);
         if (!lu) {
             trsm(slot + 1, d, w, x + j1 + (i64)j0 * ld, R - j1, sn.ld, 1, 0);
         } else {
@@ -82,11 +95,16 @@ struct PanelEmitter {
         const i64 x = sn.xoff, ld = sn.ld;
         const int n = sn.nscol, R = sn.nsrow, m = R - n;
         const int w = widths[depth - 1], stride = nslots[depth - 1] + 1;
+        // leaf look-ahead (sub-blocks are leaves): the update of leaf i leaves the next diagonal block alone; that block
+        // subtracts the K = w product itself, so its factorization depends on leaf i's solves only, not on the update
+        const bool leaf_la = leaf_lookahead && depth == 1;
         int i = 0;
         for (int b0 = c0; b0 < c1; b0 += w, ++i) {
             const int b1 = std::min(b0 + w, c1), K = b1 - b0;
-            block(b0, b1, depth - 1, slot + i * stride);
+            if (depth == 1) leaf(b0, b1, slot + i * stride, leaf_la && i > 0 ? b0 - w : -1);
+            else block(b0, b1, depth - 1, slot + i * stride);
             if (b1 >= c1) continue;
+            const int head = leaf_la ? std::min(b1 + w, c1) - b1 : 0;
             const int gs = slot + i * stride + nslots[depth - 1];
             // look-ahead split of the TOP-level update: [b1, s1) = the next block column (main stream), [s1, c1) = the rest
             const bool split = lookahead && depth == (int)widths.size() && b1 + w < c1;
@@ -97,11 +115,11 @@ struct PanelEmitter {
             if (!lu) {
                 // C rows [b1,R) x cols [b1,s1) is diagonal-aligned; the REST block (cols >= s1) only has rows >= s1 below
                 // its own diagonal, so it is issued as its own diagonal-aligned op on rows [s1,R)
-                gemm(gs, x + b1 + (i64)b0 * ld, x + b1 + (i64)b0 * ld, x + b1 + (i64)b1 * ld, R - b1, s1 - b1, K, G_LOWER);
+                gemm(gs, x + b1 + (i64)b0 * ld, x + b1 + (i64)b0 * ld, x + b1 + (i64)b1 * ld, R - b1, s1 - b1, K, G_LOWER, false, head);
                 if (split)
                     gemm(gs, x + s1 + (i64)b0 * ld, x + s1 + (i64)b0 * ld, x + s1 + (i64)s1 * ld, R - s1, c1 - s1, K, G_LOWER, true);
             } else {
-                gemm(gs, x + b1 + (i64)b0 * ld, x + b0 + (i64)b1 * ld, x + b1 + (i64)b1 * ld, R - b1, s1 - b1, K, G_B_KMAJOR);
+                gemm(gs, x + b1 + (i64)b0 * ld, x + b0 + (i64)b1 * ld, x + b1 + (i64)b1 * ld, R - b1, s1 - b1, K, G_B_KMAJOR, false, head);
                 gemm(gs, x + R + (i64)b0 * ld, x + b1 + (i64)b0 * ld, x + R + (i64)b1 * ld, m, s1 - b1, K, 0);
                 if (split) {
                     // LU: the next block column's factorization also works on its ROW block right of the diagonal (the U11 row
@@ -374,17 +392,21 @@ int build_plan(const Symbolic &S, const PlanParams &prm, HostPlan &P, int rank, 
             }
         };
         auto emit_slots = [&](std::map<int, SlotOps> &slots, int stride) {
-            for (auto &kv : slots) {
-                SlotOps &so = kv.second;
-                const int top_block = stride > 0 ? kv.first / stride : -1;
-                if (!so.diag.empty()) {
-                    Launch L{};
-                    L.kind = lu ? L_GETRF : L_POTRF; L.level = lev; L.top_block = top_block;
-                    L.first = (int32_t)P.diag_ops.size();
-                    L.count = L.grid = (int32_t)so.diag.size();
-                    P.diag_ops.insert(P.diag_ops.end(), so.diag.begin(), so.diag.end());
-                    P.launches.push_back(L);
-                }
+            bool wait_diag = false;              // the next main-stream launch must join the diagonal-block stream
+            auto emit_diag = [&](SlotOps &so, int top_block, int lflags) {
+                Launch L{};
+                L.kind = lu ? L_GETRF : L_POTRF; L.level = lev; L.top_block = top_block; L.flags = lflags;
+                L.first = (int32_t)P.diag_ops.size();
+                L.count = L.grid = (int32_t)so.diag.size();
+                P.diag_ops.insert(P.diag_ops.end(), so.diag.begin(), so.diag.end());
+                P.launches.push_back(L);
+                so.diag.clear();
+            };
+            for (auto it = slots.begin(); it != slots.end(); ++it) {
+                SlotOps &so = it->second;
+                const int top_block = stride > 0 ? it->first / stride : -1;
+                const size_t first_launch = P.launches.size();
+                if (!so.diag.empty()) emit_diag(so, top_block, 0);
                 if (!so.trsm.empty()) {
                     Launch L{};
                     L.kind = L_TRSM; L.level = lev; L.top_block = top_block;
@@ -399,8 +421,19 @@ int build_plan(const Symbolic &S, const PlanParams &prm, HostPlan &P, int rank, 
                     L.grid = (int32_t)ctas;
                     P.launches.push_back(L);
                 }
-                if (!so.gemm.empty()) emit_gemm(so.gemm, top_block, so.next_of_split ? LF_WAIT_SIDE : 0);
+                // whatever this slot issued first on the main stream is the first consumer of a block factorized ahead
+                if (wait_diag && P.launches.size() > first_launch) { P.launches[first_launch].flags |= LF_WAIT_DIAG; wait_diag = false; }
+                // leaf look-ahead: the next slot's diagonal blocks only need this slot's predecessors (the solves of the
+                // leaf), so they are issued BEFORE this slot's update and run next to it on their own stream
+                auto nx = std::next(it);
+                const bool ahead = so.feeds_diag_ahead && nx != slots.end() && nx->first == it->first + 1 && nx->second.diag_ahead &&
+                                   !nx->second.diag.empty();
+                if (ahead) emit_diag(nx->second, top_block, LF_DIAG_AHEAD);
+                const size_t first_gemm = P.launches.size();
+                if (!so.gemm.empty()) emit_gemm(so.gemm, top_block, (so.next_of_split ? LF_WAIT_SIDE : 0) | (ahead ? LF_LEAVE_SMS : 0));
                 if (!so.side.empty()) emit_gemm(so.side, top_block, LF_SIDE);
+                if (wait_diag && P.launches.size() > first_gemm) { P.launches[first_gemm].flags |= LF_WAIT_DIAG; wait_diag = false; }
+                if (ahead) wait_diag = true;
             }
         };
         // a segment = the collectives gathered so far, then the launches emitted since the previous segment ended
@@ -475,7 +508,7 @@ int build_plan(const Symbolic &S, const PlanParams &prm, HostPlan &P, int rank, 
                 for (int k = 0; k < 4; ++k) if (pb <= small_limits[k]) { c = k; break; }
             if (c >= 0 && !dist_update) { cls[c].push_back(s); ++P.nsmall; continue; }
             ++P.nlarge;
-            { PanelEmitter pe(d, lu, widths, slots); pe.lookahead = prm.lookahead != 0; pe.run(); }
+            { PanelEmitter pe(d, lu, widths, slots); pe.lookahead = prm.lookahead != 0; pe.leaf_lookahead = prm.leaf_lookahead != 0; pe.run(); }
             if (!dist_update) scatter_ops(scatter, 1, 0);
         }
         for (int c = 0; c < 4; ++c) {
@@ -509,6 +542,7 @@ int build_plan(const Symbolic &S, const PlanParams &prm, HostPlan &P, int rank, 
                     const int b0 = b * Wd;
                     if (b0 >= d.nscol || block_owner(s, b) != rank) continue;
                     PanelEmitter pe(d, false, dist_widths, fs);
+                    pe.leaf_lookahead = prm.leaf_lookahead != 0;
                     pe.block(b0, std::min(b0 + Wd, (int)d.nscol), 1, 0);
                 }
                 emit_slots(fs, 0);

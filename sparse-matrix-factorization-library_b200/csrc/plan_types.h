@@ -28,6 +28,8 @@ enum GemmFlags : int32_t {
     G_B_KMAJOR  = 1 << 2,   // B is stored K x N (k contiguous) instead of N x K        (LU: U11 row blocks)
     G_LIM_SEGB  = 1 << 3,   // scatter mask: row >= first row of the column's ancestor segment   (LU, L side)
     G_LIM_SEGE  = 1 << 4,   // scatter mask: row >= end of the column's ancestor segment, dest += u-offset (LU, U side)
+    G_SKIP_HEAD = 1 << 5,   // the leading meta x meta block of C is left alone: the next diagonal block applies this
+                            // update itself (DiagOp::upd_k) so that it can be factorized while this GEMM still runs
 };
 
 struct GemmOp {
@@ -62,9 +64,13 @@ struct TrsmOp {
 
 // ---- diagonal block factorization --------------------------------------------------------------------------
 struct DiagOp {
-    int64_t a_off;
-    int32_t ld;
+    int64_t a_off;      // the nb x nb diagonal block (ld)
+    int64_t l_off;      // leaf look-ahead: before factorizing, A -= L * U with L = nb x upd_k at l_off (ld; the panel
+    int64_t u_off;      // rows of this block in the previous leaf's columns) and U = upd_k x nb at u_off (ld; LU only --
+    int32_t ld;         // Cholesky uses L^T and touches the lower triangle only).  upd_k = 0: nothing pending.
     int32_t nb;
+    int32_t upd_k;
+    int32_t pad;
 };
 
 // ---- one kernel launch of the static schedule ---------------------------------------------------------------
@@ -99,6 +105,9 @@ struct Launch {
 enum LaunchFlags : int32_t {
     LF_SIDE      = 1 << 0,   // issue on the side stream (after everything issued so far on the main stream)
     LF_WAIT_SIDE = 1 << 1,   // main-stream launch that must wait for the side stream's work issued so far
+    LF_DIAG_AHEAD = 1 << 2,  // diagonal blocks factorized on their own stream while the previous leaf's update still runs
+    LF_WAIT_DIAG = 1 << 3,   // main-stream launch that must wait for those
+    LF_LEAVE_SMS = 1 << 4,   // persistent GEMM that runs next to an LF_DIAG_AHEAD launch: do not occupy every SM
 };
 
 // ---- multi-GPU: the schedule of one rank is a list of SEGMENTS: first the segment's collectives (issued by the host

@@ -208,6 +208,35 @@ def test_full_size_backward_error(cfg):
     plan.close()
 
 
+@pytest.mark.parametrize("gen,g,kind", [("lap3d", 30, "cholesky"), ("cd3d", 24, "lu")])
+def test_graph_replays_match_the_first_plain_run(gen, g, kind):
+    """The engine issues the first factorization of a plan plainly, captures the second one as a CUDA graph and replays
+    that graph afterwards (device-resident path, streamed copy-out into one page-locked buffer).  Every replay, also
+    with new matrix values, must give what a fresh plan gives."""
+    import torch
+    A, _ = build_matrix(gen, g)
+    S = sf.analyze(A, kind)
+    st = oracle_structure(S)
+    ux = S.array("Ux") if "Up" in st else None
+    lx = S.array("Lx")
+    ref_lsx, bad = sforacle.factorize(kind, st, lx, ux)
+    assert bad == 0
+    plan = sf.Plan(S)
+    pinned = torch.empty(S.int("xsize"), dtype=torch.float64).pin_memory()
+    for it in range(4):                                    # plain, capture, replay, replay
+        pinned.zero_()
+        out = plan.factorize(lx, ux, out=pinned.numpy())   # streamed copy-out (page-locked destination)
+        compare(kind, st, ref_lsx, out)
+    for it in range(4):                                    # pageable destination: device path + pack + one copy
+        compare(kind, st, ref_lsx, plan.factorize(lx, ux))
+    # new values through the captured graphs: 3 A -> sqrt(3) L (Cholesky), L unchanged and 3 U (LU)
+    scaled = plan.factorize(3.0 * lx, None if ux is None else 3.0 * ux)
+    fresh = sf.Plan(S)
+    compare(kind, st, fresh.factorize(3.0 * lx, None if ux is None else 3.0 * ux), scaled, tol=1e-12)
+    fresh.close()
+    plan.close()
+
+
 def test_full_size_cfg4_lu_device_residual():
     """BASELINE.json's LU config (3-D convection-diffusion 100^3, 14 GB factor, fronts wide enough for every blocking
     level and for the look-ahead split) at full size: factorize without copy-out, solve and take the reference's
