@@ -884,8 +884,15 @@ int sfb200_solve_device(sfb200_plan *p, double *d_B, int nrhs) {
     cudaEvent_t a, b;
     CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b));
     CK(cudaEventRecord(a, p->stream));
-    for (const SolveLaunch &L : H.solve_fwd) launch_solve(p->d_X, p->d_lsi32, d_B, H.n, nrhs, lu, p->d_solve + L.first, L.kind, L.count, p->stream);
-    for (const SolveLaunch &L : H.solve_bwd) launch_solve(p->d_X, p->d_lsi32, d_B, H.n, nrhs, lu, p->d_solve + L.first, L.kind, L.count, p->stream);
+    // the sweeps are a fixed launch sequence too: one graph per (right-hand-side buffer, count)
+    const int64_t keep = p->launches;
+    const int rcg = run_graphed(p, 3, (size_t)nrhs, 0, d_B, [&]() -> int {
+        for (const SolveLaunch &L : H.solve_fwd) launch_solve(p->d_X, p->d_lsi32, d_B, H.n, nrhs, lu, p->d_solve + L.first, L.kind, L.count, p->stream);
+        for (const SolveLaunch &L : H.solve_bwd) launch_solve(p->d_X, p->d_lsi32, d_B, H.n, nrhs, lu, p->d_solve + L.first, L.kind, L.count, p->stream);
+        return cudaGetLastError() == cudaSuccess ? SFB200_OK : SFB200_ERR_CUDA;
+    });
+    p->launches = keep;
+    if (rcg) return rcg;
     CK(cudaEventRecord(b, p->stream));
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(p->stream));

@@ -976,40 +976,50 @@ __device__ __forceinline__ int solve_gidx(const SolveTask &t, const int32_t *lsi
     return i < t.nscol ? t.col0 + i : lsi[t.lsip + i];
 }
 
-// x_b = T^-1 b_b on one 64 x 64 diagonal block (64 threads, column-oriented elimination in shared memory)
+// x_b = T^-1 b_b on one 64 x 64 diagonal block.
 //   mode 0: forward, T lower (unit diagonal for LU);  mode 1: backward Cholesky, T = L^T;  mode 2: backward LU, T = U
+// 64 threads stage the block (thread r fetches row r: 64 independent loads in flight, coalesced across threads) and the
+// reciprocals of its diagonal; then ONE warp runs the substitution with register-resident unknowns (lane l owns
+// equations l and l + 32) and a shuffle broadcast per unknown -- no block-wide barrier inside the 64 dependent steps.
+// x_j = v_j * (1 / t_jj): the reciprocal is formed once per block outside the dependent chain (<= 1 ulp from v_j / t_jj).
 __global__ void __launch_bounds__(64) k_solve_diag(SolveArgs A, const SolveTask *__restrict__ tasks, int mode) {
     __shared__ double T[64 * 65];
-    __shared__ double v[64];
+    __shared__ double rd[64];
     const SolveTask t = tasks[blockIdx.x];
     const int tid = threadIdx.x, w = t.w;
     const double *D = A.X + t.xoff + t.j0 + (int64_t)t.j0 * t.ld;
-    for (int idx = tid; idx < w * w; idx += 64) {
-        const int c = idx / w, r = idx - c * w;
-        T[r * 65 + c] = D[(int64_t)c * t.ld + r];         // T[r][c] = block(r, c)
-    }
     const bool unit = A.is_lu && mode == 0;
+    {
+        double row[64];
+#pragma unroll
+        for (int c = 0; c < 64; ++c) row[c] = (tid < w && c < w) ? D[(int64_t)c * t.ld + tid] : (c == tid ? 1.0 : 0.0);
+#pragma unroll
+        for (int c = 0; c < 64; ++c) T[tid * 65 + c] = row[c];         // T[r][c] = block(r, c); identity beyond w
+        rd[tid] = unit ? 1.0 : 1.0 / T[tid * 65 + tid];              // own row: written by this thread just above
+    }
+    __syncthreads();
+    if (tid >= 32) return;
+    const int lane = tid;
     const int64_t g0 = t.col0 + t.j0;
     for (int q = 0; q < A.nrhs; ++q) {
         double *b = A.rhs + (int64_t)q * A.n + g0;
-        __syncthreads();
-        if (tid < w) v[tid] = b[tid];
-        __syncthreads();
-        for (int s = 0; s < w; ++s) {
-            const int j = mode == 0 ? s : w - 1 - s;
+        double v0 = lane < w ? b[lane] : 0.0, v1 = lane + 32 < w ? b[lane + 32] : 0.0;
+#pragma unroll 8
+        for (int s = 0; s < 64; ++s) {
+            const int j = mode == 0 ? s : 63 - s;
             // coefficient of unknown j in equation i:  mode 0: block(i, j), i > j;  mode 1: block(j, i) (L^T), i < j;
             //                                           mode 2: block(i, j) (U), i < j
-            if (tid == j && !unit) v[j] = v[j] / T[j * 65 + j];
-            __syncthreads();
-            const double xj = v[j];
-            const bool later = mode == 0 ? tid > j : tid < j;
-            if (tid < w && later) {
-                const double coef = mode == 1 ? T[j * 65 + tid] : T[tid * 65 + j];
-                v[tid] = fma(-coef, xj, v[tid]);
-            }
-            __syncthreads();
+            const double mine = (j & 32) ? v1 : v0;
+            const double xj = __shfl_sync(0xffffffffu, mine, j & 31) * rd[j];
+            if (lane == (j & 31)) { if (j & 32) v1 = xj; else v0 = xj; }
+            const double c0 = mode == 1 ? T[j * 65 + lane] : T[lane * 65 + j];
+            const double c1 = mode == 1 ? T[j * 65 + lane + 32] : T[(lane + 32) * 65 + j];
+            const bool l0 = mode == 0 ? lane > j : lane < j, l1 = mode == 0 ? lane + 32 > j : lane + 32 < j;
+            if (l0) v0 = fma(-c0, xj, v0);
+            if (l1) v1 = fma(-c1, xj, v1);
         }
-        if (tid < w) b[tid] = v[tid];
+        if (lane < w) b[lane] = v0;
+        if (lane + 32 < w) b[lane + 32] = v1;
     }
 }
 
@@ -1025,6 +1035,7 @@ __global__ void __launch_bounds__(256) k_solve_upd_fwd(SolveArgs A, const SolveT
         __syncthreads();
         for (int i = t.r0 + threadIdx.x; i < t.r1; i += 256) {
             double acc = 0.0;
+#pragma unroll 16
             for (int jj = 0; jj < t.w; ++jj) acc = fma(P[(int64_t)jj * t.ld + i], xb[jj], acc);
             atomicAdd(b + solve_gidx(t, A.lsi, i), -acc);
         }
@@ -1048,6 +1059,7 @@ __global__ void __launch_bounds__(256) k_solve_upd_bwd(SolveArgs A, const SolveT
         for (int jj = warp; jj < t.w; jj += 8) {
             const double *col = P + (int64_t)jj * t.ld + t.r0;
             double acc = 0.0;
+#pragma unroll 8
             for (int k = lane; k < cnt; k += 32) acc = fma(col[k], xs[k], acc);
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
@@ -1065,6 +1077,7 @@ __global__ void __launch_bounds__(64) k_solve_upd_bwd_u(SolveArgs A, const Solve
     for (int q = 0; q < A.nrhs; ++q) {
         double *b = A.rhs + (int64_t)q * A.n;
         double acc = 0.0;
+#pragma unroll 8
         for (int c = t.r0; c < t.r1; ++c) acc = fma(P[(int64_t)c * t.ld], b[t.col0 + c], acc);
         atomicAdd(b + t.col0 + t.j0 + jj, -acc);
     }

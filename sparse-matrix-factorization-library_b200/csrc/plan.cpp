@@ -612,7 +612,7 @@ int build_plan(const Symbolic &S, const PlanParams &prm, HostPlan &P, int rank, 
             P.unz_row.resize(P.unnz);
             for (i64 i = 0; i < n; ++i) for (i64 p = S.U.ptr[i]; p < S.U.ptr[i + 1]; ++p) P.unz_row[p] = (int32_t)i;
         }
-        const int SB = 64, SLAB = 1024;
+        const int SB = 64, SLAB = 256;       // one row per thread of the 256-thread update kernels
         auto base_task = [&](i64 s, int j0) {
             const SnodeDev &d = P.snode[s];
             SolveTask t{};
