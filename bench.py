@@ -208,7 +208,10 @@ def main():
         "small %d large %d" % (rank, cfg, n, S.int("nsuper"), S.int("xsize") * 8e-9, flops, t_analyze, t_plan,
                                plan.int("nlevels"), plan.int("nlaunches"), plan.int("nsmall"), plan.int("nlarge")))
 
-    stream = torch.cuda.current_stream()
+    # one explicit (capturable) stream for everything: the engine's launches and graph replays, torch's collectives and
+    # the timing events -- the legacy default stream cannot be captured into CUDA graphs
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
     plan.set_stream(stream.cuda_stream)
     d_lx = torch.from_numpy(lx).cuda()
     d_ux = torch.from_numpy(ux).cuda() if split else None

@@ -29,7 +29,8 @@ S = sf.analyze(A, kind)
 t_an = time.time() - t0
 split = kind == "lu" and S.int("symmetric") == 0
 plan = sf.Plan(S, device=local, rank=rank, world=world)
-stream = torch.cuda.current_stream()
+stream = torch.cuda.Stream()          # capturable (the legacy default stream is not): segments replay as CUDA graphs
+torch.cuda.set_stream(stream)
 plan.set_stream(stream.cuda_stream)
 d_lx = torch.from_numpy(S.array("Lx")).cuda()
 d_ux = torch.from_numpy(S.array("Ux")).cuda() if split else None

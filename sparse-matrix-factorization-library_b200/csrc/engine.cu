@@ -212,7 +212,13 @@ int run_graphed(sfb200_plan *p, int kind, size_t first, size_t count, const void
     }
     if (!it->second.exec) {
         const int64_t before = p->launches;
-        CK(cudaStreamBeginCapture(p->stream, cudaStreamCaptureModeThreadLocal));
+        // the legacy default stream (a caller's sfb200_plan_set_stream(0)) cannot be captured: such plans replay plainly
+        if (p->stream == nullptr || p->stream == cudaStreamLegacy || p->stream == cudaStreamPerThread ||
+            cudaStreamBeginCapture(p->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+            cudaGetLastError();
+            p->use_graphs = false;
+            return issue();
+        }
         const int rc = issue();
         cudaGraph_t g = nullptr;
         const cudaError_t e = cudaStreamEndCapture(p->stream, &g);
