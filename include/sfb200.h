@@ -54,6 +54,13 @@ const char *sfb200_last_error(void);
 int sfb200_analyze(int kind, int is_symmetric, int64_t n, const int64_t *Cp, const int64_t *Ci, const double *Cx,
                    uint64_t dev_slot_size, sfb200_symbolic **out);
 
+/* Same analysis with the fill-reducing ordering supplied by the caller instead of METIS_NodeND (which is 96 % of the
+ * analysis time on the 3-D configs): order[k] = original index placed at position k, i.e. the array "Order"
+ * of an earlier analysis of the same pattern -- which this call then reproduces bit for bit -- or any other permutation
+ * (geometric nested dissection, AMD, identity).  SFB200_ERR_ORDERING if `order` is not a permutation of 0..n-1. */
+int sfb200_analyze_ordered(int kind, int is_symmetric, int64_t n, const int64_t *Cp, const int64_t *Ci, const double *Cx,
+                           uint64_t dev_slot_size, const int64_t *order, sfb200_symbolic **out);
+
 /* Wrap a structure computed elsewhere (e.g. by the reference's own SparseFrame_analyze): only what the
  * factorize step reads.  Arrays are copied.  Up/Ui may be NULL (Cholesky, or LU on a symmetric matrix). */
 int sfb200_symbolic_wrap(int kind, int64_t n, int64_t nsuper, const int64_t *Super, const int64_t *Lsip,
@@ -63,7 +70,11 @@ int sfb200_symbolic_wrap(int kind, int64_t n, int64_t nsuper, const int64_t *Sup
 /* Scalars: "n","nnz","nsuper","nfsuper","isize","xsize","csize","nstage","nsleaf","unnz".  -1 if unknown. */
 int64_t sfb200_symbolic_int(const sfb200_symbolic *s, const char *name);
 
-/* Arrays by the reference's field names: "Perm","Parent","Post","ColCount","Lp","Li","LTp","LTi","Up","Ui",
+/* Wall time of the analysis stages in seconds: "t_order" (adjacency + METIS), "t_tree" (permute, etree, postorder,
+ * column counts), "t_structure" (supernodes, row lists, stages); "flops".  -1 if unknown. */
+double sfb200_symbolic_double(const sfb200_symbolic *s, const char *name);
+
+/* Arrays by the reference's field names: "Order" (the ordering METIS returned, input of sfb200_analyze_ordered), "Perm","Parent","Post","ColCount","Lp","Li","LTp","LTi","Up","Ui",
  * "UTp","UTi","Super","SuperMap","Sparent","Lsip","Lsxp","Lsi","ST_Map","ST_Pointer","ST_Index","LeafQueue",
  * "Aoffset","Moffset" (int64) and "Lx","LTx","Ux","UTx" (double).  Returns NULL if absent; *count = length. */
 const void *sfb200_symbolic_array(const sfb200_symbolic *s, const char *name, int64_t *count);

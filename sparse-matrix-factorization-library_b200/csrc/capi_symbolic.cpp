@@ -17,8 +17,8 @@ extern "C" {
 const char *sfb200_version(void) { return "sfb200 0.1 (sm_100a)"; }
 const char *sfb200_last_error(void) { return g_last_error.c_str(); }
 
-int sfb200_analyze(int kind, int is_symmetric, int64_t n, const int64_t *Cp, const int64_t *Ci, const double *Cx,
-                   uint64_t dev_slot_size, sfb200_symbolic **out) {
+int sfb200_analyze_ordered(int kind, int is_symmetric, int64_t n, const int64_t *Cp, const int64_t *Ci, const double *Cx,
+                           uint64_t dev_slot_size, const int64_t *order, sfb200_symbolic **out) {
     if (!out || !Cp || n < 0 || (kind != SFB200_CHOLESKY && kind != SFB200_LU)) {
         set_error("sfb200_analyze: bad argument");
         return SFB200_ERR_ARG;
@@ -26,14 +26,31 @@ int sfb200_analyze(int kind, int is_symmetric, int64_t n, const int64_t *Cp, con
     CscView A;
     A.n = n; A.colptr = Cp; A.rowind = Ci; A.val = Cx; A.symmetric = is_symmetric != 0;
     auto *s = new sfb200_symbolic();
-    const int rc = analyze(A, kind == SFB200_LU ? Kind::LU : Kind::Cholesky, dev_slot_size, s->S);
+    const int rc = analyze(A, kind == SFB200_LU ? Kind::LU : Kind::Cholesky, dev_slot_size, s->S, order);
     if (rc != 0) {
         delete s;
-        set_error(rc == 2 ? "sfb200_analyze: METIS did not return a permutation" : "sfb200_analyze: malformed matrix");
+        set_error(rc == 2 ? (order ? "sfb200_analyze_ordered: `order` is not a permutation of 0..n-1"
+                                   : "sfb200_analyze: METIS did not return a permutation")
+                          : "sfb200_analyze: malformed matrix");
         return rc == 2 ? SFB200_ERR_ORDERING : SFB200_ERR_ARG;
     }
     *out = s;
     return SFB200_OK;
+}
+
+int sfb200_analyze(int kind, int is_symmetric, int64_t n, const int64_t *Cp, const int64_t *Ci, const double *Cx,
+                   uint64_t dev_slot_size, sfb200_symbolic **out) {
+    return sfb200_analyze_ordered(kind, is_symmetric, n, Cp, Ci, Cx, dev_slot_size, nullptr, out);
+}
+
+double sfb200_symbolic_double(const sfb200_symbolic *s, const char *name) {
+    if (!s || !name) return -1.0;
+    const std::string k(name);
+    if (k == "t_order") return s->S.t_order;
+    if (k == "t_tree") return s->S.t_tree;
+    if (k == "t_structure") return s->S.t_structure;
+    if (k == "flops") return sfb200_symbolic_flops(s);
+    return -1.0;
 }
 
 int sfb200_symbolic_wrap(int kind, int64_t n, int64_t nsuper, const int64_t *Super, const int64_t *Lsip,
@@ -98,6 +115,7 @@ const void *sfb200_symbolic_array(const sfb200_symbolic *s, const char *name, in
         return v.empty() ? nullptr : (const void *)v.data();
     };
     if (k == "Perm") return give(S.Perm);
+    if (k == "Order") return give(S.Order);
     if (k == "Parent") return give(S.Parent);
     if (k == "Post") return give(S.Post);
     if (k == "ColCount") return give(S.ColCount);

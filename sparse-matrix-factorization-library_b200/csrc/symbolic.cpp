@@ -3,6 +3,7 @@
 #include "symbolic.hpp"
 
 #include <algorithm>
+#include <chrono>
 #include <cstring>
 #include <numeric>
 
@@ -459,8 +460,15 @@ static void supernodal_structure(const CscView &A, Symbolic &S) {
     }
 }
 
-int analyze(const CscView &A, Kind kind, uint64_t devSlotSize, Symbolic &S) {
+static double wall() {
+    return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+int analyze(const CscView &A, Kind kind, uint64_t devSlotSize, Symbolic &S, const i64 *given_perm) {
     if (A.n < 0 || !A.colptr || (A.colptr[A.n] > 0 && !A.rowind)) return 1;
+    for (i64 j = 0; j < A.n; ++j) if (A.colptr[j + 1] < A.colptr[j]) return 1;
+    for (i64 p = 0; p < A.colptr[A.n]; ++p) if (A.rowind[p] < 0 || A.rowind[p] >= A.n) return 1;
+    const double t0 = wall();
     S = Symbolic();
     S.kind = kind;
     S.symmetric = (kind == Kind::Cholesky) ? true : A.symmetric;
@@ -469,8 +477,10 @@ int analyze(const CscView &A, Kind kind, uint64_t devSlotSize, Symbolic &S) {
     S.devSlotSize = devSlotSize;
     const bool split = kind == Kind::LU && !A.symmetric;
 
-    if (split) {
-        symmetrized_lower_pattern(A, S.CPCTp, S.CPCTi);
+    if (split) symmetrized_lower_pattern(A, S.CPCTp, S.CPCTi);       // part of matrix_info either way
+    if (given_perm) {
+        S.Perm.assign(given_perm, given_perm + A.n);
+    } else if (split) {
         fill_reducing_order(A.n, S.CPCTp.data(), S.CPCTi.data(), S.Perm);
     } else {
         fill_reducing_order(A.n, A.colptr, A.rowind, S.Perm);
@@ -482,6 +492,9 @@ int analyze(const CscView &A, Kind kind, uint64_t devSlotSize, Symbolic &S) {
             seen[S.Perm[j]] = 1;
         }
     }
+    S.Order = S.Perm;
+    const double t1 = wall();
+    S.t_order = given_perm ? 0.0 : t1 - t0;
     CscView Av = A;
     Av.symmetric = S.symmetric;
     permute_triangles(Av, kind, S.Perm, S.L, S.LT, S.U, S.UT);
@@ -489,7 +502,10 @@ int analyze(const CscView &A, Kind kind, uint64_t devSlotSize, Symbolic &S) {
     tree_postorder(S.n, S.Parent, nullptr, S.Post);
     column_counts(S.n, S.L, split ? &S.U : nullptr, S.Parent, S.Post, S.ColCount);
     tree_postorder(S.n, S.Parent, &S.ColCount, S.Post);
+    const double t2 = wall();
+    S.t_tree = t2 - t1;
     supernodal_structure(Av, S);
+    S.t_structure = wall() - t2;
     return 0;
 }
 

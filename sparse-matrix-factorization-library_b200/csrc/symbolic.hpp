@@ -38,6 +38,7 @@ struct Symbolic {
     i64 nnz = 0;
     uint64_t devSlotSize = 0;       // common_info->devSlotSize; the structure depends on it (CH.c:1476-1496, 1556-1574)
 
+    std::vector<i64> Order;         // fill-reducing ordering as METIS_NodeND returned it (before the postorder relabelling)
     std::vector<i64> Perm;          // final ordering: METIS composed with the weighted postorder (CH.c:1438-1443)
     std::vector<i64> Parent;        // etree of the permuted matrix, relabelled (CH.c:1439)
     std::vector<i64> Post;          // weighted postorder in pre-relabel labels (matrix_info->Post)
@@ -62,13 +63,22 @@ struct Symbolic {
     // LU + unsymmetric only: pattern of lower(C + C^T) fed to METIS (LU.c:2254-2396)
     std::vector<i64> CPCTp, CPCTi;
 
+    // wall time of the stages in seconds (where the analysis time goes)
+    double t_order = 0.0;           // adjacency + METIS_NodeND (0 when the caller supplied the ordering)
+    double t_tree = 0.0;            // permutation into triangles, etree, postorders, column counts
+    double t_structure = 0.0;       // supernodes, row lists, stages
+
     i64 panel_entries(i64 nscol, i64 nsrow) const {
         return kind == Kind::LU ? nscol * (2 * nsrow - nscol) : nscol * nsrow;
     }
 };
 
-// Full analysis.  Returns 0 on success, non-zero on a malformed input or a METIS failure.
-int analyze(const CscView &A, Kind kind, uint64_t devSlotSize, Symbolic &out);
+// Full analysis.  Returns 0 on success, non-zero on a malformed input or a METIS failure (2: not a permutation).
+// given_perm != nullptr: use this fill-reducing ordering (new position k holds old index given_perm[k], the meaning of
+// METIS_NodeND's perm / matrix_info->Perm before the postorder relabelling) instead of calling METIS -- the ordering is
+// 96 % of the analysis time on the 3-D configs, and an ordering saved from an earlier analysis of the same pattern
+// reproduces that analysis bit for bit.
+int analyze(const CscView &A, Kind kind, uint64_t devSlotSize, Symbolic &out, const i64 *given_perm = nullptr);
 
 // Individual stages, exposed for the unit tests.
 void fill_reducing_order(i64 n, const i64 *colptr, const i64 *rowind, std::vector<i64> &perm);

@@ -8,7 +8,8 @@
  * What each entry point does here vs. the reference (CH.c = Cholesky/Source/SparseFrame.c):
  *   SparseFrame_allocate_gpu   CH.c:16-285    no arenas / cuBLAS handles; only counts devices and derives devSlotSize with
  *                                             the reference's formula (the symbolic structure depends on it)
- *   SparseFrame_read_matrix    CH.c:400-691   MatrixMarket coordinate reader + compress, same semantics
+ *   SparseFrame_read_matrix    CH.c:400-691   MatrixMarket coordinate reader + compress, same semantics; whole-file,
+ *                                             multi-threaded parse, plus a binary container (matrix_reader.hpp)
  *   SparseFrame_analyze        CH.c:1916-1978 host symbolic analysis (csrc/symbolic.cpp), bit-exact arrays, plus the
  *                                             device plan (cached per matrix_info, freed by cleanup)
  *   SparseFrame_factorize      CH.c:3019-3034 sfb200_factorize: H2D of Lx, GPU numeric factorization, D2H into Lsx
@@ -38,6 +39,7 @@
 
 #include "../../include/sfb200.h"
 #include "sparseframe_abi.h"
+#include "matrix_reader.hpp"
 
 namespace {
 
@@ -57,6 +59,48 @@ T *dup_array(const sfb200_symbolic *s, const char *name, int64_t min_count = 0) 
     T *dst = (T *)malloc((size_t)(alloc > 0 ? alloc : 1) * sizeof(T));
     if (cnt > 0) memcpy(dst, src, (size_t)cnt * sizeof(T));
     return dst;
+}
+
+/* Ordering cache: METIS_NodeND is 96 % of the analysis time on the 3-D configs and depends on the pattern
+ * only.  With SF_ORDER_CACHE=<directory> the ordering of every analysed pattern is kept in <directory>/<hash>.order
+ * (n int64, hash = FNV-1a over kind, symmetry, n, Cp, Ci) and a later analysis of the same pattern -- a new time step, a
+ * second run of the driver -- skips METIS and reproduces the first analysis bit for bit. */
+std::string order_cache_path(const matrix_info_struct *m) {
+    const char *dir = getenv("SF_ORDER_CACHE");
+    if (!dir || !*dir) return std::string();
+    uint64_t h = 1469598103934665603ull;
+    auto mix = [&](const void *ptr, size_t bytes) {
+        const unsigned char *b = (const unsigned char *)ptr;
+        for (size_t i = 0; i < bytes; ++i) { h ^= b[i]; h *= 1099511628211ull; }
+    };
+    const int64_t head[3] = {SF_KIND, m->isSymmetric, (int64_t)m->nrow};
+    mix(head, sizeof(head));
+    mix(m->Cp, (size_t)(m->nrow + 1) * sizeof(Long));
+    mix(m->Ci, (size_t)m->Cp[m->nrow] * sizeof(Long));
+    char name[64];
+    snprintf(name, sizeof(name), "/%016llx.order", (unsigned long long)h);
+    return std::string(dir) + name;
+}
+
+bool load_order(const std::string &path, Long n, std::vector<int64_t> &order) {
+    FILE *f = fopen(path.c_str(), "rb");
+    if (!f) return false;
+    order.resize((size_t)n);
+    const bool ok = fread(order.data(), sizeof(int64_t), (size_t)n, f) == (size_t)n && fgetc(f) == EOF;
+    fclose(f);
+    return ok;
+}
+
+void store_order(const std::string &path, const sfb200_symbolic *s) {
+    int64_t cnt = 0;
+    const void *src = sfb200_symbolic_array(s, "Order", &cnt);
+    if (!src || cnt <= 0) return;
+    const std::string tmp = path + ".tmp" + std::to_string((long)getpid());
+    FILE *f = fopen(tmp.c_str(), "wb");
+    if (!f) return;
+    const bool ok = fwrite(src, sizeof(int64_t), (size_t)cnt, f) == (size_t)cnt;
+    if (fclose(f) == 0 && ok) rename(tmp.c_str(), path.c_str());
+    else remove(tmp.c_str());
 }
 
 void drop_cached(const matrix_info_struct *m) {
@@ -158,49 +202,50 @@ int SparseFrame_initialize_matrix(struct matrix_info_struct *m) {
     return 0;
 }
 
-/* MatrixMarket coordinate reader: "real"/anything-else, "symmetric"/anything-else; explicit zeros are dropped,
- * indices become 0-based (CH.c:423-521). */
+/* Input: MatrixMarket coordinate text ("real"/anything-else, "symmetric"/anything-else; explicit zeros are dropped,
+ * indices become 0-based, CH.c:423-521) or the binary triplet container -- see matrix_reader.hpp.  The whole file is read
+ * at once and parsed by all host threads (SF_READ_THREADS overrides the count). */
 static int read_triplets(struct matrix_info_struct *m) {
-    char *line = nullptr;
-    size_t cap = 0;
-    char s0[1025], s1[1025], s2[1025], s3[1025], s4[1025];
-    auto next_line = [&]() { return getline(&line, &cap, m->file) != -1; };
-    bool ok = false;
-    while (next_line()) if (line[0] != '\0') { ok = true; break; }
-    if (!ok || strncmp(line, "%%MatrixMarket", 14) != 0) { printf("Matrix format error\n\n"); free(line); return 1; }
-    s3[0] = s4[0] = 0;
-    sscanf(line, "%1024s %1024s %1024s %1024s %1024s", s0, s1, s2, s3, s4);
-    m->isSymmetric = strcmp(s4, "symmetric") == 0;
-    m->isComplex = strcmp(s3, "real") != 0;
-    ok = false;
-    while (next_line()) if (line[0] != '\0' && line[0] != '%' && line[0] != '\n') { ok = true; break; }
-    long nrow = 0, ncol = 0, nz = 0;
-    if (!ok || sscanf(line, "%ld %ld %ld", &nrow, &ncol, &nz) != 3) { printf("Matrix format error\n\n"); free(line); return 1; }
+    std::vector<char> buf;
+    if (!sfio::slurp(m->file, buf)) { printf("Matrix read error\n\n"); return 1; }
+    sfio::Triplets T;
+    int nthreads = 0;
+    if (const char *e = getenv("SF_READ_THREADS")) nthreads = atoi(e);
+    const bool binary = sfio::is_binary(buf.data(), buf.size());
+    const int rc = binary ? sfio::parse_binary(buf.data(), buf.size(), T)
+                          : sfio::parse_matrix_market(buf.data(), buf.size(), T, nthreads);
+    if (rc == sfio::ERR_FORMAT) { printf("Matrix format error\n\n"); return 1; }
+    m->isSymmetric = T.symmetric;
+    m->isComplex = T.complex_field;
     printf("matrix %s is %s %s, ncol = %ld nrow = %ld nzmax = %ld\n\n", basename((char *)m->path),
-           m->isComplex ? "complex" : "real", m->isSymmetric ? "symmetric" : "unsymmetric", ncol, nrow, nz);
-    if (m->isComplex) { printf("Error: complex matrices are not supported by the B200 engine\n"); free(line); return 1; }
-    m->Tj = (Long *)malloc((size_t)(nz > 0 ? nz : 1) * sizeof(Long));
-    m->Ti = (Long *)malloc((size_t)(nz > 0 ? nz : 1) * sizeof(Long));
-    m->Tx = (Float *)malloc((size_t)(nz > 0 ? nz : 1) * sizeof(Float));
-    long cnt = 0;
-    while (next_line()) {
-        if (line[0] == '\0' || line[0] == '\n') continue;
-        long i, j;
-        double v, w;
-        const int got = sscanf(line, "%ld %ld %lg %lg", &i, &j, &v, &w);
-        if (got < 3) { printf("Error: invalid matrix entry\n"); free(line); return 1; }
-        if (v == 0.0) continue;
-        if (cnt >= nz) { printf("Error: nzmax exceeded\n"); free(line); return 1; }
-        m->Ti[cnt] = i - 1;
-        m->Tj[cnt] = j - 1;
-        m->Tx[cnt] = v;
-        ++cnt;
+           m->isComplex ? "complex" : "real", m->isSymmetric ? "symmetric" : "unsymmetric", T.ncol, T.nrow, T.nz_declared);
+    if (m->isComplex) { printf("Error: complex matrices are not supported by the B200 engine\n"); return 1; }
+    if (rc == sfio::ERR_ENTRY) { printf("Error: invalid matrix entry\n"); return 1; }
+    if (rc == sfio::ERR_IMAG) { printf("Error: imaginary part not present\n"); return 1; }
+    if (rc == sfio::ERR_NZMAX) { printf("Error: nzmax exceeded\n"); return 1; }
+    if (rc != sfio::OK) return 1;
+    const size_t cnt = T.ti.size(), alloc = cnt > 0 ? cnt : 1;
+    for (size_t k = 0; k < cnt; ++k)
+        if (T.ti[k] < 0 || T.ti[k] >= T.nrow || T.tj[k] < 0 || T.tj[k] >= T.ncol) { printf("Error: invalid matrix entry\n"); return 1; }
+    m->Tj = (Long *)malloc(alloc * sizeof(Long));
+    m->Ti = (Long *)malloc(alloc * sizeof(Long));
+    m->Tx = (Float *)malloc(alloc * sizeof(Float));
+    if (cnt) {
+        memcpy(m->Ti, T.ti.data(), cnt * sizeof(Long));
+        memcpy(m->Tj, T.tj.data(), cnt * sizeof(Long));
+        memcpy(m->Tx, T.tx.data(), cnt * sizeof(Float));
     }
-    free(line);
-    m->ncol = ncol;
-    m->nrow = nrow;
-    m->nzmax = cnt;
+    m->ncol = T.ncol;
+    m->nrow = T.nrow;
+    m->nzmax = (Long)cnt;
     return 0;
+}
+
+/* Writes triplets (0-based, file order) as the binary container SparseFrame_read_matrix recognises by its magic:
+ * reading it back gives the same Cp/Ci/Cx as the MatrixMarket file the triplets came from.  Not in the reference. */
+int SparseFrame_write_binary_matrix(const char *path, int isSymmetric, Long nrow, Long ncol, Long nz, const Long *Ti,
+                                    const Long *Tj, const Float *Tx) {
+    return sfio::write_binary(path, isSymmetric != 0, nrow, ncol, nz, (const int64_t *)Ti, (const int64_t *)Tj, Tx);
 }
 
 /* stable counting sort by column (CH.c:526-587): file order is kept inside each column, nothing is summed */
@@ -243,8 +288,17 @@ int SparseFrame_analyze(struct common_info_struct *common_info, struct matrix_in
     const double t0 = SparseFrame_time();
     drop_cached(m);
     sfb200_symbolic *s = nullptr;
-    int rc = sfb200_analyze(SF_KIND, m->isSymmetric, m->nrow, (const int64_t *)m->Cp, (const int64_t *)m->Ci, m->Cx,
+    int rc = SFB200_ERR_ORDERING;
+    const std::string cache = order_cache_path(m);
+    std::vector<int64_t> order;
+    if (!cache.empty() && load_order(cache, m->nrow, order))
+        rc = sfb200_analyze_ordered(SF_KIND, m->isSymmetric, m->nrow, (const int64_t *)m->Cp, (const int64_t *)m->Ci, m->Cx,
+                                    (uint64_t)common_info->devSlotSize, order.data(), &s);
+    if (rc == SFB200_ERR_ORDERING) {       /* no cache, or a stale / damaged file: order with METIS */
+        rc = sfb200_analyze(SF_KIND, m->isSymmetric, m->nrow, (const int64_t *)m->Cp, (const int64_t *)m->Ci, m->Cx,
                             (uint64_t)common_info->devSlotSize, &s);
+        if (rc == SFB200_OK && !cache.empty()) store_order(cache, s);
+    }
     if (rc) { printf("SparseFrame_analyze: %s\n", sfb200_last_error()); return rc; }
     const Long n = m->nrow;
     m->Perm = dup_array<Long>(s, "Perm");

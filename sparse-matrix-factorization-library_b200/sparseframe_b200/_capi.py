@@ -19,6 +19,7 @@ SYMBOLS = [
     "sfb200_plan_profile_get", "sfb200_plan_create_part", "sfb200_plan_double", "sfb200_plan_segment_info",
     "sfb200_plan_coll_info", "sfb200_plan_owner", "sfb200_plan_factor_ptr", "sfb200_partition_begin", "sfb200_segment_run",
     "sfb200_plan_panel_offsets", "sfb200_plan_profile_launch", "sfb200_solve", "sfb200_solve_device", "sfb200_residual",
+    "sfb200_analyze_ordered", "sfb200_symbolic_double",
 ]
 
 
@@ -40,6 +41,9 @@ def lib():
     L.sfb200_version.restype = C.c_char_p
     L.sfb200_last_error.restype = C.c_char_p
     L.sfb200_analyze.argtypes = [ci, ci, i64, vp, vp, vp, u64, C.POINTER(vp)]
+    L.sfb200_analyze_ordered.argtypes = [ci, ci, i64, vp, vp, vp, u64, vp, C.POINTER(vp)]
+    L.sfb200_symbolic_double.restype = dbl
+    L.sfb200_symbolic_double.argtypes = [vp, C.c_char_p]
     L.sfb200_symbolic_wrap.argtypes = [ci, i64, i64, vp, vp, vp, vp, vp, vp, vp, vp, C.POINTER(vp)]
     L.sfb200_symbolic_int.restype = i64
     L.sfb200_symbolic_int.argtypes = [vp, C.c_char_p]

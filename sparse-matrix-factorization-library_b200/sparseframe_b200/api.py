@@ -49,7 +49,7 @@ def compress(n, rows, cols, vals, symmetric=True) -> Matrix:
 class Symbolic:
     """Result of symbolic analysis (SparseFrame_analyze, CH.c:1916-1978 / LU.c:2233-2458)."""
 
-    _INT64 = ("Perm", "Parent", "Post", "ColCount", "Lp", "Li", "LTp", "LTi", "Up", "Ui", "UTp", "UTi", "Super",
+    _INT64 = ("Order", "Perm", "Parent", "Post", "ColCount", "Lp", "Li", "LTp", "LTi", "Up", "Ui", "UTp", "UTi", "Super",
               "SuperMap", "Sparent", "Lsip", "Lsxp", "Lsi", "ST_Map", "ST_Pointer", "ST_Index", "LeafQueue",
               "Aoffset", "Moffset", "CPCTp", "CPCTi")
     _F64 = ("Lx", "LTx", "Ux", "UTx")
@@ -71,6 +71,9 @@ class Symbolic:
         buf = (C.c_char * (cnt.value * 8)).from_address(p)
         return np.frombuffer(buf, dtype=dt, count=cnt.value).copy()
 
+    def double(self, name) -> float:
+        return float(_capi.lib().sfb200_symbolic_double(self._h, name.encode()))
+
     @property
     def flops(self) -> float:
         return float(_capi.lib().sfb200_symbolic_flops(self._h))
@@ -87,11 +90,18 @@ class Symbolic:
             pass
 
 
-def analyze(A: Matrix, kind="cholesky", devslot=DEFAULT_DEVSLOT) -> Symbolic:
+def analyze(A: Matrix, kind="cholesky", devslot=DEFAULT_DEVSLOT, order=None) -> Symbolic:
+    """Symbolic analysis; `order` (the "Order" array of an earlier analysis of the same pattern, or any permutation)
+    replaces the METIS call."""
     L = _capi.lib()
     h = C.c_void_p()
-    rc = L.sfb200_analyze(_kind(kind), int(A.symmetric), A.n, A.Cp.ctypes.data, A.Ci.ctypes.data, A.Cx.ctypes.data,
-                          int(devslot), C.byref(h))
+    if order is not None:
+        order = np.ascontiguousarray(order, dtype=np.int64)
+        if order.shape != (A.n,):
+            raise ValueError("order must have n entries")
+    rc = L.sfb200_analyze_ordered(_kind(kind), int(A.symmetric), A.n, A.Cp.ctypes.data, A.Ci.ctypes.data,
+                                  A.Cx.ctypes.data, int(devslot), order.ctypes.data if order is not None else None,
+                                  C.byref(h))
     if rc != 0:
         raise RuntimeError("sfb200_analyze failed (%d): %s" % (rc, _capi.last_error()))
     return Symbolic(h, _kind(kind), int(devslot))

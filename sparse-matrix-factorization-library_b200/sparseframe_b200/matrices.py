@@ -132,3 +132,19 @@ def write_matrix_market(path, n, rows, cols, vals, symmetric):
         for i in range(0, len(rows), chunk):
             np.savetxt(f, np.column_stack([rows[i:i + chunk] + 1, cols[i:i + chunk] + 1, vals[i:i + chunk]]),
                        fmt="%d %d %.17g")
+
+
+def write_binary(path, n, rows, cols, vals, symmetric):
+    """Binary triplet container of the drop-in library (dropin/matrix_reader.hpp): magic "SFB200T1", int64 flags / nrow /
+    ncol / nz, then Ti, Tj (0-based int64) and Tx (float64) in file order.  SparseFrame_read_matrix recognises it by
+    the magic and builds the same Cp/Ci/Cx as from the MatrixMarket text of the same triplets (explicit zeros are
+    dropped here, as the text reader drops them, CH.c:493)."""
+    rows, cols, vals = np.asarray(rows, np.int64), np.asarray(cols, np.int64), np.asarray(vals, np.float64)
+    keep = vals != 0.0
+    rows, cols, vals = rows[keep], cols[keep], vals[keep]
+    with open(path, "wb") as f:
+        f.write(b"SFB200T1")
+        np.array([1 if symmetric else 0, n, n, len(rows)], np.int64).tofile(f)
+        rows.tofile(f)
+        cols.tofile(f)
+        vals.tofile(f)

@@ -1,0 +1,202 @@
+"""Input side of the drop-in library: SparseFrame_read_matrix on MatrixMarket text (whole-file, multi-threaded
+parse) and on the binary triplet container must leave exactly the Cp/Ci/Cx that the reference's reader + compress build
+(CH.c:400-587): file order inside a column, explicit zeros dropped, nothing summed, values bit-identical to "%lg"."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import sparseframe_b200 as sf
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG = os.path.join(ROOT, "sparse-matrix-factorization-library_b200")
+
+# reads argv[1] through the drop-in's own entry points and dumps what it found
+PROBE = r"""
+#include <stdio.h>
+#include <string.h>
+#include "SparseFrame.h"
+int SparseFrame_initialize_matrix(struct matrix_info_struct *);
+int SparseFrame_read_matrix(struct matrix_info_struct *);
+int main(int argc, char **argv) {
+  static struct matrix_info_struct m;
+  memset(&m, 0, sizeof(m));
+  m.path = argv[1];
+  SparseFrame_initialize_matrix(&m);
+  int rc = SparseFrame_read_matrix(&m);
+  if (rc) { printf("rc=%d\n", rc); return 3; }
+  FILE *f = fopen(argv[2], "wb");
+  long h[5] = {m.nrow, m.ncol, m.nzmax, m.isSymmetric, m.isComplex};
+  fwrite(h, sizeof(long), 5, f);
+  fwrite(m.Cp, sizeof(long), m.ncol + 1, f);
+  fwrite(m.Ci, sizeof(long), m.nzmax, f);
+  fwrite(m.Cx, sizeof(double), m.nzmax, f);
+  fclose(f);
+  return 0; }
+"""
+
+
+@pytest.fixture(scope="module")
+def probe(tmp_path_factory):
+    d = tmp_path_factory.mktemp("reader")
+    src = d / "probe.c"
+    src.write_text(PROBE)
+    exe = d / "probe"
+    lib = os.path.join(PKG, "LU", "Lib")
+    subprocess.check_call(["gcc", "-fopenmp", "-I" + os.path.join(PKG, "LU", "Include"), str(src), "-o", str(exe),
+                           "-L" + lib, "-lSparseFrame", "-Wl,-rpath," + lib])
+
+    def run(path, threads=None):
+        out = str(path) + ".dump"
+        env = dict(os.environ)
+        if threads is not None:
+            env["SF_READ_THREADS"] = str(threads)
+        p = subprocess.run([str(exe), str(path), out], env=env, capture_output=True, text=True)
+        if p.returncode != 0:
+            return None, p.stdout
+        raw = np.fromfile(out, dtype=np.int64)
+        nrow, ncol, nz, sym, cplx = raw[:5]
+        cp = raw[5:5 + ncol + 1]
+        ci = raw[5 + ncol + 1:5 + ncol + 1 + nz]
+        cx = raw[5 + ncol + 1 + nz:].view(np.float64)
+        return dict(nrow=nrow, ncol=ncol, nz=nz, sym=sym, cplx=cplx, Cp=cp, Ci=ci, Cx=cx), p.stdout
+    return run
+
+
+def expected(n, r, c, x, sym):
+    A = sf.compress(n, r, c, x, sym)
+    return A.Cp, A.Ci, A.Cx
+
+
+@pytest.mark.parametrize("gen,g", [("lap2d", 30), ("cd3d", 9), ("el3d", 4)])
+@pytest.mark.parametrize("threads", [1, 3, None])
+def test_text_and_binary_give_the_reference_csc(probe, tmp_path, gen, g, threads):
+    n, r, c, x, sym = sf.matrices.generate(gen, g)
+    rng = np.random.default_rng(7)
+    x = x * (1.0 + rng.random(len(x)))                   # 17 significant digits: exercises the strtod path
+    x[::7] = np.round(x[::7], 3)                         # short decimals: the fast path
+    mtx, binf = tmp_path / "a.mtx", tmp_path / "a.sfbin"
+    sf.matrices.write_matrix_market(str(mtx), n, r, c, x, sym)
+    sf.matrices.write_binary(str(binf), n, r, c, x, sym)
+    cp, ci, cx = expected(n, r, c, x, sym)
+    for path in (mtx, binf):
+        got, out = probe(path, threads)
+        assert got is not None, out
+        assert (got["nrow"], got["ncol"], got["sym"], got["cplx"]) == (n, n, int(sym), 0)
+        assert np.array_equal(got["Cp"], cp) and np.array_equal(got["Ci"], ci)
+        assert np.array_equal(got["Cx"].view(np.int64), cx.view(np.int64))          # bit-identical values
+
+
+def test_reader_semantics(probe, tmp_path):
+    """Comments, blank lines, explicit zeros (dropped), a fourth column, exponents, signs, duplicates kept in file order."""
+    text = "\n".join([
+        "%%MatrixMarket matrix coordinate real general", "% a comment", "%another", "3 3 9",
+        "1 1 2.5", "2 1 -1e0", "3 1 0", "", "1 2 +0.125E+1 0", "2 2 4", "2 2 5.000000000000000001", "3 3 1e-3",
+        "  3   2\t7.25  ", "1 3 0.0 1.0", "3 3 123456789012345678e-17"]) + "\n"
+    p = tmp_path / "s.mtx"
+    p.write_text(text)
+    got, out = probe(p, 2)
+    assert got is not None, out
+    assert got["sym"] == 0 and got["nz"] == 9
+    assert got["Cp"].tolist() == [0, 2, 6, 9]
+    assert got["Ci"].tolist() == [0, 1, 0, 1, 1, 2, 2, 0, 2]
+    want = [2.5, -1.0, 1.25, 4.0, float("5.000000000000000001"), 7.25, 1e-3, 0.0, float("123456789012345678e-17")]
+    assert got["Cx"].tolist() == want
+
+
+@pytest.mark.parametrize("body,msg", [
+    ("%%MatrixMarket matrix coordinate real general\n2 2 1\n1 1 1\n2 2 1\n", "nzmax exceeded"),
+    ("%%MatrixMarket matrix coordinate real general\n2 2 2\n1 1\n", "invalid matrix entry"),
+    ("%%MatrixMarket matrix coordinate real general\n2 2 2\n1 3 1.0\n", "invalid matrix entry"),
+    ("%%NotMatrixMarket\n", "Matrix format error"),
+    ("%%MatrixMarket matrix coordinate real general\n2 2\n", "Matrix format error"),
+    ("%%MatrixMarket matrix coordinate complex general\n1 1 1\n1 1 1.0 0.0\n", "complex"),
+])
+def test_reader_errors(probe, tmp_path, body, msg):
+    p = tmp_path / "bad.mtx"
+    p.write_text(body)
+    got, out = probe(p)
+    assert got is None and msg in out
+
+
+# analysis through the drop-in (no device needed: the plan upload is skipped with a message), dumping the structure
+ANALYZE_PROBE = r"""
+#include <stdio.h>
+#include <string.h>
+#include "SparseFrame.h"
+int SparseFrame_initialize_matrix(struct matrix_info_struct *);
+int SparseFrame_read_matrix(struct matrix_info_struct *);
+int SparseFrame_analyze(struct common_info_struct *, struct matrix_info_struct *);
+int main(int argc, char **argv) {
+  static struct matrix_info_struct m;
+  static struct common_info_struct c;
+  memset(&m, 0, sizeof(m)); memset(&c, 0, sizeof(c));
+  c.devSlotSize = 5380000000ul;
+  m.path = argv[1];
+  SparseFrame_initialize_matrix(&m);
+  if (SparseFrame_read_matrix(&m)) return 3;
+  if (SparseFrame_analyze(&c, &m)) return 4;
+  FILE *f = fopen(argv[2], "wb");
+  long h[4] = {m.nrow, m.nsuper, m.isize, m.nzmax};
+  fwrite(h, sizeof(long), 4, f);
+  fwrite(m.Perm, sizeof(long), m.nrow, f);
+  fwrite(m.Post, sizeof(long), m.nrow, f);
+  fwrite(m.Super, sizeof(long), m.nsuper + 1, f);
+  fwrite(m.Lsip, sizeof(long), m.nsuper + 1, f);
+  fwrite(m.Lsi, sizeof(long), m.isize, f);
+  fwrite(m.Li, sizeof(long), m.nzmax, f);
+  fwrite(m.Lx, sizeof(double), m.nzmax, f);
+  fclose(f);
+  return 0; }
+"""
+
+
+def test_ordering_cache_reproduces_the_analysis(tmp_path):
+    """SF_ORDER_CACHE: the second analysis of a pattern skips METIS and must leave a bit-identical matrix_info; a damaged
+    cache file is ignored."""
+    src = tmp_path / "probe.c"
+    src.write_text(ANALYZE_PROBE)
+    exe = tmp_path / "probe"
+    lib = os.path.join(PKG, "LU", "Lib")
+    subprocess.check_call(["gcc", "-fopenmp", "-I" + os.path.join(PKG, "LU", "Include"), str(src), "-o", str(exe),
+                           "-L" + lib, "-lSparseFrame", "-Wl,-rpath," + lib])
+    n, r, c, x, sym = sf.matrices.generate("cd3d", 14)
+    mtx = tmp_path / "a.mtx"
+    sf.matrices.write_matrix_market(str(mtx), n, r, c, x, sym)
+    cache = tmp_path / "cache"
+    cache.mkdir()
+
+    def run(tag, env_extra):
+        out = tmp_path / (tag + ".dump")
+        env = dict(os.environ, **env_extra)
+        subprocess.run([str(exe), str(mtx), str(out)], env=env, check=True, capture_output=True)
+        return out.read_bytes()
+
+    plain = run("plain", {})
+    first = run("first", {"SF_ORDER_CACHE": str(cache)})
+    files = list(cache.iterdir())
+    assert len(files) == 1 and files[0].stat().st_size == 8 * n
+    second = run("second", {"SF_ORDER_CACHE": str(cache)})
+    assert plain == first == second
+    # the cached ordering is what the engine's own analysis calls "Order"
+    S = sf.analyze(sf.compress(n, r, c, x, sym), "lu")
+    assert np.array_equal(np.fromfile(files[0], dtype=np.int64), S.array("Order"))
+    files[0].write_bytes(b"\0" * (8 * n))          # not a permutation: must fall back to METIS and repair the file
+    assert run("third", {"SF_ORDER_CACHE": str(cache)}) == plain
+    assert np.array_equal(np.fromfile(files[0], dtype=np.int64), S.array("Order"))
+
+
+def test_analyze_ordered_accepts_any_permutation():
+    """A caller-supplied ordering (here: identity and a reversal) gives a valid structure whose CPU-interpreted
+    factorization has a tiny backward error; a non-permutation is refused."""
+    n, r, c, x, sym = sf.matrices.generate("lap2d", 12)
+    A = sf.compress(n, r, c, x, sym)
+    for order in (np.arange(n), np.arange(n)[::-1].copy()):
+        S = sf.analyze(A, "cholesky", order=order)
+        assert S.double("t_order") == 0.0
+        perm = S.array("Perm")
+        assert np.array_equal(np.sort(perm), np.arange(n))
+        assert S.array("Super")[-1] == n and S.int("xsize") == S.array("Lsxp")[-1]
+    with pytest.raises(RuntimeError, match="not a permutation"):
+        sf.analyze(A, "cholesky", order=np.zeros(n, dtype=np.int64))
