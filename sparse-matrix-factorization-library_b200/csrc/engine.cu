@@ -320,6 +320,7 @@ int sfb200_plan_create_part(const sfb200_symbolic *s, int device, int rank, int 
     if (const char *e = getenv("SFB200_DIST_MIN_M")) prm.dist_scatter_min_m = atoi(e);
     if (const char *e = getenv("SFB200_DIST_PANEL_MIN")) prm.dist_panel_min_cols = atoi(e);
     if (const char *e = getenv("SFB200_GEMM_WS")) prm.use_ws = atoi(e);
+    if (const char *e = getenv("SFB200_WS_KMAJOR")) prm.ws_kmajor = atoi(e);
     if (const char *e = getenv("SFB200_LOOKAHEAD")) prm.lookahead = atoi(e);
     if (const char *e = getenv("SFB200_LEAF_LOOKAHEAD")) prm.leaf_lookahead = atoi(e);
     const int rc = build_plan(s->S, prm, p->H, rank, world);

@@ -707,7 +707,12 @@ namespace ws {
 #define SFB200_WS_STAGES 4
 #endif
 constexpr int BM = 128, BN = 128, BK = 16, STAGES = SFB200_WS_STAGES, SA = 132;
-constexpr int STAGE_DOUBLES = 2 * BK * SA;
+// k-major B operands (LU: the U11 row blocks, element (k, n) at B[k + n * ldb]) are staged column by column: BK
+// contiguous doubles (one 128-byte bulk copy) per column n, at a column stride of SBK doubles -- the fragment loads of a
+// half-warp (4 columns x 4 k) then fall in 16 distinct 8-byte banks (20 * 8 B = 160 B: column c starts at bank 4c mod 16).
+constexpr int SBK = 20;
+constexpr int B_STAGE_DOUBLES = (BN * SBK > BK * SA) ? BN * SBK : BK * SA;
+constexpr int STAGE_DOUBLES = BK * SA + B_STAGE_DOUBLES;
 constexpr int SMEM_BYTES = STAGES * STAGE_DOUBLES * 8 + 2 * STAGES * 8 + 64;
 constexpr int NT = 384;
 
@@ -803,6 +808,31 @@ __global__ void __launch_bounds__(ws::NT, 1) k_gemm_ws(PlanDev P, const GemmOp *
             if (ti.skip) continue;
             const GemmOp &op = ti.op;
             const int mrem = min(BM, op.M - ti.row0), nrem = min(BN, op.N - ti.col0);
+            const int KT = (op.K + BK - 1) / BK;
+            if (op.flags & G_B_KMAJOR) {
+                // A: lanes 0-15 stage one k-row each (as below); B: every lane stages the columns lane, lane + 32, ... of the
+                // tile, BK contiguous doubles each.  The plan routes a k-major op here only if b_off and ldb are even (16-byte
+                // aligned sources) and K is a multiple of BK (plan.cpp: emit_gemm).
+                const int sha = (int)((op.a_off + ti.row0) & 1);
+                const unsigned bytes_a = (unsigned)(((mrem + sha + 1) & ~1) * 8);
+                const double *srcA = P.X + op.a_off + ti.row0 - sha + (int64_t)(lane & 15) * op.lda;
+                const double *srcB = P.X + op.b_off + (int64_t)(ti.col0 + lane) * op.ldb;
+                const int64_t stepA = (int64_t)BK * op.lda, colB = (int64_t)32 * op.ldb;
+                for (int kt = 0; kt < KT; ++kt) {
+                    mbar_wait(empty + stage, phase ^ 1);
+                    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");      // see below
+                    double *As = smem + stage * STAGE_DOUBLES, *Bs = As + BK * SA;
+                    if (lane < 16) bulk_g2s(As + lane * SA, srcA, bytes_a, full + stage);
+                    const double *sb = srcB;
+                    for (int c = lane; c < nrem; c += 32, sb += colB) bulk_g2s(Bs + c * SBK, sb, BK * 8, full + stage);
+                    srcA += stepA;
+                    srcB += BK;
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_expect_tx(full + stage, (unsigned)BK * bytes_a + (unsigned)nrem * BK * 8);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+                continue;
+            }
             const double *Ag = P.X + op.a_off + ti.row0, *Bg = P.X + op.b_off + ti.col0;
             const int sha = (int)((op.a_off + ti.row0) & 1), shb = (int)((op.b_off + ti.col0) & 1);
             const unsigned bytes_a = (unsigned)(((mrem + sha + 1) & ~1) * 8), bytes_b = (unsigned)(((nrem + shb + 1) & ~1) * 8);
@@ -812,7 +842,6 @@ __global__ void __launch_bounds__(ws::NT, 1) k_gemm_ws(PlanDev P, const GemmOp *
             const double *src = (is_b ? Bg - shb + (int64_t)k * op.ldb : Ag - sha + (int64_t)k * op.lda);
             const int64_t step = (int64_t)BK * (is_b ? op.ldb : op.lda);
             const unsigned bytes = is_b ? bytes_b : bytes_a;
-            const int KT = (op.K + BK - 1) / BK;
             for (int kt = 0; kt < KT; ++kt) {
                 mbar_wait(empty + stage, phase ^ 1);
                 // The stage was last read through the generic proxy (the consumers' shared-memory loads, this warp's zero
@@ -857,25 +886,49 @@ __global__ void __launch_bounds__(ws::NT, 1) k_gemm_ws(PlanDev P, const GemmOp *
             for (int j = 0; j < FN; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
         const int KT = (op.K + BK - 1) / BK;
-        for (int kt = 0; kt < KT; ++kt) {
-            mbar_wait(full + stage, phase);
-            const double *As = smem + stage * STAGE_DOUBLES + sha + wm0 + g;
-            const double *Bs = smem + stage * STAGE_DOUBLES + BK * SA + shb + wn0 + g;
+        if (op.flags & G_B_KMAJOR) {
+            // B staged [column][k] with a column stride of SBK (see the producer): no alignment shift on this path
+            for (int kt = 0; kt < KT; ++kt) {
+                mbar_wait(full + stage, phase);
+                const double *As = smem + stage * STAGE_DOUBLES + sha + wm0 + g;
+                const double *Bs = smem + stage * STAGE_DOUBLES + BK * SA + (wn0 + g) * SBK + t4;
 #pragma unroll
-            for (int ks = 0; ks < BK; ks += 4) {
-                double af[FM], bf[FN];
+                for (int ks = 0; ks < BK; ks += 4) {
+                    double af[FM], bf[FN];
 #pragma unroll
-                for (int i = 0; i < FM; ++i) af[i] = As[(ks + t4) * SA + 8 * i];
+                    for (int i = 0; i < FM; ++i) af[i] = As[(ks + t4) * SA + 8 * i];
 #pragma unroll
-                for (int j = 0; j < FN; ++j) bf[j] = Bs[(ks + t4) * SA + 8 * j];
+                    for (int j = 0; j < FN; ++j) bf[j] = Bs[8 * j * SBK + ks];
 #pragma unroll
-                for (int i = 0; i < FM; ++i)
+                    for (int i = 0; i < FM; ++i)
 #pragma unroll
-                    for (int j = 0; j < FN; ++j) dmma(acc[i][j][0], acc[i][j][1], bf[j], af[i]);
+                        for (int j = 0; j < FN; ++j) dmma(acc[i][j][0], acc[i][j][1], bf[j], af[i]);
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(empty + stage);
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(empty + stage);
-            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        } else {
+            for (int kt = 0; kt < KT; ++kt) {
+                mbar_wait(full + stage, phase);
+                const double *As = smem + stage * STAGE_DOUBLES + sha + wm0 + g;
+                const double *Bs = smem + stage * STAGE_DOUBLES + BK * SA + shb + wn0 + g;
+#pragma unroll
+                for (int ks = 0; ks < BK; ks += 4) {
+                    double af[FM], bf[FN];
+#pragma unroll
+                    for (int i = 0; i < FM; ++i) af[i] = As[(ks + t4) * SA + 8 * i];
+#pragma unroll
+                    for (int j = 0; j < FN; ++j) bf[j] = Bs[(ks + t4) * SA + 8 * j];
+#pragma unroll
+                    for (int i = 0; i < FM; ++i)
+#pragma unroll
+                        for (int j = 0; j < FN; ++j) dmma(acc[i][j][0], acc[i][j][1], bf[j], af[i]);
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(empty + stage);
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
         }
 
         // ---- epilogue: thread holds C[row0 + wm0 + 8i + 2*t4 + {0,1}][col0 + wn0 + 8j + g] ---------------------

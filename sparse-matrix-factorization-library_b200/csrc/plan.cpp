@@ -379,7 +379,10 @@ int build_plan(const Symbolic &S, const PlanParams &prm, HostPlan &P, int rank, 
                 i64 tiles = 0;
                 for (GemmOp g : ops) {
                     const bool big = g.M >= prm.gemm128_min_m && g.N > 64;
-                    const bool ws_ok = prm.use_ws && !(g.flags & G_B_KMAJOR);
+                    // k-major B: one 128-byte bulk copy per column and k-step (kernels.cu: k_gemm_ws) needs aligned
+                    // sources and whole k-steps
+                    const bool kmajor_ok = prm.ws_kmajor && (g.b_off & 1) == 0 && (g.ldb & 1) == 0 && g.K % 16 == 0;
+                    const bool ws_ok = prm.use_ws && (!(g.flags & G_B_KMAJOR) || kmajor_ok);
                     const int want = !big ? 2 : (ws_ok ? 0 : 1);
                     if (want != pass) continue;
                     g.tile0 = (int32_t)tiles;

@@ -22,6 +22,8 @@ struct PlanParams {
     int leaf_lookahead = 1;      // diagonal block j+1 applies leaf j's update to itself and is factorized next to that update
     int lookahead = 1;           // split the top-level trailing updates (see LaunchFlags) -- needs outer2 > 0
     int use_ws = 1;              // big GEMM ops with a row-major B go to the warp-specialized bulk-copy kernel
+    int ws_kmajor = 0;           // ... and so do LU's k-major B ops (U11 row blocks, staged column by column) when their
+                                 // sources are 16-byte aligned and K is a multiple of 16
     int dist_scatter_min_m = 512;// multi-GPU: Schur updates of shared fronts with at least this many rows are split over the group
     int dist_panel_min_cols = 2048; // multi-GPU: shared Cholesky fronts at least this wide are factorized by the whole group
                                  // (1-D block-cyclic over `outer`-wide block columns, one broadcast per block column)

@@ -18,7 +18,8 @@ pytestmark = pytest.mark.gpu
 
 ENTRY_TOL = 1e-10
 BACKWARD_TOL = 1e-12
-ENV_KEYS = ("SFB200_NB", "SFB200_OUTER", "SFB200_SMALL_A", "SFB200_SMALL_B", "SFB200_GEMM128_MIN")
+ENV_KEYS = ("SFB200_NB", "SFB200_OUTER", "SFB200_OUTER2", "SFB200_SMALL_A", "SFB200_SMALL_B", "SFB200_GEMM128_MIN",
+            "SFB200_WS_KMAJOR")
 
 
 @pytest.fixture(autouse=True)
@@ -272,6 +273,28 @@ def test_lookahead_split_with_narrow_blocking(gen, g, kind):
     assert bad == 0
     for _ in range(3):                     # a race would not need to show on the first run
         compare(kind, st, ref_lsx, plan.factorize(S.array("Lx"), ux))
+    plan.close()
+
+
+@pytest.mark.parametrize("gen,g,kind", [("cd3d", 30, "lu"), ("lap3d", 30, "lu")])
+@pytest.mark.parametrize("env", [dict(SFB200_WS_KMAJOR=1), dict(SFB200_WS_KMAJOR=1, SFB200_OUTER=128, SFB200_OUTER2=256),
+                                 dict(SFB200_WS_KMAJOR=0)], ids=["kmajor", "kmajor-narrow", "classic"])
+def test_lu_kmajor_updates_on_the_warp_specialized_kernel(gen, g, kind, env):
+    """LU's in-panel updates C -= L21 * U12 read U12 k-major (the U11 row blocks).  With SFB200_WS_KMAJOR=1 the plan sends
+    them to k_gemm_ws (one 128-byte bulk copy per column and k-step, [column][k] shared layout) instead of the classic
+    cp.async kernel: same factor, to the parity tolerance, on fronts of 900-1300 columns."""
+    A, _ = build_matrix(gen, g)
+    S = sf.analyze(A, kind)
+    st = oracle_structure(S)
+    ux = S.array("Ux") if "Up" in st else None
+    ref_lsx, bad = sforacle.factorize(kind, st, S.array("Lx"), ux)
+    assert bad == 0
+    plan, lsx = gpu_factor(S, env)
+    compare(kind, st, ref_lsx, lsx)
+    for _ in range(2):
+        compare(kind, st, ref_lsx, plan.factorize(S.array("Lx"), ux))
+    _, backward = sforacle.validate(kind, st, S.array("Lx"), lsx, ux)
+    assert backward <= BACKWARD_TOL
     plan.close()
 
 
