@@ -71,6 +71,7 @@ void trsm(double *X, const TrsmOp &t) {
             }
             if (!(t.flags & T_UNIT)) acc /= D[j + (i64)j * t.ldt];
             b[(i64)j * t.estride] = acc;
+            if (t.flags & T_COPY_T) X[t.w_off + v + (i64)j * t.ldw] = acc;
         }
     }
 }
@@ -273,6 +274,7 @@ long sfcheck_int(void *hv, const char *name) {
     if (k == "nlarge") return P.nlarge;
     if (k == "relmap") return (long)P.relmap.size();
     if (k == "xsize_pad") return P.xsize_pad;
+    if (k == "xsize_work") return P.xsize_pad + P.wsize;       // image + this rank's scratch (LU: U11^T copies)
     if (k == "xsize") return P.xsize;
     if (k == "nphases") return (long)P.phases.size();
     if (k == "nsegments") return (long)P.segments.size();
@@ -301,7 +303,7 @@ void sfcheck_owner(void *hv, int *owner) {
     const HostPlan &P = ((CheckHandle *)hv)->P;
     for (i64 s = 0; s < P.nsuper; ++s) owner[s] = P.owner[s];
 }
-/* X: xsize_pad doubles, zeroed by the caller */
+/* X: xsize_pad + wsize doubles ("xsize_work"), zeroed by the caller */
 void sfcheck_begin(void *hv, double *X) { assemble(*(CheckHandle *)hv, X); }
 long sfcheck_run_segment(void *hv, int k, double *X) {
     const HostPlan &P = ((CheckHandle *)hv)->P;
@@ -371,7 +373,7 @@ long sfcheck_factor_solve(void *hv, double *b) {
     CheckHandle &h = *(CheckHandle *)hv;
     const HostPlan &P = h.P;
     if (P.world != 1) return -1;
-    std::vector<double> X(P.xsize_pad, 0.0);
+    std::vector<double> X(P.xsize_pad + P.wsize, 0.0);
     assemble(h, X.data());
     const long bad = run_launches(P, X.data(), 0, (int)P.launches.size());
     for (const SolveLaunch &L : P.solve_fwd) for (int k = 0; k < L.count; ++k) solve_task(P, P.solve_tasks[L.first + k], L.kind, X.data(), b);
@@ -393,7 +395,7 @@ long sfcheck_factorize(int kind, int is_symmetric, long n, const long *Cp, const
         stats[4] = (long)P.relmap.size(); stats[5] = P.xsize_pad; stats[6] = P.xsize;
     }
     if (!Lsx_out || out_len < P.xsize) { delete h; return 0; }     // sizing call
-    std::vector<double> X(P.xsize_pad, 0.0);
+    std::vector<double> X(P.xsize_pad + P.wsize, 0.0);
     assemble(*h, X.data());
     int last_level = -1;
     for (const Launch &L : P.launches) {
@@ -418,7 +420,8 @@ long sfcheck_factorize_partitioned(int kind, int is_symmetric, long n, const lon
         if (!H[r]) return -1;
     }
     const i64 xp = H[0]->P.xsize_pad;
-    std::vector<std::vector<double>> X(world, std::vector<double>(xp, 0.0));
+    std::vector<std::vector<double>> X(world);
+    for (int r = 0; r < world; ++r) X[r].assign(xp + H[r]->P.wsize, 0.0);   // image, then the rank's own scratch
     for (int r = 0; r < world; ++r) { assemble(*H[r], X[r].data()); if (balance) balance[r] = H[r]->P.local_flops; }
     long bad = 0, ncoll[3] = {0, 0, 0};
     const size_t nseg = H[0]->P.segments.size();

@@ -148,8 +148,8 @@ class CheckBackend:
         if not self.h:
             raise RuntimeError("sfcheck_open failed")
         self.rank, self.world = rank, world
-        self.X = np.zeros(self.int("xsize_pad"))
-        self.image = torch.from_numpy(self.X)          # shares memory with X
+        self.X = np.zeros(self.int("xsize_work"))      # factor image, then this rank's scratch area
+        self.image = torch.from_numpy(self.X)[:self.int("xsize_pad")]          # shares memory with X
         self.bad = 0
 
         def info(fn, k, n):

@@ -321,6 +321,7 @@ int sfb200_plan_create_part(const sfb200_symbolic *s, int device, int rank, int 
     if (const char *e = getenv("SFB200_DIST_PANEL_MIN")) prm.dist_panel_min_cols = atoi(e);
     if (const char *e = getenv("SFB200_GEMM_WS")) prm.use_ws = atoi(e);
     if (const char *e = getenv("SFB200_WS_KMAJOR")) prm.ws_kmajor = atoi(e);
+    if (const char *e = getenv("SFB200_LU_UT_COPY")) prm.lu_ut_copy = atoi(e);
     if (const char *e = getenv("SFB200_LOOKAHEAD")) prm.lookahead = atoi(e);
     if (const char *e = getenv("SFB200_LEAF_LOOKAHEAD")) prm.leaf_lookahead = atoi(e);
     const int rc = build_plan(s->S, prm, p->H, rank, world);
@@ -365,7 +366,14 @@ int sfb200_plan_create_part(const sfb200_symbolic *s, int device, int rank, int 
         p->device_bytes += bytes;
         return SFB200_OK;
     };
-    if ((err = dmalloc((void **)&p->d_X, sizeof(double) * (size_t)H.xsize_pad))) return fail(err);
+    // factor image, then the U11^T scratch of the large LU fronts (never zeroed again: always written before it is read;
+    // zeroed once so that the rows a tile reads beyond an operand's extent are finite), then a tile's worth of slack for
+    // those over-reads at the very end
+    if ((err = dmalloc((void **)&p->d_X, sizeof(double) * (size_t)(H.xsize_pad + H.wsize + 256)))) return fail(err);
+    if (cudaMemsetAsync(p->d_X + H.xsize_pad, 0, sizeof(double) * (size_t)(H.wsize + 256), p->stream) != cudaSuccess) {
+        set_error("cudaMemsetAsync of the scratch area failed");
+        return fail(SFB200_ERR_CUDA);
+    }
     if ((err = dmalloc((void **)&p->d_lx, sizeof(double) * (size_t)H.nnz))) return fail(err);
     if (H.split && (err = dmalloc((void **)&p->d_ux, sizeof(double) * (size_t)H.unnz))) return fail(err);
     if ((err = dmalloc((void **)&p->d_status, sizeof(int)))) return fail(err);
@@ -474,6 +482,7 @@ int64_t sfb200_plan_int(const sfb200_plan *p, const char *name) {
     if (k == "nlarge") return H.nlarge;
     if (k == "relmap_entries") return (int64_t)H.relmap.size();
     if (k == "xsize_padded") return H.xsize_pad;
+    if (k == "scratch_elems") return H.wsize;
     if (k == "xsize") return H.xsize;
     if (k == "nnz") return H.nnz;
     if (k == "unnz") return H.unnz;

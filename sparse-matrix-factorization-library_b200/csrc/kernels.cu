@@ -389,11 +389,18 @@ __global__ void __launch_bounds__(64) k_trsm(PlanDev P, const TrsmOp *__restrict
         }
     }
     double *bout = B;
+    // T_COPY_T: second, transposed copy (consecutive vectors -> consecutive addresses: coalesced)
+    const bool copy_t = (op.flags & T_COPY_T) != 0;
+    double *wout = P.X + (copy_t ? op.w_off + v : 0);
 #pragma unroll
     for (int j = 0; j < 64; ++j) {
         const double x = b[j] * rinv[j];
         if (j < nb) *bout = x;      // x_j is final: store now so that its register dies here
         bout += op.estride;
+        if (copy_t) {
+            if (j < nb) *wout = x;
+            wout += op.ldw;
+        }
         const double nx = -x;
         // chunks of 16 columns with a compiler barrier in between: otherwise every shared-memory load of the
         // column (up to 63 doubles) is hoisted in front of the FMAs and the vector no longer fits in registers

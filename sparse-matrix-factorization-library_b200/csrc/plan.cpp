@@ -44,6 +44,8 @@ struct PanelEmitter {
 
     bool lookahead = false;
     bool leaf_lookahead = false;
+    i64 woff = -1;                // LU: offset of this front's U11^T scratch (ldw x nscol, element U11[k, j] at woff + j + k * ldw)
+    int ldw = 0;
 
     PanelEmitter(const SnodeDev &s, bool is_lu, const std::vector<int> &w, std::map<int, SlotOps> &sl)
         : sn(s), lu(is_lu), widths(w), slots(sl) {
@@ -52,18 +54,28 @@ struct PanelEmitter {
         for (size_t d = 1; d < widths.size(); ++d) nslots[d] = (widths[d] / widths[d - 1]) * (nslots[d - 1] + 1);
     }
 
-    void gemm(int slot, i64 a, i64 b, i64 c, int M, int N, int K, int flags, bool side = false, int skip_head = 0) {
+    // B = U11[k0 .. k0 + K, j0 .. j0 + N): k-major in the panel, row-major in the transposed scratch copy
+    void gemm_u(int slot, i64 a, int k0, int j0, i64 c, int M, int N, int K, bool side = false, int skip_head = 0) {
+        if (woff < 0) {
+            gemm(slot, a, sn.xoff + k0 + (i64)j0 * sn.ld, c, M, N, K, G_B_KMAJOR, side, skip_head);
+        } else {
+            gemm(slot, a, woff + j0 + (i64)k0 * ldw, c, M, N, K, 0, side, skip_head, ldw);
+        }
+    }
+    void gemm(int slot, i64 a, i64 b, i64 c, int M, int N, int K, int flags, bool side = false, int skip_head = 0, int ldb = 0) {
         if (M <= 0 || N <= 0 || K <= 0) return;
         GemmOp g{};
         g.a_off = a; g.b_off = b; g.c_off = c; g.lda = g.ldb = g.ldc = sn.ld;
+        if (ldb > 0) g.ldb = ldb;
         g.M = M; g.N = N; g.K = K; g.flags = flags; g.tile_mod = 1; g.tile_rem = 0;
         if (skip_head > 0) { g.flags |= G_SKIP_HEAD; g.meta = skip_head; slots[slot].feeds_diag_ahead = true; }
         (side ? slots[slot].side : slots[slot].gemm).push_back(g);
     }
-    void trsm(int slot, i64 d, int w, i64 b_off, int nvec, int es, int vs, int flags) {
+    void trsm(int slot, i64 d, int w, i64 b_off, int nvec, int es, int vs, int flags, i64 w_off = -1) {
         if (nvec <= 0) return;
         TrsmOp t{};
         t.t_off = d; t.b_off = b_off; t.ldt = sn.ld; t.nb = w; t.nvec = nvec; t.estride = es; t.vstride = vs; t.flags = flags;
+        if (w_off >= 0) { t.flags |= T_COPY_T; t.w_off = w_off; t.ldw = ldw; }
         slots[slot].trsm.push_back(t);
     }
 
@@ -86,7 +98,8 @@ struct PanelEmitter {
         } else {
             trsm(slot + 1, d, w, x + j1 + (i64)j0 * ld, R - j1, sn.ld, 1, T_TRANS);     // L below the block: X U11 = B
             trsm(slot + 1, d, w, x + R + (i64)j0 * ld, m, sn.ld, 1, T_UNIT);           // U12^T rows:        X L11^T = B
-            trsm(slot + 1, d, w, x + j0 + (i64)j1 * ld, n - j1, 1, sn.ld, T_UNIT);     // U11 row block, ALL later columns
+            // U11 row block, ALL later columns (vector v = column j1 + v); second copy into the U11^T scratch
+            trsm(slot + 1, d, w, x + j0 + (i64)j1 * ld, n - j1, 1, sn.ld, T_UNIT, woff < 0 ? -1 : woff + j1 + (i64)j0 * ldw);
         }
     }
 
@@ -119,17 +132,17 @@ struct PanelEmitter {
                 if (split)
                     gemm(gs, x + s1 + (i64)b0 * ld, x + s1 + (i64)b0 * ld, x + s1 + (i64)s1 * ld, R - s1, c1 - s1, K, G_LOWER, true);
             } else {
-                gemm(gs, x + b1 + (i64)b0 * ld, x + b0 + (i64)b1 * ld, x + b1 + (i64)b1 * ld, R - b1, s1 - b1, K, G_B_KMAJOR, false, head);
+                gemm_u(gs, x + b1 + (i64)b0 * ld, b0, b1, x + b1 + (i64)b1 * ld, R - b1, s1 - b1, K, false, head);
                 gemm(gs, x + R + (i64)b0 * ld, x + b1 + (i64)b0 * ld, x + R + (i64)b1 * ld, m, s1 - b1, K, 0);
                 if (split) {
                     // LU: the next block column's factorization also works on its ROW block right of the diagonal (the U11 row
                     // solves and the row-block updates reach every later column), so rows [b1,s1) of the rest stay on the
                     // main stream; the side stream gets rows >= s1 only
-                    gemm(gs, x + b1 + (i64)b0 * ld, x + b0 + (i64)s1 * ld, x + b1 + (i64)s1 * ld, s1 - b1, c1 - s1, K, G_B_KMAJOR);
-                    gemm(gs, x + s1 + (i64)b0 * ld, x + b0 + (i64)s1 * ld, x + s1 + (i64)s1 * ld, R - s1, c1 - s1, K, G_B_KMAJOR, true);
+                    gemm_u(gs, x + b1 + (i64)b0 * ld, b0, s1, x + b1 + (i64)s1 * ld, s1 - b1, c1 - s1, K);
+                    gemm_u(gs, x + s1 + (i64)b0 * ld, b0, s1, x + s1 + (i64)s1 * ld, R - s1, c1 - s1, K, true);
                     gemm(gs, x + R + (i64)b0 * ld, x + s1 + (i64)b0 * ld, x + R + (i64)s1 * ld, m, c1 - s1, K, 0, true);
                 }
-                gemm(gs, x + b1 + (i64)b0 * ld, x + b0 + (i64)c1 * ld, x + b1 + (i64)c1 * ld, c1 - b1, n - c1, K, G_B_KMAJOR);
+                gemm_u(gs, x + b1 + (i64)b0 * ld, b0, c1, x + b1 + (i64)c1 * ld, c1 - b1, n - c1, K);
             }
         }
     }
@@ -305,6 +318,7 @@ int build_plan(const Symbolic &S, const PlanParams &prm, HostPlan &P, int rank, 
     P.asm_dst_l.assign(P.nnz, 0);
     P.asm_dst_u.assign(P.unnz, 0);
     std::vector<int32_t> pos(n, -1);
+    std::vector<i64> dup_stamp(n, 0);
     for (i64 t = 0; t < ns; ++t) {
         const SnodeDev &st = P.snode[t];
         const i64 *trow = S.Lsi.data() + st.lsip;
@@ -326,18 +340,24 @@ int build_plan(const Symbolic &S, const PlanParams &prm, HostPlan &P, int rank, 
                 if (lu) for (i64 p = Usrc.ptr[j]; p < Usrc.ptr[j + 1]; ++p) P.asm_dst_u[p] = -1;
                 continue;
             }
-            for (i64 p = S.L.ptr[j]; p < S.L.ptr[j + 1]; ++p) {
+            // Duplicate entries (the reader sums nothing, CH.c:526-587): loadA assigns in p order, so the LAST copy of an
+            // (i, j) pair is the one that stays (CH.c:2018, LU.c:2498/2513).  The assembly kernel scatters all entries at
+            // once, so the earlier copies are switched off here: walk each list backwards, first visit wins.
+            for (i64 p = S.L.ptr[j + 1] - 1; p >= S.L.ptr[j]; --p) {
                 const i64 i = S.L.idx[p];
                 if (pos[i] < 0) return 4;
                 // LU takes the diagonal from U (LU.c:2496): the L copy of a diagonal entry is skipped
-                P.asm_dst_l[p] = (lu && i == j) ? -1 : st.xoff + cj * st.ld + pos[i];
+                P.asm_dst_l[p] = ((lu && i == j) || dup_stamp[i] == 2 * j + 1) ? -1 : st.xoff + cj * st.ld + pos[i];
+                dup_stamp[i] = 2 * j + 1;
             }
             if (lu) {
-                for (i64 p = Usrc.ptr[j]; p < Usrc.ptr[j + 1]; ++p) {
+                for (i64 p = Usrc.ptr[j + 1] - 1; p >= Usrc.ptr[j]; --p) {
                     const i64 i = Usrc.idx[p];   // column index of an entry of row j of U
                     if (pos[i] < 0) return 4;
-                    P.asm_dst_u[p] = pos[i] < st.nscol ? st.xoff + (i64)pos[i] * st.ld + cj
-                                                       : st.xoff + cj * st.ld + (st.nsrow - st.nscol) + pos[i];
+                    P.asm_dst_u[p] = dup_stamp[i] == 2 * j + 2 ? -1
+                                     : pos[i] < st.nscol ? st.xoff + (i64)pos[i] * st.ld + cj
+                                                         : st.xoff + cj * st.ld + (st.nsrow - st.nscol) + pos[i];
+                    dup_stamp[i] = 2 * j + 2;
                 }
             }
         }
@@ -511,7 +531,17 @@ int build_plan(const Symbolic &S, const PlanParams &prm, HostPlan &P, int rank, 
                 for (int k = 0; k < 4; ++k) if (pb <= small_limits[k]) { c = k; break; }
             if (c >= 0 && !dist_update) { cls[c].push_back(s); ++P.nsmall; continue; }
             ++P.nlarge;
-            { PanelEmitter pe(d, lu, widths, slots); pe.lookahead = prm.lookahead != 0; pe.leaf_lookahead = prm.leaf_lookahead != 0; pe.run(); }
+            {
+                PanelEmitter pe(d, lu, widths, slots);
+                pe.lookahead = prm.lookahead != 0;
+                pe.leaf_lookahead = prm.leaf_lookahead != 0;
+                if (lu && prm.lu_ut_copy && d.nscol > prm.nb) {      // a front with more than one leaf has in-panel updates
+                    pe.ldw = (int)round_up(d.nscol, 2);
+                    pe.woff = P.xsize_pad + P.wsize;
+                    P.wsize += (i64)pe.ldw * d.nscol;
+                }
+                pe.run();
+            }
             if (!dist_update) scatter_ops(scatter, 1, 0);
         }
         for (int c = 0; c < 4; ++c) {

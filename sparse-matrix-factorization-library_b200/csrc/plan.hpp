@@ -22,6 +22,8 @@ struct PlanParams {
     int leaf_lookahead = 1;      // diagonal block j+1 applies leaf j's update to itself and is factorized next to that update
     int lookahead = 1;           // split the top-level trailing updates (see LaunchFlags) -- needs outer2 > 0
     int use_ws = 1;              // big GEMM ops with a row-major B go to the warp-specialized bulk-copy kernel
+    int lu_ut_copy = 1;          // LU: large fronts keep U11^T in a scratch area behind the factor (written by the row-block
+                                 // solves), the in-panel updates read it as a row-major B operand -> warp-specialized kernel
     int ws_kmajor = 0;           // ... and so do LU's k-major B ops (U11 row blocks, staged column by column) when their
                                  // sources are 16-byte aligned and K is a multiple of 16
     int dist_scatter_min_m = 512;// multi-GPU: Schur updates of shared fronts with at least this many rows are split over the group
@@ -34,6 +36,7 @@ struct HostPlan {
     bool split = false;          // LU on an unsymmetric matrix: separate U values
     PlanParams prm;
     i64 n = 0, nsuper = 0, nnz = 0, unnz = 0, isize = 0, xsize = 0, xsize_pad = 0;
+    i64 wsize = 0;               // scratch elements behind the padded factor (offsets xsize_pad .. xsize_pad + wsize): U11^T copies
     int nlevels = 0;
     i64 nsmall = 0, nlarge = 0;
 

@@ -47,6 +47,9 @@ struct GemmOp {
 enum TrsmFlags : int32_t {
     T_TRANS = 1 << 0,   // T[j,p] is read from the upper triangle: T[j,p] = D[p,j]      (LU: X U11 = B)
     T_UNIT  = 1 << 1,   // unit diagonal                                                (LU: X L11^T = B, L11 X = B)
+    T_COPY_T = 1 << 2,  // also store the solution transposed: element j of vector v at w_off + v + j * ldw
+                        // (LU: the U11 row blocks are kept a second time as U11^T, so that the in-panel updates
+                        // C -= L21 * U12 read their B operand row-major like every other GEMM of the schedule)
 };
 
 struct TrsmOp {
@@ -59,7 +62,8 @@ struct TrsmOp {
     int32_t vstride;    // stride between vectors
     int32_t flags;
     int32_t tile0;      // first CTA of this op inside its launch (one CTA per 64 vectors)
-    int32_t pad;
+    int32_t ldw;        // T_COPY_T: leading dimension of the transposed copy
+    int64_t w_off;      // T_COPY_T: element offset of (vector 0, element 0) of the transposed copy
 };
 
 // ---- diagonal block factorization --------------------------------------------------------------------------

@@ -19,7 +19,7 @@ pytestmark = pytest.mark.gpu
 ENTRY_TOL = 1e-10
 BACKWARD_TOL = 1e-12
 ENV_KEYS = ("SFB200_NB", "SFB200_OUTER", "SFB200_OUTER2", "SFB200_SMALL_A", "SFB200_SMALL_B", "SFB200_GEMM128_MIN",
-            "SFB200_WS_KMAJOR")
+            "SFB200_WS_KMAJOR", "SFB200_LU_UT_COPY")
 
 
 @pytest.fixture(autouse=True)
@@ -150,6 +150,26 @@ def test_edge_cases():
     plan.close()
 
 
+@pytest.mark.parametrize("gen,g,kind", [("lap2d", 40, "cholesky"), ("cd3d", 10, "lu"), ("lap3d", 9, "lu")])
+def test_duplicate_entries_last_one_wins(gen, g, kind):
+    """Several copies of one (i, j): the reference's loadA assigns in storage order, the last copy stays (CH.c:2018,
+    LU.c:2498/2513).  k_assemble scatters all entries concurrently, so the plan must have switched the earlier copies off;
+    every 3rd entry gets a wrong-valued earlier twin here and the factor must equal the oracle's, run after run."""
+    n, r, c, x, sym = sf.matrices.generate(gen, g)
+    twin = np.arange(0, len(r), 3)
+    r2, c2 = np.concatenate([r[twin], r]), np.concatenate([c[twin], c])
+    x2 = np.concatenate([x[twin] * 3.0 + 1.0, x])
+    S = sf.analyze(sf.compress(n, r2, c2, x2, sym), kind)
+    st = oracle_structure(S)
+    ux = S.array("Ux") if "Up" in st else None
+    ref_lsx, bad = sforacle.factorize(kind, st, S.array("Lx"), ux)
+    assert bad == 0
+    plan = sf.Plan(S)
+    for _ in range(3):
+        compare(kind, st, ref_lsx, plan.factorize(S.array("Lx"), ux))
+    plan.close()
+
+
 def test_indefinite_matrix_is_reported():
     n, r, c, x, sym = sf.matrices.generate("lap2d", 10)
     x = x.copy()
@@ -277,12 +297,13 @@ def test_lookahead_split_with_narrow_blocking(gen, g, kind):
 
 
 @pytest.mark.parametrize("gen,g,kind", [("cd3d", 30, "lu"), ("lap3d", 30, "lu")])
-@pytest.mark.parametrize("env", [dict(SFB200_WS_KMAJOR=1), dict(SFB200_WS_KMAJOR=1, SFB200_OUTER=128, SFB200_OUTER2=256),
-                                 dict(SFB200_WS_KMAJOR=0)], ids=["kmajor", "kmajor-narrow", "classic"])
-def test_lu_kmajor_updates_on_the_warp_specialized_kernel(gen, g, kind, env):
-    """LU's in-panel updates C -= L21 * U12 read U12 k-major (the U11 row blocks).  With SFB200_WS_KMAJOR=1 the plan sends
-    them to k_gemm_ws (one 128-byte bulk copy per column and k-step, [column][k] shared layout) instead of the classic
-    cp.async kernel: same factor, to the parity tolerance, on fronts of 900-1300 columns."""
+@pytest.mark.parametrize("env", [dict(), dict(SFB200_OUTER=128, SFB200_OUTER2=256), dict(SFB200_LU_UT_COPY=0, SFB200_WS_KMAJOR=1),
+                                 dict(SFB200_LU_UT_COPY=0)], ids=["ut-copy", "ut-copy-narrow", "kmajor-ws", "kmajor-classic"])
+def test_lu_in_panel_updates_operand_paths(gen, g, kind, env):
+    """LU's in-panel updates C -= L21 * U12 need rows of U11, which the panel stores k-major.  Default: the row-block solves
+    keep a transposed copy (U11^T) in a scratch area and the updates read it row-major on the warp-specialized kernel.
+    SFB200_LU_UT_COPY=0: k-major operand on the classic cp.async kernel, or (SFB200_WS_KMAJOR=1) staged column by column
+    with 128-byte bulk copies on the warp-specialized one.  Same factor on all three paths, fronts of 900-1450 columns."""
     A, _ = build_matrix(gen, g)
     S = sf.analyze(A, kind)
     st = oracle_structure(S)

@@ -107,3 +107,25 @@ def test_lookahead_side_launches_may_run_late(gen, g, kind, monkeypatch):
     assert bad == 0
     mask = sf.lower_trapezoid_mask(kind, st["Super"], st["Lsip"], st["Lsxp"], S.int("xsize"))
     assert sf.entrywise_rel_diff(ref[mask], out[mask]) <= 1e-10
+
+
+@pytest.mark.skipif(not (sfref.available("cholesky") and sfref.available("lu")), reason="compiled reference not built")
+@pytest.mark.parametrize("gen,g,kind", [("lap2d", 14, "cholesky"), ("cd3d", 7, "lu"), ("lap3d", 6, "lu")])
+def test_duplicate_entries_last_one_wins(gen, g, kind):
+    """The reader sums nothing (CH.c:526-587) and loadA assigns in storage order (CH.c:2018, LU.c:2498/2513): of several
+    copies of one (i, j) the last stays.  The engine's assembly is one parallel scatter, so the plan switches the earlier
+    copies off -- checked here against the compiled reference on a matrix where every 5th entry has a wrong-valued
+    earlier twin."""
+    n, r, c, x, sym = sf.matrices.generate(gen, g)
+    twin = np.arange(0, len(r), 5)
+    r2 = np.concatenate([r[twin], r])            # the wrong copies come first in file order
+    c2 = np.concatenate([c[twin], c])
+    x2 = np.concatenate([x[twin] * 3.0 + 1.0, x])
+    A = sf.compress(n, r2, c2, x2, sym)
+    ref = sfref.Reference(n, r2, c2, x2, sym, kind=kind).analyze().factorize()
+    out, bad, stats = sforacle.plan_check(kind, A.n, A.Cp, A.Ci, A.Cx, A.symmetric, sf.DEFAULT_DEVSLOT)
+    assert bad == 0
+    mask = sf.lower_trapezoid_mask(kind, ref.array("Super"), ref.array("Lsip"), ref.array("Lsxp"), ref.long("xsize"))
+    a, b = ref.array("Lsx")[mask], out[mask]
+    assert sf.entrywise_rel_diff(a, b) <= 1e-10
+    ref.close()
