@@ -128,7 +128,8 @@ def reference_arm(args, cfg, gen, g, kind):
         "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": workload_name(cfg, gen, g, kind), "sample": sample, "devSlotSize": sfref.DEFAULT_DEVSLOT},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "reference", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": min(cores, 16), "host_cores": cores, "kind": "reference",
+                         "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     })
 
@@ -150,7 +151,7 @@ def cpu_baseline(kind, gen):
         t = ref.double("factorizeTime")
         best = t if best is None else min(best, t)
     ref.close()
-    return {"value": flops / best / 1e9, "unit": UNIT, "cores": cores, "kind": "reference",
+    return {"value": flops / best / 1e9, "unit": UNIT, "cores": min(cores, 16), "host_cores": cores, "kind": "reference",
             "sample": "%s %d^%d (n=%d, %.3e flop), compiled reference CPU path (oracle/_ref), best of 2, %.2f s, "
                       "OpenBLAS threads=%d (reference caps at 16, parameter.h:12)" % (
                           sgen, sg, 2 if sgen == "lap2d" else 3, n, flops, best, min(cores, 16))}
