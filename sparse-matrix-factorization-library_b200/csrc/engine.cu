@@ -317,6 +317,7 @@ int sfb200_plan_create_part(const sfb200_symbolic *s, int device, int rank, int 
     if (const char *e = getenv("SFB200_SMALL_A")) prm.small_a_bytes = atoi(e);
     if (const char *e = getenv("SFB200_SMALL_B")) prm.small_b_bytes = atoi(e);
     if (const char *e = getenv("SFB200_GEMM128_MIN")) prm.gemm128_min_m = atoi(e);
+    if (const char *e = getenv("SFB200_GEMM128_MIN_K")) prm.gemm128_min_k = atoi(e);
     if (const char *e = getenv("SFB200_DIST_MIN_M")) prm.dist_scatter_min_m = atoi(e);
     if (const char *e = getenv("SFB200_DIST_PANEL_MIN")) prm.dist_panel_min_cols = atoi(e);
     if (const char *e = getenv("SFB200_GEMM_WS")) prm.use_ws = atoi(e);

@@ -1058,10 +1058,11 @@ __global__ void __launch_bounds__(64) k_solve_diag(SolveArgs A, const SolveTask 
         rd[tid] = unit ? 1.0 : 1.0 / T[tid * 65 + tid];              // own row: written by this thread just above
     }
     __syncthreads();
-    if (tid >= 32) return;
-    const int lane = tid;
+    // one warp per right-hand side: warp 0 takes the even ones, warp 1 the odd ones (a single right-hand side leaves
+    // warp 1 idle)
+    const int lane = tid & 31;
     const int64_t g0 = t.col0 + t.j0;
-    for (int q = 0; q < A.nrhs; ++q) {
+    for (int q = tid >> 5; q < A.nrhs; q += 2) {
         double *b = A.rhs + (int64_t)q * A.n + g0;
         double v0 = lane < w ? b[lane] : 0.0, v1 = lane + 32 < w ? b[lane + 32] : 0.0;
 #pragma unroll 8
@@ -1083,63 +1084,100 @@ __global__ void __launch_bounds__(64) k_solve_diag(SolveArgs A, const SolveTask 
     }
 }
 
+// The update kernels take QB right-hand sides per pass over the factor (QB = 1 for a single one, 4 otherwise): every
+// factor entry is loaded once per pass and used QB times from registers.
+
 // forward: b[rows] -= L[rows, block] x_block, one thread per panel row of the slab
+template <int QB>
 __global__ void __launch_bounds__(256) k_solve_upd_fwd(SolveArgs A, const SolveTask *__restrict__ tasks) {
-    __shared__ double xb[64];
+    __shared__ double xb[QB][64];
     const SolveTask t = tasks[blockIdx.x];
     const double *P = A.X + t.xoff + (int64_t)t.j0 * t.ld;
-    for (int q = 0; q < A.nrhs; ++q) {
-        double *b = A.rhs + (int64_t)q * A.n;
+    for (int q0 = 0; q0 < A.nrhs; q0 += QB) {
         __syncthreads();
-        if (threadIdx.x < t.w) xb[threadIdx.x] = b[t.col0 + t.j0 + threadIdx.x];
+        for (int idx = threadIdx.x; idx < QB * 64; idx += 256) {
+            const int qq = idx >> 6, jj = idx & 63;
+            xb[qq][jj] = (q0 + qq < A.nrhs && jj < t.w) ? A.rhs[(int64_t)(q0 + qq) * A.n + t.col0 + t.j0 + jj] : 0.0;
+        }
         __syncthreads();
         for (int i = t.r0 + threadIdx.x; i < t.r1; i += 256) {
-            double acc = 0.0;
+            double acc[QB];
+#pragma unroll
+            for (int qq = 0; qq < QB; ++qq) acc[qq] = 0.0;
 #pragma unroll 16
-            for (int jj = 0; jj < t.w; ++jj) acc = fma(P[(int64_t)jj * t.ld + i], xb[jj], acc);
-            atomicAdd(b + solve_gidx(t, A.lsi, i), -acc);
+            for (int jj = 0; jj < t.w; ++jj) {
+                const double l = P[(int64_t)jj * t.ld + i];
+#pragma unroll
+                for (int qq = 0; qq < QB; ++qq) acc[qq] = fma(l, xb[qq][jj], acc[qq]);
+            }
+            const int gi = solve_gidx(t, A.lsi, i);
+#pragma unroll
+            for (int qq = 0; qq < QB; ++qq)
+                if (q0 + qq < A.nrhs) atomicAdd(A.rhs + (int64_t)(q0 + qq) * A.n + gi, -acc[qq]);
         }
     }
 }
 
 // backward: b_block -= M[rows, block]^T x[rows] over a slab of rows; M = L (Cholesky) or the U12^T rows (LU).
 // Warp w handles block columns w, w+8, ...; lanes stride the rows (coalesced), shuffle reduction, one atomic per column.
+template <int QB>
 __global__ void __launch_bounds__(256) k_solve_upd_bwd(SolveArgs A, const SolveTask *__restrict__ tasks) {
-    __shared__ double xs[1024];
+    __shared__ double xs[QB][1024];
     const SolveTask t = tasks[blockIdx.x];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int rowshift = A.is_lu ? t.nsrow - t.nscol : 0;         // LU: off-diagonal row i lives at panel row i + (R - n)
     const double *P = A.X + t.xoff + (int64_t)t.j0 * t.ld + rowshift;
     const int cnt = t.r1 - t.r0;
-    for (int q = 0; q < A.nrhs; ++q) {
-        double *b = A.rhs + (int64_t)q * A.n;
+    for (int q0 = 0; q0 < A.nrhs; q0 += QB) {
         __syncthreads();
-        for (int k = threadIdx.x; k < cnt; k += 256) xs[k] = b[solve_gidx(t, A.lsi, t.r0 + k)];
+        for (int k = threadIdx.x; k < cnt; k += 256) {
+            const int gi = solve_gidx(t, A.lsi, t.r0 + k);
+#pragma unroll
+            for (int qq = 0; qq < QB; ++qq) xs[qq][k] = q0 + qq < A.nrhs ? A.rhs[(int64_t)(q0 + qq) * A.n + gi] : 0.0;
+        }
         __syncthreads();
         for (int jj = warp; jj < t.w; jj += 8) {
             const double *col = P + (int64_t)jj * t.ld + t.r0;
-            double acc = 0.0;
-#pragma unroll 8
-            for (int k = lane; k < cnt; k += 32) acc = fma(col[k], xs[k], acc);
+            double acc[QB];
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-            if (lane == 0) atomicAdd(b + t.col0 + t.j0 + jj, -acc);
+            for (int qq = 0; qq < QB; ++qq) acc[qq] = 0.0;
+#pragma unroll 8
+            for (int k = lane; k < cnt; k += 32) {
+                const double l = col[k];
+#pragma unroll
+                for (int qq = 0; qq < QB; ++qq) acc[qq] = fma(l, xs[qq][k], acc[qq]);
+            }
+#pragma unroll
+            for (int qq = 0; qq < QB; ++qq) {
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) acc[qq] += __shfl_xor_sync(0xffffffffu, acc[qq], o);
+                if (lane == 0 && q0 + qq < A.nrhs) atomicAdd(A.rhs + (int64_t)(q0 + qq) * A.n + t.col0 + t.j0 + jj, -acc[qq]);
+            }
         }
     }
 }
 
 // backward, LU only: b_block -= U11[block rows, columns c in slab] x[c]; thread jj owns block row jj
+template <int QB>
 __global__ void __launch_bounds__(64) k_solve_upd_bwd_u(SolveArgs A, const SolveTask *__restrict__ tasks) {
     const SolveTask t = tasks[blockIdx.x];
     const int jj = threadIdx.x;
     if (jj >= t.w) return;
     const double *P = A.X + t.xoff + t.j0 + jj;
-    for (int q = 0; q < A.nrhs; ++q) {
-        double *b = A.rhs + (int64_t)q * A.n;
-        double acc = 0.0;
+    for (int q0 = 0; q0 < A.nrhs; q0 += QB) {
+        double acc[QB];
+#pragma unroll
+        for (int qq = 0; qq < QB; ++qq) acc[qq] = 0.0;
 #pragma unroll 8
-        for (int c = t.r0; c < t.r1; ++c) acc = fma(P[(int64_t)c * t.ld], b[t.col0 + c], acc);
-        atomicAdd(b + t.col0 + t.j0 + jj, -acc);
+        for (int c = t.r0; c < t.r1; ++c) {
+            const double u = P[(int64_t)c * t.ld];
+#pragma unroll
+            for (int qq = 0; qq < QB; ++qq)
+                if (q0 + qq < A.nrhs) acc[qq] = fma(u, A.rhs[(int64_t)(q0 + qq) * A.n + t.col0 + c], acc[qq]);
+        }
+#pragma unroll
+        for (int qq = 0; qq < QB; ++qq)
+            if (q0 + qq < A.nrhs) atomicAdd(A.rhs + (int64_t)(q0 + qq) * A.n + t.col0 + t.j0 + jj, -acc[qq]);
     }
 }
 
@@ -1352,9 +1390,18 @@ void launch_solve(const double *X, const int32_t *lsi, double *rhs, int64_t n, i
     switch (kind) {
         case S_DIAG_F: k_solve_diag<<<count, 64, 0, st>>>(A, tasks, 0); break;
         case S_DIAG_B: k_solve_diag<<<count, 64, 0, st>>>(A, tasks, lu ? 2 : 1); break;
-        case S_UPD_F: k_solve_upd_fwd<<<count, 256, 0, st>>>(A, tasks); break;
-        case S_UPD_B: k_solve_upd_bwd<<<count, 256, 0, st>>>(A, tasks); break;
-        case S_UPD_BU: k_solve_upd_bwd_u<<<count, 64, 0, st>>>(A, tasks); break;
+        case S_UPD_F:
+            if (nrhs == 1) k_solve_upd_fwd<1><<<count, 256, 0, st>>>(A, tasks);
+            else k_solve_upd_fwd<4><<<count, 256, 0, st>>>(A, tasks);
+            break;
+        case S_UPD_B:
+            if (nrhs == 1) k_solve_upd_bwd<1><<<count, 256, 0, st>>>(A, tasks);
+            else k_solve_upd_bwd<4><<<count, 256, 0, st>>>(A, tasks);
+            break;
+        case S_UPD_BU:
+            if (nrhs == 1) k_solve_upd_bwd_u<1><<<count, 64, 0, st>>>(A, tasks);
+            else k_solve_upd_bwd_u<4><<<count, 64, 0, st>>>(A, tasks);
+            break;
         default: break;
     }
 }

@@ -398,7 +398,7 @@ int build_plan(const Symbolic &S, const PlanParams &prm, HostPlan &P, int rank, 
                 L.first = (int32_t)P.gemm_ops.size();
                 i64 tiles = 0;
                 for (GemmOp g : ops) {
-                    const bool big = g.M >= prm.gemm128_min_m && g.N > 64;
+                    const bool big = g.M >= prm.gemm128_min_m && g.N > 64 && g.K >= prm.gemm128_min_k;
                     // k-major B: one 128-byte bulk copy per column and k-step (kernels.cu: k_gemm_ws) needs aligned
                     // sources and whole k-steps
                     const bool kmajor_ok = prm.ws_kmajor && (g.b_off & 1) == 0 && (g.ldb & 1) == 0 && g.K % 16 == 0;

@@ -19,6 +19,7 @@ struct PlanParams {
     int small_b_bytes = 49152;   //                              : 256-thread CTA
     int small_max_m = 160;       // ... and only if the update (m x m) is small enough for one CTA
     int gemm128_min_m = 192;     // GEMM ops with at least this many rows use 128x128 tiles, others 64x64
+    int gemm128_min_k = 0;       // ... and only if K is at least this (experiment: short-K updates on the 64x64 kernel)
     int leaf_lookahead = 1;      // diagonal block j+1 applies leaf j's update to itself and is factorized next to that update
     int lookahead = 1;           // split the top-level trailing updates (see LaunchFlags) -- needs outer2 > 0
     int use_ws = 1;              // big GEMM ops with a row-major B go to the warp-specialized bulk-copy kernel
