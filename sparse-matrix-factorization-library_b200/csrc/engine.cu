@@ -207,6 +207,19 @@ int run_graphed(sfb200_plan *p, int kind, size_t first, size_t count, const void
     const auto key = std::make_tuple(kind, first, count, tag);
     auto it = p->graphs.find(key);
     if (it == p->graphs.end()) {
+        // the key holds the destination pointer of the streamed copy-out: a caller that hands in a fresh buffer every time
+        // must not grow the cache without bound
+        // (entries without a tag -- device-resident runs, multi-GPU segments -- are bounded by the schedule itself)
+        if (tag) {
+            size_t tagged = 0;
+            for (auto &kv : p->graphs) tagged += std::get<3>(kv.first) != nullptr;
+            if (tagged >= 8)
+                for (auto g = p->graphs.begin(); g != p->graphs.end();) {
+                    if (std::get<3>(g->first) == nullptr) { ++g; continue; }
+                    if (g->second.exec) cudaGraphExecDestroy(g->second.exec);
+                    g = p->graphs.erase(g);
+                }
+        }
         p->graphs.emplace(key, sfb200_plan::CachedGraph{nullptr, 0});
         return issue();
     }
