@@ -381,6 +381,7 @@ int build_plan(const Symbolic &S, const PlanParams &prm, HostPlan &P, int rank, 
     const std::vector<int> dist_widths = {prm.nb, prm.outer};       // blocking inside group-factorized panels
     const int Wd = prm.outer;
 
+    const int min_k128 = prm.gemm128_min_k >= 0 ? prm.gemm128_min_k : (world == 1 ? 257 : 0);
     for (int lev = 0; lev < P.nlevels; ++lev) {
         auto emit_gemm = [&](std::vector<GemmOp> &ops, int top_block, int lflags = 0) {
             // longest tiles first: the CTAs of a launch are dispatched in index order, so the deep-K ops must not be
@@ -398,7 +399,7 @@ int build_plan(const Symbolic &S, const PlanParams &prm, HostPlan &P, int rank, 
                 L.first = (int32_t)P.gemm_ops.size();
                 i64 tiles = 0;
                 for (GemmOp g : ops) {
-                    const bool big = g.M >= prm.gemm128_min_m && g.N > 64 && g.K >= prm.gemm128_min_k;
+                    const bool big = g.M >= prm.gemm128_min_m && g.N > 64 && g.K >= min_k128;
                     // k-major B: one 128-byte bulk copy per column and k-step (kernels.cu: k_gemm_ws) needs aligned
                     // sources and whole k-steps
                     const bool kmajor_ok = prm.ws_kmajor && (g.b_off & 1) == 0 && (g.ldb & 1) == 0 && g.K % 16 == 0;

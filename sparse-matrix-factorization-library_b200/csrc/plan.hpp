@@ -19,7 +19,11 @@ struct PlanParams {
     int small_b_bytes = 49152;   //                              : 256-thread CTA
     int small_max_m = 160;       // ... and only if the update (m x m) is small enough for one CTA
     int gemm128_min_m = 192;     // GEMM ops with at least this many rows use 128x128 tiles, others 64x64
-    int gemm128_min_k = 0;       // ... and only if K is at least this (experiment: short-K updates on the 64x64 kernel)
+    int gemm128_min_k = -1;      // ... and only if K is at least this; -1 = auto: 257 on single-GPU plans -- the K = 64 and
+                                 // K = 256 in-panel updates are RMW-bound short tiles that do as well on the 64x64 kernel at
+                                 // 3 CTAs per SM, and the step gets 1.5-4 % faster (cfg2 211.2 -> 208.0 ms, cfg4 416.5 -> 408.6,
+                                 // cfg1 7.12 -> 6.81; profiles/r01_sweep_min_k_cfg4_cfg1_cfg2.log) -- and 0 on partitioned
+                                 // plans, where it has not been measured
     int leaf_lookahead = 1;      // diagonal block j+1 applies leaf j's update to itself and is factorized next to that update
     int lookahead = 1;           // split the top-level trailing updates (see LaunchFlags) -- needs outer2 > 0
     int use_ws = 1;              // big GEMM ops with a row-major B go to the warp-specialized bulk-copy kernel
