@@ -4,7 +4,6 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "sparse-matrix-factorization-library_b200"))
-sys.path.insert(0, os.path.join(ROOT, "oracle"))
 import sparseframe_b200 as sf  # noqa: E402
 
 cfg = sys.argv[1] if len(sys.argv) > 1 else "cfg2"
@@ -30,7 +29,7 @@ for env in envs:
     line = "%s env=%s launches=%d numeric %.2f ms  %.2f TFLOP/s |" % (cfg, env, plan.int("nlaunches"), best, S.flops / best / 1e9)
     for k, v in prof.items():
         line += " %s %.1fms(%d, %.1fTF)" % (k.replace("k_", ""), v["ms"], v["launches"], v["flops"] / v["ms"] / 1e9)
-    if os.environ.get("SFB200_SWEEP_VALIDATE"):       # device solve + residual for every setting
+    if os.environ.get("SFB200_SWEEP_VALIDATE", "1") != "0":       # device solve + residual for every setting
         import numpy as np
         b = 1.0 + np.arange(n) / n
         d = plan.residual(plan.solve(b), b)
@@ -49,12 +48,4 @@ for env in envs:
             d = plan.residual(np.ascontiguousarray(xlast), b)
             print("   solve nrhs=%d: %s ms, backward error of the last column %.2e" % (
                 nrhs, ["%.2f" % m for m in ms], d["rnorm"] / (d["anorm"] * d["xnorm"])), flush=True)
-    if not env and not os.environ.get("SFB200_SWEEP_VALIDATE"):
-        import sforacle
-        st = {k: S.array(k) for k in ("Super", "SuperMap", "Lsip", "Lsxp", "Lsi", "LeafQueue", "Lp", "Li")}
-        st["csize"], st["nsleaf"] = S.int("csize"), S.int("nsleaf")
-        if split:
-            st["Up"], st["Ui"] = S.array("Up"), S.array("Ui")
-        res, bwd = sforacle.validate(kind, st, lx, plan.download(), ux)
-        print("   residual %.2e backward %.2e" % (res, bwd), flush=True)
     plan.close()

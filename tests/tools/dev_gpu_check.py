@@ -6,7 +6,7 @@ import time
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, os.path.join(ROOT, "sparse-matrix-factorization-library_b200"))
 sys.path.insert(0, os.path.join(ROOT, "oracle"))
 import sparseframe_b200 as sf  # noqa: E402

@@ -1,6 +1,6 @@
 """All single-GPU BASELINE.json configs: numeric time, GFLOP/s, backward error (oracle solve + residual), per-kernel split."""
 import os, sys, time
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, os.path.join(ROOT, "sparse-matrix-factorization-library_b200"))
 sys.path.insert(0, os.path.join(ROOT, "oracle"))
 import numpy as np
