@@ -145,7 +145,10 @@ void tree_postorder(i64 n, const std::vector<i64> &parent, const std::vector<i64
         std::vector<i64> bucket(n + 1, -1);
         for (i64 j = 0; j < n; ++j)
             if (parent[j] >= 0) { const i64 w = (*weight)[j]; sibling[j] = bucket[w]; bucket[w] = j; }
-        for (i64 w = n - 1; w >= 0; --w)
+        // w = n included: a column whose count is n (the first column of a dense matrix) is a legal child.  The reference's
+        // bucket array has n entries and its scan stops at n - 1 (CH.c:1177-1200): such a column is written out of bounds and
+        // dropped from the tree there, leaving Post incomplete -- the one place where this restatement deliberately differs.
+        for (i64 w = n; w >= 0; --w)
             for (i64 j = bucket[w]; j >= 0;) {
                 const i64 nxt = sibling[j], p = parent[j];
                 sibling[j] = first_child[p];
