@@ -5,6 +5,7 @@
 #include <algorithm>
 #include <chrono>
 #include <cstring>
+#include <mutex>
 #include <numeric>
 
 extern "C" int METIS_NodeND(int64_t *nvtxs, int64_t *xadj, int64_t *adjncy, int64_t *vwgt, int64_t *options,
@@ -39,6 +40,12 @@ void fill_reducing_order(i64 n, const i64 *colptr, const i64 *rowind, std::vecto
         }
     std::vector<i64> iperm(n);
     i64 nv = n;
+    // One ordering at a time per process: this METIS build keeps its allocator core and its random-number state in plain
+    // globals (`gkmcore` is a bss symbol of libmetis_static.a, not thread-local), so two concurrent calls -- the
+    // reference's driver analyses MATRIX_THREAD_NUM matrices in parallel, CH.c:3375 -- race and return orderings that
+    // differ from run to run.  Serialised, every call starts from the same seed and is deterministic.
+    static std::mutex metis_mutex;
+    std::lock_guard<std::mutex> lock(metis_mutex);
     METIS_NodeND(&nv, xadj.data(), adj.data(), nullptr, nullptr, perm.data(), iperm.data());
 }
 

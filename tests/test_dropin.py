@@ -64,3 +64,67 @@ def test_demo_runs_and_reports_small_residual(tree, gen, g, tmp_path):
     line = [ln for ln in out.splitlines() if ln.startswith("residual")][0]
     assert float(line.split(":")[1]) < 1e-13, out
     assert "Factorize time:" in out
+
+
+# The reference calls its entry points from an OpenMP loop over matrices (MATRIX_THREAD_NUM concurrent callers, different
+# matrix_info, CH.c:3375-3440): read + analyze must be re-entrant.  Two matrices analysed concurrently must come out
+# exactly as when analysed one after the other (no device needed for these two steps).
+CONCURRENT_PROBE = r"""
+#include <stdio.h>
+#include <string.h>
+#include <omp.h>
+#include "SparseFrame.h"
+int SparseFrame_initialize_matrix(struct matrix_info_struct *);
+int SparseFrame_read_matrix(struct matrix_info_struct *);
+int SparseFrame_analyze(struct common_info_struct *, struct matrix_info_struct *);
+int SparseFrame_cleanup_matrix(struct matrix_info_struct *);
+static unsigned long long fnv(const void *p, size_t bytes, unsigned long long h) {
+  const unsigned char *b = (const unsigned char *)p;
+  for (size_t i = 0; i < bytes; ++i) { h ^= b[i]; h *= 1099511628211ull; }
+  return h; }
+static unsigned long long digest(struct matrix_info_struct *m) {
+  unsigned long long h = 1469598103934665603ull;
+  h = fnv(m->Perm, m->nrow * sizeof(long), h);     h = fnv(m->Super, (m->nsuper + 1) * sizeof(long), h);
+  h = fnv(m->Lsip, (m->nsuper + 1) * sizeof(long), h); h = fnv(m->Lsxp, (m->nsuper + 1) * sizeof(long), h);
+  h = fnv(m->Lsi, m->isize * sizeof(long), h);     h = fnv(m->Li, m->nzmax * sizeof(long), h);
+  h = fnv(m->Lx, m->nzmax * sizeof(double), h);    h = fnv(m->ST_Map, m->nsuper * sizeof(long), h);
+  return h; }
+int main(int argc, char **argv) {
+  static struct matrix_info_struct m[2];
+  static struct common_info_struct c;
+  unsigned long long seq[2], par[2];
+  memset(&c, 0, sizeof(c)); c.devSlotSize = 5380000000ul;
+  for (int pass = 0; pass < 2; ++pass) {
+    #pragma omp parallel for num_threads(2) if(pass == 1)
+    for (int k = 0; k < 2; ++k) {
+      memset(&m[k], 0, sizeof(m[k])); m[k].path = argv[1 + k]; m[k].serial = k;
+      SparseFrame_initialize_matrix(&m[k]);
+      if (SparseFrame_read_matrix(&m[k]) || SparseFrame_analyze(&c, &m[k])) { (pass ? par : seq)[k] = 0; continue; }
+      (pass ? par : seq)[k] = digest(&m[k]);
+      SparseFrame_cleanup_matrix(&m[k]);
+    }
+  }
+  printf("%llu %llu %llu %llu\n", seq[0], seq[1], par[0], par[1]);
+  return 0; }
+"""
+
+
+@pytest.mark.parametrize("tree,gens", [("Cholesky", (("lap3d", 16), ("lap2d", 70))), ("LU", (("cd3d", 14), ("lap3d", 12)))])
+def test_read_and_analyze_are_reentrant(tree, gens, tmp_path):
+    import sparseframe_b200 as sf
+    src = tmp_path / "probe.c"
+    src.write_text(CONCURRENT_PROBE)
+    exe = tmp_path / "probe"
+    lib = os.path.join(PKG, tree, "Lib")
+    subprocess.check_call(["gcc", "-fopenmp", "-I" + os.path.join(PKG, tree, "Include"), str(src), "-o", str(exe),
+                           "-L" + lib, "-lSparseFrame", "-Wl,-rpath," + lib])
+    paths = []
+    for gen, g in gens:
+        p = tmp_path / ("%s_%d.mtx" % (gen, g))
+        sf.matrices.write_matrix_market(str(p), *sf.matrices.generate(gen, g))
+        paths.append(str(p))
+    for _ in range(3):
+        out = subprocess.check_output([str(exe)] + paths, text=True).strip().splitlines()[-1].split()
+        s0, s1, p0, p1 = (int(v) for v in out)
+        assert s0 != 0 and s1 != 0 and s0 != s1
+        assert (p0, p1) == (s0, s1)
