@@ -68,3 +68,29 @@ def test_flop_formula():
     nc = np.diff(S.array("Super")).astype(float)
     m = np.diff(S.array("Lsip")) - nc
     assert S.flops == pytest.approx(float((nc ** 3 / 3 + m * nc ** 2 + m * (m + 1) * nc).sum()), rel=1e-12)
+
+
+# Full-size structure of BASELINE.json's configs as measured on the reference's own analysis ("Measured
+# structure" table: devSlotSize, nsuper, isize, xsize, csize, etree height, flops).  A scalar fingerprint, but at the size the
+# bench runs: any deviation of the ordering, the column counts or the relaxed amalgamation shows up in it.
+SURVEY_TABLE = {
+    "cfg1": dict(slot=5_700_000_000, nsuper=73_431, isize=2_014_421, xsize=104_784_416, csize=1_034_289, flops=1.923e10),
+    "cfg2": dict(slot=5_700_000_000, nsuper=104_917, isize=4_497_623, xsize=1_096_586_362, csize=124_010_496, flops=5.905e12),
+    "cfg4": dict(slot=5_380_000_000, nsuper=106_261, isize=4_508_272, xsize=1_760_091_310, csize=123_210_000, flops=1.188e13),
+}
+
+
+@pytest.mark.parametrize("cfg", sorted(SURVEY_TABLE))
+def test_full_size_structure_matches_the_reference_measurements(cfg):
+    want = SURVEY_TABLE[cfg]
+    gen, g, kind = sf.matrices.CONFIGS[cfg]
+    A, _ = build_matrix(gen, g)
+    S = sf.analyze(A, kind, devslot=want["slot"])
+    for k in ("nsuper", "isize", "xsize", "csize"):
+        assert S.int(k) == want[k], k
+    assert S.flops == pytest.approx(want["flops"], rel=5e-4)
+    # re-using the ordering skips METIS and must give the identical structure (row f3)
+    S2 = sf.analyze(A, kind, devslot=want["slot"], order=S.array("Order"))
+    assert S2.double("t_order") == 0.0
+    for k in ("Perm", "Super", "Lsip", "Lsxp", "Lsi"):
+        assert np.array_equal(S.array(k), S2.array(k)), k
