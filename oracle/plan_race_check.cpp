@@ -16,6 +16,7 @@
  *   - a main launch flagged LF_WAIT_SIDE (LF_WAIT_DIAG) waits for every side (diag) launch issued before it;
  *   - a range of launches (an etree level on one GPU, a segment on several) ends with all streams joined.
  */
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <vector>
@@ -273,6 +274,58 @@ long sfcheck_race_check(void *hv, int by_segment, int drop_flags) {
     // the streamed copy-out exists on the single-GPU host-buffer path only; SFCHECK_RACE_NO_COPY leaves it out
     Checker c(P);
     return c.run(ranges, !by_segment && !getenv("SFCHECK_RACE_NO_COPY"));
+}
+
+/* The solve sweeps run on one stream, launch after launch: the only concurrency is between the tasks of one launch
+ * (k_solve_diag: plain read-modify-write of its 64 unknowns; the update kernels: reads of the right-hand side, atomic adds
+ * into it).  Returns the number of right-hand-side entries on which two DIFFERENT tasks of one launch conflict (plain write
+ * against anything, atomic add against a read). */
+long sfcheck_solve_race_check(void *hv) {
+    CheckHandle *h = (CheckHandle *)hv;
+    const HostPlan &P = h->P;
+    if (P.world != 1) return -1;
+    const size_t n = (size_t)P.n;
+    // per entry, for the launch being scanned: task that wrote / added / read it (-1 none, -2 several tasks)
+    std::vector<int32_t> w(n), a(n), r(n);
+    long hazards = 0;
+    auto scan = [&](const std::vector<SolveLaunch> &sweep) {
+        for (const SolveLaunch &L : sweep) {
+            std::fill(w.begin(), w.end(), -1); std::fill(a.begin(), a.end(), -1); std::fill(r.begin(), r.end(), -1);
+            auto mark = [](std::vector<int32_t> &v, i64 e, int task) { if (v[e] == -1) v[e] = task; else if (v[e] != task) v[e] = -2; };
+            for (int k = 0; k < L.count; ++k) {
+                const SolveTask &t = P.solve_tasks[L.first + k];
+                auto gidx = [&](int i) { return i < t.nscol ? (i64)t.col0 + i : (i64)P.lsi32[t.lsip + i]; };
+                const i64 blk = (i64)t.col0 + t.j0;
+                switch (L.kind) {
+                    case S_DIAG_F: case S_DIAG_B: for (int j = 0; j < t.w; ++j) mark(w, blk + j, k); break;
+                    case S_UPD_F:
+                        for (int j = 0; j < t.w; ++j) mark(r, blk + j, k);
+                        for (int i = t.r0; i < t.r1; ++i) mark(a, gidx(i), k);
+                        break;
+                    case S_UPD_B:
+                        for (int i = t.r0; i < t.r1; ++i) mark(r, gidx(i), k);
+                        for (int j = 0; j < t.w; ++j) mark(a, blk + j, k);
+                        break;
+                    case S_UPD_BU:
+                        for (int c = t.r0; c < t.r1; ++c) mark(r, (i64)t.col0 + c, k);
+                        for (int j = 0; j < t.w; ++j) mark(a, blk + j, k);
+                        break;
+                    default: break;
+                }
+            }
+            for (size_t e = 0; e < n; ++e) {
+                const bool wrote = w[e] != -1, added = a[e] != -1, read = r[e] != -1;
+                bool bad = false;
+                if (wrote && (w[e] == -2 || (added && a[e] != w[e]) || (read && r[e] != w[e]))) bad = true;   // plain write vs another task
+                if (added && read && (a[e] == -2 || r[e] == -2 || a[e] != r[e])) bad = true;                    // add vs another task's read
+                if (bad && hazards++ < 8)
+                    fprintf(stderr, "solve race: launch kind %d, right-hand-side entry %zu (writer %d, adder %d, reader %d)\n", L.kind, e, w[e], a[e], r[e]);
+            }
+        }
+    };
+    scan(P.solve_fwd);
+    scan(P.solve_bwd);
+    return hazards;
 }
 
 }  // extern "C"

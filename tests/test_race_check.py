@@ -76,3 +76,17 @@ def test_rank_schedules_of_a_partition_are_race_free(gen, g, kind, world, monkey
         b = sforacle.CheckBackend(kind, A, sf.DEFAULT_DEVSLOT, rank, world, nb=8, outer=16, small_a=0, small_b=0)
         assert race_check(b, by_segment=1) == 0
         b.close()
+
+
+@pytest.mark.parametrize("gen,g,kind", [("lap3d", 24, "cholesky"), ("lap2d", 150, "cholesky"), ("cd3d", 20, "lu"), ("lap3d", 14, "lu"),
+                                        ("el3d", 7, "cholesky")])
+def test_solve_schedule_has_no_conflicting_tasks_in_one_launch(gen, g, kind):
+    """Device solve (row f1): the sweeps are one stream; inside a launch the tasks run concurrently and touch the
+    right-hand side with plain read-modify-writes (diagonal blocks) and atomic adds (updates)."""
+    A, _ = build_matrix(gen, g)
+    b = sforacle.CheckBackend(kind, A, sf.DEFAULT_DEVSLOT, 0, 1)
+    fn = b.L.sfcheck_solve_race_check
+    fn.restype = C.c_long
+    fn.argtypes = [C.c_void_p]
+    assert fn(b.h) == 0
+    b.close()
