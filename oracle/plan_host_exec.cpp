@@ -8,6 +8,7 @@
  * reference's: loadA (CH.c:1998-2028 / LU.c:2478-2536), SYRK/GEMM + mapped subtract (CH.c:2055-2086 /
  * LU.c:2564-2604), POTRF + TRSM (CH.c:2134-2145), GETRF-nopiv + TRSM (LU.c:2652-2663).
  */
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -264,6 +265,30 @@ void *sfcheck_open(int kind, int is_symmetric, long n, const long *Cp, const lon
     return h;
 }
 void sfcheck_close(void *hv) { delete (CheckHandle *)hv; }
+
+/* launch i of the schedule: out[8] = {kind, level, grid, ops, flags, algorithmic flops of its GEMM / diag / trsm ops, max K,
+ * min K} (K = 0 for non-GEMM launches) -- lets a host-only tool join an ncu launch list with the plan. */
+long sfcheck_launch_info(void *hv, int i, double *out) {
+    const HostPlan &P = ((CheckHandle *)hv)->P;
+    if (i < 0 || i >= (int)P.launches.size()) return -1;
+    const Launch &L = P.launches[i];
+    double flops = 0, kmax = 0, kmin = 0;
+    if (L.kind == L_GEMM128 || L.kind == L_GEMM64 || L.kind == L_GEMM128WS) {
+        kmin = 1e30;
+        for (int q = L.first; q < L.first + L.count; ++q) {
+            const GemmOp &g = P.gemm_ops[q];
+            const double pairs = (g.flags & G_LOWER) ? (double)g.N * (g.N + 1) / 2 + (double)(g.M - g.N) * g.N : (double)g.M * g.N;
+            flops += 2.0 * pairs * g.K / g.tile_mod;
+            kmax = std::max(kmax, (double)g.K); kmin = std::min(kmin, (double)g.K);
+        }
+    } else if (L.kind == L_POTRF || L.kind == L_GETRF) {
+        for (int q = L.first; q < L.first + L.count; ++q) { const double nb = P.diag_ops[q].nb; flops += (L.kind == L_GETRF ? 2.0 : 1.0) * nb * nb * nb / 3.0; }
+    } else if (L.kind == L_TRSM) {
+        for (int q = L.first; q < L.first + L.count; ++q) flops += (double)P.trsm_ops[q].nb * P.trsm_ops[q].nb * P.trsm_ops[q].nvec;
+    }
+    out[0] = L.kind; out[1] = L.level; out[2] = L.grid; out[3] = L.count; out[4] = L.flags; out[5] = flops; out[6] = kmax; out[7] = kmin;
+    return 0;
+}
 
 long sfcheck_int(void *hv, const char *name) {
     const HostPlan &P = ((CheckHandle *)hv)->P;
