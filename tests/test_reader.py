@@ -200,3 +200,45 @@ def test_analyze_ordered_accepts_any_permutation():
         assert S.array("Super")[-1] == n and S.int("xsize") == S.array("Lsxp")[-1]
     with pytest.raises(RuntimeError, match="not a permutation"):
         sf.analyze(A, "cholesky", order=np.zeros(n, dtype=np.int64))
+
+
+def test_decimal_scanner_is_bit_exact_on_many_formats(probe, tmp_path):
+    """Values written in every format a MatrixMarket writer might use -- %.17g, %.3f, %e, %.10E, integers, leading '.',
+    trailing '.', '+' signs, huge / tiny exponents, more than 19 significant digits -- must come out with exactly the
+    bits Python's (correctly rounded) float() gives for the same text, whether the scanner's fast path or strtod took it."""
+    rng = np.random.default_rng(123)
+    n = 20000
+    mags = 10.0 ** rng.uniform(-30, 30, n) * rng.choice([-1.0, 1.0], n)
+    texts = []
+    for k, v in enumerate(mags):
+        f = k % 12
+        if f == 0: t = "%.17g" % v
+        elif f == 1: t = "%.3f" % (v % 1000.0)
+        elif f == 2: t = "%e" % v
+        elif f == 3: t = "%.10E" % v
+        elif f == 4: t = str(int(v % 1e9) + 1)
+        elif f == 5: t = ("%.6f" % abs(v % 1.0 + 0.001)).lstrip("0")              # ".123456"
+        elif f == 6: t = "%d." % (int(abs(v)) % 100000 + 1)                        # "123."
+        elif f == 7: t = "+%.5g" % abs(v)
+        elif f == 8: t = "%.25g" % v                                               # > 19 significant digits
+        elif f == 9: t = "%.15g" % v
+        elif f == 10: t = "%.12ge%+d" % (rng.uniform(1, 10), int(rng.integers(-300, 300)))
+        else: t = "%.16g" % v
+        if float(t) == 0.0:
+            t = "1"
+        texts.append(t)
+    texts[7] = "1e-320"          # subnormal
+    texts[19] = "1.7976931348623157e308"
+    texts[31] = "4.9406564584124654e-324"
+    path = tmp_path / "fmt.mtx"
+    with open(path, "w") as f:
+        f.write("%%%%MatrixMarket matrix coordinate real general\n%d 1 %d\n" % (n, n))
+        for k, t in enumerate(texts):
+            f.write("%d 1 %s\n" % (k + 1, t))
+    for threads in (1, 4):
+        got, out = probe(path, threads)
+        assert got is not None, out
+        assert got["nz"] == n and np.array_equal(got["Ci"], np.arange(n))
+        want = np.array([float(t) for t in texts])
+        bad = np.flatnonzero(got["Cx"].view(np.int64) != want.view(np.int64))
+        assert bad.size == 0, [(texts[i], got["Cx"][i], want[i]) for i in bad[:5]]
