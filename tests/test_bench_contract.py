@@ -1,0 +1,55 @@
+"""The bench line is a contract with the driver: keys of the committed GPU run (profiles/) and of a live run of the
+reference arm (CPU only, one bounded sample)."""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BASE_KEYS = {"metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+             "vs_baseline", "dtype", "data", "config"}
+
+
+def test_committed_bench_line_has_every_contract_key():
+    j = json.load(open(os.path.join(ROOT, "profiles", "r01_bench_v7.json")))
+    assert BASE_KEYS <= set(j)
+    base = json.load(open(os.path.join(ROOT, "BASELINE.json")))
+    assert "numeric-factorization" in base["metric"] and j["metric"] == "fp64_numeric_factorization_gflops"
+    assert j["unit"] == "GFLOP/s" and j["higher_is_better"] is True and j["dtype"] == "f64" and j["vs_baseline"] is None
+    assert j["config"]["workload"].startswith("cfg2") and "model" not in j["config"]
+    assert {"sm_mhz", "sm_max_mhz", "reasons"} <= set(j["clocks"]) and not j["clocks"]["reasons"]
+    assert j["gpu_launches"] > 0
+    e = j["e2e"]
+    assert {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"} <= set(e)
+    assert e["h2d_bytes_per_step"] > 0 and e["d2h_bytes_per_step"] > 8e9 and 0 < e["value"] < j["value"]
+    r = j["roofline"]
+    assert {"bound", "achieved", "peak", "unit", "frac", "traffic"} <= set(r)
+    assert r["bound"] == "tensor" and r["unit"] == "TFLOP/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-12
+    assert 0 < r["frac"] < 1 and r["traffic"] > 0
+    c = j["cpu_baseline"]
+    assert {"value", "unit", "cores", "kind", "sample"} <= set(c) and c["kind"] == "reference" and c["cores"] <= 16
+    assert j["value"] == abs(j["value"]) and abs(j["value"] - j["config"]["flops_per_step"] / j["ms_per_step"] / 1e6) < 1e-6 * j["value"]
+
+
+def test_reference_arm_prints_one_json_line_with_the_same_metric():
+    if not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libsfref_chol.so")):
+        import pytest
+        pytest.skip("compiled reference not built")
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                       capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stderr[-2000:]
+    lines = [ln for ln in p.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1, p.stdout                       # the reference's own printf goes to stderr
+    j = json.loads(lines[0])
+    assert j["impl"] == "reference" and BASE_KEYS <= set(j)
+    assert j["metric"] == "fp64_numeric_factorization_gflops" and j["unit"] == "GFLOP/s" and j["higher_is_better"] is True
+    assert j["config"]["workload"].startswith("cfg2")
+    assert j["e2e"] == {"value": j["value"], "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    c = j["cpu_baseline"]
+    assert c["kind"] == "reference" and c["value"] == j["value"] and 1 <= c["cores"] <= 16 and "64^3" in c["sample"]
+    assert 1.0 < j["value"] < 5000.0                       # GFLOP/s of a CPU, not of a GPU
+
+    # the other ranks of a torchrun launch print nothing and exit 0
+    q = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2"],
+                       capture_output=True, text=True, timeout=120, env=dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1"))
+    assert q.returncode == 0 and q.stdout.strip() == ""
