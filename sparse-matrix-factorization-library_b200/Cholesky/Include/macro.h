@@ -1,2 +1,15 @@
-/* forwarding header kept for source compatibility with code that includes the reference's macro.h */
-#include "SparseFrame.h"
+/* Cholesky/Include/macro.h -- helper macros (reference: Include/macro.h). */
+#ifndef INCLUDE_MACRO_H
+#define INCLUDE_MACRO_H
+
+#ifndef TRUE
+#define FALSE 0
+#define TRUE 1
+#endif
+
+#ifndef MAX
+#define MAX(a, b) (((a) > (b)) ? (a) : (b))
+#define MIN(a, b) (((a) < (b)) ? (a) : (b))
+#endif
+
+#endif

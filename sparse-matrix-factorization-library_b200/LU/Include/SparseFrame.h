@@ -1,8 +1,6 @@
-/* LU/Include/SparseFrame.h -- public header of the drop-in LU library (reference: LU/Include/SparseFrame.h:43 declares
- * only SparseFrame(argc, argv); the analyze / factorize / solve entry points the reference exports without declaring
- * are declared here too).  Types and prototypes live in dropin/sparseframe_abi.h. */
-#ifndef INCLUDE_SPARSEFRAME_H
-#define INCLUDE_SPARSEFRAME_H
+/* LU/Include/SparseFrame.h -- LU flavour of the shared header (the reference keeps two edited copies of every header; the
+ * differences -- ten more matrix_info members, getrf prototypes, mappedSubtract's signature -- are selected by SPARSEFRAME_LU) */
+#ifndef SPARSEFRAME_LU
 #define SPARSEFRAME_LU 1
-#include "../../dropin/sparseframe_abi.h"
 #endif
+#include "../../Cholesky/Include/SparseFrame.h"

@@ -1,2 +1,6 @@
-/* forwarding header kept for source compatibility with code that includes the reference's info.h */
-#include "SparseFrame.h"
+/* LU/Include/info.h -- LU flavour of the shared header (the reference keeps two edited copies of every header; the
+ * differences -- ten more matrix_info members, getrf prototypes, mappedSubtract's signature -- are selected by SPARSEFRAME_LU) */
+#ifndef SPARSEFRAME_LU
+#define SPARSEFRAME_LU 1
+#endif
+#include "../../Cholesky/Include/info.h"

@@ -60,6 +60,38 @@ int sfb200_symbolic_wrap(int kind, int64_t n, int64_t nsuper, const int64_t *Sup
         set_error("sfb200_symbolic_wrap: bad argument");
         return SFB200_ERR_ARG;
     }
+    if (kind != SFB200_CHOLESKY && kind != SFB200_LU) { set_error("sfb200_symbolic_wrap: bad kind"); return SFB200_ERR_ARG; }
+    // The plan builder indexes SuperMap[Lsi[..]], pos[Li[..]] and Super[t] with these values: everything it relies on is
+    // checked here, so that a malformed structure is an error code and never an out-of-bounds access.
+    {
+        const bool lu = kind == SFB200_LU;
+        auto bad = [&](const char *what) {
+            set_error(std::string("sfb200_symbolic_wrap: invalid supernodal structure: ") + what);
+            return SFB200_ERR_ARG;
+        };
+        if (Super[0] != 0 || Super[nsuper] != n) return bad("Super does not cover 0..n");
+        if (Lsip[0] != 0 || Lsxp[0] != 0) return bad("Lsip / Lsxp do not start at 0");
+        for (int64_t k = 0; k < nsuper; ++k) {
+            const int64_t nscol = Super[k + 1] - Super[k], nsrow = Lsip[k + 1] - Lsip[k];
+            if (nscol <= 0) return bad("Super is not strictly increasing");
+            if (nsrow < nscol || nsrow > n) return bad("a supernode has fewer rows than columns (Lsip)");
+            const int64_t panel = lu ? (2 * nsrow - nscol) * nscol : nsrow * nscol;
+            if (Lsxp[k + 1] - Lsxp[k] != panel) return bad("Lsxp does not match the panel sizes");
+            const int64_t *rows = Lsi + Lsip[k];
+            for (int64_t i = 0; i < nscol; ++i)
+                if (rows[i] != Super[k] + i) return bad("the leading rows of a supernode are not its own columns");
+            for (int64_t i = nscol; i < nsrow; ++i)
+                if (rows[i] <= rows[i - 1] || rows[i] >= n) return bad("off-diagonal rows not ascending inside 0..n");
+        }
+        auto check_csc = [&](const int64_t *ptr, const int64_t *idx) {
+            if (ptr[0] != 0) return false;
+            for (int64_t j = 0; j < n; ++j) if (ptr[j + 1] < ptr[j]) return false;
+            for (int64_t p = 0; p < ptr[n]; ++p) if (idx[p] < 0 || idx[p] >= n) return false;
+            return true;
+        };
+        if (!check_csc(Lp, Li)) return bad("Lp / Li");
+        if (lu && Up && Ui && !check_csc(Up, Ui)) return bad("Up / Ui");
+    }
     auto *s = new sfb200_symbolic();
     Symbolic &S = s->S;
     S.kind = kind == SFB200_LU ? Kind::LU : Kind::Cholesky;

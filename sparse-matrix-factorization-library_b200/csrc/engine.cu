@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <cstring>
 #include <map>
+#include <mutex>
 #include <string>
 #include <tuple>
 #include <vector>
@@ -20,6 +21,7 @@ using namespace sfb200;
 struct sfb200_plan {
     HostPlan H;
     int device = 0;
+    int sms = 0;                               // multiprocessors of `device` (grid sizing of the persistent / grid-stride kernels)
     cudaStream_t stream = nullptr;
     bool own_stream = true;
     // per-launch-kind profile of the last sfb200_plan_profile() call: ms, launches, algorithmic flops, bytes
@@ -28,6 +30,7 @@ struct sfb200_plan {
     std::vector<float> prof_launch_ms;     // per launch of the schedule
     std::vector<double> prof_launch_flops;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};   // numeric begin/end, e2e begin/end
+    cudaEvent_t ev_solve[2] = {nullptr, nullptr};               // around the last solve (created on first use)
     PlanDev D{};
     // device copies of the plan
     SnodeDev *d_snode = nullptr;
@@ -64,7 +67,7 @@ struct sfb200_plan {
     // created helper objects exist by the time the second replay is captured.)
     struct CachedGraph { cudaGraphExec_t exec; int64_t launches; };
     std::map<std::tuple<int, size_t, size_t, const void *>, CachedGraph> graphs;
-    bool use_graphs = true;
+    bool use_graphs = true, graphs_wanted = true;
     // streamed copy-out (host-buffer call with a page-locked Lsx): copy stream, per-level work lists
     cudaStream_t copy_stream = nullptr;
     std::vector<cudaEvent_t> copy_events;
@@ -87,7 +90,18 @@ struct sfb200_plan {
 
 namespace {
 
-bool g_kernels_ready = false;
+// cudaFuncSetAttribute is per device: every device a plan is created on gets its own opt-in, once
+std::mutex g_kernels_mutex;
+std::vector<char> g_kernels_ready;
+
+int ensure_kernels(int device) {
+    std::lock_guard<std::mutex> lk(g_kernels_mutex);
+    if ((int)g_kernels_ready.size() <= device) g_kernels_ready.resize(device + 1, 0);
+    if (g_kernels_ready[device]) return SFB200_OK;
+    if (kernels_init() != cudaSuccess) { cudaGetLastError(); return SFB200_ERR_CUDA; }
+    g_kernels_ready[device] = 1;
+    return SFB200_OK;
+}
 
 #define CK(call)                                                                                   \
     do {                                                                                           \
@@ -117,7 +131,7 @@ int issue_launch_on(sfb200_plan *p, const Launch &L, cudaStream_t st, int spare_
         case L_TRSM: launch_trsm(p->D, p->d_trsm + L.first, L.count, L.grid, st); break;
         case L_GEMM128: launch_gemm(p->D, p->d_gemm + L.first, L.count, L.grid, true, st); break;
         case L_GEMM64: launch_gemm(p->D, p->d_gemm + L.first, L.count, L.grid, false, st); break;
-        case L_GEMM128WS: launch_gemm_ws(p->D, p->d_gemm + L.first, L.count, L.grid, spare_sms, st); break;
+        case L_GEMM128WS: launch_gemm_ws(p->D, p->d_gemm + L.first, L.count, L.grid, p->sms - spare_sms, st); break;
         default: set_error("corrupt plan: unknown launch kind"); return SFB200_ERR_STATE;
     }
     return SFB200_OK;
@@ -177,10 +191,10 @@ int begin_factor(sfb200_plan *p) {
     cudaStream_t st = p->stream;
     CK(cudaMemsetAsync(p->d_status, 0, sizeof(int), st));
     CK(cudaMemsetAsync(p->d_X, 0, sizeof(double) * (size_t)H.xsize_pad, st));
-    launch_assemble(p->d_lx, p->d_asm_l, H.nnz, p->d_X, st);
+    launch_assemble(p->d_lx, p->d_asm_l, H.nnz, p->d_X, p->sms, st);
     p->launches = 2;
     if (H.kind == Kind::LU) {
-        launch_assemble(H.split ? p->d_ux : p->d_lx, p->d_asm_u, H.unnz, p->d_X, st);
+        launch_assemble(H.split ? p->d_ux : p->d_lx, p->d_asm_u, H.unnz, p->d_X, p->sms, st);
         ++p->launches;
     }
     return SFB200_OK;
@@ -270,6 +284,7 @@ int check_status(sfb200_plan *p) {
     CK(cudaMemcpyAsync(&status, p->d_status, sizeof(int), cudaMemcpyDeviceToHost, p->stream));
     CK(cudaStreamSynchronize(p->stream));
     if (status & 1) {
+        p->factored = false;          // the image holds NaNs / garbage: solve and download refuse it
         set_error("non-positive (Cholesky) or zero (LU) pivot met");
         return SFB200_ERR_NOT_POSDEF;
     }
@@ -296,6 +311,7 @@ void sfb200_plan_free(sfb200_plan *p) {
                     p->d_ux, p->d_status};
     for (void *q : ptrs) if (q) cudaFree(q);
     for (auto &e : p->ev) if (e) cudaEventDestroy(e);
+    for (auto &e : p->ev_solve) if (e) cudaEventDestroy(e);
     for (auto &e : p->copy_events) if (e) cudaEventDestroy(e);
     if (p->copy_done) cudaEventDestroy(p->copy_done);
     if (p->d_spack) cudaFree(p->d_spack);
@@ -347,10 +363,8 @@ int sfb200_plan_create_part(const sfb200_symbolic *s, int device, int rank, int 
     int err = SFB200_OK;
     auto fail = [&](int code) { sfb200_plan_free(p); return code; };
     if (cudaSetDevice(device) != cudaSuccess) { set_error("cudaSetDevice failed"); return fail(SFB200_ERR_CUDA); }
-    if (!g_kernels_ready) {
-        if (kernels_init() != cudaSuccess) { set_error("kernel attribute setup failed (not an sm_100a device?)"); return fail(SFB200_ERR_CUDA); }
-        g_kernels_ready = true;
-    }
+    if (ensure_kernels(device) != SFB200_OK) { set_error("kernel attribute setup failed (not an sm_100a device?)"); return fail(SFB200_ERR_CUDA); }
+    if (cudaDeviceGetAttribute(&p->sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || p->sms <= 0) { set_error("cannot query the SM count"); return fail(SFB200_ERR_CUDA); }
     if (cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking) != cudaSuccess) { set_error("stream"); return fail(SFB200_ERR_CUDA); }
     for (auto &e : p->ev) if (cudaEventCreate(&e) != cudaSuccess) { set_error("event"); return fail(SFB200_ERR_CUDA); }
     const HostPlan &H = p->H;
@@ -481,7 +495,7 @@ int sfb200_plan_create_part(const sfb200_symbolic *s, int device, int rank, int 
     p->D.status = p->d_status;
     p->D.is_lu = H.kind == Kind::LU;
     p->D.dbg = getenv("SFB200_DBG") ? atoi(getenv("SFB200_DBG")) : 0;
-    if (const char *e = getenv("SFB200_GRAPHS")) p->use_graphs = atoi(e) != 0;
+    if (const char *e = getenv("SFB200_GRAPHS")) p->use_graphs = p->graphs_wanted = atoi(e) != 0;
     *out = p;
     return SFB200_OK;
 }
@@ -788,6 +802,9 @@ int sfb200_plan_set_stream(sfb200_plan *p, void *cuda_stream) {
     if (p->own_stream && p->stream) cudaStreamDestroy(p->stream);
     p->stream = (cudaStream_t)cuda_stream;
     p->own_stream = false;
+    // graphs captured on the old stream replay fine on the new one, but a plan that fell back to plain replay because its
+    // stream could not be captured gets another chance
+    p->use_graphs = p->graphs_wanted;
     return SFB200_OK;
 }
 
@@ -799,15 +816,20 @@ int sfb200_plan_profile(sfb200_plan *p) {
     const HostPlan &H = p->H;
     cudaStream_t st = p->stream;
     const size_t nl = H.launches.size();
-    std::vector<cudaEvent_t> ev(nl + 1);
+    struct Events {          // destroyed on every exit path
+        std::vector<cudaEvent_t> v;
+        ~Events() { for (auto e : v) if (e) cudaEventDestroy(e); }
+    } evs;
+    evs.v.assign(nl + 1, nullptr);
+    std::vector<cudaEvent_t> &ev = evs.v;
     for (auto &e : ev) CK(cudaEventCreate(&e));
     for (int k = 0; k < 8; ++k) { p->prof_ms[k] = p->prof_flops[k] = p->prof_bytes[k] = 0; p->prof_launches[k] = 0; }
     p->prof_launch_ms.clear();
     p->prof_launch_flops.clear();
     CK(cudaMemsetAsync(p->d_status, 0, sizeof(int), st));
     CK(cudaMemsetAsync(p->d_X, 0, sizeof(double) * (size_t)H.xsize_pad, st));
-    launch_assemble(p->d_lx, p->d_asm_l, H.nnz, p->d_X, st);
-    if (H.kind == Kind::LU) launch_assemble(H.split ? p->d_ux : p->d_lx, p->d_asm_u, H.unnz, p->d_X, st);
+    launch_assemble(p->d_lx, p->d_asm_l, H.nnz, p->d_X, p->sms, st);
+    if (H.kind == Kind::LU) launch_assemble(H.split ? p->d_ux : p->d_lx, p->d_asm_u, H.unnz, p->d_X, p->sms, st);
     for (size_t i = 0; i < nl; ++i) {
         const Launch &L = H.launches[i];
         CK(cudaEventRecord(ev[i], st));
@@ -857,7 +879,6 @@ int sfb200_plan_profile(sfb200_plan *p) {
         p->prof_launch_ms.push_back(ms);
         p->prof_launch_flops.push_back(fl);
     }
-    for (auto &e : ev) cudaEventDestroy(e);
     // a partitioned plan replayed alone misses the other ranks' contributions: its pivots mean nothing
     if (H.world > 1) { CK(cudaStreamSynchronize(st)); return SFB200_OK; }
     return check_status(p);
@@ -911,8 +932,8 @@ int sfb200_solve_device(sfb200_plan *p, double *d_B, int nrhs) {
     CK(cudaSetDevice(p->device));
     const HostPlan &H = p->H;
     const bool lu = H.kind == Kind::LU;
-    cudaEvent_t a, b;
-    CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b));
+    if (!p->ev_solve[0]) { CK(cudaEventCreate(&p->ev_solve[0])); CK(cudaEventCreate(&p->ev_solve[1])); }
+    cudaEvent_t a = p->ev_solve[0], b = p->ev_solve[1];
     CK(cudaEventRecord(a, p->stream));
     // the sweeps are a fixed launch sequence too: one graph per (right-hand-side buffer, count)
     const int64_t keep = p->launches;
@@ -927,7 +948,6 @@ int sfb200_solve_device(sfb200_plan *p, double *d_B, int nrhs) {
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(p->stream));
     cudaEventElapsedTime(&p->ms_solve, a, b);
-    cudaEventDestroy(a); cudaEventDestroy(b);
     return SFB200_OK;
 }
 
@@ -958,7 +978,7 @@ int sfb200_residual(sfb200_plan *p, const double *x, const double *b, double *ou
     CK(cudaMemcpyAsync(p->d_rhs, x, nb, cudaMemcpyHostToDevice, p->stream));
     CK(cudaMemcpyAsync(d_b, b, nb, cudaMemcpyHostToDevice, p->stream));
     launch_residual(p->d_lx, p->d_nz_row, p->d_nz_col, H.nnz, p->d_ux, p->d_unz_row, p->d_unz_col, H.unnz, H.split, p->d_rhs, d_b,
-                    d_r, d_w, H.n, p->d_norms, p->stream);
+                    d_r, d_w, H.n, p->d_norms, p->sms, p->stream);
     CK(cudaGetLastError());
     unsigned long long bits[4];
     CK(cudaMemcpyAsync(bits, p->d_norms, sizeof(bits), cudaMemcpyDeviceToHost, p->stream));
@@ -989,7 +1009,9 @@ double sfb200_probe_fp64_peak(int device, int which, int iters) {
     // which: 0 DFMA, 1 DMMA (register operands, 8 accumulators/warp), 2 DMMA fed from shared memory like the GEMM inner
     // loop (1 CTA of 8 warps per SM), 3 same tile shape with register-resident fragments
     const bool tile = which >= 2;
-    const int grid = tile ? 148 : 148 * 8, block = 256;
+    int sms = 0;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || sms <= 0) return -1.0;
+    const int grid = tile ? sms : sms * 8, block = 256;
     double *d = nullptr;
     if (cudaMalloc((void **)&d, sizeof(double) * grid * block) != cudaSuccess) return -1.0;
     cudaEvent_t a, b;

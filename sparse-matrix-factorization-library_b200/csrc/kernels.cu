@@ -1324,10 +1324,10 @@ cudaError_t kernels_init() {
     return e;
 }
 
-void launch_assemble(const double *vals, const int64_t *dst, int64_t count, double *X, cudaStream_t st) {
+void launch_assemble(const double *vals, const int64_t *dst, int64_t count, double *X, int sms, cudaStream_t st) {
     if (count <= 0) return;
     const int block = 256;
-    const int grid = (int)std::min<int64_t>((count + block - 1) / block, 148 * 16);
+    const int grid = (int)std::min<int64_t>((count + block - 1) / block, (int64_t)sms * 16);
     k_assemble<<<grid, block, 0, st>>>(vals, dst, count, X);
 }
 
@@ -1369,11 +1369,9 @@ void launch_gemm(const PlanDev &P, const GemmOp *ops, int count, int grid, bool 
     }
 }
 
-void launch_gemm_ws(const PlanDev &P, const GemmOp *ops, int count, int tiles, int spare_sms, cudaStream_t st) {
+void launch_gemm_ws(const PlanDev &P, const GemmOp *ops, int count, int tiles, int use_sms, cudaStream_t st) {
     if (count <= 0 || tiles <= 0) return;
-    static int sms = 0;
-    if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); if (sms <= 0) sms = 148; }
-    const int avail = sms - spare_sms > 8 ? sms - spare_sms : 8;      // look-ahead: leave a few SMs to the critical path
+    const int avail = use_sms > 8 ? use_sms : 8;      // look-ahead launches leave a few SMs to the critical path
     const int grid = tiles < avail ? tiles : avail;      // persistent: one CTA per SM walks the tile list
     k_gemm_ws<<<grid, ws::NT, ws::SMEM_BYTES, st>>>(P, ops, count, tiles);
 }
@@ -1408,8 +1406,8 @@ void launch_solve(const double *X, const int32_t *lsi, double *rhs, int64_t n, i
 
 void launch_residual(const double *lx, const int64_t *li, const int32_t *lcol, int64_t nnz, const double *ux, const int32_t *urow,
                      const int64_t *ui, int64_t unnz, bool split, const double *x, const double *b, double *r, double *colsum,
-                     int64_t n, unsigned long long *out4, cudaStream_t st) {
-    const int block = 256, grid = 148 * 8;
+                     int64_t n, unsigned long long *out4, int sms, cudaStream_t st) {
+    const int block = 256, grid = sms * 8;
     k_axpby<<<grid, block, 0, st>>>(r, b, -1.0, n);
     cudaMemsetAsync(colsum, 0, sizeof(double) * n, st);
     cudaMemsetAsync(out4, 0, sizeof(unsigned long long) * 4, st);

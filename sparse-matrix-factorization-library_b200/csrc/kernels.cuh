@@ -22,15 +22,15 @@ struct PlanDev {
     int dbg;                         // timing experiments only (SFB200_DBG): bit0 no staging copies, bit1 no barriers
 };
 
-// one-time: opt in to large dynamic shared memory for the kernels that need it
+// once per DEVICE (function attributes are per device): opt in to large dynamic shared memory for the kernels that need it
 cudaError_t kernels_init();
 
-void launch_assemble(const double *vals, const int64_t *dst, int64_t count, double *X, cudaStream_t st);
+void launch_assemble(const double *vals, const int64_t *dst, int64_t count, double *X, int sms, cudaStream_t st);
 void launch_small(const PlanDev &P, const int32_t *tasks, int count, int smem, bool big_cta, cudaStream_t st);
 void launch_diag(const PlanDev &P, const DiagOp *ops, int count, cudaStream_t st);
 void launch_trsm(const PlanDev &P, const TrsmOp *ops, int count, int grid, cudaStream_t st);
 void launch_gemm(const PlanDev &P, const GemmOp *ops, int count, int grid, bool tile128, cudaStream_t st);
-void launch_gemm_ws(const PlanDev &P, const GemmOp *ops, int count, int tiles, int spare_sms, cudaStream_t st);
+void launch_gemm_ws(const PlanDev &P, const GemmOp *ops, int count, int tiles, int use_sms, cudaStream_t st);   // persistent grid = min(tiles, use_sms)
 void launch_pack(const double *X, double *out, const PackTask *tasks, int count, cudaStream_t st);
 
 // device-resident triangular solve / residual
@@ -38,7 +38,7 @@ void launch_solve(const double *X, const int32_t *lsi, double *rhs, int64_t n, i
                   int kind, int count, cudaStream_t st);
 void launch_residual(const double *lx, const int64_t *li, const int32_t *lcol, int64_t nnz, const double *ux, const int32_t *urow,
                      const int64_t *ui, int64_t unnz, bool split, const double *x, const double *b, double *r, double *colsum,
-                     int64_t n, unsigned long long *out4, cudaStream_t st);
+                     int64_t n, unsigned long long *out4, int sms, cudaStream_t st);
 
 // micro-benchmarks of the two FP64 pipes (peak measurement for the roofline denominators)
 void launch_peak_dfma(double *out, int iters, int grid, int block, cudaStream_t st);

@@ -196,7 +196,7 @@ int build_plan(const Symbolic &S, const PlanParams &prm, HostPlan &P, int rank, 
     for (i64 s = 0; s < ns; ++s) {     // parents have larger indices (postordered)
         const i64 p = sparent[s];
         if (p >= 0) {
-            assert(p > s);
+            if (p <= s || p >= ns) return 5;      // parents follow their children (postordered structure)
             P.snode[p].level = std::max(P.snode[p].level, P.snode[s].level + 1);
         }
         maxlev = std::max(maxlev, (int)P.snode[s].level);

@@ -539,6 +539,21 @@ int SparseFrame_cleanup_matrix(struct matrix_info_struct *m) {
     return 0;
 }
 
+/* The reference's helper-kernel launchers (Include/cuda_kernel.cuh:9-23): exported so that programs linked against the
+ * reference library still link.  The engine builds its relative maps on the host and fuses the mapped subtract into its
+ * update kernels, so there is nothing for them to do. */
+static void retired_launcher(const char *name) {
+    fprintf(stderr, "libSparseFrame (B200 engine): %s() is a retired helper of the reference's GPU path; nothing launched\n", name);
+}
+void createMap(Long *, Long *, Long, Long, cudaStream_t) { retired_launcher("createMap"); }
+void createRelativeMap(Long *, Long *, Long *, Long, Long, cudaStream_t) { retired_launcher("createRelativeMap"); }
+#ifdef SPARSEFRAME_LU
+void mappedSubtract(int, int, void *, Long, Long, Long, void *, Long, Long, Long, Long, Long, Long *, cudaStream_t) { retired_launcher("mappedSubtract"); }
+#else
+void mappedSubtract(int, int, void *, Long, void *, Long, Long, Long, Long, Long, Long *, cudaStream_t) { retired_launcher("mappedSubtract"); }
+#endif
+void deviceSum(int, void *, void *, void *, Long, Long, Long, cudaStream_t) { retired_launcher("deviceSum"); }
+
 int SparseFrame(int argc, char **argv) {
     struct common_info_struct common;
     memset(&common, 0, sizeof(common));

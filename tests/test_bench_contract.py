@@ -35,18 +35,22 @@ def test_reference_arm_prints_one_json_line_with_the_same_metric():
     if not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libsfref_chol.so")):
         import pytest
         pytest.skip("compiled reference not built")
-    p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
-                       capture_output=True, text=True, timeout=600)
+    # cfg1 here (2 s per step on 8 cores); the driver's run is cfg2, the config of the GPU line
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "2", "--warmup", "1",
+                        "--config", "cfg1"], capture_output=True, text=True, timeout=600)
     assert p.returncode == 0, p.stderr[-2000:]
     lines = [ln for ln in p.stdout.splitlines() if ln.strip()]
     assert len(lines) == 1, p.stdout                       # the reference's own printf goes to stderr
     j = json.loads(lines[0])
     assert j["impl"] == "reference" and BASE_KEYS <= set(j)
     assert j["metric"] == "fp64_numeric_factorization_gflops" and j["unit"] == "GFLOP/s" and j["higher_is_better"] is True
-    assert j["config"]["workload"].startswith("cfg2")
+    assert j["config"]["workload"].startswith("cfg1") and j["config"]["same_config_as_gpu_arm"] is True
+    assert j["steps"] == 2 and j["warmup"] == 1
+    assert abs(j["config"]["sample"].count("1.923e+10") - 1) == 0          # flops of cfg1, from the reference's arrays
     assert j["e2e"] == {"value": j["value"], "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     c = j["cpu_baseline"]
-    assert c["kind"] == "reference" and c["value"] == j["value"] and 1 <= c["cores"] <= 16 and "64^3" in c["sample"]
+    assert c["kind"] == "reference" and c["value"] == j["value"] and 1 <= c["cores"] <= 16 and "the whole matrix" in c["sample"]
+    assert {"host_cores", "affinity_cores", "loadavg_1_5_15"} <= set(c["host"])
     assert 1.0 < j["value"] < 5000.0                       # GFLOP/s of a CPU, not of a GPU
 
     # the other ranks of a torchrun launch print nothing and exit 0

@@ -46,6 +46,46 @@ def test_wrap_structure_roundtrip():
     assert W.flops == S.flops
 
 
+@pytest.mark.parametrize("kind,gen,g", [("cholesky", "lap2d", 12), ("lu", "cd3d", 6)])
+def test_wrap_structure_rejects_malformed_structures(kind, gen, g):
+    """A structure from somebody else's analysis is checked before the plan builder indexes with it: every corruption is
+    SFB200_ERR_ARG with a message, never an out-of-bounds access or an abort inside the library."""
+    A = sf.compress(*sf.matrices.generate(gen, g))
+    S = sf.analyze(A, kind)
+    good = {k: S.array(k) for k in ("Super", "Lsip", "Lsxp", "Lsi", "Lp", "Li")}
+    lu = kind == "lu"
+    if lu:
+        good["Up"], good["Ui"] = S.array("Up"), S.array("Ui")
+
+    def wrap(d):
+        return sf.api.wrap_structure(kind, A.n, d["Super"], d["Lsip"], d["Lsxp"], d["Lsi"], d["Lp"], d["Li"],
+                                     d.get("Up"), d.get("Ui"))
+    wrap(good).close()
+    ns = len(good["Super"]) - 1
+    big = int(np.argmax(np.diff(good["Lsip"]) - np.diff(good["Super"])))      # a supernode with off-diagonal rows
+
+    def corrupt(name, fn):
+        d = {k: v.copy() for k, v in good.items()}
+        fn(d[name])
+        return d
+    cases = [
+        corrupt("Super", lambda a: a.__setitem__(ns, A.n + 1)),
+        corrupt("Super", lambda a: a.__setitem__(1, a[0])),
+        corrupt("Lsip", lambda a: a.__setitem__(1, a[1] + 1)),
+        corrupt("Lsxp", lambda a: a.__setitem__(ns, a[ns] + 2)),
+        corrupt("Lsi", lambda a: a.__setitem__(good["Lsip"][big], a[good["Lsip"][big]] + 1)),                    # not its own column
+        corrupt("Lsi", lambda a: a.__setitem__(good["Lsip"][big + 1] - 1, A.n)),                                 # row outside 0..n
+        corrupt("Lsi", lambda a: a.__setitem__(good["Lsip"][big + 1] - 1, a[good["Lsip"][big]])),                # not ascending
+        corrupt("Lp", lambda a: a.__setitem__(3, a[2] - 1)),
+        corrupt("Li", lambda a: a.__setitem__(0, -1)),
+    ]
+    if lu:
+        cases.append(corrupt("Ui", lambda a: a.__setitem__(0, A.n)))
+    for d in cases:
+        with pytest.raises(RuntimeError, match="invalid supernodal structure"):
+            wrap(d)
+
+
 @pytest.mark.skipif(sf.device_count() > 0, reason="this check is for the CPU-only box")
 def test_numeric_path_fails_loudly_without_gpu():
     A = sf.compress(*sf.matrices.generate("lap2d", 8))

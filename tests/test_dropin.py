@@ -13,7 +13,9 @@ PKG = os.path.join(ROOT, "sparse-matrix-factorization-library_b200")
 ENTRY_POINTS = ["SparseFrame", "SparseFrame_time", "SparseFrame_allocate_gpu", "SparseFrame_free_gpu",
                 "SparseFrame_allocate_matrix", "SparseFrame_free_matrix", "SparseFrame_initialize_matrix",
                 "SparseFrame_read_matrix", "SparseFrame_compress", "SparseFrame_analyze", "SparseFrame_factorize",
-                "SparseFrame_solve_supernodal", "SparseFrame_validate", "SparseFrame_cleanup_matrix"]
+                "SparseFrame_solve_supernodal", "SparseFrame_validate", "SparseFrame_cleanup_matrix",
+                # helper-kernel launchers of Include/cuda_kernel.cuh:9-23, kept as symbols (they launch nothing)
+                "createMap", "createRelativeMap", "mappedSubtract", "deviceSum"]
 
 # sizeof / offsetof measured on the REFERENCE headers (Include/info.h of each tree) with gcc x86-64:
 # sizeof(common_info), sizeof(gpu_info), sizeof(matrix_info), then offsets of common.devSlotSize, gpu.lastMatrix,
@@ -52,6 +54,34 @@ def test_struct_layout_matches_reference(tree, tmp_path):
     subprocess.check_call(["gcc", "-fopenmp", "-I" + os.path.join(PKG, tree, "Include"), str(src), "-o", str(exe)])
     got = [int(v) for v in subprocess.check_output([str(exe)]).split()]
     assert got == REFERENCE_ABI[tree]
+
+
+HEADERS = ["SparseFrame.h", "arch.h", "constant.h", "cuda_kernel.cuh", "extern.h", "info.h", "macro.h", "parameter.h", "type.h"]
+
+
+@pytest.mark.parametrize("tree", ["Cholesky", "LU"])
+def test_include_tree_has_the_reference_headers(tree, tmp_path):
+    """north_star keeps the Include headers: every header of the reference's Include/ exists, compiles on its own as C,
+    and parameter.h carries the policy functions with the reference's decisions (parameter.h:31-103)."""
+    inc = os.path.join(PKG, tree, "Include")
+    assert sorted(os.listdir(inc)) == sorted(HEADERS)
+    for h in HEADERS:
+        src = tmp_path / ("one_%s.c" % h.replace(".", "_"))
+        src.write_text('#include "%s"\nint main(void) { return 0; }\n' % h)
+        subprocess.check_call(["gcc", "-fopenmp", "-Wall", "-Wno-unused", "-I" + inc, str(src), "-o", str(tmp_path / "a.out")])
+    src = tmp_path / "policy.c"
+    src.write_text(r"""
+#include <stdio.h>
+#include "SparseFrame.h"
+int main(void) {
+  printf("%d %d %d %d %d ", should_relax(16, 0.9), should_relax(17, 0.9), should_relax(65, 0.11), should_relax(300, 0.04), should_relax(300, 0.06));
+  printf("%ld %ld %ld ", get_node_score_from_dimension(16, 0, 16), get_node_score_from_dimension(32, 32, 32), get_node_score_from_dimension(20, 0, 20));
+  printf("%d %d %d %ld %ld %d\n", set_factorize_location(255, 510), set_factorize_location(256, 256), MATRIX_THREAD_NUM, potrf_split_threshold, potrf_split_block, (int)minus_one[0]);
+  return 0; }
+""")
+    exe = tmp_path / "policy"
+    subprocess.check_call(["gcc", "-fopenmp", "-I" + inc, str(src), "-o", str(exe)])
+    assert subprocess.check_output([str(exe)], text=True).split() == "1 0 0 1 0 0 2048 -400 1 0 2 512 256 -1".split()
 
 
 @pytest.mark.gpu

@@ -258,20 +258,56 @@ def test_graph_replays_match_the_first_plain_run(gen, g, kind):
     plan.close()
 
 
-def test_full_size_cfg4_lu_device_residual():
-    """BASELINE.json's LU config (3-D convection-diffusion 100^3, 14 GB factor, fronts wide enough for every blocking
-    level and for the look-ahead split) at full size: factorize without copy-out, solve and take the reference's
-    residual on the device (the device solve itself is checked against the oracle in test_device_solve_and_residual)."""
-    gen, g, kind = sf.matrices.CONFIGS["cfg4"]
+@pytest.mark.parametrize("cfg", ["cfg3", "cfg4", "cfg5"])
+def test_full_size_device_residual(cfg):
+    """BASELINE.json configs[2], [3], [4] at full size on ONE GPU -- 27-point 3-dof elasticity 80^3 (36.9 GB factor),
+    LU of the 3-D convection-diffusion 100^3 (14 GB factor, fronts wide enough for every blocking level and for the
+    look-ahead split) and the 160^3 Laplacian (58.4 GB factor, the multi-GPU config, which fits one B200): factorize
+    without copy-out, solve and take the reference's residual (CH.c:3197-3263) on the device (the device solve itself is
+    checked against the oracle in test_device_solve_and_residual)."""
+    gen, g, kind = sf.matrices.CONFIGS[cfg]
     A, _ = build_matrix(gen, g)
     S = sf.analyze(A, kind)
     plan = sf.Plan(S)
-    plan.factorize(S.array("Lx"), S.array("Ux"), download=False)
+    split = kind == "lu" and not A.symmetric
+    plan.factorize(S.array("Lx"), S.array("Ux") if split else None, download=False)
     b = 1.0 + np.arange(A.n) / A.n
     x = plan.solve(b)
     dev = plan.residual(x, b)
+    assert np.isfinite(x).all()
     assert dev["rnorm"] / (dev["anorm"] * dev["xnorm"]) <= BACKWARD_TOL
+    assert dev["residual"] <= 1e-13
     plan.close()
+
+
+@pytest.mark.skipif(not sfref.available("cholesky"), reason="compiled reference did not travel")
+@pytest.mark.skipif(os.environ.get("SFB200_SKIP_SLOW") == "1", reason="SFB200_SKIP_SLOW=1")
+def test_cfg2_entrywise_against_compiled_reference():
+    """The BASELINE config itself (3-D Laplacian 100^3, 1.1e9 factor entries) entry by entry against the compiled
+    reference's CPU factorization (about a minute of host time): structure bit-exact, every entry within 1e-10 relative,
+    explicit zeros exactly zero.  Compared in slices so that the temporaries stay small next to the two 8.8 GB factors."""
+    gen, g, kind = sf.matrices.CONFIGS["cfg2"]
+    A, (n, r, c, x, sym) = build_matrix(gen, g)
+    ref = sfref.Reference(n, r, c, x, sym, kind=kind, blas_threads=min(os.cpu_count(), 16)).analyze().factorize()
+    S = sf.analyze(A, kind)
+    for k in ("Perm", "Super", "Lsip", "Lsxp", "Lsi"):
+        assert np.array_equal(S.array(k), ref.array(k)[:len(S.array(k))]), k
+    ref_lsx = ref.array("Lsx")
+    ref.close()
+    plan, lsx = gpu_factor(S)
+    plan.close()
+    st = oracle_structure(S)
+    mask = sf.lower_trapezoid_mask(kind, st["Super"], st["Lsip"], st["Lsxp"], len(ref_lsx))
+    worst = 0.0
+    step = 1 << 26
+    for i in range(0, len(ref_lsx), step):
+        m = mask[i:i + step]
+        a, b = ref_lsx[i:i + step][m], lsx[i:i + step][m]
+        assert not np.isnan(b).any()
+        assert np.array_equal(a == 0, b == 0), "explicit zeros must stay exactly zero"
+        worst = max(worst, sf.entrywise_rel_diff(a, b))
+    print("cfg2 entrywise max relative difference vs the compiled reference: %.3e over %d entries" % (worst, int(mask.sum())))
+    assert worst <= ENTRY_TOL
 
 
 @pytest.mark.parametrize("gen,g,kind", [("cd3d", 30, "lu"), ("lap3d", 30, "lu"), ("lap3d", 34, "cholesky")])
