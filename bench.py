@@ -216,6 +216,88 @@ def cpu_baseline(cfg, gen, g, kind):
             "host": host_state()}
 
 
+def distributed_parity(sf, torch, dist, S, plan, pf, d_lx, d_ux, stream, rank, world, local_rank, split, flops):
+    """After the timed region of an N>1 run: (1) rank 0 factorizes the SAME matrix alone (3 timed steps: the one-GPU point of
+    the strong-scaling curve on this workload); (2) every rank's owned panels travel to rank 0, are compared entry by entry
+    with that single-GPU factor and replace it; (3) rank 0 solves with the gathered, distributed factor and takes the
+    reference's residual (CH.c:3197-3263).  Bars: entrywise 1e-10, backward error 1e-12 (BASELINE.json north_star)."""
+    from sparseframe_b200.parallel import owned_runs
+    from sparseframe_b200.parallel import _CudaView
+    single, full, full_img = None, None, None
+    nsuper = S.int("nsuper")
+    goff = torch.empty(nsuper + 1, dtype=torch.int64, device="cuda")
+    if rank == 0:
+        full = sf.Plan(S, device=local_rank)
+        full.set_stream(stream.cuda_stream)
+        dux = d_ux.data_ptr() if split else 0
+        for _ in range(2):                      # plain run, then the graph capture
+            full.factorize_device(d_lx.data_ptr(), dux)
+        full.sync()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 3
+        a.record(stream)
+        for _ in range(reps):
+            full.factorize_device(d_lx.data_ptr(), dux)
+        b.record(stream)
+        full.sync()
+        ms = a.elapsed_time(b) / reps
+        single = {"ms_per_step": ms, "value": flops / (ms * 1e-3) / 1e9, "unit": UNIT, "steps": reps,
+                  "note": "the same matrix factorized by rank 0 alone (device-resident), measured after the timed region"}
+        goff.copy_(torch.from_numpy(full.panel_offsets()))
+        full_img = torch.as_tensor(_CudaView(full.factor_ptr(), full.int("xsize_padded")), device="cuda")
+    dist.broadcast(goff, src=0)
+    goff_h = goff.cpu().numpy()
+    # one more partitioned factorization of the unscaled values, so that what is gathered is what was timed
+    pf.factorize(wait=True)
+    torch.cuda.synchronize()
+    image = torch.as_tensor(_CudaView(plan.factor_ptr(), max(plan.int("xsize_padded"), 1)), device="cuda")
+    runs = owned_runs(plan.owner(), plan.panel_offsets(), goff_h, rank)
+    all_runs = [None] * world
+    dist.all_gather_object(all_runs, runs)
+    chunk = 1 << 27                             # 1 GiB of doubles per message
+    worst, gathered = 0.0, 0
+    buf = torch.empty(chunk, dtype=torch.float64, device="cuda") if rank == 0 else None
+    for r in range(world):
+        for (loc, glob, count) in all_runs[r]:
+            for o in range(0, count, chunk):
+                cnt = min(chunk, count - o)
+                if rank == r and r != 0:
+                    dist.send(image[loc + o:loc + o + cnt], dst=0)
+                if rank == 0:
+                    if r == 0:
+                        piece = image[loc + o:loc + o + cnt]
+                    else:
+                        piece = buf[:cnt]
+                        dist.recv(piece, src=r)
+                    ref = full_img[glob + o:glob + o + cnt]
+                    den = torch.maximum(ref.abs(), piece.abs())
+                    rel = (ref - piece).abs() / den.clamp_min(1e-300)
+                    rel[den == 0] = 0
+                    worst = max(worst, float(rel.max().item()))
+                    if not bool(torch.isfinite(piece).all().item()):
+                        worst = float("inf")
+                    ref.copy_(piece)
+                    gathered += cnt
+                    del den, rel
+    parity = None
+    if rank == 0:
+        n = S.int("n")
+        full.adopt_factor(d_lx.data_ptr(), d_ux.data_ptr() if split else 0)
+        b = 1.0 + np.arange(n) / n
+        x = full.solve(b)
+        res = full.residual(x, b)
+        backward = res["rnorm"] / (res["anorm"] * res["xnorm"])
+        parity = {"backward": backward, "residual": res["residual"], "max_rel_vs_single_gpu": worst,
+                  "entries_gathered": int(gathered), "entries_expected": int(full.int("xsize_padded")),
+                  "ok": bool(backward <= 1e-12 and worst <= 1e-10 and gathered == full.int("xsize_padded")),
+                  "how": "owned panels of all ranks gathered on rank 0, compared entrywise with rank 0's single-GPU factor of "
+                         "the same matrix, then solve + residual on the device with the gathered factor"}
+        log("parity of the distributed factor: %r" % (parity,))
+        full.close()
+    dist.barrier()
+    return parity, single
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -255,7 +337,19 @@ def main():
     t0 = time.time()
     n, r, c, x, sym = sf.matrices.generate(gen, g)
     A = sf.compress(n, r, c, x, sym)
-    S = sf.analyze(A, kind)
+    if world > 1:
+        # the fill-reducing ordering (METIS, 95 % of the analysis time) is computed once and shared; every rank then runs the
+        # cheap rest of the analysis itself and arrives at the bit-identical structure (sfb200_analyze_ordered)
+        order = torch.empty(n, dtype=torch.int64, device="cuda")
+        S0 = None
+        if rank == 0:
+            S0 = sf.analyze(A, kind)
+            order.copy_(torch.from_numpy(S0.array("Order")))
+        dist.broadcast(order, src=0)
+        S = S0 if rank == 0 else sf.analyze(A, kind, order=order.cpu().numpy())
+        del order
+    else:
+        S = sf.analyze(A, kind)
     t_analyze = time.time() - t0
     t0 = time.time()
     plan = sf.Plan(S, device=local_rank, rank=rank, world=world)
@@ -278,12 +372,14 @@ def main():
 
     pf = None
     if world > 1:
+        # connect the ranks: CUDA IPC handles of every rank's image and flags travel through torch.distributed once; from then on
+        # a factorization is one device-side replay per rank (remote adds, pushes and flags over NVLink, no host round trip)
         from sparseframe_b200.parallel import DeviceBackend, PartitionedFactorization
         pf = PartitionedFactorization(DeviceBackend(plan, d_lx, d_ux), dist)
 
     def step():
         if pf is not None:
-            pf.factorize()          # segments: NCCL collectives on the shared panels, then the rank's launches
+            pf.factorize(wait=False)
         else:
             plan.factorize_device(d_lx.data_ptr(), d_ux.data_ptr() if split else 0)
 
@@ -326,31 +422,16 @@ def main():
             if rc != 0:
                 raise RuntimeError(_capi.last_error())
     else:
-        # every rank uploads the values and brings home the panels it owns (contiguous runs of the padded image)
-        owner = plan.owner()
-        snode_off = plan.panel_offsets()
-        image = pf.b.image
-        runs = []
-        mine = np.flatnonzero(owner == rank)
-        if mine.size:
-            brk = np.flatnonzero(np.diff(mine) != 1)
-            starts = np.concatenate([[mine[0]], mine[brk + 1]])
-            ends = np.concatenate([mine[brk], [mine[-1]]])
-            runs = [(int(snode_off[a]), int(snode_off[b + 1])) for a, b in zip(starts, ends)]
-        own_elems = sum(b - a for a, b in runs)
+        # every rank uploads the values and brings home the panels it owns, packed (sfb200_factorize_owned): same C-ABI call
+        # shape as the single-GPU one, host buffers in and out
+        own_elems = plan.int("owned_elems")
         h_out = torch.empty(max(own_elems, 1), dtype=torch.float64).pin_memory()
         d2h_bytes = own_elems * 8
 
         def e2e_step():
-            d_lx.copy_(h_lx, non_blocking=True)
-            if split:
-                d_ux.copy_(h_ux, non_blocking=True)
-            pf.factorize()
-            pos = 0
-            for a, b in runs:
-                h_out[pos:pos + (b - a)].copy_(image[a:b], non_blocking=True)
-                pos += b - a
-            torch.cuda.synchronize()
+            rc = L.sfb200_factorize_owned(plan._h, h_lx.data_ptr(), h_ux.data_ptr() if split else None, h_out.data_ptr())
+            if rc != 0:
+                raise RuntimeError(_capi.last_error())
 
     for _ in range(max(3, min(args.warmup, 3))):      # >= 3: the second call captures the CUDA graph, later ones replay it
         e2e_step()
@@ -375,6 +456,23 @@ def main():
         dist.all_gather(share_list, shares)
     else:
         share_list = [shares]
+
+    exchange = None
+    if world > 1:
+        vols = torch.tensor([plan.double("remote_update_bytes"), plan.double("push_bytes"), float(plan.int("xsize_padded")) * 8],
+                            dtype=torch.float64, device="cuda")
+        allv = [torch.zeros_like(vols) for _ in range(world)]
+        dist.all_gather(allv, vols)
+        allv = torch.stack(allv).cpu().numpy()
+        exchange = {"medium": "peer memory over NVLink: remote red.global.add.f64 from the scatter epilogues, peer copies of factored "
+                              "blocks, flags; NCCL carries no payload",
+                    "remote_update_GB_per_step": float(allv[:, 0].sum()) / 1e9, "pushed_GB_per_step": float(allv[:, 1].sum()) / 1e9,
+                    "nvlink_GB_per_rank_max": float((allv[:, 0] + allv[:, 1]).max()) / 1e9,
+                    "image_GB_per_rank": [round(float(v) / 1e9, 2) for v in allv[:, 2]],
+                    "exchange_steps": plan.int("ncolls")}
+    parity, single = None, None
+    if world > 1:
+        parity, single = distributed_parity(sf, torch, dist, S, plan, pf, d_lx, d_ux, stream, rank, world, local_rank, split, flops)
 
     if rank == 0:
         # ---- roofline of the dominant kernel: live CUDA-event profile of one replay ------------------------------
@@ -432,11 +530,17 @@ def main():
                            "per rank: H2D values, partitioned factorization, D2H of the owned panels (pinned)"},
             "roofline": roof, "cpu_baseline": base,
         }
+        if world > 1:
+            out["parity"] = parity
+            out["single_gpu_same_config"] = single
+            out["exchange"] = exchange
         emit(out)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     plan.close()
+    if parity is not None and not parity["ok"]:
+        raise SystemExit("distributed factor failed the parity check: %r" % (parity,))
 
 
 if __name__ == "__main__":

@@ -90,29 +90,51 @@ int sfb200_device_count(void);
 
 int sfb200_plan_create(const sfb200_symbolic *s, int device, sfb200_plan **out);
 
-/* One rank of an etree-subtree partition over `world` GPUs (one process per GPU).  Whole subtrees are local to a rank;
- * the supernodes above them ("top") are shared by a contiguous group of ranks [lo,hi) and receive partial updates from
- * all of them: every rank keeps a full-size zero-initialised image of the factor and accumulates its updates there.
- * The plan of a rank is a list of SEGMENTS; a segment is a list of collectives on regions of that image followed by
- * kernel launches.  The collectives are the caller's job (NCCL through torch.distributed in
- * sparseframe_b200/parallel.py, on the plan's stream): the plan only lists them, identically on every rank.
- *   sfb200_plan_int: "nsegments", "ncolls", "rank", "world";  sfb200_plan_double: "flops", "local_flops"
+/* One rank of an etree-subtree partition over `world` GPUs of one box.  Whole subtrees are local to a rank; the
+ * supernodes above them ("top") are shared by a contiguous group of ranks [lo,hi).  The exchange medium is peer memory over
+ * NVLink -- the reference's only medium is host RAM (CH.c:2596-2685):
+ *   - a rank's image holds the panels it stores (the ones it owns plus the shared fronts its group works on together);
+ *   - an update aimed at a panel stored elsewhere is added straight into the destination rank's image by the scatter
+ *     epilogue of the update kernels (extend-add fused into the producing GEMM);
+ *   - wide shared Cholesky fronts are factorized by their group (block columns owned round-robin), the Schur update of a
+ *     shared front is split over its group; factored blocks are pushed to the group with peer copies;
+ *   - the remaining synchronisation is flags in peer memory (barrier per group and level, one flag per pushed block):
+ *     no host round trip, the whole factorization of a rank is one CUDA graph.
+ * The ranks are connected either across processes (one process per GPU: sfb200_plan_exchange_handle on every rank, exchange
+ * the 128-byte handles by any means -- torch.distributed in sparseframe_b200/parallel.py --, sfb200_plan_connect) or inside
+ * one process (sfb200_group_create, one host thread per GPU like the reference, CH.c:2267-2290).  Once connected,
+ * sfb200_factorize_device / sfb200_factorize run this rank's part; all ranks must call them (they wait for each other on the
+ * device; a rank that never arrives is reported after SFB200_PEER_TIMEOUT_S seconds, default 30).
+ *   sfb200_plan_int: "nsegments", "ncolls", "rank", "world", "connected", "owned_elems"
+ *   sfb200_plan_double: "flops", "local_flops", "remote_update_bytes", "push_bytes"
  *   segment k = {coll_first, coll_count, launch_first, launch_count, level}
- *   coll i    = {type, offset, count (elements of the padded factor), root, lo, hi}; ranks outside [lo,hi) skip it
- *       type 0 reduce:     the images of a shared panel are summed into its owner (root) before it is factorized
- *       type 1 all-reduce: ... into every rank of the group (wide Cholesky panels are factorized by the whole group,
- *                          block columns owned round-robin)
- *       type 2 broadcast:  root's image of a factored panel / block column replaces the group's */
+ *   exchange step i = {type (0 barrier, 1 push), root, lo, hi, offset in this rank's image, rows, cols, ld} */
 int sfb200_plan_create_part(const sfb200_symbolic *s, int device, int rank, int world, sfb200_plan **out);
 double sfb200_plan_double(const sfb200_plan *p, const char *name);
 int sfb200_plan_segment_info(const sfb200_plan *p, int k, int64_t out[5]);
-int sfb200_plan_coll_info(const sfb200_plan *p, int i, int64_t out[6]);
+int sfb200_plan_coll_info(const sfb200_plan *p, int i, int64_t out[8]);
 int sfb200_plan_owner(const sfb200_plan *p, int32_t *owner /* nsuper */);
-void *sfb200_plan_factor_ptr(sfb200_plan *p);                 /* device pointer of the padded factor image */
-int sfb200_plan_panel_offsets(const sfb200_plan *p, int64_t *xoff /* nsuper + 1 */);   /* panel offsets in that image */
-int sfb200_partition_begin(sfb200_plan *p, const double *d_Lx, const double *d_Ux);   /* zero + assemble owned panels */
-int sfb200_segment_run(sfb200_plan *p, int k);                /* launches of segment k, asynchronous on the plan's stream */
+void *sfb200_plan_factor_ptr(sfb200_plan *p);                 /* device pointer of this rank's image of the padded factor */
+/* offsets of the panels in that image (-1: not stored by this rank); xoff[nsuper] = elements of the image */
+int sfb200_plan_panel_offsets(const sfb200_plan *p, int64_t *xoff /* nsuper + 1 */);
+int sfb200_plan_exchange_handle(sfb200_plan *p, void *out /* 128 bytes */);
+int sfb200_plan_connect(sfb200_plan *p, const void *handles /* world x 128 bytes, in rank order */);
 void sfb200_plan_free(sfb200_plan *p);
+
+/* The whole partition inside one process: rank r on devices[r] (entries may repeat). */
+typedef struct sfb200_group sfb200_group;
+int sfb200_group_create(const sfb200_symbolic *s, int world, const int *devices, sfb200_group **out);
+int sfb200_group_size(const sfb200_group *g);
+sfb200_plan *sfb200_group_plan(sfb200_group *g, int rank);
+/* host buffers, one host thread per rank; every rank writes the panels it owns into Lsx (may be NULL) */
+int sfb200_group_factorize(sfb200_group *g, const double *Lx, const double *Ux, double *Lsx);
+double sfb200_group_last_ms(const sfb200_group *g, int which);
+void sfb200_group_free(sfb200_group *g);
+
+/* The caller has written a complete factor into the image of this single-GPU plan (sfb200_plan_factor_ptr +
+ * sfb200_plan_panel_offsets), e.g. gathered from the ranks of a partition; d_Lx / d_Ux = the matrix values it belongs to.
+ * Afterwards sfb200_solve / sfb200_residual / sfb200_download_factor work on it. */
+int sfb200_plan_adopt_factor(sfb200_plan *p, const double *d_Lx, const double *d_Ux);
 
 /* Scalars: "nlevels","nlaunches","nsmall","nlarge","relmap_entries","xsize_padded","device_bytes", ... */
 int64_t sfb200_plan_int(const sfb200_plan *p, const char *name);
@@ -125,12 +147,21 @@ int64_t sfb200_plan_int(const sfb200_plan *p, const char *name);
  * the device.  Blocks until done. */
 int sfb200_factorize(sfb200_plan *p, const double *Lx, const double *Ux, double *Lsx);
 
+/* One process of a multi-process partition: like sfb200_factorize, but the output is only the panels this rank owns, packed back
+ * to back in supernode order ("owned_elems" doubles; sfb200_plan_owned_runs maps the pieces into Lsx) -- a full-size Lsx per
+ * process would cost world times the factor in host memory. */
+int sfb200_factorize_owned(sfb200_plan *p, const double *Lx, const double *Ux, double *packed);
+int sfb200_download_owned(sfb200_plan *p, double *packed);
+/* runs[3k..3k+2] = {offset in the packed buffer, offset in Lsx, elements}; returns the number of runs (runs = NULL: just count) */
+int64_t sfb200_plan_owned_runs(const sfb200_plan *p, int64_t *runs);
+
 /* Device-resident call: values already in HBM (device pointers), factor stays in HBM. Asynchronous on the
  * plan's stream; sfb200_plan_sync() waits. */
 int sfb200_factorize_device(sfb200_plan *p, const double *d_Lx, const double *d_Ux);
 int sfb200_plan_sync(sfb200_plan *p);
 
-/* Run the plan on a caller-owned CUDA stream (cudaStream_t passed as void*) instead of the plan's own one. */
+/* Run the plan on a caller-owned CUDA stream (cudaStream_t passed as void*) instead of the plan's own one.  The stream is
+ * BORROWED: it must outlive the plan or be replaced by another call before it is destroyed. */
 int sfb200_plan_set_stream(sfb200_plan *p, void *cuda_stream);
 
 /* Instrumented replay (CUDA events around every launch) of the last factorization's values; per-kernel totals are
@@ -141,7 +172,8 @@ double sfb200_plan_profile_get(const sfb200_plan *p, int kind, int what);
 /* per launch i of the schedule: out[8] = {kind, level, grid, ops, ms, algorithmic flops, max K, min K} */
 int sfb200_plan_profile_launch(const sfb200_plan *p, int i, double *out);
 
-/* Copy the device-resident factor into the reference's host layout (xsize doubles). */
+/* Copy the device-resident factor into the reference's host layout (Lsx = the whole array of xsize doubles; a rank of a
+ * partitioned plan writes only the panels it owns). */
 int sfb200_download_factor(sfb200_plan *p, double *Lsx);
 
 /* ---- consumers of the device-resident factor ---------------------------------------------------------

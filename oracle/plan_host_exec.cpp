@@ -77,8 +77,10 @@ void trsm(double *X, const TrsmOp &t) {
     }
 }
 
-// one op; B = tile size of its launch (tiles matter only when the op is shared between ranks: tile_mod > 1)
-void gemm(double *X, const GemmOp &g, const HostPlan &P, int B = 128) {
+// one op; B = tile size of its launch (tiles matter only when the op is shared between ranks: tile_mod > 1).
+// img[r] = image of rank r: a scattered entry goes into the image of the rank its upd_coloff names (the peer-memory adds of
+// the GPU kernels); X = this rank's own image.
+void gemm(double *X, double *const *img, const GemmOp &g, const HostPlan &P, int B = 128) {
     const double *A = X + g.a_off, *Bm = X + g.b_off;
     const bool lower = (g.flags & G_LOWER) != 0;
     const i64 ntile = gemm_tiles(g.M, g.N, B, lower);
@@ -88,9 +90,11 @@ void gemm(double *X, const GemmOp &g, const HostPlan &P, int B = 128) {
         for (int j = tj * B; j < std::min(g.N, (tj + 1) * B); ++j) {
             int lim = 0;
             i64 col = 0, relbase = 0;
+            double *D = X;
             if (g.flags & G_SCATTER) {
                 const i64 q = g.meta + j;
-                col = P.upd_coloff[q];
+                col = P.upd_coloff[q] & kOffsetMask;
+                D = img[P.upd_coloff[q] >> kOwnerShift];
                 relbase = P.upd_relbase[q];
                 lim = (g.flags & G_LIM_SEGB) ? P.upd_segb[q] : (g.flags & G_LIM_SEGE) ? P.upd_sege[q] : j;
                 if (g.flags & G_LIM_SEGE) col += P.upd_uoff[q];
@@ -104,14 +108,14 @@ void gemm(double *X, const GemmOp &g, const HostPlan &P, int B = 128) {
                     const double b = (g.flags & G_B_KMAJOR) ? Bm[k + (i64)j * g.ldb] : Bm[j + (i64)k * g.ldb];
                     acc += A[i + (i64)k * g.lda] * b;
                 }
-                if (g.flags & G_SCATTER) X[col + P.relmap[relbase + i]] -= acc;
+                if (g.flags & G_SCATTER) D[col + P.relmap[relbase + i]] -= acc;
                 else X[g.c_off + i + (i64)j * g.ldc] -= acc;
             }
         }
     }
 }
 
-int small_front(double *X, const HostPlan &P, i64 s) {
+int small_front(double *X, double *const *img, const HostPlan &P, i64 s) {
     const SnodeDev &d = P.snode[s];
     const int n = d.nscol, R = d.nsrow, m = R - n;
     double *A = X + d.xoff;
@@ -130,7 +134,7 @@ int small_front(double *X, const HostPlan &P, i64 s) {
         }
         if (m > 0) {
             g.a_off = g.b_off = d.xoff + n; g.flags = G_LOWER | G_SCATTER;
-            gemm(X, g, P);
+            gemm(X, img, g, P);
         }
     } else {
         const int rows = R + m;      // L11\U11, L21, U12^T
@@ -146,9 +150,9 @@ int small_front(double *X, const HostPlan &P, i64 s) {
         }
         if (m > 0) {
             g.a_off = d.xoff + n; g.b_off = d.xoff + R; g.flags = G_SCATTER | G_LIM_SEGB;
-            gemm(X, g, P);
+            gemm(X, img, g, P);
             g.a_off = d.xoff + R; g.b_off = d.xoff + n; g.flags = G_SCATTER | G_LIM_SEGE;
-            gemm(X, g, P);
+            gemm(X, img, g, P);
         }
     }
     return 0;
@@ -171,11 +175,11 @@ void assemble(const CheckHandle &h, double *X) {
     }
 }
 
-long run_one(const HostPlan &P, double *X, const Launch &L) {
+long run_one(const HostPlan &P, double *X, double *const *img, const Launch &L) {
     long bad = 0;
     switch (L.kind) {
         case L_SMALL_A: case L_SMALL_B:
-            for (int k = 0; k < L.count; ++k) bad += small_front(X, P, P.small_tasks[L.first + k]);
+            for (int k = 0; k < L.count; ++k) bad += small_front(X, img, P, P.small_tasks[L.first + k]);
             break;
         case L_POTRF:
             for (int k = 0; k < L.count; ++k) { const DiagOp &d = P.diag_ops[L.first + k]; diag_pending_update(X, d, false); bad += diag_cholesky(X + d.a_off, d.ld, d.nb); }
@@ -194,7 +198,7 @@ long run_one(const HostPlan &P, double *X, const Launch &L) {
                 const GemmOp &g = P.gemm_ops[L.first + k];
                 if (g.tile0 != tiles) return -101;
                 tiles += share_of_tiles(gemm_tiles(g.M, g.N, B, (g.flags & G_LOWER) != 0), g.tile_mod, g.tile_rem);
-                gemm(X, g, P, B);
+                gemm(X, img, g, P, B);
             }
             if (tiles != L.grid) return -102;
             break;
@@ -209,12 +213,12 @@ long run_one(const HostPlan &P, double *X, const Launch &L) {
  * up to the next LF_WAIT_DIAG launch.  The default order here is
  * "immediately"; SFCHECK_SIDE_LATE=1 runs them as LATE as that contract allows, so that a side launch that overlaps
  * something the main stream does in between shows up as a wrong factor in the CPU test tier. */
-long run_launches(const HostPlan &P, double *X, int first, int count) {
+long run_launches(const HostPlan &P, double *X, double *const *img, int first, int count) {
     const bool late = getenv("SFCHECK_SIDE_LATE") != nullptr;
     std::vector<int> deferred, deferred_diag;
     long bad = 0;
     auto flush = [&](std::vector<int> &q) -> long {
-        for (int li : q) { const long b = run_one(P, X, P.launches[li]); if (b < 0) return b; bad += b; }
+        for (int li : q) { const long b = run_one(P, X, img, P.launches[li]); if (b < 0) return b; bad += b; }
         q.clear();
         return 0;
     };
@@ -224,7 +228,7 @@ long run_launches(const HostPlan &P, double *X, int first, int count) {
         if (late && (L.flags & LF_DIAG_AHEAD)) { deferred_diag.push_back(li); continue; }
         if (L.flags & LF_WAIT_SIDE) { const long b = flush(deferred); if (b < 0) return b; }
         if (L.flags & LF_WAIT_DIAG) { const long b = flush(deferred_diag); if (b < 0) return b; }
-        const long b = run_one(P, X, L);
+        const long b = run_one(P, X, img, L);
         if (b < 0) return b;
         bad += b;
     }
@@ -319,21 +323,44 @@ void sfcheck_segment(void *hv, int k, long *out) {
     const Segment &sg = ((CheckHandle *)hv)->P.segments[k];
     out[0] = sg.coll_first; out[1] = sg.coll_count; out[2] = sg.launch_first; out[3] = sg.launch_count; out[4] = sg.level;
 }
-/* out[6] = {type, offset, count, root, lo, hi} */
-void sfcheck_coll(void *hv, int i, long *out) {
-    const Coll &c = ((CheckHandle *)hv)->P.colls[i];
-    out[0] = c.type; out[1] = c.offset; out[2] = c.count; out[3] = c.root; out[4] = c.lo; out[5] = c.hi;
+/* out[8] = {type, root, lo, hi, offset in this rank's image, rows, cols, ld}; dst (may be NULL) receives, on the root of a
+ * C_BCAST, the block's offset in the image of every rank lo..hi-1 */
+void sfcheck_coll(void *hv, int i, long *out, long *dst) {
+    const HostPlan &P = ((CheckHandle *)hv)->P;
+    const Coll &c = P.colls[i];
+    out[0] = c.type; out[1] = c.root; out[2] = c.lo; out[3] = c.hi; out[4] = c.offset; out[5] = c.rows; out[6] = c.cols; out[7] = c.ld;
+    if (dst && c.dst_first >= 0) for (int q = 0; q < c.hi - c.lo; ++q) dst[q] = P.coll_dst[c.dst_first + q];
+}
+/* image_elems[r] for r < world: elements of every rank's image (without the rank's private scratch) */
+void sfcheck_image_elems(void *hv, long *out) {
+    const HostPlan &P = ((CheckHandle *)hv)->P;
+    for (int r = 0; r < P.world; ++r) out[r] = P.image_elems[r];
 }
 void sfcheck_owner(void *hv, int *owner) {
     const HostPlan &P = ((CheckHandle *)hv)->P;
     for (i64 s = 0; s < P.nsuper; ++s) owner[s] = P.owner[s];
 }
-/* X: xsize_pad + wsize doubles ("xsize_work"), zeroed by the caller */
+/* X: this rank's image, xsize_pad + wsize doubles ("xsize_work"), zeroed by the caller */
 void sfcheck_begin(void *hv, double *X) { assemble(*(CheckHandle *)hv, X); }
-long sfcheck_run_segment(void *hv, int k, double *X) {
+/* img[r] = base address of rank r's image as THIS process sees it (shared memory between the test's processes, the
+ * stand-in for CUDA IPC mappings); remote update entries are subtracted there directly */
+long sfcheck_run_segment(void *hv, int k, double *const *img) {
     const HostPlan &P = ((CheckHandle *)hv)->P;
     const Segment &sg = P.segments[k];
-    return run_launches(P, X, sg.launch_first, sg.launch_count);
+    return run_launches(P, img[P.rank], img, sg.launch_first, sg.launch_count);
+}
+/* root side of exchange step i (C_BCAST): copy the block from the root's image into every other image of the group */
+long sfcheck_push(void *hv, int i, double *const *img) {
+    const HostPlan &P = ((CheckHandle *)hv)->P;
+    const Coll &c = P.colls[i];
+    if (c.type != C_BCAST || c.root != P.rank || c.dst_first < 0) return -1;
+    for (int q = c.lo; q < c.hi; ++q) {
+        if (q == c.root) continue;
+        const i64 dst = P.coll_dst[c.dst_first + (q - c.lo)];
+        for (int col = 0; col < c.cols; ++col)
+            std::memcpy(img[q] + dst + (i64)col * c.ld, img[c.root] + c.offset + (i64)col * c.ld, sizeof(double) * c.rows);
+    }
+    return 0;
 }
 /* copy only the panels this rank owns into Lsx_out (reference layout); others are left untouched */
 void sfcheck_pack_owned(void *hv, const double *X, double *Lsx_out) {
@@ -400,7 +427,8 @@ long sfcheck_factor_solve(void *hv, double *b) {
     if (P.world != 1) return -1;
     std::vector<double> X(P.xsize_pad + P.wsize, 0.0);
     assemble(h, X.data());
-    const long bad = run_launches(P, X.data(), 0, (int)P.launches.size());
+    double *self = X.data();
+    const long bad = run_launches(P, X.data(), &self, 0, (int)P.launches.size());
     for (const SolveLaunch &L : P.solve_fwd) for (int k = 0; k < L.count; ++k) solve_task(P, P.solve_tasks[L.first + k], L.kind, X.data(), b);
     for (const SolveLaunch &L : P.solve_bwd) for (int k = 0; k < L.count; ++k) solve_task(P, P.solve_tasks[L.first + k], L.kind, X.data(), b);
     return bad;
@@ -427,68 +455,77 @@ long sfcheck_factorize(int kind, int is_symmetric, long n, const long *Cp, const
         if (L.level < last_level) { delete h; return -100; }       // schedule must be level-monotone
         last_level = L.level;
     }
-    const long bad = run_launches(P, X.data(), 0, (int)P.launches.size());
+    double *self = X.data();
+    const long bad = run_launches(P, X.data(), &self, 0, (int)P.launches.size());
     pack(P, X.data(), Lsx_out);
     delete h;
     return bad;
 }
 
-/* All `world` ranks simulated in one process: every rank has its own zeroed image of the padded factor, segments run in
- * lock step, the collectives of a segment act on the images of the ranks of their group.  Lsx_out = union of the owned
- * panels.  balance[r] receives the flops owned by rank r; ncoll_out[3] counts the collectives met by type. */
+/* All `world` ranks simulated in one process: every rank has its own zeroed image (its compact layout), segments run in
+ * lock step -- in rank order, or in reverse rank order with SFCHECK_RANKS_REVERSED=1: the result must not depend on which
+ * rank of a segment runs first -- remote update entries land directly in the destination's image, a C_BCAST copies the
+ * block from the root's image to the group's.  Lsx_out = union of the owned panels.  balance[r] receives the flops owned by
+ * rank r; ncoll_out[2] counts the exchange steps met by type; image_out[r] (may be NULL) the elements of rank r's image. */
 long sfcheck_factorize_partitioned(int kind, int is_symmetric, long n, const long *Cp, const long *Ci, const double *Cx,
                                    unsigned long long dev_slot, int nb, int outer, int small_a, int small_b, int world,
-                                   double *Lsx_out, double *balance, long *ncoll_out) {
+                                   double *Lsx_out, double *balance, long *ncoll_out, long *image_out) {
     std::vector<CheckHandle *> H(world);
     for (int r = 0; r < world; ++r) {
         H[r] = (CheckHandle *)sfcheck_open(kind, is_symmetric, n, Cp, Ci, Cx, dev_slot, nb, outer, small_a, small_b, 0, r, world);
         if (!H[r]) return -1;
     }
-    const i64 xp = H[0]->P.xsize_pad;
     std::vector<std::vector<double>> X(world);
-    for (int r = 0; r < world; ++r) X[r].assign(xp + H[r]->P.wsize, 0.0);   // image, then the rank's own scratch
+    std::vector<double *> img(world);
+    for (int r = 0; r < world; ++r) {
+        // every rank computes every rank's layout: they must agree
+        for (int q = 0; q < world; ++q) if (H[r]->P.image_elems[q] != H[q]->P.xsize_pad) return -197;
+        X[r].assign(H[r]->P.xsize_pad + H[r]->P.wsize, 0.0);     // image, then the rank's own scratch
+        img[r] = X[r].data();
+        if (image_out) image_out[r] = H[r]->P.xsize_pad;
+    }
     for (int r = 0; r < world; ++r) { assemble(*H[r], X[r].data()); if (balance) balance[r] = H[r]->P.local_flops; }
-    long bad = 0, ncoll[3] = {0, 0, 0};
+    long bad = 0, ncoll[2] = {0, 0};
     const size_t nseg = H[0]->P.segments.size();
     for (int r = 1; r < world; ++r)
         if (H[r]->P.segments.size() != nseg || H[r]->P.colls.size() != H[0]->P.colls.size()) return -199;
-    std::vector<double> sum;
+    const bool reversed = getenv("SFCHECK_RANKS_REVERSED") != nullptr;
     for (size_t k = 0; k < nseg; ++k) {
         const Segment &sg = H[0]->P.segments[k];
         for (int i = sg.coll_first; i < sg.coll_first + sg.coll_count; ++i) {
             const Coll &c = H[0]->P.colls[i];
-            // every rank must hold the identical step at the identical position (collectives are matched by order)
+            // every rank must hold the identical step at the identical position (steps are matched by order)
             for (int q = 1; q < world; ++q) {
                 const Coll &cq = H[q]->P.colls[i];
                 const Segment &sq = H[q]->P.segments[k];
                 if (sq.coll_first != sg.coll_first || sq.coll_count != sg.coll_count) return -198;
-                if (cq.type != c.type || cq.offset != c.offset || cq.count != c.count || cq.root != c.root || cq.lo != c.lo || cq.hi != c.hi) return -200;
+                if (cq.type != c.type || cq.root != c.root || cq.lo != c.lo || cq.hi != c.hi || cq.rows != c.rows || cq.cols != c.cols || cq.ld != c.ld) return -200;
             }
             if (c.type == C_BCAST) {
-                for (int q = c.lo; q < c.hi; ++q)
-                    if (q != c.root) std::memcpy(X[q].data() + c.offset, X[c.root].data() + c.offset, sizeof(double) * c.count);
-            } else {
-                // ranks outside [lo,hi) must not have touched the panel
-                for (int q = 0; q < world; ++q)
-                    if (q < c.lo || q >= c.hi)
-                        for (i64 e = 0; e < c.count; ++e) if (X[q][c.offset + e] != 0.0) return -201;
-                sum.assign(X[c.root].begin() + c.offset, X[c.root].begin() + c.offset + c.count);
-                for (int q = c.lo; q < c.hi; ++q)
-                    if (q != c.root) for (i64 e = 0; e < c.count; ++e) sum[e] += X[q][c.offset + e];
-                for (int q = c.lo; q < c.hi; ++q)
-                    if (q == c.root || c.type == C_ALLREDUCE) std::memcpy(X[q].data() + c.offset, sum.data(), sizeof(double) * c.count);
+                const HostPlan &R = H[c.root]->P;
+                const Coll &cr = R.colls[i];
+                if (cr.dst_first < 0 || cr.offset < 0) return -202;
+                for (int q = c.lo; q < c.hi; ++q) {
+                    // the root's idea of where the block lives in q's image is q's own idea
+                    if (R.coll_dst[cr.dst_first + (q - c.lo)] != H[q]->P.colls[i].offset) return -203;
+                    if (q == c.root) continue;
+                    for (int col = 0; col < c.cols; ++col)
+                        std::memcpy(img[q] + H[q]->P.colls[i].offset + (i64)col * c.ld, img[c.root] + cr.offset + (i64)col * c.ld, sizeof(double) * c.rows);
+                }
+                for (int q = 0; q < world; ++q) if ((q < c.lo || q >= c.hi) && H[q]->P.colls[i].offset != -1) return -204;
             }
             ++ncoll[c.type];
         }
-        for (int r = 0; r < world; ++r) {
+        for (int rr = 0; rr < world; ++rr) {
+            const int r = reversed ? world - 1 - rr : rr;
             const Segment &sr = H[r]->P.segments[k];
-            const long b = run_launches(H[r]->P, X[r].data(), sr.launch_first, sr.launch_count);
+            const long b = run_launches(H[r]->P, X[r].data(), img.data(), sr.launch_first, sr.launch_count);
             if (b < 0) return b;
             bad += b;
         }
     }
     for (int r = 0; r < world; ++r) sfcheck_pack_owned(H[r], X[r].data(), Lsx_out);
-    if (ncoll_out) for (int t = 0; t < 3; ++t) ncoll_out[t] = ncoll[t];
+    if (ncoll_out) for (int t = 0; t < 2; ++t) ncoll_out[t] = ncoll[t];
     for (auto *h : H) delete h;
     return bad;
 }

@@ -119,7 +119,10 @@ struct Checker {
             decode_tile(t, g.M, g.N, B, lower, ti, tj);
             for (int j = tj * B; j < std::min(g.N, (tj + 1) * B); ++j) {
                 const i64 q = g.meta + j;
-                i64 col = P.upd_coloff[q];
+                // adds into another rank's image are ordered by the exchange steps (the group barrier in front of the target's
+                // level), not by this rank's streams: this checker covers one rank's image
+                if ((int)(P.upd_coloff[q] >> kOwnerShift) != P.rank) continue;
+                i64 col = P.upd_coloff[q] & kOffsetMask;
                 const i64 relbase = P.upd_relbase[q];
                 int lim = (g.flags & G_LIM_SEGB) ? P.upd_segb[q] : (g.flags & G_LIM_SEGE) ? P.upd_sege[q] : j;
                 if (g.flags & G_LIM_SEGE) col += P.upd_uoff[q];

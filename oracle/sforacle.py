@@ -117,12 +117,17 @@ def plan_check(kind, A_n, Cp, Ci, Cx, symmetric, devslot, nb=0, outer=0, small_a
 
 
 class CheckBackend:
-    """One rank of a `world`-way etree partition executed by the CPU plan interpreter (oracle/plan_host_exec.cpp).
-    Same backend protocol as sparseframe_b200.parallel.DeviceBackend, so that the multi-rank orchestration can be
-    tested with gloo on a box without GPUs."""
+    """One rank of a `world`-way etree partition executed by the CPU plan interpreter (oracle/plan_host_exec.cpp), behind
+    the backend protocol of sparseframe_b200.parallel (exchange_handle / connect / factorize / finish) so that the
+    multi-rank host logic can be tested with gloo on a box without GPUs.
 
-    def __init__(self, kind, A, devslot, rank, world, nb=0, outer=0, small_a=-1, small_b=-1):
-        import torch
+    Stand-ins for the device mechanisms: the rank's image lives in a POSIX shared-memory segment (CUDA IPC mapping: the
+    128-byte exchange handle carries the segment's name), remote update entries are subtracted directly in the peer's
+    segment (red.global.add over NVLink), a pushed block is copied into the peers' segments (peer copies), and every
+    flag wait is a gloo barrier of the step's group -- stricter than the pairwise flags, never weaker."""
+
+    def __init__(self, kind, A, devslot, rank, world, nb=0, outer=0, small_a=-1, small_b=-1, dist=None):
+        from multiprocessing import shared_memory
         global _chk
         if _chk is None:
             _chk = C.CDLL(os.path.join(_HERE, "_ref", "libsfcheck.so"))
@@ -133,33 +138,48 @@ class CheckBackend:
         L.sfcheck_int.argtypes = [C.c_void_p, C.c_char_p]
         L.sfcheck_double.restype = C.c_double
         L.sfcheck_double.argtypes = [C.c_void_p, C.c_char_p]
-        for f in ("sfcheck_segment", "sfcheck_coll"):
-            getattr(L, f).argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        L.sfcheck_segment.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        L.sfcheck_coll.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        L.sfcheck_image_elems.argtypes = [C.c_void_p, C.c_void_p]
         L.sfcheck_owner.argtypes = [C.c_void_p, C.c_void_p]
         L.sfcheck_begin.argtypes = [C.c_void_p, C.c_void_p]
         L.sfcheck_run_segment.restype = C.c_long
         L.sfcheck_run_segment.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        L.sfcheck_push.restype = C.c_long
+        L.sfcheck_push.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         L.sfcheck_pack_owned.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.sfcheck_close.argtypes = [C.c_void_p]
         self.L = L
         self.A = A
+        self.dist = dist
         self.h = L.sfcheck_open(int(kind in (1, "lu")), int(A.symmetric), A.n, A.Cp.ctypes.data, A.Ci.ctypes.data,
                                 A.Cx.ctypes.data, int(devslot), nb, outer, small_a, small_b, 0, rank, world)
         if not self.h:
             raise RuntimeError("sfcheck_open failed")
         self.rank, self.world = rank, world
-        self.X = np.zeros(self.int("xsize_work"))      # factor image, then this rank's scratch area
-        self.image = torch.from_numpy(self.X)[:self.int("xsize_pad")]          # shares memory with X
+        elems = max(self.int("xsize_work"), 1)          # factor image, then this rank's scratch area
+        self.shm = shared_memory.SharedMemory(create=True, size=8 * elems)
+        self.X = np.ndarray((elems,), dtype=np.float64, buffer=self.shm.buf)
+        self.X[:] = 0.0
+        self.peers_shm = [None] * world
+        self.img = (C.c_void_p * world)()
+        self.img[rank] = self.X.ctypes.data
+        self.connected = world == 1
         self.bad = 0
+        self.pushed_bytes = 0
+        self.groups = {}
 
-        def info(fn, k, n):
+        def info(fn, k, n, *extra):
             out = np.zeros(n, dtype=np.int64)
-            fn(self.h, k, out.ctypes.data)
+            fn(self.h, k, out.ctypes.data, *extra)
             return [int(v) for v in out]
         self.segments = [dict(zip(("coll_first", "coll_count", "launch_first", "launch_count", "level"),
                                   info(L.sfcheck_segment, k, 5))) for k in range(self.int("nsegments"))]
-        self.colls = [dict(zip(("type", "offset", "count", "root", "lo", "hi"), info(L.sfcheck_coll, i, 6)))
+        self.colls = [dict(zip(("type", "root", "lo", "hi", "offset", "rows", "cols", "ld"), info(L.sfcheck_coll, i, 8, None)))
                       for i in range(self.int("ncolls"))]
+        image_elems = np.zeros(world, dtype=np.int64)
+        L.sfcheck_image_elems(self.h, image_elems.ctypes.data)
+        self.image_elems = [int(v) for v in image_elems]
 
     def int(self, name):
         return int(self.L.sfcheck_int(self.h, name.encode()))
@@ -172,13 +192,54 @@ class CheckBackend:
         self.L.sfcheck_owner(self.h, out.ctypes.data)
         return out
 
-    def begin(self):
+    # ---- backend protocol of sparseframe_b200.parallel ------------------------------------------------------------
+    def exchange_handle(self) -> bytes:
+        return self.shm.name.encode().ljust(128, b"\0")
+
+    def connect(self, handles: bytes):
+        from multiprocessing import shared_memory
+        for q in range(self.world):
+            if q == self.rank:
+                continue
+            name = handles[128 * q:128 * (q + 1)].rstrip(b"\0").decode()
+            self.peers_shm[q] = shared_memory.SharedMemory(name=name)
+            view = np.ndarray((self.peers_shm[q].size // 8,), dtype=np.float64, buffer=self.peers_shm[q].buf)
+            self.img[q] = view.ctypes.data
+        if self.dist is not None:
+            # groups must be created by every rank, in the same order (the step list is the same on all ranks)
+            for c in self.colls:
+                key = (c["lo"], c["hi"])
+                if key not in self.groups:
+                    self.groups[key] = None if key == (0, self.world) else self.dist.new_group(ranks=list(range(*key)))
+        self.connected = True
+
+    def _meet(self, c):
+        if self.dist is not None and self.world > 1:
+            self.dist.barrier(group=self.groups[(c["lo"], c["hi"])])
+
+    def factorize(self):
+        assert self.connected
         self.X[:] = 0.0
         self.bad = 0
+        self.pushed_bytes = 0
         self.L.sfcheck_begin(self.h, self.X.ctypes.data)
-
-    def run_segment(self, k):
-        self.bad += self.L.sfcheck_run_segment(self.h, k, self.X.ctypes.data)
+        for k, sg in enumerate(self.segments):
+            for i in range(sg["coll_first"], sg["coll_first"] + sg["coll_count"]):
+                c = self.colls[i]
+                if not (c["lo"] <= self.rank < c["hi"]):
+                    continue
+                if c["type"] == 0:                       # barrier: the group's remote adds are in place
+                    self._meet(c)
+                else:                                    # push: root copies the block into the group's images, then flags
+                    if c["root"] == self.rank:
+                        assert self.L.sfcheck_push(self.h, i, self.img) == 0
+                        self.pushed_bytes += 8 * c["rows"] * c["cols"] * (c["hi"] - c["lo"] - 1)
+                    self._meet(c)
+            self.bad += self.L.sfcheck_run_segment(self.h, k, self.img)
+        # the device side needs no closing step (every remote write is followed by a flag its target waits for); the
+        # processes of the test must not unmap their segments while a slower peer still works in them
+        if self.dist is not None and self.world > 1:
+            self.dist.barrier()
 
     def finish(self):
         pass
@@ -192,3 +253,15 @@ class CheckBackend:
         if self.h:
             self.L.sfcheck_close(self.h)
             self.h = None
+        self.X = None
+        for q, m in enumerate(self.peers_shm):
+            if m is not None:
+                m.close()
+        self.peers_shm = []
+        if self.shm is not None:
+            self.shm.close()
+            try:
+                self.shm.unlink()
+            except FileNotFoundError:
+                pass
+            self.shm = None

@@ -8,6 +8,7 @@
 #include <map>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <tuple>
 #include <vector>
 
@@ -82,6 +83,28 @@ struct sfb200_plan {
     std::vector<std::vector<std::pair<i64, i64>>> small_runs;
     int merge_level = 0;
     int top_width = 256;                               // width of the widest blocking level
+    // ---- partitioned plans (world > 1): exchange over peer memory, see plan_types.h (Coll) ---------------------------
+    struct CollSync { std::vector<std::pair<int, unsigned>> sig, wait; };   // (peer, sequence number) lists of one step
+    std::vector<CollSync> coll_sync;
+    std::vector<double *> peer_img;                    // image of every rank as this device addresses it
+    std::vector<unsigned long long *> peer_flags;      // flag array of every rank
+    double **d_peer = nullptr;                         // device copies of the two tables
+    unsigned long long **d_peer_flags = nullptr;
+    unsigned long long *d_flags = nullptr;             // this rank's flags: [2][kMaxWorld] signal values, then the epoch counter
+    unsigned long long *d_epoch = nullptr;
+    std::vector<void *> ipc_mapped;                    // mappings opened with cudaIpcOpenMemHandle
+    bool connected = false;
+    cudaStream_t comm_stream = nullptr;                // pushes of factored panels / block columns to the group
+    cudaEvent_t ev_to_comm = nullptr, ev_from_comm = nullptr;
+    bool comm_pending = false;
+    int push_mode = 0;                                 // 0: copy engines (cudaMemcpy2DAsync to the peer mapping), 1: k_push on the SMs
+    unsigned long long peer_timeout_ns = 30ull * 1000000000ull;
+    // copy-out of the panels this rank owns: packed (reference layout, owned panels back to back) in d_out, then one
+    // device-to-host copy per run of consecutive owned supernodes
+    struct OutRun { i64 packed, lsx, count; };
+    std::vector<OutRun> out_runs;
+    i64 out_elems = 0;
+    int n_pack = 0;
     size_t device_bytes = 0;
     float ms_numeric = 0.f, ms_e2e = 0.f;
     int64_t launches = 0;
@@ -120,6 +143,25 @@ int upload(sfb200_plan *p, T *&dptr, const std::vector<T> &h) {
     p->device_bytes += h.size() * sizeof(T);
     CK(cudaMemcpyAsync(dptr, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice, p->stream));
     return SFB200_OK;
+}
+
+int upload_peer_tables(sfb200_plan *p) {
+    CK(cudaMemcpyAsync(p->d_peer, p->peer_img.data(), sizeof(double *) * p->peer_img.size(), cudaMemcpyHostToDevice, p->stream));
+    CK(cudaMemcpyAsync(p->d_peer_flags, p->peer_flags.data(), sizeof(unsigned long long *) * p->peer_flags.size(), cudaMemcpyHostToDevice, p->stream));
+    CK(cudaStreamSynchronize(p->stream));
+    return SFB200_OK;
+}
+
+SyncArgs sync_args(const sfb200_plan *p, int chan, const std::vector<std::pair<int, unsigned>> &list, size_t first, size_t count) {
+    SyncArgs a{};
+    a.peer_flags = p->d_peer_flags;
+    a.my_flags = p->d_flags;
+    a.epoch = p->d_epoch;
+    a.me = p->H.rank;
+    a.n = (int)count;
+    a.chan = chan;
+    for (size_t k = 0; k < count; ++k) { a.peer[k] = list[first + k].first; a.seq[k] = list[first + k].second; }
+    return a;
 }
 
 int issue_launch_on(sfb200_plan *p, const Launch &L, cudaStream_t st, int spare_sms) {
@@ -213,6 +255,45 @@ int run_launches(sfb200_plan *p, size_t first, size_t count) {
     return SFB200_OK;
 }
 
+// One exchange step of a partitioned plan (plan_types.h: Coll), entirely on the device: no host synchronisation, so the
+// whole factorization of a rank -- kernels, pushes, flags -- is one stream-ordered sequence and replays as one CUDA graph.
+int issue_coll(sfb200_plan *p, size_t i) {
+    const HostPlan &H = p->H;
+    const Coll &c = H.colls[i];
+    if (H.rank < c.lo || H.rank >= c.hi) return SFB200_OK;
+    const auto &cs = p->coll_sync[i];
+    if (c.type == C_BARRIER) {
+        // everything this rank has added into its peers' images so far precedes the signal in stream order (side streams
+        // are joined at every segment end)
+        launch_signal(sync_args(p, 0, cs.sig, 0, cs.sig.size()), p->stream);
+        launch_wait(sync_args(p, 0, cs.wait, 0, cs.wait.size()), p->d_status, p->peer_timeout_ns, p->stream);
+        p->launches += 2;
+    } else if (H.rank == c.root) {
+        // the factored block leaves on the push stream; this rank's own next launches do not wait for it
+        CK(cudaEventRecord(p->ev_to_comm, p->stream));
+        CK(cudaStreamWaitEvent(p->comm_stream, p->ev_to_comm, 0));
+        const double *src = p->d_X + c.offset;
+        for (size_t k = 0; k < cs.sig.size(); ++k) {
+            const int q = cs.sig[k].first;
+            double *dst = p->peer_img[q] + H.coll_dst[c.dst_first + (q - c.lo)];
+            if (p->push_mode == 0) {
+                CK(cudaMemcpy2DAsync(dst, sizeof(double) * c.ld, src, sizeof(double) * c.ld, sizeof(double) * c.rows, (size_t)c.cols,
+                                     cudaMemcpyDefault, p->comm_stream));
+            } else {
+                launch_push(src, dst, c.rows, c.cols, c.ld, 32, p->comm_stream);
+                ++p->launches;
+            }
+            launch_signal(sync_args(p, 1, cs.sig, k, 1), p->comm_stream);       // one flag per destination, as soon as its copy is done
+            ++p->launches;
+        }
+        p->comm_pending = true;
+    } else {
+        launch_wait(sync_args(p, 1, cs.wait, 0, cs.wait.size()), p->d_status, p->peer_timeout_ns, p->stream);
+        ++p->launches;
+    }
+    return SFB200_OK;
+}
+
 // Replay `issue` (stream-ordered work on p->stream and the plan's helper streams, joined at the end) through a cached
 // CUDA graph: captured the first time the key is seen, launched afterwards.
 template <class F>
@@ -279,10 +360,38 @@ int run_schedule(sfb200_plan *p) {
     });
 }
 
+// One rank's part of a partitioned factorization: epoch bump, zero + assemble, then segment after segment its exchange
+// steps and launches.  Every rank of the partition must run it (the barriers wait for all of them).
+int run_partitioned(sfb200_plan *p) {
+    p->launches = 0;
+    return run_graphed(p, 4, 0, p->H.segments.size(), nullptr, [&]() -> int {
+        launch_epoch_inc(p->d_epoch, p->stream);
+        int rc = begin_factor(p);
+        if (rc) return rc;
+        ++p->launches;
+        for (const Segment &sg : p->H.segments) {
+            for (int i = sg.coll_first; i < sg.coll_first + sg.coll_count; ++i)
+                if ((rc = issue_coll(p, (size_t)i))) return rc;
+            if ((rc = run_launches(p, (size_t)sg.launch_first, (size_t)sg.launch_count))) return rc;
+        }
+        if (p->comm_pending) {          // the last pushes are on their way before the factorization counts as done
+            CK(cudaEventRecord(p->ev_from_comm, p->comm_stream));
+            CK(cudaStreamWaitEvent(p->stream, p->ev_from_comm, 0));
+            p->comm_pending = false;
+        }
+        return SFB200_OK;
+    });
+}
+
 int check_status(sfb200_plan *p) {
     int status = 0;
     CK(cudaMemcpyAsync(&status, p->d_status, sizeof(int), cudaMemcpyDeviceToHost, p->stream));
     CK(cudaStreamSynchronize(p->stream));
+    if (status & 4) {
+        p->factored = false;
+        set_error("a rank of the partition did not reach an exchange step in time (peer flag timeout)");
+        return SFB200_ERR_STATE;
+    }
     if (status & 1) {
         p->factored = false;          // the image holds NaNs / garbage: solve and download refuse it
         set_error("non-positive (Cholesky) or zero (LU) pivot met");
@@ -319,6 +428,13 @@ void sfb200_plan_free(sfb200_plan *p) {
     if (p->ev_to_side) cudaEventDestroy(p->ev_to_side);
     if (p->ev_from_side) cudaEventDestroy(p->ev_from_side);
     if (p->side_stream) cudaStreamDestroy(p->side_stream);
+    for (void *m : p->ipc_mapped) cudaIpcCloseMemHandle(m);
+    if (p->d_peer) cudaFree(p->d_peer);
+    if (p->d_peer_flags) cudaFree(p->d_peer_flags);
+    if (p->d_flags) cudaFree(p->d_flags);
+    if (p->ev_to_comm) cudaEventDestroy(p->ev_to_comm);
+    if (p->ev_from_comm) cudaEventDestroy(p->ev_from_comm);
+    if (p->comm_stream) cudaStreamDestroy(p->comm_stream);
     for (auto &kv : p->graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
     if (p->ev_to_diag) cudaEventDestroy(p->ev_to_diag);
     if (p->ev_from_diag) cudaEventDestroy(p->ev_from_diag);
@@ -381,7 +497,31 @@ int sfb200_plan_create_part(const sfb200_symbolic *s, int device, int rank, int 
     if ((err = upload(p, p->d_diag, H.diag_ops))) return fail(err);
     if ((err = upload(p, p->d_trsm, H.trsm_ops))) return fail(err);
     if ((err = upload(p, p->d_gemm, H.gemm_ops))) return fail(err);
-    if ((err = upload(p, p->d_pack, H.pack_tasks))) return fail(err);
+    {   // copy-out of the owned panels: packed back to back in d_out, one host copy per run of consecutive owned supernodes
+        const bool lu_ = H.kind == Kind::LU;
+        std::vector<PackTask> ptasks;
+        i64 packed = 0;
+        for (i64 sidx = 0; sidx < H.nsuper; ++sidx) {
+            if (H.owner[sidx] != H.rank) continue;
+            const SnodeDev &d = H.snode[sidx];
+            const int rows = lu_ ? 2 * d.nsrow - d.nscol : d.nsrow;
+            const i64 elems = (i64)rows * d.nscol;
+            if (!p->out_runs.empty() && p->out_runs.back().lsx + p->out_runs.back().count == H.lsxp[sidx]) p->out_runs.back().count += elems;
+            else p->out_runs.push_back({packed, H.lsxp[sidx], elems});
+            const int chunk = std::max(1, 65536 / std::max(rows, 1));
+            for (int c0 = 0; c0 < d.nscol; c0 += chunk) {
+                PackTask t{};
+                t.src = d.xoff + (i64)c0 * d.ld;
+                t.dst = packed + (i64)c0 * rows;
+                t.rows = rows; t.ld = d.ld; t.cols = std::min(chunk, d.nscol - c0);
+                ptasks.push_back(t);
+            }
+            packed += elems;
+        }
+        p->out_elems = packed;
+        p->n_pack = (int)ptasks.size();
+        if ((err = upload(p, p->d_pack, ptasks))) return fail(err);
+    }
     if ((err = upload(p, p->d_lsi32, H.lsi32))) return fail(err);
     if ((err = upload(p, p->d_nz_col, H.nz_col))) return fail(err);
     if ((err = upload(p, p->d_nz_row, H.nz_row))) return fail(err);
@@ -405,6 +545,49 @@ int sfb200_plan_create_part(const sfb200_symbolic *s, int device, int rank, int 
     if ((err = dmalloc((void **)&p->d_lx, sizeof(double) * (size_t)H.nnz))) return fail(err);
     if (H.split && (err = dmalloc((void **)&p->d_ux, sizeof(double) * (size_t)H.unnz))) return fail(err);
     if ((err = dmalloc((void **)&p->d_status, sizeof(int)))) return fail(err);
+    {   // exchange state: image / flag tables (one entry on a single-GPU plan), flags + epoch counter, push stream
+        p->peer_img.assign(H.world, nullptr);
+        p->peer_flags.assign(H.world, nullptr);
+        if ((err = dmalloc((void **)&p->d_flags, sizeof(unsigned long long) * (kFlagSlots + 1)))) return fail(err);
+        if ((err = dmalloc((void **)&p->d_peer, sizeof(double *) * H.world))) return fail(err);
+        if ((err = dmalloc((void **)&p->d_peer_flags, sizeof(unsigned long long *) * H.world))) return fail(err);
+        if (cudaMemsetAsync(p->d_flags, 0, sizeof(unsigned long long) * (kFlagSlots + 1), p->stream) != cudaSuccess) { set_error("flags"); return fail(SFB200_ERR_CUDA); }
+        p->d_epoch = p->d_flags + kFlagSlots;
+        p->peer_img[H.rank] = p->d_X;
+        p->peer_flags[H.rank] = p->d_flags;
+        if ((err = upload_peer_tables(p))) return fail(err);
+        p->connected = H.world == 1;
+        if (H.world > 1) {
+            if (H.world > kMaxWorld) { set_error("at most 16 ranks"); return fail(SFB200_ERR_ARG); }
+            if (cudaStreamCreateWithFlags(&p->comm_stream, cudaStreamNonBlocking) != cudaSuccess ||
+                cudaEventCreateWithFlags(&p->ev_to_comm, cudaEventDisableTiming) != cudaSuccess ||
+                cudaEventCreateWithFlags(&p->ev_from_comm, cudaEventDisableTiming) != cudaSuccess) { set_error("push stream"); return fail(SFB200_ERR_CUDA); }
+            if (const char *e = getenv("SFB200_PUSH")) p->push_mode = (std::string(e) == "sm") ? 1 : 0;
+            if (const char *e = getenv("SFB200_PEER_TIMEOUT_S")) p->peer_timeout_ns = (unsigned long long)(atof(e) * 1e9);
+            // sequence numbers: both ends of a (signaller, waiter) pair walk the same step list and count the signals of
+            // that pair, so the n-th signal from rank a to rank b is "n" on both sides without any communication
+            // (counted per channel: barriers and pushes are signalled from different streams, see kernels.cuh)
+            std::vector<unsigned> sent(H.world, 0), recv(H.world, 0), psent(H.world, 0), precv(H.world, 0);
+            p->coll_sync.resize(H.colls.size());
+            for (size_t i = 0; i < H.colls.size(); ++i) {
+                const Coll &c = H.colls[i];
+                if (H.rank < c.lo || H.rank >= c.hi) continue;
+                auto &cs = p->coll_sync[i];
+                if (c.type == C_BARRIER) {
+                    for (int q = c.lo; q < c.hi; ++q)
+                        if (q != H.rank) { cs.sig.push_back({q, ++sent[q]}); cs.wait.push_back({q, ++recv[q]}); }
+                } else if (H.rank == c.root) {
+                    // the owner of the next block column first: it is the one the factorization chain waits for
+                    for (int k = 1; k < c.hi - c.lo; ++k) {
+                        const int q = c.lo + (c.root - c.lo + k) % (c.hi - c.lo);
+                        cs.sig.push_back({q, ++psent[q]});
+                    }
+                } else {
+                    cs.wait.push_back({c.root, ++precv[c.root]});
+                }
+            }
+        }
+    }
     if (prm.leaf_lookahead) {
         if (const char *e = getenv("SFB200_LEAVE_SMS")) p->leave_sms = atoi(e);
         int lo_prio = 0, hi_prio = 0;
@@ -419,7 +602,7 @@ int sfb200_plan_create_part(const sfb200_symbolic *s, int device, int rank, int 
         p->top_width = prm.outer2 > 0 ? prm.outer2 : prm.outer;
         p->big_by_level.assign(H.nlevels, {});
         std::vector<std::vector<PackTask>> small(H.nlevels);
-        for (i64 sidx = 0; sidx < H.nsuper; ++sidx) {
+        for (i64 sidx = 0; sidx < H.nsuper && H.world == 1; ++sidx) {      // streamed copy-out: single-GPU plans
             const SnodeDev &d = H.snode[sidx];
             const int rows = lu ? 2 * d.nsrow - d.nscol : d.nsrow;
             if ((i64)rows * d.nscol * 8 >= (1 << 20)) { p->big_by_level[d.level].push_back(sidx); continue; }
@@ -438,7 +621,7 @@ int sfb200_plan_create_part(const sfb200_symbolic *s, int device, int rank, int 
             flat.insert(flat.end(), small[l].begin(), small[l].end());
         }
         if ((err = upload(p, p->d_spack, flat))) return fail(err);
-        {
+        if (H.world == 1) {
             // Flush point: every level up to `merge_level` leaves in one batch when that level is final.  Each run costs
             // one copy call (a few microseconds of host time during which no kernel is enqueued), and the leaf-side levels
             // interleave in the postorder -- cfg2: 18 246 runs if every level flushes on its own, 467 when levels 0..5 go
@@ -485,6 +668,7 @@ int sfb200_plan_create_part(const sfb200_symbolic *s, int device, int rank, int 
     }
     if (cudaStreamSynchronize(p->stream) != cudaSuccess) { set_error("plan upload failed"); return fail(SFB200_ERR_CUDA); }
     p->D.X = p->d_X;
+    p->D.peer = p->d_peer;
     p->D.snode = p->d_snode;
     p->D.upd_coloff = p->d_coloff;
     p->D.upd_relbase = p->d_relbase;
@@ -525,6 +709,9 @@ int64_t sfb200_plan_int(const sfb200_plan *p, const char *name) {
     if (k == "ncolls") return (int64_t)H.colls.size();
     if (k == "rank") return H.rank;
     if (k == "world") return H.world;
+    if (k == "connected") return p->connected;
+    if (k == "owned_elems") return p->out_elems;
+    if (k == "sms") return p->sms;
     if (k == "nsuper") return H.nsuper;
     return -1;
 }
@@ -534,6 +721,12 @@ double sfb200_plan_double(const sfb200_plan *p, const char *name) {
     const std::string k(name);
     if (k == "flops") return p->H.flops;
     if (k == "local_flops") return p->H.local_flops;
+    if (k == "remote_update_bytes") return 8.0 * p->H.remote_update_entries;      // payload this rank adds into peer images
+    if (k == "push_bytes") {            // factored blocks this rank pushes to its groups, per factorization
+        double b = 0.0;
+        for (const Coll &c : p->H.colls) if (c.type == C_BCAST && c.root == p->H.rank) b += 8.0 * c.rows * (double)c.cols * (c.hi - c.lo - 1);
+        return b;
+    }
     return -1.0;
 }
 
@@ -547,7 +740,7 @@ int sfb200_plan_segment_info(const sfb200_plan *p, int k, int64_t *out) {
 int sfb200_plan_coll_info(const sfb200_plan *p, int i, int64_t *out) {
     if (!p || !out || i < 0 || i >= (int)p->H.colls.size()) return SFB200_ERR_ARG;
     const Coll &c = p->H.colls[i];
-    out[0] = c.type; out[1] = c.offset; out[2] = c.count; out[3] = c.root; out[4] = c.lo; out[5] = c.hi;
+    out[0] = c.type; out[1] = c.root; out[2] = c.lo; out[3] = c.hi; out[4] = c.offset; out[5] = c.rows; out[6] = c.cols; out[7] = c.ld;
     return SFB200_OK;
 }
 
@@ -562,36 +755,7 @@ void *sfb200_plan_factor_ptr(sfb200_plan *p) { return p ? (void *)p->d_X : nullp
 int sfb200_plan_panel_offsets(const sfb200_plan *p, int64_t *xoff) {
     if (!p || !xoff) return SFB200_ERR_ARG;
     for (i64 s = 0; s < p->H.nsuper; ++s) xoff[s] = p->H.snode[s].xoff;
-    xoff[p->H.nsuper] = p->H.xsize_pad;
-    return SFB200_OK;
-}
-
-int sfb200_partition_begin(sfb200_plan *p, const double *d_Lx, const double *d_Ux) {
-    if (!p || !d_Lx) { set_error("sfb200_partition_begin: bad argument"); return SFB200_ERR_ARG; }
-    CK(cudaSetDevice(p->device));
-    const HostPlan &H = p->H;
-    CK(cudaEventRecord(p->ev[0], p->stream));
-    if (d_Lx != p->d_lx) CK(cudaMemcpyAsync(p->d_lx, d_Lx, sizeof(double) * (size_t)H.nnz, cudaMemcpyDeviceToDevice, p->stream));
-    if (H.split) {
-        if (!d_Ux) { set_error("unsymmetric LU needs Ux"); return SFB200_ERR_ARG; }
-        if (d_Ux != p->d_ux) CK(cudaMemcpyAsync(p->d_ux, d_Ux, sizeof(double) * (size_t)H.unnz, cudaMemcpyDeviceToDevice, p->stream));
-    }
-    return begin_factor(p);
-}
-
-int sfb200_segment_run(sfb200_plan *p, int k) {
-    if (!p || k < 0 || k >= (int)p->H.segments.size()) { set_error("sfb200_segment_run: bad segment"); return SFB200_ERR_ARG; }
-    CK(cudaSetDevice(p->device));
-    const Segment &sg = p->H.segments[k];
-    if (sg.launch_count > 0) {
-        const int rc = run_graphed(p, 2, (size_t)sg.launch_first, (size_t)sg.launch_count, nullptr,
-                                   [&]() -> int { return run_launches(p, (size_t)sg.launch_first, (size_t)sg.launch_count); });
-        if (rc) return rc;
-    }
-    if (k + 1 == (int)p->H.segments.size()) {
-        CK(cudaEventRecord(p->ev[1], p->stream));
-        p->factored = true;
-    }
+    xoff[p->H.nsuper] = p->H.xsize_pad;      /* elements of this rank's image; panels it does not store are -1 */
     return SFB200_OK;
 }
 
@@ -605,7 +769,11 @@ int sfb200_factorize_device(sfb200_plan *p, const double *d_Lx, const double *d_
         if (!d_Ux) { set_error("unsymmetric LU needs Ux"); return SFB200_ERR_ARG; }
         if (d_Ux != p->d_ux) CK(cudaMemcpyAsync(p->d_ux, d_Ux, sizeof(double) * (size_t)H.unnz, cudaMemcpyDeviceToDevice, p->stream));
     }
-    const int rc = run_schedule(p);
+    if (H.world > 1 && !p->connected) {
+        set_error("sfb200_factorize_device: this rank of a partitioned plan is not connected to its peers (sfb200_plan_connect / sfb200_group_create)");
+        return SFB200_ERR_STATE;
+    }
+    const int rc = H.world > 1 ? run_partitioned(p) : run_schedule(p);
     if (rc) return rc;
     CK(cudaEventRecord(p->ev[1], p->stream));
     p->factored = true;
@@ -622,20 +790,48 @@ int sfb200_plan_sync(sfb200_plan *p) {
     return rc;
 }
 
-int sfb200_download_factor(sfb200_plan *p, double *Lsx) {
-    if (!p || !Lsx) { set_error("sfb200_download_factor: bad argument"); return SFB200_ERR_ARG; }
+static int ensure_out(sfb200_plan *p) {
+    if (p->d_out) return SFB200_OK;
+    CK(cudaMalloc((void **)&p->d_out, sizeof(double) * (size_t)std::max<i64>(p->out_elems, 1)));
+    p->device_bytes += sizeof(double) * (size_t)p->out_elems;
+    return SFB200_OK;
+}
+
+/* The panels this rank owns (all of them on a single-GPU plan) into the reference's layout: Lsx is the WHOLE factor array
+ * (xsize doubles); a rank of a partitioned plan writes its own panels and leaves the rest alone. */
+static int download(sfb200_plan *p, double *out, bool packed) {
+    if (!p || !out) { set_error("sfb200_download_factor: bad argument"); return SFB200_ERR_ARG; }
     if (!p->factored) { set_error("sfb200_download_factor: nothing factorized yet"); return SFB200_ERR_STATE; }
     CK(cudaSetDevice(p->device));
-    const HostPlan &H = p->H;
-    if (!p->d_out) {
-        CK(cudaMalloc((void **)&p->d_out, sizeof(double) * (size_t)std::max<i64>(H.xsize, 1)));
-        p->device_bytes += sizeof(double) * (size_t)H.xsize;
-    }
-    launch_pack(p->d_X, p->d_out, p->d_pack, (int)H.pack_tasks.size(), p->stream);
+    int rc = ensure_out(p);
+    if (rc) return rc;
+    launch_pack(p->d_X, p->d_out, p->d_pack, p->n_pack, p->stream);
     CK(cudaGetLastError());
-    CK(cudaMemcpyAsync(Lsx, p->d_out, sizeof(double) * (size_t)H.xsize, cudaMemcpyDeviceToHost, p->stream));
+    if (packed) {
+        CK(cudaMemcpyAsync(out, p->d_out, sizeof(double) * (size_t)p->out_elems, cudaMemcpyDeviceToHost, p->stream));
+    } else {
+        for (const auto &run : p->out_runs)
+            CK(cudaMemcpyAsync(out + run.lsx, p->d_out + run.packed, sizeof(double) * (size_t)run.count, cudaMemcpyDeviceToHost, p->stream));
+    }
     CK(cudaStreamSynchronize(p->stream));
     return SFB200_OK;
+}
+
+int sfb200_download_factor(sfb200_plan *p, double *Lsx) { return download(p, Lsx, false); }
+
+/* The panels this rank owns, back to back in supernode order ("owned_elems" doubles): what one process of a multi-process
+ * partition brings home.  sfb200_plan_owned_runs lists where the pieces belong in the reference's Lsx. */
+int sfb200_download_owned(sfb200_plan *p, double *packed) { return download(p, packed, true); }
+
+/* runs[3 * k .. 3 * k + 2] = {offset in the packed buffer, offset in Lsx, elements}; returns the number of runs (call with
+ * runs = NULL to size the array) */
+int64_t sfb200_plan_owned_runs(const sfb200_plan *p, int64_t *runs) {
+    if (!p) return -1;
+    if (runs)
+        for (size_t k = 0; k < p->out_runs.size(); ++k) {
+            runs[3 * k] = p->out_runs[k].packed; runs[3 * k + 1] = p->out_runs[k].lsx; runs[3 * k + 2] = p->out_runs[k].count;
+        }
+    return (int64_t)p->out_runs.size();
 }
 
 namespace {
@@ -740,10 +936,7 @@ int factorize_streamed_issue(sfb200_plan *p, double *Lsx, bool trace) {
 // CUDA graph per destination buffer from the second call on.
 int factorize_streamed(sfb200_plan *p, double *Lsx) {
     const HostPlan &H = p->H;
-    if (!p->d_out) {
-        CK(cudaMalloc((void **)&p->d_out, sizeof(double) * (size_t)std::max<i64>(H.xsize, 1)));
-        p->device_bytes += sizeof(double) * (size_t)H.xsize;
-    }
+    { const int rco = ensure_out(p); if (rco) return rco; }
     const bool trace = getenv("SFB200_COPY_TRACE") != nullptr;
     p->launches = 0;
     int rc;
@@ -756,15 +949,14 @@ int factorize_streamed(sfb200_plan *p, double *Lsx) {
 
 }  // namespace
 
-int sfb200_factorize(sfb200_plan *p, const double *Lx, const double *Ux, double *Lsx) {
+static int factorize_host(sfb200_plan *p, const double *Lx, const double *Ux, double *Lsx, bool packed) {
     if (!p || !Lx) { set_error("sfb200_factorize: bad argument"); return SFB200_ERR_ARG; }
     CK(cudaSetDevice(p->device));
     const HostPlan &H = p->H;
     if (H.split && !Ux) { set_error("unsymmetric LU needs Ux"); return SFB200_ERR_ARG; }
-    if (H.world > 1) { set_error("sfb200_factorize: partitioned plans are driven segment by segment (sfb200_segment_run)"); return SFB200_ERR_STATE; }
     // page-locked destination -> stream the copy-out behind the factorization; pageable -> pack + one copy at the end
     double *alias = nullptr;
-    if (Lsx && !getenv("SFB200_NO_STREAMED_COPY")) {
+    if (Lsx && H.world == 1 && !packed && !getenv("SFB200_NO_STREAMED_COPY")) {
         cudaPointerAttributes attr;
         if (cudaPointerGetAttributes(&attr, Lsx) == cudaSuccess && attr.type == cudaMemoryTypeHost && attr.devicePointer)
             alias = (double *)attr.devicePointer;
@@ -783,7 +975,7 @@ int sfb200_factorize(sfb200_plan *p, const double *Lx, const double *Ux, double 
         rc = sfb200_factorize_device(p, p->d_lx, p->d_ux);
         if (rc) return rc;
         if (Lsx) {
-            rc = sfb200_download_factor(p, Lsx);
+            rc = download(p, Lsx, packed);
             if (rc) return rc;
         }
     }
@@ -794,6 +986,12 @@ int sfb200_factorize(sfb200_plan *p, const double *Lx, const double *Ux, double 
     else cudaGetLastError();
     return rc;
 }
+
+int sfb200_factorize(sfb200_plan *p, const double *Lx, const double *Ux, double *Lsx) { return factorize_host(p, Lx, Ux, Lsx, false); }
+
+/* Same call for one process of a multi-process partition: the output is this rank's owned panels, packed
+ * (sfb200_download_owned); a full-size Lsx per process would be world times the factor in host memory. */
+int sfb200_factorize_owned(sfb200_plan *p, const double *Lx, const double *Ux, double *packed) { return factorize_host(p, Lx, Ux, packed, true); }
 
 int sfb200_plan_set_stream(sfb200_plan *p, void *cuda_stream) {
     if (!p) return SFB200_ERR_ARG;
@@ -1001,6 +1199,159 @@ void *sfb200_host_alloc(size_t bytes) {
     return ptr;
 }
 void sfb200_host_free(void *ptr) { if (ptr) cudaFreeHost(ptr); }
+
+/* ---- partitioned plans: connecting the ranks (peer memory) ------------------------------------------------------------- */
+namespace {
+int set_peers(sfb200_plan *p, const std::vector<double *> &images, const std::vector<unsigned long long *> &flags) {
+    const HostPlan &H = p->H;
+    for (int q = 0; q < H.world; ++q) {
+        if (q == H.rank) continue;
+        if (!images[q] || !flags[q]) { set_error("sfb200_plan_connect: missing peer mapping"); return SFB200_ERR_ARG; }
+        p->peer_img[q] = images[q];
+        p->peer_flags[q] = flags[q];
+    }
+    const int rc = upload_peer_tables(p);
+    if (rc) return rc;
+    p->connected = true;
+    return SFB200_OK;
+}
+}  // namespace
+
+int sfb200_plan_exchange_handle(sfb200_plan *p, void *out) {
+    if (!p || !out) { set_error("sfb200_plan_exchange_handle: bad argument"); return SFB200_ERR_ARG; }
+    CK(cudaSetDevice(p->device));
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle layout");
+    cudaIpcMemHandle_t h[2];
+    CK(cudaIpcGetMemHandle(&h[0], p->d_X));
+    CK(cudaIpcGetMemHandle(&h[1], p->d_flags));
+    memcpy(out, h, sizeof(h));
+    return SFB200_OK;
+}
+
+int sfb200_plan_connect(sfb200_plan *p, const void *handles) {
+    if (!p || !handles) { set_error("sfb200_plan_connect: bad argument"); return SFB200_ERR_ARG; }
+    CK(cudaSetDevice(p->device));
+    const HostPlan &H = p->H;
+    std::vector<double *> images(H.world, nullptr);
+    std::vector<unsigned long long *> flags(H.world, nullptr);
+    const cudaIpcMemHandle_t *h = (const cudaIpcMemHandle_t *)handles;
+    for (int q = 0; q < H.world; ++q) {
+        if (q == H.rank) continue;
+        void *a = nullptr, *b = nullptr;
+        CK(cudaIpcOpenMemHandle(&a, h[2 * q], cudaIpcMemLazyEnablePeerAccess));
+        p->ipc_mapped.push_back(a);
+        CK(cudaIpcOpenMemHandle(&b, h[2 * q + 1], cudaIpcMemLazyEnablePeerAccess));
+        p->ipc_mapped.push_back(b);
+        images[q] = (double *)a;
+        flags[q] = (unsigned long long *)b;
+    }
+    return set_peers(p, images, flags);
+}
+
+struct sfb200_group {
+    std::vector<sfb200_plan *> plans;
+};
+
+/* All ranks of a partition inside one process, one device per rank (the reference's arrangement: one host thread per GPU
+ * inside SparseFrame_factorize_supernodal, CH.c:2267-2290).  devices[r] may repeat: several ranks on one GPU exchange
+ * through the same mechanism (used by the one-GPU tests). */
+int sfb200_group_create(const sfb200_symbolic *s, int world, const int *devices, sfb200_group **out) {
+    if (!s || !out || world < 1 || world > kMaxWorld || !devices) { set_error("sfb200_group_create: bad argument"); return SFB200_ERR_ARG; }
+    auto *g = new sfb200_group();
+    g->plans.assign(world, nullptr);
+    std::vector<int> rcs(world, SFB200_OK);
+    std::vector<std::string> errs(world);
+    {
+        std::vector<std::thread> th;
+        for (int r = 0; r < world; ++r)
+            th.emplace_back([&, r]() {
+                rcs[r] = sfb200_plan_create_part(s, devices[r], r, world, &g->plans[r]);
+                if (rcs[r]) errs[r] = sfb200_last_error();
+            });
+        for (auto &t : th) t.join();
+    }
+    for (int r = 0; r < world; ++r)
+        if (rcs[r]) { set_error(errs[r]); const int rc = rcs[r]; sfb200_group_free(g); return rc; }
+    auto fail = [&](int rc) { sfb200_group_free(g); return rc; };
+    for (int a = 0; a < world; ++a)
+        for (int b = 0; b < world; ++b) {
+            if (devices[a] == devices[b]) continue;
+            int can = 0;
+            if (cudaDeviceCanAccessPeer(&can, devices[a], devices[b]) != cudaSuccess || !can) {
+                set_error("sfb200_group_create: no peer access between devices " + std::to_string(devices[a]) + " and " + std::to_string(devices[b]));
+                return fail(SFB200_ERR_CUDA);
+            }
+            cudaSetDevice(devices[a]);
+            const cudaError_t e = cudaDeviceEnablePeerAccess(devices[b], 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { set_error(std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(e)); return fail(SFB200_ERR_CUDA); }
+            cudaGetLastError();
+        }
+    std::vector<double *> images(world);
+    std::vector<unsigned long long *> flags(world);
+    for (int r = 0; r < world; ++r) { images[r] = g->plans[r]->d_X; flags[r] = g->plans[r]->d_flags; }
+    for (int r = 0; r < world; ++r) {
+        cudaSetDevice(devices[r]);
+        const int rc = set_peers(g->plans[r], images, flags);
+        if (rc) return fail(rc);
+    }
+    *out = g;
+    return SFB200_OK;
+}
+
+int sfb200_group_size(const sfb200_group *g) { return g ? (int)g->plans.size() : 0; }
+sfb200_plan *sfb200_group_plan(sfb200_group *g, int rank) { return (g && rank >= 0 && rank < (int)g->plans.size()) ? g->plans[rank] : nullptr; }
+
+/* Host-buffer factorization by the whole group: one host thread per rank uploads the values, runs its part and writes the
+ * panels it owns into Lsx (may be NULL: factor stays on the devices).  Returns the first non-zero status. */
+int sfb200_group_factorize(sfb200_group *g, const double *Lx, const double *Ux, double *Lsx) {
+    if (!g || !Lx) { set_error("sfb200_group_factorize: bad argument"); return SFB200_ERR_ARG; }
+    const int world = (int)g->plans.size();
+    std::vector<int> rcs(world, SFB200_OK);
+    std::vector<std::string> errs(world);
+    std::vector<std::thread> th;
+    for (int r = 0; r < world; ++r)
+        th.emplace_back([&, r]() {
+            rcs[r] = sfb200_factorize(g->plans[r], Lx, Ux, Lsx);
+            if (rcs[r]) errs[r] = sfb200_last_error();
+        });
+    for (auto &t : th) t.join();
+    for (int r = 0; r < world; ++r)
+        if (rcs[r]) { set_error("rank " + std::to_string(r) + ": " + errs[r]); return rcs[r]; }
+    return SFB200_OK;
+}
+
+/* numeric time of the last factorization: the slowest rank (which = 0) / including the copies (which = 1) */
+double sfb200_group_last_ms(const sfb200_group *g, int which) {
+    double ms = -1.0;
+    if (g) for (const sfb200_plan *p : g->plans) ms = std::max(ms, sfb200_last_ms(p, which));
+    return ms;
+}
+
+void sfb200_group_free(sfb200_group *g) {
+    if (!g) return;
+    for (sfb200_plan *p : g->plans) sfb200_plan_free(p);
+    delete g;
+}
+
+/* The caller has filled this (single-GPU) plan's image -- sfb200_plan_factor_ptr, panel offsets from
+ * sfb200_plan_panel_offsets -- with a complete factor of the matrix whose values are d_Lx / d_Ux, e.g. gathered from the
+ * ranks of a partitioned factorization: from here on sfb200_solve / sfb200_residual / sfb200_download_factor use it. */
+int sfb200_plan_adopt_factor(sfb200_plan *p, const double *d_Lx, const double *d_Ux) {
+    if (!p || !d_Lx) { set_error("sfb200_plan_adopt_factor: bad argument"); return SFB200_ERR_ARG; }
+    if (p->H.world != 1) { set_error("sfb200_plan_adopt_factor: single-GPU plans only"); return SFB200_ERR_STATE; }
+    CK(cudaSetDevice(p->device));
+    const HostPlan &H = p->H;
+    if (d_Lx != p->d_lx) CK(cudaMemcpyAsync(p->d_lx, d_Lx, sizeof(double) * (size_t)H.nnz, cudaMemcpyDeviceToDevice, p->stream));
+    if (H.split) {
+        if (!d_Ux) { set_error("unsymmetric LU needs Ux"); return SFB200_ERR_ARG; }
+        if (d_Ux != p->d_ux) CK(cudaMemcpyAsync(p->d_ux, d_Ux, sizeof(double) * (size_t)H.unnz, cudaMemcpyDeviceToDevice, p->stream));
+    }
+    CK(cudaMemsetAsync(p->d_status, 0, sizeof(int), p->stream));
+    CK(cudaEventRecord(p->ev[0], p->stream));
+    CK(cudaEventRecord(p->ev[1], p->stream));
+    p->factored = true;
+    return SFB200_OK;
+}
 
 /* FP64 pipe probes for the roofline denominators: returns TFLOP/s.  which = 0 DFMA (vector pipe), 1 DMMA (tensor pipe) */
 double sfb200_probe_fp64_peak(int device, int which, int iters) {

@@ -160,7 +160,9 @@ __device__ __forceinline__ void smem_scatter(const PlanDev &P, const double *Sa,
             const int j = j0 + b;
             if (j >= m) break;
             const int64_t q = meta + j;
-            int64_t col = P.upd_coloff[q];
+            const int64_t tgt = P.upd_coloff[q];                  // (destination rank << 56) | offset in its image
+            int64_t col = tgt & kOffsetMask;
+            double *img = P.peer[tgt >> kOwnerShift];
             const int64_t relb = P.upd_relbase[q];
             int lim = j;
             if (mode == 1) lim = P.upd_segb[q];
@@ -168,7 +170,7 @@ __device__ __forceinline__ void smem_scatter(const PlanDev &P, const double *Sa,
 #pragma unroll
             for (int a = 0; a < 4; ++a) {
                 const int i = i0 + a;
-                if (i < m && i >= lim) atomicAdd(P.X + col + P.relmap[relb + i], -acc[a][b]);
+                if (i < m && i >= lim) atomicAdd(img + col + P.relmap[relb + i], -acc[a][b]);
             }
         }
     }
@@ -636,12 +638,13 @@ __global__ void __launch_bounds__(WARPS_M *WARPS_N * 32)
             const int c = col0 + wn0 + 8 * j + g;
             if (c >= N) continue;
             const int64_t q = op.meta + c;
-            int64_t col = P.upd_coloff[q];
+            const int64_t tgt = P.upd_coloff[q];                  // (destination rank << 56) | offset in its image
+            int64_t col = tgt & kOffsetMask;
             const int64_t relb = P.upd_relbase[q];
             int lim = c;
             if (op.flags & G_LIM_SEGB) lim = P.upd_segb[q];
             if (op.flags & G_LIM_SEGE) { lim = P.upd_sege[q]; col += P.upd_uoff[q]; }
-            double *dst = P.X + col;
+            double *dst = P.peer[tgt >> kOwnerShift] + col;       // possibly another GPU's memory: the add travels over NVLink
             const int32_t *rel = P.relmap + relb;
 #pragma unroll
             for (int i = 0; i < FM; ++i) {
@@ -945,12 +948,13 @@ __global__ void __launch_bounds__(ws::NT, 1) k_gemm_ws(PlanDev P, const GemmOp *
                 const int c = col0 + wn0 + 8 * j + g;
                 if (c >= N) continue;
                 const int64_t q = op.meta + c;
-                int64_t col = P.upd_coloff[q];
+                const int64_t tgt = P.upd_coloff[q];                  // (destination rank << 56) | offset in its image
+                int64_t col = tgt & kOffsetMask;
                 const int64_t relb = P.upd_relbase[q];
                 int lim = c;
                 if (op.flags & G_LIM_SEGB) lim = P.upd_segb[q];
                 if (op.flags & G_LIM_SEGE) { lim = P.upd_sege[q]; col += P.upd_uoff[q]; }
-                double *dst = P.X + col;
+                double *dst = P.peer[tgt >> kOwnerShift] + col;       // possibly another GPU's memory: the add travels over NVLink
                 const int32_t *rel = P.relmap + relb;
 #pragma unroll
                 for (int i = 0; i < FM; ++i) {
@@ -1300,6 +1304,56 @@ __global__ void __launch_bounds__(256) k_peak_dmma_tile(double *out, int iters, 
     out[blockIdx.x * blockDim.x + tid] = s;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Exchange steps of a partitioned factorization (plan_types.h: Coll): flags in peer memory, one warp each.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void k_epoch_inc(unsigned long long *epoch) { *epoch += 1; }
+
+// Everything this rank has issued before (kernels whose epilogues added into peer images, peer copies) is complete
+// when this kernel starts (stream order); the fence orders those writes before the flag as seen from the peer.
+__global__ void k_signal(SyncArgs a) {
+    const int t = threadIdx.x;
+    if (t >= a.n) return;
+    __threadfence_system();
+    const unsigned long long v = *a.epoch * kEpochStride + a.seq[t];
+    unsigned long long *dst = a.peer_flags[a.peer[t]] + a.chan * kMaxWorld + a.me;
+    asm volatile("st.release.sys.global.u64 [%0], %1;\n" ::"l"(dst), "l"(v) : "memory");
+}
+
+__global__ void k_wait(SyncArgs a, int *status, unsigned long long timeout_ns) {
+    const int t = threadIdx.x;
+    if (t >= a.n) return;
+    const unsigned long long want = *a.epoch * kEpochStride + a.seq[t];
+    const unsigned long long *src = a.my_flags + a.chan * kMaxWorld + a.peer[t];
+    unsigned long long t0, now, v;
+    asm volatile("mov.u64 %0, %%globaltimer;\n" : "=l"(t0));
+    while (true) {
+        asm volatile("ld.acquire.sys.global.u64 %0, [%1];\n" : "=l"(v) : "l"(src) : "memory");
+        if (v >= want) break;
+        asm volatile("mov.u64 %0, %%globaltimer;\n" : "=l"(now));
+        if (now - t0 > timeout_ns) { atomicOr(status, 4); break; }      // a peer never arrived: report, do not hang the device
+        __nanosleep(200);
+    }
+    __threadfence_system();
+}
+
+// rows x cols block, column stride ld, local image -> peer image.  16-byte accesses when both sides allow it.
+__global__ void __launch_bounds__(256) k_push(const double *__restrict__ src, double *__restrict__ dst, int rows, int cols, int ld) {
+    const bool vec = (((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0) && (ld & 1) == 0;
+    const int rv = vec ? rows >> 1 : 0;                      // double2 per column
+    const int64_t nvec = (int64_t)rv * cols, nthr = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nvec; i += nthr) {
+        const int c = (int)(i / rv), r = (int)(i - (int64_t)c * rv) << 1;
+        *reinterpret_cast<double2 *>(dst + (int64_t)c * ld + r) = *reinterpret_cast<const double2 *>(src + (int64_t)c * ld + r);
+    }
+    const int tail = rows - 2 * rv;                          // scalar rest of every column
+    const int64_t nrest = (int64_t)tail * cols;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nrest; i += nthr) {
+        const int c = (int)(i / tail), r = 2 * rv + (int)(i - (int64_t)c * tail);
+        dst[(int64_t)c * ld + r] = src[(int64_t)c * ld + r];
+    }
+}
+
 }  // namespace
 
 // =================================================================================================================
@@ -1374,6 +1428,18 @@ void launch_gemm_ws(const PlanDev &P, const GemmOp *ops, int count, int tiles, i
     const int avail = use_sms > 8 ? use_sms : 8;      // look-ahead launches leave a few SMs to the critical path
     const int grid = tiles < avail ? tiles : avail;      // persistent: one CTA per SM walks the tile list
     k_gemm_ws<<<grid, ws::NT, ws::SMEM_BYTES, st>>>(P, ops, count, tiles);
+}
+
+void launch_epoch_inc(unsigned long long *epoch, cudaStream_t st) { k_epoch_inc<<<1, 1, 0, st>>>(epoch); }
+void launch_signal(const SyncArgs &a, cudaStream_t st) {
+    if (a.n > 0) k_signal<<<1, 32, 0, st>>>(a);
+}
+void launch_wait(const SyncArgs &a, int *status, unsigned long long timeout_ns, cudaStream_t st) {
+    if (a.n > 0) k_wait<<<1, 32, 0, st>>>(a, status, timeout_ns);
+}
+void launch_push(const double *src, double *dst, int rows, int cols, int ld, int ctas, cudaStream_t st) {
+    if (rows <= 0 || cols <= 0) return;
+    k_push<<<ctas > 0 ? ctas : 1, 256, 0, st>>>(src, dst, rows, cols, ld);
 }
 
 void launch_pack(const double *X, double *out, const PackTask *tasks, int count, cudaStream_t st) {

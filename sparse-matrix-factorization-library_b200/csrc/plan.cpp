@@ -175,7 +175,6 @@ int build_plan(const Symbolic &S, const PlanParams &prm, HostPlan &P, int rank, 
     // ---- panels, levels -------------------------------------------------------------------------------------
     P.snode.resize(ns);
     std::vector<i64> sparent(ns, -1);
-    i64 xo = 0;
     for (i64 s = 0; s < ns; ++s) {
         SnodeDev &d = P.snode[s];
         d.nscol = (int32_t)(S.Super[s + 1] - S.Super[s]);
@@ -183,15 +182,13 @@ int build_plan(const Symbolic &S, const PlanParams &prm, HostPlan &P, int rank, 
         d.lsip = S.Lsip[s];
         const i64 rows = lu ? 2 * (i64)d.nsrow - d.nscol : d.nsrow;
         d.ld = (int32_t)round_up(rows, prm.ld_align);
-        d.xoff = xo;
+        d.xoff = -1;               // assigned below, once it is known which panels this rank stores
         d.level = 0;
-        xo += (i64)d.ld * d.nscol;
         if (d.nscol < d.nsrow) sparent[s] = S.SuperMap[S.Lsi[S.Lsip[s] + d.nscol]];
         const double c = d.nscol, m = d.nsrow - d.nscol;
         P.flops += lu ? 2.0 * c * c * c / 3.0 + 2.0 * m * c * c + 2.0 * m * m * c
                       : c * c * c / 3.0 + m * c * c + m * (m + 1.0) * c;
     }
-    P.xsize_pad = xo;
     int maxlev = 0;
     for (i64 s = 0; s < ns; ++s) {     // parents have larger indices (postordered)
         const i64 p = sparent[s];
@@ -278,6 +275,43 @@ int build_plan(const Symbolic &S, const PlanParams &prm, HostPlan &P, int rank, 
     }
     auto mine = [&](i64 s) { return P.owner[s] == rank; };
 
+    // ---- which shared fronts the group works on together, and where every rank keeps what --------------------------------
+    // dist_panel : a wide shared Cholesky front is factorized by its whole group: `outer`-wide block columns are owned
+    //              round-robin (block_owner), every update aimed at a block column goes straight to that rank's image,
+    //              each factored block column is pushed to the group
+    // dist_update: the Schur update of a shared front with enough off-diagonal rows is split over the group (1/G of the
+    //              tiles each); needs the factored panel in every image of the group
+    // A rank STORES the panels it owns and the dist_panel / dist_update fronts of the groups it belongs to; its image holds
+    // them back to back in supernode order.  All ranks compute all layouts (they are needed to aim remote updates).
+    const int Wd = prm.outer;
+    std::vector<char> dist_panel_of(ns, 0), dist_update_of(ns, 0);
+    for (i64 s = 0; s < ns; ++s) {
+        const SnodeDev &d = P.snode[s];
+        const bool shared = P.group_hi[s] - P.group_lo[s] > 1;
+        dist_panel_of[s] = shared && !lu && d.nscol >= prm.dist_panel_min_cols;
+        dist_update_of[s] = shared && d.nsrow - d.nscol >= prm.dist_scatter_min_m;
+    }
+    auto block_owner = [&](i64 s, int b) { return P.group_lo[s] + b % (P.group_hi[s] - P.group_lo[s]); };
+    // destination of column c of supernode t: the rank whose image accumulates it (and assembles its matrix entries)
+    auto dest_rank = [&](i64 t, i64 c) { return dist_panel_of[t] ? block_owner(t, (int)(c / Wd)) : P.owner[t]; };
+    auto stores = [&](int r, i64 s) {
+        return P.owner[s] == r || ((dist_panel_of[s] || dist_update_of[s]) && r >= P.group_lo[s] && r < P.group_hi[s]);
+    };
+    std::vector<std::vector<i64>> xoffs(world, std::vector<i64>(ns, -1));
+    P.image_elems.assign(world, 0);
+    for (int r = 0; r < world; ++r) {
+        i64 xo = 0;
+        for (i64 s = 0; s < ns; ++s) {
+            if (!stores(r, s)) continue;
+            xoffs[r][s] = xo;
+            xo += (i64)P.snode[s].ld * P.snode[s].nscol;
+        }
+        P.image_elems[r] = xo;
+        if (xo > kOffsetMask) return 2;
+    }
+    for (i64 s = 0; s < ns; ++s) P.snode[s].xoff = xoffs[rank][s];
+    P.xsize_pad = P.image_elems[rank];
+
     // ---- ancestor segments and relative-index tables -----------------------------------------------------------
     struct Seg { i64 d; int32_t b, e; i64 rel_off; };
     std::vector<std::vector<Seg>> incoming(ns);
@@ -299,7 +333,16 @@ int build_plan(const Symbolic &S, const PlanParams &prm, HostPlan &P, int rank, 
             const SnodeDev &st = P.snode[t];
             for (int j = b; j < e; ++j) {
                 const i64 q = sd.lsip + sd.nscol + j;
-                P.upd_coloff[q] = st.xoff + (rows[j] - S.Super[t]) * (i64)st.ld;
+                const i64 tc = rows[j] - S.Super[t];
+                const int dst = dest_rank(t, tc);
+                P.upd_coloff[q] = ((i64)dst << kOwnerShift) | (xoffs[dst][t] + tc * (i64)st.ld);
+                if (dst != rank) {        // entries of d's update this rank sends over NVLink (its share of d's update tiles)
+                    const double cnt = lu ? (double)(m - b) + (double)(m - e) : (double)(m - j);
+                    double share = 0.0;
+                    if (dist_update_of[d]) { if (rank >= P.group_lo[d] && rank < P.group_hi[d]) share = 1.0 / (P.group_hi[d] - P.group_lo[d]); }
+                    else if (P.owner[d] == rank) share = 1.0;
+                    P.remote_update_entries += cnt * share;
+                }
                 P.upd_relbase[q] = rel_total - b;
                 P.upd_segb[q] = b;
                 P.upd_sege[q] = e;
@@ -335,7 +378,7 @@ int build_plan(const Symbolic &S, const PlanParams &prm, HostPlan &P, int rank, 
         }
         for (i64 j = S.Super[t]; j < S.Super[t + 1]; ++j) {
             const i64 cj = j - S.Super[t];
-            if (!mine(t)) {       // another rank assembles this panel: here it only collects partial updates
+            if (dest_rank(t, cj) != rank) {       // another rank assembles (and accumulates) this column
                 for (i64 p = S.L.ptr[j]; p < S.L.ptr[j + 1]; ++p) P.asm_dst_l[p] = -1;
                 if (lu) for (i64 p = Usrc.ptr[j]; p < Usrc.ptr[j + 1]; ++p) P.asm_dst_u[p] = -1;
                 continue;
@@ -379,7 +422,26 @@ int build_plan(const Symbolic &S, const PlanParams &prm, HostPlan &P, int rank, 
     int top_stride = 2 + 1;
     for (size_t d = 1; d < widths.size(); ++d) top_stride = (widths[d] / widths[d - 1]) * top_stride + 1;
     const std::vector<int> dist_widths = {prm.nb, prm.outer};       // blocking inside group-factorized panels
-    const int Wd = prm.outer;
+    // a rows x cols block of supernode s starting at panel element (r0, c0): root's copy goes to the images of [lo,hi)
+    auto make_bcast = [&](i64 s, int root, int r0, int c0, int rows, int cols) {
+        const SnodeDev &d = P.snode[s];
+        const int lo = P.group_lo[s], hi = P.group_hi[s];
+        const i64 rel = r0 + (i64)c0 * d.ld;
+        Coll c{};
+        c.type = C_BCAST; c.root = root; c.lo = lo; c.hi = hi;
+        c.offset = (rank >= lo && rank < hi) ? xoffs[rank][s] + rel : -1;
+        c.rows = rows; c.cols = cols; c.ld = d.ld; c.dst_first = -1;
+        if (rank == root) {
+            c.dst_first = (int32_t)P.coll_dst.size();
+            for (int q = lo; q < hi; ++q) P.coll_dst.push_back(xoffs[q][s] + rel);
+        }
+        return c;
+    };
+    auto make_barrier = [&](int lo, int hi) {
+        Coll c{};
+        c.type = C_BARRIER; c.root = lo; c.lo = lo; c.hi = hi; c.offset = -1; c.dst_first = -1;
+        return c;
+    };
 
     const int min_k128 = prm.gemm128_min_k >= 0 ? prm.gemm128_min_k : (world == 1 ? 257 : 0);
     for (int lev = 0; lev < P.nlevels; ++lev) {
@@ -482,20 +544,36 @@ int build_plan(const Symbolic &S, const PlanParams &prm, HostPlan &P, int rank, 
         std::vector<GemmOp> scatter_dist;           // this rank's share of the Schur updates of shared fronts
         std::vector<Coll> panel_bcasts;             // factored shared panels, owner -> group (before the shared updates)
         std::vector<i64> dist_panels;               // shared fronts factorized by their whole group
+        if (world > 1) {
+            // first step of a factorization: nobody adds into a peer's image before that peer has zeroed and assembled it
+            if (lev == 0) P.colls.push_back(make_barrier(0, world));
+            // the shared fronts of this level are about to be factorized: the ranks of each group meet first -- everything
+            // they have aimed at those fronts (remote adds of all lower levels) is then in place.  One barrier per distinct
+            // group; a group inside another one of this level is covered by it.
+            std::vector<std::pair<int, int>> groups;
+            for (i64 s : by_level[lev]) {
+                const std::pair<int, int> g{P.group_lo[s], P.group_hi[s]};
+                if (g.second - g.first > 1 && std::find(groups.begin(), groups.end(), g) == groups.end()) groups.push_back(g);
+            }
+            for (size_t a = 0; a < groups.size(); ++a) {
+                bool covered = lev == 0;             // the start barrier already spans everybody
+                for (size_t b = 0; b < groups.size() && !covered; ++b)
+                    covered = b != a && groups[b].first <= groups[a].first && groups[a].second <= groups[b].second &&
+                              (groups[b] != groups[a]);
+                if (!covered) P.colls.push_back(make_barrier(groups[a].first, groups[a].second));
+            }
+        }
         for (i64 s : by_level[lev]) {
             const SnodeDev &d = P.snode[s];
             const int m = d.nsrow - d.nscol;
             const int glo = P.group_lo[s], ghi = P.group_hi[s];
-            const bool shared = ghi - glo > 1;
             const bool in_group = rank >= glo && rank < ghi;
-            const i64 panel_elems = (i64)d.ld * d.nscol;
-            // (1) a wide shared Cholesky front is factorized by its whole group: every rank gets the summed panel
-            //     (all-reduce), block columns are owned round-robin, each one is broadcast once it is factorized
-            const bool dist_panel = shared && !lu && d.nscol >= prm.dist_panel_min_cols;
-            // (2) Schur update of a shared front: every rank of the group computes 1/G of the update tiles into its own
-            //     image of the ancestors (summed later anyway); needs the factored panel everywhere
-            const bool dist_update = shared && m >= prm.dist_scatter_min_m;
-            if (shared) P.colls.push_back(Coll{d.xoff, panel_elems, dist_panel ? C_ALLREDUCE : C_REDUCE, P.owner[s], glo, ghi});
+            // (1) a wide shared Cholesky front is factorized by its whole group: block columns are owned round-robin and
+            //     collect their updates directly, each one is pushed to the group once it is factorized
+            const bool dist_panel = dist_panel_of[s] != 0;
+            // (2) Schur update of a shared front: every rank of the group computes 1/G of the update tiles and adds them
+            //     straight into the images of the ancestors' owners; needs the factored panel in every image of the group
+            const bool dist_update = dist_update_of[s] != 0;
             auto scatter_ops = [&](std::vector<GemmOp> &out, int mod, int rem) {
                 if (m <= 0) return;
                 GemmOp g{};
@@ -516,7 +594,8 @@ int build_plan(const Symbolic &S, const PlanParams &prm, HostPlan &P, int rank, 
                 }
             };
             if (dist_update) {
-                if (!dist_panel) panel_bcasts.push_back(Coll{d.xoff, panel_elems, C_BCAST, P.owner[s], glo, ghi});
+                // the group only reads the rows below the diagonal block (L21; LU: L21 and U12^T)
+                if (!dist_panel) panel_bcasts.push_back(make_bcast(s, P.owner[s], d.nscol, 0, (lu ? 2 * d.nsrow - d.nscol : d.nsrow) - d.nscol, d.nscol));
                 if (in_group) scatter_ops(scatter_dist, ghi - glo, rank - glo);
             }
             if (dist_panel) {
@@ -568,7 +647,6 @@ int build_plan(const Symbolic &S, const PlanParams &prm, HostPlan &P, int rank, 
         if (!dist_panels.empty()) {
             int nsteps = 0;
             for (i64 s : dist_panels) nsteps = std::max(nsteps, (P.snode[s].nscol + Wd - 1) / Wd);
-            auto block_owner = [&](i64 s, int b) { return P.group_lo[s] + b % (P.group_hi[s] - P.group_lo[s]); };
             auto factor_block = [&](int b) {         // F(b): diag / trsm / inner updates of block column b, on its owner
                 std::map<int, SlotOps> fs;
                 for (i64 s : dist_panels) {
@@ -592,7 +670,8 @@ int build_plan(const Symbolic &S, const PlanParams &prm, HostPlan &P, int rank, 
                 for (i64 s : dist_panels) {
                     const SnodeDev &d = P.snode[s];
                     const int b0 = b * Wd, b1 = std::min(b0 + Wd, (int)d.nscol);
-                    if (b0 < d.nscol) P.colls.push_back(Coll{d.xoff + (i64)b0 * d.ld, (i64)(b1 - b0) * d.ld, C_BCAST, block_owner(s, b), P.group_lo[s], P.group_hi[s]});
+                    // rows above the block column's diagonal block are structurally zero: they stay home
+                    if (b0 < d.nscol) P.colls.push_back(make_bcast(s, block_owner(s, b), b0, b0, d.nsrow - b0, b1 - b0));
                 }
                 if (!deferred.empty()) { emit_gemm(deferred, -1, 0); deferred.clear(); }
                 // ... every rank applies it to the later block columns it owns, then the owner of the next one factorizes it
@@ -698,6 +777,7 @@ int build_plan(const Symbolic &S, const PlanParams &prm, HostPlan &P, int rank, 
     // ---- copy-out tasks ------------------------------------------------------------------------------------------
     for (i64 s = 0; s < ns; ++s) {
         const SnodeDev &d = P.snode[s];
+        if (!mine(s)) continue;              // every panel leaves through its owner
         const int rows = lu ? 2 * d.nsrow - d.nscol : d.nsrow;
         const int chunk = std::max(1, 65536 / std::max(rows, 1));
         for (int c0 = 0; c0 < d.nscol; c0 += chunk) {

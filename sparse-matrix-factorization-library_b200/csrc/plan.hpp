@@ -40,7 +40,8 @@ struct HostPlan {
     Kind kind = Kind::Cholesky;
     bool split = false;          // LU on an unsymmetric matrix: separate U values
     PlanParams prm;
-    i64 n = 0, nsuper = 0, nnz = 0, unnz = 0, isize = 0, xsize = 0, xsize_pad = 0;
+    i64 n = 0, nsuper = 0, nnz = 0, unnz = 0, isize = 0, xsize = 0;
+    i64 xsize_pad = 0;           // elements of THIS rank's image of the padded factor (world == 1: the whole factor)
     i64 wsize = 0;               // scratch elements behind the padded factor (offsets xsize_pad .. xsize_pad + wsize): U11^T copies
     int nlevels = 0;
     i64 nsmall = 0, nlarge = 0;
@@ -77,8 +78,11 @@ struct HostPlan {
     std::vector<int32_t> owner;             // owning rank of every supernode
     std::vector<int32_t> group_lo, group_hi;// ranks [lo,hi) that hold descendants of the supernode (hi-lo > 1: "shared")
     double local_flops = 0.0;               // flops of the supernodes this rank owns
-    std::vector<Coll> colls;                // collectives, grouped by segment (identical list on every rank)
-    std::vector<Segment> segments;          // collectives, then launches
+    std::vector<Coll> colls;                // exchange steps, grouped by segment (the same list on every rank)
+    std::vector<i64> coll_dst;              // C_BCAST steps this rank is the root of: block offset in every destination's image
+    std::vector<Segment> segments;          // exchange steps, then launches
+    std::vector<i64> image_elems;           // image size of every rank (elements); image_elems[rank] == xsize_pad
+    double remote_update_entries = 0.0;     // update entries this rank adds into other ranks' images per factorization
     std::vector<Phase> phases;              // one per etree level
 };
 

@@ -114,19 +114,35 @@ enum LaunchFlags : int32_t {
     LF_LEAVE_SMS = 1 << 4,   // persistent GEMM that runs next to an LF_DIAG_AHEAD launch: do not occupy every SM
 };
 
-// ---- multi-GPU: the schedule of one rank is a list of SEGMENTS: first the segment's collectives (issued by the host
-// layer through torch.distributed / NCCL on the plan's stream), then its launches.  Collective lists are identical on
-// every rank (collectives are matched by order); a rank outside [lo,hi) skips the entry. --------------------------------
+// ---- multi-GPU: the schedule of one rank is a list of SEGMENTS: first the segment's exchange steps, then its launches.
+// The step lists are identical on every rank (steps are matched by order); a rank outside [lo,hi) skips the entry.
+//
+// Exchange medium = peer memory over NVLink (CUDA peer access inside one process, CUDA IPC between processes):
+//   * every rank keeps an image of the panels it STORES -- the ones it owns plus the shared panels its group works on
+//     together -- at its own offsets (compact: a rank's image is about 1/world of the factor plus the shared tops);
+//   * an update aimed at a panel stored elsewhere is added straight into the destination rank's image by the scatter
+//     epilogue of the update kernels (red.global.add.f64 through the peer mapping): upd_coloff carries the destination
+//     rank in its top byte and the element offset inside THAT rank's image below it (extend-add fused into the producing
+//     GEMM);
+//   * what is left of the collectives are two kinds of steps, both device-side flags in peer memory (no host involvement,
+//     capturable into the CUDA graph of the factorization):
 enum CollType : int32_t {
-    C_REDUCE    = 0,   // sum the ranks' partial images of a shared panel into its owner (root)
-    C_ALLREDUCE = 1,   // ... into every rank of the group (panels factorized by the whole group)
-    C_BCAST     = 2,   // root's image of the region overwrites the group's (factored panel / block column)
+    C_BARRIER = 0,   // every rank of [lo,hi) signals the others and waits for them: all updates the group has aimed at the
+                     // shared panels of this level (or, first step of a factorization: all images are zeroed) are in place
+    C_BCAST   = 1,   // a rows x cols block (column stride ld) of a factored panel / block column: root's copy is pushed
+                     // into the image of every other rank of [lo,hi) (peer-to-peer copies), then a flag per destination
 };
 
+constexpr int kOwnerShift = 56;                                   // upd_coloff = (destination rank << 56) | element offset
+constexpr int64_t kOffsetMask = ((int64_t)1 << kOwnerShift) - 1;
+constexpr int kMaxWorld = 16;
+
 struct Coll {
-    int64_t offset;    // element offset in the padded factor image
-    int64_t count;     // elements (always a contiguous run of whole columns)
     int32_t type, root, lo, hi;
+    int64_t offset;        // C_BCAST: first element of the block in THIS rank's image (-1 if this rank is outside [lo,hi))
+    int32_t rows, cols;    // C_BCAST: block shape (rows contiguous)
+    int32_t ld;            // C_BCAST: column stride (the panel's leading dimension, the same on every rank)
+    int32_t dst_first;     // C_BCAST on its root: HostPlan::coll_dst[dst_first + (q - lo)] = offset of the block in rank q's image
 };
 
 struct Segment {

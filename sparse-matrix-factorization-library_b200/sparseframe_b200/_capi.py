@@ -17,8 +17,10 @@ SYMBOLS = [
     "sfb200_plan_sync", "sfb200_download_factor", "sfb200_last_ms", "sfb200_last_launches", "sfb200_host_alloc",
     "sfb200_host_free", "sfb200_probe_fp64_peak", "sfb200_plan_set_stream", "sfb200_plan_profile",
     "sfb200_plan_profile_get", "sfb200_plan_create_part", "sfb200_plan_double", "sfb200_plan_segment_info",
-    "sfb200_plan_coll_info", "sfb200_plan_owner", "sfb200_plan_factor_ptr", "sfb200_partition_begin", "sfb200_segment_run",
-    "sfb200_plan_panel_offsets", "sfb200_plan_profile_launch", "sfb200_solve", "sfb200_solve_device", "sfb200_residual",
+    "sfb200_plan_coll_info", "sfb200_plan_owner", "sfb200_plan_factor_ptr", "sfb200_plan_exchange_handle",
+    "sfb200_plan_connect", "sfb200_group_create", "sfb200_group_size", "sfb200_group_plan", "sfb200_group_factorize",
+    "sfb200_group_last_ms", "sfb200_group_free", "sfb200_plan_adopt_factor", "sfb200_plan_panel_offsets", "sfb200_factorize_owned", "sfb200_download_owned",
+    "sfb200_plan_owned_runs", "sfb200_plan_profile_launch", "sfb200_solve", "sfb200_solve_device", "sfb200_residual",
     "sfb200_analyze_ordered", "sfb200_symbolic_double",
 ]
 
@@ -83,8 +85,22 @@ def lib():
     L.sfb200_plan_factor_ptr.argtypes = [vp]
     L.sfb200_plan_panel_offsets.argtypes = [vp, vp]
     L.sfb200_plan_profile_launch.argtypes = [vp, ci, vp]
-    L.sfb200_partition_begin.argtypes = [vp, vp, vp]
-    L.sfb200_segment_run.argtypes = [vp, ci]
+    L.sfb200_plan_exchange_handle.argtypes = [vp, vp]
+    L.sfb200_plan_connect.argtypes = [vp, vp]
+    L.sfb200_group_create.argtypes = [vp, ci, vp, C.POINTER(vp)]
+    L.sfb200_group_size.argtypes = [vp]
+    L.sfb200_group_plan.restype = vp
+    L.sfb200_group_plan.argtypes = [vp, ci]
+    L.sfb200_group_factorize.argtypes = [vp, vp, vp, vp]
+    L.sfb200_group_last_ms.restype = dbl
+    L.sfb200_group_last_ms.argtypes = [vp, ci]
+    L.sfb200_group_free.argtypes = [vp]
+    L.sfb200_group_free.restype = None
+    L.sfb200_plan_adopt_factor.argtypes = [vp, vp, vp]
+    L.sfb200_factorize_owned.argtypes = [vp, vp, vp, vp]
+    L.sfb200_download_owned.argtypes = [vp, vp]
+    L.sfb200_plan_owned_runs.restype = i64
+    L.sfb200_plan_owned_runs.argtypes = [vp, vp]
     L.sfb200_solve.argtypes = [vp, vp, ci]
     L.sfb200_solve_device.argtypes = [vp, vp, ci]
     L.sfb200_residual.argtypes = [vp, vp, vp, vp]

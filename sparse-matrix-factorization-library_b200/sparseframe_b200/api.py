@@ -134,12 +134,16 @@ def fp64_peak(device=0, which="dmma", iters=4096) -> float:
 class Plan:
     """Device-resident numeric schedule for one symbolic structure."""
 
-    def __init__(self, sym: Symbolic, device=0, rank=0, world=1):
+    def __init__(self, sym: Symbolic, device=0, rank=0, world=1, _handle=None):
         L = _capi.lib()
-        h = C.c_void_p()
-        rc = L.sfb200_plan_create_part(sym._h, int(device), int(rank), int(world), C.byref(h))
-        if rc != 0:
-            raise RuntimeError("sfb200_plan_create failed (%d): %s" % (rc, _capi.last_error()))
+        self._owned = _handle is None
+        if _handle is None:
+            h = C.c_void_p()
+            rc = L.sfb200_plan_create_part(sym._h, int(device), int(rank), int(world), C.byref(h))
+            if rc != 0:
+                raise RuntimeError("sfb200_plan_create failed (%d): %s" % (rc, _capi.last_error()))
+        else:
+            h = C.c_void_p(_handle)           # a rank of a Group: freed with the group
         self._h = h
         self.sym = sym
         self.rank, self.world = int(rank), int(world)
@@ -155,10 +159,9 @@ class Plan:
                     level=int(out[4]))
 
     def coll_info(self, i):
-        out = np.zeros(6, dtype=np.int64)
+        out = np.zeros(8, dtype=np.int64)
         _capi.lib().sfb200_plan_coll_info(self._h, int(i), out.ctypes.data)
-        return dict(type=int(out[0]), offset=int(out[1]), count=int(out[2]), root=int(out[3]), lo=int(out[4]),
-                    hi=int(out[5]))
+        return dict(zip(("type", "root", "lo", "hi", "offset", "rows", "cols", "ld"), (int(v) for v in out)))
 
     def owner(self) -> np.ndarray:
         out = np.zeros(self.int("nsuper"), dtype=np.int32)
@@ -166,6 +169,7 @@ class Plan:
         return out
 
     def panel_offsets(self) -> np.ndarray:
+        """Offsets of the panels in this rank's image (-1: not stored here); last entry = elements of the image."""
         out = np.zeros(self.int("nsuper") + 1, dtype=np.int64)
         _capi.lib().sfb200_plan_panel_offsets(self._h, out.ctypes.data)
         return out
@@ -173,15 +177,26 @@ class Plan:
     def factor_ptr(self) -> int:
         return int(_capi.lib().sfb200_plan_factor_ptr(self._h))
 
-    def partition_begin(self, d_lx_ptr: int, d_ux_ptr: int = 0):
-        rc = _capi.lib().sfb200_partition_begin(self._h, d_lx_ptr, d_ux_ptr or None)
+    def exchange_handle(self) -> bytes:
+        """128 bytes another process needs to map this rank's image and flags (CUDA IPC)."""
+        buf = C.create_string_buffer(128)
+        rc = _capi.lib().sfb200_plan_exchange_handle(self._h, buf)
         if rc != 0:
-            raise RuntimeError("sfb200_partition_begin failed (%d): %s" % (rc, _capi.last_error()))
+            raise RuntimeError("sfb200_plan_exchange_handle failed (%d): %s" % (rc, _capi.last_error()))
+        return buf.raw
 
-    def segment_run(self, k):
-        rc = _capi.lib().sfb200_segment_run(self._h, int(k))
+    def connect(self, handles: bytes):
+        """handles = the exchange handles of all ranks, concatenated in rank order."""
+        if len(handles) != 128 * self.world:
+            raise ValueError("need %d bytes of handles" % (128 * self.world))
+        rc = _capi.lib().sfb200_plan_connect(self._h, C.c_char_p(handles))
         if rc != 0:
-            raise RuntimeError("sfb200_segment_run failed (%d): %s" % (rc, _capi.last_error()))
+            raise RuntimeError("sfb200_plan_connect failed (%d): %s" % (rc, _capi.last_error()))
+
+    def adopt_factor(self, d_lx_ptr: int, d_ux_ptr: int = 0):
+        rc = _capi.lib().sfb200_plan_adopt_factor(self._h, d_lx_ptr, d_ux_ptr or None)
+        if rc != 0:
+            raise RuntimeError("sfb200_plan_adopt_factor failed (%d): %s" % (rc, _capi.last_error()))
 
     def int(self, name) -> int:
         return int(_capi.lib().sfb200_plan_int(self._h, name.encode()))
@@ -279,7 +294,56 @@ class Plan:
 
     def close(self):
         if self._h:
-            _capi.lib().sfb200_plan_free(self._h)
+            if self._owned:
+                _capi.lib().sfb200_plan_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Group:
+    """All ranks of an etree partition inside one process, rank r on devices[r] (sfb200_group_*): what the drop-in's
+    SparseFrame_factorize drives when numGPU > 1 (the reference: one host thread per GPU, CH.c:2267-2290)."""
+
+    def __init__(self, sym: Symbolic, devices):
+        L = _capi.lib()
+        devs = (C.c_int * len(devices))(*[int(d) for d in devices])
+        h = C.c_void_p()
+        rc = L.sfb200_group_create(sym._h, len(devices), devs, C.byref(h))
+        if rc != 0:
+            raise RuntimeError("sfb200_group_create failed (%d): %s" % (rc, _capi.last_error()))
+        self._h = h
+        self.sym = sym
+        self.world = len(devices)
+        self.plans = [Plan(sym, devices[r], r, self.world, _handle=L.sfb200_group_plan(h, r)) for r in range(self.world)]
+
+    def factorize(self, Lx, Ux=None, out=None, download=True):
+        """Host buffers in, factor in the reference layout out (every rank writes the panels it owns)."""
+        L = _capi.lib()
+        Lx = np.ascontiguousarray(Lx, dtype=np.float64)
+        ux_p = None
+        if Ux is not None:
+            Ux = np.ascontiguousarray(Ux, dtype=np.float64)
+            ux_p = Ux.ctypes.data
+        if download and out is None:
+            out = np.full(self.plans[0].int("xsize"), np.nan)
+        rc = L.sfb200_group_factorize(self._h, Lx.ctypes.data, ux_p, out.ctypes.data if download else None)
+        if rc != 0:
+            raise RuntimeError("sfb200_group_factorize failed (%d): %s" % (rc, _capi.last_error()))
+        return out
+
+    def last_ms(self, which=0) -> float:
+        return float(_capi.lib().sfb200_group_last_ms(self._h, which))
+
+    def close(self):
+        if self._h:
+            for p in self.plans:
+                p.close()
+            _capi.lib().sfb200_group_free(self._h)
             self._h = None
 
     def __del__(self):

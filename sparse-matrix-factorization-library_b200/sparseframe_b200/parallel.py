@@ -1,22 +1,24 @@
-"""Etree-subtree-partitioned factorization over several GPUs of one box: one process per GPU,
-torch.distributed for the plumbing.
+"""Etree-subtree-partitioned factorization over several GPUs of one box, one process per GPU.
 
-Each rank factorizes the subtrees it owns.  The supernodes above them ("top") are shared by a group of ranks: every rank
-accumulates its updates to them in its own zero-initialised image of the factor, and the plan lists the exchange steps
-(csrc/plan_types.h `Coll`) that turn the images into the factor:
-  reduce      the images of a shared panel are summed into its owner right before its level is factorized;
-  all-reduce  ... into the whole group, for wide Cholesky panels that the group factorizes together (block columns
-              owned round-robin, one broadcast per factorized block column);
-  broadcast   a factored panel / block column goes to the group, which then splits the tiles of its Schur update.
-NCCL over NVLink on GPUs, gloo in the CPU tests.  The reference's equivalent of these steps is its host-RAM round trip
-of factored panels (CH.c:2596-2685); nothing else is communicated.
+Each rank factorizes the subtrees it owns.  The supernodes above them ("top") are shared by a group of ranks; the
+exchange medium is peer memory over NVLink (include/sfb200.h, csrc/plan_types.h `Coll`):
+  * an update aimed at a panel another rank stores is added straight into that rank's image by the scatter epilogue of
+    the update kernels (`red.global.add.f64` through the peer mapping);
+  * wide shared Cholesky fronts are factorized by their whole group (block columns owned round-robin), the Schur update
+    of a shared front is split over its group; factored blocks are pushed to the group with peer-to-peer copies;
+  * synchronisation is flags in peer memory: no host round trip, a rank's whole factorization replays as one CUDA graph.
+The reference's equivalent is its host-RAM round trip of factored panels (CH.c:2596-2685).
 
-The segment loop is backend-agnostic so that the same orchestration code runs on the GPU engine (`DeviceBackend`) and,
-in the CPU test tier, on the plan interpreter of the oracle (tests/test_multirank_gloo.py).
+What is left for the host layer -- and all this module does -- is to CONNECT the ranks once: every rank exports a
+128-byte handle of its image and flag array (CUDA IPC), the handles travel through torch.distributed (NCCL or gloo: plumbing,
+no payload ever goes through it), every rank maps its peers.  The same code connects the CPU plan interpreters of the test
+tier, whose "images" are shared-memory segments (tests/test_multirank_gloo.py).
 """
 from __future__ import annotations
 
 import numpy as np
+
+HANDLE_BYTES = 128
 
 
 class _CudaView:
@@ -27,75 +29,75 @@ class _CudaView:
                                          "version": 2}
 
 
-REDUCE, ALLREDUCE, BCAST = 0, 1, 2
+def all_gather_handles(dist, handle: bytes, world: int) -> bytes:
+    """The ranks' exchange handles, concatenated in rank order."""
+    import torch
+    if len(handle) != HANDLE_BYTES:
+        raise ValueError("an exchange handle has %d bytes" % HANDLE_BYTES)
+    dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
+    mine = torch.frombuffer(bytearray(handle), dtype=torch.uint8).to(dev)
+    parts = [torch.empty(HANDLE_BYTES, dtype=torch.uint8, device=dev) for _ in range(world)]
+    dist.all_gather(parts, mine)
+    return b"".join(bytes(t.cpu().numpy().tobytes()) for t in parts)
 
 
 class DeviceBackend:
-    """One rank's sfb200_plan (created with rank/world) behind the backend protocol."""
+    """One rank's sfb200_plan (created with rank / world) and its matrix values in HBM."""
 
     def __init__(self, plan, d_lx, d_ux=None):
         import torch
         self.plan = plan
         self.rank, self.world = plan.rank, plan.world
         self.d_lx, self.d_ux = d_lx, d_ux
-        self.image = torch.as_tensor(_CudaView(plan.factor_ptr(), plan.int("xsize_padded")), device=d_lx.device)
-        self.segments = [plan.segment_info(k) for k in range(plan.int("nsegments"))]
-        self.colls = [plan.coll_info(i) for i in range(plan.int("ncolls"))]
+        # The plan's launches must be ordered after whatever produced d_lx / d_ux and before whatever reads the factor:
+        # both live on torch's current stream, so the plan runs there (a plan left on its private stream would race with them).
+        self.stream = torch.cuda.current_stream(d_lx.device)
+        plan.set_stream(self.stream.cuda_stream)
 
-    def begin(self):
-        self.plan.partition_begin(self.d_lx.data_ptr(), self.d_ux.data_ptr() if self.d_ux is not None else 0)
+    def exchange_handle(self) -> bytes:
+        return self.plan.exchange_handle()
 
-    def run_segment(self, k):
-        self.plan.segment_run(k)
+    def connect(self, handles: bytes):
+        self.plan.connect(handles)
+
+    def factorize(self):
+        """This rank's part: asynchronous on the plan's stream; every rank of the partition must call it."""
+        self.plan.factorize_device(self.d_lx.data_ptr(), self.d_ux.data_ptr() if self.d_ux is not None else 0)
 
     def finish(self):
         self.plan.sync()
 
 
 class PartitionedFactorization:
-    """Segment loop: the segment's collectives on regions of the factor image, then its launches."""
+    """Connects the ranks (once), then every factorize() is one device-side replay per rank."""
 
-    def __init__(self, backend, dist=None):
+    def __init__(self, backend, dist):
         self.b = backend
         self.dist = dist
-        self.groups = {}
-        if dist is not None and backend.world > 1:
-            # groups must be created by every rank, in the same order: the collective list is identical on all ranks
-            for c in backend.colls:
-                key = (c["lo"], c["hi"])
-                if key not in self.groups:
-                    full = key == (0, backend.world)
-                    self.groups[key] = None if full else dist.new_group(ranks=list(range(key[0], key[1])))
-        self.bytes = {REDUCE: 0, ALLREDUCE: 0, BCAST: 0}
+        if backend.world > 1:
+            backend.connect(all_gather_handles(dist, backend.exchange_handle(), backend.world))
 
-    @property
-    def reduced_bytes(self):
-        return self.bytes[REDUCE] + self.bytes[ALLREDUCE]
+    def factorize(self, wait=True):
+        self.b.factorize()
+        if wait:
+            self.b.finish()
 
-    @property
-    def bcast_bytes(self):
-        return self.bytes[BCAST]
 
-    def factorize(self):
-        b, dist = self.b, self.dist
-        b.begin()
-        self.bytes = {REDUCE: 0, ALLREDUCE: 0, BCAST: 0}
-        for k, sg in enumerate(b.segments):
-            for i in range(sg["coll_first"], sg["coll_first"] + sg["coll_count"]):
-                c = b.colls[i]
-                if b.world == 1 or not (c["lo"] <= b.rank < c["hi"]):
-                    continue
-                view = b.image[c["offset"]:c["offset"] + c["count"]]
-                group = self.groups[(c["lo"], c["hi"])]
-                if c["type"] == REDUCE:
-                    dist.reduce(view, dst=c["root"], op=dist.ReduceOp.SUM, group=group)
-                elif c["type"] == ALLREDUCE:
-                    dist.all_reduce(view, op=dist.ReduceOp.SUM, group=group)
-                else:
-                    dist.broadcast(view, src=c["root"], group=group)
-                self.bytes[c["type"]] += 8 * c["count"]
-            b.run_segment(k)
-        b.finish()
+def owned_runs(owner, my_offsets, global_offsets, rank):
+    """Runs of consecutive supernodes `rank` owns: (offset in its image, offset in the single-GPU image, elements).
+    Consecutive stored panels are back to back in both layouts."""
+    owner = np.asarray(owner)
+    mine = np.flatnonzero(owner == rank)
+    runs = []
+    if mine.size == 0:
+        return runs
+    brk = np.flatnonzero(np.diff(mine) != 1)
+    starts = np.concatenate([[mine[0]], mine[brk + 1]])
+    ends = np.concatenate([mine[brk], [mine[-1]]])
+    for a, b in zip(starts, ends):
+        count = int(global_offsets[b + 1] - global_offsets[a])
+        runs.append((int(my_offsets[a]), int(global_offsets[a]), count))
+    return runs
 
 
 def owned_mask(owner, Lsxp, rank):

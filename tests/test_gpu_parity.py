@@ -355,75 +355,97 @@ def test_lu_in_panel_updates_operand_paths(gen, g, kind, env):
     plan.close()
 
 
-@pytest.mark.parametrize("gen,g,kind,world,group_panels", [
-    ("lap3d", 20, "cholesky", 2, 0), ("lap3d", 20, "cholesky", 4, 0), ("cd3d", 16, "lu", 3, 0),
-    ("lap3d", 24, "cholesky", 2, 1), ("lap3d", 24, "cholesky", 4, 1), ("lap3d", 24, "cholesky", 3, 1)])
-def test_partitioned_plans_emulated_on_one_gpu(gen, g, kind, world, group_panels):
-    """The etree-partitioned device path without NCCL: all `world` rank plans live on this one GPU, segments run in
-    lock step and the collectives are done with torch adds / copies -- the same order of operations torch.distributed
-    gives.  group_panels: shared fronts of >= 256 columns are factorized by their whole group (128-wide block columns
-    owned round-robin, one broadcast per block column)."""
-    import torch
-    from sparseframe_b200.parallel import DeviceBackend, owned_mask, REDUCE, ALLREDUCE, BCAST
-    env = dict(SFB200_DIST_MIN_M="48")           # small fronts too: exercise the broadcast + tile-share path
+PARTITION_CASES = [("lap3d", 20, "cholesky", 2, 0), ("lap3d", 20, "cholesky", 4, 0), ("cd3d", 16, "lu", 3, 0),
+                   ("lap3d", 24, "cholesky", 2, 1), ("lap3d", 24, "cholesky", 4, 1), ("lap3d", 24, "cholesky", 3, 1)]
+
+PARTITION_CHILD = r"""
+import os, sys
+import numpy as np
+sys.path.insert(0, os.path.join(%(root)r, "sparse-matrix-factorization-library_b200"))
+sys.path.insert(0, os.path.join(%(root)r, "oracle"))
+sys.path.insert(0, os.path.join(%(root)r, "tests"))
+import sforacle
+import sparseframe_b200 as sf
+from conftest import build_matrix
+gen, g, kind, world, devices = %(gen)r, %(g)d, %(kind)r, %(world)d, %(devices)r
+A, _ = build_matrix(gen, g)
+S = sf.analyze(A, kind)
+st = {k: S.array(k) for k in ("Super", "SuperMap", "Lsip", "Lsxp", "Lsi", "LeafQueue", "Lp", "Li")}
+st["csize"], st["nsleaf"] = S.int("csize"), S.int("nsleaf")
+split = kind == "lu" and S.int("symmetric") == 0
+ux = None
+if split:
+    st["Up"], st["Ui"] = S.array("Up"), S.array("Ui")
+    ux = S.array("Ux")
+ref, bad = sforacle.factorize(kind, st, S.array("Lx"), ux)
+assert bad == 0
+grp = sf.Group(S, devices)
+assert sum(p.double("local_flops") for p in grp.plans) == S.flops or abs(sum(p.double("local_flops") for p in grp.plans) / S.flops - 1) < 1e-12
+types = [grp.plans[0].coll_info(i)["type"] for i in range(grp.plans[0].int("ncolls"))]
+assert types.count(0) >= 2 and types.count(1) > 0, "barriers and pushes expected: %%r" %% (types,)
+full = sf.Plan(S).int("xsize_padded")
+images = [p.int("xsize_padded") for p in grp.plans]
+assert max(images) < full <= sum(images), (images, full)         # compact images: nobody holds the whole factor
+mask = sf.lower_trapezoid_mask(kind, st["Super"], st["Lsip"], st["Lsxp"], len(ref))
+worst = 0.0
+for it in range(4):                     # plain, graph capture, two replays -- the flags' epochs advance with each one
+    out = grp.factorize(S.array("Lx"), ux)
+    assert not np.isnan(out[mask]).any(), "a panel was not written by its owner"
+    worst = max(worst, sf.entrywise_rel_diff(ref[mask], out[mask]))
+    assert np.array_equal(ref[mask] == 0, out[mask] == 0)
+_, backward = sforacle.validate(kind, st, S.array("Lx"), out, ux)
+print("RESULT", worst, backward, sum(p.double("remote_update_bytes") for p in grp.plans), sum(p.double("push_bytes") for p in grp.plans), grp.last_ms(0))
+grp.close()
+"""
+
+
+def run_partition_child(gen, g, kind, world, devices, env):
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = PARTITION_CHILD % dict(root=root, gen=gen, g=g, kind=kind, world=world, devices=list(devices))
+    # several ranks share one GPU here: each needs its own hardware queues, or a spinning flag wait of one rank could sit in
+    # front of the kernels of the rank it waits for
+    full_env = dict(os.environ, CUDA_DEVICE_MAX_CONNECTIONS="32", SFB200_PEER_TIMEOUT_S="20", **{k: str(v) for k, v in env.items()})
+    p = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600, env=full_env)
+    assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-4000:]
+    line = [ln for ln in p.stdout.splitlines() if ln.startswith("RESULT")][-1].split()
+    return [float(v) for v in line[1:]]
+
+
+def partition_env(group_panels):
+    env = dict(SFB200_DIST_MIN_M="48")           # small fronts too: exercise the push + tile-share path
     env["SFB200_DIST_PANEL_MIN"] = "256" if group_panels else "1000000"
     if group_panels:
         env.update(SFB200_OUTER="128", SFB200_OUTER2="256")
-    os.environ.update(env)
-    A, _ = build_matrix(gen, g)
-    S = sf.analyze(A, kind)
-    split = kind == "lu" and S.int("symmetric") == 0
-    d_lx = torch.from_numpy(S.array("Lx")).cuda()
-    d_ux = torch.from_numpy(S.array("Ux")).cuda() if split else None
-    plans = [sf.Plan(S, rank=r, world=world) for r in range(world)]
-    for k in env:
-        os.environ.pop(k, None)
-    stream = torch.cuda.current_stream()
-    for p in plans:
-        p.set_stream(stream.cuda_stream)
-    backs = [DeviceBackend(p, d_lx, d_ux) for p in plans]
-    assert sum(p.double("local_flops") for p in plans) == pytest.approx(S.flops, rel=1e-12)
-    assert all(b.colls == backs[0].colls and len(b.segments) == len(backs[0].segments) for b in backs)
-    for b in backs:
-        b.begin()
-    ncoll = [0, 0, 0]
-    for k, sg in enumerate(backs[0].segments):
-        for i in range(sg["coll_first"], sg["coll_first"] + sg["coll_count"]):
-            c = backs[0].colls[i]
-            sl = slice(c["offset"], c["offset"] + c["count"])
-            group = range(c["lo"], c["hi"])
-            if c["type"] == BCAST:
-                for q in group:
-                    if q != c["root"]:
-                        backs[q].image[sl] = backs[c["root"]].image[sl]
-            else:
-                for q in group:
-                    if q != c["root"]:
-                        backs[c["root"]].image[sl] += backs[q].image[sl]
-                if c["type"] == ALLREDUCE:
-                    for q in group:
-                        if q != c["root"]:
-                            backs[q].image[sl] = backs[c["root"]].image[sl]
-            ncoll[c["type"]] += 1
-        for b in backs:
-            b.run_segment(k)
-    for b in backs:
-        b.finish()
-    assert ncoll[BCAST] > 0, "the test should exercise the distributed Schur updates"
-    assert ncoll[REDUCE] + ncoll[ALLREDUCE] > 0
-    assert (ncoll[ALLREDUCE] > 0) == bool(group_panels)
-    Lsxp = S.array("Lsxp")
-    merged = np.zeros(S.int("xsize"))
-    owner = plans[0].owner()
-    for r, p in enumerate(plans):
-        m = owned_mask(owner, Lsxp, r)
-        merged[m] = p.download()[m]
-    st = oracle_structure(S)
-    ref_lsx, bad = sforacle.factorize(kind, st, S.array("Lx"), S.array("Ux") if split else None)
-    assert bad == 0
-    compare(kind, st, ref_lsx, merged)
-    for p in plans:
-        p.close()
+    return env
+
+
+@pytest.mark.parametrize("push", ["dma", "sm"])
+@pytest.mark.parametrize("gen,g,kind,world,group_panels", PARTITION_CASES)
+def test_partitioned_ranks_sharing_one_gpu(gen, g, kind, world, group_panels, push):
+    """The etree-partitioned device path as it runs on several GPUs -- remote adds from the scatter epilogues, pushes of
+    factored blocks, flags in peer memory, one CUDA graph per rank -- with all `world` ranks on THIS one GPU (every "peer"
+    mapping points into the same device): an in-process group, one host thread per rank (sfb200_group_*, what the drop-in
+    drives for numGPU > 1).  group_panels: shared fronts of >= 256 columns are factorized by their whole group (128-wide
+    block columns owned round-robin, one push per block column).  push: copy engines / SM copy kernel."""
+    env = partition_env(group_panels)
+    env["SFB200_PUSH"] = push
+    worst, backward, remote_bytes, push_bytes, ms = run_partition_child(gen, g, kind, world, [0] * world, env)
+    assert worst <= ENTRY_TOL and backward <= BACKWARD_TOL
+    assert remote_bytes > 0 and push_bytes > 0
+
+
+@pytest.mark.parametrize("gen,g,kind,group_panels", [("lap3d", 40, "cholesky", 1), ("cd3d", 24, "lu", 0), ("lap3d", 32, "cholesky", 0)])
+def test_partitioned_ranks_on_separate_gpus(gen, g, kind, group_panels):
+    """The same over real peer access (NVLink): one rank per visible GPU, up to 4."""
+    import torch
+    ngpu = min(torch.cuda.device_count(), 4)
+    if ngpu < 2:
+        pytest.skip("needs at least 2 GPUs")
+    worst, backward, remote_bytes, push_bytes, ms = run_partition_child(gen, g, kind, ngpu, list(range(ngpu)), partition_env(group_panels))
+    assert worst <= ENTRY_TOL and backward <= BACKWARD_TOL
+    assert remote_bytes > 0
 
 
 def test_streamed_copy_out_into_pinned_memory():

@@ -179,13 +179,13 @@ def test_dense_matrix_against_numpy(n):
     (250, 0.03, 14, "lu", 8, 16), (600, 0.004, 15, "cholesky", 8, 0), (120, 0.1, 16, "lu", 4, 8)])
 def test_partitioned_schedule_on_irregular_trees(n, density, seed, kind, world, nb):
     """Etree-subtree partition over `world` ranks on irregular (random) elimination trees and forests: all ranks simulated
-    in one process, collectives applied to their images; the union of the owned panels must be the single-rank factor."""
+    in one process, remote update entries and pushed blocks applied to their images; the union of the owned panels must be the single-rank factor."""
     import ctypes as C
     import os
     lib = C.CDLL(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "libsfcheck.so"))
     lib.sfcheck_factorize_partitioned.restype = C.c_long
     lib.sfcheck_factorize_partitioned.argtypes = [C.c_int, C.c_int, C.c_long, C.c_void_p, C.c_void_p, C.c_void_p,
-                                                  C.c_ulonglong] + [C.c_int] * 5 + [C.c_void_p] * 3
+                                                  C.c_ulonglong] + [C.c_int] * 5 + [C.c_void_p] * 4
     nn, r, c, x, sym = random_matrix(n, density, seed, kind == "cholesky", seed % 2 == 0)
     A = sf.compress(nn, r, c, x, sym)
     S = sf.analyze(A, kind)
@@ -199,10 +199,10 @@ def test_partitioned_schedule_on_irregular_trees(n, density, seed, kind, world, 
     assert bad == 0
     out = np.full(S.int("xsize"), np.nan)
     bal = np.zeros(world)
-    ncoll = (C.c_long * 3)()
+    ncoll = (C.c_long * 2)()
     rc = lib.sfcheck_factorize_partitioned(int(kind == "lu"), int(A.symmetric), A.n, A.Cp.ctypes.data, A.Ci.ctypes.data,
                                            A.Cx.ctypes.data, sf.DEFAULT_DEVSLOT, nb, 2 * nb, 0 if nb else -1,
-                                           0 if nb else -1, world, out.ctypes.data, bal.ctypes.data, ncoll)
+                                           0 if nb else -1, world, out.ctypes.data, bal.ctypes.data, ncoll, None)
     assert rc == 0
     mask = sf.lower_trapezoid_mask(kind, st["Super"], st["Lsip"], st["Lsxp"], S.int("xsize"))
     assert sf.entrywise_rel_diff(ref[mask], out[mask]) <= 1e-10

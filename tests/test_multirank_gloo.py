@@ -1,6 +1,8 @@
-"""N>1 path on CPU: world_size-2 (and 3) gloo process groups run the SAME orchestration code as the GPUs
-(sparseframe_b200.parallel.PartitionedFactorization) over the CPU plan interpreter of the oracle, and the union of the
-owned panels must reproduce the golden factor."""
+"""N>1 path on CPU: world_size-2 (and 3) gloo process groups run the SAME host logic as the GPUs
+(sparseframe_b200.parallel.PartitionedFactorization: exchange of the ranks' handles, connect, factorize) over the CPU plan
+interpreter of the oracle.  The interpreters' images are shared-memory segments -- the stand-in for CUDA IPC mappings --
+so remote update entries and pushed blocks really cross process boundaries, and the union of the owned panels must
+reproduce the golden factor."""
 import os
 import socket
 import sys
@@ -27,24 +29,27 @@ def _worker(rank, world, port, gen, g, kind, devslot, group_panels, out_path):
     from sparseframe_b200.parallel import PartitionedFactorization
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
-    os.environ["SFCHECK_DIST_MIN_M"] = "8"       # tiny fronts too: exercise the broadcast + tile-share path
+    os.environ["SFCHECK_DIST_MIN_M"] = "8"       # tiny fronts too: exercise the push + tile-share path
     # group_panels: shared Cholesky fronts of >= 24 columns are factorized by their whole group in 16-wide block columns
     os.environ["SFCHECK_DIST_PANEL_MIN"] = "24" if group_panels else "1000000"
     dist.init_process_group("gloo", rank=rank, world_size=world)
     A = sf.compress(*sf.matrices.generate(gen, g))
-    backend = sforacle.CheckBackend(kind, A, devslot, rank, world, nb=8 if group_panels else 0, outer=16 if group_panels else 0)
+    backend = sforacle.CheckBackend(kind, A, devslot, rank, world, nb=8 if group_panels else 0, outer=16 if group_panels else 0,
+                                    dist=dist)
     pf = PartitionedFactorization(backend, dist)
-    pf.factorize()
-    assert backend.bad == 0
+    for _ in range(2):                                  # a second factorization re-zeroes and re-uses the mappings
+        pf.factorize()
+        assert backend.bad == 0
     owned = torch.from_numpy(backend.pack_owned())      # zeros outside the owned panels -> SUM = union
     dist.reduce(owned, dst=0, op=dist.ReduceOp.SUM)
-    stats = torch.tensor([backend.double("local_flops"), float(pf.reduced_bytes), float(pf.bcast_bytes),
-                          float(pf.bytes[1])], dtype=torch.float64)
+    ntypes = np.bincount([c["type"] for c in backend.colls], minlength=2)
+    stats = torch.tensor([backend.double("local_flops"), float(backend.pushed_bytes), float(backend.int("xsize_pad")),
+                          float(backend.image_elems[rank])], dtype=torch.float64)
     gathered = [torch.zeros(4, dtype=torch.float64) for _ in range(world)] if rank == 0 else None
     dist.gather(stats, gathered, dst=0)
     if rank == 0:
         np.savez(out_path, lsx=owned.numpy(), stats=torch.stack(gathered).numpy(), total=backend.double("flops"),
-                 ncoll=np.bincount([c["type"] for c in backend.colls], minlength=3))
+                 ncoll=ntypes, full_image=float(sum(int(c) for c in [0])))
     dist.barrier()
     dist.destroy_process_group()
     backend.close()
@@ -68,18 +73,16 @@ def test_partitioned_factorization_over_gloo(world, name, group_panels, tmp_path
     a, b = gold["Lsx"][mask], res["lsx"][mask]
     assert sf.entrywise_rel_diff(a, b) <= 1e-10
     assert np.array_equal(a == 0, b == 0)
-    # every flop is owned by exactly one rank, and something really had to be exchanged
+    # every flop is owned by exactly one rank; there is at least the start barrier and one group barrier
     ncoll = res["ncoll"]
     assert res["stats"][:, 0].sum() == pytest.approx(float(res["total"]), rel=1e-12)
-    assert ncoll[0] + ncoll[1] > 0 and res["stats"][:, 1].sum() > 0
-    # shared fronts with off-diagonal rows are broadcast and their Schur update is split over the group
-    assert (res["stats"][:, 2].sum() > 0) == (ncoll[2] > 0)
+    assert ncoll[0] >= 2
+    # shared fronts with off-diagonal rows are pushed to their group and their Schur update is split over it
+    assert (res["stats"][:, 1].sum() > 0) == (ncoll[1] > 0)
     if name == "lap3d_10_chol_slot":
-        assert ncoll[2] > 0, "this case must exercise the distributed Schur updates"
-        assert (ncoll[1] > 0) == bool(group_panels), "group-factorized panels are announced by all-reduces"
-        assert (res["stats"][:, 3].sum() > 0) == bool(group_panels)
-    if gold["kind"] == "lu":
-        assert ncoll[1] == 0, "LU panels stay with their owner"
+        assert ncoll[1] > 0, "this case must exercise the distributed Schur updates"
+    # every rank computed every rank's layout and they agree; no rank holds the whole factor any more
+    assert np.array_equal(res["stats"][:, 2], res["stats"][:, 3])
 
 
 @pytest.mark.parametrize("group_panels", [0, 1])
@@ -96,7 +99,7 @@ def test_partition_simulated_up_to_8_ranks(group_panels, monkeypatch):
     lib = C.CDLL(os.path.join(ROOT, "oracle", "_ref", "libsfcheck.so"))
     lib.sfcheck_factorize_partitioned.restype = C.c_long
     lib.sfcheck_factorize_partitioned.argtypes = [C.c_int, C.c_int, C.c_long, C.c_void_p, C.c_void_p, C.c_void_p,
-                                                  C.c_ulonglong] + [C.c_int] * 5 + [C.c_void_p] * 3
+                                                  C.c_ulonglong] + [C.c_int] * 5 + [C.c_void_p] * 4
     for gen, g, kind in (("lap3d", 14, "cholesky"), ("cd3d", 12, "lu")):
         A = sf.compress(*sf.matrices.generate(gen, g))
         S = sf.analyze(A, kind)
@@ -109,17 +112,29 @@ def test_partition_simulated_up_to_8_ranks(group_panels, monkeypatch):
         ref, bad = sforacle.factorize(kind, st, S.array("Lx"), ux)
         assert bad == 0
         mask = sf.lower_trapezoid_mask(kind, st["Super"], st["Lsip"], st["Lsxp"], S.int("xsize"))
-        for world in (2, 4, 5, 8):
-            out = np.full(S.int("xsize"), np.nan)
-            bal = np.zeros(world)
-            ncoll = (C.c_long * 3)()
-            rc = lib.sfcheck_factorize_partitioned(int(kind == "lu"), int(A.symmetric), A.n, A.Cp.ctypes.data,
-                                                   A.Ci.ctypes.data, A.Cx.ctypes.data, sf.DEFAULT_DEVSLOT,
-                                                   8 if group_panels else 0, 16 if group_panels else 0, -1, -1,
-                                                   world, out.ctypes.data, bal.ctypes.data, ncoll)
-            assert rc == 0
-            assert ncoll[0] + ncoll[1] > 0
-            assert (ncoll[1] > 0) == (bool(group_panels) and kind == "cholesky")
-            assert sf.entrywise_rel_diff(ref[mask], out[mask]) <= 1e-10
-            assert bal.sum() == pytest.approx(S.flops, rel=1e-12)
-            assert bal.max() / bal.sum() < 0.75          # no rank is left with (almost) everything
+        plan_elems = None
+        for world in (1, 2, 4, 5, 8):
+            for reversed_ranks in (False, True):        # the result must not depend on which rank of a segment runs first
+                if reversed_ranks:
+                    monkeypatch.setenv("SFCHECK_RANKS_REVERSED", "1")
+                else:
+                    monkeypatch.delenv("SFCHECK_RANKS_REVERSED", raising=False)
+                out = np.full(S.int("xsize"), np.nan)
+                bal = np.zeros(world)
+                ncoll = (C.c_long * 2)()
+                image = (C.c_long * world)()
+                rc = lib.sfcheck_factorize_partitioned(int(kind == "lu"), int(A.symmetric), A.n, A.Cp.ctypes.data,
+                                                       A.Ci.ctypes.data, A.Cx.ctypes.data, sf.DEFAULT_DEVSLOT,
+                                                       8 if group_panels else 0, 16 if group_panels else 0, -1, -1,
+                                                       world, out.ctypes.data, bal.ctypes.data, ncoll, image)
+                assert rc == 0
+                assert sf.entrywise_rel_diff(ref[mask], out[mask]) <= 1e-10
+                assert bal.sum() == pytest.approx(S.flops, rel=1e-12)
+                if world == 1:
+                    plan_elems = image[0]
+                    assert ncoll[0] == 0 and ncoll[1] == 0
+                    continue
+                assert ncoll[0] >= 2                         # the start barrier and at least one group barrier
+                assert bal.max() / bal.sum() < 0.75          # no rank is left with (almost) everything
+                # images are compact: a rank stores its own panels and the shared fronts of its groups, not the whole factor
+                assert max(image) < plan_elems and sum(image) >= plan_elems
