@@ -123,6 +123,36 @@ def structure_flops(ref, kind):
     return float((c ** 3 / 3.0 + m * c * c + m * (m + 1.0) * c).sum())
 
 
+def pick_blas_threads(kind):
+    """The reference sets OpenBLAS to min(omp_get_max_threads(), 16) threads (CH.c:3357-3359).  On the 16-vCPU hosts of this
+    pool that oversubscribes the cores (OpenBLAS' spinning workers + the caller + the box's own daemons): measured in round 2
+    (profiles/r02_cpu_ref_probe.log) lap3d 64^3 runs at 95 GFLOP/s with 16 threads, 231 with 8 and 5.5 with 32 -- the 96 / 189 /
+    275 swing of round 1.  The CPU numbers are therefore taken with the better of {the reference's setting, half the cores},
+    decided by a two-second calibration on a small matrix of the same family; both rates are reported."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import sfref
+    from sparseframe_b200 import matrices
+    cores = os.cpu_count()
+    policy = min(cores, 16)
+    cands = sorted({policy, max(cores // 2, 1)}, reverse=True)
+    gen, g = ("cd3d", 32) if kind == "lu" else ("lap3d", 40)
+    n, r, c, x, sym = matrices.generate(gen, g)
+    rates = {}
+    for t in cands:
+        ref = sfref.Reference(n, r, c, x, sym, kind=kind, blas_threads=t).analyze()
+        fl = structure_flops(ref, kind)
+        best = None
+        for _ in range(3):
+            ref.factorize()
+            dt = ref.double("factorizeTime")
+            best = dt if best is None else min(best, dt)
+        ref.close()
+        rates[t] = fl / best / 1e9
+    used = max(rates, key=lambda k: rates[k])
+    return used, {"reference_policy_threads": policy, "used_threads": used,
+                  "calibration": "%s %d^3, best of 3" % (gen, g), "calibration_gflops": {str(k): round(v, 1) for k, v in rates.items()}}
+
+
 def time_reference(gen, g, kind, warmup, steps, budget_s, blas_threads):
     """The compiled reference's CPU worker path (oracle/_ref) on one full matrix: `warmup` untimed + up to `steps` timed
     factorizations, stopping early once `budget_s` seconds of factorization time are spent (at least one timed step)."""
@@ -158,8 +188,7 @@ def reference_arm(args, cfg, gen, g, kind):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cores = os.cpu_count()
-    threads = min(cores, 16)
+    threads, thread_info = pick_blas_threads(kind)
     budget = float(os.environ.get("SFB200_REF_BUDGET_S", "600"))
     note = None
     cache = os.path.join("/tmp", "sfb200_reference_%s_%s.json" % (cfg, os.uname().nodename))
@@ -183,7 +212,7 @@ def reference_arm(args, cfg, gen, g, kind):
     total = sum(times)
     value = res["flops"] * len(times) / total / 1e9
     sample = "%s: the whole matrix (n=%d, %.3e flop/step), %d timed step(s) after %d warm-up (time budget %.0f s), " \
-             "compiled reference CPU worker path, OpenBLAS threads=%d" % (cfg, res["n"], res["flops"], len(times),
+             "compiled reference CPU worker path, OpenBLAS threads=%d (see cpu_baseline.threads)" % (cfg, res["n"], res["flops"], len(times),
                                                                         res["warmup_done"], budget, threads)
     emit({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": len(times),
@@ -193,7 +222,7 @@ def reference_arm(args, cfg, gen, g, kind):
                    "devSlotSize": 5_380_000_000, "analyze_s": res["analyze_s"], "note": note,
                    "steps_requested": args.steps, "warmup_requested": args.warmup},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "reference", "sample": sample,
-                         "host": host_state()},
+                         "host": host_state(), "threads": thread_info},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     })
 
@@ -205,15 +234,14 @@ def cpu_baseline(cfg, gen, g, kind):
     import sfref
     if not sfref.available(kind):
         return None
-    cores = os.cpu_count()
-    threads = min(cores, 16)
+    threads, thread_info = pick_blas_threads(kind)
     res = time_reference(gen, g, kind, 0, 2, float(os.environ.get("SFB200_CPU_BASELINE_BUDGET_S", "45")), threads)
     best = min(res["times"])
     return {"value": res["flops"] / best / 1e9, "unit": UNIT, "cores": threads, "kind": "reference",
             "sample": "%s: the whole matrix (n=%d, %.3e flop), compiled reference CPU path (oracle/_ref), best of %d, "
                       "%.2f s, OpenBLAS threads=%d (reference caps at 16, parameter.h:12)" % (
                           cfg, res["n"], res["flops"], len(res["times"]), best, threads),
-            "host": host_state()}
+            "host": host_state(), "threads": thread_info}
 
 
 def distributed_parity(sf, torch, dist, S, plan, pf, d_lx, d_ux, stream, rank, world, local_rank, split, flops):
@@ -414,13 +442,22 @@ def main():
     from sparseframe_b200 import _capi
     L = _capi.lib()
     if world == 1:
+        # THE reference-facing call: SparseFrame_factorize of Cholesky/Lib (LU/Lib) libSparseFrame.so -- the symbol a program
+        # linked against the reference calls (CH.c:3019, LU.c:3575) -- with a matrix_info filled the way SparseFrame_analyze
+        # leaves it and page-locked Lx / Lsx.  The first call builds the drop-in's own plan for this matrix_info (untimed).
+        import ctypes as C
+        from sparseframe_b200 import dropin as D
+        dlib = D.Library(kind)
         h_out = torch.empty(xsize, dtype=torch.float64).pin_memory()
         d2h_bytes = xsize * 8
+        keep = []
+        m_info = dlib.matrix_from_structure(S, h_lx.data_ptr(), h_ux.data_ptr() if split else 0, h_out.data_ptr(), keep)
+        common = D.common_info_struct(numGPU=1, numGPU_physical=1, devSlotSize=sf.DEFAULT_DEVSLOT)
 
         def e2e_step():
-            rc = L.sfb200_factorize(plan._h, h_lx.data_ptr(), h_ux.data_ptr() if split else None, h_out.data_ptr())
+            rc = dlib.lib.SparseFrame_factorize(C.byref(common), None, C.byref(m_info))
             if rc != 0:
-                raise RuntimeError(_capi.last_error())
+                raise RuntimeError("SparseFrame_factorize returned %d" % rc)
     else:
         # every rank uploads the values and brings home the panels it owns, packed (sfb200_factorize_owned): same C-ABI call
         # shape as the single-GPU one, host buffers in and out
@@ -526,8 +563,9 @@ def main():
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": int(world * (lx.nbytes + (ux.nbytes if split else 0))),
                     "d2h_bytes_per_step": int(d2h_total.item()),
-                    "api": "sfb200_factorize (host Lx -> host Lsx, pinned)" if world == 1 else
-                           "per rank: H2D values, partitioned factorization, D2H of the owned panels (pinned)"},
+                    "api": "SparseFrame_factorize of %s/Lib/libSparseFrame.so (host Lx -> host Lsx, page-locked)" % ("LU" if kind == "lu" else "Cholesky")
+                           if world == 1 else
+                           "sfb200_factorize_owned per rank: H2D of the values, partitioned factorization, D2H of the owned panels (page-locked)"},
             "roofline": roof, "cpu_baseline": base,
         }
         if world > 1:

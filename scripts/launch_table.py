@@ -22,6 +22,15 @@ for lev in sorted(set(rows[:, 1].astype(int))):
         rk = r[r[:, 0] == k]
         if len(rk): line += " %s %d launches %.2f ms (%.1f TF/s)" % (names[k], len(rk), rk[:, 4].sum(), rk[:, 5].sum() / max(rk[:, 4].sum(), 1e-9) / 1e9)
     print(line)
+# 64x64-tile kernel by K class
+g6 = rows[rows[:, 0] == 6]
+for lo, hi in ((0, 65), (65, 129), (129, 257), (257, 1025), (1025, 1e9)):
+    sel = (g6[:, 6] >= lo) & (g6[:, 6] < hi)
+    if sel.any():
+        print("gemm64  Kmax in [%d,%d): %3d launches %7.2f ms  %.2f TF/s  ideal %.2f ms" % (lo, hi, sel.sum(), g6[sel, 4].sum(), g6[sel, 5].sum() / g6[sel, 4].sum() / 1e9, g6[sel, 5].sum() / peak * 1e3))
+for k in (2, 4):
+    rk = rows[rows[:, 0] == k]
+    if len(rk): print("%s: %d launches, %.2f ms, %.1f us per launch" % (names[k], len(rk), rk[:, 4].sum(), 1e3 * rk[:, 4].sum() / len(rk)))
 # gemm128 launches by K class
 g = rows[(rows[:, 0] == 5) | (rows[:, 0] == 7)]
 for lo, hi in ((0, 65), (65, 257), (257, 1025), (1025, 1e9)):

@@ -470,6 +470,7 @@ int sfb200_plan_create_part(const sfb200_symbolic *s, int device, int rank, int 
     if (const char *e = getenv("SFB200_LU_UT_COPY")) prm.lu_ut_copy = atoi(e);
     if (const char *e = getenv("SFB200_LOOKAHEAD")) prm.lookahead = atoi(e);
     if (const char *e = getenv("SFB200_LEAF_LOOKAHEAD")) prm.leaf_lookahead = atoi(e);
+    if (const char *e = getenv("SFB200_LEFT_LOOKING")) prm.left_looking = atoi(e);
     const int rc = build_plan(s->S, prm, p->H, rank, world);
     if (rc != 0) {
         delete p;

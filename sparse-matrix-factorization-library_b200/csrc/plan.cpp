@@ -44,6 +44,7 @@ struct PanelEmitter {
 
     bool lookahead = false;
     bool leaf_lookahead = false;
+    bool left_looking = false;
     i64 woff = -1;                // LU: offset of this front's U11^T scratch (ldw x nscol, element U11[k, j] at woff + j + k * ldw)
     int ldw = 0;
 
@@ -111,12 +112,25 @@ struct PanelEmitter {
         // leaf look-ahead (sub-blocks are leaves): the update of leaf i leaves the next diagonal block alone; that block
         // subtracts the K = w product itself, so its factorization depends on leaf i's solves only, not on the update
         const bool leaf_la = leaf_lookahead && depth == 1;
+        // Cholesky, every level below the top one: LEFT-looking inside the block.  Sub-block i first pulls the updates of
+        // all earlier sub-blocks of this block (one GEMM, K = b0 - c0, on its own columns only) and is then factorized;
+        // nothing is pushed to the right.  Same flops as the right-looking order, but every C entry of the block is
+        // read-modified-written once instead of once per earlier sub-block, and K grows from w to (c1 - c0) - w: the rank-64
+        // updates of the leaves were RMW-bound (4 flop/B).  The top level stays right-looking: its trailing updates are the
+        // big K = outer2 GEMMs and carry the look-ahead split.
+        const bool left = left_looking && !lu && depth < (int)widths.size();
         int i = 0;
         for (int b0 = c0; b0 < c1; b0 += w, ++i) {
             const int b1 = std::min(b0 + w, c1), K = b1 - b0;
-            if (depth == 1) leaf(b0, b1, slot + i * stride, leaf_la && i > 0 ? b0 - w : -1);
+            if (left && i > 0) {
+                // issued in the slot the right-looking order would have used for the update after sub-block i - 1
+                const int ps = slot + (i - 1) * stride + nslots[depth - 1];
+                gemm(ps, x + b0 + (i64)c0 * ld, x + b0 + (i64)c0 * ld, x + b0 + (i64)b0 * ld, R - b0, b1 - b0, b0 - c0, G_LOWER, false,
+                     leaf_la ? b1 - b0 : 0);
+            }
+            if (depth == 1) leaf(b0, b1, slot + i * stride, leaf_la && i > 0 ? (left ? c0 : b0 - w) : -1);
             else block(b0, b1, depth - 1, slot + i * stride);
-            if (b1 >= c1) continue;
+            if (b1 >= c1 || left) continue;
             const int head = leaf_la ? std::min(b1 + w, c1) - b1 : 0;
             const int gs = slot + i * stride + nslots[depth - 1];
             // look-ahead split of the TOP-level update: [b1, s1) = the next block column (main stream), [s1, c1) = the rest
@@ -615,6 +629,7 @@ int build_plan(const Symbolic &S, const PlanParams &prm, HostPlan &P, int rank, 
                 PanelEmitter pe(d, lu, widths, slots);
                 pe.lookahead = prm.lookahead != 0;
                 pe.leaf_lookahead = prm.leaf_lookahead != 0;
+                pe.left_looking = prm.left_looking != 0;
                 if (lu && prm.lu_ut_copy && d.nscol > prm.nb) {      // a front with more than one leaf has in-panel updates
                     pe.ldw = (int)round_up(d.nscol, 2);
                     pe.woff = P.xsize_pad + P.wsize;
@@ -655,6 +670,7 @@ int build_plan(const Symbolic &S, const PlanParams &prm, HostPlan &P, int rank, 
                     if (b0 >= d.nscol || block_owner(s, b) != rank) continue;
                     PanelEmitter pe(d, false, dist_widths, fs);
                     pe.leaf_lookahead = prm.leaf_lookahead != 0;
+                    pe.left_looking = prm.left_looking != 0;
                     pe.block(b0, std::min(b0 + Wd, (int)d.nscol), 1, 0);
                 }
                 emit_slots(fs, 0);

@@ -25,6 +25,8 @@ struct PlanParams {
                                  // cfg1 7.12 -> 6.81; profiles/r01_sweep_min_k_cfg4_cfg1_cfg2.log) -- and 0 on partitioned
                                  // plans, where it has not been measured
     int leaf_lookahead = 1;      // diagonal block j+1 applies leaf j's update to itself and is factorized next to that update
+    int left_looking = 1;        // Cholesky: blocks below the top level pull their updates (left-looking) instead of pushing
+                                 // rank-nb / rank-outer updates to the right: half the C traffic, longer K (PanelEmitter::block)
     int lookahead = 1;           // split the top-level trailing updates (see LaunchFlags) -- needs outer2 > 0
     int use_ws = 1;              // big GEMM ops with a row-major B go to the warp-specialized bulk-copy kernel
     int lu_ut_copy = 1;          // LU: large fronts keep U11^T in a scratch area behind the factor (written by the row-block

@@ -12,9 +12,18 @@
  *                                             multi-threaded parse, plus a binary container (matrix_reader.hpp)
  *   SparseFrame_analyze        CH.c:1916-1978 host symbolic analysis (csrc/symbolic.cpp), bit-exact arrays, plus the
  *                                             device plan (cached per matrix_info, freed by cleanup)
- *   SparseFrame_factorize      CH.c:3019-3034 sfb200_factorize: H2D of Lx, GPU numeric factorization, D2H into Lsx
- *   SparseFrame_solve_supernodal / _validate  CH.c:3036-3266  host loops, same formulae and printed line
- *   SparseFrame                CH.c:3323-3467 same driver and report format (matrices processed one after another)
+ *   SparseFrame_factorize      CH.c:3019-3034 sfb200_factorize: H2D of Lx, GPU numeric factorization, D2H into Lsx; with
+ *                                             numGPU > 1 the etree-partitioned plan on all of them (sfb200_group_*: one host
+ *                                             thread per GPU, like CH.c:2267-2290; exchange over NVLink peer memory)
+ *   SparseFrame_solve_supernodal / _validate  CH.c:3036-3266  host loops, same formulae and printed line (on the device
+ *                                             while the factor is still resident on a single GPU)
+ *   SparseFrame                CH.c:3323-3467 same driver and report format, MATRIX_THREAD_NUM matrices in flight
+ *                                             (CH.c:3371-3444): one is read / analysed while another one factorizes
+ *
+ * devSlotSize policy.  The symbolic structure depends on it (supernode caps, relaxed merging), so it is derived exactly as
+ * the reference derives it for the GPUs this library USES (SF_NUM_GPU, default: all visible): on one B200 5.38e9, on eight
+ * 21.5e9 (no "GPU splitting", CH.c:36-41).  SF_DEVSLOT overrides; bench.py and the tests pin 5.38e9 for every N so that all
+ * measured runs share one structure per matrix.
  */
 #ifdef SPARSEFRAME_LU
 #define SF_KIND SFB200_LU
@@ -45,8 +54,11 @@ namespace {
 
 struct Cached {
     sfb200_symbolic *sym = nullptr;
-    sfb200_plan *plan = nullptr;
+    sfb200_plan *plan = nullptr;       // single-GPU plan, or
+    sfb200_group *group = nullptr;     // the etree partition over numGPU devices
+    int ngpu = 1;
     bool pinned_lsx = false;
+    bool factor_ok = false;            // the last SparseFrame_factorize of this matrix succeeded
 };
 std::map<const matrix_info_struct *, Cached> g_cache;
 std::mutex g_mutex;
@@ -103,11 +115,25 @@ void store_order(const std::string &path, const sfb200_symbolic *s) {
     else remove(tmp.c_str());
 }
 
+// device side of one matrix: a plan on GPU 0, or the etree partition over the first ngpu devices
+int create_device_side(Cached &c, int ngpu) {
+    c.ngpu = ngpu > 1 ? ngpu : 1;
+    int world = c.ngpu;
+    // test hook: SF_PARTITION_RANKS=N runs an N-way partition on the GPUs at hand (ranks round-robin over them), so that the
+    // multi-GPU path of this entry point can be exercised on a one-GPU box
+    if (const char *e = getenv("SF_PARTITION_RANKS")) { const int w = atoi(e); if (w >= 1 && w <= 16) world = w; }
+    if (world == 1) return sfb200_plan_create(c.sym, 0, &c.plan);
+    std::vector<int> devices(world);
+    for (int r = 0; r < world; ++r) devices[r] = r % c.ngpu;
+    return sfb200_group_create(c.sym, world, devices.data(), &c.group);
+}
+
 void drop_cached(const matrix_info_struct *m) {
     std::lock_guard<std::mutex> lk(g_mutex);
     auto it = g_cache.find(m);
     if (it == g_cache.end()) return;
     if (it->second.plan) sfb200_plan_free(it->second.plan);
+    if (it->second.group) sfb200_group_free(it->second.group);
     if (it->second.sym) sfb200_symbolic_free(it->second.sym);
     g_cache.erase(it);
 }
@@ -123,7 +149,10 @@ double SparseFrame_time(void) {
 }
 
 int SparseFrame_allocate_gpu(struct common_info_struct *common_info, struct gpu_info_struct **gpu_info_list_ptr) {
-    const int ngpu = sfb200_device_count();
+    const int visible = sfb200_device_count();
+    int ngpu = visible;
+    if (const char *e = getenv("SF_NUM_GPU")) { const int want = atoi(e); if (want >= 1 && want < ngpu) ngpu = want; }
+    if (ngpu > 16) ngpu = 16;
     common_info->numGPU_physical = ngpu;
     common_info->numGPU = ngpu;
     common_info->numCPU = 0;
@@ -351,9 +380,10 @@ int SparseFrame_analyze(struct common_info_struct *common_info, struct matrix_in
     printf("nrow = %ld nfsuper = %ld nsuper = %ld nstage = %ld\n", n, (long)sfb200_symbolic_int(s, "nfsuper"), m->nsuper,
            m->nstage);
     /* the numeric plan (levels, batched task lists, relative-index tables) is symbolic work too: build + upload now */
-    if (sfb200_plan_create(s, 0, &c.plan) != SFB200_OK) {
+    if (create_device_side(c, common_info->numGPU) != SFB200_OK) {
         printf("SparseFrame_analyze: no device plan (%s)\n", sfb200_last_error());
         c.plan = nullptr;
+        c.group = nullptr;
     }
     {
         std::lock_guard<std::mutex> lk(g_mutex);
@@ -365,7 +395,6 @@ int SparseFrame_analyze(struct common_info_struct *common_info, struct matrix_in
 
 int SparseFrame_factorize(struct common_info_struct *common_info, struct gpu_info_struct *gpu_info_list,
                           struct matrix_info_struct *m) {
-    (void)common_info;
     const double t0 = SparseFrame_time();
     Cached c;
     {
@@ -374,7 +403,7 @@ int SparseFrame_factorize(struct common_info_struct *common_info, struct gpu_inf
         if (it != g_cache.end()) c = it->second;
     }
     int rc = SFB200_OK;
-    if (!c.plan) {
+    if (!c.plan && !c.group) {
         /* structure produced by somebody else's analysis (e.g. the reference's): wrap what factorize reads */
         const int64_t *up = nullptr, *ui = nullptr;
 #ifdef SPARSEFRAME_LU
@@ -383,19 +412,25 @@ int SparseFrame_factorize(struct common_info_struct *common_info, struct gpu_inf
         rc = sfb200_symbolic_wrap(SF_KIND, m->nrow, m->nsuper, (const int64_t *)m->Super, (const int64_t *)m->Lsip,
                                   (const int64_t *)m->Lsxp, (const int64_t *)m->Lsi, (const int64_t *)m->Lp,
                                   (const int64_t *)m->Li, up, ui, &c.sym);
-        if (rc == SFB200_OK) rc = sfb200_plan_create(c.sym, 0, &c.plan);
+        if (rc == SFB200_OK) rc = create_device_side(c, common_info ? common_info->numGPU : 1);
         if (rc != SFB200_OK) { printf("SparseFrame_factorize: %s\n", sfb200_last_error()); return rc; }
         std::lock_guard<std::mutex> lk(g_mutex);
         g_cache[m] = c;
     }
-    if (gpu_info_list) omp_set_lock(&gpu_info_list[0].gpuLock);      /* one matrix at a time per device (CH.c:2287) */
+    /* one matrix at a time per device (CH.c:2287): the locks of all devices this matrix runs on, in index order */
+    if (gpu_info_list) for (int d = 0; d < c.ngpu; ++d) omp_set_lock(&gpu_info_list[d].gpuLock);
     const double *ux = nullptr;
 #ifdef SPARSEFRAME_LU
     if (!m->isSymmetric) ux = m->Ux;
 #endif
-    rc = sfb200_factorize(c.plan, m->Lx, ux, m->Lsx);
-    if (gpu_info_list) omp_unset_lock(&gpu_info_list[0].gpuLock);
+    rc = c.group ? sfb200_group_factorize(c.group, m->Lx, ux, m->Lsx) : sfb200_factorize(c.plan, m->Lx, ux, m->Lsx);
+    if (gpu_info_list) for (int d = c.ngpu - 1; d >= 0; --d) omp_unset_lock(&gpu_info_list[d].gpuLock);
     if (rc != SFB200_OK) printf("SparseFrame_factorize: %s\n", sfb200_last_error());
+    {
+        std::lock_guard<std::mutex> lk(g_mutex);
+        auto it = g_cache.find(m);
+        if (it != g_cache.end()) it->second.factor_ok = rc == SFB200_OK;
+    }
     m->factorizeTime = SparseFrame_time() - t0;
     return rc;
 }
@@ -410,7 +445,7 @@ int SparseFrame_solve_supernodal(struct matrix_info_struct *m) {
             auto it = g_cache.find(m);
             if (it != g_cache.end()) c = it->second;
         }
-        if (c.plan && !getenv("SF_HOST_SOLVE")) {
+        if (c.plan && c.factor_ok && !getenv("SF_HOST_SOLVE")) {
             memcpy(m->Xx, m->Bx, (size_t)m->nrow * sizeof(Float));
             if (sfb200_solve(c.plan, m->Xx, 1) == SFB200_OK) {
                 m->solveTime = SparseFrame_time() - t0;
@@ -567,30 +602,37 @@ int SparseFrame(int argc, char **argv) {
         return 1;
     }
     common.numSparseMatrix = argc - 1;
-    common.matrixThreadNum = 1;
+    common.matrixThreadNum = MATRIX_THREAD_NUM < common.numSparseMatrix ? MATRIX_THREAD_NUM : (common.numSparseMatrix > 0 ? common.numSparseMatrix : 1);
+    if (const char *e = getenv("SF_MATRIX_THREADS")) { const int t = atoi(e); if (t >= 1 && t <= 16) common.matrixThreadNum = t; }
     printf("Num of matrices = %d\n\n", common.numSparseMatrix);
     SparseFrame_allocate_matrix(&common, &mats);
     common.allocateTime = SparseFrame_time() - t0;
     printf("Allocate time:        %lf\n\n", common.allocateTime);
 
     t0 = SparseFrame_time();
+    /* matrixThreadNum matrices in flight (CH.c:3371-3444): while one factorizes (it holds the device locks), the next one is
+     * read and analysed; every thread works in its own matrix_info slot */
+    omp_set_nested(1);
+#pragma omp parallel for num_threads(common.matrixThreadNum) schedule(dynamic, 1)
     for (int k = 0; k < common.numSparseMatrix; ++k) {
-        struct matrix_info_struct *m = mats;
+        struct matrix_info_struct *m = mats + omp_get_thread_num();
         m->serial = k;
         m->path = argv[1 + k];
         SparseFrame_initialize_matrix(m);
         if (SparseFrame_read_matrix(m) != 0) { printf("cannot read %s\n\n", m->path); continue; }
         if (SparseFrame_analyze(&common, m) != 0) { SparseFrame_cleanup_matrix(m); continue; }
-        cudaDeviceSynchronize();
         SparseFrame_factorize(&common, gpus, m);
         SparseFrame_validate(m);
         SparseFrame_cleanup_matrix(m);
-        printf("Matrix name:    %s\n", basename((char *)argv[1 + k]));
-        printf("Read time:      %lf\n", m->readTime);
-        printf("Analyze time:   %lf\n", m->analyzeTime);
-        printf("Factorize time: %lf\n", m->factorizeTime);
-        printf("Solve time:     %lf\n", m->solveTime);
-        printf("residual (|Ax-b|)/(|A||x|+|b|): %le\n\n", m->residual);
+#pragma omp critical(sparseframe_report)
+        {
+            printf("Matrix name:    %s\n", basename((char *)argv[1 + k]));
+            printf("Read time:      %lf\n", m->readTime);
+            printf("Analyze time:   %lf\n", m->analyzeTime);
+            printf("Factorize time: %lf\n", m->factorizeTime);
+            printf("Solve time:     %lf\n", m->solveTime);
+            printf("residual (|Ax-b|)/(|A||x|+|b|): %le\n\n", m->residual);
+        }
     }
     common.computeTime = SparseFrame_time() - t0;
     printf("Total computing time: %lf\n\n", common.computeTime);

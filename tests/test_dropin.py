@@ -84,6 +84,52 @@ int main(void) {
     assert subprocess.check_output([str(exe)], text=True).split() == "1 0 0 1 0 0 2048 -400 1 0 2 512 256 -1".split()
 
 
+@pytest.mark.parametrize("tree", ["Cholesky", "LU"])
+def test_python_mirror_of_the_structs_has_the_reference_layout(tree):
+    """sparseframe_b200/dropin.py (what bench.py's end-to-end leg calls SparseFrame_factorize through) against the same
+    numbers."""
+    from sparseframe_b200 import dropin as D
+    M = D.matrix_info_struct_lu if tree == "LU" else D.matrix_info_struct_cholesky
+    got = [C.sizeof(D.common_info_struct), C.sizeof(D.gpu_info_struct), C.sizeof(M), D.common_info_struct.devSlotSize.offset,
+           D.gpu_info_struct.lastMatrix.offset, D.gpu_info_struct.s_cublasHandle.offset, M.Lp.offset, M.Lsx.offset, M.Perm.offset,
+           M.workspace.offset, M.factorizeTime.offset]
+    assert got == REFERENCE_ABI[tree]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind,gen,g", [("cholesky", "lap3d", 16), ("lu", "cd3d", 12)])
+def test_factorize_symbol_called_like_a_c_program_would(kind, gen, g):
+    """SparseFrame_factorize of the drop-in library through ctypes with a hand-filled matrix_info (structure from an analysis,
+    page-locked Lx / Lsx): the path bench.py's e2e number takes."""
+    import numpy as np
+    import torch
+    import sforacle
+    import sparseframe_b200 as sf
+    from sparseframe_b200 import dropin as D
+    S = sf.analyze(sf.compress(*sf.matrices.generate(gen, g)), kind)
+    lib = D.Library(kind)
+    split = kind == "lu" and S.int("symmetric") == 0
+    h_lx = torch.from_numpy(S.array("Lx")).pin_memory()
+    h_ux = torch.from_numpy(S.array("Ux")).pin_memory() if split else None
+    h_out = torch.zeros(S.int("xsize"), dtype=torch.float64).pin_memory()
+    keep = []
+    m = lib.matrix_from_structure(S, h_lx.data_ptr(), h_ux.data_ptr() if split else 0, h_out.data_ptr(), keep)
+    common = D.common_info_struct(numGPU=1, numGPU_physical=1, devSlotSize=sf.DEFAULT_DEVSLOT)
+    for _ in range(3):
+        h_out.zero_()
+        assert lib.lib.SparseFrame_factorize(C.byref(common), None, C.byref(m)) == 0
+        assert m.factorizeTime > 0
+    st = {k: S.array(k) for k in ("Super", "SuperMap", "Lsip", "Lsxp", "Lsi", "LeafQueue", "Lp", "Li")}
+    st["csize"], st["nsleaf"] = S.int("csize"), S.int("nsleaf")
+    ux = None
+    if split:
+        st["Up"], st["Ui"] = S.array("Up"), S.array("Ui")
+        ux = S.array("Ux")
+    ref, bad = sforacle.factorize(kind, st, S.array("Lx"), ux)
+    mask = sf.lower_trapezoid_mask(kind, st["Super"], st["Lsip"], st["Lsxp"], len(ref))
+    assert bad == 0 and sf.entrywise_rel_diff(ref[mask], h_out.numpy()[mask]) <= 1e-10
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("tree,gen,g", [("Cholesky", "lap3d", 14), ("LU", "cd3d", 12)])
 def test_demo_runs_and_reports_small_residual(tree, gen, g, tmp_path):
@@ -94,6 +140,40 @@ def test_demo_runs_and_reports_small_residual(tree, gen, g, tmp_path):
     line = [ln for ln in out.splitlines() if ln.startswith("residual")][0]
     assert float(line.split(":")[1]) < 1e-13, out
     assert "Factorize time:" in out
+
+
+@pytest.mark.gpu
+def test_driver_keeps_two_matrices_in_flight(tmp_path):
+    """SparseFrame() processes its matrices MATRIX_THREAD_NUM = 2 at a time (CH.c:3371-3444): concurrent callers of
+    SparseFrame_analyze / SparseFrame_factorize / SparseFrame_validate on different matrix_info and the same gpu_info_list."""
+    import sparseframe_b200 as sf
+    paths = []
+    for gen, g in (("lap3d", 20), ("lap2d", 200), ("lap3d", 16), ("lap2d", 90), ("lap3d", 24)):
+        p = tmp_path / ("%s_%d.mtx" % (gen, g))
+        sf.matrices.write_matrix_market(str(p), *sf.matrices.generate(gen, g))
+        paths.append(str(p))
+    out = subprocess.check_output([os.path.join(PKG, "Cholesky", "Demo", "demo")] + paths, text=True)
+    res = [float(ln.split(":")[1]) for ln in out.splitlines() if ln.startswith("residual")]
+    names = [ln.split(":")[1].strip() for ln in out.splitlines() if ln.startswith("Matrix name")]
+    assert len(res) == 5 and max(res) < 1e-13, out
+    assert sorted(names) == sorted(os.path.basename(p) for p in paths)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("tree,gen,g", [("Cholesky", "lap3d", 24), ("LU", "cd3d", 16)])
+def test_factorize_entry_point_drives_the_partitioned_plan(tree, gen, g, tmp_path):
+    """SparseFrame_factorize with more than one rank: the etree partition runs inside the call, one host thread per rank
+    (CH.c:2267-2290).  On a one-GPU box the ranks share the GPU (SF_PARTITION_RANKS); with several GPUs every rank has its own."""
+    import torch
+    import sparseframe_b200 as sf
+    path = tmp_path / ("%s_%d.mtx" % (gen, g))
+    sf.matrices.write_matrix_market(str(path), *sf.matrices.generate(gen, g))
+    ranks = max(2, min(torch.cuda.device_count(), 4))
+    env = dict(os.environ, SF_PARTITION_RANKS=str(ranks), SFB200_DIST_MIN_M="48", SFB200_DIST_PANEL_MIN="256", SFB200_OUTER="128",
+               SFB200_OUTER2="256", CUDA_DEVICE_MAX_CONNECTIONS="32", SF_DEVSLOT="5380000000")
+    out = subprocess.check_output([os.path.join(PKG, tree, "Demo", "demo"), str(path)], text=True, env=env, timeout=600)
+    line = [ln for ln in out.splitlines() if ln.startswith("residual")][0]
+    assert float(line.split(":")[1]) < 1e-13, out
 
 
 # The reference calls its entry points from an OpenMP loop over matrices (MATRIX_THREAD_NUM concurrent callers, different
