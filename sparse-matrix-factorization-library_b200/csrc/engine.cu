@@ -3,8 +3,10 @@
 // per-descendant loop, no PCIe staging of panels, no cuBLAS / cuSOLVER -- a fixed sequence of batched launches over
 // a factor that never leaves HBM until the final copy-out.
 #include <chrono>
+#include <condition_variable>
 #include <cstdio>
 #include <cstring>
+#include <functional>
 #include <map>
 #include <mutex>
 #include <string>
@@ -69,6 +71,9 @@ struct sfb200_plan {
     struct CachedGraph { cudaGraphExec_t exec; int64_t launches; };
     std::map<std::tuple<int, size_t, size_t, const void *>, CachedGraph> graphs;
     bool use_graphs = true, graphs_wanted = true;
+    // ranks of one process (sfb200_group): called right before a freshly instantiated graph is launched, so that every rank
+    // has finished capturing / instantiating (which may allocate) before the first one starts waiting on the device
+    std::function<void()> before_first_graph_launch;
     // streamed copy-out (host-buffer call with a page-locked Lsx): copy stream, per-level work lists
     cudaStream_t copy_stream = nullptr;
     std::vector<cudaEvent_t> copy_events;
@@ -80,7 +85,7 @@ struct sfb200_plan {
     // small panels are first packed on the device into the dense reference layout (d_out), then leave as contiguous runs
     // of the dense buffer: per level, [offset, count) element ranges that become final at that level.  All levels up to
     // `merge_level` are flushed together (their supernodes are neighbours in the postorder, so the runs are long).
-    std::vector<std::vector<std::pair<i64, i64>>> small_runs;
+    std::vector<std::vector<std::pair<i64, i64>>> small_runs;     // per flush level: (first supernode of the run, elements)
     int merge_level = 0;
     int top_width = 256;                               // width of the widest blocking level
     // ---- partitioned plans (world > 1): exchange over peer memory, see plan_types.h (Coll) ---------------------------
@@ -103,6 +108,7 @@ struct sfb200_plan {
     // device-to-host copy per run of consecutive owned supernodes
     struct OutRun { i64 packed, lsx, count; };
     std::vector<OutRun> out_runs;
+    std::vector<i64> packed_off;                       // offset of every owned panel in the packed layout (-1: not owned)
     i64 out_elems = 0;
     int n_pack = 0;
     size_t device_bytes = 0;
@@ -142,6 +148,13 @@ int upload(sfb200_plan *p, T *&dptr, const std::vector<T> &h) {
     CK(cudaMalloc((void **)&dptr, h.size() * sizeof(T)));
     p->device_bytes += h.size() * sizeof(T);
     CK(cudaMemcpyAsync(dptr, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice, p->stream));
+    return SFB200_OK;
+}
+
+int ensure_out(sfb200_plan *p) {
+    if (p->d_out) return SFB200_OK;
+    CK(cudaMalloc((void **)&p->d_out, sizeof(double) * (size_t)std::max<i64>(p->out_elems, 1)));
+    p->device_bytes += sizeof(double) * (size_t)p->out_elems;
     return SFB200_OK;
 }
 
@@ -342,6 +355,7 @@ int run_graphed(sfb200_plan *p, int kind, size_t first, size_t count, const void
         if (ei != cudaSuccess) { set_error(std::string("cudaGraphInstantiate: ") + cudaGetErrorString(ei)); return SFB200_ERR_CUDA; }
         it->second = sfb200_plan::CachedGraph{ex, p->launches - before};
         p->launches = before;
+        if (p->before_first_graph_launch) p->before_first_graph_launch();
     }
     CK(cudaGraphLaunch(it->second.exec, p->stream));
     p->launches += it->second.launches;
@@ -502,8 +516,10 @@ int sfb200_plan_create_part(const sfb200_symbolic *s, int device, int rank, int 
         const bool lu_ = H.kind == Kind::LU;
         std::vector<PackTask> ptasks;
         i64 packed = 0;
+        p->packed_off.assign(H.nsuper, -1);
         for (i64 sidx = 0; sidx < H.nsuper; ++sidx) {
             if (H.owner[sidx] != H.rank) continue;
+            p->packed_off[sidx] = packed;
             const SnodeDev &d = H.snode[sidx];
             const int rows = lu_ ? 2 * d.nsrow - d.nscol : d.nsrow;
             const i64 elems = (i64)rows * d.nscol;
@@ -522,6 +538,11 @@ int sfb200_plan_create_part(const sfb200_symbolic *s, int device, int rank, int 
         p->out_elems = packed;
         p->n_pack = (int)ptasks.size();
         if ((err = upload(p, p->d_pack, ptasks))) return fail(err);
+        // A rank of a partition must not allocate (cudaMalloc may wait for the device to go idle, with the context lock held)
+        // between the launch of its part and the moment every rank has launched its own: a rank whose flag wait is already
+        // spinning on the device would then block the host thread that is about to launch the signal it waits for (seen in
+        // round 2 with several ranks in one process).  Its copy-out buffer therefore exists from the start.
+        if (H.world > 1 && (err = ensure_out(p))) return fail(err);
     }
     if ((err = upload(p, p->d_lsi32, H.lsi32))) return fail(err);
     if ((err = upload(p, p->d_nz_col, H.nz_col))) return fail(err);
@@ -597,21 +618,29 @@ int sfb200_plan_create_part(const sfb200_symbolic *s, int device, int rank, int 
             cudaEventCreateWithFlags(&p->ev_to_diag, cudaEventDisableTiming) != cudaSuccess ||
             cudaEventCreateWithFlags(&p->ev_from_diag, cudaEventDisableTiming) != cudaSuccess) { set_error("diagonal-block stream"); return fail(SFB200_ERR_CUDA); }
     }
-    {   // copy-out work lists: small panels go through k_pack (written straight into mapped host memory), panels of
-        // at least 1 MiB through the DMA engine (cudaMemcpy2DAsync), block column by block column for the widest fronts
+    {   // copy-out work lists of the panels this rank owns: small panels are packed on the device (k_pack, packed layout in
+        // d_out) and leave as long contiguous runs; panels of at least 1 MiB go straight from the image through the DMA engine
+        // (cudaMemcpy2DAsync), block column by block column for the widest fronts of a single-GPU plan
         const bool lu = H.kind == Kind::LU;
         p->top_width = prm.outer2 > 0 ? prm.outer2 : prm.outer;
         p->big_by_level.assign(H.nlevels, {});
         std::vector<std::vector<PackTask>> small(H.nlevels);
-        for (i64 sidx = 0; sidx < H.nsuper && H.world == 1; ++sidx) {      // streamed copy-out: single-GPU plans
+        auto owned = [&](i64 sidx) { return H.owner[sidx] == H.rank; };
+        auto is_small = [&](i64 sidx) {
             const SnodeDev &d = H.snode[sidx];
             const int rows = lu ? 2 * d.nsrow - d.nscol : d.nsrow;
-            if ((i64)rows * d.nscol * 8 >= (1 << 20)) { p->big_by_level[d.level].push_back(sidx); continue; }
+            return (i64)rows * d.nscol * 8 < (1 << 20);
+        };
+        for (i64 sidx = 0; sidx < H.nsuper; ++sidx) {
+            if (!owned(sidx)) continue;
+            const SnodeDev &d = H.snode[sidx];
+            const int rows = lu ? 2 * d.nsrow - d.nscol : d.nsrow;
+            if (!is_small(sidx)) { p->big_by_level[d.level].push_back(sidx); continue; }
             const int chunk = std::max(1, 65536 / std::max(rows, 1));
             for (int c0 = 0; c0 < d.nscol; c0 += chunk) {
                 PackTask t{};
                 t.src = d.xoff + (i64)c0 * d.ld;
-                t.dst = H.lsxp[sidx] + (i64)c0 * rows;
+                t.dst = p->packed_off[sidx] + (i64)c0 * rows;
                 t.rows = rows; t.ld = d.ld; t.cols = std::min(chunk, d.nscol - c0);
                 small[d.level].push_back(t);
             }
@@ -622,21 +651,17 @@ int sfb200_plan_create_part(const sfb200_symbolic *s, int device, int rank, int 
             flat.insert(flat.end(), small[l].begin(), small[l].end());
         }
         if ((err = upload(p, p->d_spack, flat))) return fail(err);
-        if (H.world == 1) {
+        {
             // Flush point: every level up to `merge_level` leaves in one batch when that level is final.  Each run costs
             // one copy call (a few microseconds of host time during which no kernel is enqueued), and the leaf-side levels
             // interleave in the postorder -- cfg2: 18 246 runs if every level flushes on its own, 467 when levels 0..5 go
             // together -- so the merge level is the lowest one that keeps the whole factorization under 512 runs.
-            auto is_small = [&](i64 sidx) {
-                const SnodeDev &d = H.snode[sidx];
-                const int rows = lu ? 2 * d.nsrow - d.nscol : d.nsrow;
-                return (i64)rows * d.nscol * 8 < (1 << 20);
-            };
+            // A run = consecutive owned small supernodes: contiguous in the packed layout and in the reference's Lsx.
             auto count_runs = [&](int ml) {
                 i64 runs = 0;
                 int prev = -1;
                 for (i64 sidx = 0; sidx < H.nsuper; ++sidx) {
-                    if (!is_small(sidx)) { prev = -1; continue; }
+                    if (!owned(sidx) || !is_small(sidx)) { prev = -1; continue; }
                     const int fl = std::max<int>(H.snode[sidx].level, ml);
                     if (fl != prev) ++runs;
                     prev = fl;
@@ -648,11 +673,15 @@ int sfb200_plan_create_part(const sfb200_symbolic *s, int device, int rank, int 
             p->small_runs.assign(H.nlevels, {});
             auto flush_level = [&](i64 sidx) { return std::max<int>(H.snode[sidx].level, p->merge_level); };
             for (i64 sidx = 0; sidx < H.nsuper;) {
-                if (!is_small(sidx)) { ++sidx; continue; }
+                if (!owned(sidx) || !is_small(sidx)) { ++sidx; continue; }
                 const int fl = flush_level(sidx);
-                i64 e = sidx + 1;
-                while (e < H.nsuper && is_small(e) && flush_level(e) == fl) ++e;
-                p->small_runs[fl].push_back({H.lsxp[sidx], H.lsxp[e] - H.lsxp[sidx]});
+                i64 e = sidx + 1, count = 0;
+                while (e < H.nsuper && owned(e) && is_small(e) && flush_level(e) == fl) ++e;
+                for (i64 q = sidx; q < e; ++q) {
+                    const SnodeDev &d = H.snode[q];
+                    count += (i64)(lu ? 2 * d.nsrow - d.nscol : d.nsrow) * d.nscol;
+                }
+                p->small_runs[fl].push_back({sidx, count});       // (first supernode of the run, elements)
                 sidx = e;
             }
         }
@@ -679,6 +708,7 @@ int sfb200_plan_create_part(const sfb200_symbolic *s, int device, int rank, int 
     p->D.relmap = p->d_relmap;
     p->D.status = p->d_status;
     p->D.is_lu = H.kind == Kind::LU;
+    p->D.multi = H.world > 1;
     p->D.dbg = getenv("SFB200_DBG") ? atoi(getenv("SFB200_DBG")) : 0;
     if (const char *e = getenv("SFB200_GRAPHS")) p->use_graphs = p->graphs_wanted = atoi(e) != 0;
     *out = p;
@@ -791,16 +821,9 @@ int sfb200_plan_sync(sfb200_plan *p) {
     return rc;
 }
 
-static int ensure_out(sfb200_plan *p) {
-    if (p->d_out) return SFB200_OK;
-    CK(cudaMalloc((void **)&p->d_out, sizeof(double) * (size_t)std::max<i64>(p->out_elems, 1)));
-    p->device_bytes += sizeof(double) * (size_t)p->out_elems;
-    return SFB200_OK;
-}
-
 /* The panels this rank owns (all of them on a single-GPU plan) into the reference's layout: Lsx is the WHOLE factor array
  * (xsize doubles); a rank of a partitioned plan writes its own panels and leaves the rest alone. */
-static int download(sfb200_plan *p, double *out, bool packed) {
+static int download(sfb200_plan *p, double *out, bool packed, bool wait = true) {
     if (!p || !out) { set_error("sfb200_download_factor: bad argument"); return SFB200_ERR_ARG; }
     if (!p->factored) { set_error("sfb200_download_factor: nothing factorized yet"); return SFB200_ERR_STATE; }
     CK(cudaSetDevice(p->device));
@@ -814,7 +837,7 @@ static int download(sfb200_plan *p, double *out, bool packed) {
         for (const auto &run : p->out_runs)
             CK(cudaMemcpyAsync(out + run.lsx, p->d_out + run.packed, sizeof(double) * (size_t)run.count, cudaMemcpyDeviceToHost, p->stream));
     }
-    CK(cudaStreamSynchronize(p->stream));
+    if (wait) CK(cudaStreamSynchronize(p->stream));
     return SFB200_OK;
 }
 
@@ -846,21 +869,26 @@ cudaEvent_t next_copy_event(sfb200_plan *p) {
     return p->copy_events[p->copy_events_used++];
 }
 
-// copy columns [c0,c1) of supernode s from the padded factor to the reference layout on the host (DMA engine)
-int copy_columns(sfb200_plan *p, i64 sidx, int c0, int c1, double *Lsx) {
+// where an owned panel goes in the caller's buffer: the reference's Lsx layout, or the packed layout of the owned panels
+inline i64 host_off(const sfb200_plan *p, i64 sidx, bool packed) { return packed ? p->packed_off[sidx] : p->H.lsxp[sidx]; }
+
+// copy columns [c0,c1) of supernode s from this rank's image to the host (DMA engine)
+int copy_columns(sfb200_plan *p, i64 sidx, int c0, int c1, double *out, bool packed) {
     const HostPlan &H = p->H;
     const SnodeDev &d = H.snode[sidx];
     const int rows = H.kind == Kind::LU ? 2 * d.nsrow - d.nscol : d.nsrow;
-    CK(cudaMemcpy2DAsync(Lsx + H.lsxp[sidx] + (i64)c0 * rows, sizeof(double) * rows, p->d_X + d.xoff + (i64)c0 * d.ld,
+    CK(cudaMemcpy2DAsync(out + host_off(p, sidx, packed) + (i64)c0 * rows, sizeof(double) * rows, p->d_X + d.xoff + (i64)c0 * d.ld,
                          sizeof(double) * d.ld, sizeof(double) * rows, (size_t)(c1 - c0), cudaMemcpyDeviceToHost,
                          p->copy_stream));
     return SFB200_OK;
 }
 
-// Factorization with the copy-out streamed behind it: as soon as an etree level (or, for the widest fronts, a block
-// column of the level) is final, its panels leave for the host on a second stream while the next level computes.
-int factorize_streamed_issue(sfb200_plan *p, double *Lsx, bool trace) {
+// Factorization with the copy-out streamed behind it: as soon as an etree level (or, for the widest fronts of a single-GPU
+// plan, a block column of the level) is final, the panels this rank owns leave for the host on a second stream while the
+// next level computes.  A partitioned plan runs its segments -- exchange steps, then launches -- level by level.
+int factorize_streamed_issue(sfb200_plan *p, double *out, bool packed, bool trace) {
     const HostPlan &H = p->H;
+    if (H.world > 1) launch_epoch_inc(p->d_epoch, p->stream);
     int rc = begin_factor(p);
     if (rc) return rc;
     p->copy_events_used = 0;
@@ -876,39 +904,52 @@ int factorize_streamed_issue(sfb200_plan *p, double *Lsx, bool trace) {
         const int lev = ph.level;
         const std::vector<i64> &big = p->big_by_level[lev];
         std::vector<int> sent(big.size(), 0);            // columns of each big front already on their way
-        int cur_block = -1;
-        for (int li = ph.launch_first; li < ph.launch_first + ph.launch_count; ++li) {
-            const Launch &L = H.launches[li];
-            if (L.top_block > cur_block && cur_block >= 0) {
-                // the schedule moves on to block column L.top_block: everything left of it is final in every front
-                bool any = false;
-                for (size_t b = 0; b < big.size(); ++b)
-                    if (std::min<int>(H.snode[big[b]].nscol, L.top_block * p->top_width) > sent[b]) any = true;
-                if (any) {
-                    if (!publish()) { set_error("event"); return SFB200_ERR_CUDA; }
-                    for (size_t b = 0; b < big.size(); ++b) {
-                        const int c1 = std::min<int>(H.snode[big[b]].nscol, L.top_block * p->top_width);
-                        if (c1 > sent[b]) { rc = copy_columns(p, big[b], sent[b], c1, Lsx); if (rc) return rc; sent[b] = c1; }
+        if (H.world > 1) {
+            // a level of a partitioned plan: its segments in order; a panel is final once the level is (pushed block columns
+            // of group-factorized fronts have been waited for inside the level)
+            for (int k = ph.seg_first; k < ph.seg_first + ph.seg_count; ++k) {
+                const Segment &sg = H.segments[k];
+                for (int i = sg.coll_first; i < sg.coll_first + sg.coll_count; ++i)
+                    if ((rc = issue_coll(p, (size_t)i))) return rc;
+                if ((rc = run_launches(p, (size_t)sg.launch_first, (size_t)sg.launch_count))) return rc;
+            }
+        } else {
+            int cur_block = -1;
+            for (int li = ph.launch_first; li < ph.launch_first + ph.launch_count; ++li) {
+                const Launch &L = H.launches[li];
+                if (L.top_block > cur_block && cur_block >= 0) {
+                    // the schedule moves on to block column L.top_block: everything left of it is final in every front
+                    bool any = false;
+                    for (size_t b = 0; b < big.size(); ++b)
+                        if (std::min<int>(H.snode[big[b]].nscol, L.top_block * p->top_width) > sent[b]) any = true;
+                    if (any) {
+                        if (!publish()) { set_error("event"); return SFB200_ERR_CUDA; }
+                        for (size_t b = 0; b < big.size(); ++b) {
+                            const int c1 = std::min<int>(H.snode[big[b]].nscol, L.top_block * p->top_width);
+                            if (c1 > sent[b]) { rc = copy_columns(p, big[b], sent[b], c1, out, packed); if (rc) return rc; sent[b] = c1; }
+                        }
                     }
                 }
+                if (L.top_block >= 0) cur_block = std::max(cur_block, (int)L.top_block);
+                rc = issue_launch_la(p, L);
+                if (rc) return rc;
+                ++p->launches;
             }
-            if (L.top_block >= 0) cur_block = std::max(cur_block, (int)L.top_block);
-            rc = issue_launch_la(p, L);
-            if (rc) return rc;
-            ++p->launches;
+            if ((rc = join_side(p))) return rc;
         }
-        if ((rc = join_side(p))) return rc;
         // the level is final: remaining columns of its big fronts, then all of its small fronts
-        if (!publish()) { set_error("event"); return SFB200_ERR_CUDA; }
-        for (size_t b = 0; b < big.size(); ++b) {
-            const int n = H.snode[big[b]].nscol;
-            if (sent[b] < n) { rc = copy_columns(p, big[b], sent[b], n, Lsx); if (rc) return rc; }
-        }
         const auto range = p->spack_range[lev];
-        if (range.second > 0) launch_pack(p->d_X, p->d_out, p->d_spack + range.first, range.second, p->copy_stream);
-        for (const auto &run : p->small_runs[lev])
-            CK(cudaMemcpyAsync(Lsx + run.first, p->d_out + run.first, sizeof(double) * (size_t)run.second, cudaMemcpyDeviceToHost,
-                               p->copy_stream));
+        if (!big.empty() || range.second > 0 || !p->small_runs[lev].empty()) {
+            if (!publish()) { set_error("event"); return SFB200_ERR_CUDA; }
+            for (size_t b = 0; b < big.size(); ++b) {
+                const int n = H.snode[big[b]].nscol;
+                if (sent[b] < n) { rc = copy_columns(p, big[b], sent[b], n, out, packed); if (rc) return rc; }
+            }
+            if (range.second > 0) launch_pack(p->d_X, p->d_out, p->d_spack + range.first, range.second, p->copy_stream);
+            for (const auto &run : p->small_runs[lev])
+                CK(cudaMemcpyAsync(out + host_off(p, run.first, packed), p->d_out + p->packed_off[run.first],
+                                   sizeof(double) * (size_t)run.second, cudaMemcpyDeviceToHost, p->copy_stream));
+        }
         if (trace) {
             cudaEvent_t a, b;
             CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b));
@@ -917,6 +958,11 @@ int factorize_streamed_issue(sfb200_plan *p, double *Lsx, bool trace) {
         }
     }
     CK(cudaGetLastError());
+    if (p->comm_pending) {          // the last pushes of a partitioned plan are on their way before the call counts as done
+        CK(cudaEventRecord(p->ev_from_comm, p->comm_stream));
+        CK(cudaStreamWaitEvent(p->stream, p->ev_from_comm, 0));
+        p->comm_pending = false;
+    }
     if (trace) CK(cudaEventRecord(p->ev[1], p->stream));
     CK(cudaEventRecord(p->copy_done, p->copy_stream));
     CK(cudaStreamWaitEvent(p->stream, p->copy_done, 0));
@@ -933,16 +979,16 @@ int factorize_streamed_issue(sfb200_plan *p, double *Lsx, bool trace) {
     return SFB200_OK;
 }
 
-// Streamed copy-out: kernels, k_pack launches and device-to-host copies of one factorization into `Lsx`, replayed as one
-// CUDA graph per destination buffer from the second call on.
-int factorize_streamed(sfb200_plan *p, double *Lsx) {
+// Streamed copy-out: kernels, exchange steps, k_pack launches and device-to-host copies of one factorization into `out`,
+// replayed as one CUDA graph per destination buffer from the second call on.
+int factorize_streamed(sfb200_plan *p, double *out, bool packed) {
     const HostPlan &H = p->H;
     { const int rco = ensure_out(p); if (rco) return rco; }
     const bool trace = getenv("SFB200_COPY_TRACE") != nullptr;
     p->launches = 0;
     int rc;
-    if (trace) rc = factorize_streamed_issue(p, Lsx, true);
-    else rc = run_graphed(p, 1, 0, H.launches.size(), Lsx, [&]() -> int { return factorize_streamed_issue(p, Lsx, false); });
+    if (trace) rc = factorize_streamed_issue(p, out, packed, true);
+    else rc = run_graphed(p, packed ? 5 : 1, 0, H.launches.size(), out, [&]() -> int { return factorize_streamed_issue(p, out, packed, false); });
     if (rc) return rc;
     if (!trace) CK(cudaEventRecord(p->ev[1], p->stream));      // includes the copy tail (the pieces are one graph)
     return SFB200_OK;
@@ -950,14 +996,21 @@ int factorize_streamed(sfb200_plan *p, double *Lsx) {
 
 }  // namespace
 
-static int factorize_host(sfb200_plan *p, const double *Lx, const double *Ux, double *Lsx, bool packed) {
+// The host-buffer call in two halves: `enqueue` only issues work (uploads, this rank's factorization, pack and copy-out) and
+// never waits for the device; `finish` waits and reads the status.  A group runs the first half on every rank before any
+// rank enters the second (sfb200_group_factorize).
+static int factorize_host_enqueue(sfb200_plan *p, const double *Lx, const double *Ux, double *Lsx, bool packed) {
     if (!p || !Lx) { set_error("sfb200_factorize: bad argument"); return SFB200_ERR_ARG; }
     CK(cudaSetDevice(p->device));
     const HostPlan &H = p->H;
     if (H.split && !Ux) { set_error("unsymmetric LU needs Ux"); return SFB200_ERR_ARG; }
+    if (H.world > 1 && !p->connected) {
+        set_error("sfb200_factorize: this rank of a partitioned plan is not connected to its peers (sfb200_plan_connect / sfb200_group_create)");
+        return SFB200_ERR_STATE;
+    }
     // page-locked destination -> stream the copy-out behind the factorization; pageable -> pack + one copy at the end
     double *alias = nullptr;
-    if (Lsx && H.world == 1 && !packed && !getenv("SFB200_NO_STREAMED_COPY")) {
+    if (Lsx && !getenv("SFB200_NO_STREAMED_COPY")) {
         cudaPointerAttributes attr;
         if (cudaPointerGetAttributes(&attr, Lsx) == cudaSuccess && attr.type == cudaMemoryTypeHost && attr.devicePointer)
             alias = (double *)attr.devicePointer;
@@ -969,23 +1022,33 @@ static int factorize_host(sfb200_plan *p, const double *Lx, const double *Ux, do
     int rc;
     if (alias) {
         CK(cudaEventRecord(p->ev[0], p->stream));
-        rc = factorize_streamed(p, Lsx);
+        rc = factorize_streamed(p, Lsx, packed);
         if (rc) return rc;
         p->factored = true;
     } else {
         rc = sfb200_factorize_device(p, p->d_lx, p->d_ux);
         if (rc) return rc;
         if (Lsx) {
-            rc = download(p, Lsx, packed);
+            rc = download(p, Lsx, packed, false);
             if (rc) return rc;
         }
     }
     CK(cudaEventRecord(p->ev[3], p->stream));
-    rc = sfb200_plan_sync(p);
+    return SFB200_OK;
+}
+
+static int factorize_host_finish(sfb200_plan *p) {
+    CK(cudaSetDevice(p->device));
+    const int rc = sfb200_plan_sync(p);
     float ms = 0.f;
     if (cudaEventElapsedTime(&ms, p->ev[2], p->ev[3]) == cudaSuccess) p->ms_e2e = ms;
     else cudaGetLastError();
     return rc;
+}
+
+static int factorize_host(sfb200_plan *p, const double *Lx, const double *Ux, double *Lsx, bool packed) {
+    const int rc = factorize_host_enqueue(p, Lx, Ux, Lsx, packed);
+    return rc ? rc : factorize_host_finish(p);
 }
 
 int sfb200_factorize(sfb200_plan *p, const double *Lx, const double *Ux, double *Lsx) { return factorize_host(p, Lx, Ux, Lsx, false); }
@@ -1251,6 +1314,7 @@ int sfb200_plan_connect(sfb200_plan *p, const void *handles) {
 
 struct sfb200_group {
     std::vector<sfb200_plan *> plans;
+    long calls = 0;                      // sfb200_group_factorize calls so far (the second one captures the CUDA graphs)
 };
 
 /* All ranks of a partition inside one process, one device per rank (the reference's arrangement: one host thread per GPU
@@ -1310,10 +1374,35 @@ int sfb200_group_factorize(sfb200_group *g, const double *Lx, const double *Ux, 
     std::vector<int> rcs(world, SFB200_OK);
     std::vector<std::string> errs(world);
     std::vector<std::thread> th;
+    // Two halves with a host-side meeting point in between: no thread may enter a call that waits for the device (or takes a
+    // driver lock while doing so) before EVERY rank has launched its part -- the ranks wait for each other on the device.
+    std::mutex mtx;
+    std::condition_variable cv;
+    int arrived = 0;
+    long generation = 0;
+    auto meet = [&]() {                    // reusable barrier of the `world` host threads
+        std::unique_lock<std::mutex> lk(mtx);
+        const long gen = generation;
+        if (++arrived == world) { arrived = 0; ++generation; cv.notify_all(); }
+        else cv.wait(lk, [&] { return generation != gen; });
+    };
+    // the call in which the ranks capture + instantiate their graphs is the same on every rank (the second one): they meet
+    // once more between instantiation and launch
+    const bool will_capture = g->calls == 1 && g->plans[0]->use_graphs;
+    ++g->calls;
     for (int r = 0; r < world; ++r)
         th.emplace_back([&, r]() {
-            rcs[r] = sfb200_factorize(g->plans[r], Lx, Ux, Lsx);
+            bool met = false;
+            g->plans[r]->before_first_graph_launch = [&]() { if (will_capture) { met = true; meet(); } };
+            rcs[r] = factorize_host_enqueue(g->plans[r], Lx, Ux, Lsx, false);
+            g->plans[r]->before_first_graph_launch = nullptr;
             if (rcs[r]) errs[r] = sfb200_last_error();
+            if (will_capture && !met) meet();          // a rank that failed before its launch must not leave the others waiting
+            meet();
+            if (rcs[r] == SFB200_OK) {
+                rcs[r] = factorize_host_finish(g->plans[r]);
+                if (rcs[r]) errs[r] = sfb200_last_error();
+            }
         });
     for (auto &t : th) t.join();
     for (int r = 0; r < world; ++r)

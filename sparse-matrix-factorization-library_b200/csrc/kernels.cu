@@ -41,6 +41,15 @@ __device__ __forceinline__ void dmma(double &c0, double &c1, double a, double b)
                  : "d"(a), "d"(b));
 }
 
+// Fire-and-forget FP64 add into global memory -- this GPU's HBM or, through a peer mapping, another GPU's over NVLink.
+// Explicit PTX: the destination base comes out of a pointer table, so the compiler cannot prove the address space and
+// would emit a generic ATOM (returns a value, plus a shared-memory CAS fallback) instead of RED.  System scope on
+// partitioned plans: several GPUs add into the same entries of a shared panel concurrently.
+__device__ __forceinline__ void red_add(double *addr, double v, int sys) {
+    if (sys) asm volatile("red.relaxed.sys.global.add.f64 [%0], %1;\n" ::"l"(__cvta_generic_to_global(addr)), "d"(v) : "memory");
+    else asm volatile("red.relaxed.gpu.global.add.f64 [%0], %1;\n" ::"l"(__cvta_generic_to_global(addr)), "d"(v) : "memory");
+}
+
 // first op whose tile range contains `tile` (ops sorted by tile0)
 template <class Op>
 __device__ __forceinline__ int find_op(const Op *ops, int nops, int tile) {
@@ -170,7 +179,7 @@ __device__ __forceinline__ void smem_scatter(const PlanDev &P, const double *Sa,
 #pragma unroll
             for (int a = 0; a < 4; ++a) {
                 const int i = i0 + a;
-                if (i < m && i >= lim) atomicAdd(img + col + P.relmap[relb + i], -acc[a][b]);
+                if (i < m && i >= lim) red_add(img + col + P.relmap[relb + i], -acc[a][b], P.multi);
             }
         }
     }
@@ -649,8 +658,8 @@ __global__ void __launch_bounds__(WARPS_M *WARPS_N * 32)
 #pragma unroll
             for (int i = 0; i < FM; ++i) {
                 const int r = row0 + wm0 + 8 * i + 2 * t4;
-                if (r < M && r >= lim) atomicAdd(dst + rel[r], -acc[i][j][0]);
-                if (r + 1 < M && r + 1 >= lim) atomicAdd(dst + rel[r + 1], -acc[i][j][1]);
+                if (r < M && r >= lim) red_add(dst + rel[r], -acc[i][j][0], P.multi);
+                if (r + 1 < M && r + 1 >= lim) red_add(dst + rel[r + 1], -acc[i][j][1], P.multi);
             }
         }
     } else {
@@ -959,8 +968,8 @@ __global__ void __launch_bounds__(ws::NT, 1) k_gemm_ws(PlanDev P, const GemmOp *
 #pragma unroll
                 for (int i = 0; i < FM; ++i) {
                     const int r = row0 + wm0 + 8 * i + 2 * t4;
-                    if (r < M && r >= lim) atomicAdd(dst + rel[r], -acc[i][j][0]);
-                    if (r + 1 < M && r + 1 >= lim) atomicAdd(dst + rel[r + 1], -acc[i][j][1]);
+                    if (r < M && r >= lim) red_add(dst + rel[r], -acc[i][j][0], P.multi);
+                    if (r + 1 < M && r + 1 >= lim) red_add(dst + rel[r + 1], -acc[i][j][1], P.multi);
                 }
             }
         } else {

@@ -21,6 +21,7 @@ struct PlanDev {
     const int32_t *relmap;
     int *status;                     // bit 0: bad pivot met
     int is_lu;
+    int multi;                       // partitioned plan: scattered adds may cross NVLink and race with other GPUs' (system scope)
     int dbg;                         // timing experiments only (SFB200_DBG): bit0 no staging copies, bit1 no barriers
 };
 

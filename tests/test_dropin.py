@@ -159,23 +159,6 @@ def test_driver_keeps_two_matrices_in_flight(tmp_path):
     assert sorted(names) == sorted(os.path.basename(p) for p in paths)
 
 
-@pytest.mark.gpu
-@pytest.mark.parametrize("tree,gen,g", [("Cholesky", "lap3d", 24), ("LU", "cd3d", 16)])
-def test_factorize_entry_point_drives_the_partitioned_plan(tree, gen, g, tmp_path):
-    """SparseFrame_factorize with more than one rank: the etree partition runs inside the call, one host thread per rank
-    (CH.c:2267-2290).  On a one-GPU box the ranks share the GPU (SF_PARTITION_RANKS); with several GPUs every rank has its own."""
-    import torch
-    import sparseframe_b200 as sf
-    path = tmp_path / ("%s_%d.mtx" % (gen, g))
-    sf.matrices.write_matrix_market(str(path), *sf.matrices.generate(gen, g))
-    ranks = max(2, min(torch.cuda.device_count(), 4))
-    env = dict(os.environ, SF_PARTITION_RANKS=str(ranks), SFB200_DIST_MIN_M="48", SFB200_DIST_PANEL_MIN="256", SFB200_OUTER="128",
-               SFB200_OUTER2="256", CUDA_DEVICE_MAX_CONNECTIONS="32", SF_DEVSLOT="5380000000")
-    out = subprocess.check_output([os.path.join(PKG, tree, "Demo", "demo"), str(path)], text=True, env=env, timeout=600)
-    line = [ln for ln in out.splitlines() if ln.startswith("residual")][0]
-    assert float(line.split(":")[1]) < 1e-13, out
-
-
 # The reference calls its entry points from an OpenMP loop over matrices (MATRIX_THREAD_NUM concurrent callers, different
 # matrix_info, CH.c:3375-3440): read + analyze must be re-entrant.  Two matrices analysed concurrently must come out
 # exactly as when analysed one after the other (no device needed for these two steps).

@@ -355,105 +355,6 @@ def test_lu_in_panel_updates_operand_paths(gen, g, kind, env):
     plan.close()
 
 
-PARTITION_CASES = [("lap3d", 20, "cholesky", 2, 0), ("lap3d", 20, "cholesky", 4, 0), ("cd3d", 16, "lu", 3, 0),
-                   ("lap3d", 24, "cholesky", 2, 1), ("lap3d", 24, "cholesky", 4, 1), ("lap3d", 24, "cholesky", 3, 1)]
-
-PARTITION_CHILD = r"""
-import os, sys
-import numpy as np
-sys.path.insert(0, os.path.join(%(root)r, "sparse-matrix-factorization-library_b200"))
-sys.path.insert(0, os.path.join(%(root)r, "oracle"))
-sys.path.insert(0, os.path.join(%(root)r, "tests"))
-import sforacle
-import sparseframe_b200 as sf
-from conftest import build_matrix
-gen, g, kind, world, devices = %(gen)r, %(g)d, %(kind)r, %(world)d, %(devices)r
-A, _ = build_matrix(gen, g)
-S = sf.analyze(A, kind)
-st = {k: S.array(k) for k in ("Super", "SuperMap", "Lsip", "Lsxp", "Lsi", "LeafQueue", "Lp", "Li")}
-st["csize"], st["nsleaf"] = S.int("csize"), S.int("nsleaf")
-split = kind == "lu" and S.int("symmetric") == 0
-ux = None
-if split:
-    st["Up"], st["Ui"] = S.array("Up"), S.array("Ui")
-    ux = S.array("Ux")
-ref, bad = sforacle.factorize(kind, st, S.array("Lx"), ux)
-assert bad == 0
-grp = sf.Group(S, devices)
-assert sum(p.double("local_flops") for p in grp.plans) == S.flops or abs(sum(p.double("local_flops") for p in grp.plans) / S.flops - 1) < 1e-12
-types = [grp.plans[0].coll_info(i)["type"] for i in range(grp.plans[0].int("ncolls"))]
-assert types.count(0) >= 2 and types.count(1) > 0, "barriers and pushes expected: %%r" %% (types,)
-full = sf.Plan(S).int("xsize_padded")
-images = [p.int("xsize_padded") for p in grp.plans]
-assert max(images) < full <= sum(images), (images, full)         # compact images: nobody holds the whole factor
-mask = sf.lower_trapezoid_mask(kind, st["Super"], st["Lsip"], st["Lsxp"], len(ref))
-worst = 0.0
-for it in range(4):                     # plain, graph capture, two replays -- the flags' epochs advance with each one
-    out = grp.factorize(S.array("Lx"), ux)
-    assert not np.isnan(out[mask]).any(), "a panel was not written by its owner"
-    worst = max(worst, sf.entrywise_rel_diff(ref[mask], out[mask]))
-    assert np.array_equal(ref[mask] == 0, out[mask] == 0)
-_, backward = sforacle.validate(kind, st, S.array("Lx"), out, ux)
-print("RESULT", worst, backward, sum(p.double("remote_update_bytes") for p in grp.plans), sum(p.double("push_bytes") for p in grp.plans), grp.last_ms(0))
-grp.close()
-"""
-
-
-def run_partition_child(gen, g, kind, world, devices, env):
-    import subprocess
-    import sys
-    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    code = PARTITION_CHILD % dict(root=root, gen=gen, g=g, kind=kind, world=world, devices=list(devices))
-    # When several ranks share one GPU, a spinning flag wait of one rank must never sit in front of the kernels of the rank
-    # it waits for: every stream gets its own hardware queue (CUDA_DEVICE_MAX_CONNECTIONS) and the launches are issued plainly
-    # (SFB200_GRAPHS=0: how the driver maps the branches of two concurrently running graphs onto queues is not ours to
-    # control -- round 2 saw a flag timeout with graphs on a shared GPU, never with one GPU per rank).  Ranks with a GPU of
-    # their own replay CUDA graphs as in production.
-    shared = len(set(devices)) < len(devices)
-    full_env = dict(os.environ, CUDA_DEVICE_MAX_CONNECTIONS="32", SFB200_PEER_TIMEOUT_S="20", **{k: str(v) for k, v in env.items()})
-    if shared:
-        full_env["SFB200_GRAPHS"] = "0"
-    p = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600, env=full_env)
-    assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-4000:]
-    line = [ln for ln in p.stdout.splitlines() if ln.startswith("RESULT")][-1].split()
-    return [float(v) for v in line[1:]]
-
-
-def partition_env(group_panels):
-    env = dict(SFB200_DIST_MIN_M="48")           # small fronts too: exercise the push + tile-share path
-    env["SFB200_DIST_PANEL_MIN"] = "256" if group_panels else "1000000"
-    if group_panels:
-        env.update(SFB200_OUTER="128", SFB200_OUTER2="256")
-    return env
-
-
-@pytest.mark.parametrize("push", ["dma", "sm"])
-@pytest.mark.parametrize("gen,g,kind,world,group_panels", PARTITION_CASES)
-def test_partitioned_ranks_sharing_one_gpu(gen, g, kind, world, group_panels, push):
-    """The etree-partitioned device path as it runs on several GPUs -- remote adds from the scatter epilogues, pushes of
-    factored blocks, flags in peer memory, one CUDA graph per rank -- with all `world` ranks on THIS one GPU (every "peer"
-    mapping points into the same device): an in-process group, one host thread per rank (sfb200_group_*, what the drop-in
-    drives for numGPU > 1).  group_panels: shared fronts of >= 256 columns are factorized by their whole group (128-wide
-    block columns owned round-robin, one push per block column).  push: copy engines / SM copy kernel."""
-    env = partition_env(group_panels)
-    env["SFB200_PUSH"] = push
-    worst, backward, remote_bytes, push_bytes, ms = run_partition_child(gen, g, kind, world, [0] * world, env)
-    assert worst <= ENTRY_TOL and backward <= BACKWARD_TOL
-    assert remote_bytes > 0 and push_bytes > 0
-
-
-@pytest.mark.parametrize("gen,g,kind,group_panels", [("lap3d", 40, "cholesky", 1), ("cd3d", 24, "lu", 0), ("lap3d", 32, "cholesky", 0)])
-def test_partitioned_ranks_on_separate_gpus(gen, g, kind, group_panels):
-    """The same over real peer access (NVLink): one rank per visible GPU, up to 4."""
-    import torch
-    ngpu = min(torch.cuda.device_count(), 4)
-    if ngpu < 2:
-        pytest.skip("needs at least 2 GPUs")
-    worst, backward, remote_bytes, push_bytes, ms = run_partition_child(gen, g, kind, ngpu, list(range(ngpu)), partition_env(group_panels))
-    assert worst <= ENTRY_TOL and backward <= BACKWARD_TOL
-    assert remote_bytes > 0
-
-
 def test_streamed_copy_out_into_pinned_memory():
     """Page-locked destination: the factor is copied out level by level (and block column by block column for the wide
     fronts) behind the factorization.  Must give the same factor as the pack-then-copy path used for pageable memory."""
