@@ -77,6 +77,19 @@ void trsm(double *X, const TrsmOp &t) {
     }
 }
 
+// The scatter epilogues of the GPU kernels add with red.global.add.f64: several ranks (processes of the gloo test tier,
+// working in each other's shared-memory images) may hit the same entry of a shared panel at the same time.
+static inline void atomic_sub(double *p, double v) {
+    uint64_t *u = reinterpret_cast<uint64_t *>(p);
+    uint64_t old = __atomic_load_n(u, __ATOMIC_RELAXED), neu;
+    do {
+        double d;
+        std::memcpy(&d, &old, sizeof(d));
+        d -= v;
+        std::memcpy(&neu, &d, sizeof(d));
+    } while (!__atomic_compare_exchange_n(u, &old, neu, true, __ATOMIC_RELAXED, __ATOMIC_RELAXED));
+}
+
 // one op; B = tile size of its launch (tiles matter only when the op is shared between ranks: tile_mod > 1).
 // img[r] = image of rank r: a scattered entry goes into the image of the rank its upd_coloff names (the peer-memory adds of
 // the GPU kernels); X = this rank's own image.
@@ -108,7 +121,7 @@ void gemm(double *X, double *const *img, const GemmOp &g, const HostPlan &P, int
                     const double b = (g.flags & G_B_KMAJOR) ? Bm[k + (i64)j * g.ldb] : Bm[j + (i64)k * g.ldb];
                     acc += A[i + (i64)k * g.lda] * b;
                 }
-                if (g.flags & G_SCATTER) D[col + P.relmap[relbase + i]] -= acc;
+                if (g.flags & G_SCATTER) atomic_sub(D + col + P.relmap[relbase + i], acc);
                 else X[g.c_off + i + (i64)j * g.ldc] -= acc;
             }
         }
