@@ -200,7 +200,7 @@ long run_one(const HostPlan &P, double *X, double *const *img, const Launch &L) 
         case L_GETRF:
             for (int k = 0; k < L.count; ++k) { const DiagOp &d = P.diag_ops[L.first + k]; diag_pending_update(X, d, true); bad += diag_lu(X + d.a_off, d.ld, d.nb); }
             break;
-        case L_TRSM:
+        case L_TRSM: case L_TRSM_MMA:
             for (int k = 0; k < L.count; ++k) trsm(X, P.trsm_ops[L.first + k]);
             break;
         case L_GEMM128: case L_GEMM64: case L_GEMM128WS: {
@@ -300,7 +300,7 @@ long sfcheck_launch_info(void *hv, int i, double *out) {
         }
     } else if (L.kind == L_POTRF || L.kind == L_GETRF) {
         for (int q = L.first; q < L.first + L.count; ++q) { const double nb = P.diag_ops[q].nb; flops += (L.kind == L_GETRF ? 2.0 : 1.0) * nb * nb * nb / 3.0; }
-    } else if (L.kind == L_TRSM) {
+    } else if (L.kind == L_TRSM || L.kind == L_TRSM_MMA) {
         for (int q = L.first; q < L.first + L.count; ++q) flops += (double)P.trsm_ops[q].nb * P.trsm_ops[q].nb * P.trsm_ops[q].nvec;
     }
     out[0] = L.kind; out[1] = L.level; out[2] = L.grid; out[3] = L.count; out[4] = L.flags; out[5] = flops; out[6] = kmax; out[7] = kmin;

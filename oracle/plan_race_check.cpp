@@ -242,7 +242,7 @@ struct Checker {
                     case L_SMALL_A: case L_SMALL_B: small(id, P.small_tasks[L.first + k]); break;
                     case L_POTRF: diag(id, P.diag_ops[L.first + k], false); break;
                     case L_GETRF: diag(id, P.diag_ops[L.first + k], true); break;
-                    case L_TRSM: trsm(id, P.trsm_ops[L.first + k]); break;
+                    case L_TRSM: case L_TRSM_MMA: trsm(id, P.trsm_ops[L.first + k]); break;
                     case L_GEMM128: case L_GEMM128WS: gemm(id, P.gemm_ops[L.first + k], 128); break;
                     case L_GEMM64: gemm(id, P.gemm_ops[L.first + k], 64); break;
                     default: return -103;

@@ -12,7 +12,7 @@ plan.factorize(S.array("Lx"), S.array("Ux") if (kind == "lu") else None, downloa
 plan.profile()
 rows = plan.profile_launches()
 peak = 37.0e12
-names = {0: "smallA", 1: "smallB", 2: "potrf", 3: "getrf", 4: "trsm", 5: "gemm128", 6: "gemm64", 7: "gemmWS"}
+names = {0: "smallA", 1: "smallB", 2: "potrf", 3: "getrf", 4: "trsm", 5: "gemm128", 6: "gemm64", 7: "gemmWS", 8: "trsm_mma"}
 print("total profiled ms %.2f" % rows[:, 4].sum())
 # per level summary
 for lev in sorted(set(rows[:, 1].astype(int))):
@@ -28,7 +28,7 @@ for lo, hi in ((0, 65), (65, 129), (129, 257), (257, 1025), (1025, 1e9)):
     sel = (g6[:, 6] >= lo) & (g6[:, 6] < hi)
     if sel.any():
         print("gemm64  Kmax in [%d,%d): %3d launches %7.2f ms  %.2f TF/s  ideal %.2f ms" % (lo, hi, sel.sum(), g6[sel, 4].sum(), g6[sel, 5].sum() / g6[sel, 4].sum() / 1e9, g6[sel, 5].sum() / peak * 1e3))
-for k in (2, 4):
+for k in (2, 4, 8):
     rk = rows[rows[:, 0] == k]
     if len(rk): print("%s: %d launches, %.2f ms, %.1f us per launch" % (names[k], len(rk), rk[:, 4].sum(), 1e3 * rk[:, 4].sum() / len(rk)))
 # gemm128 launches by K class

@@ -28,8 +28,8 @@ struct sfb200_plan {
     cudaStream_t stream = nullptr;
     bool own_stream = true;
     // per-launch-kind profile of the last sfb200_plan_profile() call: ms, launches, algorithmic flops, bytes
-    double prof_ms[8] = {0}, prof_flops[8] = {0}, prof_bytes[8] = {0};
-    int64_t prof_launches[8] = {0};
+    double prof_ms[L_KINDS] = {0}, prof_flops[L_KINDS] = {0}, prof_bytes[L_KINDS] = {0};
+    int64_t prof_launches[L_KINDS] = {0};
     std::vector<float> prof_launch_ms;     // per launch of the schedule
     std::vector<double> prof_launch_flops;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};   // numeric begin/end, e2e begin/end
@@ -184,6 +184,7 @@ int issue_launch_on(sfb200_plan *p, const Launch &L, cudaStream_t st, int spare_
         case L_POTRF:
         case L_GETRF: launch_diag(p->D, p->d_diag + L.first, L.count, st); break;
         case L_TRSM: launch_trsm(p->D, p->d_trsm + L.first, L.count, L.grid, st); break;
+        case L_TRSM_MMA: launch_trsm_mma(p->D, p->d_trsm + L.first, L.count, L.grid, st); break;
         case L_GEMM128: launch_gemm(p->D, p->d_gemm + L.first, L.count, L.grid, true, st); break;
         case L_GEMM64: launch_gemm(p->D, p->d_gemm + L.first, L.count, L.grid, false, st); break;
         case L_GEMM128WS: launch_gemm_ws(p->D, p->d_gemm + L.first, L.count, L.grid, p->sms - spare_sms, st); break;
@@ -244,8 +245,12 @@ int join_side(sfb200_plan *p) {
 int begin_factor(sfb200_plan *p) {
     const HostPlan &H = p->H;
     cudaStream_t st = p->stream;
-    CK(cudaMemsetAsync(p->d_status, 0, sizeof(int), st));
-    CK(cudaMemsetAsync(p->d_X, 0, sizeof(double) * (size_t)H.xsize_pad, st));
+    if (H.world > 1) {
+        launch_zero(p->d_X, H.xsize_pad, p->d_status, p->sms, st);      // never a memset while ranks may wait for each other
+    } else {
+        CK(cudaMemsetAsync(p->d_status, 0, sizeof(int), st));
+        CK(cudaMemsetAsync(p->d_X, 0, sizeof(double) * (size_t)H.xsize_pad, st));
+    }
     launch_assemble(p->d_lx, p->d_asm_l, H.nnz, p->d_X, p->sms, st);
     p->launches = 2;
     if (H.kind == Kind::LU) {
@@ -485,6 +490,7 @@ int sfb200_plan_create_part(const sfb200_symbolic *s, int device, int rank, int 
     if (const char *e = getenv("SFB200_LOOKAHEAD")) prm.lookahead = atoi(e);
     if (const char *e = getenv("SFB200_LEAF_LOOKAHEAD")) prm.leaf_lookahead = atoi(e);
     if (const char *e = getenv("SFB200_LEFT_LOOKING")) prm.left_looking = atoi(e);
+    if (const char *e = getenv("SFB200_TRSM_MMA")) prm.trsm_mma = atoi(e);
     const int rc = build_plan(s->S, prm, p->H, rank, world);
     if (rc != 0) {
         delete p;
@@ -1085,7 +1091,7 @@ int sfb200_plan_profile(sfb200_plan *p) {
     evs.v.assign(nl + 1, nullptr);
     std::vector<cudaEvent_t> &ev = evs.v;
     for (auto &e : ev) CK(cudaEventCreate(&e));
-    for (int k = 0; k < 8; ++k) { p->prof_ms[k] = p->prof_flops[k] = p->prof_bytes[k] = 0; p->prof_launches[k] = 0; }
+    for (int k = 0; k < L_KINDS; ++k) { p->prof_ms[k] = p->prof_flops[k] = p->prof_bytes[k] = 0; p->prof_launches[k] = 0; }
     p->prof_launch_ms.clear();
     p->prof_launch_flops.clear();
     CK(cudaMemsetAsync(p->d_status, 0, sizeof(int), st));
@@ -1120,7 +1126,7 @@ int sfb200_plan_profile(sfb200_plan *p) {
                 const double share = g.tile_mod > 1 ? 1.0 / g.tile_mod : 1.0;
                 fl += 2.0 * g.K * outputs * share;
                 by += (8.0 * ((double)g.M * g.K + (double)g.N * g.K) + 16.0 * outputs) * share;
-            } else if (k == L_TRSM) {
+            } else if (k == L_TRSM || k == L_TRSM_MMA) {
                 const TrsmOp &t = H.trsm_ops[L.first + q];
                 fl += (double)t.nvec * t.nb * t.nb;
                 by += 16.0 * t.nvec * t.nb + 8.0 * t.nb * t.nb;
@@ -1149,7 +1155,7 @@ int sfb200_plan_profile(sfb200_plan *p) {
 /* kind: 0/1 small fronts (64/256-thread CTAs), 2 potrf, 3 getrf, 4 trsm, 5 gemm 128x128, 6 gemm 64x64.
  * what: 0 = total ms, 1 = launches, 2 = algorithmic flops, 3 = algorithmic bytes */
 double sfb200_plan_profile_get(const sfb200_plan *p, int kind, int what) {
-    if (!p || kind < 0 || kind > 7) return -1.0;
+    if (!p || kind < 0 || kind >= L_KINDS) return -1.0;
     switch (what) {
         case 0: return p->prof_ms[kind];
         case 1: return (double)p->prof_launches[kind];

@@ -426,6 +426,112 @@ __global__ void __launch_bounds__(64) k_trsm(PlanDev P, const TrsmOp *__restrict
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// Triangular solve on the FP64 tensor pipe (Cholesky: X L^T = B for the panel rows below a diagonal block L, nb <= 64).
+// One CTA = 128 rows: the tile B (rows x 64) and L live in shared memory, each warp owns 32 rows -- rows are independent
+// in this solve, so there is no CTA-wide barrier after the staging.  Blocked forward substitution over 8-column blocks:
+//     X_j = (B_j - sum_{p<j} X_p L[j,p]^T) L[j,j]^-T
+// the sum is a chain of DMMA 8x8x4 (A = X columns already solved, from shared memory; B = rows of L), the 8 x 8 diagonal
+// blocks are inverted once per CTA (64 threads, 8 steps each) and applied with two more DMMA.  Replaces the one-vector-
+// per-thread k_trsm (vector pipe, 4 TFLOP/s, 24 us per launch on the critical path of every leaf) for Cholesky.
+// ---------------------------------------------------------------------------------------------------------------
+namespace tm {
+constexpr int ROWS = 128, SR = ROWS + 4, ST = 64 + 4;
+constexpr int SMEM_BYTES = (64 * SR + 64 * ST + 8 * 64) * 8;
+}  // namespace tm
+
+__global__ void __launch_bounds__(128) k_trsm_mma(PlanDev P, const TrsmOp *__restrict__ ops, int nops) {
+    using namespace tm;
+    extern __shared__ __align__(16) double smem_tm[];
+    double *Xs = smem_tm;                 // Xs[c * SR + r]   : tile element (row r, column c)
+    double *Ts = Xs + 64 * SR;            // Ts[k * ST + j]   : L[j][k] for k <= j (identity beyond nb)
+    double *Ti = Ts + 64 * ST;            // Ti[jb*64 + k*8 + n] : inverse of diagonal block jb, entry (n, k)
+    const TrsmOp op = ops[find_op(ops, nops, (int)blockIdx.x)];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nb = op.nb;
+    const int r0 = ((int)blockIdx.x - op.tile0) * ROWS;
+    const int nrows = min(ROWS, op.nvec - r0);
+    const double *D = P.X + op.t_off;
+    double *B = P.X + op.b_off + r0;       // element (r, c) at B[r + c * estride]
+    const int64_t ldb = op.estride;
+    {
+        double v[32];
+#pragma unroll
+        for (int q = 0; q < 32; ++q) {
+            const int idx = tid + 128 * q, j = idx & 63, k = idx >> 6;
+            v[q] = (j < nb && k <= j) ? D[j + (int64_t)k * op.ldt] : (j == k ? 1.0 : 0.0);
+        }
+#pragma unroll
+        for (int q = 0; q < 32; ++q) {
+            const int idx = tid + 128 * q, j = idx & 63, k = idx >> 6;
+            Ts[k * ST + j] = v[q];
+        }
+    }
+    {
+        const bool rok = tid < nrows;
+#pragma unroll 16
+        for (int c = 0; c < 64; ++c) Xs[c * SR + tid] = (rok && c < nb) ? B[tid + (int64_t)c * ldb] : 0.0;
+    }
+    __syncthreads();
+    if (tid < 64) {
+        // column c of the inverse of diagonal block jb: L_jb x = e_c
+        const int jb = tid >> 3, c = tid & 7;
+        const double *Lb = Ts + (jb * 8) * ST + jb * 8;       // Lb[k * ST + i] = block entry (i, k)
+        double x[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            double acc = i == c ? 1.0 : 0.0;
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+                if (k < i && k >= c) acc = fma(-Lb[k * ST + i], x[k], acc);
+            x[i] = i >= c ? acc / Lb[i * ST + i] : 0.0;
+            Ti[jb * 64 + c * 8 + i] = x[i];
+        }
+    }
+    __syncthreads();
+
+    const int g = lane >> 2, t = lane & 3;
+    const int wr = warp * 32;
+#pragma unroll 1
+    for (int jb = 0; jb < 8; ++jb) {
+        if (jb * 8 >= nb) break;
+        double acc[4][2];
+#pragma unroll
+        for (int mt = 0; mt < 4; ++mt) acc[mt][0] = acc[mt][1] = 0.0;
+        for (int p = 0; p < 8 * jb; p += 4) {
+            const double b = Ts[(p + t) * ST + jb * 8 + g];
+#pragma unroll
+            for (int mt = 0; mt < 4; ++mt) dmma(acc[mt][0], acc[mt][1], Xs[(p + t) * SR + wr + 8 * mt + g], b);
+        }
+        double *y0 = Xs + (jb * 8 + 2 * t) * SR + wr + g, *y1 = y0 + SR;
+#pragma unroll
+        for (int mt = 0; mt < 4; ++mt) {
+            y0[8 * mt] -= acc[mt][0];
+            y1[8 * mt] -= acc[mt][1];
+            acc[mt][0] = acc[mt][1] = 0.0;
+        }
+        __syncwarp();
+#pragma unroll
+        for (int ks = 0; ks < 8; ks += 4) {
+            const double b = Ti[jb * 64 + (ks + t) * 8 + g];
+#pragma unroll
+            for (int mt = 0; mt < 4; ++mt) dmma(acc[mt][0], acc[mt][1], Xs[(jb * 8 + ks + t) * SR + wr + 8 * mt + g], b);
+        }
+        __syncwarp();
+#pragma unroll
+        for (int mt = 0; mt < 4; ++mt) {
+            y0[8 * mt] = acc[mt][0];
+            y1[8 * mt] = acc[mt][1];
+        }
+        __syncwarp();
+    }
+    __syncthreads();
+    if (tid < nrows) {
+#pragma unroll 16
+        for (int c = 0; c < 64; ++c)
+            if (c < nb) B[tid + (int64_t)c * ldb] = Xs[c * SR + tid];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // DMMA GEMM tiles.  C(BM x BN) -= A(BM x K) * B(BN x K)^T, operands column-major (rows contiguous).
 //   shared tile layout: [k][row] with a row stride of (BM + 4) doubles -> the 8-byte fragment loads of one half-warp
 //   (4 k x 4 rows) fall in 16 distinct 8-byte banks.
@@ -1318,6 +1424,21 @@ __global__ void __launch_bounds__(256) k_peak_dmma_tile(double *out, int iters, 
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void k_epoch_inc(unsigned long long *epoch) { *epoch += 1; }
 
+// Zero fill of a rank's image.  A kernel, not cudaMemsetAsync: a device memory set is one of the operations that make the
+// driver serialize commands of DIFFERENT streams around it (CUDA programming guide, "implicit synchronization"); with
+// several ranks on one device the memset of one rank then waits for the spinning flag wait of another, which waits for
+// that very rank -- seen in round 2 as flag timeouts whenever ranks shared a GPU.
+__global__ void __launch_bounds__(256) k_zero(double *__restrict__ x, int64_t n, int *status) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) *status = 0;
+    const int64_t nthr = (int64_t)gridDim.x * blockDim.x, tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int64_t head = (reinterpret_cast<uintptr_t>(x) & 8) ? 1 : 0;       // to a 16-byte boundary
+    if (tid == 0 && head && n > 0) x[0] = 0.0;
+    double2 *v = reinterpret_cast<double2 *>(x + head);
+    const int64_t nv = (n - head) >> 1;
+    for (int64_t i = tid; i < nv; i += nthr) v[i] = make_double2(0.0, 0.0);
+    if (tid == 0 && ((n - head) & 1)) x[n - 1] = 0.0;
+}
+
 // Everything this rank has issued before (kernels whose epilogues added into peer images, peer copies) is complete
 // when this kernel starts (stream order); the fence orders those writes before the flag as seen from the peer.
 __global__ void k_signal(SyncArgs a) {
@@ -1381,6 +1502,7 @@ cudaError_t kernels_init() {
     if ((e = gemm_optin<Gemm128w16k32, 128, 128, 4, 4, 3, 32>()) != cudaSuccess) return e;
     if ((e = gemm_optin<Gemm64, 64, 64, 2, 2, 4, 16>()) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(k_gemm_ws, cudaFuncAttributeMaxDynamicSharedMemorySize, ws::SMEM_BYTES)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(k_trsm_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, tm::SMEM_BYTES)) != cudaSuccess) return e;
     e = cudaFuncSetAttribute(k_small<256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(k_small<256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
@@ -1416,6 +1538,11 @@ void launch_trsm(const PlanDev &P, const TrsmOp *ops, int count, int grid, cudaS
     k_trsm<<<grid, 64, 0, st>>>(P, ops, count);
 }
 
+void launch_trsm_mma(const PlanDev &P, const TrsmOp *ops, int count, int grid, cudaStream_t st) {
+    if (count <= 0 || grid <= 0) return;
+    k_trsm_mma<<<grid, 128, tm::SMEM_BYTES, st>>>(P, ops, count);
+}
+
 void launch_gemm(const PlanDev &P, const GemmOp *ops, int count, int grid, bool tile128, cudaStream_t st) {
     if (count <= 0 || grid <= 0) return;
     // SFB200_GEMM_VARIANT: 0 = 8 warps, BK 16 (default); 1 = 16 warps, BK 16; 2 = 8 warps, BK 32; 3 = 16 warps, BK 32
@@ -1440,6 +1567,7 @@ void launch_gemm_ws(const PlanDev &P, const GemmOp *ops, int count, int tiles, i
 }
 
 void launch_epoch_inc(unsigned long long *epoch, cudaStream_t st) { k_epoch_inc<<<1, 1, 0, st>>>(epoch); }
+void launch_zero(double *x, int64_t n, int *status, int sms, cudaStream_t st) { k_zero<<<sms * 8, 256, 0, st>>>(x, n, status); }
 void launch_signal(const SyncArgs &a, cudaStream_t st) {
     if (a.n > 0) k_signal<<<1, 32, 0, st>>>(a);
 }

@@ -32,6 +32,7 @@ void launch_assemble(const double *vals, const int64_t *dst, int64_t count, doub
 void launch_small(const PlanDev &P, const int32_t *tasks, int count, int smem, bool big_cta, cudaStream_t st);
 void launch_diag(const PlanDev &P, const DiagOp *ops, int count, cudaStream_t st);
 void launch_trsm(const PlanDev &P, const TrsmOp *ops, int count, int grid, cudaStream_t st);
+void launch_trsm_mma(const PlanDev &P, const TrsmOp *ops, int count, int grid, cudaStream_t st);
 void launch_gemm(const PlanDev &P, const GemmOp *ops, int count, int grid, bool tile128, cudaStream_t st);
 void launch_gemm_ws(const PlanDev &P, const GemmOp *ops, int count, int tiles, int use_sms, cudaStream_t st);   // persistent grid = min(tiles, use_sms)
 void launch_pack(const double *X, double *out, const PackTask *tasks, int count, cudaStream_t st);
@@ -54,6 +55,7 @@ struct SyncArgs {
     unsigned seq[kMaxWorld];
 };
 void launch_epoch_inc(unsigned long long *epoch, cudaStream_t st);
+void launch_zero(double *x, int64_t n, int *status, int sms, cudaStream_t st);     // image = 0, *status = 0 (no cudaMemset: see kernels.cu)
 void launch_signal(const SyncArgs &a, cudaStream_t st);
 // spins until every listed peer's flag has reached its value; gives up after timeout_ns and sets bit 2 of *status
 void launch_wait(const SyncArgs &a, int *status, unsigned long long timeout_ns, cudaStream_t st);

@@ -508,18 +508,25 @@ int build_plan(const Symbolic &S, const PlanParams &prm, HostPlan &P, int rank, 
                 const size_t first_launch = P.launches.size();
                 if (!so.diag.empty()) emit_diag(so, top_block, 0);
                 if (!so.trsm.empty()) {
-                    Launch L{};
-                    L.kind = L_TRSM; L.level = lev; L.top_block = top_block;
-                    L.first = (int32_t)P.trsm_ops.size();
-                    i64 ctas = 0;
-                    for (TrsmOp t : so.trsm) {
-                        t.tile0 = (int32_t)ctas;
-                        ctas += (t.nvec + 63) / 64;
-                        P.trsm_ops.push_back(t);
+                    // Cholesky's solves (vectors = panel rows, contiguous in every column) go to the tensor-pipe kernel, 128 rows
+                    // per CTA; LU's three flavours stay on the vector-pipe kernel, 64 vectors per CTA
+                    for (int pass = 0; pass < 2; ++pass) {
+                        const int per_cta = pass == 0 ? 128 : 64;
+                        Launch L{};
+                        L.kind = pass == 0 ? L_TRSM_MMA : L_TRSM; L.level = lev; L.top_block = top_block;
+                        L.first = (int32_t)P.trsm_ops.size();
+                        i64 ctas = 0;
+                        for (TrsmOp t : so.trsm) {
+                            const bool mma = prm.trsm_mma && !lu && t.flags == 0 && t.vstride == 1;
+                            if (mma != (pass == 0)) continue;
+                            t.tile0 = (int32_t)ctas;
+                            ctas += (t.nvec + per_cta - 1) / per_cta;
+                            P.trsm_ops.push_back(t);
+                        }
+                        L.count = (int32_t)P.trsm_ops.size() - L.first;
+                        L.grid = (int32_t)ctas;
+                        if (L.count > 0) P.launches.push_back(L);
                     }
-                    L.count = (int32_t)so.trsm.size();
-                    L.grid = (int32_t)ctas;
-                    P.launches.push_back(L);
                 }
                 // whatever this slot issued first on the main stream is the first consumer of a block factorized ahead
                 if (wait_diag && P.launches.size() > first_launch) { P.launches[first_launch].flags |= LF_WAIT_DIAG; wait_diag = false; }

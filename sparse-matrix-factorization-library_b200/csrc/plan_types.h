@@ -87,6 +87,8 @@ enum LaunchKind : int32_t {
     L_GEMM128 = 5,   // 128x128 CTA tiles
     L_GEMM64  = 6,   // 64x64 CTA tiles
     L_GEMM128WS = 7, // 128x128 tiles, persistent warp-specialized kernel: bulk-copy (TMA) producer warp + 8 DMMA consumer warps
+    L_TRSM_MMA = 8,  // Cholesky row solves X L^T = B on the tensor pipe: 128 rows per CTA, blocked substitution with DMMA
+    L_KINDS = 9,
 };
 
 struct Launch {

@@ -240,7 +240,7 @@ class Plan:
             raise RuntimeError("sfb200_plan_set_stream failed (%d): %s" % (rc, _capi.last_error()))
 
     KERNELS = {0: "k_small<64>", 1: "k_small<256>", 2: "k_diag<potrf>", 3: "k_diag<getrf>", 4: "k_trsm",
-               5: "k_gemm<128x128>", 6: "k_gemm<64x64>", 7: "k_gemm_ws<128x128>"}
+               5: "k_gemm<128x128>", 6: "k_gemm<64x64>", 7: "k_gemm_ws<128x128>", 8: "k_trsm_mma"}
 
     def profile(self):
         """Instrumented replay: {kernel: dict(ms, launches, flops, bytes)} for the last factorization's values."""

@@ -94,14 +94,16 @@ def partition_env(group_panels):
     return env
 
 
-@pytest.mark.parametrize("push", ["dma", "sm"])
 @pytest.mark.parametrize("gen,g,kind,world,group_panels", PARTITION_CASES)
-def test_partitioned_ranks_sharing_one_gpu(gen, g, kind, world, group_panels, push):
+def test_partitioned_ranks_sharing_one_gpu(gen, g, kind, world, group_panels, push="sm"):
     """The etree-partitioned device path as it runs on several GPUs -- remote adds from the scatter epilogues, pushes of
     factored blocks, flags in peer memory, one CUDA graph per rank -- with all `world` ranks on THIS one GPU (every "peer"
     mapping points into the same device): an in-process group, one host thread per rank (sfb200_group_*, what the drop-in
     drives for numGPU > 1).  group_panels: shared fronts of >= 256 columns are factorized by their whole group (128-wide
-    block columns owned round-robin, one push per block column).  push: copy engines / SM copy kernel."""
+    block columns owned round-robin, one push per block column).  Factored blocks travel with the SM copy kernel here: a
+    copy-engine transfer between two addresses of ONE device is, like a memset, an operation the driver serializes other
+    streams around (CUDA "implicit synchronization"), which deadlocks ranks that wait for each other on that device; with a
+    GPU per rank (next test) the copy engines are used as in production."""
     env = partition_env(group_panels)
     env["SFB200_PUSH"] = push
     worst, backward, remote_bytes, push_bytes, ms = run_partition_child(gen, g, kind, world, [0] * world, env)
@@ -133,6 +135,8 @@ def test_factorize_entry_point_drives_the_partitioned_plan(tree, gen, g, tmp_pat
     ranks = max(2, min(torch.cuda.device_count(), 4))
     env = dict(os.environ, SF_PARTITION_RANKS=str(ranks), SFB200_DIST_MIN_M="48", SFB200_DIST_PANEL_MIN="256", SFB200_OUTER="128",
                SFB200_OUTER2="256", CUDA_DEVICE_MAX_CONNECTIONS="32", SF_DEVSLOT="5380000000", SFB200_PEER_TIMEOUT_S="20")
+    if torch.cuda.device_count() < ranks:
+        env["SFB200_PUSH"] = "sm"           # ranks share a device: see test_partitioned_ranks_sharing_one_gpu
     out = subprocess.check_output([os.path.join(PKG, tree, "Demo", "demo"), str(path)], text=True, env=env, timeout=600)
     line = [ln for ln in out.splitlines() if ln.startswith("residual")][0]
     assert float(line.split(":")[1]) < 1e-13, out
@@ -194,6 +198,8 @@ def test_ranks_in_separate_processes_connect_over_cuda_ipc(gen, g, kind, world, 
     from sparseframe_b200.parallel import owned_mask
     ngpu = torch.cuda.device_count()
     env = dict(SFB200_DIST_MIN_M="48", SFB200_DIST_PANEL_MIN="256" if group_panels else "1000000", SFB200_PEER_TIMEOUT_S="60")
+    if ngpu < world:
+        env["SFB200_PUSH"] = "sm"           # ranks share a device (separate contexts, but keep the copies on the SMs all the same)
     if group_panels:
         env.update(SFB200_OUTER="128", SFB200_OUTER2="256")
     mp.spawn(_worker, args=(world, _free_port(), gen, g, kind, env, ngpu, str(tmp_path)), nprocs=world, join=True)
