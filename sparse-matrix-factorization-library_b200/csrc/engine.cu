@@ -98,6 +98,9 @@ struct sfb200_plan {
     unsigned long long *d_flags = nullptr;             // this rank's flags: [2][kMaxWorld] signal values, then the epoch counter
     unsigned long long *d_epoch = nullptr;
     std::vector<void *> ipc_mapped;                    // mappings opened with cudaIpcOpenMemHandle
+    double *pending_out = nullptr;                     // pageable destination of a host-buffer call, filled in its second half
+    bool pending_packed = false;
+    double *h_stage = nullptr;                         // page-locked staging for the matrix values of a host-buffer call
     bool connected = false;
     cudaStream_t comm_stream = nullptr;                // pushes of factored panels / block columns to the group
     cudaEvent_t ev_to_comm = nullptr, ev_from_comm = nullptr;
@@ -448,6 +451,7 @@ void sfb200_plan_free(sfb200_plan *p) {
     if (p->ev_from_side) cudaEventDestroy(p->ev_from_side);
     if (p->side_stream) cudaStreamDestroy(p->side_stream);
     for (void *m : p->ipc_mapped) cudaIpcCloseMemHandle(m);
+    if (p->h_stage) cudaFreeHost(p->h_stage);
     if (p->d_peer) cudaFree(p->d_peer);
     if (p->d_peer_flags) cudaFree(p->d_peer_flags);
     if (p->d_flags) cudaFree(p->d_flags);
@@ -549,6 +553,12 @@ int sfb200_plan_create_part(const sfb200_symbolic *s, int device, int rank, int 
         // spinning on the device would then block the host thread that is about to launch the signal it waits for (seen in
         // round 2 with several ranks in one process).  Its copy-out buffer therefore exists from the start.
         if (H.world > 1 && (err = ensure_out(p))) return fail(err);
+        // ... and its matrix values never come from pageable memory: such a copy makes the driver wait inside the call (and,
+        // with several ranks in one process, behind the other ranks' work); they are staged through a page-locked buffer
+        if (H.world > 1 && cudaMallocHost((void **)&p->h_stage, sizeof(double) * (size_t)std::max<i64>(H.nnz + H.unnz, 1)) != cudaSuccess) {
+            set_error("cudaMallocHost of the value staging buffer failed");
+            return fail(SFB200_ERR_CUDA);
+        }
     }
     if ((err = upload(p, p->d_lsi32, H.lsi32))) return fail(err);
     if ((err = upload(p, p->d_nz_col, H.nz_col))) return fail(err);
@@ -1023,6 +1033,23 @@ static int factorize_host_enqueue(sfb200_plan *p, const double *Lx, const double
         else cudaGetLastError();
     }
     CK(cudaEventRecord(p->ev[2], p->stream));
+    if (p->h_stage) {
+        auto pinned = [](const void *q) {
+            cudaPointerAttributes a;
+            if (cudaPointerGetAttributes(&a, q) != cudaSuccess) { cudaGetLastError(); return false; }
+            return a.type == cudaMemoryTypeHost;
+        };
+        if (!pinned(Lx)) {
+            CK(cudaStreamSynchronize(p->stream));          // the previous call's upload has left the staging buffer
+            memcpy(p->h_stage, Lx, sizeof(double) * (size_t)H.nnz);
+            Lx = p->h_stage;
+        }
+        if (H.split && !pinned(Ux)) {
+            if (Lx != p->h_stage) CK(cudaStreamSynchronize(p->stream));
+            memcpy(p->h_stage + H.nnz, Ux, sizeof(double) * (size_t)H.unnz);
+            Ux = p->h_stage + H.nnz;
+        }
+    }
     CK(cudaMemcpyAsync(p->d_lx, Lx, sizeof(double) * (size_t)H.nnz, cudaMemcpyHostToDevice, p->stream));
     if (H.split) CK(cudaMemcpyAsync(p->d_ux, Ux, sizeof(double) * (size_t)H.unnz, cudaMemcpyHostToDevice, p->stream));
     int rc;
@@ -1034,10 +1061,10 @@ static int factorize_host_enqueue(sfb200_plan *p, const double *Lx, const double
     } else {
         rc = sfb200_factorize_device(p, p->d_lx, p->d_ux);
         if (rc) return rc;
-        if (Lsx) {
-            rc = download(p, Lsx, packed, false);
-            if (rc) return rc;
-        }
+        // a pageable destination is filled in the second half: a copy into pageable memory blocks inside the call until the
+        // stream gets there, i.e. until the other ranks have played their part
+        p->pending_out = Lsx;
+        p->pending_packed = packed;
     }
     CK(cudaEventRecord(p->ev[3], p->stream));
     return SFB200_OK;
@@ -1045,6 +1072,13 @@ static int factorize_host_enqueue(sfb200_plan *p, const double *Lx, const double
 
 static int factorize_host_finish(sfb200_plan *p) {
     CK(cudaSetDevice(p->device));
+    if (p->pending_out) {
+        double *out = p->pending_out;
+        p->pending_out = nullptr;
+        const int rcd = download(p, out, p->pending_packed, true);
+        if (rcd) return rcd;
+        CK(cudaEventRecord(p->ev[3], p->stream));
+    }
     const int rc = sfb200_plan_sync(p);
     float ms = 0.f;
     if (cudaEventElapsedTime(&ms, p->ev[2], p->ev[3]) == cudaSuccess) p->ms_e2e = ms;

@@ -76,24 +76,34 @@ __global__ void k_assemble(const double *__restrict__ vals, const int64_t *__res
 // in-shared-memory panel factorizations.  Panel is column-major with leading dimension PR (= number of rows).
 // ---------------------------------------------------------------------------------------------------------------
 // Right-looking Cholesky of the leading n columns of a PR x n trapezoid (POTRF of the n x n block + TRSM of the rows
-// below in one sweep).  The diagonal is left un-rooted in shared memory (d_j); the caller stores sqrt(d_j).
+// below in one sweep).  ONE barrier per column: the sweep is square-root free -- column j stays unscaled in shared memory
+// and every thread forms 1 / d_j itself, A[r,c] -= A[r,j] A[c,j] / d_j -- and the columns are scaled by 1 / sqrt(d_j) in one
+// pass at the end (the two-barrier version, scale then update, was barrier-bound: 65 us per front on cfg1's 256-thread
+// class).  The diagonal is left un-rooted in shared memory (d_j); the caller stores sqrt(d_j).
 template <int NT>
 __device__ __forceinline__ void smem_cholesky(double *sh, int PR, int n, int *status) {
+    __shared__ double dsc[256];
     const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
     constexpr int TY = NT / 32;
     for (int j = 0; j < n; ++j) {
         __syncthreads();
         const double d = sh[j * PR + j];
         if (!(d > 0.0) && tid == 0) atomicOr(status, 1);
-        const double rinv = 1.0 / sqrt(d);
-        double *colj = sh + j * PR;
-        for (int r = j + 1 + tid; r < PR; r += NT) colj[r] *= rinv;
-        __syncthreads();
+        const double rd = 1.0 / d;
+        const double *colj = sh + j * PR;
         for (int c = j + 1 + ty; c < n; c += TY) {
-            const double lcj = colj[c];
+            const double lcj = colj[c] * rd;
             double *colc = sh + c * PR;
             for (int r = c + tx; r < PR; r += 32) colc[r] = fma(-colj[r], lcj, colc[r]);
         }
+    }
+    __syncthreads();
+    for (int c = tid; c < n; c += NT) dsc[c] = rsqrt(sh[c * PR + c]);
+    __syncthreads();
+    const int total = PR * n;
+    for (int idx = tid; idx < total; idx += NT) {
+        const int c = idx / PR, r = idx - c * PR;
+        if (r > c) sh[idx] *= dsc[c];
     }
     __syncthreads();
 }

@@ -25,7 +25,9 @@ struct PlanParams {
                                  // cfg1 7.12 -> 6.81; profiles/r01_sweep_min_k_cfg4_cfg1_cfg2.log) -- and 0 on partitioned
                                  // plans, where it has not been measured
     int leaf_lookahead = 1;      // diagonal block j+1 applies leaf j's update to itself and is factorized next to that update
-    int trsm_mma = 1;            // Cholesky: the solves below a diagonal block run on the tensor pipe (k_trsm_mma)
+    int trsm_mma = 0;            // Cholesky: the solves below a diagonal block on the tensor pipe (k_trsm_mma).  Off: measured
+                                 // no faster than the vector-pipe kernel, both are bound by the latency of their staging
+                                 // (profiles/r02_ncu_k_trsm_mma_v1.txt)
     int left_looking = 1;        // Cholesky: blocks below the top level pull their updates (left-looking) instead of pushing
                                  // rank-nb / rank-outer updates to the right: half the C traffic, longer K (PanelEmitter::block)
     int lookahead = 1;           // split the top-level trailing updates (see LaunchFlags) -- needs outer2 > 0

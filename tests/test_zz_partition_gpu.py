@@ -77,7 +77,7 @@ def run_partition_child(gen, g, kind, world, devices, env):
     # control -- round 2 saw a flag timeout with graphs on a shared GPU, never with one GPU per rank).  Ranks with a GPU of
     # their own replay CUDA graphs as in production.
     shared = len(set(devices)) < len(devices)
-    full_env = dict(os.environ, CUDA_DEVICE_MAX_CONNECTIONS="32", SFB200_PEER_TIMEOUT_S="20", **{k: str(v) for k, v in env.items()})
+    full_env = dict(os.environ, CUDA_DEVICE_MAX_CONNECTIONS="32", SFB200_PEER_TIMEOUT_S=os.environ.get("SFB200_PEER_TIMEOUT_S", "20"), **{k: str(v) for k, v in env.items()})
     if shared and os.environ.get("SFB200_TEST_SHARED_GRAPHS") != "1":
         full_env["SFB200_GRAPHS"] = "0"
     p = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600, env=full_env)
@@ -134,7 +134,7 @@ def test_factorize_entry_point_drives_the_partitioned_plan(tree, gen, g, tmp_pat
     sf.matrices.write_matrix_market(str(path), *sf.matrices.generate(gen, g))
     ranks = max(2, min(torch.cuda.device_count(), 4))
     env = dict(os.environ, SF_PARTITION_RANKS=str(ranks), SFB200_DIST_MIN_M="48", SFB200_DIST_PANEL_MIN="256", SFB200_OUTER="128",
-               SFB200_OUTER2="256", CUDA_DEVICE_MAX_CONNECTIONS="32", SF_DEVSLOT="5380000000", SFB200_PEER_TIMEOUT_S="20")
+               SFB200_OUTER2="256", CUDA_DEVICE_MAX_CONNECTIONS="32", SF_DEVSLOT="5380000000", SFB200_PEER_TIMEOUT_S=os.environ.get("SFB200_PEER_TIMEOUT_S", "20"))
     if torch.cuda.device_count() < ranks:
         env["SFB200_PUSH"] = "sm"           # ranks share a device: see test_partitioned_ranks_sharing_one_gpu
     out = subprocess.check_output([os.path.join(PKG, tree, "Demo", "demo"), str(path)], text=True, env=env, timeout=600)
