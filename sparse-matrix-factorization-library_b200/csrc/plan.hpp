@@ -36,6 +36,8 @@ struct PlanParams {
                                  // solves), the in-panel updates read it as a row-major B operand -> warp-specialized kernel
     int ws_kmajor = 0;           // ... and so do LU's k-major B ops (U11 row blocks, staged column by column) when their
                                  // sources are 16-byte aligned and K is a multiple of 16
+    double balance_tol = 1.05;   // multi-GPU: subtrees are opened (their roots become shared fronts) until the heaviest rank's
+                                 // local work is within this factor of the average
     int dist_scatter_min_m = 512;// multi-GPU: Schur updates of shared fronts with at least this many rows are split over the group
     int dist_panel_min_cols = 2048; // multi-GPU: shared Cholesky fronts at least this wide are factorized by the whole group
                                  // (1-D block-cyclic over `outer`-wide block columns, one broadcast per block column)
