@@ -496,6 +496,7 @@ int sfb200_plan_create_part(const sfb200_symbolic *s, int device, int rank, int 
     if (const char *e = getenv("SFB200_LEFT_LOOKING")) prm.left_looking = atoi(e);
     if (const char *e = getenv("SFB200_TRSM_MMA")) prm.trsm_mma = atoi(e);
     if (const char *e = getenv("SFB200_BALANCE_TOL")) prm.balance_tol = atof(e);
+    if (const char *e = getenv("SFB200_WEIGHTED_BLOCKS")) prm.weighted_blocks = atoi(e);
     const int rc = build_plan(s->S, prm, p->H, rank, world);
     if (rc != 0) {
         delete p;

@@ -343,7 +343,10 @@ int build_plan(const Symbolic &S, const PlanParams &prm, HostPlan &P, int rank, 
                 if (k + 1 == G || cand <= sorted[k + 1]) { h = cand; break; }
             }
             std::vector<double> w(G);
-            for (int r = 0; r < G; ++r) { w[r] = std::max(0.0, h - l[r]) / W; load[glo + r] += w[r] * W; }
+            for (int r = 0; r < G; ++r) {
+                w[r] = prm.weighted_blocks ? std::max(0.0, h - l[r]) / W : 1.0 / G;      // even deal = plain round-robin
+                load[glo + r] += w[r] * W;
+            }
             const int nblk = (P.snode[s].nscol + Wd - 1) / Wd;
             blk_owner[s].resize(nblk);
             std::vector<double> credit(G, 0.0);

@@ -38,6 +38,10 @@ struct PlanParams {
                                  // sources are 16-byte aligned and K is a multiple of 16
     double balance_tol = 1.05;   // multi-GPU: subtrees are opened (their roots become shared fronts) until the heaviest rank's
                                  // local work is within this factor of the average
+    int weighted_blocks = 0;     // multi-GPU: deal the block columns of group-factorized fronts in a weighted cyclic order that
+                                 // evens out the ranks' total flops.  Off: measured no gain (cfg5 on 4 GPUs 965.8 -> 974.9 ms) --
+                                 // the schedule is level-synchronous, a rank that is light in the subtree phase waits at the first
+                                 // group barrier whatever it is given later (profiles/r02_bench_n4_cfg5_v2_weighted_blocks.json)
     int dist_scatter_min_m = 512;// multi-GPU: Schur updates of shared fronts with at least this many rows are split over the group
     int dist_panel_min_cols = 2048; // multi-GPU: shared Cholesky fronts at least this wide are factorized by the whole group
                                  // (1-D block-cyclic over `outer`-wide block columns, one broadcast per block column)
