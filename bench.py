@@ -554,8 +554,9 @@ def main():
             "config": {"workload": workload_name(cfg, gen, g, kind), "n": n, "nnz_stored": int(A.Cp[-1]),
                        "nsuper": S.int("nsuper"), "factor_GB": xsize * 8e-9, "flops_per_step": flops,
                        "devSlotSize": sf.DEFAULT_DEVSLOT, "l2": "factor (%.1f GB) >> 126 MB L2, no flush needed" % (xsize * 8e-9),
-                       "parallelism": ("etree subtrees over %d GPUs, %d NCCL collectives on shared panels per step, "
-                                       "flop share per rank %s" % (world, plan.int("ncolls"),
+                       "parallelism": ("etree subtrees over %d GPUs, %d exchange steps per factorization (barriers / pushes of "
+                                       "factored blocks in NVLink peer memory; remote adds are fused into the update kernels), "
+                                       "owned-flop share per rank %s" % (world, plan.int("ncolls"),
                                                                    [round(float(v.item()), 3) for v in share_list]))
                        if world > 1 else "1 GPU",
                        "analyze_s": t_analyze, "plan_s": t_plan},

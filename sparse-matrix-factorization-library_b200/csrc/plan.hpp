@@ -36,8 +36,11 @@ struct PlanParams {
                                  // solves), the in-panel updates read it as a row-major B operand -> warp-specialized kernel
     int ws_kmajor = 0;           // ... and so do LU's k-major B ops (U11 row blocks, staged column by column) when their
                                  // sources are 16-byte aligned and K is a multiple of 16
-    double balance_tol = 1.05;   // multi-GPU: subtrees are opened (their roots become shared fronts) until the heaviest rank's
-                                 // local work is within this factor of the average
+    double balance_tol = 1.10;   // multi-GPU: subtrees are opened (their roots become shared fronts) until the heaviest rank's
+                                 // local work is within this factor of the average.  Measured on cfg5 (profiles/
+                                 // r02_mgpu_sweep_n{4,8}_cfg5.log): 4 ranks 1.10 = 1.05 = 967 ms, 1.02 990, 1.01 1125; 8 ranks
+                                 // 1.05 666 ms (528 exchange steps, 147 GB pushed), 1.10 645 ms (308 steps, 94 GB): every
+                                 // opened subtree adds shared fronts whose chains cost more than the imbalance they remove
     int weighted_blocks = 0;     // multi-GPU: deal the block columns of group-factorized fronts in a weighted cyclic order that
                                  // evens out the ranks' total flops.  Off: measured no gain (cfg5 on 4 GPUs 965.8 -> 974.9 ms) --
                                  // the schedule is level-synchronous, a rank that is light in the subtree phase waits at the first
