@@ -180,6 +180,28 @@ def time_reference(gen, g, kind, warmup, steps, budget_s, blas_threads):
     return {"n": n, "flops": flops, "times": times, "analyze_s": t_analyze, "warmup_done": warm_done}
 
 
+# configs whose CPU factorization takes minutes and tens of GB: (factor GB, flops), SURVEY.md section 8
+BIG_CONFIGS = {"cfg3": (36.9, 4.703e13), "cfg5": (58.4, 1.065e14)}
+
+
+def mem_available_gb():
+    try:
+        for line in open("/proc/meminfo"):
+            if line.startswith("MemAvailable:"):
+                return float(line.split()[1]) / 1e6
+    except OSError:
+        pass
+    return 0.0
+
+
+def reference_child(cfg, gen, g, kind):
+    """One factorization of a big config by the compiled reference, in a process of its own (see reference_arm)."""
+    threads = int(os.environ.get("SFB200_REF_THREADS", str(min(os.cpu_count(), 16))))
+    res = time_reference(gen, g, kind, 0, 1, 1e9, threads)
+    res.update(same_config=True, extrapolated=False)
+    emit(res)
+
+
 def reference_arm(args, cfg, gen, g, kind):
     """--impl reference: the reference's own CPU implementation of the path (compiled from its sources into
     oracle/_ref, unmodified), all the host threads it uses (it caps BLAS at 16, parameter.h:12), on the SAME matrix as
@@ -190,35 +212,68 @@ def reference_arm(args, cfg, gen, g, kind):
         return
     threads, thread_info = pick_blas_threads(kind)
     budget = float(os.environ.get("SFB200_REF_BUDGET_S", "600"))
-    note = None
+    note, same_config, extrapolated = None, True, False
     cache = os.path.join("/tmp", "sfb200_reference_%s_%s.json" % (cfg, os.uname().nodename))
     res = None
-    if cfg == "cfg5":
+    big = cfg in BIG_CONFIGS
+    if big:
         # one CPU worker does the same work whatever N is: the 2/4/8-GPU lines of one box share one measurement
         try:
             res = json.load(open(cache))
             note = "measured once on this box by an earlier --impl reference run (N-independent CPU work), re-used"
+            same_config, extrapolated = res.get("same_config", True), res.get("extrapolated", False)
         except (OSError, ValueError):
             res = None
-    if res is None:
-        big = cfg in ("cfg3", "cfg5")
-        res = time_reference(gen, g, kind, 0 if big else min(args.warmup, 1), 1 if big else args.steps, budget, threads)
-        if cfg == "cfg5":
+    if res is None and big:
+        # The big configs cost the CPU minutes and tens of GB (cfg5: 1.07e14 flop, 58 GB factor + 5 GB update buffer).  Learn
+        # the large-matrix rate on cfg2's sibling first, then run the real thing in a child process only if the host has the
+        # memory and the predicted time fits; otherwise report the extrapolation and say so.
+        factor_gb, big_flops = BIG_CONFIGS[cfg]
+        pgen, pg = ("lap3d", 100) if gen == "lap3d" else (gen, max(g // 2, 8))
+        probe = time_reference(pgen, pg, kind, 0, 1, budget, threads)
+        rate = probe["flops"] / probe["times"][0]
+        predicted = big_flops / rate
+        avail = mem_available_gb()
+        need = 1.25 * factor_gb + 12.0
+        big_budget = float(os.environ.get("SFB200_REF_BIG_BUDGET_S", "900"))
+        log("reference arm: %s predicted %.0f s at %.1f GFLOP/s (probe %s %d), host memory available %.0f GB, needed %.0f GB"
+            % (cfg, predicted, rate / 1e9, pgen, pg, avail, need))
+        if avail >= need and predicted <= big_budget:
             try:
-                json.dump(res, open(cache, "w"))
-            except OSError:
-                pass
+                child = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference-child", "--config", cfg],
+                                       stdout=subprocess.PIPE, stderr=sys.stderr, text=True, timeout=2.5 * predicted + 600,
+                                       env=dict(os.environ, SFB200_REF_THREADS=str(threads)))
+                if child.returncode == 0:
+                    res = json.loads(child.stdout.strip().splitlines()[-1])
+            except (subprocess.TimeoutExpired, ValueError, IndexError) as e:
+                log("reference arm: the %s child did not finish (%r)" % (cfg, e))
+        if res is None:
+            same_config, extrapolated = False, True
+            res = {"n": probe["n"], "flops": probe["flops"], "times": probe["times"], "analyze_s": probe["analyze_s"],
+                   "warmup_done": 0, "same_config": False, "extrapolated": True}
+            note = ("%s itself was not run on this host (predicted %.0f s, %.0f GB available, %.0f GB needed): the value is the "
+                    "reference's rate on %s %d^3, the same generator at the size of cfg2" % (cfg, predicted, avail, need, pgen, pg))
+            res["note"] = note
+        try:
+            json.dump(res, open(cache, "w"))
+        except OSError:
+            pass
+        note = note or res.get("note")
+    if res is None:
+        res = time_reference(gen, g, kind, min(args.warmup, 1), args.steps, budget, threads)
     times = res["times"]
     total = sum(times)
     value = res["flops"] * len(times) / total / 1e9
+    what = cfg if same_config else "stand-in for %s (see config.note)" % cfg
     sample = "%s: the whole matrix (n=%d, %.3e flop/step), %d timed step(s) after %d warm-up (time budget %.0f s), " \
-             "compiled reference CPU worker path, OpenBLAS threads=%d (see cpu_baseline.threads)" % (cfg, res["n"], res["flops"], len(times),
+             "compiled reference CPU worker path, OpenBLAS threads=%d (see cpu_baseline.threads)" % (what, res["n"], res["flops"], len(times),
                                                                         res["warmup_done"], budget, threads)
     emit({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": len(times),
         "warmup": res["warmup_done"], "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_name(cfg, gen, g, kind), "sample": sample, "same_config_as_gpu_arm": True,
+        "config": {"workload": workload_name(cfg, gen, g, kind), "sample": sample, "same_config_as_gpu_arm": same_config,
+                   "extrapolated": extrapolated,
                    "devSlotSize": 5_380_000_000, "analyze_s": res["analyze_s"], "note": note,
                    "steps_requested": args.steps, "warmup_requested": args.warmup},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "reference", "sample": sample,
@@ -342,6 +397,9 @@ def main():
     gen, g, kind = sf.matrices.CONFIGS[cfg]
     if args.impl == "reference":
         reference_arm(args, cfg, gen, g, kind)
+        return
+    if args.impl == "reference-child":
+        reference_child(cfg, gen, g, kind)
         return
 
     import torch

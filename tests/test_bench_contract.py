@@ -11,7 +11,7 @@ BASE_KEYS = {"metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_ste
 
 
 def test_committed_bench_line_has_every_contract_key():
-    j = json.load(open(os.path.join(ROOT, "profiles", "r01_bench_v7.json")))
+    j = json.load(open(os.path.join(ROOT, "profiles", "r02_bench_final.json")))
     assert BASE_KEYS <= set(j)
     base = json.load(open(os.path.join(ROOT, "BASELINE.json")))
     assert "numeric-factorization" in base["metric"] and j["metric"] == "fp64_numeric_factorization_gflops"
@@ -26,9 +26,28 @@ def test_committed_bench_line_has_every_contract_key():
     assert {"bound", "achieved", "peak", "unit", "frac", "traffic"} <= set(r)
     assert r["bound"] == "tensor" and r["unit"] == "TFLOP/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-12
     assert 0 < r["frac"] < 1 and r["traffic"] > 0
+    assert "SparseFrame_factorize" in e["api"]                 # the reference-facing symbol of the drop-in library
     c = j["cpu_baseline"]
     assert {"value", "unit", "cores", "kind", "sample"} <= set(c) and c["kind"] == "reference" and c["cores"] <= 16
+    assert c["sample"].startswith("cfg2: the whole matrix") and {"reference_policy_threads", "used_threads"} <= set(c["threads"])
     assert j["value"] == abs(j["value"]) and abs(j["value"] - j["config"]["flops_per_step"] / j["ms_per_step"] / 1e6) < 1e-6 * j["value"]
+
+
+def test_committed_multi_gpu_lines_carry_parity_and_the_same_config_baseline():
+    """N > 1: the distributed factor is checked inside the bench run, and the one-GPU point of the curve is measured on the
+    same matrix in the same run."""
+    for name, n in (("r02_bench_n2_cfg2_v2_streamed_e2e.json", 2), ("r02_bench_n4_cfg5_v1.json", 4), ("r02_bench_n8_cfg5_v1.json", 8)):
+        j = json.load(open(os.path.join(ROOT, "profiles", name)))
+        assert BASE_KEYS <= set(j) and j["n_gpus"] == n and j["scaling"] == "strong"
+        p = j["parity"]
+        assert p["ok"] is True and p["backward"] <= 1e-12 and p["max_rel_vs_single_gpu"] <= 1e-10
+        assert p["entries_gathered"] == p["entries_expected"] > 1e9
+        s1 = j["single_gpu_same_config"]
+        assert s1["ms_per_step"] > j["ms_per_step"] and 1.0 < s1["ms_per_step"] / j["ms_per_step"] <= n
+        x = j["exchange"]
+        assert x["remote_update_GB_per_step"] > 0 and x["pushed_GB_per_step"] > 0 and len(x["image_GB_per_rank"]) == n
+        assert max(x["image_GB_per_rank"]) < j["config"]["factor_GB"]            # compact images: nobody holds the whole factor
+        assert j["e2e"]["d2h_bytes_per_step"] >= 8 * p["entries_expected"] * 0.99 and j["e2e"]["value"] < j["value"]
 
 
 def test_reference_arm_prints_one_json_line_with_the_same_metric():
