@@ -9,6 +9,9 @@
  * LU.c:2564-2604), POTRF + TRSM (CH.c:2134-2145), GETRF-nopiv + TRSM (LU.c:2652-2663).
  */
 #include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <thread>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -541,6 +544,92 @@ long sfcheck_factorize_partitioned(int kind, int is_symmetric, long n, const lon
     if (ncoll_out) for (int t = 0; t < 2; ++t) ncoll_out[t] = ncoll[t];
     for (auto *h : H) delete h;
     return bad;
+}
+
+/* The exchange PROTOCOL under real concurrency: one host thread per rank, no lock step.  Every rank runs `epochs`
+ * factorizations back to back exactly as the device does -- bump its epoch, zero and assemble its own image, then segment by
+ * segment the exchange steps and launches -- and the steps use the plan's own flag sequence numbers (HostPlan::coll_sync):
+ * a signal is a release store of epoch * 2^24 + seq into the peer's flag slot of its channel, a wait spins (acquire) until
+ * the slot has reached its value, gives up after `timeout_s` and reports -300.  Remote update entries are atomic
+ * subtractions in the peer's image, pushed blocks are copied by the root before it signals.  `jitter` > 0 makes every rank
+ * sleep a rank- and step-dependent few microseconds before its exchange steps, so that repeated runs see different
+ * interleavings.  What this catches that the lock-step simulation cannot: a missing or misplaced barrier (a remote add that
+ * lands after its target was factorized, or before its target's owner zeroed the image of the next factorization), wrong
+ * sequence numbers, a wait nobody signals (dead lock -> timeout).  Lsx_out = union of the owned panels after the last epoch. */
+long sfcheck_factorize_threaded(int kind, int is_symmetric, long n, const long *Cp, const long *Ci, const double *Cx,
+                                unsigned long long dev_slot, int nb, int outer, int small_a, int small_b, int world, int epochs,
+                                int jitter, double timeout_s, double *Lsx_out) {
+    if (world < 1 || world > kMaxWorld) return -1;
+    std::vector<CheckHandle *> H(world);
+    for (int r = 0; r < world; ++r) {
+        H[r] = (CheckHandle *)sfcheck_open(kind, is_symmetric, n, Cp, Ci, Cx, dev_slot, nb, outer, small_a, small_b, 0, r, world);
+        if (!H[r]) return -1;
+    }
+    std::vector<std::vector<double>> X(world);
+    std::vector<double *> img(world);
+    for (int r = 0; r < world; ++r) { X[r].assign(H[r]->P.xsize_pad + H[r]->P.wsize, 0.0); img[r] = X[r].data(); }
+    // flags[r][chan][src]
+    std::vector<std::atomic<unsigned long long>> flags((size_t)world * 2 * kMaxWorld);
+    for (auto &f : flags) f.store(0);
+    std::atomic<long> failure{0}, bad{0};
+    const bool no_wait = getenv("SFCHECK_THREADED_NO_WAIT") != nullptr;
+    auto rank_main = [&](int r) {
+        const HostPlan &P = H[r]->P;
+        unsigned long long epoch = 0;
+        auto slot = [&](int dst, int chan, int src) -> std::atomic<unsigned long long> & { return flags[((size_t)dst * 2 + chan) * kMaxWorld + src]; };
+        for (int e = 0; e < epochs && failure.load() == 0; ++e) {
+            ++epoch;
+            std::fill(X[r].begin(), X[r].begin() + P.xsize_pad, 0.0);
+            assemble(*H[r], X[r].data());
+            for (size_t k = 0; k < P.segments.size() && failure.load() == 0; ++k) {
+                const Segment &sg = P.segments[k];
+                for (int i = sg.coll_first; i < sg.coll_first + sg.coll_count; ++i) {
+                    const Coll &c = P.colls[i];
+                    if (r < c.lo || r >= c.hi) continue;
+                    const CollSync &cs = P.coll_sync[i];
+                    if (jitter > 0) std::this_thread::sleep_for(std::chrono::microseconds((r * 7 + i * 13 + e * 3) % (jitter + 1)));
+                    if (c.type == C_BCAST && r == c.root) {
+                        for (int q = 0; q < cs.sig_count; ++q) {          // copy, then the destination's flag
+                            const SyncPoint &sp = P.sync_points[cs.sig_first + q];
+                            const i64 dst = P.coll_dst[c.dst_first + (sp.peer - c.lo)];
+                            for (int col = 0; col < c.cols; ++col)
+                                std::memcpy(img[sp.peer] + dst + (i64)col * c.ld, img[r] + c.offset + (i64)col * c.ld, sizeof(double) * c.rows);
+                            slot(sp.peer, cs.chan, r).store(epoch * (1ull << 24) + sp.seq, std::memory_order_release);
+                        }
+                    } else {
+                        for (int q = 0; q < cs.sig_count; ++q) {
+                            const SyncPoint &sp = P.sync_points[cs.sig_first + q];
+                            slot(sp.peer, cs.chan, r).store(epoch * (1ull << 24) + sp.seq, std::memory_order_release);
+                        }
+                    }
+                    // self-test of this checker: SFCHECK_THREADED_NO_WAIT=1 drops every wait -- the factor must then come out wrong
+                    for (int q = 0; q < (no_wait ? 0 : cs.wait_count); ++q) {
+                        const SyncPoint &sp = P.sync_points[cs.wait_first + q];
+                        const unsigned long long want = epoch * (1ull << 24) + sp.seq;
+                        const auto t0 = std::chrono::steady_clock::now();
+                        while (slot(r, cs.chan, sp.peer).load(std::memory_order_acquire) < want) {
+                            if (failure.load() != 0) return;
+                            if (std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() > timeout_s) { failure.store(-300); return; }
+                            std::this_thread::yield();
+                        }
+                    }
+                }
+                const long b = run_launches(P, X[r].data(), img.data(), sg.launch_first, sg.launch_count);
+                if (b < 0) { failure.store(b); return; }
+                bad += b;
+            }
+        }
+    };
+    std::vector<std::thread> th;
+    for (int r = 0; r < world; ++r) th.emplace_back(rank_main, r);
+    for (auto &t : th) t.join();
+    long rc = failure.load();
+    if (rc == 0) {
+        for (int r = 0; r < world; ++r) sfcheck_pack_owned(H[r], X[r].data(), Lsx_out);
+        rc = bad.load();
+    }
+    for (auto *h : H) delete h;
+    return rc;
 }
 
 }  // extern "C"

@@ -89,8 +89,6 @@ struct sfb200_plan {
     int merge_level = 0;
     int top_width = 256;                               // width of the widest blocking level
     // ---- partitioned plans (world > 1): exchange over peer memory, see plan_types.h (Coll) ---------------------------
-    struct CollSync { std::vector<std::pair<int, unsigned>> sig, wait; };   // (peer, sequence number) lists of one step
-    std::vector<CollSync> coll_sync;
     std::vector<double *> peer_img;                    // image of every rank as this device addresses it
     std::vector<unsigned long long *> peer_flags;      // flag array of every rank
     double **d_peer = nullptr;                         // device copies of the two tables
@@ -168,7 +166,8 @@ int upload_peer_tables(sfb200_plan *p) {
     return SFB200_OK;
 }
 
-SyncArgs sync_args(const sfb200_plan *p, int chan, const std::vector<std::pair<int, unsigned>> &list, size_t first, size_t count) {
+SyncArgs sync_args(const sfb200_plan *p, int chan, size_t first, size_t count) {      // `count` entries of H.sync_points from `first`
+    const std::vector<SyncPoint> &list = p->H.sync_points;
     SyncArgs a{};
     a.peer_flags = p->d_peer_flags;
     a.my_flags = p->d_flags;
@@ -176,7 +175,7 @@ SyncArgs sync_args(const sfb200_plan *p, int chan, const std::vector<std::pair<i
     a.me = p->H.rank;
     a.n = (int)count;
     a.chan = chan;
-    for (size_t k = 0; k < count; ++k) { a.peer[k] = list[first + k].first; a.seq[k] = list[first + k].second; }
+    for (size_t k = 0; k < count; ++k) { a.peer[k] = list[first + k].peer; a.seq[k] = list[first + k].seq; }
     return a;
 }
 
@@ -282,20 +281,20 @@ int issue_coll(sfb200_plan *p, size_t i) {
     const HostPlan &H = p->H;
     const Coll &c = H.colls[i];
     if (H.rank < c.lo || H.rank >= c.hi) return SFB200_OK;
-    const auto &cs = p->coll_sync[i];
+    const CollSync &cs = H.coll_sync[i];
     if (c.type == C_BARRIER) {
         // everything this rank has added into its peers' images so far precedes the signal in stream order (side streams
         // are joined at every segment end)
-        launch_signal(sync_args(p, 0, cs.sig, 0, cs.sig.size()), p->stream);
-        launch_wait(sync_args(p, 0, cs.wait, 0, cs.wait.size()), p->d_status, p->peer_timeout_ns, p->stream);
+        launch_signal(sync_args(p, 0, (size_t)cs.sig_first, (size_t)cs.sig_count), p->stream);
+        launch_wait(sync_args(p, 0, (size_t)cs.wait_first, (size_t)cs.wait_count), p->d_status, p->peer_timeout_ns, p->stream);
         p->launches += 2;
     } else if (H.rank == c.root) {
         // the factored block leaves on the push stream; this rank's own next launches do not wait for it
         CK(cudaEventRecord(p->ev_to_comm, p->stream));
         CK(cudaStreamWaitEvent(p->comm_stream, p->ev_to_comm, 0));
         const double *src = p->d_X + c.offset;
-        for (size_t k = 0; k < cs.sig.size(); ++k) {
-            const int q = cs.sig[k].first;
+        for (int k = 0; k < cs.sig_count; ++k) {
+            const int q = H.sync_points[cs.sig_first + k].peer;
             double *dst = p->peer_img[q] + H.coll_dst[c.dst_first + (q - c.lo)];
             if (p->push_mode == 0) {
                 CK(cudaMemcpy2DAsync(dst, sizeof(double) * c.ld, src, sizeof(double) * c.ld, sizeof(double) * c.rows, (size_t)c.cols,
@@ -304,12 +303,12 @@ int issue_coll(sfb200_plan *p, size_t i) {
                 launch_push(src, dst, c.rows, c.cols, c.ld, 32, p->comm_stream);
                 ++p->launches;
             }
-            launch_signal(sync_args(p, 1, cs.sig, k, 1), p->comm_stream);       // one flag per destination, as soon as its copy is done
+            launch_signal(sync_args(p, 1, (size_t)(cs.sig_first + k), 1), p->comm_stream);       // one flag per destination, as soon as its copy is done
             ++p->launches;
         }
         p->comm_pending = true;
     } else {
-        launch_wait(sync_args(p, 1, cs.wait, 0, cs.wait.size()), p->d_status, p->peer_timeout_ns, p->stream);
+        launch_wait(sync_args(p, 1, (size_t)cs.wait_first, (size_t)cs.wait_count), p->d_status, p->peer_timeout_ns, p->stream);
         ++p->launches;
     }
     return SFB200_OK;
@@ -604,28 +603,6 @@ int sfb200_plan_create_part(const sfb200_symbolic *s, int device, int rank, int 
                 cudaEventCreateWithFlags(&p->ev_from_comm, cudaEventDisableTiming) != cudaSuccess) { set_error("push stream"); return fail(SFB200_ERR_CUDA); }
             if (const char *e = getenv("SFB200_PUSH")) p->push_mode = (std::string(e) == "sm") ? 1 : 0;
             if (const char *e = getenv("SFB200_PEER_TIMEOUT_S")) p->peer_timeout_ns = (unsigned long long)(atof(e) * 1e9);
-            // sequence numbers: both ends of a (signaller, waiter) pair walk the same step list and count the signals of
-            // that pair, so the n-th signal from rank a to rank b is "n" on both sides without any communication
-            // (counted per channel: barriers and pushes are signalled from different streams, see kernels.cuh)
-            std::vector<unsigned> sent(H.world, 0), recv(H.world, 0), psent(H.world, 0), precv(H.world, 0);
-            p->coll_sync.resize(H.colls.size());
-            for (size_t i = 0; i < H.colls.size(); ++i) {
-                const Coll &c = H.colls[i];
-                if (H.rank < c.lo || H.rank >= c.hi) continue;
-                auto &cs = p->coll_sync[i];
-                if (c.type == C_BARRIER) {
-                    for (int q = c.lo; q < c.hi; ++q)
-                        if (q != H.rank) { cs.sig.push_back({q, ++sent[q]}); cs.wait.push_back({q, ++recv[q]}); }
-                } else if (H.rank == c.root) {
-                    // the owner of the next block column first: it is the one the factorization chain waits for
-                    for (int k = 1; k < c.hi - c.lo; ++k) {
-                        const int q = c.lo + (c.root - c.lo + k) % (c.hi - c.lo);
-                        cs.sig.push_back({q, ++psent[q]});
-                    }
-                } else {
-                    cs.wait.push_back({c.root, ++precv[c.root]});
-                }
-            }
         }
     }
     if (prm.leaf_lookahead) {

@@ -790,6 +790,35 @@ int build_plan(const Symbolic &S, const PlanParams &prm, HostPlan &P, int rank, 
         P.phases.push_back(ph);
     }
 
+    // ---- flags of the exchange steps (see plan_types.h: CollSync) ------------------------------------------------------------
+    if (world > 1) {
+        std::vector<uint32_t> sent(world, 0), recv(world, 0), psent(world, 0), precv(world, 0);
+        P.coll_sync.assign(P.colls.size(), CollSync{0, 0, 0, 0, 0, 0});
+        for (size_t i = 0; i < P.colls.size(); ++i) {
+            const Coll &c = P.colls[i];
+            CollSync &cs = P.coll_sync[i];
+            cs.chan = c.type == C_BARRIER ? 0 : 1;
+            if (rank < c.lo || rank >= c.hi) continue;
+            cs.sig_first = (int32_t)P.sync_points.size();
+            if (c.type == C_BARRIER) {
+                for (int q = c.lo; q < c.hi; ++q) if (q != rank) P.sync_points.push_back(SyncPoint{q, ++sent[q]});
+            } else if (rank == c.root) {
+                for (int k = 1; k < c.hi - c.lo; ++k) {
+                    const int q = c.lo + (c.root - c.lo + k) % (c.hi - c.lo);
+                    P.sync_points.push_back(SyncPoint{q, ++psent[q]});
+                }
+            }
+            cs.sig_count = (int32_t)P.sync_points.size() - cs.sig_first;
+            cs.wait_first = (int32_t)P.sync_points.size();
+            if (c.type == C_BARRIER) {
+                for (int q = c.lo; q < c.hi; ++q) if (q != rank) P.sync_points.push_back(SyncPoint{q, ++recv[q]});
+            } else if (rank != c.root) {
+                P.sync_points.push_back(SyncPoint{c.root, ++precv[c.root]});
+            }
+            cs.wait_count = (int32_t)P.sync_points.size() - cs.wait_first;
+        }
+    }
+
     // ---- triangular-solve schedule (device-resident factor; single-GPU plans only) -----------------------------------
     if (world == 1) {
         P.lsi32.assign(S.Lsi.begin(), S.Lsi.end());

@@ -93,6 +93,8 @@ struct HostPlan {
     std::vector<int32_t> group_lo, group_hi;// ranks [lo,hi) that hold descendants of the supernode (hi-lo > 1: "shared")
     double local_flops = 0.0;               // flops of the supernodes this rank owns
     std::vector<Coll> colls;                // exchange steps, grouped by segment (the same list on every rank)
+    std::vector<CollSync> coll_sync;        // flags of every exchange step, as THIS rank sees them (plan_types.h)
+    std::vector<SyncPoint> sync_points;
     std::vector<i64> coll_dst;              // C_BCAST steps this rank is the root of: block offset in every destination's image
     std::vector<Segment> segments;          // exchange steps, then launches
     std::vector<i64> image_elems;           // image size of every rank (elements); image_elems[rank] == xsize_pad

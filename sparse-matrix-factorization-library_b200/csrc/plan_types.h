@@ -147,6 +147,20 @@ struct Coll {
     int32_t dst_first;     // C_BCAST on its root: HostPlan::coll_dst[dst_first + (q - lo)] = offset of the block in rank q's image
 };
 
+// Flags of the exchange steps: both ends of a (signaller, waiter) pair walk the same step list and count the signals of that
+// pair per channel, so the n-th signal from rank a to rank b on a channel is "n" on both sides without any communication.
+// Channel 0: barriers (signalled from the main stream), channel 1: pushed blocks (signalled from the push stream).
+struct SyncPoint {
+    int32_t peer;
+    uint32_t seq;
+};
+struct CollSync {               // per exchange step: ranges into HostPlan::sync_points (empty on ranks outside [lo,hi))
+    int32_t sig_first, sig_count;     // signals this rank sends (barrier: to every other rank of the group; push: root to each destination,
+                                      // the owner of the next block column first)
+    int32_t wait_first, wait_count;   // flags this rank waits for
+    int32_t chan, pad;
+};
+
 struct Segment {
     int32_t level;
     int32_t coll_first, coll_count;

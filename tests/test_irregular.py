@@ -207,3 +207,15 @@ def test_partitioned_schedule_on_irregular_trees(n, density, seed, kind, world, 
     mask = sf.lower_trapezoid_mask(kind, st["Super"], st["Lsip"], st["Lsxp"], S.int("xsize"))
     assert sf.entrywise_rel_diff(ref[mask], out[mask]) <= 1e-10
     assert bal.sum() == pytest.approx(S.flops, rel=1e-12)
+    # the same partition with one free-running thread per rank and the real flags (groups of irregular forests overlap in
+    # ways the regular grids never produce)
+    lib.sfcheck_factorize_threaded.restype = C.c_long
+    lib.sfcheck_factorize_threaded.argtypes = [C.c_int, C.c_int, C.c_long, C.c_void_p, C.c_void_p, C.c_void_p, C.c_ulonglong] + \
+        [C.c_int] * 7 + [C.c_double, C.c_void_p]
+    for jitter in (0, 30):
+        out2 = np.full(S.int("xsize"), np.nan)
+        rc = lib.sfcheck_factorize_threaded(int(kind == "lu"), int(A.symmetric), A.n, A.Cp.ctypes.data, A.Ci.ctypes.data,
+                                            A.Cx.ctypes.data, sf.DEFAULT_DEVSLOT, nb, 2 * nb, 0 if nb else -1, 0 if nb else -1,
+                                            world, 2, jitter, 60.0, out2.ctypes.data)
+        assert rc == 0
+        assert sf.entrywise_rel_diff(ref[mask], out2[mask]) <= 1e-10

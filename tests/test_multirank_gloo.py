@@ -138,3 +138,72 @@ def test_partition_simulated_up_to_8_ranks(group_panels, monkeypatch):
                 assert bal.max() / bal.sum() < 0.75          # no rank is left with (almost) everything
                 # images are compact: a rank stores its own panels and the shared fronts of its groups, not the whole factor
                 assert max(image) < plan_elems and sum(image) >= plan_elems
+
+
+@pytest.mark.parametrize("gen,g,kind,group_panels", [("lap3d", 14, "cholesky", 0), ("lap3d", 14, "cholesky", 1), ("cd3d", 12, "lu", 0),
+                                                     ("lap2d", 60, "cholesky", 1)])
+def test_exchange_protocol_under_real_concurrency(gen, g, kind, group_panels, monkeypatch):
+    """The flags themselves: one host thread per rank, NO lock step, three factorizations back to back, the plan's own
+    sequence numbers and epochs (oracle/plan_host_exec.cpp: sfcheck_factorize_threaded).  A remote add that is not fenced by
+    a barrier, a wait nobody signals, or a start barrier that lets a fast rank add into an image its owner has not zeroed
+    yet shows up as a wrong factor or a timeout; per-step jitter varies the interleaving from run to run."""
+    monkeypatch.setenv("SFCHECK_DIST_PANEL_MIN", "32" if group_panels else "1000000")
+    monkeypatch.setenv("SFCHECK_DIST_MIN_M", "24" if group_panels else "48")
+    import ctypes as C
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import sforacle
+    import sparseframe_b200 as sf
+    lib = C.CDLL(os.path.join(ROOT, "oracle", "_ref", "libsfcheck.so"))
+    lib.sfcheck_factorize_threaded.restype = C.c_long
+    lib.sfcheck_factorize_threaded.argtypes = [C.c_int, C.c_int, C.c_long, C.c_void_p, C.c_void_p, C.c_void_p, C.c_ulonglong] + \
+        [C.c_int] * 7 + [C.c_double, C.c_void_p]
+    A = sf.compress(*sf.matrices.generate(gen, g))
+    S = sf.analyze(A, kind)
+    st = {k: S.array(k) for k in ("Super", "SuperMap", "Lsip", "Lsxp", "Lsi", "LeafQueue", "Lp", "Li")}
+    st["csize"], st["nsleaf"] = S.int("csize"), S.int("nsleaf")
+    ux = None
+    if kind == "lu":
+        st["Up"], st["Ui"] = S.array("Up"), S.array("Ui")
+        ux = S.array("Ux")
+    ref, bad = sforacle.factorize(kind, st, S.array("Lx"), ux)
+    assert bad == 0
+    mask = sf.lower_trapezoid_mask(kind, st["Super"], st["Lsip"], st["Lsxp"], S.int("xsize"))
+    for world in (2, 3, 4, 8):
+        for jitter in (0, 40):
+            out = np.full(S.int("xsize"), np.nan)
+            rc = lib.sfcheck_factorize_threaded(int(kind == "lu"), int(A.symmetric), A.n, A.Cp.ctypes.data, A.Ci.ctypes.data,
+                                                A.Cx.ctypes.data, sf.DEFAULT_DEVSLOT, 8 if group_panels else 0,
+                                                16 if group_panels else 0, -1, -1, world, 3, jitter, 60.0, out.ctypes.data)
+            assert rc == 0, "world %d jitter %d: rc %d (-300 = a flag wait timed out)" % (world, jitter, rc)
+            assert not np.isnan(out[mask]).any()
+            assert sf.entrywise_rel_diff(ref[mask], out[mask]) <= 1e-10, (world, jitter)
+            assert np.array_equal(ref[mask] == 0, out[mask] == 0)
+
+
+def test_concurrency_checker_notices_missing_waits(monkeypatch):
+    """Self-test of the threaded checker: with every flag wait dropped the ranks run past each other and the factor is wrong."""
+    monkeypatch.setenv("SFCHECK_DIST_PANEL_MIN", "32")
+    monkeypatch.setenv("SFCHECK_DIST_MIN_M", "24")
+    monkeypatch.setenv("SFCHECK_THREADED_NO_WAIT", "1")
+    import ctypes as C
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import sforacle
+    import sparseframe_b200 as sf
+    lib = C.CDLL(os.path.join(ROOT, "oracle", "_ref", "libsfcheck.so"))
+    lib.sfcheck_factorize_threaded.restype = C.c_long
+    lib.sfcheck_factorize_threaded.argtypes = [C.c_int, C.c_int, C.c_long, C.c_void_p, C.c_void_p, C.c_void_p, C.c_ulonglong] + \
+        [C.c_int] * 7 + [C.c_double, C.c_void_p]
+    A = sf.compress(*sf.matrices.generate("lap3d", 14))
+    S = sf.analyze(A, "cholesky")
+    st = {k: S.array(k) for k in ("Super", "SuperMap", "Lsip", "Lsxp", "Lsi", "LeafQueue", "Lp", "Li")}
+    st["csize"], st["nsleaf"] = S.int("csize"), S.int("nsleaf")
+    ref, _ = sforacle.factorize("cholesky", st, S.array("Lx"), None)
+    mask = sf.lower_trapezoid_mask("cholesky", st["Super"], st["Lsip"], st["Lsxp"], S.int("xsize"))
+    wrong = 0
+    for jitter in (0, 20, 60, 100):
+        out = np.full(S.int("xsize"), np.nan)
+        rc = lib.sfcheck_factorize_threaded(0, 1, A.n, A.Cp.ctypes.data, A.Ci.ctypes.data, A.Cx.ctypes.data, sf.DEFAULT_DEVSLOT,
+                                            8, 16, -1, -1, 4, 3, jitter, 30.0, out.ctypes.data)
+        good = rc == 0 and not np.isnan(out[mask]).any() and sf.entrywise_rel_diff(ref[mask], out[mask]) <= 1e-10
+        wrong += not good
+    assert wrong > 0
