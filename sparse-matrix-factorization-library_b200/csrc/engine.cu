@@ -1093,6 +1093,10 @@ int sfb200_plan_set_stream(sfb200_plan *p, void *cuda_stream) {
  * accumulated per launch kind.  Slower than a plain replay (event records serialise nothing but add ~2 us each). */
 int sfb200_plan_profile(sfb200_plan *p) {
     if (!p) return SFB200_ERR_ARG;
+    if (p->H.world > 1 && !p->connected) {       // its scatter epilogues add into the peers' images
+        set_error("sfb200_plan_profile: this rank of a partitioned plan is not connected to its peers");
+        return SFB200_ERR_STATE;
+    }
     CK(cudaSetDevice(p->device));
     const HostPlan &H = p->H;
     cudaStream_t st = p->stream;
