@@ -35,9 +35,35 @@ int magma_dgetrf_nopiv ( int m, int n, double *A, int lda, int *info )
     return 0;
 }
 
+/* Complex twin (LU.c:2655): same column-by-column elimination in double-complex arithmetic (division as a multiplication
+ * by the reciprocal pivot, formed with a scaled modulus; products as four real multiplies).  Parity UNPINNED at this call
+ * for the same reason as above. */
 int magma_zgetrf_nopiv ( int m, int n, cuDoubleComplex *A, int lda, int *info )
 {
-    (void) m; (void) n; (void) A; (void) lda;
-    *info = -1;     /* complex LU is outside the scope of this oracle */
-    return -1;
+    int mn = m < n ? m : n;
+    *info = 0;
+    for ( int k = 0; k < mn; k++ )
+    {
+        cuDoubleComplex *colk = A + (long) k * lda;
+        cuDoubleComplex pivot = colk[k];
+        if ( pivot.x == 0.0 && pivot.y == 0.0 )
+        {
+            if ( *info == 0 ) *info = k + 1;
+            continue;
+        }
+        for ( int i = k + 1; i < m; i++ )
+            colk[i] = cuCdiv ( colk[i], pivot );
+        for ( int j = k + 1; j < n; j++ )
+        {
+            cuDoubleComplex *colj = A + (long) j * lda;
+            cuDoubleComplex u = colj[k];
+            if ( u.x != 0.0 || u.y != 0.0 )
+                for ( int i = k + 1; i < m; i++ )
+                {
+                    colj[i].x -= colk[i].x * u.x - colk[i].y * u.y;
+                    colj[i].y -= colk[i].x * u.y + colk[i].y * u.x;
+                }
+        }
+    }
+    return 0;
 }

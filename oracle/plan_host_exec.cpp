@@ -19,6 +19,7 @@
 #include <string>
 #include <vector>
 
+#include "complex_embed.hpp"
 #include "plan.hpp"
 #include "symbolic.hpp"
 
@@ -177,6 +178,15 @@ int small_front(double *X, double *const *img, const HostPlan &P, i64 s) {
 struct CheckHandle {
     Symbolic S;
     HostPlan P;
+};
+
+// a complex matrix on the interpreter: Z = its analysis, the base handle holds the real embedding (complex_embed.hpp)
+struct ZCheckHandle {
+    Symbolic Z;
+    ComplexEmbedding E;
+    CheckHandle base;
+    std::vector<double> phase;      // empty: rows not rotated
+    std::vector<ZExtractTask> tasks;
 };
 
 void assemble(const CheckHandle &h, double *X) {
@@ -475,6 +485,63 @@ long sfcheck_factorize(int kind, int is_symmetric, long n, const long *Cp, const
     const long bad = run_launches(P, X.data(), &self, 0, (int)P.launches.size());
     pack(P, X.data(), Lsx_out);
     delete h;
+    return bad;
+}
+
+/* ---- complex matrices: analysis with the complex element size, real embedding, the ordinary schedule on the embedded
+ * structure, complex panels read back (csrc/complex_embed.hpp).  Cz: interleaved (re, im) values; row_phase != 0 rotates every
+ * row by the phase of its diagonal entry first (LU), as the engine does.  Lsz_out: xsize complex numbers (2 * xsize doubles);
+ * stats = {nsuper, xsize (complex entries), embedded xsize_pad, nlaunches, embedded nnz, embedded unnz}.  With a null Lsz_out only
+ * the sizes are returned.  struct_out (may be NULL) receives pointers-by-copy is not needed: the structure equals the one
+ * sfb200_analyze_complex returns.  Return value like sfcheck_factorize. */
+long sfcheck_factorize_complex(int kind, int is_symmetric, long n, const long *Cp, const long *Ci, const double *Cz,
+                               unsigned long long dev_slot, int nb, int outer, int small_a, int small_b, int row_phase,
+                               double *Lsz_out, long *stats, double *rhs /* may be NULL: n complex, solved in place */) {
+    ZCheckHandle h;
+    CscView A;
+    A.n = n; A.colptr = (const i64 *)Cp; A.rowind = (const i64 *)Ci; A.val = Cz; A.symmetric = is_symmetric != 0; A.is_complex = true;
+    if (analyze(A, kind ? Kind::LU : Kind::Cholesky, dev_slot, h.Z) != 0) return -1;
+    if (embed_complex(h.Z, h.E) != 0) return -2;
+    if (row_phase && kind) {
+        std::vector<i64> pos;
+        diagonal_positions(h.Z, pos);
+        h.phase.resize(2 * (size_t)n);
+        const bool from_u = !h.Z.symmetric;
+        row_phases(pos, (from_u ? h.Z.U.val : h.Z.L.val).data(), h.phase.data());
+    }
+    if (expand_embedding(h.Z, h.E, h.phase.empty() ? nullptr : h.phase.data()) != 0) return -3;
+    h.base.S = h.E.R;
+    PlanParams prm;
+    if (nb > 0) prm.nb = nb;
+    if (outer > 0) prm.outer = outer % 100000;
+    if (outer >= 100000) prm.outer2 = outer / 100000;
+    if (small_a >= 0) prm.small_a_bytes = small_a;
+    if (small_b >= 0) prm.small_b_bytes = small_b;
+    if (build_plan(h.base.S, prm, h.base.P, 0, 1) != 0) return -4;
+    const HostPlan &P = h.base.P;
+    if (stats) {
+        stats[0] = h.Z.nsuper; stats[1] = h.Z.xsize; stats[2] = P.xsize_pad; stats[3] = (long)P.launches.size();
+        stats[4] = P.nnz; stats[5] = P.unnz;
+    }
+    if (!Lsz_out) return 0;
+    std::vector<double> X(P.xsize_pad + P.wsize, 0.0);
+    assemble(h.base, X.data());
+    double *self = X.data();
+    const long bad = run_launches(P, X.data(), &self, 0, (int)P.launches.size());
+    build_zextract_tasks(P, h.Z, h.tasks);
+    const double *ph = h.phase.empty() ? nullptr : h.phase.data();
+    for (const ZExtractTask &t : h.tasks) zextract_host(t, X.data(), Lsz_out, ph, h.Z.Lsi.data());
+    if (rhs) {
+        // the complex solve IS the real solve of the embedded system on the interleaved right-hand side; rotated rows:
+        // (D^H A) x = D^H b
+        if (ph)
+            for (long k = 0; k < n; ++k) {
+                const double re = rhs[2 * k], im = rhs[2 * k + 1], dr = ph[2 * k], di = ph[2 * k + 1];
+                rhs[2 * k] = dr * re + di * im; rhs[2 * k + 1] = dr * im - di * re;
+            }
+        for (const SolveLaunch &L : P.solve_fwd) for (int k = 0; k < L.count; ++k) solve_task(P, P.solve_tasks[L.first + k], L.kind, X.data(), rhs);
+        for (const SolveLaunch &L : P.solve_bwd) for (int k = 0; k < L.count; ++k) solve_task(P, P.solve_tasks[L.first + k], L.kind, X.data(), rhs);
+    }
     return bad;
 }
 

@@ -41,9 +41,12 @@ struct sfref_handle
     int validated;
 };
 
-void *sfref_create ( int is_symmetric, long n, long nz, const long *Ti, const long *Tj, const double *Tx,
+/* is_complex: Tx holds nz interleaved (re, im) pairs -- the reference's Complex (Include/type.h), as its reader stores
+ * a MatrixMarket file whose field is not "real" (CH.c:440-445, 505-511) */
+static void *sfref_create_any ( int is_symmetric, int is_complex, long n, long nz, const long *Ti, const long *Tj, const double *Tx,
         unsigned long long dev_slot_size, int blas_threads )
 {
+    size_t elem = is_complex ? sizeof(Complex) : sizeof(Float);
     struct sfref_handle *h = calloc ( 1, sizeof ( struct sfref_handle ) );
     struct matrix_info_struct *m = &h->matrix;
 
@@ -68,16 +71,16 @@ void *sfref_create ( int is_symmetric, long n, long nz, const long *Ti, const lo
     SparseFrame_initialize_matrix ( m );
 
     m->isSymmetric = is_symmetric;
-    m->isComplex = FALSE;
+    m->isComplex = is_complex ? TRUE : FALSE;
     m->ncol = n;
     m->nrow = n;
     m->nzmax = nz;
     m->Tj = malloc ( ( nz > 0 ? nz : 1 ) * sizeof(Long) );
     m->Ti = malloc ( ( nz > 0 ? nz : 1 ) * sizeof(Long) );
-    m->Tx = malloc ( ( nz > 0 ? nz : 1 ) * sizeof(Float) );
+    m->Tx = malloc ( ( nz > 0 ? nz : 1 ) * elem );
     memcpy ( m->Tj, Tj, nz * sizeof(Long) );
     memcpy ( m->Ti, Ti, nz * sizeof(Long) );
-    memcpy ( m->Tx, Tx, nz * sizeof(Float) );
+    memcpy ( m->Tx, Tx, nz * elem );
 
     /* workspace sizing rule of SparseFrame_read_matrix; calloc because the LU
      * analysis counts into it without zeroing (LU.c:2271-2283) */
@@ -89,6 +92,18 @@ void *sfref_create ( int is_symmetric, long n, long nz, const long *Ti, const lo
     SparseFrame_compress ( m );
 
     return h;
+}
+
+void *sfref_create ( int is_symmetric, long n, long nz, const long *Ti, const long *Tj, const double *Tx,
+        unsigned long long dev_slot_size, int blas_threads )
+{
+    return sfref_create_any ( is_symmetric, 0, n, nz, Ti, Tj, Tx, dev_slot_size, blas_threads );
+}
+
+void *sfref_create_complex ( int is_symmetric, long n, long nz, const long *Ti, const long *Tj, const double *Tz,
+        unsigned long long dev_slot_size, int blas_threads )
+{
+    return sfref_create_any ( is_symmetric, 1, n, nz, Ti, Tj, Tz, dev_slot_size, blas_threads );
 }
 
 int sfref_analyze ( void *hv )
@@ -131,6 +146,7 @@ long sfref_long ( void *hv, const char *name )
     if ( !strcmp ( name, "nsleaf" ) ) return m->nsleaf;
     if ( !strcmp ( name, "nstage" ) ) return m->nstage;
     if ( !strcmp ( name, "isSymmetric" ) ) return m->isSymmetric;
+    if ( !strcmp ( name, "isComplex" ) ) return m->isComplex;
     return -1;
 }
 

@@ -116,6 +116,32 @@ def plan_check(kind, A_n, Cp, Ci, Cx, symmetric, devslot, nb=0, outer=0, small_a
     return out, int(rc), stats
 
 
+def check_plan_complex(kind, A_n, Cp, Ci, Cz, symmetric, devslot, nb=0, outer=0, small_a=-1, small_b=-1, row_phase=False,
+                       rhs=None):
+    """A complex matrix on the CPU interpreter: analysis with the complex element size, real embedding
+    (csrc/complex_embed.cpp), the ordinary schedule on the embedded structure, complex panels read back.
+    Returns (Lsx complex128, failed pivots, stats, x or None)."""
+    global _chk
+    if _chk is None:
+        _chk = C.CDLL(os.path.join(_HERE, "_ref", "libsfcheck.so"))
+    f = _chk.sfcheck_factorize_complex
+    f.restype = C.c_long
+    f.argtypes = [C.c_int, C.c_int, C.c_long, C.c_void_p, C.c_void_p, C.c_void_p, C.c_ulonglong] + [C.c_int] * 5 + \
+        [C.c_void_p, C.c_void_p, C.c_void_p]
+    Cp, Ci = _i64(Cp), _i64(Ci)
+    Cz = np.ascontiguousarray(Cz, dtype=np.complex128)
+    stats = np.zeros(8, dtype=np.int64)
+    args = (int(kind in (1, "lu")), int(symmetric), int(A_n), Cp.ctypes.data, Ci.ctypes.data, Cz.ctypes.data, int(devslot),
+            nb, outer, small_a, small_b, int(bool(row_phase)))
+    rc = f(*args, None, stats.ctypes.data, None)
+    if rc < 0:
+        raise RuntimeError("complex plan check failed: %d" % rc)
+    out = np.zeros(int(stats[1]), dtype=np.complex128)
+    x = None if rhs is None else np.ascontiguousarray(rhs, dtype=np.complex128).copy()
+    rc = f(*args, out.ctypes.data, stats.ctypes.data, None if x is None else x.ctypes.data)
+    return out, int(rc), stats, x
+
+
 class CheckBackend:
     """One rank of a `world`-way etree partition executed by the CPU plan interpreter (oracle/plan_host_exec.cpp), behind
     the backend protocol of sparseframe_b200.parallel (exchange_handle / connect / factorize / finish) so that the

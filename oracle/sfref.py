@@ -30,6 +30,8 @@ def _lib(kind: str):
         lib.sfref_create.restype = C.c_void_p
         lib.sfref_create.argtypes = [C.c_int, C.c_long, C.c_long, C.c_void_p, C.c_void_p, C.c_void_p,
                                      C.c_ulonglong, C.c_int]
+        lib.sfref_create_complex.restype = C.c_void_p
+        lib.sfref_create_complex.argtypes = lib.sfref_create.argtypes
         for f in ("sfref_analyze", "sfref_factorize", "sfref_validate"):
             getattr(lib, f).restype = C.c_int
             getattr(lib, f).argtypes = [C.c_void_p]
@@ -46,16 +48,20 @@ def _lib(kind: str):
 
 
 class Reference:
-    """One matrix going through the reference's analyze / factorize / validate."""
+    """One matrix going through the reference's analyze / factorize / validate.  Complex `vals` select the reference's
+    isComplex path (values travel as interleaved (re, im) pairs, value arrays come back as complex128)."""
 
     def __init__(self, n, rows, cols, vals, symmetric, kind="cholesky", devslot=DEFAULT_DEVSLOT, blas_threads=0):
         self.kind = kind
         self.lib = _lib(kind)
         rows = np.ascontiguousarray(rows, dtype=np.int64)
         cols = np.ascontiguousarray(cols, dtype=np.int64)
-        vals = np.ascontiguousarray(vals, dtype=np.float64)
-        self.h = self.lib.sfref_create(int(bool(symmetric)), int(n), int(rows.size), rows.ctypes.data,
-                                       cols.ctypes.data, vals.ctypes.data, int(devslot), int(blas_threads))
+        self.complex = np.iscomplexobj(vals)
+        self.vdtype = np.complex128 if self.complex else np.float64
+        vals = np.ascontiguousarray(vals, dtype=self.vdtype)
+        create = self.lib.sfref_create_complex if self.complex else self.lib.sfref_create
+        self.h = create(int(bool(symmetric)), int(n), int(rows.size), rows.ctypes.data,
+                        cols.ctypes.data, vals.ctypes.data, int(devslot), int(blas_threads))
         self.n = int(n)
 
     def analyze(self):
@@ -99,13 +105,13 @@ class Reference:
             return self._arr(name, int(self.array(ptr)[-1]), np.int64)
         if name in ("Lx", "LTx", "Ux", "UTx"):
             ptr = {"Lx": "Lp", "LTx": "LTp", "Ux": "Up", "UTx": "UTp"}[name]
-            return self._arr(name, int(self.array(ptr)[-1]), np.float64)
+            return self._arr(name, int(self.array(ptr)[-1]), self.vdtype)
         if name == "Cx":
-            return self._arr(name, nz, np.float64)
+            return self._arr(name, nz, self.vdtype)
         if name == "Lsx":
-            return self._arr(name, self.long("xsize"), np.float64)
+            return self._arr(name, self.long("xsize"), self.vdtype)
         if name in ("Xx", "Bx"):
-            return self._arr(name, n, np.float64)
+            return self._arr(name, n, self.vdtype)
         return self._arr(name, sizes[name], np.int64)
 
     def structure(self):

@@ -17,14 +17,14 @@ extern "C" {
 const char *sfb200_version(void) { return "sfb200 0.1 (sm_100a)"; }
 const char *sfb200_last_error(void) { return g_last_error.c_str(); }
 
-int sfb200_analyze_ordered(int kind, int is_symmetric, int64_t n, const int64_t *Cp, const int64_t *Ci, const double *Cx,
-                           uint64_t dev_slot_size, const int64_t *order, sfb200_symbolic **out) {
+static int analyze_any(int kind, int is_symmetric, bool is_complex, int64_t n, const int64_t *Cp, const int64_t *Ci,
+                       const double *Cx, uint64_t dev_slot_size, const int64_t *order, sfb200_symbolic **out) {
     if (!out || !Cp || n < 0 || (kind != SFB200_CHOLESKY && kind != SFB200_LU)) {
         set_error("sfb200_analyze: bad argument");
         return SFB200_ERR_ARG;
     }
     CscView A;
-    A.n = n; A.colptr = Cp; A.rowind = Ci; A.val = Cx; A.symmetric = is_symmetric != 0;
+    A.n = n; A.colptr = Cp; A.rowind = Ci; A.val = Cx; A.symmetric = is_symmetric != 0; A.is_complex = is_complex;
     auto *s = new sfb200_symbolic();
     const int rc = analyze(A, kind == SFB200_LU ? Kind::LU : Kind::Cholesky, dev_slot_size, s->S, order);
     if (rc != 0) {
@@ -36,6 +36,24 @@ int sfb200_analyze_ordered(int kind, int is_symmetric, int64_t n, const int64_t 
     }
     *out = s;
     return SFB200_OK;
+}
+
+int sfb200_analyze_ordered(int kind, int is_symmetric, int64_t n, const int64_t *Cp, const int64_t *Ci, const double *Cx,
+                           uint64_t dev_slot_size, const int64_t *order, sfb200_symbolic **out) {
+    return analyze_any(kind, is_symmetric, false, n, Cp, Ci, Cx, dev_slot_size, order, out);
+}
+
+int sfb200_analyze_complex(int kind, int is_symmetric, int64_t n, const int64_t *Cp, const int64_t *Ci, const double *Cz,
+                           uint64_t dev_slot_size, const int64_t *order, sfb200_symbolic **out) {
+    return analyze_any(kind, is_symmetric, true, n, Cp, Ci, Cz, dev_slot_size, order, out);
+}
+
+int sfb200_symbolic_wrap_complex(int kind, int64_t n, int64_t nsuper, const int64_t *Super, const int64_t *Lsip,
+                                 const int64_t *Lsxp, const int64_t *Lsi, const int64_t *Lp, const int64_t *Li,
+                                 const int64_t *Up, const int64_t *Ui, sfb200_symbolic **out) {
+    const int rc = sfb200_symbolic_wrap(kind, n, nsuper, Super, Lsip, Lsxp, Lsi, Lp, Li, Up, Ui, out);
+    if (rc == SFB200_OK) (*out)->S.is_complex = true;
+    return rc;
 }
 
 int sfb200_analyze(int kind, int is_symmetric, int64_t n, const int64_t *Cp, const int64_t *Ci, const double *Cx,
@@ -134,6 +152,7 @@ int64_t sfb200_symbolic_int(const sfb200_symbolic *s, const char *name) {
     if (k == "nsleaf") return S.nsleaf;
     if (k == "kind") return (int64_t)S.kind;
     if (k == "symmetric") return S.symmetric;
+    if (k == "complex") return S.is_complex;
     return -1;
 }
 

@@ -60,10 +60,11 @@ void permute_triangles(const CscView &A, Kind kind, const std::vector<i64> &perm
     std::vector<i64> inv(n, -1);
     for (i64 j = 0; j < n; ++j) if (perm[j] >= 0) inv[perm[j]] = j;
 
+    const i64 vw = A.is_complex ? 2 : 1;      // doubles per value (CH.c:1050-1060: Complex entries are moved whole)
     auto reset = [&](Tri &t, bool on) {
         t.ptr.assign(on ? n + 1 : 0, 0);
         t.idx.assign(on ? nnz : 0, 0);
-        t.val.assign(on ? nnz : 0, 0.0);
+        t.val.assign(on ? nnz * vw : 0, 0.0);
     };
     reset(L, true); reset(LT, true); reset(U, split); reset(UT, split);
 
@@ -83,7 +84,7 @@ void permute_triangles(const CscView &A, Kind kind, const std::vector<i64> &perm
     }
     auto scan = [](Tri &t) { if (!t.ptr.empty()) std::partial_sum(t.ptr.begin(), t.ptr.end(), t.ptr.begin()); };
     scan(L); scan(LT); scan(U); scan(UT);
-    auto trim = [&](Tri &t) { if (!t.ptr.empty()) { t.idx.resize(t.ptr[n]); t.val.resize(t.ptr[n]); } };
+    auto trim = [&](Tri &t) { if (!t.ptr.empty()) { t.idx.resize(t.ptr[n]); t.val.resize(t.ptr[n] * vw); } };
     trim(L); trim(LT); trim(U); trim(UT);
 
     std::vector<i64> cl(L.ptr.begin(), L.ptr.end() - 1), clt(LT.ptr.begin(), LT.ptr.end() - 1), cu, cut;
@@ -94,20 +95,19 @@ void permute_triangles(const CscView &A, Kind kind, const std::vector<i64> &perm
         if (jo < 0) continue;
         for (i64 p = A.colptr[jo]; p < A.colptr[jo + 1]; ++p) {
             const i64 i = inv[A.rowind[p]];
-            const double v = A.val ? A.val[p] : 0.0;
+            // a value moves as it is: an entry of a complex "symmetric" matrix that the permutation carries across the
+            // diagonal is NOT conjugated (CH.c:1048-1060)
+            auto put = [&](Tri &t, i64 q, i64 index) {
+                t.idx[q] = index;
+                for (i64 w = 0; w < vw; ++w) t.val[q * vw + w] = A.val ? A.val[p * vw + w] : 0.0;
+            };
             if (!split) {
                 const i64 lo = std::min(i, j), hi = std::max(i, j);
-                i64 q = cl[lo]++;  L.idx[q] = hi;  L.val[q] = v;
-                q = clt[hi]++;     LT.idx[q] = lo; LT.val[q] = v;
+                put(L, cl[lo]++, hi);
+                put(LT, clt[hi]++, lo);
             } else {
-                if (j <= i) {
-                    i64 q = cl[j]++;  L.idx[q] = i;  L.val[q] = v;
-                    q = clt[i]++;     LT.idx[q] = j; LT.val[q] = v;
-                }
-                if (j >= i) {
-                    i64 q = cu[i]++;  U.idx[q] = j;  U.val[q] = v;
-                    q = cut[j]++;     UT.idx[q] = i; UT.val[q] = v;
-                }
+                if (j <= i) { put(L, cl[j]++, i); put(LT, clt[i]++, j); }
+                if (j >= i) { put(U, cu[i]++, j); put(UT, cut[j]++, i); }
             }
         }
     }
@@ -266,7 +266,8 @@ static void supernodal_structure(const CscView &A, Symbolic &S) {
     const bool lu = S.kind == Kind::LU;
     const bool split = lu && !S.symmetric;
     const uint64_t slot = S.devSlotSize;
-    const uint64_t FB = sizeof(double), IB = sizeof(i64);
+    // bytes per panel entry: Float or Complex (CH.c:1480-1496, 1558-1574, 1743-1790, 1893-1896)
+    const uint64_t FB = S.is_complex ? 2 * sizeof(double) : sizeof(double), IB = sizeof(i64);
 
     // relabel by the weighted postorder and rebuild the triangles in the final ordering (CH.c:1429-1447)
     {
@@ -482,6 +483,7 @@ int analyze(const CscView &A, Kind kind, uint64_t devSlotSize, Symbolic &S, cons
     S = Symbolic();
     S.kind = kind;
     S.symmetric = (kind == Kind::Cholesky) ? true : A.symmetric;
+    S.is_complex = A.is_complex;
     S.n = A.n;
     S.nnz = A.colptr[A.n];
     S.devSlotSize = devSlotSize;

@@ -23,17 +23,19 @@ struct CscView {
     const i64 *rowind = nullptr;
     const double *val = nullptr;
     bool symmetric = true;
+    bool is_complex = false;     // val holds interleaved (re, im) pairs: the reference's Complex (Include/arch.h:9-16)
 };
 
 // One triangular half in compressed form (pointer / index / value), reference field names in comments.
 struct Tri {
     std::vector<i64> ptr, idx;
-    std::vector<double> val;
+    std::vector<double> val;     // one double per entry; two (re, im) for a complex matrix
 };
 
 struct Symbolic {
     Kind kind = Kind::Cholesky;
     bool symmetric = true;          // LU only: unsymmetric input keeps a separate U
+    bool is_complex = false;        // matrix_info->isComplex: values are (re, im) pairs, panels hold Complex (CH.c:1648-1651)
     i64 n = 0;
     i64 nnz = 0;
     uint64_t devSlotSize = 0;       // common_info->devSlotSize; the structure depends on it (CH.c:1476-1496, 1556-1574)
