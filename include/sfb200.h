@@ -67,7 +67,18 @@ int sfb200_symbolic_wrap(int kind, int64_t n, int64_t nsuper, const int64_t *Sup
                          const int64_t *Lsxp, const int64_t *Lsi, const int64_t *Lp, const int64_t *Li,
                          const int64_t *Up, const int64_t *Ui, sfb200_symbolic **out);
 
-/* Scalars: "n","nnz","nsuper","nfsuper","isize","xsize","csize","nstage","nsleaf","unnz".  -1 if unknown. */
+/* Complex matrices (matrix_info->isComplex; the reference's Complex = interleaved (re, im) doubles, Include/arch.h:9-16).
+ * Same analysis, with the element size of a Complex wherever the structure depends on it (supernode caps CH.c:1480-1496,
+ * relaxed merging 1558-1574, stages 1743-1790, Aoffset 1893-1896); values are carried as pairs ("Lx" etc. then hold 2 doubles
+ * per entry).  A complex "symmetric" matrix keeps the reference's meaning: Cholesky reads the permuted lower triangle as the
+ * lower triangle of a Hermitian matrix (zherk / zpotrf), LU as A = A^T.  `order` may be NULL (METIS). */
+int sfb200_analyze_complex(int kind, int is_symmetric, int64_t n, const int64_t *Cp, const int64_t *Ci, const double *Cz,
+                           uint64_t dev_slot_size, const int64_t *order, sfb200_symbolic **out);
+int sfb200_symbolic_wrap_complex(int kind, int64_t n, int64_t nsuper, const int64_t *Super, const int64_t *Lsip,
+                                 const int64_t *Lsxp, const int64_t *Lsi, const int64_t *Lp, const int64_t *Li,
+                                 const int64_t *Up, const int64_t *Ui, sfb200_symbolic **out);
+
+/* Scalars: "n","nnz","nsuper","nfsuper","isize","xsize","csize","nstage","nsleaf","unnz","complex".  -1 if unknown. */
 int64_t sfb200_symbolic_int(const sfb200_symbolic *s, const char *name);
 
 /* Wall time of the analysis stages in seconds: "t_order" (adjacency + METIS), "t_tree" (permute, etree, postorder,
@@ -184,6 +195,31 @@ int sfb200_solve_device(sfb200_plan *p, double *d_B, int nrhs);       /* device 
 /* Residual of the permuted system with the matrix values of the last factorize (SparseFrame_validate, CH.c:3197-3263):
  * out[5] = {||A||_1, ||b||_inf, ||x||_inf, ||Ax-b||_inf, ||Ax-b||_inf / (||A||_1 ||x||_inf + ||b||_inf)}. */
 int sfb200_residual(sfb200_plan *p, const double *x, const double *b, double out[5]);
+
+/* ---- complex factorization: zherk/zgemm/zpotrf/ztrsm (CH.c:2060-2070, 2134-2145) and
+ * zgemm/magma_zgetrf_nopiv/ztrsm (LU.c:2569-2581, 2652-2663) ---------------------------------------------------------------
+ * A zplan runs the FP64 engine on the real embedding of the complex matrix (every entry a+ib becomes the 2x2 block
+ * [a -b; b a]; csrc/complex_embed.hpp): chol(phi(A)) = phi(L), and the no-pivot LU factors are read off the embedded ones
+ * without arithmetic.  It needs a single GPU, twice the factor's bytes and executes twice the real flops of a native complex
+ * kernel; every kernel on its path is the FP64 engine's.  LU: rows are first rotated by the phase of their diagonal entry (the
+ * embedded elimination divides by Re u_kk; sfb200_zplan_set_row_phase(zp, 0) or SFB200_ZPHASE=0 switches that off), and the
+ * factors handed back are those of the ORIGINAL matrix either way.
+ * All complex arrays are interleaved (re, im) doubles: Lz / Uz like Lx / Ux (same order as Lp/Li, Up/Ui), Lsz = xsize
+ * Complex in the reference's panel layout, Bz = n x nrhs Complex. */
+typedef struct sfb200_zplan sfb200_zplan;
+int sfb200_zplan_create(const sfb200_symbolic *complex_structure, int device, sfb200_zplan **out);
+void sfb200_zplan_free(sfb200_zplan *zp);
+sfb200_plan *sfb200_zplan_real(sfb200_zplan *zp);              /* the plan of the embedded structure (owned by the zplan) */
+int64_t sfb200_zplan_int(const sfb200_zplan *zp, const char *name);   /* "n","nnz","unnz","xsize","row_phase", else as sfb200_plan_int of the embedded plan */
+int sfb200_zplan_set_row_phase(sfb200_zplan *zp, int on);
+int sfb200_zfactorize(sfb200_zplan *zp, const double *Lz, const double *Uz, double *Lsz /* may be NULL */);
+int sfb200_zfactorize_device(sfb200_zplan *zp, const double *d_Lz, const double *d_Uz);    /* asynchronous */
+int sfb200_zplan_sync(sfb200_zplan *zp);
+int sfb200_zdownload_factor(sfb200_zplan *zp, double *Lsz);
+/* The reference's complex solve / validate are `// TODO` (CH.c:3088-3131, 3229-3256); these are what they would be. */
+int sfb200_zsolve(sfb200_zplan *zp, double *Bz, int nrhs);
+int sfb200_zresidual(sfb200_zplan *zp, const double *xz, const double *bz, double out[5]);
+double sfb200_zlast_ms(const sfb200_zplan *zp);
 
 /* Device time of the last factorize call in milliseconds (which = 2: the last solve) (CUDA events on the plan's stream):
  * which = 0 numeric only (assemble + factor), 1 = including H2D/D2H copies of the host-buffer call. */

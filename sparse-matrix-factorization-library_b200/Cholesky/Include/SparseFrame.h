@@ -44,6 +44,8 @@ int SparseFrame_cleanup_matrix(struct matrix_info_struct *matrix_info);
 /* addition of the B200 drop-in (not in the reference): binary triplet container, see dropin/matrix_reader.hpp */
 int SparseFrame_write_binary_matrix(const char *path, int isSymmetric, Long nrow, Long ncol, Long nz, const Long *Ti,
                                     const Long *Tj, const Float *Tx);
+int SparseFrame_write_binary_matrix_complex(const char *path, int isSymmetric, Long nrow, Long ncol, Long nz, const Long *Ti,
+                                            const Long *Tj, const Complex *Tz);
 
 #ifdef __cplusplus
 }

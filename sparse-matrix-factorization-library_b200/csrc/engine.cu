@@ -16,6 +16,7 @@
 
 #include "../../include/sfb200.h"
 #include "capi_internal.hpp"
+#include "engine_internal.hpp"
 #include "kernels.cuh"
 #include "plan.hpp"
 
@@ -1502,3 +1503,7 @@ double sfb200_probe_fp64_peak(int device, int which, int iters) {
 }
 
 }  // extern "C"
+
+namespace sfb200 {
+PlanInternals plan_internals(sfb200_plan *p) { return PlanInternals{&p->H, p->d_X, p->d_lx, p->d_ux, p->stream, p->device, p->sms}; }
+}  // namespace sfb200

@@ -31,7 +31,7 @@ struct Triplets {
     bool symmetric = false, complex_field = false;
     long nrow = 0, ncol = 0, nz_declared = 0;
     std::vector<int64_t> ti, tj;     // 0-based
-    std::vector<double> tx;
+    std::vector<double> tx;          // one double per entry; (re, im) pairs when complex_field (CH.c:505-511)
 };
 
 enum { OK = 0, ERR_FORMAT = 1, ERR_ENTRY = 2, ERR_NZMAX = 3, ERR_IMAG = 4, ERR_IO = 5 };
@@ -141,6 +141,7 @@ inline void parse_entries(const char *p, const char *end, bool complex_field, Ch
                 c.ti.push_back(i - 1);
                 c.tj.push_back(j - 1);
                 c.tx.push_back(v);
+                if (complex_field) c.tx.push_back(w);
             }
         }
         p = nl ? nl + 1 : end;
@@ -205,13 +206,14 @@ inline int parse_matrix_market(const char *buf, size_t len, Triplets &T, int nth
     size_t total = 0;
     for (auto &c : chunks) { if (c.err) return c.err; total += c.ti.size(); }
     if ((long)total > T.nz_declared) return ERR_NZMAX;       // CH.c:495-499
-    T.ti.resize(total); T.tj.resize(total); T.tx.resize(total);
+    const size_t vw = T.complex_field ? 2 : 1;
+    T.ti.resize(total); T.tj.resize(total); T.tx.resize(total * vw);
     size_t at = 0;
     for (auto &c : chunks) {
         if (c.ti.empty()) continue;
         memcpy(T.ti.data() + at, c.ti.data(), c.ti.size() * sizeof(int64_t));
         memcpy(T.tj.data() + at, c.tj.data(), c.tj.size() * sizeof(int64_t));
-        memcpy(T.tx.data() + at, c.tx.data(), c.tx.size() * sizeof(double));
+        memcpy(T.tx.data() + at * vw, c.tx.data(), c.tx.size() * sizeof(double));
         at += c.ti.size();
     }
     return OK;
@@ -219,32 +221,35 @@ inline int parse_matrix_market(const char *buf, size_t len, Triplets &T, int nth
 
 // ---- binary triplet container ----------------------------------------------------------------------------------------
 // magic[8] | int64 flags (bit 0 symmetric, bit 1 complex) | int64 nrow | int64 ncol | int64 nz | Ti[nz] | Tj[nz] | Tx[nz]
+// (complex: Tx holds nz (re, im) pairs)
 inline bool is_binary(const char *buf, size_t len) { return len >= 8 && memcmp(buf, BIN_MAGIC, 8) == 0; }
 
 inline int parse_binary(const char *buf, size_t len, Triplets &T) {
     if (len < 40 || !is_binary(buf, len)) return ERR_FORMAT;
     int64_t h[4];
     memcpy(h, buf + 8, sizeof(h));
-    if (h[1] < 0 || h[2] < 0 || h[3] < 0 || (size_t)h[3] > (len - 40) / 24) return ERR_FORMAT;
     T.symmetric = (h[0] & 1) != 0;
     T.complex_field = (h[0] & 2) != 0;
+    const size_t vw = T.complex_field ? 2 : 1;
+    if (h[1] < 0 || h[2] < 0 || h[3] < 0 || (size_t)h[3] > (len - 40) / (16 + 8 * vw)) return ERR_FORMAT;
     T.nrow = (long)h[1]; T.ncol = (long)h[2]; T.nz_declared = (long)h[3];
     const size_t nz = (size_t)h[3];
-    T.ti.resize(nz); T.tj.resize(nz); T.tx.resize(nz);
+    T.ti.resize(nz); T.tj.resize(nz); T.tx.resize(nz * vw);
     memcpy(T.ti.data(), buf + 40, nz * 8);
     memcpy(T.tj.data(), buf + 40 + nz * 8, nz * 8);
-    memcpy(T.tx.data(), buf + 40 + nz * 16, nz * 8);
+    memcpy(T.tx.data(), buf + 40 + nz * 16, nz * 8 * vw);
     return OK;
 }
 
 inline int write_binary(const char *path, bool symmetric, int64_t nrow, int64_t ncol, int64_t nz, const int64_t *ti,
-                        const int64_t *tj, const double *tx) {
+                        const int64_t *tj, const double *tx, bool complex_field = false) {
     FILE *f = fopen(path, "wb");
     if (!f) return ERR_IO;
-    const int64_t h[4] = {symmetric ? 1 : 0, nrow, ncol, nz};
+    const int64_t h[4] = {(symmetric ? 1 : 0) | (complex_field ? 2 : 0), nrow, ncol, nz};
+    const size_t nv = (size_t)nz * (complex_field ? 2 : 1);
     bool ok = fwrite(BIN_MAGIC, 1, 8, f) == 8 && fwrite(h, 8, 4, f) == 4;
     ok = ok && fwrite(ti, 8, (size_t)nz, f) == (size_t)nz && fwrite(tj, 8, (size_t)nz, f) == (size_t)nz &&
-         fwrite(tx, 8, (size_t)nz, f) == (size_t)nz;
+         fwrite(tx, 8, nv, f) == nv;
     ok = (fclose(f) == 0) && ok;
     return ok ? OK : ERR_IO;
 }

@@ -20,6 +20,10 @@
  *   SparseFrame                CH.c:3323-3467 same driver and report format, MATRIX_THREAD_NUM matrices in flight
  *                                             (CH.c:3371-3444): one is read / analysed while another one factorizes
  *
+ * Complex matrices (isComplex: every MatrixMarket field other than "real", CH.c:440-445) run through sfb200_zplan_* (the
+ * FP64 engine on the real embedding, csrc/complex_embed.hpp) on one GPU; all value arrays of matrix_info then hold Complex
+ * like the reference's.  Its complex solve / validate are `// TODO` (CH.c:3088-3131, 3229-3256): here they are carried out.
+ *
  * devSlotSize policy.  The symbolic structure depends on it (supernode caps, relaxed merging), so it is derived exactly as
  * the reference derives it for the GPUs this library USES (SF_NUM_GPU, default: all visible): on one B200 5.38e9, on eight
  * 21.5e9 (no "GPU splitting", CH.c:36-41).  SF_DEVSLOT overrides; bench.py and the tests pin 5.38e9 for every N so that all
@@ -39,6 +43,7 @@
 #include <time.h>
 #include <unistd.h>
 
+#include <complex>
 #include <map>
 #include <mutex>
 #include <string>
@@ -56,6 +61,7 @@ struct Cached {
     sfb200_symbolic *sym = nullptr;
     sfb200_plan *plan = nullptr;       // single-GPU plan, or
     sfb200_group *group = nullptr;     // the etree partition over numGPU devices
+    sfb200_zplan *zplan = nullptr;     // complex matrix: the engine on its real embedding (one GPU)
     int ngpu = 1;
     bool pinned_lsx = false;
     bool factor_ok = false;            // the last SparseFrame_factorize of this matrix succeeded
@@ -117,6 +123,10 @@ void store_order(const std::string &path, const sfb200_symbolic *s) {
 
 // device side of one matrix: a plan on GPU 0, or the etree partition over the first ngpu devices
 int create_device_side(Cached &c, int ngpu) {
+    if (sfb200_symbolic_int(c.sym, "complex") == 1) {       // complex: one GPU
+        c.ngpu = 1;
+        return sfb200_zplan_create(c.sym, 0, &c.zplan);
+    }
     c.ngpu = ngpu > 1 ? ngpu : 1;
     int world = c.ngpu;
     // test hook: SF_PARTITION_RANKS=N runs an N-way partition on the GPUs at hand (ranks round-robin over them), so that the
@@ -133,6 +143,7 @@ void drop_cached(const matrix_info_struct *m) {
     auto it = g_cache.find(m);
     if (it == g_cache.end()) return;
     if (it->second.plan) sfb200_plan_free(it->second.plan);
+    if (it->second.zplan) sfb200_zplan_free(it->second.zplan);
     if (it->second.group) sfb200_group_free(it->second.group);
     if (it->second.sym) sfb200_symbolic_free(it->second.sym);
     g_cache.erase(it);
@@ -217,6 +228,7 @@ int SparseFrame_free_matrix(struct common_info_struct *common_info, struct matri
 }
 
 int SparseFrame_initialize_matrix(struct matrix_info_struct *m) {
+    drop_cached(m);                 /* a re-initialized matrix_info has no plan: the slot is about to hold another matrix */
     const int serial = m->serial;
     const char *path = m->path;
     memset(m, 0, sizeof(*m));
@@ -248,21 +260,21 @@ static int read_triplets(struct matrix_info_struct *m) {
     m->isComplex = T.complex_field;
     printf("matrix %s is %s %s, ncol = %ld nrow = %ld nzmax = %ld\n\n", basename((char *)m->path),
            m->isComplex ? "complex" : "real", m->isSymmetric ? "symmetric" : "unsymmetric", T.ncol, T.nrow, T.nz_declared);
-    if (m->isComplex) { printf("Error: complex matrices are not supported by the B200 engine\n"); return 1; }
     if (rc == sfio::ERR_ENTRY) { printf("Error: invalid matrix entry\n"); return 1; }
     if (rc == sfio::ERR_IMAG) { printf("Error: imaginary part not present\n"); return 1; }
     if (rc == sfio::ERR_NZMAX) { printf("Error: nzmax exceeded\n"); return 1; }
     if (rc != sfio::OK) return 1;
     const size_t cnt = T.ti.size(), alloc = cnt > 0 ? cnt : 1;
+    const size_t vbytes = m->isComplex ? sizeof(Complex) : sizeof(Float);        /* CH.c:474-477 */
     for (size_t k = 0; k < cnt; ++k)
         if (T.ti[k] < 0 || T.ti[k] >= T.nrow || T.tj[k] < 0 || T.tj[k] >= T.ncol) { printf("Error: invalid matrix entry\n"); return 1; }
     m->Tj = (Long *)malloc(alloc * sizeof(Long));
     m->Ti = (Long *)malloc(alloc * sizeof(Long));
-    m->Tx = (Float *)malloc(alloc * sizeof(Float));
+    m->Tx = (Float *)malloc(alloc * vbytes);
     if (cnt) {
         memcpy(m->Ti, T.ti.data(), cnt * sizeof(Long));
         memcpy(m->Tj, T.tj.data(), cnt * sizeof(Long));
-        memcpy(m->Tx, T.tx.data(), cnt * sizeof(Float));
+        memcpy(m->Tx, T.tx.data(), cnt * vbytes);
     }
     m->ncol = T.ncol;
     m->nrow = T.nrow;
@@ -276,20 +288,28 @@ int SparseFrame_write_binary_matrix(const char *path, int isSymmetric, Long nrow
                                     const Long *Tj, const Float *Tx) {
     return sfio::write_binary(path, isSymmetric != 0, nrow, ncol, nz, (const int64_t *)Ti, (const int64_t *)Tj, Tx);
 }
+/* the same container for a complex matrix: Tz = nz (re, im) pairs */
+int SparseFrame_write_binary_matrix_complex(const char *path, int isSymmetric, Long nrow, Long ncol, Long nz, const Long *Ti,
+                                            const Long *Tj, const Complex *Tz) {
+    return sfio::write_binary(path, isSymmetric != 0, nrow, ncol, nz, (const int64_t *)Ti, (const int64_t *)Tj,
+                              (const double *)Tz, true);
+}
 
 /* stable counting sort by column (CH.c:526-587): file order is kept inside each column, nothing is summed */
 int SparseFrame_compress(struct matrix_info_struct *m) {
     const Long ncol = m->ncol, nz = m->nzmax;
     m->Cp = (Long *)calloc((size_t)ncol + 1, sizeof(Long));
     m->Ci = (Long *)malloc((size_t)(nz > 0 ? nz : 1) * sizeof(Long));
-    m->Cx = (Float *)malloc((size_t)(nz > 0 ? nz : 1) * sizeof(Float));
+    const bool cplx = m->isComplex != 0;
+    m->Cx = (Float *)malloc((size_t)(nz > 0 ? nz : 1) * (cplx ? sizeof(Complex) : sizeof(Float)));
     for (Long k = 0; k < nz; ++k) ++m->Cp[m->Tj[k] + 1];
     for (Long j = 0; j < ncol; ++j) m->Cp[j + 1] += m->Cp[j];
     std::vector<Long> cursor(m->Cp, m->Cp + ncol);
     for (Long k = 0; k < nz; ++k) {
         const Long p = cursor[m->Tj[k]]++;
         m->Ci[p] = m->Ti[k];
-        m->Cx[p] = m->Tx[k];
+        if (!cplx) m->Cx[p] = m->Tx[k];
+        else ((Complex *)m->Cx)[p] = ((const Complex *)m->Tx)[k];
     }
     free(m->Tj); free(m->Ti); free(m->Tx);
     m->Tj = m->Ti = nullptr;
@@ -320,12 +340,17 @@ int SparseFrame_analyze(struct common_info_struct *common_info, struct matrix_in
     int rc = SFB200_ERR_ORDERING;
     const std::string cache = order_cache_path(m);
     std::vector<int64_t> order;
-    if (!cache.empty() && load_order(cache, m->nrow, order))
-        rc = sfb200_analyze_ordered(SF_KIND, m->isSymmetric, m->nrow, (const int64_t *)m->Cp, (const int64_t *)m->Ci, m->Cx,
-                                    (uint64_t)common_info->devSlotSize, order.data(), &s);
+    const bool cplx = m->isComplex != 0;
+    const Long vw = cplx ? 2 : 1;          /* Floats per value */
+    auto analyze_with = [&](const int64_t *ord) {
+        return cplx ? sfb200_analyze_complex(SF_KIND, m->isSymmetric, m->nrow, (const int64_t *)m->Cp, (const int64_t *)m->Ci,
+                                             m->Cx, (uint64_t)common_info->devSlotSize, ord, &s)
+                    : sfb200_analyze_ordered(SF_KIND, m->isSymmetric, m->nrow, (const int64_t *)m->Cp, (const int64_t *)m->Ci,
+                                             m->Cx, (uint64_t)common_info->devSlotSize, ord, &s);
+    };
+    if (!cache.empty() && load_order(cache, m->nrow, order)) rc = analyze_with(order.data());
     if (rc == SFB200_ERR_ORDERING) {       /* no cache, or a stale / damaged file: order with METIS */
-        rc = sfb200_analyze(SF_KIND, m->isSymmetric, m->nrow, (const int64_t *)m->Cp, (const int64_t *)m->Ci, m->Cx,
-                            (uint64_t)common_info->devSlotSize, &s);
+        rc = analyze_with(nullptr);
         if (rc == SFB200_OK && !cache.empty()) store_order(cache, s);
     }
     if (rc) { printf("SparseFrame_analyze: %s\n", sfb200_last_error()); return rc; }
@@ -333,18 +358,18 @@ int SparseFrame_analyze(struct common_info_struct *common_info, struct matrix_in
     m->Perm = dup_array<Long>(s, "Perm");
     m->Lp = dup_array<Long>(s, "Lp");
     m->Li = dup_array<Long>(s, "Li", m->nzmax);
-    m->Lx = dup_array<Float>(s, "Lx", m->nzmax);
+    m->Lx = dup_array<Float>(s, "Lx", vw * m->nzmax);
     m->LTp = dup_array<Long>(s, "LTp");
     m->LTi = dup_array<Long>(s, "LTi", m->nzmax);
-    m->LTx = dup_array<Float>(s, "LTx", m->nzmax);
+    m->LTx = dup_array<Float>(s, "LTx", vw * m->nzmax);
 #ifdef SPARSEFRAME_LU
     if (!m->isSymmetric) {
         m->Up = dup_array<Long>(s, "Up");
         m->Ui = dup_array<Long>(s, "Ui", m->nzmax);
-        m->Ux = dup_array<Float>(s, "Ux", m->nzmax);
+        m->Ux = dup_array<Float>(s, "Ux", vw * m->nzmax);
         m->UTp = dup_array<Long>(s, "UTp");
         m->UTi = dup_array<Long>(s, "UTi", m->nzmax);
-        m->UTx = dup_array<Float>(s, "UTx", m->nzmax);
+        m->UTx = dup_array<Float>(s, "UTx", vw * m->nzmax);
         m->CPCTp = dup_array<Long>(s, "CPCTp");
         m->CPCTi = dup_array<Long>(s, "CPCTi");
         m->nzCPCT = m->CPCTp[n];
@@ -374,9 +399,10 @@ int SparseFrame_analyze(struct common_info_struct *common_info, struct matrix_in
     /* the factor buffer: page-locked so that the copy-out of factorize runs at PCIe speed */
     Cached c;
     c.sym = s;
-    m->Lsx = (Float *)sfb200_host_alloc((size_t)(m->xsize > 0 ? m->xsize : 1) * sizeof(Float));
+    const size_t lsx_bytes = (size_t)(m->xsize > 0 ? m->xsize : 1) * (cplx ? sizeof(Complex) : sizeof(Float));   /* CH.c:1648-1651 */
+    m->Lsx = (Float *)sfb200_host_alloc(lsx_bytes);
     c.pinned_lsx = m->Lsx != nullptr;
-    if (!m->Lsx) m->Lsx = (Float *)malloc((size_t)(m->xsize > 0 ? m->xsize : 1) * sizeof(Float));
+    if (!m->Lsx) m->Lsx = (Float *)malloc(lsx_bytes);
     printf("nrow = %ld nfsuper = %ld nsuper = %ld nstage = %ld\n", n, (long)sfb200_symbolic_int(s, "nfsuper"), m->nsuper,
            m->nstage);
     /* the numeric plan (levels, batched task lists, relative-index tables) is symbolic work too: build + upload now */
@@ -384,6 +410,7 @@ int SparseFrame_analyze(struct common_info_struct *common_info, struct matrix_in
         printf("SparseFrame_analyze: no device plan (%s)\n", sfb200_last_error());
         c.plan = nullptr;
         c.group = nullptr;
+        c.zplan = nullptr;
     }
     {
         std::lock_guard<std::mutex> lk(g_mutex);
@@ -403,15 +430,21 @@ int SparseFrame_factorize(struct common_info_struct *common_info, struct gpu_inf
         if (it != g_cache.end()) c = it->second;
     }
     int rc = SFB200_OK;
-    if (!c.plan && !c.group) {
+    if (c.sym && (sfb200_symbolic_int(c.sym, "n") != m->nrow || sfb200_symbolic_int(c.sym, "nsuper") != m->nsuper ||
+                  sfb200_symbolic_int(c.sym, "xsize") != m->xsize || (sfb200_symbolic_int(c.sym, "complex") == 1) != (m->isComplex != 0))) {
+        /* the caller re-used this matrix_info for another structure without analyze / cleanup: the cached plan is stale */
+        drop_cached(m);
+        c = Cached();
+    }
+    if (!c.plan && !c.group && !c.zplan) {
         /* structure produced by somebody else's analysis (e.g. the reference's): wrap what factorize reads */
         const int64_t *up = nullptr, *ui = nullptr;
 #ifdef SPARSEFRAME_LU
         if (!m->isSymmetric) { up = (const int64_t *)m->Up; ui = (const int64_t *)m->Ui; }
 #endif
-        rc = sfb200_symbolic_wrap(SF_KIND, m->nrow, m->nsuper, (const int64_t *)m->Super, (const int64_t *)m->Lsip,
-                                  (const int64_t *)m->Lsxp, (const int64_t *)m->Lsi, (const int64_t *)m->Lp,
-                                  (const int64_t *)m->Li, up, ui, &c.sym);
+        rc = (m->isComplex ? sfb200_symbolic_wrap_complex : sfb200_symbolic_wrap)(
+            SF_KIND, m->nrow, m->nsuper, (const int64_t *)m->Super, (const int64_t *)m->Lsip, (const int64_t *)m->Lsxp,
+            (const int64_t *)m->Lsi, (const int64_t *)m->Lp, (const int64_t *)m->Li, up, ui, &c.sym);
         if (rc == SFB200_OK) rc = create_device_side(c, common_info ? common_info->numGPU : 1);
         if (rc != SFB200_OK) { printf("SparseFrame_factorize: %s\n", sfb200_last_error()); return rc; }
         std::lock_guard<std::mutex> lk(g_mutex);
@@ -423,7 +456,8 @@ int SparseFrame_factorize(struct common_info_struct *common_info, struct gpu_inf
 #ifdef SPARSEFRAME_LU
     if (!m->isSymmetric) ux = m->Ux;
 #endif
-    rc = c.group ? sfb200_group_factorize(c.group, m->Lx, ux, m->Lsx) : sfb200_factorize(c.plan, m->Lx, ux, m->Lsx);
+    rc = c.zplan ? sfb200_zfactorize(c.zplan, m->Lx, ux, m->Lsx)
+         : c.group ? sfb200_group_factorize(c.group, m->Lx, ux, m->Lsx) : sfb200_factorize(c.plan, m->Lx, ux, m->Lsx);
     if (gpu_info_list) for (int d = c.ngpu - 1; d >= 0; --d) omp_unset_lock(&gpu_info_list[d].gpuLock);
     if (rc != SFB200_OK) printf("SparseFrame_factorize: %s\n", sfb200_last_error());
     {
@@ -435,6 +469,54 @@ int SparseFrame_factorize(struct common_info_struct *common_info, struct gpu_inf
     return rc;
 }
 
+/* The substitution loops of SparseFrame_solve_supernodal for a complex factor -- the statements the reference leaves as
+ * `// TODO` (CH.c:3088-3131, LU.c:3644-3690), in std::complex arithmetic on the interleaved arrays. */
+static void solve_supernodal_complex_host(struct matrix_info_struct *m) {
+    typedef std::complex<double> cd;
+    const Long ns = m->nsuper;
+    const Long *Super = m->Super, *Lsip = m->Lsip, *Lsxp = m->Lsxp, *Lsi = m->Lsi;
+    const cd *Lsx = (const cd *)m->Lsx;
+    cd *x = (cd *)m->Xx;
+    for (Long s = 0; s < ns; ++s) {
+        const Long nc = Super[s + 1] - Super[s], nr = Lsip[s + 1] - Lsip[s];
+#ifdef SPARSEFRAME_LU
+        const Long ld = 2 * nr - nc;
+#else
+        const Long ld = nr;
+#endif
+        const Long *rows = Lsi + Lsip[s];
+        const cd *P = Lsx + Lsxp[s];
+        for (Long j = 0; j < nc; ++j) {
+#ifndef SPARSEFRAME_LU
+            x[rows[j]] /= P[j * ld + j];
+#endif
+            const cd xj = x[rows[j]];
+            for (Long i = j + 1; i < nr; ++i) x[rows[i]] -= P[j * ld + i] * xj;
+        }
+    }
+    for (Long s = ns - 1; s >= 0; --s) {
+        const Long nc = Super[s + 1] - Super[s], nr = Lsip[s + 1] - Lsip[s];
+        const Long *rows = Lsi + Lsip[s];
+        const cd *P = Lsx + Lsxp[s];
+#ifdef SPARSEFRAME_LU
+        const Long ld = 2 * nr - nc;
+        for (Long j = nc - 1; j >= 0; --j) {
+            cd acc = x[rows[j]];
+            for (Long i = j + 1; i < nc; ++i) acc -= P[i * ld + j] * x[rows[i]];
+            for (Long i = nc; i < nr; ++i) acc -= P[j * ld + (nr - nc) + i] * x[rows[i]];
+            x[rows[j]] = acc / P[j * ld + j];
+        }
+#else
+        const Long ld = nr;
+        for (Long j = nc - 1; j >= 0; --j) {              /* L^H x = y */
+            cd acc = x[rows[j]];
+            for (Long i = j + 1; i < nr; ++i) acc -= std::conj(P[j * ld + i]) * x[rows[i]];
+            x[rows[j]] = acc / P[j * ld + j];
+        }
+#endif
+    }
+}
+
 /* forward / backward substitution over the supernodal factor (CH.c:3074-3134, LU.c:3630-3694) */
 int SparseFrame_solve_supernodal(struct matrix_info_struct *m) {
     const double t0 = SparseFrame_time();
@@ -444,6 +526,15 @@ int SparseFrame_solve_supernodal(struct matrix_info_struct *m) {
             std::lock_guard<std::mutex> lk(g_mutex);
             auto it = g_cache.find(m);
             if (it != g_cache.end()) c = it->second;
+        }
+        if (m->isComplex) {
+            memcpy(m->Xx, m->Bx, (size_t)m->nrow * sizeof(Complex));
+            if (!(c.zplan && c.factor_ok && !getenv("SF_HOST_SOLVE") && sfb200_zsolve(c.zplan, m->Xx, 1) == SFB200_OK)) {
+                memcpy(m->Xx, m->Bx, (size_t)m->nrow * sizeof(Complex));
+                solve_supernodal_complex_host(m);
+            }
+            m->solveTime = SparseFrame_time() - t0;
+            return 0;
         }
         if (c.plan && c.factor_ok && !getenv("SF_HOST_SOLVE")) {
             memcpy(m->Xx, m->Bx, (size_t)m->nrow * sizeof(Float));
@@ -501,7 +592,66 @@ int SparseFrame_solve_supernodal(struct matrix_info_struct *m) {
 }
 
 /* b_i = 1 + i/n, solve, residual of the permuted system, printed like the reference (CH.c:3141-3266) */
+/* complex: b_i = (1 + i/n) + i (n/2 - i)/(3n) (CH.c:3188-3192); the norms the reference leaves as `// TODO` (CH.c:3229-3256)
+ * are taken with complex moduli: ||A||_1, max |b_i|, max |x_i|, max |r_i| */
+static int validate_complex(struct matrix_info_struct *m) {
+    typedef std::complex<double> cd;
+    const Long n = m->nrow;
+    const size_t bytes = (size_t)(n > 0 ? n : 1) * sizeof(Complex);
+    m->Bx = (Float *)malloc(bytes);
+    m->Xx = (Float *)malloc(bytes);
+    m->Rx = (Float *)malloc(bytes);
+    cd *b = (cd *)m->Bx, *r = (cd *)m->Rx;
+    for (Long i = 0; i < n; ++i) b[i] = cd(1 + i / (Float)n, ((Float)n / 2 - i) / (3 * n));
+    SparseFrame_solve_supernodal(m);
+    const cd *x = (const cd *)m->Xx;
+    const cd *Lx = (const cd *)m->Lx;
+    std::vector<Float> colsum((size_t)(n > 0 ? n : 1), 0.0);
+    for (Long i = 0; i < n; ++i) r[i] = -b[i];
+    bool split = false;
+#ifdef SPARSEFRAME_LU
+    split = !m->isSymmetric;
+    const bool hermitian = false;                 /* LU of a "symmetric" complex matrix: A = A^T */
+#else
+    const bool hermitian = true;                  /* zherk / zpotrf read the lower triangle of a Hermitian matrix */
+#endif
+    for (Long j = 0; j < n; ++j)
+        for (Long p = m->Lp[j]; p < m->Lp[j + 1]; ++p) {
+            const Long i = m->Li[p];
+            const cd v = (hermitian && i == j) ? cd(Lx[p].real(), 0.0) : Lx[p];
+            if (!split) {
+                r[i] += v * x[j];
+                colsum[j] += std::abs(v);
+                if (i != j) { r[j] += (hermitian ? std::conj(v) : v) * x[i]; colsum[i] += std::abs(v); }
+            } else if (i > j) {
+                r[i] += v * x[j];
+                colsum[j] += std::abs(v);
+            }
+        }
+#ifdef SPARSEFRAME_LU
+    if (split) {
+        const cd *Ux = (const cd *)m->Ux;
+        for (Long i = 0; i < n; ++i)
+            for (Long p = m->Up[i]; p < m->Up[i + 1]; ++p) {
+                r[i] += Ux[p] * x[m->Ui[p]];
+                colsum[m->Ui[p]] += std::abs(Ux[p]);
+            }
+    }
+#endif
+    Float anorm = 0, bnorm = 0, xnorm = 0, rnorm = 0;
+    for (Long i = 0; i < n; ++i) {
+        if (colsum[i] > anorm) anorm = colsum[i];
+        if (std::abs(b[i]) > bnorm) bnorm = std::abs(b[i]);
+        if (std::abs(x[i]) > xnorm) xnorm = std::abs(x[i]);
+        if (std::abs(r[i]) > rnorm) rnorm = std::abs(r[i]);
+    }
+    printf("anorm = %le bnorm = %le xnorm = %le rnorm = %le\n", anorm, bnorm, xnorm, rnorm);
+    m->residual = rnorm / (anorm * xnorm + bnorm);
+    return 0;
+}
+
 int SparseFrame_validate(struct matrix_info_struct *m) {
+    if (m->isComplex) return validate_complex(m);
     const Long n = m->nrow;
     m->Bx = (Float *)malloc((size_t)(n > 0 ? n : 1) * sizeof(Float));
     m->Xx = (Float *)malloc((size_t)(n > 0 ? n : 1) * sizeof(Float));

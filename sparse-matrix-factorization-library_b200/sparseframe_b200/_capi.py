@@ -22,6 +22,10 @@ SYMBOLS = [
     "sfb200_group_last_ms", "sfb200_group_free", "sfb200_plan_adopt_factor", "sfb200_plan_panel_offsets", "sfb200_factorize_owned", "sfb200_download_owned",
     "sfb200_plan_owned_runs", "sfb200_plan_profile_launch", "sfb200_solve", "sfb200_solve_device", "sfb200_residual",
     "sfb200_analyze_ordered", "sfb200_symbolic_double",
+    # complex matrices (real embedding, csrc/zengine.cu)
+    "sfb200_analyze_complex", "sfb200_symbolic_wrap_complex", "sfb200_zplan_create", "sfb200_zplan_free", "sfb200_zplan_real",
+    "sfb200_zplan_int", "sfb200_zplan_set_row_phase", "sfb200_zfactorize", "sfb200_zfactorize_device", "sfb200_zplan_sync",
+    "sfb200_zdownload_factor", "sfb200_zsolve", "sfb200_zresidual", "sfb200_zlast_ms",
 ]
 
 
@@ -108,6 +112,24 @@ def lib():
     L.sfb200_plan_profile.argtypes = [vp]
     L.sfb200_plan_profile_get.restype = dbl
     L.sfb200_plan_profile_get.argtypes = [vp, ci, ci]
+    L.sfb200_analyze_complex.argtypes = [ci, ci, i64, vp, vp, vp, u64, vp, C.POINTER(vp)]
+    L.sfb200_symbolic_wrap_complex.argtypes = L.sfb200_symbolic_wrap.argtypes
+    L.sfb200_zplan_create.argtypes = [vp, ci, C.POINTER(vp)]
+    L.sfb200_zplan_free.argtypes = [vp]
+    L.sfb200_zplan_free.restype = None
+    L.sfb200_zplan_real.restype = vp
+    L.sfb200_zplan_real.argtypes = [vp]
+    L.sfb200_zplan_int.restype = i64
+    L.sfb200_zplan_int.argtypes = [vp, C.c_char_p]
+    L.sfb200_zplan_set_row_phase.argtypes = [vp, ci]
+    L.sfb200_zfactorize.argtypes = [vp, vp, vp, vp]
+    L.sfb200_zfactorize_device.argtypes = [vp, vp, vp]
+    L.sfb200_zplan_sync.argtypes = [vp]
+    L.sfb200_zdownload_factor.argtypes = [vp, vp]
+    L.sfb200_zsolve.argtypes = [vp, vp, ci]
+    L.sfb200_zresidual.argtypes = [vp, vp, vp, vp]
+    L.sfb200_zlast_ms.restype = dbl
+    L.sfb200_zlast_ms.argtypes = [vp]
     _lib = L
     return L
 

@@ -35,10 +35,10 @@ class Matrix:
 
 def compress(n, rows, cols, vals, symmetric=True) -> Matrix:
     """Triplets -> CSC by a stable counting sort on the column (CH.c:560-576): file order is kept inside each
-    column, nothing is summed or sorted."""
+    column, nothing is summed or sorted.  Complex values make a complex matrix (matrix_info->isComplex)."""
     rows = np.asarray(rows, dtype=np.int64)
     cols = np.asarray(cols, dtype=np.int64)
-    vals = np.asarray(vals, dtype=np.float64)
+    vals = np.asarray(vals, dtype=np.complex128 if np.iscomplexobj(vals) else np.float64)
     order = np.argsort(cols, kind="stable")
     cp = np.zeros(n + 1, dtype=np.int64)
     np.add.at(cp, cols + 1, 1)
@@ -58,6 +58,7 @@ class Symbolic:
         self._h = handle
         self.kind = kind
         self.devslot = devslot
+        self.complex = bool(_capi.lib().sfb200_symbolic_int(handle, b"complex") == 1)
 
     def int(self, name) -> int:
         return int(_capi.lib().sfb200_symbolic_int(self._h, name.encode()))
@@ -69,7 +70,8 @@ class Symbolic:
         if not p or cnt.value == 0:
             return np.zeros(0, dtype=dt)
         buf = (C.c_char * (cnt.value * 8)).from_address(p)
-        return np.frombuffer(buf, dtype=dt, count=cnt.value).copy()
+        a = np.frombuffer(buf, dtype=dt, count=cnt.value).copy()
+        return a.view(np.complex128) if (self.complex and name in self._F64) else a
 
     def double(self, name) -> float:
         return float(_capi.lib().sfb200_symbolic_double(self._h, name.encode()))
@@ -99,24 +101,25 @@ def analyze(A: Matrix, kind="cholesky", devslot=DEFAULT_DEVSLOT, order=None) -> 
         order = np.ascontiguousarray(order, dtype=np.int64)
         if order.shape != (A.n,):
             raise ValueError("order must have n entries")
-    rc = L.sfb200_analyze_ordered(_kind(kind), int(A.symmetric), A.n, A.Cp.ctypes.data, A.Ci.ctypes.data,
-                                  A.Cx.ctypes.data, int(devslot), order.ctypes.data if order is not None else None,
-                                  C.byref(h))
+    fn = L.sfb200_analyze_complex if np.iscomplexobj(A.Cx) else L.sfb200_analyze_ordered
+    rc = fn(_kind(kind), int(A.symmetric), A.n, A.Cp.ctypes.data, A.Ci.ctypes.data,
+            A.Cx.ctypes.data, int(devslot), order.ctypes.data if order is not None else None, C.byref(h))
     if rc != 0:
         raise RuntimeError("sfb200_analyze failed (%d): %s" % (rc, _capi.last_error()))
     return Symbolic(h, _kind(kind), int(devslot))
 
 
-def wrap_structure(kind, n, Super, Lsip, Lsxp, Lsi, Lp, Li, Up=None, Ui=None) -> Symbolic:
+def wrap_structure(kind, n, Super, Lsip, Lsxp, Lsi, Lp, Li, Up=None, Ui=None, is_complex=False) -> Symbolic:
     """Symbolic object around a structure computed elsewhere (e.g. by the reference's own analysis)."""
     L = _capi.lib()
     arrs = [np.ascontiguousarray(a, dtype=np.int64) for a in (Super, Lsip, Lsxp, Lsi, Lp, Li)]
     up = np.ascontiguousarray(Up, dtype=np.int64) if Up is not None else None
     ui = np.ascontiguousarray(Ui, dtype=np.int64) if Ui is not None else None
     h = C.c_void_p()
-    rc = L.sfb200_symbolic_wrap(_kind(kind), int(n), len(arrs[0]) - 1, *[a.ctypes.data for a in arrs],
-                                up.ctypes.data if up is not None else None,
-                                ui.ctypes.data if ui is not None else None, C.byref(h))
+    wrap = L.sfb200_symbolic_wrap_complex if is_complex else L.sfb200_symbolic_wrap
+    rc = wrap(_kind(kind), int(n), len(arrs[0]) - 1, *[a.ctypes.data for a in arrs],
+                up.ctypes.data if up is not None else None,
+                ui.ctypes.data if ui is not None else None, C.byref(h))
     if rc != 0:
         raise RuntimeError("sfb200_symbolic_wrap failed (%d): %s" % (rc, _capi.last_error()))
     return Symbolic(h, _kind(kind), 0)
@@ -296,6 +299,79 @@ class Plan:
         if self._h:
             if self._owned:
                 _capi.lib().sfb200_plan_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class ZPlan:
+    """Numeric plan of a COMPLEX matrix (sfb200_zplan_*): the FP64 engine on the real embedding of the matrix, complex
+    panels read back in the reference's layout (csrc/complex_embed.hpp).  Values are complex128 arrays."""
+
+    def __init__(self, sym: Symbolic, device=0, row_phase=None):
+        L = _capi.lib()
+        h = C.c_void_p()
+        rc = L.sfb200_zplan_create(sym._h, int(device), C.byref(h))
+        if rc != 0:
+            raise RuntimeError("sfb200_zplan_create failed (%d): %s" % (rc, _capi.last_error()))
+        self._h = h
+        self.sym = sym
+        if row_phase is not None:
+            L.sfb200_zplan_set_row_phase(h, int(bool(row_phase)))
+        # the plan of the embedded real structure, for inspection (freed with the zplan)
+        self.real = Plan(sym, device, _handle=L.sfb200_zplan_real(h))
+
+    def int(self, name) -> int:
+        return int(_capi.lib().sfb200_zplan_int(self._h, name.encode()))
+
+    def factorize(self, Lz, Uz=None, download=True):
+        L = _capi.lib()
+        Lz = np.ascontiguousarray(Lz, dtype=np.complex128)
+        uz_p = None
+        if Uz is not None:
+            Uz = np.ascontiguousarray(Uz, dtype=np.complex128)
+            uz_p = Uz.ctypes.data
+        out = np.empty(self.int("xsize"), dtype=np.complex128) if download else None
+        rc = L.sfb200_zfactorize(self._h, Lz.ctypes.data, uz_p, out.ctypes.data if download else None)
+        if rc != 0:
+            raise RuntimeError("sfb200_zfactorize failed (%d): %s" % (rc, _capi.last_error()))
+        return out
+
+    def download(self):
+        out = np.empty(self.int("xsize"), dtype=np.complex128)
+        rc = _capi.lib().sfb200_zdownload_factor(self._h, out.ctypes.data)
+        if rc != 0:
+            raise RuntimeError("sfb200_zdownload_factor failed (%d): %s" % (rc, _capi.last_error()))
+        return out
+
+    def solve(self, b):
+        x = np.array(b, dtype=np.complex128, order="F", copy=True)
+        nrhs = 1 if x.ndim == 1 else x.shape[1]
+        rc = _capi.lib().sfb200_zsolve(self._h, x.ctypes.data, nrhs)
+        if rc != 0:
+            raise RuntimeError("sfb200_zsolve failed (%d): %s" % (rc, _capi.last_error()))
+        return x
+
+    def residual(self, x, b):
+        x = np.ascontiguousarray(x, dtype=np.complex128)
+        b = np.ascontiguousarray(b, dtype=np.complex128)
+        out = np.zeros(5)
+        rc = _capi.lib().sfb200_zresidual(self._h, x.ctypes.data, b.ctypes.data, out.ctypes.data)
+        if rc != 0:
+            raise RuntimeError("sfb200_zresidual failed (%d): %s" % (rc, _capi.last_error()))
+        return dict(zip(("anorm", "bnorm", "xnorm", "rnorm", "residual"), out.tolist()))
+
+    def last_ms(self) -> float:
+        return float(_capi.lib().sfb200_zlast_ms(self._h))
+
+    def close(self):
+        if self._h:
+            self.real._h = None
+            _capi.lib().sfb200_zplan_free(self._h)
             self._h = None
 
     def __del__(self):

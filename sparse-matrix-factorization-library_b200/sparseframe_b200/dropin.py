@@ -96,6 +96,7 @@ class Library:
         m.factorizeType = TYPE_LU if self.lu else TYPE_CHOLESKY
         m.permMethod = PERM_METIS
         m.isSymmetric = int(S.int("symmetric"))
+        m.isComplex = int(S.int("complex") == 1)          # value arrays then hold Complex (interleaved pairs)
         m.nrow = m.ncol = S.int("n")
         m.nsuper, m.isize, m.xsize, m.csize = S.int("nsuper"), S.int("isize"), S.int("xsize"), S.int("csize")
         m.nsleaf, m.nstage = S.int("nsleaf"), S.int("nstage")

@@ -123,15 +123,36 @@ def generate(kind: str, g: int):
     return GENERATORS[kind](g)
 
 
+def generate_complex(kind: str, g: int, hermitian: bool, amplitude: float = 0.45, diag_phase=None):
+    """A complex matrix on the pattern of generate(kind, g): every entry (i, j) of the real matrix is rotated by the
+    closed-form phase theta = amplitude * sin(1.3 i + 0.7 j + 0.5) (no RNG).  hermitian=True keeps the diagonal real, so that
+    the lower triangle of a "symmetric" pattern is the lower triangle of a Hermitian positive definite matrix (diagonal
+    dominance is a statement about moduli) -- the input of the reference's zpotrf path; hermitian=False also rotates the
+    diagonal, by theta or, if given, by exactly diag_phase (pi/2: a purely IMAGINARY dominant diagonal) -- for the LU path,
+    where a "symmetric" pattern then means A = A^T."""
+    n, rows, cols, vals, symmetric = GENERATORS[kind](g)
+    theta = amplitude * np.sin(1.3 * rows + 0.7 * cols + 0.5)
+    diag = rows == cols
+    if hermitian:
+        theta[diag] = 0.0
+    elif diag_phase is not None:
+        theta[diag] = diag_phase
+    return n, rows, cols, vals * np.exp(1j * theta), symmetric
+
+
 def write_matrix_market(path, n, rows, cols, vals, symmetric):
-    """MatrixMarket coordinate text, the only input format of the reference's driver."""
+    """MatrixMarket coordinate text, the only input format of the reference's driver.  Complex values are written with the
+    field "complex" and two numbers per entry (the reader takes every field other than "real" as complex, CH.c:440-445)."""
+    cplx = np.iscomplexobj(vals)
     with open(path, "w") as f:
-        f.write("%%%%MatrixMarket matrix coordinate real %s\n" % ("symmetric" if symmetric else "general"))
+        f.write("%%%%MatrixMarket matrix coordinate %s %s\n" % ("complex" if cplx else "real",
+                                                               "symmetric" if symmetric else "general"))
         f.write("%d %d %d\n" % (n, n, len(rows)))
         chunk = 5_000_000
         for i in range(0, len(rows), chunk):
-            np.savetxt(f, np.column_stack([rows[i:i + chunk] + 1, cols[i:i + chunk] + 1, vals[i:i + chunk]]),
-                       fmt="%d %d %.17g")
+            v = vals[i:i + chunk]
+            cols_ = [rows[i:i + chunk] + 1, cols[i:i + chunk] + 1] + ([v.real, v.imag] if cplx else [v])
+            np.savetxt(f, np.column_stack(cols_), fmt="%d %d %.17g" + (" %.17g" if cplx else ""))
 
 
 def write_binary(path, n, rows, cols, vals, symmetric):
@@ -139,12 +160,14 @@ def write_binary(path, n, rows, cols, vals, symmetric):
     ncol / nz, then Ti, Tj (0-based int64) and Tx (float64) in file order.  SparseFrame_read_matrix recognises it by
     the magic and builds the same Cp/Ci/Cx as from the MatrixMarket text of the same triplets (explicit zeros are
     dropped here, as the text reader drops them, CH.c:493)."""
-    rows, cols, vals = np.asarray(rows, np.int64), np.asarray(cols, np.int64), np.asarray(vals, np.float64)
+    cplx = np.iscomplexobj(vals)             # flag bit 1; the values are then (re, im) pairs
+    rows, cols = np.asarray(rows, np.int64), np.asarray(cols, np.int64)
+    vals = np.asarray(vals, np.complex128 if cplx else np.float64)
     keep = vals != 0.0
     rows, cols, vals = rows[keep], cols[keep], vals[keep]
     with open(path, "wb") as f:
         f.write(b"SFB200T1")
-        np.array([1 if symmetric else 0, n, n, len(rows)], np.int64).tofile(f)
+        np.array([(1 if symmetric else 0) | (2 if cplx else 0), n, n, len(rows)], np.int64).tofile(f)
         rows.tofile(f)
         cols.tofile(f)
         vals.tofile(f)

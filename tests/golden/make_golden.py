@@ -28,14 +28,32 @@ CASES = [
     ("cd3d_9_lu_slot", "cd3d", 9, "lu", 60_000),
 ]
 
+# Complex matrices (matrix_info->isComplex): fixtures under tests/golden/complex/ (matrices.generate_complex; Hermitian for the
+# zpotrf path, general phases for the LU path).  name, generator, grid, factorization, devSlotSize, diag_phase (-1: the
+# generator's own phases on the diagonal too)
+COMPLEX_CASES = [
+    ("z_lap3d_7_chol", "lap3d", 7, "cholesky", sfref.DEFAULT_DEVSLOT, -1.0),
+    ("z_lap2d_14_chol_slot", "lap2d", 14, "cholesky", 12_000, -1.0),  # slot caps counted in sizeof(Complex) (CH.c:1489-1496)
+    ("z_el3d_3_chol", "el3d", 3, "cholesky", sfref.DEFAULT_DEVSLOT, -1.0),
+    ("z_cd3d_7_lu", "cd3d", 7, "lu", sfref.DEFAULT_DEVSLOT, -1.0),
+    ("z_lap2d_12_lu", "lap2d", 12, "lu", sfref.DEFAULT_DEVSLOT, -1.0),   # complex symmetric (A = A^T): U aliases L
+    ("z_cd3d_6_lu_imagdiag", "cd3d", 6, "lu", 30_000, 1.5707963267948966),   # purely imaginary dominant diagonal
+]
+
 INT_ARRAYS = ["Perm", "Parent", "Post", "ColCount", "Lp", "Li", "LTp", "LTi", "Super", "SuperMap", "Sparent", "Lsip",
               "Lsxp", "Lsi", "ST_Map", "ST_Pointer", "ST_Index", "LeafQueue", "Aoffset", "Moffset"]
 
 
 def main():
     out_dir = os.path.dirname(os.path.abspath(__file__))
-    for name, gen, g, fk, slot in CASES:
-        n, r, c, x, sym = matrices.generate(gen, g)
+    os.makedirs(os.path.join(out_dir, "complex"), exist_ok=True)
+    cases = [c + (None,) for c in CASES] + [(os.path.join("complex", c[0]),) + c[1:] for c in COMPLEX_CASES]
+    for name, gen, g, fk, slot, diag_phase in cases:
+        if diag_phase is None:
+            n, r, c, x, sym = matrices.generate(gen, g)
+        else:
+            n, r, c, x, sym = matrices.generate_complex(gen, g, hermitian=(fk == "cholesky"),
+                                                        diag_phase=None if diag_phase < 0 else diag_phase)
         ref = sfref.Reference(n, r, c, x, sym, kind=fk, devslot=slot, blas_threads=1).analyze()
         leaf_queue = ref.array("LeafQueue")        # factorize appends to it (CH.c:2976): keep the analysis-time value
         ref.factorize()
@@ -51,10 +69,13 @@ def main():
                 d[k] = ref.array(k)
             d["Ux"] = ref.array("Ux")
         d["Lsx"] = ref.array("Lsx")
-        d["residual"] = np.array([ref.validate()])
+        # the reference's complex solve / validate are `// TODO` (CH.c:3088-3131): no residual to record
+        d["residual"] = np.array([ref.validate() if diag_phase is None else np.nan])
         d["scalars"] = np.array([n, ns, ref.long("isize"), ref.long("xsize"), ref.long("csize"), ref.long("nstage"),
                                  ref.long("nsleaf"), slot, g], dtype=np.int64)
         d["meta"] = np.array([gen, fk, "symmetric" if sym else "general"])
+        if diag_phase is not None:
+            d["diag_phase"] = np.array([diag_phase])
         np.savez_compressed(os.path.join(out_dir, name + ".npz"), **d)
         print(name, "n", n, "nsuper", ns, "xsize", ref.long("xsize"), "residual %.2e" % d["residual"][0])
         ref.close()

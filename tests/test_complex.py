@@ -1,0 +1,245 @@
+"""Complex matrices (matrix_info->isComplex), CPU tier.
+
+The reference factorizes them with zherk/zgemm/zpotrf/ztrsm (CH.c:2060-2070, 2134-2145) and zgemm/magma_zgetrf_nopiv/ztrsm
+(LU.c:2569-2581, 2652-2663); its complex solve / validate are `// TODO` (CH.c:3088-3131).  The engine runs them as the real
+embedding of csrc/complex_embed.hpp.  Checked here without a GPU:
+  * the analysis with the complex element size is bit-identical to the compiled reference's and to the golden fixtures;
+  * the embedded schedule on the CPU interpreter + the panel read-back reproduce the reference's complex factor;
+  * the embedded substitution is the complex solve; the row-phase rotation rescues matrices whose pivots have small real parts.
+"""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+import sforacle
+import sfref
+import sparseframe_b200 as sf
+from conftest import ROOT
+
+ZGOLDEN = sorted(glob.glob(os.path.join(ROOT, "tests", "golden", "complex", "*.npz")))
+INT_ARRAYS = ["Perm", "Parent", "Post", "ColCount", "Lp", "Li", "LTp", "LTi", "Super", "SuperMap", "Sparent", "Lsip", "Lsxp",
+              "Lsi", "ST_Map", "ST_Pointer", "ST_Index", "Aoffset", "Moffset"]
+
+
+def load(path):
+    d = dict(np.load(path))
+    gen, fk, symtxt = [str(v) for v in d["meta"]]
+    n, ns, isize, xsize, csize, nstage, nsleaf, slot, g = [int(v) for v in d["scalars"]]
+    d.update(gen=gen, kind=fk, symmetric=(symtxt == "symmetric"), n=n, nsuper=ns, isize=isize, xsize=xsize, csize=csize,
+             nstage=nstage, nsleaf=nsleaf, devslot=slot, grid=g, phase=float(d["diag_phase"][0]))
+    return d
+
+
+@pytest.fixture(params=ZGOLDEN, ids=[os.path.basename(p)[:-4] for p in ZGOLDEN])
+def zgolden(request):
+    return load(request.param)
+
+
+def matrix_of(gd):
+    n, r, c, z, sym = sf.matrices.generate_complex(gd["gen"], gd["grid"], hermitian=(gd["kind"] == "cholesky"),
+                                                   diag_phase=None if gd["phase"] < 0 else gd["phase"])
+    return sf.compress(n, r, c, z, sym), (n, r, c, z, sym)
+
+
+def defined_mask(gd):
+    return sf.lower_trapezoid_mask(gd["kind"], gd["Super"], gd["Lsip"], gd["Lsxp"], gd["xsize"])
+
+
+def test_there_are_complex_goldens():
+    assert len(ZGOLDEN) >= 6
+
+
+def test_complex_analysis_reproduces_golden(zgolden):
+    A, _ = matrix_of(zgolden)
+    S = sf.analyze(A, zgolden["kind"], devslot=zgolden["devslot"])
+    assert S.complex
+    for k in INT_ARRAYS:
+        got = S.array(k)
+        if k == "Sparent":
+            got = got[:zgolden["nsuper"]]
+        assert np.array_equal(got, zgolden[k]), k
+    for k in ("isize", "xsize", "csize", "nstage", "nsleaf", "nsuper"):
+        assert S.int(k) == zgolden[k], k
+    assert np.array_equal(S.array("LeafQueue")[:zgolden["nsleaf"]], zgolden["LeafQueue"][:zgolden["nsleaf"]])
+    assert np.array_equal(S.array("Lx"), zgolden["Lx"])           # complex values move whole, never conjugated (CH.c:1048-1060)
+    if "Ux" in zgolden:
+        assert np.array_equal(S.array("Ux"), zgolden["Ux"])
+        for k in ("Up", "Ui", "UTp", "UTi"):
+            assert np.array_equal(S.array(k), zgolden[k]), k
+
+
+def test_slot_caps_count_complex_bytes():
+    """The same pattern and slot size give a different structure for real and for complex values: the caps are in bytes of
+    the panel's element type (CH.c:1480-1496)."""
+    gd = load([p for p in ZGOLDEN if "slot" in p][0])
+    A, (n, r, c, z, sym) = matrix_of(gd)
+    Sz = sf.analyze(A, gd["kind"], devslot=gd["devslot"])
+    Sr = sf.analyze(sf.compress(n, r, c, np.abs(z), sym), gd["kind"], devslot=gd["devslot"])
+    assert Sz.int("nsuper") == gd["nsuper"]
+    assert Sr.int("nsuper") != Sz.int("nsuper") or Sr.int("nstage") != Sz.int("nstage")
+
+
+@pytest.mark.parametrize("row_phase", [False, True])
+@pytest.mark.parametrize("small", [(-1, -1), (0, 0)], ids=["default", "all_large"])
+def test_embedded_schedule_reproduces_golden(zgolden, row_phase, small):
+    if zgolden["phase"] >= 0.0 and not row_phase:
+        pytest.skip("purely imaginary diagonal: covered by test_row_phase_rescues_an_imaginary_diagonal")
+    A, _ = matrix_of(zgolden)
+    out, bad, stats, _ = sforacle.check_plan_complex(zgolden["kind"], A.n, A.Cp, A.Ci, A.Cx, A.symmetric, zgolden["devslot"],
+                                                     small_a=small[0], small_b=small[1], row_phase=row_phase)
+    assert bad == 0
+    assert stats[0] == zgolden["nsuper"] and stats[1] == zgolden["xsize"]
+    ref = zgolden["Lsx"]
+    mask = defined_mask(zgolden)
+    assert sf.entrywise_rel_diff(out[mask], ref[mask]) <= 1e-10
+    assert np.abs(out[mask] - ref[mask]).max() <= 1e-13 * np.abs(ref).max()
+    if zgolden["kind"] == "cholesky":
+        # the reference's panels: zeros above the diagonal (loadA's memset), a real diagonal (zpotrf)
+        assert not out[~mask].any() and not ref[~mask].any()
+        for s in range(zgolden["nsuper"]):
+            nc, nr = zgolden["Super"][s + 1] - zgolden["Super"][s], zgolden["Lsip"][s + 1] - zgolden["Lsip"][s]
+            dg = out[zgolden["Lsxp"][s]:zgolden["Lsxp"][s] + nc * nr].reshape(nc, nr)[np.arange(nc), np.arange(nc)]
+            assert not dg.imag.any() and (dg.real > 0).all()
+
+
+@pytest.mark.skipif(not sfref.available("cholesky"), reason="compiled reference not built")
+@pytest.mark.parametrize("gen,g,kind,devslot", [("lap3d", 9, "cholesky", sfref.DEFAULT_DEVSLOT), ("el3d", 4, "cholesky", 200_000),
+                                                ("cd3d", 9, "lu", sfref.DEFAULT_DEVSLOT), ("lap3d", 6, "lu", 50_000)])
+def test_embedded_schedule_reproduces_compiled_reference(gen, g, kind, devslot):
+    n, r, c, z, sym = sf.matrices.generate_complex(gen, g, hermitian=(kind == "cholesky"))
+    A = sf.compress(n, r, c, z, sym)
+    R = sfref.Reference(n, r, c, z, sym, kind, devslot=devslot, blas_threads=1).analyze().factorize()
+    ref, st = R.array("Lsx"), R.structure()
+    S = sf.analyze(A, kind, devslot=devslot)
+    for k in ("Perm", "Super", "Lsip", "Lsxp", "Lsi"):
+        assert np.array_equal(S.array(k)[:len(st[k])], st[k]), k
+    mask = sf.lower_trapezoid_mask(kind, st["Super"], st["Lsip"], st["Lsxp"], R.long("xsize"))
+    for row_phase in (False, True):
+        out, bad, _, _ = sforacle.check_plan_complex(kind, n, A.Cp, A.Ci, A.Cx, sym, devslot, nb=32, outer=64, row_phase=row_phase)
+        assert bad == 0
+        assert np.abs(out[mask] - ref[mask]).max() <= 1e-13 * np.abs(ref).max()
+
+
+def dense_permuted(S, kind, hermitian):
+    """P A P^T as the factorization reads it: Cholesky -- the permuted lower triangle completed as a HERMITIAN matrix
+    (zherk / zpotrf read nothing else, the diagonal's imaginary part included); LU -- lower + upper values, or A = A^T."""
+    n = S.int("n")
+    Lp, Li, Lx = S.array("Lp"), S.array("Li"), S.array("Lx")
+    M = np.zeros((n, n), complex)
+    cols = np.repeat(np.arange(n), np.diff(Lp))
+    if kind == "cholesky":
+        M[Li, cols] = Lx
+        M = np.tril(M, -1) + np.tril(M, -1).conj().T + np.diag(np.diag(M).real)
+    elif S.int("symmetric"):
+        M[Li, cols] = Lx
+        M = M + M.T - np.diag(np.diag(M))
+    else:
+        M[Li, cols] = Lx
+        Up, Ui, Ux = S.array("Up"), S.array("Ui"), S.array("Ux")
+        M[np.repeat(np.arange(n), np.diff(Up)), Ui] = Ux
+    return M
+
+
+@pytest.mark.parametrize("gen,g,kind", [("lap3d", 7, "cholesky"), ("cd3d", 7, "lu"), ("lap2d", 12, "lu")])
+def test_embedded_substitution_is_the_complex_solve(gen, g, kind):
+    n, r, c, z, sym = sf.matrices.generate_complex(gen, g, hermitian=(kind == "cholesky"))
+    A = sf.compress(n, r, c, z, sym)
+    S = sf.analyze(A, kind)
+    M = dense_permuted(S, kind, kind == "cholesky")
+    b = (1 + np.arange(n) / n) + 1j * ((n / 2 - np.arange(n)) / (3 * n))        # the reference's complex Bx (CH.c:3190-3191)
+    for row_phase in (False, True):
+        _, bad, _, x = sforacle.check_plan_complex(kind, n, A.Cp, A.Ci, A.Cx, sym, sf.DEFAULT_DEVSLOT, row_phase=row_phase, rhs=b)
+        assert bad == 0
+        assert np.abs(M @ x - b).max() <= 1e-13 * (np.abs(M).sum(axis=0).max() * np.abs(x).max() + np.abs(b).max())
+
+
+def test_row_phase_rescues_an_imaginary_diagonal(zgolden):
+    """A purely IMAGINARY dominant diagonal: the pivots of the embedded elimination are the real parts of the complex pivots,
+    here 0 at the first column -- without the rotation the elimination stops (or the factor is garbage); with it the result is
+    the reference's."""
+    if zgolden["phase"] < 0.0:
+        pytest.skip("only the imaginary-diagonal fixture")
+    A, _ = matrix_of(zgolden)
+    ref = zgolden["Lsx"]
+    good, bad, _, _ = sforacle.check_plan_complex("lu", A.n, A.Cp, A.Ci, A.Cx, A.symmetric, zgolden["devslot"], row_phase=True)
+    assert bad == 0 and np.abs(good - ref).max() <= 1e-13 * np.abs(ref).max()
+    plain, bad0, _, _ = sforacle.check_plan_complex("lu", A.n, A.Cp, A.Ci, A.Cx, A.symmetric, zgolden["devslot"], row_phase=False)
+    assert bad0 > 0 or not np.isfinite(plain).all() or np.abs(plain - ref).max() > 1e-6 * np.abs(ref).max()
+
+
+# ---- the drop-in library on complex input (no device needed: reader, analysis, and the host loops of solve / validate) ------
+
+def test_dropin_completes_the_reference_todo_solve_and_validate(zgolden):
+    """SparseFrame_validate on a complex factor: the reference leaves the substitution and the norms as `// TODO`
+    (CH.c:3088-3131, 3229-3256) and prints NaN; the drop-in carries them out.  Fed with the REFERENCE's own factor (golden
+    Lsx), no device involved: the residual of the permuted system must be at rounding level."""
+    import ctypes as C
+    from sparseframe_b200 import dropin
+    A, _ = matrix_of(zgolden)
+    S = sf.analyze(A, zgolden["kind"], devslot=zgolden["devslot"])
+    lib = dropin.Library(zgolden["kind"])
+    keep = []
+    lsx = np.ascontiguousarray(zgolden["Lsx"])
+    ux = S.array("Ux") if (zgolden["kind"] == "lu" and not zgolden["symmetric"]) else None
+    m = lib.matrix_from_structure(S, S.array("Lx"), ux, lsx.ctypes.data, keep)
+    assert m.isComplex == 1
+    assert lib.lib.SparseFrame_validate(C.byref(m)) == 0
+    assert 0.0 <= m.residual <= 1e-14
+    n = zgolden["n"]
+    x = np.ctypeslib.as_array(C.cast(m.Xx, C.POINTER(C.c_double)), shape=(2 * n,)).view(np.complex128)
+    b = np.ctypeslib.as_array(C.cast(m.Bx, C.POINTER(C.c_double)), shape=(2 * n,)).view(np.complex128)
+    assert np.allclose(b, (1 + np.arange(n) / n) + 1j * ((n / 2 - np.arange(n)) / (3 * n)))      # CH.c:3190-3191
+    M = dense_permuted(S, zgolden["kind"], zgolden["kind"] == "cholesky")
+    assert np.abs(M @ x - b).max() <= 1e-13 * (np.abs(M).sum(axis=0).max() * np.abs(x).max() + 1)
+
+
+def test_dropin_reads_and_analyzes_a_complex_file(zgolden, tmp_path):
+    """SparseFrame_read_matrix + SparseFrame_analyze of the drop-in on a complex MatrixMarket file leave the reference's
+    matrix_info: isComplex set, structure and permuted complex values bit-identical to the golden fixture."""
+    import subprocess
+    from test_reader import PKG
+    probe = r"""
+#include <stdio.h>
+#include <string.h>
+#include "SparseFrame.h"
+int main(int argc, char **argv) {
+  static struct matrix_info_struct m;
+  static struct common_info_struct c;
+  memset(&m, 0, sizeof(m)); memset(&c, 0, sizeof(c));
+  c.devSlotSize = strtoul(argv[3], 0, 10);
+  m.path = argv[1];
+  SparseFrame_initialize_matrix(&m);
+  if (SparseFrame_read_matrix(&m)) return 3;
+  if (SparseFrame_analyze(&c, &m)) return 4;
+  FILE *f = fopen(argv[2], "wb");
+  long h[6] = {m.nrow, m.nsuper, m.isize, m.nzmax, m.isComplex, m.xsize};
+  fwrite(h, sizeof(long), 6, f);
+  fwrite(m.Perm, sizeof(long), m.nrow, f);
+  fwrite(m.Super, sizeof(long), m.nsuper + 1, f);
+  fwrite(m.Lsip, sizeof(long), m.nsuper + 1, f);
+  fwrite(m.Lsxp, sizeof(long), m.nsuper + 1, f);
+  fwrite(m.Lsi, sizeof(long), m.isize, f);
+  fwrite(m.Lx, sizeof(Complex), m.Lp[m.nrow], f);
+  fclose(f);
+  return 0; }
+"""
+    tree = "LU" if zgolden["kind"] == "lu" else "Cholesky"
+    src, exe = tmp_path / "probe.c", tmp_path / "probe"
+    src.write_text("#include <stdlib.h>\n" + probe)
+    lib = os.path.join(PKG, tree, "Lib")
+    subprocess.check_call(["gcc", "-fopenmp", "-I" + os.path.join(PKG, tree, "Include"), str(src), "-o", str(exe),
+                           "-L" + lib, "-lSparseFrame", "-Wl,-rpath," + lib])
+    _, (n, r, c, z, sym) = matrix_of(zgolden)
+    mtx, out = tmp_path / "z.mtx", tmp_path / "z.dump"
+    sf.matrices.write_matrix_market(str(mtx), n, r, c, z, sym)
+    subprocess.run([str(exe), str(mtx), str(out), str(zgolden["devslot"])], check=True, capture_output=True)
+    raw = np.fromfile(out, dtype=np.int64)
+    nrow, ns, isize, nz, cplx, xsize = raw[:6]
+    assert (nrow, ns, isize, cplx, xsize) == (n, zgolden["nsuper"], zgolden["isize"], 1, zgolden["xsize"])
+    at = 6
+    for name, cnt in (("Perm", n), ("Super", ns + 1), ("Lsip", ns + 1), ("Lsxp", ns + 1), ("Lsi", isize)):
+        assert np.array_equal(raw[at:at + cnt], zgolden[name][:cnt]), name
+        at += cnt
+    assert np.array_equal(raw[at:].view(np.complex128), zgolden["Lx"])

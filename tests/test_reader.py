@@ -31,7 +31,7 @@ int main(int argc, char **argv) {
   fwrite(h, sizeof(long), 5, f);
   fwrite(m.Cp, sizeof(long), m.ncol + 1, f);
   fwrite(m.Ci, sizeof(long), m.nzmax, f);
-  fwrite(m.Cx, sizeof(double), m.nzmax, f);
+  fwrite(m.Cx, sizeof(double), m.nzmax * (m.isComplex ? 2 : 1), f);
   fclose(f);
   return 0; }
 """
@@ -88,6 +88,27 @@ def test_text_and_binary_give_the_reference_csc(probe, tmp_path, gen, g, threads
         assert np.array_equal(got["Cx"].view(np.int64), cx.view(np.int64))          # bit-identical values
 
 
+@pytest.mark.parametrize("gen,g,hermitian", [("lap3d", 6, True), ("cd3d", 5, False)])
+def test_complex_text_and_binary_give_the_reference_csc(probe, tmp_path, gen, g, hermitian):
+    """field "complex": (re, im) pairs, stored whole (CH.c:505-511, 572-575); an entry is dropped only if both parts are zero."""
+    n, r, c, z, sym = sf.matrices.generate_complex(gen, g, hermitian=hermitian)
+    z = z.copy()
+    z[3] = 0.0                      # dropped
+    z[5] = 1j * z[5].imag           # kept: zero real part, non-zero imaginary part
+    mtx, binf = tmp_path / "z.mtx", tmp_path / "z.sfbin"
+    sf.matrices.write_matrix_market(str(mtx), n, r, c, z, sym)
+    sf.matrices.write_binary(str(binf), n, r, c, z, sym)
+    keep = z != 0
+    A = sf.compress(n, r[keep], c[keep], z[keep], sym)
+    for path in (mtx, binf):
+        for threads in (1, 3):
+            got, out = probe(path, threads)
+            assert got is not None, out
+            assert (got["nrow"], got["ncol"], got["sym"], got["cplx"], got["nz"]) == (n, n, int(sym), 1, int(keep.sum()))
+            assert np.array_equal(got["Cp"], A.Cp) and np.array_equal(got["Ci"], A.Ci)
+            assert np.array_equal(got["Cx"].view(np.int64), A.Cx.view(np.float64).view(np.int64))
+
+
 def test_reader_semantics(probe, tmp_path):
     """Comments, blank lines, explicit zeros (dropped), a fourth column, exponents, signs, duplicates kept in file order."""
     text = "\n".join([
@@ -111,7 +132,9 @@ def test_reader_semantics(probe, tmp_path):
     ("%%MatrixMarket matrix coordinate real general\n2 2 2\n1 3 1.0\n", "invalid matrix entry"),
     ("%%NotMatrixMarket\n", "Matrix format error"),
     ("%%MatrixMarket matrix coordinate real general\n2 2\n", "Matrix format error"),
-    ("%%MatrixMarket matrix coordinate complex general\n1 1 1\n1 1 1.0 0.0\n", "complex"),
+    ("%%MatrixMarket matrix coordinate complex general\n1 1 1\n1 1 1.0\n", "imaginary part not present"),
+    # every field other than "real" is complex to the reference's reader (CH.c:440-445): a pattern file has no values at all
+    ("%%MatrixMarket matrix coordinate pattern general\n1 1 1\n1 1\n", "invalid matrix entry"),
 ])
 def test_reader_errors(probe, tmp_path, body, msg):
     p = tmp_path / "bad.mtx"
