@@ -63,8 +63,12 @@ def test_row_phase_on_the_device(zgolden):
     off = sf.ZPlan(S, row_phase=False)
     assert off.int("row_phase") == 0
     if zgolden["phase"] >= 0.0:
-        with pytest.raises(RuntimeError):
-            off.factorize(lz, uz)
+        # Re a_kk is 0 up to the rounding of exp(i pi/2): a zero pivot is reported, a tiny one wrecks the factor
+        try:
+            out = off.factorize(lz, uz)
+            assert not np.isfinite(out).all() or np.abs(out - ref).max() > 1e-6 * np.abs(ref).max()
+        except RuntimeError:
+            pass
     else:
         out = off.factorize(lz, uz)
         assert np.abs(out - ref).max() <= 1e-12 * np.abs(ref).max()
