@@ -92,14 +92,23 @@ def validate(kind, st, Lx, Lsx, Ux=None):
     return res, float(norms[3] / (norms[0] * norms[2]))
 
 
-def plan_check(kind, A_n, Cp, Ci, Cx, symmetric, devslot, nb=0, outer=0, small_a=-1, small_b=-1, ld_align=0):
-    """analyze + build the engine's schedule + interpret it on the CPU (oracle/plan_host_exec.cpp)."""
+def _load_chk():
+    """libsfcheck.so with the prototypes of its plain entry points (whoever loads it first sets them all)."""
     global _chk
     if _chk is None:
         _chk = C.CDLL(os.path.join(_HERE, "_ref", "libsfcheck.so"))
         _chk.sfcheck_factorize.restype = C.c_long
         _chk.sfcheck_factorize.argtypes = [C.c_int, C.c_int, C.c_long, C.c_void_p, C.c_void_p, C.c_void_p,
                                            C.c_ulonglong] + [C.c_int] * 5 + [C.c_void_p, C.c_void_p, C.c_long]
+        _chk.sfcheck_factorize_complex.restype = C.c_long
+        _chk.sfcheck_factorize_complex.argtypes = [C.c_int, C.c_int, C.c_long, C.c_void_p, C.c_void_p, C.c_void_p,
+                                                   C.c_ulonglong] + [C.c_int] * 5 + [C.c_void_p, C.c_void_p, C.c_void_p]
+    return _chk
+
+
+def plan_check(kind, A_n, Cp, Ci, Cx, symmetric, devslot, nb=0, outer=0, small_a=-1, small_b=-1, ld_align=0):
+    """analyze + build the engine's schedule + interpret it on the CPU (oracle/plan_host_exec.cpp)."""
+    _load_chk()
     Cp, Ci = _i64(Cp), _i64(Ci)
     Cx = np.ascontiguousarray(Cx, dtype=np.float64)
     stats = np.zeros(8, dtype=np.int64)
@@ -121,13 +130,7 @@ def check_plan_complex(kind, A_n, Cp, Ci, Cz, symmetric, devslot, nb=0, outer=0,
     """A complex matrix on the CPU interpreter: analysis with the complex element size, real embedding
     (csrc/complex_embed.cpp), the ordinary schedule on the embedded structure, complex panels read back.
     Returns (Lsx complex128, failed pivots, stats, x or None)."""
-    global _chk
-    if _chk is None:
-        _chk = C.CDLL(os.path.join(_HERE, "_ref", "libsfcheck.so"))
-    f = _chk.sfcheck_factorize_complex
-    f.restype = C.c_long
-    f.argtypes = [C.c_int, C.c_int, C.c_long, C.c_void_p, C.c_void_p, C.c_void_p, C.c_ulonglong] + [C.c_int] * 5 + \
-        [C.c_void_p, C.c_void_p, C.c_void_p]
+    f = _load_chk().sfcheck_factorize_complex
     Cp, Ci = _i64(Cp), _i64(Ci)
     Cz = np.ascontiguousarray(Cz, dtype=np.complex128)
     stats = np.zeros(8, dtype=np.int64)
@@ -154,10 +157,7 @@ class CheckBackend:
 
     def __init__(self, kind, A, devslot, rank, world, nb=0, outer=0, small_a=-1, small_b=-1, dist=None):
         from multiprocessing import shared_memory
-        global _chk
-        if _chk is None:
-            _chk = C.CDLL(os.path.join(_HERE, "_ref", "libsfcheck.so"))
-        L = _chk
+        L = _load_chk()
         L.sfcheck_open.restype = C.c_void_p
         L.sfcheck_open.argtypes = [C.c_int, C.c_int, C.c_long, C.c_void_p, C.c_void_p, C.c_void_p, C.c_ulonglong] + [C.c_int] * 7
         L.sfcheck_int.restype = C.c_long

@@ -34,6 +34,9 @@ int SparseFrame_free_matrix(struct common_info_struct *common_info, struct matri
 int SparseFrame_initialize_matrix(struct matrix_info_struct *matrix_info);
 int SparseFrame_read_matrix(struct matrix_info_struct *matrix_info);
 int SparseFrame_compress(struct matrix_info_struct *matrix_info);
+#ifdef SPARSEFRAME_LU
+int SparseFrame_pivot(struct matrix_info_struct *matrix_info);      /* LU.c:589-673; called by the reader when SF_STATIC_PIVOT=1 */
+#endif
 int SparseFrame_analyze(struct common_info_struct *common_info, struct matrix_info_struct *matrix_info);
 int SparseFrame_factorize(struct common_info_struct *common_info, struct gpu_info_struct *gpu_info_list,
                           struct matrix_info_struct *matrix_info);

@@ -104,7 +104,7 @@ struct matrix_info_struct
 
     enum PermMethod permMethod;
 #ifdef SPARSEFRAME_LU
-    Long *PivInv;               /* static pre-pivoting is disabled in the reference (LU.c:784-787): always NULL */
+    Long *PivInv;               /* static pre-pivoting is disabled in the reference (LU.c:784-787): NULL unless SF_STATIC_PIVOT=1 */
 #endif
     Long *Perm;
     Long *Parent, *Post, *ColCount;

@@ -317,6 +317,43 @@ int SparseFrame_compress(struct matrix_info_struct *m) {
     return 0;
 }
 
+#ifdef SPARSEFRAME_LU
+/* Static pivoting before the analysis: the reference's SparseFrame_pivot (LU.c:589-673), which its reader has under `#if 0`
+ * (LU.c:784-787); here behind SF_STATIC_PIVOT=1.  Column by column, the not yet used row with the largest modulus (the first
+ * one among equals) becomes that column's diagonal row; the row indices of Ci are relabelled, so that everything downstream
+ * factorizes P_r A without pivoting.  PivInv[j] = original row now in position j.  One deliberate difference: a row the
+ * greedy pass leaves unmatched keeps its old index in the reference (which may then collide with a relabelled one); here
+ * such rows take the unused positions in ascending order, so that the relabelling is always a permutation. */
+int SparseFrame_pivot(struct matrix_info_struct *m) {
+    const Long n = m->nrow, ncol = m->ncol;
+    const bool cplx = m->isComplex != 0;
+    std::vector<Long> piv((size_t)(n > 0 ? n : 1), -1);
+    Long *inv = (Long *)malloc((size_t)(n > 0 ? n : 1) * sizeof(Long));
+    for (Long i = 0; i < n; ++i) inv[i] = -1;
+    for (Long j = 0; j < ncol && j < n; ++j) {
+        Long best = -1;
+        Float big = 0;
+        for (Long p = m->Cp[j]; p < m->Cp[j + 1]; ++p) {
+            const Long i = m->Ci[p];
+            const Float a = cplx ? m->Cx[2 * p] * m->Cx[2 * p] + m->Cx[2 * p + 1] * m->Cx[2 * p + 1] : m->Cx[p] * m->Cx[p];
+            if (piv[i] < 0 && a > big) { best = i; big = a; }
+        }
+        if (best >= 0) { piv[best] = j; inv[j] = best; }
+    }
+    Long free_pos = 0;
+    for (Long i = 0; i < n; ++i) {
+        if (piv[i] >= 0) continue;
+        while (free_pos < n && inv[free_pos] >= 0) ++free_pos;
+        piv[i] = free_pos;
+        inv[free_pos] = i;
+    }
+    for (Long p = 0; p < m->Cp[ncol]; ++p) m->Ci[p] = piv[m->Ci[p]];
+    if (m->PivInv) free(m->PivInv);
+    m->PivInv = inv;
+    return 0;
+}
+#endif
+
 int SparseFrame_read_matrix(struct matrix_info_struct *m) {
     const double t0 = SparseFrame_time();
     m->file = fopen(m->path, "r");
@@ -329,6 +366,9 @@ int SparseFrame_read_matrix(struct matrix_info_struct *m) {
     m->workSize = (size_t)(10 * m->nrow + (2 * m->nzmax - m->nrow) + 1) * sizeof(Long);
     m->workspace = calloc(1, m->workSize);
     SparseFrame_compress(m);
+#ifdef SPARSEFRAME_LU
+    if (!m->isSymmetric && m->nrow == m->ncol && getenv("SF_STATIC_PIVOT") && atoi(getenv("SF_STATIC_PIVOT")) != 0) SparseFrame_pivot(m);
+#endif
     m->readTime = SparseFrame_time() - t0;
     return 0;
 }
@@ -713,7 +753,7 @@ int SparseFrame_cleanup_matrix(struct matrix_info_struct *m) {
                      m->Rx};
     for (void *q : owned) if (q) free(q);
 #ifdef SPARSEFRAME_LU
-    void *owned_lu[] = {m->CPCTp, m->CPCTi, m->Up, m->Ui, m->Ux, m->UTp, m->UTi, m->UTx};
+    void *owned_lu[] = {m->CPCTp, m->CPCTi, m->Up, m->Ui, m->Ux, m->UTp, m->UTi, m->UTx, m->PivInv};
     for (void *q : owned_lu) if (q) free(q);
 #endif
     if (m->Lsx) { if (pinned) sfb200_host_free(m->Lsx); else free(m->Lsx); }

@@ -265,3 +265,60 @@ def test_decimal_scanner_is_bit_exact_on_many_formats(probe, tmp_path):
         want = np.array([float(t) for t in texts])
         bad = np.flatnonzero(got["Cx"].view(np.int64) != want.view(np.int64))
         assert bad.size == 0, [(texts[i], got["Cx"][i], want[i]) for i in bad[:5]]
+
+
+def greedy_static_pivot(n, Cp, Ci, Cx):
+    """The reference's SparseFrame_pivot (LU.c:589-673) restated: column by column, the unused row of largest modulus."""
+    piv = -np.ones(n, dtype=np.int64)
+    for j in range(n):
+        best, big = -1, 0.0
+        for p in range(Cp[j], Cp[j + 1]):
+            a = abs(Cx[p]) ** 2
+            if piv[Ci[p]] < 0 and a > big:
+                best, big = Ci[p], a
+        if best >= 0:
+            piv[best] = j
+    free = iter(sorted(set(range(n)) - set(piv[piv >= 0].tolist())))
+    for i in range(n):
+        if piv[i] < 0:
+            piv[i] = next(free)
+    return piv
+
+
+@pytest.mark.parametrize("cplx", [False, True])
+def test_static_pivoting_prepass(probe, tmp_path, cplx):
+    """SF_STATIC_PIVOT=1 runs the reference's (compiled-out, LU.c:784-787) SparseFrame_pivot after compress: rows are
+    relabelled so that a large entry of every column sits on the diagonal.  A convection-diffusion matrix whose rows were
+    rotated by one position (its diagonal is then a weak off-diagonal entry, or empty) comes back as the original, diagonally
+    dominant matrix; what is then factorized equals the reference's factorization of the same relabelled triplets."""
+    import sforacle
+    import sfref
+    if cplx:
+        n, r, c, x, sym = sf.matrices.generate_complex("cd3d", 6, hermitian=False)
+    else:
+        n, r, c, x, sym = sf.matrices.generate("cd3d", 6)
+    shifted = (r + 1) % n
+    mtx = tmp_path / "shifted.mtx"
+    sf.matrices.write_matrix_market(str(mtx), n, shifted, c, x, sym)
+    plain, out = probe(mtx)
+    assert plain is not None, out
+    os.environ["SF_STATIC_PIVOT"] = "1"
+    try:
+        got, out = probe(mtx)
+    finally:
+        del os.environ["SF_STATIC_PIVOT"]
+    assert got is not None, out
+    cx = plain["Cx"].view(np.complex128) if cplx else plain["Cx"]
+    piv = greedy_static_pivot(n, plain["Cp"], plain["Ci"], cx)
+    assert np.array_equal(np.sort(piv), np.arange(n))
+    assert np.array_equal(got["Ci"], piv[plain["Ci"]]) and np.array_equal(got["Cp"], plain["Cp"])
+    A0 = sf.compress(n, r, c, x, sym)
+    assert np.array_equal(got["Ci"], A0.Ci)              # the rotation is undone: the dominant diagonal is back
+    check = sforacle.check_plan_complex if cplx else sforacle.plan_check
+    res = check("lu", n, got["Cp"], got["Ci"], cx, False, sf.DEFAULT_DEVSLOT)
+    assert res[1] == 0
+    if sfref.available("lu"):
+        cols = np.repeat(np.arange(n), np.diff(got["Cp"]))
+        R = sfref.Reference(n, got["Ci"], cols, cx, False, "lu").analyze().factorize()
+        ref = R.array("Lsx")
+        assert np.abs(res[0] - ref).max() <= 1e-13 * np.abs(ref).max()
