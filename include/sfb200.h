@@ -61,6 +61,14 @@ int sfb200_analyze(int kind, int is_symmetric, int64_t n, const int64_t *Cp, con
 int sfb200_analyze_ordered(int kind, int is_symmetric, int64_t n, const int64_t *Cp, const int64_t *Ci, const double *Cx,
                            uint64_t dev_slot_size, const int64_t *order, sfb200_symbolic **out);
 
+/* Opt-in parallel ordering (METIS_NodeND is 93-96 % of the analysis time and single-threaded).  procs > 1:
+ * nested dissection whose top log2(procs) separator levels are computed with METIS_ComputeVertexSeparator and whose subgraphs
+ * are ordered by METIS_NodeND in forked processes (csrc/parallel_order.cpp).  The ordering is of the same kind and quality but
+ * NOT the permutation a single METIS_NodeND call returns, so the structure that follows is self-consistent, not bit-identical
+ * to the reference's: the default (1) stays the reference's ordering.  Process-wide; returns the value in force.  Also set by the
+ * environment variable SFB200_PARALLEL_ORDER (when this function was never called). */
+int sfb200_set_ordering_processes(int procs);
+
 /* Wrap a structure computed elsewhere (e.g. by the reference's own SparseFrame_analyze): only what the
  * factorize step reads.  Arrays are copied.  Up/Ui may be NULL (Cholesky, or LU on a symmetric matrix). */
 int sfb200_symbolic_wrap(int kind, int64_t n, int64_t nsuper, const int64_t *Super, const int64_t *Lsip,

@@ -1,7 +1,7 @@
 // Host-only statistics of the numeric schedule for a 3-D 7-point Laplacian g^3 (cfg2: g = 100, cfg5: g = 160) partitioned over
 // several world sizes: launches, segments, collective payload, image / scratch / table sizes and, per rank, the tile flops it
 // actually executes (in-panel updates and Schur scatters, with the tile shares of split updates).  No GPU, no oracle.
-//   R=sparse-matrix-factorization-library_b200/csrc; g++ -O2 -std=c++17 -I$R scripts/plan_stats.cpp $R/plan.cpp $R/symbolic.cpp \
+//   R=sparse-matrix-factorization-library_b200/csrc; g++ -O2 -std=c++17 -I$R scripts/plan_stats.cpp $R/plan.cpp $R/symbolic.cpp $R/parallel_order.cpp \
 //       $R/xstat_shim.c /usr/local/cuda/targets/x86_64-linux/lib/libmetis_static.a -o /tmp/plan_stats && /tmp/plan_stats 160 2 4 8
 #include "plan.hpp"
 #include <chrono>

@@ -56,6 +56,11 @@ int sfb200_symbolic_wrap_complex(int kind, int64_t n, int64_t nsuper, const int6
     return rc;
 }
 
+int sfb200_set_ordering_processes(int procs) {
+    set_ordering_processes(procs);
+    return ordering_processes();
+}
+
 int sfb200_analyze(int kind, int is_symmetric, int64_t n, const int64_t *Cp, const int64_t *Ci, const double *Cx,
                    uint64_t dev_slot_size, sfb200_symbolic **out) {
     return sfb200_analyze_ordered(kind, is_symmetric, n, Cp, Ci, Cx, dev_slot_size, nullptr, out);

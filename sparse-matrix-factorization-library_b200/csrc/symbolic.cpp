@@ -3,15 +3,34 @@
 #include "symbolic.hpp"
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <numeric>
+#include <thread>
 
 extern "C" int METIS_NodeND(int64_t *nvtxs, int64_t *xadj, int64_t *adjncy, int64_t *vwgt, int64_t *options,
                             int64_t *perm, int64_t *iperm);
 
 namespace sfb200 {
+
+// parallel_order.cpp
+bool parallel_nested_dissection(i64 n, const std::vector<i64> &xadj, const std::vector<i64> &adj, int procs, std::vector<i64> &perm);
+
+// processes used by the ordering: 1 = one METIS_NodeND call, the reference's ordering (default); > 1 = the opt-in parallel
+// nested dissection of parallel_order.cpp (a different, equally valid permutation).  -1: not set, SFB200_PARALLEL_ORDER decides.
+static std::atomic<int> g_ordering_processes{-1};
+void set_ordering_processes(int procs) { g_ordering_processes.store(procs < 1 ? 1 : procs); }
+int ordering_processes() {
+    int p = g_ordering_processes.load();
+    if (p < 0) {
+        const char *e = getenv("SFB200_PARALLEL_ORDER");
+        p = e ? std::max(1, atoi(e)) : 1;
+    }
+    return p;
+}
 
 // ---------------------------------------------------------------------------------------------------------
 // Ordering.  Reference: SparseFrame_metis, CH.c:864-954 (LU.c:965-1066 feeds it lower(C+C^T) instead).
@@ -46,6 +65,8 @@ void fill_reducing_order(i64 n, const i64 *colptr, const i64 *rowind, std::vecto
     // differ from run to run.  Serialised, every call starts from the same seed and is deterministic.
     static std::mutex metis_mutex;
     std::lock_guard<std::mutex> lock(metis_mutex);
+    const int procs = ordering_processes();
+    if (procs > 1 && parallel_nested_dissection(n, xadj, adj, procs, perm)) return;
     METIS_NodeND(&nv, xadj.data(), adj.data(), nullptr, nullptr, perm.data(), iperm.data());
 }
 
@@ -59,58 +80,67 @@ void permute_triangles(const CscView &A, Kind kind, const std::vector<i64> &perm
     const i64 nnz = A.colptr[n];
     std::vector<i64> inv(n, -1);
     for (i64 j = 0; j < n; ++j) if (perm[j] >= 0) inv[perm[j]] = j;
-
     const i64 vw = A.is_complex ? 2 : 1;      // doubles per value (CH.c:1050-1060: Complex entries are moved whole)
-    auto reset = [&](Tri &t, bool on) {
-        t.ptr.assign(on ? n + 1 : 0, 0);
-        t.idx.assign(on ? nnz : 0, 0);
-        t.val.assign(on ? nnz * vw : 0, 0.0);
-    };
-    reset(L, true); reset(LT, true); reset(U, split); reset(UT, split);
 
-    for (i64 j = 0; j < n; ++j) {
-        const i64 jo = perm[j];
-        if (jo < 0) continue;
-        for (i64 p = A.colptr[jo]; p < A.colptr[jo + 1]; ++p) {
-            const i64 i = inv[A.rowind[p]];
-            if (!split) {
-                ++L.ptr[std::min(i, j) + 1];
-                ++LT.ptr[std::max(i, j) + 1];
-            } else {
-                if (j <= i) { ++L.ptr[j + 1]; ++LT.ptr[i + 1]; }
-                if (j >= i) { ++U.ptr[i + 1]; ++UT.ptr[j + 1]; }
-            }
-        }
-    }
-    auto scan = [](Tri &t) { if (!t.ptr.empty()) std::partial_sum(t.ptr.begin(), t.ptr.end(), t.ptr.begin()); };
-    scan(L); scan(LT); scan(U); scan(UT);
-    auto trim = [&](Tri &t) { if (!t.ptr.empty()) { t.idx.resize(t.ptr[n]); t.val.resize(t.ptr[n] * vw); } };
-    trim(L); trim(LT); trim(U); trim(UT);
-
-    std::vector<i64> cl(L.ptr.begin(), L.ptr.end() - 1), clt(LT.ptr.begin(), LT.ptr.end() - 1), cu, cut;
-    if (split) { cu.assign(U.ptr.begin(), U.ptr.end() - 1); cut.assign(UT.ptr.begin(), UT.ptr.end() - 1); }
-
-    for (i64 j = 0; j < n; ++j) {
-        const i64 jo = perm[j];
-        if (jo < 0) continue;
-        for (i64 p = A.colptr[jo]; p < A.colptr[jo + 1]; ++p) {
-            const i64 i = inv[A.rowind[p]];
-            // a value moves as it is: an entry of a complex "symmetric" matrix that the permutation carries across the
-            // diagonal is NOT conjugated (CH.c:1048-1060)
-            auto put = [&](Tri &t, i64 q, i64 index) {
-                t.idx[q] = index;
-                for (i64 w = 0; w < vw; ++w) t.val[q * vw + w] = A.val ? A.val[p * vw + w] : 0.0;
-            };
+    // Every output is a stable counting sort of the same traversal (new column ascending, old entries in file order) on its
+    // own key, so the four of them are built independently -- and concurrently: this stage is a third of the analysis once
+    // the ordering is cached (cfg2: 0.27 s per call, two calls).  which: 0 = L, 1 = LT, 2 = U, 3 = UT.
+    auto build = [&](int which, Tri &t) {
+        // destination list of entry (i, j), or -1 if this output does not take it
+        auto key = [&](i64 i, i64 j, i64 &index) -> i64 {
             if (!split) {
                 const i64 lo = std::min(i, j), hi = std::max(i, j);
-                put(L, cl[lo]++, hi);
-                put(LT, clt[hi]++, lo);
-            } else {
-                if (j <= i) { put(L, cl[j]++, i); put(LT, clt[i]++, j); }
-                if (j >= i) { put(U, cu[i]++, j); put(UT, cut[j]++, i); }
+                if (which == 0) { index = hi; return lo; }
+                index = lo; return hi;
+            }
+            switch (which) {
+                case 0: index = i; return j <= i ? j : -1;      // L by column
+                case 1: index = j; return j <= i ? i : -1;      // LT by row
+                case 2: index = j; return j >= i ? i : -1;      // U by row
+                default: index = i; return j >= i ? j : -1;     // UT by column
+            }
+        };
+        t.ptr.assign(n + 1, 0);
+        for (i64 j = 0; j < n; ++j) {
+            const i64 jo = perm[j];
+            if (jo < 0) continue;
+            for (i64 p = A.colptr[jo]; p < A.colptr[jo + 1]; ++p) {
+                i64 index;
+                const i64 k = key(inv[A.rowind[p]], j, index);
+                if (k >= 0) ++t.ptr[k + 1];
             }
         }
+        std::partial_sum(t.ptr.begin(), t.ptr.end(), t.ptr.begin());
+        t.idx.assign(t.ptr[n], 0);
+        t.val.assign(t.ptr[n] * vw, 0.0);
+        std::vector<i64> cur(t.ptr.begin(), t.ptr.end() - 1);
+        for (i64 j = 0; j < n; ++j) {
+            const i64 jo = perm[j];
+            if (jo < 0) continue;
+            for (i64 p = A.colptr[jo]; p < A.colptr[jo + 1]; ++p) {
+                i64 index;
+                const i64 k = key(inv[A.rowind[p]], j, index);
+                if (k < 0) continue;
+                // a value moves as it is: an entry of a complex "symmetric" matrix that the permutation carries across the
+                // diagonal is NOT conjugated (CH.c:1048-1060)
+                const i64 q = cur[k]++;
+                t.idx[q] = index;
+                for (i64 w = 0; w < vw; ++w) t.val[q * vw + w] = A.val ? A.val[p * vw + w] : 0.0;
+            }
+        }
+    };
+    auto clear = [](Tri &t) { t.ptr.clear(); t.idx.clear(); t.val.clear(); };
+    if (!split) { clear(U); clear(UT); }
+    if (nnz < 200000) {                       // small: not worth a thread
+        build(0, L); build(1, LT);
+        if (split) { build(2, U); build(3, UT); }
+        return;
     }
+    std::vector<std::thread> th;
+    th.emplace_back(build, 1, std::ref(LT));
+    if (split) { th.emplace_back(build, 2, std::ref(U)); th.emplace_back(build, 3, std::ref(UT)); }
+    build(0, L);
+    for (auto &x : th) x.join();
 }
 
 // ---------------------------------------------------------------------------------------------------------

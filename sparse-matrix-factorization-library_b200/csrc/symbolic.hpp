@@ -82,6 +82,12 @@ struct Symbolic {
 // reproduces that analysis bit for bit.
 int analyze(const CscView &A, Kind kind, uint64_t devSlotSize, Symbolic &out, const i64 *given_perm = nullptr);
 
+// Processes the fill-reducing ordering may use: 1 (default) = one METIS_NodeND call, bit-identical to the reference's ordering;
+// > 1 = nested dissection whose top separators are computed here and whose subgraphs are ordered by METIS_NodeND in forked
+// processes (parallel_order.cpp) -- same kind of ordering, not the same permutation.
+void set_ordering_processes(int procs);
+int ordering_processes();
+
 // Individual stages, exposed for the unit tests.
 void fill_reducing_order(i64 n, const i64 *colptr, const i64 *rowind, std::vector<i64> &perm);
 void permute_triangles(const CscView &A, Kind kind, const std::vector<i64> &perm, Tri &L, Tri &LT, Tri &U, Tri &UT);

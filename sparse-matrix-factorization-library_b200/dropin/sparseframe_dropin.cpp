@@ -91,7 +91,9 @@ std::string order_cache_path(const matrix_info_struct *m) {
         const unsigned char *b = (const unsigned char *)ptr;
         for (size_t i = 0; i < bytes; ++i) { h ^= b[i]; h *= 1099511628211ull; }
     };
-    const int64_t head[3] = {SF_KIND, m->isSymmetric, (int64_t)m->nrow};
+    /* an ordering computed by the opt-in parallel nested dissection is not the reference's: it gets its own cache entry */
+    const char *par = getenv("SF_PARALLEL_ORDER");
+    const int64_t head[4] = {SF_KIND, m->isSymmetric, (int64_t)m->nrow, (par && atoi(par) > 1) ? 1 : 0};
     mix(head, sizeof(head));
     mix(m->Cp, (size_t)(m->nrow + 1) * sizeof(Long));
     mix(m->Ci, (size_t)m->Cp[m->nrow] * sizeof(Long));
@@ -376,6 +378,9 @@ int SparseFrame_read_matrix(struct matrix_info_struct *m) {
 int SparseFrame_analyze(struct common_info_struct *common_info, struct matrix_info_struct *m) {
     const double t0 = SparseFrame_time();
     drop_cached(m);
+    /* SF_PARALLEL_ORDER=<processes>: opt-in parallel nested dissection (csrc/parallel_order.cpp) instead of the single
+     * METIS_NodeND call -- 3x faster on the 3-D configs, same quality, but not the reference's permutation */
+    if (const char *e = getenv("SF_PARALLEL_ORDER")) sfb200_set_ordering_processes(atoi(e));
     sfb200_symbolic *s = nullptr;
     int rc = SFB200_ERR_ORDERING;
     const std::string cache = order_cache_path(m);

@@ -21,7 +21,7 @@ SYMBOLS = [
     "sfb200_plan_connect", "sfb200_group_create", "sfb200_group_size", "sfb200_group_plan", "sfb200_group_factorize",
     "sfb200_group_last_ms", "sfb200_group_free", "sfb200_plan_adopt_factor", "sfb200_plan_panel_offsets", "sfb200_factorize_owned", "sfb200_download_owned",
     "sfb200_plan_owned_runs", "sfb200_plan_profile_launch", "sfb200_solve", "sfb200_solve_device", "sfb200_residual",
-    "sfb200_analyze_ordered", "sfb200_symbolic_double",
+    "sfb200_analyze_ordered", "sfb200_symbolic_double", "sfb200_set_ordering_processes",
     # complex matrices (real embedding, csrc/zengine.cu)
     "sfb200_analyze_complex", "sfb200_symbolic_wrap_complex", "sfb200_zplan_create", "sfb200_zplan_free", "sfb200_zplan_real",
     "sfb200_zplan_int", "sfb200_zplan_set_row_phase", "sfb200_zfactorize", "sfb200_zfactorize_device", "sfb200_zplan_sync",
@@ -112,6 +112,7 @@ def lib():
     L.sfb200_plan_profile.argtypes = [vp]
     L.sfb200_plan_profile_get.restype = dbl
     L.sfb200_plan_profile_get.argtypes = [vp, ci, ci]
+    L.sfb200_set_ordering_processes.argtypes = [ci]
     L.sfb200_analyze_complex.argtypes = [ci, ci, i64, vp, vp, vp, u64, vp, C.POINTER(vp)]
     L.sfb200_symbolic_wrap_complex.argtypes = L.sfb200_symbolic_wrap.argtypes
     L.sfb200_zplan_create.argtypes = [vp, ci, C.POINTER(vp)]

@@ -94,3 +94,38 @@ def test_full_size_structure_matches_the_reference_measurements(cfg):
     assert S2.double("t_order") == 0.0
     for k in ("Perm", "Super", "Lsip", "Lsxp", "Lsi"):
         assert np.array_equal(S.array(k), S2.array(k)), k
+
+
+def test_parallel_ordering_is_opt_in_and_equivalent():
+    """sfb200_set_ordering_processes(p > 1): nested dissection with the top separators computed in the caller and the subgraphs
+    ordered by METIS_NodeND in forked processes (csrc/parallel_order.cpp).  Not the reference's permutation -- which stays
+    the default -- but a valid one of the same quality, and the factorization built on it is correct."""
+    import sforacle
+    import sparseframe_b200 as sf
+    from sparseframe_b200 import _capi
+    L = _capi.lib()
+    n, r, c, x, sym = sf.matrices.generate("lap3d", 30)          # 27 000 vertices: one separator level is opened
+    A = sf.compress(n, r, c, x, sym)
+    assert L.sfb200_set_ordering_processes(1) == 1
+    ref = sf.analyze(A, "cholesky")
+    try:
+        assert L.sfb200_set_ordering_processes(4) == 4
+        par = sf.analyze(A, "cholesky")
+    finally:
+        L.sfb200_set_ordering_processes(1)
+    again = sf.analyze(A, "cholesky")
+    assert np.array_equal(again.array("Perm"), ref.array("Perm"))          # the default is untouched
+    perm = par.array("Perm")
+    assert np.array_equal(np.sort(perm), np.arange(n)) and not np.array_equal(perm, ref.array("Perm"))
+    assert par.array("Super")[-1] == n and par.int("xsize") == par.array("Lsxp")[-1]
+    assert 0.8 <= par.flops / ref.flops <= 1.2 and 0.85 <= par.int("xsize") / ref.int("xsize") <= 1.15
+    # the structure built on that ordering factorizes correctly: interpreter with the ordering fed back through analyze_ordered
+    S2 = sf.analyze(A, "cholesky", order=par.array("Order"))
+    for k in ("Perm", "Super", "Lsip", "Lsi"):
+        assert np.array_equal(S2.array(k), par.array(k)), k
+    st = {k: par.array(k) for k in ("Super", "SuperMap", "Lsip", "Lsxp", "Lsi", "LeafQueue", "Lp", "Li")}
+    st["csize"], st["nsleaf"] = par.int("csize"), par.int("nsleaf")
+    lsx, bad = sforacle.factorize("cholesky", st, par.array("Lx"))
+    assert bad == 0
+    _, backward = sforacle.validate("cholesky", st, par.array("Lx"), lsx)
+    assert backward <= 1e-13
