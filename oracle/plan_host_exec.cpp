@@ -492,8 +492,8 @@ long sfcheck_factorize(int kind, int is_symmetric, long n, const long *Cp, const
  * structure, complex panels read back (csrc/complex_embed.hpp).  Cz: interleaved (re, im) values; row_phase != 0 rotates every
  * row by the phase of its diagonal entry first (LU), as the engine does.  Lsz_out: xsize complex numbers (2 * xsize doubles);
  * stats = {nsuper, xsize (complex entries), embedded xsize_pad, nlaunches, embedded nnz, embedded unnz}.  With a null Lsz_out only
- * the sizes are returned.  struct_out (may be NULL) receives pointers-by-copy is not needed: the structure equals the one
- * sfb200_analyze_complex returns.  Return value like sfcheck_factorize. */
+ * the sizes are returned.  The structure behind Lsz_out is the one sfb200_analyze_complex returns for the same input.
+ * rhs (may be NULL): n complex numbers, solved in place with the embedded substitution.  Return value like sfcheck_factorize. */
 long sfcheck_factorize_complex(int kind, int is_symmetric, long n, const long *Cp, const long *Ci, const double *Cz,
                                unsigned long long dev_slot, int nb, int outer, int small_a, int small_b, int row_phase,
                                double *Lsz_out, long *stats, double *rhs /* may be NULL: n complex, solved in place */) {
