@@ -37,12 +37,12 @@ def run(gen, g, kind, steps=5, with_ref=True):
     x = plan.solve(b)
     res = plan.residual(x, b)["residual"]
     t0 = time.time()
-    out = plan.factorize(lz, uz)
-    t_e2e = time.time() - t0
+    out = plan.factorize(lz, uz) if with_ref else None        # host buffers in, complex factor out (pageable memory here)
+    t_e2e = time.time() - t0 if with_ref else None
     line = dict(case="%s %d %s complex" % (gen, g, kind), n=n, nsuper=S.int("nsuper"), xsize_complex=S.int("xsize"),
                 analyze_s=round(t_an, 3), plan_s=round(t_plan, 3), ms_all=[round(v, 3) for v in ms], ms=round(best, 3),
                 complex_gflops=round(4 * real_flops / best / 1e6, 1), executed_gflops=round(plan.real.double("flops") / best / 1e6, 1),
-                launches=plan.real.last_launches(), e2e_host_s=round(t_e2e, 3), residual=res,
+                launches=plan.real.last_launches(), e2e_host_s=None if t_e2e is None else round(t_e2e, 3), residual=res,
                 embedded_factor_GB=round(8e-9 * plan.real.int("xsize_padded"), 3))
     if with_ref:
         import sfref
@@ -63,6 +63,15 @@ def run(gen, g, kind, steps=5, with_ref=True):
 
 if __name__ == "__main__":
     args = sys.argv[1:]
+    no_ref = "--no-ref" in args             # skip the compiled reference (minutes of CPU at the BASELINE sizes)
+    procs = 1
+    for a in list(args):
+        if a.startswith("--order-procs="):  # opt-in parallel nested dissection (not the reference's permutation)
+            procs = int(a.split("=")[1])
+    args = [a for a in args if not a.startswith("--")]
+    if procs > 1:
+        from sparseframe_b200 import _capi
+        _capi.lib().sfb200_set_ordering_processes(procs)
     cases = [(args[i], int(args[i + 1]), args[i + 2]) for i in range(0, len(args) - 2, 3)] or [("lap3d", 40, "cholesky"), ("cd3d", 32, "lu")]
     for gen, g, kind in cases:
-        run(gen, g, kind)
+        run(gen, g, kind, steps=3 if no_ref else 5, with_ref=not no_ref)
