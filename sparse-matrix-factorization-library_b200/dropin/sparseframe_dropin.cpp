@@ -476,7 +476,8 @@ int SparseFrame_factorize(struct common_info_struct *common_info, struct gpu_inf
     }
     int rc = SFB200_OK;
     if (c.sym && (sfb200_symbolic_int(c.sym, "n") != m->nrow || sfb200_symbolic_int(c.sym, "nsuper") != m->nsuper ||
-                  sfb200_symbolic_int(c.sym, "xsize") != m->xsize || (sfb200_symbolic_int(c.sym, "complex") == 1) != (m->isComplex != 0))) {
+                  (m->Lsxp && sfb200_symbolic_int(c.sym, "xsize") != m->Lsxp[m->nsuper]) ||
+                  (sfb200_symbolic_int(c.sym, "complex") == 1) != (m->isComplex != 0))) {
         /* the caller re-used this matrix_info for another structure without analyze / cleanup: the cached plan is stale */
         drop_cached(m);
         c = Cached();

@@ -338,3 +338,19 @@ def test_complex_forest_and_tiny(kind):
             Lc = np.linalg.cholesky(M)
             got = out.reshape(n1, n1).T
             assert np.abs(np.tril(got) - Lc).max() <= 1e-14
+
+
+def test_zplan_needs_a_device_and_a_complex_structure():
+    """No CPU fallback: without a CUDA device the numeric entry point fails loudly; a real structure is refused."""
+    import ctypes as C
+    from sparseframe_b200 import _capi
+    L = _capi.lib()
+    n, r, c, z, sym = sf.matrices.generate_complex("lap2d", 6, hermitian=True)
+    Sz = sf.analyze(sf.compress(n, r, c, z, sym), "cholesky")
+    Sr = sf.analyze(sf.compress(n, r, c, np.abs(z), sym), "cholesky")
+    h = C.c_void_p()
+    assert L.sfb200_zplan_create(Sr._h, 0, C.byref(h)) == 1 and b"complex" in L.sfb200_last_error()      # SFB200_ERR_ARG
+    if sf.device_count() == 0:
+        assert L.sfb200_zplan_create(Sz._h, 0, C.byref(h)) == 3 and b"no CPU fallback" in L.sfb200_last_error()
+        with pytest.raises(RuntimeError):
+            sf.ZPlan(Sz)
