@@ -13,7 +13,9 @@
 //         l_ik = F[2i+1, 2k+1] - i F[2i, 2k+1]  (i > k),      u_kj = F[2k, 2j] - i F[2k, 2j+1]  (j >= k).
 //     The real elimination divides by Re u_kk where the complex one divides by u_kk: it needs Re u_kk != 0 and loses accuracy
 //     when |Re u_kk| << |u_kk|.  zengine.cu therefore rotates every row by the phase of its diagonal entry first (a unitary
-//     diagonal scaling, undone exactly when the factors are read back).
+//     diagonal scaling, undone exactly when the factors are read back).  For a matrix that is strictly diagonally dominant by
+//     columns the pivots stay in the discs |u_kk - a_kk| <= sum_{i != k} |a_ik|, so after the rotation
+//     Re u'_kk >= |a_kk| - sum_{i != k} |a_ik| > 0: the bound the complex elimination has for |u_kk|.
 //   * the supernodal structure of phi(A) is the structure of A with every index doubled, so no second analysis is needed;
 //   * forward / backward substitution with the embedded factor on the interleaved right-hand side IS the complex solve.
 // The price: the embedded factorization executes twice the real flops of a native complex kernel (8/3 n^3 instead of 4/3 n^3
