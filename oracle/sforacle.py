@@ -29,7 +29,66 @@ def lib():
         _lib.sforacle_solve.argtypes = [C.c_int, C.c_long, C.c_long] + [C.c_void_p] * 7
         _lib.sforacle_residual.restype = C.c_double
         _lib.sforacle_residual.argtypes = [C.c_int, C.c_long] + [C.c_void_p] * 9
+        # complex twins (oracle/sf_oracle_z.c)
+        _lib.sforacle_zfactorize.restype = C.c_long
+        _lib.sforacle_zfactorize.argtypes = _lib.sforacle_factorize.argtypes
+        _lib.sforacle_zsolve.restype = None
+        _lib.sforacle_zsolve.argtypes = _lib.sforacle_solve.argtypes
+        _lib.sforacle_zresidual.restype = C.c_double
+        _lib.sforacle_zresidual.argtypes = _lib.sforacle_residual.argtypes
     return _lib
+
+
+def zfactorize(kind, st, Lz, Uz=None):
+    """Complex twin of factorize (oracle/sf_oracle_z.c: the reference's isComplex branches); values are complex128."""
+    lu = kind in (1, "lu")
+    n = len(st["SuperMap"])
+    ns = len(st["Super"]) - 1
+    arr = {k: _i64(st[k]) for k in ("Super", "SuperMap", "Lsip", "Lsxp", "Lsi", "LeafQueue", "Lp", "Li")}
+    Lz = np.ascontiguousarray(Lz, dtype=np.complex128)
+    up = ui = uz = None
+    if lu and Uz is not None:
+        up, ui, uz = _i64(st["Up"]), _i64(st["Ui"]), np.ascontiguousarray(Uz, dtype=np.complex128)
+    out = np.zeros(int(arr["Lsxp"][-1]), dtype=np.complex128)
+    bad = lib().sforacle_zfactorize(
+        int(lu), n, ns, arr["Super"].ctypes.data, arr["SuperMap"].ctypes.data, arr["Lsip"].ctypes.data,
+        arr["Lsxp"].ctypes.data, arr["Lsi"].ctypes.data, int(st["csize"]), int(st["nsleaf"]),
+        arr["LeafQueue"].ctypes.data, arr["Lp"].ctypes.data, arr["Li"].ctypes.data, Lz.ctypes.data,
+        up.ctypes.data if up is not None else None, ui.ctypes.data if ui is not None else None,
+        uz.ctypes.data if uz is not None else None, out.ctypes.data)
+    return out, int(bad)
+
+
+def zsolve(kind, st, Lsz, b):
+    lu = kind in (1, "lu")
+    n = len(b)
+    ns = len(st["Super"]) - 1
+    arr = {k: _i64(st[k]) for k in ("Super", "Lsip", "Lsxp", "Lsi")}
+    Lsz = np.ascontiguousarray(Lsz, dtype=np.complex128)
+    b = np.ascontiguousarray(b, dtype=np.complex128)
+    x = np.zeros(n, dtype=np.complex128)
+    lib().sforacle_zsolve(int(lu), n, ns, arr["Super"].ctypes.data, arr["Lsip"].ctypes.data, arr["Lsxp"].ctypes.data,
+                          arr["Lsi"].ctypes.data, Lsz.ctypes.data, b.ctypes.data, x.ctypes.data)
+    return x
+
+
+def zvalidate(kind, st, Lz, Lsz, Uz=None):
+    """b as the reference sets it for a complex matrix (CH.c:3188-3192), solve, residual of the permuted system:
+    (residual, norms[4], x)."""
+    lu = kind in (1, "lu")
+    n = len(st["SuperMap"])
+    b = (1.0 + np.arange(n) / n) + 1j * ((n / 2 - np.arange(n)) / (3 * n))
+    x = zsolve(kind, st, Lsz, b)
+    Lp, Li = _i64(st["Lp"]), _i64(st["Li"])
+    Lz = np.ascontiguousarray(Lz, dtype=np.complex128)
+    up = ui = uz = None
+    if lu and Uz is not None:
+        up, ui, uz = _i64(st["Up"]), _i64(st["Ui"]), np.ascontiguousarray(Uz, dtype=np.complex128)
+    norms = np.zeros(4)
+    res = lib().sforacle_zresidual(int(lu), n, Lp.ctypes.data, Li.ctypes.data, Lz.ctypes.data,
+                                   up.ctypes.data if up is not None else None, ui.ctypes.data if ui is not None else None,
+                                   uz.ctypes.data if uz is not None else None, b.ctypes.data, x.ctypes.data, norms.ctypes.data)
+    return float(res), norms, x
 
 
 def factorize(kind, st, Lx, Ux=None):

@@ -354,3 +354,51 @@ def test_zplan_needs_a_device_and_a_complex_structure():
         assert L.sfb200_zplan_create(Sz._h, 0, C.byref(h)) == 3 and b"no CPU fallback" in L.sfb200_last_error()
         with pytest.raises(RuntimeError):
             sf.ZPlan(Sz)
+
+
+# ---- the plain-C restatement of the reference's isComplex branches (oracle/sf_oracle_z.c) is pinned here ------------------
+
+def structure_of(gd):
+    st = {k: gd[k] for k in ("Super", "SuperMap", "Lsip", "Lsxp", "Lsi", "LeafQueue", "Lp", "Li")}
+    st["csize"], st["nsleaf"] = gd["csize"], gd["nsleaf"]
+    if "Up" in gd:
+        st["Up"], st["Ui"] = gd["Up"], gd["Ui"]
+    return st
+
+
+def test_complex_restatement_reproduces_golden(zgolden):
+    st = structure_of(zgolden)
+    out, bad = sforacle.zfactorize(zgolden["kind"], st, zgolden["Lx"], zgolden.get("Ux"))
+    assert bad == 0
+    ref, mask = zgolden["Lsx"], defined_mask(zgolden)
+    assert np.abs(out[mask] - ref[mask]).max() <= 1e-13 * np.abs(ref).max()
+    assert np.array_equal(out == 0, ref == 0)                    # the panels' zero pattern, undefined corner included
+    res, norms, x = sforacle.zvalidate(zgolden["kind"], st, zgolden["Lx"], out, zgolden.get("Ux"))
+    assert 0.0 <= res <= 1e-14
+    # ... and the solve it completes agrees with the dense permuted matrix
+    A, _ = matrix_of(zgolden)
+    S = sf.analyze(A, zgolden["kind"], devslot=zgolden["devslot"])
+    M = dense_permuted(S, zgolden["kind"], zgolden["kind"] == "cholesky")
+    n = zgolden["n"]
+    b = (1 + np.arange(n) / n) + 1j * ((n / 2 - np.arange(n)) / (3 * n))
+    assert np.abs(M @ x - b).max() <= 1e-13 * (np.abs(M).sum(axis=0).max() * np.abs(x).max() + 1)
+    assert abs(norms[0] - np.abs(M).sum(axis=0).max()) <= 1e-12 * norms[0]
+
+
+@pytest.mark.skipif(not sfref.available("lu"), reason="compiled reference not built")
+@pytest.mark.parametrize("gen,g,kind", [("lap3d", 8, "cholesky"), ("el3d", 3, "cholesky"), ("cd3d", 8, "lu"), ("lap2d", 15, "lu")])
+def test_complex_restatement_reproduces_compiled_reference(gen, g, kind):
+    n, r, c, z, sym = sf.matrices.generate_complex(gen, g, hermitian=(kind == "cholesky"))
+    R = sfref.Reference(n, r, c, z, sym, kind, blas_threads=1).analyze()
+    leaf = R.array("LeafQueue")
+    R.factorize()
+    st = {k: R.array(k) for k in ("Super", "SuperMap", "Lsip", "Lsxp", "Lsi", "Lp", "Li")}
+    st["LeafQueue"], st["csize"], st["nsleaf"] = leaf, R.long("csize"), R.long("nsleaf")
+    uz = None
+    if kind == "lu" and not sym:
+        st["Up"], st["Ui"], uz = R.array("Up"), R.array("Ui"), R.array("Ux")
+    out, bad = sforacle.zfactorize(kind, st, R.array("Lx"), uz)
+    ref = R.array("Lsx")
+    assert bad == 0 and np.abs(out - ref).max() <= 1e-13 * np.abs(ref).max()
+    assert np.array_equal(out == 0, ref == 0)
+    R.close()
