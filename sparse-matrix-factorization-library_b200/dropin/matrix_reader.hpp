@@ -192,7 +192,9 @@ inline int parse_matrix_market(const char *buf, size_t len, Triplets &T, int nth
         cut[t] = nl ? nl + 1 : end;
     }
     std::vector<Chunk> chunks(nt);
-    const size_t guess = (size_t)std::max<long>(T.nz_declared, 0) / nt + 16;
+    // the declared count is only a hint for the reservation: a chunk cannot hold more entries than bytes / 4 ("1 1\n" ...),
+    // so a damaged size line (a count of 10^15) cannot ask for an absurd allocation
+    const size_t guess = std::min((size_t)std::max<long>(T.nz_declared, 0) / nt, body / nt / 4) + 16;
     auto work = [&](int t) {
         chunks[t].ti.reserve(guess); chunks[t].tj.reserve(guess); chunks[t].tx.reserve(guess);
         parse_entries(cut[t], cut[t + 1], T.complex_field, chunks[t]);
@@ -235,9 +237,11 @@ inline int parse_binary(const char *buf, size_t len, Triplets &T) {
     T.nrow = (long)h[1]; T.ncol = (long)h[2]; T.nz_declared = (long)h[3];
     const size_t nz = (size_t)h[3];
     T.ti.resize(nz); T.tj.resize(nz); T.tx.resize(nz * vw);
-    memcpy(T.ti.data(), buf + 40, nz * 8);
-    memcpy(T.tj.data(), buf + 40 + nz * 8, nz * 8);
-    memcpy(T.tx.data(), buf + 40 + nz * 16, nz * 8 * vw);
+    if (nz > 0) {
+        memcpy(T.ti.data(), buf + 40, nz * 8);
+        memcpy(T.tj.data(), buf + 40 + nz * 8, nz * 8);
+        memcpy(T.tx.data(), buf + 40 + nz * 16, nz * 8 * vw);
+    }
     return OK;
 }
 

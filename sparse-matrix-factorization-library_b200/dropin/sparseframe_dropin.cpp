@@ -266,6 +266,7 @@ static int read_triplets(struct matrix_info_struct *m) {
     if (rc == sfio::ERR_IMAG) { printf("Error: imaginary part not present\n"); return 1; }
     if (rc == sfio::ERR_NZMAX) { printf("Error: nzmax exceeded\n"); return 1; }
     if (rc != sfio::OK) return 1;
+    if (T.nrow < 0 || T.ncol < 0) { printf("Matrix format error\n\n"); return 1; }
     const size_t cnt = T.ti.size(), alloc = cnt > 0 ? cnt : 1;
     const size_t vbytes = m->isComplex ? sizeof(Complex) : sizeof(Float);        /* CH.c:474-477 */
     for (size_t k = 0; k < cnt; ++k)
@@ -304,6 +305,13 @@ int SparseFrame_compress(struct matrix_info_struct *m) {
     m->Ci = (Long *)malloc((size_t)(nz > 0 ? nz : 1) * sizeof(Long));
     const bool cplx = m->isComplex != 0;
     m->Cx = (Float *)malloc((size_t)(nz > 0 ? nz : 1) * (cplx ? sizeof(Complex) : sizeof(Float)));
+    if (!m->Cp || !m->Ci || !m->Cx) {          /* e.g. a damaged size line that declares 10^15 columns */
+        printf("Error: cannot allocate the compressed matrix (%ld columns, %ld entries)\n", (long)ncol, (long)nz);
+        free(m->Cp); free(m->Ci); free(m->Cx);
+        m->Cp = m->Ci = nullptr;
+        m->Cx = nullptr;
+        return 1;
+    }
     for (Long k = 0; k < nz; ++k) ++m->Cp[m->Tj[k] + 1];
     for (Long j = 0; j < ncol; ++j) m->Cp[j + 1] += m->Cp[j];
     std::vector<Long> cursor(m->Cp, m->Cp + ncol);
@@ -367,7 +375,8 @@ int SparseFrame_read_matrix(struct matrix_info_struct *m) {
     /* callers of the reference own a workspace of this size (CH.c:679-684); kept for ABI parity, zeroed */
     m->workSize = (size_t)(10 * m->nrow + (2 * m->nzmax - m->nrow) + 1) * sizeof(Long);
     m->workspace = calloc(1, m->workSize);
-    SparseFrame_compress(m);
+    if (!m->workspace) { printf("Error: cannot allocate the workspace of a %ld x %ld matrix\n", (long)m->nrow, (long)m->ncol); return 1; }
+    if (SparseFrame_compress(m) != 0) return 1;
 #ifdef SPARSEFRAME_LU
     if (!m->isSymmetric && m->nrow == m->ncol && getenv("SF_STATIC_PIVOT") && atoi(getenv("SF_STATIC_PIVOT")) != 0) SparseFrame_pivot(m);
 #endif
@@ -378,6 +387,8 @@ int SparseFrame_read_matrix(struct matrix_info_struct *m) {
 int SparseFrame_analyze(struct common_info_struct *common_info, struct matrix_info_struct *m) {
     const double t0 = SparseFrame_time();
     drop_cached(m);
+    /* the factorizations are defined for square matrices only; the reference goes on and reads Cp out of bounds */
+    if (m->nrow != m->ncol) { printf("SparseFrame_analyze: the matrix is not square (%ld x %ld)\n", (long)m->nrow, (long)m->ncol); return 1; }
     /* SF_PARALLEL_ORDER=<processes>: opt-in parallel nested dissection (csrc/parallel_order.cpp) instead of the single
      * METIS_NodeND call -- 3x faster on the 3-D configs, same quality, but not the reference's permutation */
     if (const char *e = getenv("SF_PARALLEL_ORDER")) sfb200_set_ordering_processes(atoi(e));

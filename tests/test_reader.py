@@ -135,11 +135,17 @@ def test_reader_semantics(probe, tmp_path):
     ("%%MatrixMarket matrix coordinate complex general\n1 1 1\n1 1 1.0\n", "imaginary part not present"),
     # every field other than "real" is complex to the reference's reader (CH.c:440-445): a pattern file has no values at all
     ("%%MatrixMarket matrix coordinate pattern general\n1 1 1\n1 1\n", "invalid matrix entry"),
+    # a damaged size line: an absurd entry count is only a hint, an absurd dimension is refused instead of crashing
+    ("%%MatrixMarket matrix coordinate real general\n2 2 999999999999999999\n1 1 1.0\n2 2 1.0\n", None),
+    ("%%MatrixMarket matrix coordinate real general\n999999999999999 999999999999999 1\n1 1 1.0\n", "cannot allocate"),
 ])
 def test_reader_errors(probe, tmp_path, body, msg):
     p = tmp_path / "bad.mtx"
     p.write_text(body)
     got, out = probe(p)
+    if msg is None:                       # readable after all
+        assert got is not None and got["nz"] == 2
+        return
     assert got is None and msg in out
 
 
@@ -322,3 +328,18 @@ def test_static_pivoting_prepass(probe, tmp_path, cplx):
         R = sfref.Reference(n, got["Ci"], cols, cx, False, "lu").analyze().factorize()
         ref = R.array("Lsx")
         assert np.abs(res[0] - ref).max() <= 1e-13 * np.abs(ref).max()
+
+
+def test_analyze_refuses_a_rectangular_matrix(tmp_path):
+    """The reader takes any shape (CH.c:449-521), the analysis needs a square matrix: the reference indexes Cp with row
+    numbers regardless; the drop-in says so and returns."""
+    src = tmp_path / "probe.c"
+    src.write_text(ANALYZE_PROBE)
+    exe = tmp_path / "probe"
+    lib = os.path.join(PKG, "LU", "Lib")
+    subprocess.check_call(["gcc", "-fopenmp", "-I" + os.path.join(PKG, "LU", "Include"), str(src), "-o", str(exe),
+                           "-L" + lib, "-lSparseFrame", "-Wl,-rpath," + lib])
+    mtx = tmp_path / "rect.mtx"
+    mtx.write_text("%%MatrixMarket matrix coordinate real general\n3 2 2\n1 1 1.0\n3 2 2.0\n")
+    p = subprocess.run([str(exe), str(mtx), str(tmp_path / "out")], capture_output=True, text=True)
+    assert p.returncode == 4 and "not square" in p.stdout

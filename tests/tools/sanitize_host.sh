@@ -14,3 +14,7 @@ g++ -O1 -g -std=c++17 -fsanitize=address,undefined -fno-omit-frame-pointer -w -I
     "$CSRC/parallel_order.cpp" "$CSRC/complex_embed.cpp" "$ROOT/oracle/_ref/xstat.o" \
     /usr/local/cuda/targets/x86_64-linux/lib/libmetis_static.a -pthread -o "$OUT/run"
 ASAN_OPTIONS=detect_leaks=0 "$OUT/run"
+# the MatrixMarket / binary reader on 300 000 mutated inputs (header-only, no GPU library needed)
+g++ -O1 -g -std=c++17 -fsanitize=address,undefined -fno-omit-frame-pointer -w -I"$ROOT/sparse-matrix-factorization-library_b200/dropin" \
+    "$ROOT/tests/tools/fuzz_reader.cpp" -pthread -o "$OUT/fuzz_reader"
+ASAN_OPTIONS=detect_leaks=0 "$OUT/fuzz_reader" 300000
