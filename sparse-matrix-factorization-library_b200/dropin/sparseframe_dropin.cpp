@@ -499,6 +499,12 @@ int SparseFrame_factorize(struct common_info_struct *common_info, struct gpu_inf
 #ifdef SPARSEFRAME_LU
         if (!m->isSymmetric) { up = (const int64_t *)m->Up; ui = (const int64_t *)m->Ui; }
 #endif
+        /* the engine takes the lengths of Li / Lsi from Lp[n] / Lsip[nsuper]; matrix_info carries them a second time */
+        if (!m->Lp || !m->Lsip || m->nsuper < 0 || (m->nzmax > 0 && m->Lp[m->nrow] > m->nzmax) ||
+            (m->isize > 0 && m->Lsip[m->nsuper] != m->isize)) {
+            printf("SparseFrame_factorize: matrix_info is inconsistent (Lp[nrow] vs nzmax, Lsip[nsuper] vs isize)\n");
+            return SFB200_ERR_ARG;
+        }
         rc = (m->isComplex ? sfb200_symbolic_wrap_complex : sfb200_symbolic_wrap)(
             SF_KIND, m->nrow, m->nsuper, (const int64_t *)m->Super, (const int64_t *)m->Lsip, (const int64_t *)m->Lsxp,
             (const int64_t *)m->Lsi, (const int64_t *)m->Lp, (const int64_t *)m->Li, up, ui, &c.sym);

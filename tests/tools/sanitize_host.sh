@@ -18,3 +18,8 @@ ASAN_OPTIONS=detect_leaks=0 "$OUT/run"
 g++ -O1 -g -std=c++17 -fsanitize=address,undefined -fno-omit-frame-pointer -w -I"$ROOT/sparse-matrix-factorization-library_b200/dropin" \
     "$ROOT/tests/tools/fuzz_reader.cpp" -pthread -o "$OUT/fuzz_reader"
 ASAN_OPTIONS=detect_leaks=0 "$OUT/fuzz_reader" 300000
+# a foreign supernodal structure damaged in a few places must be refused or digested, never indexed out of bounds
+g++ -O1 -g -std=c++17 -fsanitize=address,undefined -fno-omit-frame-pointer -w -I"$CSRC" "$ROOT/tests/tools/fuzz_wrap.cpp" \
+    "$CSRC/capi_symbolic.cpp" "$CSRC/plan.cpp" "$CSRC/symbolic.cpp" "$CSRC/parallel_order.cpp" "$CSRC/complex_embed.cpp" \
+    "$ROOT/oracle/_ref/xstat.o" /usr/local/cuda/targets/x86_64-linux/lib/libmetis_static.a -pthread -o "$OUT/fuzz_wrap"
+ASAN_OPTIONS=detect_leaks=0 "$OUT/fuzz_wrap" 5000
