@@ -229,6 +229,16 @@ int sfb200_zsolve(sfb200_zplan *zp, double *Bz, int nrhs);
 int sfb200_zresidual(sfb200_zplan *zp, const double *xz, const double *bz, double out[5]);
 double sfb200_zlast_ms(const sfb200_zplan *zp);
 
+/* Complex matrices on several GPUs of one box: the etree partition of the embedded structure as an sfb200_group (rank r on
+ * devices[r]); values expanded and complex panels read back on the host (a page-locked copy of the embedded factor, 4 x xsize
+ * doubles, is staged there).  A composition of the group and of the host halves of the complex path: no device code of its own. */
+typedef struct sfb200_zgroup sfb200_zgroup;
+int sfb200_zgroup_create(const sfb200_symbolic *complex_structure, int world, const int *devices, sfb200_zgroup **out);
+sfb200_group *sfb200_zgroup_real(sfb200_zgroup *g);
+int sfb200_zgroup_factorize(sfb200_zgroup *g, const double *Lz, const double *Uz, double *Lsz /* may be NULL */);
+double sfb200_zgroup_last_ms(const sfb200_zgroup *g, int which);
+void sfb200_zgroup_free(sfb200_zgroup *g);
+
 /* Device time of the last factorize call in milliseconds (which = 2: the last solve) (CUDA events on the plan's stream):
  * which = 0 numeric only (assemble + factor), 1 = including H2D/D2H copies of the host-buffer call. */
 double sfb200_last_ms(const sfb200_plan *p, int which);

@@ -550,6 +550,8 @@ long sfcheck_factorize_complex(int kind, int is_symmetric, long n, const long *C
  * rank of a segment runs first -- remote update entries land directly in the destination's image, a C_BCAST copies the
  * block from the root's image to the group's.  Lsx_out = union of the owned panels.  balance[r] receives the flops owned by
  * rank r; ncoll_out[2] counts the exchange steps met by type; image_out[r] (may be NULL) the elements of rank r's image. */
+static long run_partition(std::vector<CheckHandle *> &H, double *Lsx_out, double *balance, long *ncoll_out, long *image_out);
+
 long sfcheck_factorize_partitioned(int kind, int is_symmetric, long n, const long *Cp, const long *Ci, const double *Cx,
                                    unsigned long long dev_slot, int nb, int outer, int small_a, int small_b, int world,
                                    double *Lsx_out, double *balance, long *ncoll_out, long *image_out) {
@@ -558,6 +560,64 @@ long sfcheck_factorize_partitioned(int kind, int is_symmetric, long n, const lon
         H[r] = (CheckHandle *)sfcheck_open(kind, is_symmetric, n, Cp, Ci, Cx, dev_slot, nb, outer, small_a, small_b, 0, r, world);
         if (!H[r]) return -1;
     }
+    return run_partition(H, Lsx_out, balance, ncoll_out, image_out);
+}
+
+/* A complex matrix on `world` ranks, the way sfb200_zgroup_factorize composes it (csrc/zengine.cu): analysis with the complex
+ * element size, real embedding, values expanded on the host (rows rotated first if row_phase), the partition of the EMBEDDED
+ * structure simulated in lock step, the embedded factor packed in the reference's layout, complex panels read out of it. */
+long sfcheck_factorize_complex_partitioned(int kind, int is_symmetric, long n, const long *Cp, const long *Ci, const double *Cz,
+                                           unsigned long long dev_slot, int nb, int outer, int small_a, int small_b, int world,
+                                           int row_phase, double *Lsz_out) {
+    Symbolic Z;
+    CscView A;
+    A.n = n; A.colptr = (const i64 *)Cp; A.rowind = (const i64 *)Ci; A.val = Cz; A.symmetric = is_symmetric != 0; A.is_complex = true;
+    if (analyze(A, kind ? Kind::LU : Kind::Cholesky, dev_slot, Z) != 0) return -1;
+    ComplexEmbedding E;
+    if (embed_complex(Z, E) != 0) return -2;
+    std::vector<double> phase;
+    if (row_phase && kind) {
+        std::vector<i64> pos;
+        diagonal_positions(Z, pos);
+        phase.resize(2 * (size_t)n);
+        row_phases(pos, (!Z.symmetric ? Z.U.val : Z.L.val).data(), phase.data());
+    }
+    if (expand_embedding(Z, E, phase.empty() ? nullptr : phase.data()) != 0) return -3;
+    PlanParams prm;
+    if (nb > 0) prm.nb = nb;
+    if (outer > 0) prm.outer = outer % 100000;
+    if (outer >= 100000) prm.outer2 = outer / 100000;
+    if (small_a >= 0) prm.small_a_bytes = small_a;
+    if (small_b >= 0) prm.small_b_bytes = small_b;
+    if (const char *e = getenv("SFCHECK_DIST_MIN_M")) prm.dist_scatter_min_m = atoi(e);
+    if (const char *e = getenv("SFCHECK_DIST_PANEL_MIN")) prm.dist_panel_min_cols = atoi(e);
+    std::vector<CheckHandle *> H(world);
+    for (int r = 0; r < world; ++r) {
+        H[r] = new CheckHandle();
+        H[r]->S = E.R;
+        if (build_plan(H[r]->S, prm, H[r]->P, r, world) != 0) return -4;
+    }
+    std::vector<double> real_factor((size_t)E.R.xsize, 0.0);
+    const long bad = run_partition(H, real_factor.data(), nullptr, nullptr, nullptr);      // frees the handles
+    if (bad < 0) return bad;
+    const bool lu = kind != 0;
+    for (i64 s = 0; s < Z.nsuper; ++s) {
+        ZExtractTask t{};
+        t.nscol = (int32_t)(Z.Super[s + 1] - Z.Super[s]);
+        t.nsrow = (int32_t)(Z.Lsip[s + 1] - Z.Lsip[s]);
+        t.src = E.R.Lsxp[s];
+        t.dst = Z.Lsxp[s];
+        t.lsip = Z.Lsip[s];
+        t.c0 = 0; t.ncols = t.nscol;
+        t.ld = lu ? 4 * t.nsrow - 2 * t.nscol : 2 * t.nsrow;
+        t.mode = lu ? 1 : 0;
+        zextract_host(t, real_factor.data(), Lsz_out, phase.empty() ? nullptr : phase.data(), Z.Lsi.data());
+    }
+    return bad;
+}
+
+static long run_partition(std::vector<CheckHandle *> &H, double *Lsx_out, double *balance, long *ncoll_out, long *image_out) {
+    const int world = (int)H.size();
     std::vector<std::vector<double>> X(world);
     std::vector<double *> img(world);
     for (int r = 0; r < world; ++r) {

@@ -204,6 +204,25 @@ def check_plan_complex(kind, A_n, Cp, Ci, Cz, symmetric, devslot, nb=0, outer=0,
     return out, int(rc), stats, x
 
 
+def check_plan_complex_partitioned(kind, A_n, Cp, Ci, Cz, symmetric, devslot, world, nb=0, outer=0, small_a=-1, small_b=-1,
+                                   row_phase=False, xsize=None):
+    """A complex matrix on `world` ranks the way sfb200_zgroup_factorize composes it: partition of the embedded structure
+    simulated in lock step, complex panels read out of the packed embedded factor.  Returns (Lsx complex128, failed pivots)."""
+    f = _load_chk().sfcheck_factorize_complex_partitioned
+    f.restype = C.c_long
+    f.argtypes = [C.c_int, C.c_int, C.c_long, C.c_void_p, C.c_void_p, C.c_void_p, C.c_ulonglong] + [C.c_int] * 6 + [C.c_void_p]
+    Cp, Ci = _i64(Cp), _i64(Ci)
+    Cz = np.ascontiguousarray(Cz, dtype=np.complex128)
+    if xsize is None:
+        xsize = check_plan_complex(kind, A_n, Cp, Ci, Cz, symmetric, devslot)[2][1]
+    out = np.zeros(int(xsize), dtype=np.complex128)
+    rc = f(int(kind in (1, "lu")), int(symmetric), int(A_n), Cp.ctypes.data, Ci.ctypes.data, Cz.ctypes.data, int(devslot),
+           nb, outer, small_a, small_b, int(world), int(bool(row_phase)), out.ctypes.data)
+    if rc < 0:
+        raise RuntimeError("partitioned complex plan check failed: %d" % rc)
+    return out, int(rc)
+
+
 class CheckBackend:
     """One rank of a `world`-way etree partition executed by the CPU plan interpreter (oracle/plan_host_exec.cpp), behind
     the backend protocol of sparseframe_b200.parallel (exchange_handle / connect / factorize / finish) so that the

@@ -7,6 +7,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/sfb200.h"
@@ -367,5 +368,117 @@ int sfb200_zresidual(sfb200_zplan *zp, const double *xz, const double *bz, doubl
 }
 
 double sfb200_zlast_ms(const sfb200_zplan *zp) { return zp ? (double)zp->ms_numeric : -1.0; }
+
+}  // extern "C"
+
+/* ---- complex matrices on several GPUs ------------------------------------------------------------------------------------
+ * Pure composition of pieces that exist: the etree partition of the EMBEDDED structure over `world` GPUs is an ordinary
+ * sfb200_group (peer-memory exchange, one host thread per GPU); the complex values are expanded on the host (the arrays are
+ * the size of the matrix, not of the factor), the group writes the embedded factor into a page-locked staging buffer in the
+ * reference's layout, and the complex panels are read out of it by zextract_host (complex_embed.cpp) on all host threads.
+ * No device code of its own.  Costs a host copy of the embedded factor (4 x xsize doubles); buys the distributed memory of
+ * the group: a complex matrix whose embedded factor does not fit one GPU. */
+struct sfb200_zgroup {
+    Kind kind = Kind::Cholesky;
+    i64 n = 0, nnz = 0, unnz = 0, xsize = 0, rxsize = 0;
+    bool split = false, u_from_l = false, row_phase = false;
+    std::vector<i64> src_l, src_u, diagpos, lsi;
+    std::vector<int32_t> row_l, row_u;
+    std::vector<ZExtractTask> tasks;             // per supernode, offsets in the REFERENCE layout of the embedded factor
+    sfb200_symbolic rsym;
+    sfb200_group *rg = nullptr;
+    std::vector<double> lx, ux, phase;
+    double *h_lsx = nullptr;
+    bool h_pinned = false;
+};
+
+extern "C" {
+
+void sfb200_zgroup_free(sfb200_zgroup *g) {
+    if (!g) return;
+    if (g->rg) sfb200_group_free(g->rg);
+    if (g->h_lsx) { if (g->h_pinned) sfb200_host_free(g->h_lsx); else free(g->h_lsx); }
+    delete g;
+}
+
+int sfb200_zgroup_create(const sfb200_symbolic *zs, int world, const int *devices, sfb200_zgroup **out) {
+    if (!zs || !out || !devices || world < 1) { set_error("sfb200_zgroup_create: bad argument"); return SFB200_ERR_ARG; }
+    const Symbolic &Z = zs->S;
+    if (!Z.is_complex) { set_error("sfb200_zgroup_create: the structure is not that of a complex matrix"); return SFB200_ERR_ARG; }
+    auto *g = new sfb200_zgroup();
+    g->kind = Z.kind;
+    g->n = Z.n;
+    g->nnz = Z.L.ptr.empty() ? 0 : Z.L.ptr[Z.n];
+    g->split = Z.kind == Kind::LU && !Z.symmetric;
+    g->unnz = g->split ? Z.U.ptr[Z.n] : 0;
+    g->xsize = Z.xsize;
+    g->row_phase = Z.kind == Kind::LU;
+    if (const char *e = getenv("SFB200_ZPHASE")) g->row_phase = g->row_phase && atoi(e) != 0;
+    ComplexEmbedding E;
+    if (embed_complex(Z, E) != 0) { delete g; set_error("sfb200_zgroup_create: not a valid supernodal structure of a complex matrix"); return SFB200_ERR_ARG; }
+    g->u_from_l = E.u_from_l;
+    g->src_l.swap(E.src_l); g->src_u.swap(E.src_u); g->row_l.swap(E.row_l); g->row_u.swap(E.row_u);
+    diagonal_positions(Z, g->diagpos);
+    g->lsi = Z.Lsi;
+    g->rxsize = E.R.xsize;
+    const bool lu = Z.kind == Kind::LU;
+    for (i64 s = 0; s < Z.nsuper; ++s) {
+        ZExtractTask t{};
+        t.nscol = (int32_t)(Z.Super[s + 1] - Z.Super[s]);
+        t.nsrow = (int32_t)(Z.Lsip[s + 1] - Z.Lsip[s]);
+        t.src = E.R.Lsxp[s];
+        t.dst = Z.Lsxp[s];
+        t.lsip = Z.Lsip[s];
+        t.c0 = 0; t.ncols = t.nscol;
+        t.ld = lu ? 4 * t.nsrow - 2 * t.nscol : 2 * t.nsrow;          // no padding in the reference layout
+        t.mode = lu ? 1 : 0;
+        g->tasks.push_back(t);
+    }
+    g->lx.resize(g->src_l.size());
+    g->ux.resize(g->src_u.size());
+    g->rsym.S = std::move(E.R);
+    const int rc = sfb200_group_create(&g->rsym, world, devices, &g->rg);
+    g->rsym.S = Symbolic();
+    if (rc) { sfb200_zgroup_free(g); return rc; }
+    *out = g;
+    return SFB200_OK;
+}
+
+sfb200_group *sfb200_zgroup_real(sfb200_zgroup *g) { return g ? g->rg : nullptr; }
+
+/* Host buffers: Lz / Uz interleaved complex values (as for sfb200_zfactorize), Lsz = xsize Complex or NULL (the embedded factor
+ * then stays on the devices). */
+int sfb200_zgroup_factorize(sfb200_zgroup *g, const double *Lz, const double *Uz, double *Lsz) {
+    if (!g || !Lz || (g->split && !Uz)) { set_error("sfb200_zgroup_factorize: bad argument (an unsymmetric LU needs Uz)"); return SFB200_ERR_ARG; }
+    const double *phase = nullptr;
+    if (g->row_phase && g->kind == Kind::LU) {
+        g->phase.resize(2 * (size_t)g->n);
+        row_phases(g->diagpos, g->split ? Uz : Lz, g->phase.data());
+        phase = g->phase.data();
+    } else {
+        g->phase.clear();
+    }
+    expand_values(g->src_l, Lz, g->row_l.data(), phase, g->lx.data());
+    if (g->kind == Kind::LU) expand_values(g->src_u, g->u_from_l ? Lz : Uz, g->row_u.data(), phase, g->ux.data());
+    if (Lsz && !g->h_lsx) {
+        const size_t bytes = sizeof(double) * (size_t)std::max<i64>(g->rxsize, 1);
+        g->h_lsx = (double *)sfb200_host_alloc(bytes);
+        g->h_pinned = g->h_lsx != nullptr;
+        if (!g->h_lsx) g->h_lsx = (double *)malloc(bytes);
+        if (!g->h_lsx) { set_error("sfb200_zgroup_factorize: cannot allocate the staging buffer of the embedded factor"); return SFB200_ERR_ARG; }
+    }
+    const int rc = sfb200_group_factorize(g->rg, g->lx.data(), g->kind == Kind::LU ? g->ux.data() : nullptr, Lsz ? g->h_lsx : nullptr);
+    if (rc || !Lsz) return rc;
+    const unsigned hw = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+    std::vector<std::thread> th;
+    for (unsigned w = 0; w < hw; ++w)
+        th.emplace_back([&, w]() {
+            for (size_t k = w; k < g->tasks.size(); k += hw) zextract_host(g->tasks[k], g->h_lsx, Lsz, phase, g->lsi.data());
+        });
+    for (auto &t : th) t.join();
+    return SFB200_OK;
+}
+
+double sfb200_zgroup_last_ms(const sfb200_zgroup *g, int which) { return g ? sfb200_group_last_ms(g->rg, which) : -1.0; }
 
 }  // extern "C"

@@ -21,7 +21,8 @@
  *                                             (CH.c:3371-3444): one is read / analysed while another one factorizes
  *
  * Complex matrices (isComplex: every MatrixMarket field other than "real", CH.c:440-445) run through sfb200_zplan_* (the
- * FP64 engine on the real embedding, csrc/complex_embed.hpp) on one GPU; all value arrays of matrix_info then hold Complex
+ * FP64 engine on the real embedding, csrc/complex_embed.hpp; with numGPU > 1 sfb200_zgroup_*, the partition of the embedded
+ * structure over all GPUs, when SF_COMPLEX_MULTI_GPU=1); all value arrays of matrix_info then hold Complex
  * like the reference's.  Its complex solve / validate are `// TODO` (CH.c:3088-3131, 3229-3256): here they are carried out.
  *
  * devSlotSize policy.  The symbolic structure depends on it (supernode caps, relaxed merging), so it is derived exactly as
@@ -61,7 +62,8 @@ struct Cached {
     sfb200_symbolic *sym = nullptr;
     sfb200_plan *plan = nullptr;       // single-GPU plan, or
     sfb200_group *group = nullptr;     // the etree partition over numGPU devices
-    sfb200_zplan *zplan = nullptr;     // complex matrix: the engine on its real embedding (one GPU)
+    sfb200_zplan *zplan = nullptr;     // complex matrix: the engine on its real embedding (one GPU), or
+    sfb200_zgroup *zgroup = nullptr;   // the etree partition of the embedded structure over numGPU devices
     int ngpu = 1;
     bool pinned_lsx = false;
     bool factor_ok = false;            // the last SparseFrame_factorize of this matrix succeeded
@@ -125,7 +127,16 @@ void store_order(const std::string &path, const sfb200_symbolic *s) {
 
 // device side of one matrix: a plan on GPU 0, or the etree partition over the first ngpu devices
 int create_device_side(Cached &c, int ngpu) {
-    if (sfb200_symbolic_int(c.sym, "complex") == 1) {       // complex: one GPU
+    if (sfb200_symbolic_int(c.sym, "complex") == 1) {
+        // complex: the real embedding on GPU 0; with SF_COMPLEX_MULTI_GPU=1 its partition over all GPUs (sfb200_zgroup_*: a
+        // composition of the group and of the host halves of the complex path that has been simulated rank by rank on the CPU
+        // but not yet run on several GPUs, hence opt-in)
+        if (ngpu > 1 && getenv("SF_COMPLEX_MULTI_GPU") && atoi(getenv("SF_COMPLEX_MULTI_GPU")) != 0) {
+            c.ngpu = ngpu;
+            std::vector<int> devices(ngpu);
+            for (int r = 0; r < ngpu; ++r) devices[r] = r;
+            return sfb200_zgroup_create(c.sym, ngpu, devices.data(), &c.zgroup);
+        }
         c.ngpu = 1;
         return sfb200_zplan_create(c.sym, 0, &c.zplan);
     }
@@ -146,6 +157,7 @@ void drop_cached(const matrix_info_struct *m) {
     if (it == g_cache.end()) return;
     if (it->second.plan) sfb200_plan_free(it->second.plan);
     if (it->second.zplan) sfb200_zplan_free(it->second.zplan);
+    if (it->second.zgroup) sfb200_zgroup_free(it->second.zgroup);
     if (it->second.group) sfb200_group_free(it->second.group);
     if (it->second.sym) sfb200_symbolic_free(it->second.sym);
     g_cache.erase(it);
@@ -467,6 +479,7 @@ int SparseFrame_analyze(struct common_info_struct *common_info, struct matrix_in
         c.plan = nullptr;
         c.group = nullptr;
         c.zplan = nullptr;
+        c.zgroup = nullptr;
     }
     {
         std::lock_guard<std::mutex> lk(g_mutex);
@@ -493,7 +506,7 @@ int SparseFrame_factorize(struct common_info_struct *common_info, struct gpu_inf
         drop_cached(m);
         c = Cached();
     }
-    if (!c.plan && !c.group && !c.zplan) {
+    if (!c.plan && !c.group && !c.zplan && !c.zgroup) {
         /* structure produced by somebody else's analysis (e.g. the reference's): wrap what factorize reads */
         const int64_t *up = nullptr, *ui = nullptr;
 #ifdef SPARSEFRAME_LU
@@ -520,6 +533,7 @@ int SparseFrame_factorize(struct common_info_struct *common_info, struct gpu_inf
     if (!m->isSymmetric) ux = m->Ux;
 #endif
     rc = c.zplan ? sfb200_zfactorize(c.zplan, m->Lx, ux, m->Lsx)
+         : c.zgroup ? sfb200_zgroup_factorize(c.zgroup, m->Lx, ux, m->Lsx)
          : c.group ? sfb200_group_factorize(c.group, m->Lx, ux, m->Lsx) : sfb200_factorize(c.plan, m->Lx, ux, m->Lsx);
     if (gpu_info_list) for (int d = c.ngpu - 1; d >= 0; --d) omp_unset_lock(&gpu_info_list[d].gpuLock);
     if (rc != SFB200_OK) printf("SparseFrame_factorize: %s\n", sfb200_last_error());

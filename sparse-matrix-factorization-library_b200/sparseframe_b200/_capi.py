@@ -26,6 +26,7 @@ SYMBOLS = [
     "sfb200_analyze_complex", "sfb200_symbolic_wrap_complex", "sfb200_zplan_create", "sfb200_zplan_free", "sfb200_zplan_real",
     "sfb200_zplan_int", "sfb200_zplan_set_row_phase", "sfb200_zfactorize", "sfb200_zfactorize_device", "sfb200_zplan_sync",
     "sfb200_zdownload_factor", "sfb200_zsolve", "sfb200_zresidual", "sfb200_zlast_ms",
+    "sfb200_zgroup_create", "sfb200_zgroup_real", "sfb200_zgroup_factorize", "sfb200_zgroup_last_ms", "sfb200_zgroup_free",
 ]
 
 
@@ -131,6 +132,14 @@ def lib():
     L.sfb200_zresidual.argtypes = [vp, vp, vp, vp]
     L.sfb200_zlast_ms.restype = dbl
     L.sfb200_zlast_ms.argtypes = [vp]
+    L.sfb200_zgroup_create.argtypes = [vp, ci, vp, C.POINTER(vp)]
+    L.sfb200_zgroup_real.restype = vp
+    L.sfb200_zgroup_real.argtypes = [vp]
+    L.sfb200_zgroup_factorize.argtypes = [vp, vp, vp, vp]
+    L.sfb200_zgroup_last_ms.restype = dbl
+    L.sfb200_zgroup_last_ms.argtypes = [vp, ci]
+    L.sfb200_zgroup_free.argtypes = [vp]
+    L.sfb200_zgroup_free.restype = None
     _lib = L
     return L
 

@@ -381,6 +381,49 @@ class ZPlan:
             pass
 
 
+class ZGroup:
+    """A COMPLEX matrix on several GPUs of one box (sfb200_zgroup_*): the etree partition of the embedded structure as an
+    in-process group, values expanded and complex panels read back on the host."""
+
+    def __init__(self, sym: Symbolic, devices):
+        L = _capi.lib()
+        devs = (C.c_int * len(devices))(*[int(d) for d in devices])
+        h = C.c_void_p()
+        rc = L.sfb200_zgroup_create(sym._h, len(devices), devs, C.byref(h))
+        if rc != 0:
+            raise RuntimeError("sfb200_zgroup_create failed (%d): %s" % (rc, _capi.last_error()))
+        self._h = h
+        self.sym = sym
+        self.world = len(devices)
+
+    def factorize(self, Lz, Uz=None, download=True):
+        L = _capi.lib()
+        Lz = np.ascontiguousarray(Lz, dtype=np.complex128)
+        uz_p = None
+        if Uz is not None:
+            Uz = np.ascontiguousarray(Uz, dtype=np.complex128)
+            uz_p = Uz.ctypes.data
+        out = np.full(self.sym.int("xsize"), np.nan + 0j, dtype=np.complex128) if download else None
+        rc = L.sfb200_zgroup_factorize(self._h, Lz.ctypes.data, uz_p, out.ctypes.data if download else None)
+        if rc != 0:
+            raise RuntimeError("sfb200_zgroup_factorize failed (%d): %s" % (rc, _capi.last_error()))
+        return out
+
+    def last_ms(self, which=0) -> float:
+        return float(_capi.lib().sfb200_zgroup_last_ms(self._h, which))
+
+    def close(self):
+        if self._h:
+            _capi.lib().sfb200_zgroup_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class Group:
     """All ranks of an etree partition inside one process, rank r on devices[r] (sfb200_group_*): what the drop-in's
     SparseFrame_factorize drives when numGPU > 1 (the reference: one host thread per GPU, CH.c:2267-2290)."""

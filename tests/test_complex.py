@@ -402,3 +402,44 @@ def test_complex_restatement_reproduces_compiled_reference(gen, g, kind):
     assert bad == 0 and np.abs(out - ref).max() <= 1e-13 * np.abs(ref).max()
     assert np.array_equal(out == 0, ref == 0)
     R.close()
+
+
+# ---- complex matrices on several ranks (sfb200_zgroup_*: the partition of the embedded structure + host expand / read-back) ---
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_partitioned_embedding_reproduces_golden(zgolden, world, monkeypatch):
+    """The composition sfb200_zgroup_factorize runs -- expanded values, the etree partition of the EMBEDDED structure (group-
+    factorized panels and split Schur updates forced by small thresholds), complex panels read out of the packed embedded
+    factor -- on the CPU: lock step in both rank orders against the reference's golden factor."""
+    monkeypatch.setenv("SFCHECK_DIST_PANEL_MIN", "32")
+    monkeypatch.setenv("SFCHECK_DIST_MIN_M", "16")
+    A, _ = matrix_of(zgolden)
+    ref, mask = zgolden["Lsx"], defined_mask(zgolden)
+    for reverse in (False, True):
+        if reverse:
+            monkeypatch.setenv("SFCHECK_RANKS_REVERSED", "1")
+        out, bad = sforacle.check_plan_complex_partitioned(zgolden["kind"], A.n, A.Cp, A.Ci, A.Cx, A.symmetric, zgolden["devslot"],
+                                                           world, nb=8, outer=16, small_a=0, small_b=0, row_phase=True,
+                                                           xsize=zgolden["xsize"])
+        assert bad == 0
+        assert np.abs(out[mask] - ref[mask]).max() <= 1e-13 * np.abs(ref).max()
+        assert np.array_equal(out[mask] == 0, ref[mask] == 0)
+
+
+@pytest.mark.skipif(not sfref.available("lu"), reason="compiled reference not built")
+@pytest.mark.parametrize("gen,g,kind,world", [("lap3d", 11, "cholesky", 4), ("lap3d", 12, "cholesky", 8), ("cd3d", 10, "lu", 5),
+                                              ("lap2d", 40, "lu", 8)])
+def test_partitioned_embedding_reproduces_compiled_reference(gen, g, kind, world, monkeypatch):
+    monkeypatch.setenv("SFCHECK_DIST_PANEL_MIN", "64")
+    monkeypatch.setenv("SFCHECK_DIST_MIN_M", "32")
+    n, r, c, z, sym = sf.matrices.generate_complex(gen, g, hermitian=(kind == "cholesky"))
+    A = sf.compress(n, r, c, z, sym)
+    R = sfref.Reference(n, r, c, z, sym, kind, blas_threads=1).analyze().factorize()
+    ref = R.array("Lsx")
+    mask = sf.lower_trapezoid_mask(kind, R.array("Super"), R.array("Lsip"), R.array("Lsxp"), R.long("xsize"))
+    for row_phase in ((False, True) if kind == "lu" else (False,)):
+        out, bad = sforacle.check_plan_complex_partitioned(kind, n, A.Cp, A.Ci, A.Cx, sym, sf.DEFAULT_DEVSLOT, world,
+                                                           row_phase=row_phase, xsize=R.long("xsize"))
+        assert bad == 0
+        assert np.abs(out[mask] - ref[mask]).max() <= 1e-13 * np.abs(ref).max()
+    R.close()

@@ -158,3 +158,20 @@ def test_demo_runs_on_a_complex_file(tmp_path, tree, gen, g):
     assert "is complex" in p.stdout
     res = [float(line.split(":")[1]) for line in p.stdout.splitlines() if line.startswith("residual")]
     assert len(res) == 1 and 0.0 <= res[0] <= 1e-13, p.stdout
+
+
+def test_zgroup_on_several_gpus(zgolden):
+    """A complex matrix on two GPUs (sfb200_zgroup_*: the etree partition of the embedded structure as an in-process group,
+    values expanded and complex panels read back on the host).  Needs a GPU per rank."""
+    if sf.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs (ranks of one process need a GPU each, DESIGN.md section 9)")
+    A, _ = matrix_of(zgolden)
+    S = sf.analyze(A, zgolden["kind"], devslot=zgolden["devslot"])
+    lz, uz = values_of(S, zgolden["kind"], zgolden["symmetric"])
+    ref, mask = zgolden["Lsx"], defined_mask(zgolden)
+    grp = sf.ZGroup(S, [0, 1])
+    for _ in range(3):
+        out = grp.factorize(lz, uz)
+        assert sf.entrywise_rel_diff(out[mask], ref[mask]) <= 1e-10
+        assert np.array_equal(out[mask] == 0, ref[mask] == 0)
+    grp.close()
