@@ -1,3 +1,5 @@
+#include <algorithm>
+#include <cmath>
 #include <complex>
 #include <cstdio>
 #include <cstdlib>
@@ -8,6 +10,9 @@ extern "C" long sfcheck_factorize_complex(int kind, int is_symmetric, long n, co
 extern "C" long sfcheck_factorize(int kind, int is_symmetric, long n, const long *Cp, const long *Ci, const double *Cx,
                        unsigned long long dev_slot, int nb, int outer, int small_a, int small_b, int ld_align,
                        double *Lsx_out, long *stats, long out_len);
+extern "C" long sfcheck_factorize_complex_partitioned(int kind, int is_symmetric, long n, const long *Cp, const long *Ci, const double *Cz,
+                                           unsigned long long dev_slot, int nb, int outer, int small_a, int small_b, int world,
+                                           int row_phase, double *Lsz_out);
 extern "C" int sfb200_set_ordering_processes(int);
 namespace sfb200 { void set_ordering_processes(int); }
 int main() {
@@ -34,6 +39,14 @@ int main() {
         std::vector<double> out(2 * (size_t)stats[1] + 2), rhs(2 * (size_t)n, 1.0);
         rc = sfcheck_factorize_complex(kind, kind ? 0 : 1, n, cp.data(), ci.data(), (const double *)cz.data(), 5380000000ull, 8, 16, 0, 0, kind, out.data(), stats, rhs.data());
         printf("kind %d g %d: rc %ld nsuper %ld xsize %ld launches %ld\n", kind, g, rc, stats[0], stats[1], stats[3]);
+        if (g == 9) {   // the same matrix on 3 ranks (sfb200_zgroup's composition), small thresholds so that fronts are shared work
+            setenv("SFCHECK_DIST_PANEL_MIN", "32", 1); setenv("SFCHECK_DIST_MIN_M", "16", 1);
+            std::vector<double> out3(out.size());
+            rc = sfcheck_factorize_complex_partitioned(kind, kind ? 0 : 1, n, cp.data(), ci.data(), (const double *)cz.data(), 5380000000ull, 8, 16, 0, 0, 3, kind, out3.data());
+            double dmax = 0;
+            for (size_t q = 0; q < 2 * (size_t)stats[1]; ++q) dmax = std::max(dmax, std::abs(out3[q] - out[q]));
+            printf("kind %d g %d on 3 ranks: rc %ld, max |difference to one rank| %.2e\n", kind, g, rc, dmax);
+        }
     }
     // parallel ordering under the sanitizer (forks)
     sfb200::set_ordering_processes(4);
