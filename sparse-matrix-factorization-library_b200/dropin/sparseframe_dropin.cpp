@@ -468,13 +468,23 @@ int SparseFrame_analyze(struct common_info_struct *common_info, struct matrix_in
     Cached c;
     c.sym = s;
     const size_t lsx_bytes = (size_t)(m->xsize > 0 ? m->xsize : 1) * (cplx ? sizeof(Complex) : sizeof(Float));   /* CH.c:1648-1651 */
+    const double t_alloc0 = SparseFrame_time();
     m->Lsx = (Float *)sfb200_host_alloc(lsx_bytes);
     c.pinned_lsx = m->Lsx != nullptr;
     if (!m->Lsx) m->Lsx = (Float *)malloc(lsx_bytes);
+    const double t_alloc = SparseFrame_time() - t_alloc0;
     printf("nrow = %ld nfsuper = %ld nsuper = %ld nstage = %ld\n", n, (long)sfb200_symbolic_int(s, "nfsuper"), m->nsuper,
            m->nstage);
     /* the numeric plan (levels, batched task lists, relative-index tables) is symbolic work too: build + upload now */
-    if (create_device_side(c, common_info->numGPU) != SFB200_OK) {
+    const double t_plan0 = SparseFrame_time();
+    const int rc_plan = create_device_side(c, common_info->numGPU);
+    if (getenv("SF_TIMING"))        /* where "Analyze time" goes */
+        printf("analyze stages: ordering %.3f s, tree %.3f s, structure %.3f s, arrays into matrix_info %.3f s, page-locked Lsx "
+               "(%.2f GB) %.3f s, plan build + upload %.3f s\n", sfb200_symbolic_double(s, "t_order"), sfb200_symbolic_double(s, "t_tree"),
+               sfb200_symbolic_double(s, "t_structure"),
+               t_alloc0 - t0 - sfb200_symbolic_double(s, "t_order") - sfb200_symbolic_double(s, "t_tree") - sfb200_symbolic_double(s, "t_structure"),
+               lsx_bytes / 1e9, t_alloc, SparseFrame_time() - t_plan0);
+    if (rc_plan != SFB200_OK) {
         printf("SparseFrame_analyze: no device plan (%s)\n", sfb200_last_error());
         c.plan = nullptr;
         c.group = nullptr;
