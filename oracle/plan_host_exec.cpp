@@ -683,6 +683,8 @@ static long run_partition(std::vector<CheckHandle *> &H, double *Lsx_out, double
  * interleavings.  What this catches that the lock-step simulation cannot: a missing or misplaced barrier (a remote add that
  * lands after its target was factorized, or before its target's owner zeroed the image of the next factorization), wrong
  * sequence numbers, a wait nobody signals (dead lock -> timeout).  Lsx_out = union of the owned panels after the last epoch. */
+static long run_threaded(std::vector<CheckHandle *> &H, int epochs, int jitter, double timeout_s, double *Lsx_out);
+
 long sfcheck_factorize_threaded(int kind, int is_symmetric, long n, const long *Cp, const long *Ci, const double *Cx,
                                 unsigned long long dev_slot, int nb, int outer, int small_a, int small_b, int world, int epochs,
                                 int jitter, double timeout_s, double *Lsx_out) {
@@ -692,6 +694,56 @@ long sfcheck_factorize_threaded(int kind, int is_symmetric, long n, const long *
         H[r] = (CheckHandle *)sfcheck_open(kind, is_symmetric, n, Cp, Ci, Cx, dev_slot, nb, outer, small_a, small_b, 0, r, world);
         if (!H[r]) return -1;
     }
+    return run_threaded(H, epochs, jitter, timeout_s, Lsx_out);
+}
+
+/* The same protocol check on the partition sfb200_zgroup builds for a COMPLEX matrix: the plans of the embedded structure, one
+ * free-running thread per rank, the plan's own flag sequence numbers; complex panels read out of the packed embedded factor. */
+long sfcheck_factorize_complex_threaded(int kind, int is_symmetric, long n, const long *Cp, const long *Ci, const double *Cz,
+                                        unsigned long long dev_slot, int nb, int outer, int small_a, int small_b, int world,
+                                        int epochs, int jitter, double timeout_s, double *Lsz_out) {
+    if (world < 1 || world > kMaxWorld) return -1;
+    Symbolic Z;
+    CscView A;
+    A.n = n; A.colptr = (const i64 *)Cp; A.rowind = (const i64 *)Ci; A.val = Cz; A.symmetric = is_symmetric != 0; A.is_complex = true;
+    if (analyze(A, kind ? Kind::LU : Kind::Cholesky, dev_slot, Z) != 0) return -1;
+    ComplexEmbedding E;
+    if (embed_complex(Z, E) != 0 || expand_embedding(Z, E, nullptr) != 0) return -2;
+    PlanParams prm;
+    if (nb > 0) prm.nb = nb;
+    if (outer > 0) prm.outer = outer % 100000;
+    if (outer >= 100000) prm.outer2 = outer / 100000;
+    if (small_a >= 0) prm.small_a_bytes = small_a;
+    if (small_b >= 0) prm.small_b_bytes = small_b;
+    if (const char *e = getenv("SFCHECK_DIST_MIN_M")) prm.dist_scatter_min_m = atoi(e);
+    if (const char *e = getenv("SFCHECK_DIST_PANEL_MIN")) prm.dist_panel_min_cols = atoi(e);
+    std::vector<CheckHandle *> H(world);
+    for (int r = 0; r < world; ++r) {
+        H[r] = new CheckHandle();
+        H[r]->S = E.R;
+        if (build_plan(H[r]->S, prm, H[r]->P, r, world) != 0) return -4;
+    }
+    std::vector<double> real_factor((size_t)E.R.xsize, 0.0);
+    const long rc = run_threaded(H, epochs, jitter, timeout_s, real_factor.data());        // frees the handles
+    if (rc < 0) return rc;
+    const bool lu = kind != 0;
+    for (i64 s = 0; s < Z.nsuper; ++s) {
+        ZExtractTask t{};
+        t.nscol = (int32_t)(Z.Super[s + 1] - Z.Super[s]);
+        t.nsrow = (int32_t)(Z.Lsip[s + 1] - Z.Lsip[s]);
+        t.src = E.R.Lsxp[s];
+        t.dst = Z.Lsxp[s];
+        t.lsip = Z.Lsip[s];
+        t.c0 = 0; t.ncols = t.nscol;
+        t.ld = lu ? 4 * t.nsrow - 2 * t.nscol : 2 * t.nsrow;
+        t.mode = lu ? 1 : 0;
+        zextract_host(t, real_factor.data(), Lsz_out, nullptr, Z.Lsi.data());
+    }
+    return rc;
+}
+
+static long run_threaded(std::vector<CheckHandle *> &H, int epochs, int jitter, double timeout_s, double *Lsx_out) {
+    const int world = (int)H.size();
     std::vector<std::vector<double>> X(world);
     std::vector<double *> img(world);
     for (int r = 0; r < world; ++r) { X[r].assign(H[r]->P.xsize_pad + H[r]->P.wsize, 0.0); img[r] = X[r].data(); }

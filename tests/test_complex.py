@@ -443,3 +443,28 @@ def test_partitioned_embedding_reproduces_compiled_reference(gen, g, kind, world
         assert bad == 0
         assert np.abs(out[mask] - ref[mask]).max() <= 1e-13 * np.abs(ref).max()
     R.close()
+
+
+@pytest.mark.parametrize("world", [2, 3, 4])
+def test_partitioned_embedding_under_the_threaded_protocol(zgolden, world, monkeypatch):
+    """The exchange protocol of the partition sfb200_zgroup builds (plans of the embedded structure): one free-running thread
+    per rank, the plan's own flag sequence numbers, two factorizations back to back, with and without jitter -- on the small
+    fixtures some ranks own almost nothing, the case a lock-step simulation cannot hang on."""
+    import ctypes as C
+    monkeypatch.setenv("SFCHECK_DIST_PANEL_MIN", "32")
+    monkeypatch.setenv("SFCHECK_DIST_MIN_M", "16")
+    f = sforacle._load_chk().sfcheck_factorize_complex_threaded
+    f.restype = C.c_long
+    f.argtypes = [C.c_int, C.c_int, C.c_long, C.c_void_p, C.c_void_p, C.c_void_p, C.c_ulonglong] + [C.c_int] * 7 + \
+        [C.c_double, C.c_void_p]
+    A, _ = matrix_of(zgolden)
+    if zgolden["phase"] >= 0.0:
+        pytest.skip("the purely imaginary diagonal needs the row rotation (covered by the lock-step test)")
+    ref, mask = zgolden["Lsx"], defined_mask(zgolden)
+    Cz = np.ascontiguousarray(A.Cx, dtype=np.complex128)
+    for jitter in (0, 25):
+        out = np.zeros(zgolden["xsize"], dtype=np.complex128)
+        rc = f(int(zgolden["kind"] == "lu"), int(A.symmetric), A.n, A.Cp.ctypes.data, A.Ci.ctypes.data, Cz.ctypes.data,
+               zgolden["devslot"], 8, 16, 0, 0, world, 2, jitter, 60.0, out.ctypes.data)
+        assert rc == 0
+        assert np.abs(out[mask] - ref[mask]).max() <= 1e-13 * np.abs(ref).max()
