@@ -468,3 +468,24 @@ def test_partitioned_embedding_under_the_threaded_protocol(zgolden, world, monke
                zgolden["devslot"], 8, 16, 0, 0, world, 2, jitter, 60.0, out.ctypes.data)
         assert rc == 0
         assert np.abs(out[mask] - ref[mask]).max() <= 1e-13 * np.abs(ref).max()
+
+
+@pytest.mark.parametrize("kind", ["cholesky", "lu"])
+def test_empty_and_diagonal_complex_matrices(kind):
+    """n = 0 and a matrix without off-diagonal entries (METIS skipped, every column its own chain, CH.c:933-939)."""
+    e = np.zeros(0, dtype=np.int64)
+    A = sf.compress(0, e, e, np.zeros(0, dtype=complex), True)
+    S = sf.analyze(A, kind)
+    assert S.complex and S.int("nsuper") == 0 and S.int("xsize") == 0
+    out, bad, stats, _ = sforacle.check_plan_complex(kind, 0, A.Cp, A.Ci, A.Cx, True, sf.DEFAULT_DEVSLOT)
+    assert out.size == 0 and bad == 0
+    n = 7
+    d = np.arange(1.0, n + 1) * (np.exp(0.3j) if kind == "lu" else 1.0)
+    A = sf.compress(n, np.arange(n), np.arange(n), d.astype(complex), kind == "cholesky")
+    S = sf.analyze(A, kind)
+    out, bad, _, x = sforacle.check_plan_complex(kind, n, A.Cp, A.Ci, A.Cx, kind == "cholesky", sf.DEFAULT_DEVSLOT,
+                                                 row_phase=True, rhs=np.ones(n, complex))
+    assert bad == 0
+    dp = d[S.array("Perm")]
+    assert np.abs(x * dp - 1).max() <= 1e-15
+    assert np.abs(out - (np.sqrt(dp.real) if kind == "cholesky" else dp)).max() <= 1e-15
