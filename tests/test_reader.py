@@ -343,3 +343,19 @@ def test_analyze_refuses_a_rectangular_matrix(tmp_path):
     mtx.write_text("%%MatrixMarket matrix coordinate real general\n3 2 2\n1 1 1.0\n3 2 2.0\n")
     p = subprocess.run([str(exe), str(mtx), str(tmp_path / "out")], capture_output=True, text=True)
     assert p.returncode == 4 and "not square" in p.stdout
+
+
+def test_static_pivoting_is_the_identity_on_the_cfg4_generator(probe, tmp_path):
+    """BASELINE config 4 is "LU ... (static pivoting)": on the convection-diffusion matrices the diagonal entry is the largest
+    of its column, so the reference's pre-pass (SF_STATIC_PIVOT=1) relabels nothing and the factorization is the one measured."""
+    n, r, c, x, sym = sf.matrices.generate("cd3d", 8)
+    mtx = tmp_path / "cd.mtx"
+    sf.matrices.write_matrix_market(str(mtx), n, r, c, x, sym)
+    plain, out = probe(mtx)
+    os.environ["SF_STATIC_PIVOT"] = "1"
+    try:
+        piv, out = probe(mtx)
+    finally:
+        del os.environ["SF_STATIC_PIVOT"]
+    assert plain is not None and piv is not None
+    assert np.array_equal(plain["Ci"], piv["Ci"]) and np.array_equal(plain["Cp"], piv["Cp"])
