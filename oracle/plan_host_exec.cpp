@@ -697,6 +697,38 @@ long sfcheck_factorize_threaded(int kind, int is_symmetric, long n, const long *
     return run_threaded(H, epochs, jitter, timeout_s, Lsx_out);
 }
 
+long sfcheck_race_check(void *hv, int by_segment, int drop_flags);      // plan_race_check.cpp
+
+/* Happens-before race check (plan_race_check.cpp) of the schedule(s) the engine replays for a COMPLEX matrix: the plan of the
+ * embedded structure on one rank, or every rank's plan of its `world`-way partition.  Returns the number of hazards. */
+long sfcheck_race_check_complex(int kind, int is_symmetric, long n, const long *Cp, const long *Ci, const double *Cz,
+                                unsigned long long dev_slot, int nb, int outer, int small_a, int small_b, int world) {
+    Symbolic Z;
+    CscView A;
+    A.n = n; A.colptr = (const i64 *)Cp; A.rowind = (const i64 *)Ci; A.val = Cz; A.symmetric = is_symmetric != 0; A.is_complex = true;
+    if (analyze(A, kind ? Kind::LU : Kind::Cholesky, dev_slot, Z) != 0) return -1;
+    ComplexEmbedding E;
+    if (embed_complex(Z, E) != 0) return -2;
+    PlanParams prm;
+    if (nb > 0) prm.nb = nb;
+    if (outer > 0) prm.outer = outer % 100000;
+    if (outer >= 100000) prm.outer2 = outer / 100000;
+    if (small_a >= 0) prm.small_a_bytes = small_a;
+    if (small_b >= 0) prm.small_b_bytes = small_b;
+    if (const char *e = getenv("SFCHECK_DIST_MIN_M")) prm.dist_scatter_min_m = atoi(e);
+    if (const char *e = getenv("SFCHECK_DIST_PANEL_MIN")) prm.dist_panel_min_cols = atoi(e);
+    long hazards = 0;
+    for (int r = 0; r < world; ++r) {
+        CheckHandle h;
+        h.S = E.R;
+        if (build_plan(h.S, prm, h.P, r, world) != 0) return -4;
+        const long rc = sfcheck_race_check(&h, world > 1 ? 1 : 0, 0);
+        if (rc < 0) return rc;
+        hazards += rc;
+    }
+    return hazards;
+}
+
 /* The same protocol check on the partition sfb200_zgroup builds for a COMPLEX matrix: the plans of the embedded structure, one
  * free-running thread per rank, the plan's own flag sequence numbers; complex panels read out of the packed embedded factor. */
 long sfcheck_factorize_complex_threaded(int kind, int is_symmetric, long n, const long *Cp, const long *Ci, const double *Cz,

@@ -489,3 +489,25 @@ def test_empty_and_diagonal_complex_matrices(kind):
     dp = d[S.array("Perm")]
     assert np.abs(x * dp - 1).max() <= 1e-15
     assert np.abs(out - (np.sqrt(dp.real) if kind == "cholesky" else dp)).max() <= 1e-15
+
+
+@pytest.mark.parametrize("gen,g,kind,world,prm", [
+    ("lap3d", 16, "cholesky", 1, dict(nb=8, outer=32 * 100000 + 16, small_a=0, small_b=0)),
+    ("cd3d", 12, "lu", 1, dict(nb=8, outer=32 * 100000 + 16, small_a=0, small_b=0)),
+    ("lap3d", 24, "cholesky", 1, dict()),
+    ("lap3d", 14, "cholesky", 4, dict(nb=8, outer=16, small_a=0, small_b=0)),
+    ("cd3d", 10, "lu", 3, dict(nb=8, outer=16, small_a=0, small_b=0))])
+def test_embedded_schedules_are_race_free(gen, g, kind, world, prm, monkeypatch):
+    """The happens-before check of tests/test_race_check.py on the schedules a complex matrix is replayed with: the embedded
+    plan with both look-aheads (three blocking levels), and every rank's plan of a partition."""
+    import ctypes as C
+    monkeypatch.setenv("SFCHECK_DIST_PANEL_MIN", "64")
+    monkeypatch.setenv("SFCHECK_DIST_MIN_M", "32")
+    f = sforacle._load_chk().sfcheck_race_check_complex
+    f.restype = C.c_long
+    f.argtypes = [C.c_int, C.c_int, C.c_long, C.c_void_p, C.c_void_p, C.c_void_p, C.c_ulonglong] + [C.c_int] * 5
+    n, r, c, z, sym = sf.matrices.generate_complex(gen, g, hermitian=(kind == "cholesky"))
+    A = sf.compress(n, r, c, z, sym)
+    hazards = f(int(kind == "lu"), int(sym), n, A.Cp.ctypes.data, A.Ci.ctypes.data, A.Cx.ctypes.data, sf.DEFAULT_DEVSLOT,
+                prm.get("nb", 0), prm.get("outer", 0), prm.get("small_a", -1), prm.get("small_b", -1), world)
+    assert hazards == 0
