@@ -57,6 +57,32 @@ void fill_reducing_order(i64 n, const i64 *colptr, const i64 *rowind, std::vecto
             const i64 i = rowind[p];
             if (j < i) { adj[cursor[j]++] = i; adj[cursor[i]++] = j; }
         }
+    // Duplicate (i, j) entries -- the reader sums nothing -- would give METIS adjacency lists with repeated neighbours, which
+    // it does not allow: the reference does exactly that (CH.c:920-931), and a 17-vertex band matrix with duplicates corrupts
+    // its heap inside METIS_NodeND (found by tests/tools/differential_fuzz.py; the reference segfaults on it).  Repeated
+    // neighbours are therefore removed first, keeping the first occurrence.  A matrix without duplicates -- every list is
+    // already a set -- goes to METIS exactly as the reference sends it, so its ordering stays bit-identical.
+    if (!getenv("SFB200_METIS_KEEP_DUPLICATES")) {
+        std::vector<i64> stamp(n, -1);
+        bool any = false;
+        for (i64 v = 0; v < n && !any; ++v)
+            for (i64 p = xadj[v]; p < xadj[v + 1]; ++p) {
+                if (stamp[adj[p]] == v) { any = true; break; }
+                stamp[adj[p]] = v;
+            }
+        if (any) {
+            std::fill(stamp.begin(), stamp.end(), i64(-1));
+            std::vector<i64> xadj2(n + 1, 0), adj2;
+            adj2.reserve(nadj);
+            for (i64 v = 0; v < n; ++v) {
+                for (i64 p = xadj[v]; p < xadj[v + 1]; ++p)
+                    if (stamp[adj[p]] != v) { stamp[adj[p]] = v; adj2.push_back(adj[p]); }
+                xadj2[v + 1] = (i64)adj2.size();
+            }
+            xadj.swap(xadj2);
+            adj.swap(adj2);
+        }
+    }
     std::vector<i64> iperm(n);
     i64 nv = n;
     // One ordering at a time per process: this METIS build keeps its allocator core and its random-number state in plain

@@ -292,9 +292,11 @@ def test_random_complex_lu(n, density, seed, patsym, prm):
 
 @pytest.mark.skipif(not sfref.available("lu"), reason="compiled reference not built")
 @pytest.mark.parametrize("kind", ["cholesky", "lu"])
-def test_complex_duplicates_last_one_wins(kind):
+def test_complex_duplicates_last_one_wins(kind, monkeypatch):
     """Duplicate (i, j) entries: nothing is summed, loadA keeps the last copy (CH.c:2018, LU.c:2498/2513) -- of the diagonal
-    too, whose phase the row rotation is taken from."""
+    too, whose phase the row rotation is taken from.  (The switch reproduces the reference's METIS input, repeated neighbours
+    included, so that the structures can be compared; tests/test_plan.py::test_heavily_duplicated_entries_do_not_reach_metis.)"""
+    monkeypatch.setenv("SFB200_METIS_KEEP_DUPLICATES", "1")
     from test_irregular import random_matrix
     n, r, c, x, sym = random_matrix(120, 0.04, 21, kind == "cholesky")
     z = complexify(r, c, x, kind == "cholesky", 21)

@@ -111,11 +111,14 @@ def test_lookahead_side_launches_may_run_late(gen, g, kind, monkeypatch):
 
 @pytest.mark.skipif(not (sfref.available("cholesky") and sfref.available("lu")), reason="compiled reference not built")
 @pytest.mark.parametrize("gen,g,kind", [("lap2d", 14, "cholesky"), ("cd3d", 7, "lu"), ("lap3d", 6, "lu")])
-def test_duplicate_entries_last_one_wins(gen, g, kind):
+def test_duplicate_entries_last_one_wins(gen, g, kind, monkeypatch):
     """The reader sums nothing (CH.c:526-587) and loadA assigns in storage order (CH.c:2018, LU.c:2498/2513): of several
     copies of one (i, j) the last stays.  The engine's assembly is one parallel scatter, so the plan switches the earlier
     copies off -- checked here against the compiled reference on a matrix where every 5th entry has a wrong-valued
-    earlier twin."""
+    earlier twin.  (SFB200_METIS_KEEP_DUPLICATES: the reference hands METIS adjacency lists with repeated neighbours; the
+    engine removes them by default -- see test_heavily_duplicated_entries_do_not_reach_metis -- and this switch reproduces the
+    reference's ordering for the comparison.)"""
+    monkeypatch.setenv("SFB200_METIS_KEEP_DUPLICATES", "1")
     n, r, c, x, sym = sf.matrices.generate(gen, g)
     twin = np.arange(0, len(r), 5)
     r2 = np.concatenate([r[twin], r])            # the wrong copies come first in file order
@@ -129,3 +132,44 @@ def test_duplicate_entries_last_one_wins(gen, g, kind):
     a, b = ref.array("Lsx")[mask], out[mask]
     assert sf.entrywise_rel_diff(a, b) <= 1e-10
     ref.close()
+
+
+@pytest.mark.parametrize("gen,g,kind", [("lap2d", 4, "cholesky"), ("lap2d", 9, "cholesky"), ("cd3d", 4, "lu"), ("lap3d", 5, "lu")])
+def test_heavily_duplicated_entries_do_not_reach_metis(gen, g, kind):
+    """Every entry four times (three wrong-valued copies first): the reference builds METIS adjacency lists with repeated
+    neighbours (CH.c:920-931), which METIS does not allow -- on inputs like these it crashes, hangs or returns something that
+    is not a permutation in one case out of four (the reference with it).  The engine removes repeated neighbours first: the
+    ordering is a permutation, and the factor is the one of the matrix made of the LAST copies (oracle restatement on the
+    engine's own structure)."""
+    n, r, c, x, sym = sf.matrices.generate(gen, g)
+    r4 = np.concatenate([r, r, r, r])
+    c4 = np.concatenate([c, c, c, c])
+    x4 = np.concatenate([x * 3.0 + 1.0, -x, x * 0.5, x])
+    A = sf.compress(n, r4, c4, x4, sym)
+    S = sf.analyze(A, kind)
+    assert np.array_equal(np.sort(S.array("Perm")), np.arange(n))
+    out, bad, _ = sforacle.plan_check(kind, n, A.Cp, A.Ci, A.Cx, sym, sf.DEFAULT_DEVSLOT)
+    assert bad == 0
+    st = {k: S.array(k) for k in ("Super", "SuperMap", "Lsip", "Lsxp", "Lsi", "LeafQueue", "Lp", "Li")}
+    st["csize"], st["nsleaf"] = S.int("csize"), S.int("nsleaf")
+    ux = None
+    if kind == "lu" and not sym:
+        st["Up"], st["Ui"] = S.array("Up"), S.array("Ui")
+        ux = S.array("Ux")
+    ref, bad = sforacle.factorize(kind, st, S.array("Lx"), ux)
+    mask = sf.lower_trapezoid_mask(kind, st["Super"], st["Lsip"], st["Lsxp"], S.int("xsize"))
+    assert bad == 0 and sf.entrywise_rel_diff(ref[mask], out[mask]) <= 1e-10
+    # ... and that is the factor of the matrix without the wrong copies, analysed with the same ordering
+    Sc = sf.analyze(sf.compress(n, r, c, x, sym), kind, order=S.array("Order"))
+    for k in ("Perm", "Super", "Lsip", "Lsxp", "Lsi"):
+        assert np.array_equal(Sc.array(k), S.array(k)), k
+    stc = {k: Sc.array(k) for k in ("Super", "SuperMap", "Lsip", "Lsxp", "Lsi", "LeafQueue", "Lp", "Li")}
+    stc["csize"], stc["nsleaf"] = Sc.int("csize"), Sc.int("nsleaf")
+    uxc = None
+    if kind == "lu" and not sym:
+        stc["Up"], stc["Ui"] = Sc.array("Up"), Sc.array("Ui")
+        uxc = Sc.array("Ux")
+    clean, bad = sforacle.factorize(kind, stc, Sc.array("Lx"), uxc)
+    assert bad == 0 and sf.entrywise_rel_diff(clean[mask], out[mask]) <= 1e-10
+    _, backward = sforacle.validate(kind, stc, Sc.array("Lx"), out, uxc)
+    assert backward <= 1e-13
