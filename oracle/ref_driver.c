@@ -100,6 +100,41 @@ void *sfref_create ( int is_symmetric, long n, long nz, const long *Ti, const lo
     return sfref_create_any ( is_symmetric, 0, n, nz, Ti, Tj, Tx, dev_slot_size, blas_threads );
 }
 
+/* The matrix comes from a MatrixMarket file through the reference's OWN reader (SparseFrame_read_matrix, CH.c:652-691:
+ * getline + sscanf("%ld %ld %lg %lg"), then SparseFrame_compress) -- the oracle for the drop-in's reader.  The reference
+ * ignores the reader's return code (CH.c:673); only well-formed files are defined input. */
+int SparseFrame_read_matrix ( struct matrix_info_struct *matrix_info );
+
+void *sfref_create_from_file ( const char *path, unsigned long long dev_slot_size, int blas_threads )
+{
+    struct sfref_handle *h = calloc ( 1, sizeof ( struct sfref_handle ) );
+    struct matrix_info_struct *m = &h->matrix;
+
+    h->common.numCPU = 1;
+    h->common.numGPU = 0;
+    h->common.numGPU_physical = 0;
+    h->common.matrixThreadNum = 1;
+    h->common.numSparseMatrix = 1;
+    h->common.devSlotSize = (size_t) dev_slot_size;
+    memset ( &h->gpu[0], 0, sizeof ( h->gpu[0] ) );
+    h->gpu[0].gpuIndex_physical = -1;
+    h->gpu[0].lastMatrix = -1;
+    omp_init_lock ( &h->gpu[0].gpuLock );
+    if ( blas_threads > 0 )
+        openblas_set_num_threads ( blas_threads );
+    omp_set_nested ( TRUE );
+
+    m->serial = 0;
+    m->path = strdup ( path );
+    SparseFrame_initialize_matrix ( m );
+    if ( SparseFrame_read_matrix ( m ) != 0 )
+    {
+        free ( h );
+        return NULL;
+    }
+    return h;
+}
+
 void *sfref_create_complex ( int is_symmetric, long n, long nz, const long *Ti, const long *Tj, const double *Tz,
         unsigned long long dev_slot_size, int blas_threads )
 {

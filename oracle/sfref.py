@@ -30,6 +30,8 @@ def _lib(kind: str):
         lib.sfref_create.restype = C.c_void_p
         lib.sfref_create.argtypes = [C.c_int, C.c_long, C.c_long, C.c_void_p, C.c_void_p, C.c_void_p,
                                      C.c_ulonglong, C.c_int]
+        lib.sfref_create_from_file.restype = C.c_void_p
+        lib.sfref_create_from_file.argtypes = [C.c_char_p, C.c_ulonglong, C.c_int]
         lib.sfref_create_complex.restype = C.c_void_p
         lib.sfref_create_complex.argtypes = lib.sfref_create.argtypes
         for f in ("sfref_analyze", "sfref_factorize", "sfref_validate"):
@@ -63,6 +65,20 @@ class Reference:
         self.h = create(int(bool(symmetric)), int(n), int(rows.size), rows.ctypes.data,
                         cols.ctypes.data, vals.ctypes.data, int(devslot), int(blas_threads))
         self.n = int(n)
+
+    @classmethod
+    def from_file(cls, path, kind="cholesky", devslot=DEFAULT_DEVSLOT, blas_threads=0):
+        """The matrix read by the reference's OWN MatrixMarket reader (SparseFrame_read_matrix, CH.c:652-691)."""
+        self = cls.__new__(cls)
+        self.kind = kind
+        self.lib = _lib(kind)
+        self.h = self.lib.sfref_create_from_file(str(path).encode(), int(devslot), int(blas_threads))
+        if not self.h:
+            raise RuntimeError("the reference could not read %s" % path)
+        self.n = self.long("nrow")
+        self.complex = self.long("isComplex") == 1
+        self.vdtype = np.complex128 if self.complex else np.float64
+        return self
 
     def analyze(self):
         self.lib.sfref_analyze(self.h)

@@ -359,3 +359,55 @@ def test_static_pivoting_is_the_identity_on_the_cfg4_generator(probe, tmp_path):
         del os.environ["SF_STATIC_PIVOT"]
     assert plain is not None and piv is not None
     assert np.array_equal(plain["Ci"], piv["Ci"]) and np.array_equal(plain["Cp"], piv["Cp"])
+
+
+@pytest.mark.parametrize("seed", range(int(os.environ.get("SF_READER_FUZZ", "12"))))
+def test_reader_against_the_references_own_reader(probe, tmp_path, seed):
+    """Random well-formed MatrixMarket files -- number formats, signs, exponents, tabs and leading blanks, comment lines, a
+    fourth column in real files, explicit zeros, every banner word -- read by the drop-in and by the REFERENCE'S OWN reader
+    (SparseFrame_read_matrix_triplet + SparseFrame_compress, CH.c:400-587, through oracle/ref_driver.c): the same flags and
+    the same Cp / Ci / Cx bit for bit."""
+    import sfref
+    if not sfref.available("lu"):
+        pytest.skip("compiled reference not built")
+    rng = np.random.default_rng(100 + seed)
+    field = str(rng.choice(["real", "real", "complex", "integer"]))        # everything but "real" is complex to the reader
+    symm = str(rng.choice(["general", "symmetric", "hermitian", "skew-symmetric"]))
+    cplx = field != "real"
+    n = int(rng.integers(3, 40))
+    nz = int(rng.integers(1, 6 * n))
+    ti, tj = rng.integers(1, n + 1, nz), rng.integers(1, n + 1, nz)
+
+    def number(v):
+        f = int(rng.integers(0, 9))
+        if f == 0: return "%.17g" % v
+        if f == 1: return "%.3f" % v
+        if f == 2: return "%e" % v
+        if f == 3: return "%.10E" % v
+        if f == 4: return "%d" % int(v * 10)
+        if f == 5: return ("+%.5g" % abs(v))
+        if f == 6: return "%.25g" % v
+        if f == 7: return "0" if rng.random() < 0.5 else "0.0e0"           # explicit zero
+        return "%.12ge%+d" % (rng.uniform(1, 10), int(rng.integers(-30, 30)))
+    lines = ["%%%%MatrixMarket matrix coordinate %s %s" % (field, symm)]
+    for _ in range(int(rng.integers(0, 4))):
+        lines.append("%% comment %d" % rng.integers(0, 100))
+    lines.append("%d %d %d" % (n, n, nz))
+    for k in range(nz):
+        v, w = rng.standard_normal() * 10.0 ** rng.integers(-5, 6), rng.standard_normal()
+        sep = str(rng.choice([" ", "  ", "\t", " \t "]))
+        lead = str(rng.choice(["", " ", "\t"]))
+        parts = [str(ti[k]), str(tj[k]), number(v)]
+        if cplx or rng.random() < 0.2:
+            parts.append(number(w))                                          # a 4th column in a real file is legal (CH.c:485-496)
+        lines.append(lead + sep.join(parts))
+    path = tmp_path / "r.mtx"
+    path.write_text("\n".join(lines) + "\n")
+    R = sfref.Reference.from_file(path, "lu")
+    got, out = probe(path, int(rng.integers(1, 4)))
+    assert got is not None, out
+    assert (got["nrow"], got["ncol"], got["nz"], got["sym"], got["cplx"]) == \
+        (R.n, R.n, R.long("nzmax"), R.long("isSymmetric"), R.long("isComplex"))
+    assert np.array_equal(got["Cp"], R.array("Cp")) and np.array_equal(got["Ci"], R.array("Ci"))
+    ref_cx = R.array("Cx")
+    assert np.array_equal(got["Cx"].view(np.int64), ref_cx.view(np.float64).view(np.int64))
