@@ -221,7 +221,7 @@ sfb200_plan *sfb200_zplan_real(sfb200_zplan *zp);              /* the plan of th
 int64_t sfb200_zplan_int(const sfb200_zplan *zp, const char *name);   /* "n","nnz","unnz","xsize","row_phase", else as sfb200_plan_int of the embedded plan */
 int sfb200_zplan_set_row_phase(sfb200_zplan *zp, int on);
 int sfb200_zfactorize(sfb200_zplan *zp, const double *Lz, const double *Uz, double *Lsz /* may be NULL */);
-int sfb200_zfactorize_device(sfb200_zplan *zp, const double *d_Lz, const double *d_Uz);    /* asynchronous */
+int sfb200_zfactorize_device(sfb200_zplan *zp, const double *d_Lz, const double *d_Uz);    /* asynchronous (with row phases the call returns once the n phases have reached the host) */
 int sfb200_zplan_sync(sfb200_zplan *zp);
 int sfb200_zdownload_factor(sfb200_zplan *zp, double *Lsz);
 /* The reference's complex solve / validate are `// TODO` (CH.c:3088-3131, 3229-3256); these are what they would be. */

@@ -114,9 +114,18 @@ bool parallel_nested_dissection(i64 n, const std::vector<i64> &xadj, const std::
     g.gid.resize(n);
     std::iota(g.gid.begin(), g.gid.end(), i64(0));
     order_graph(g, levels, out);
-    perm.assign(out, out + n);
+    // every vertex exactly once, or the caller orders with the single METIS_NodeND call (a child that was killed, a METIS
+    // failure inside one: its slice stays -1)
+    std::vector<char> seen((size_t)n, 0);
+    bool ok = true;
+    for (i64 k = 0; k < n && ok; ++k) {
+        const i64 v = out[k];
+        if (v < 0 || v >= n || seen[v]) ok = false;
+        else seen[v] = 1;
+    }
+    if (ok) perm.assign(out, out + n);
     munmap(shared, bytes);
-    return true;
+    return ok;
 }
 
 }  // namespace sfb200

@@ -351,6 +351,7 @@ int SparseFrame_pivot(struct matrix_info_struct *m) {
     const bool cplx = m->isComplex != 0;
     std::vector<Long> piv((size_t)(n > 0 ? n : 1), -1);
     Long *inv = (Long *)malloc((size_t)(n > 0 ? n : 1) * sizeof(Long));
+    if (!inv) return 1;
     for (Long i = 0; i < n; ++i) inv[i] = -1;
     for (Long j = 0; j < ncol && j < n; ++j) {
         Long best = -1;
